@@ -1,0 +1,643 @@
+// TEST INFRASTRUCTURE -- CPU oracle, never shipped, never on the product path.
+//
+// ppg_cpu_tracer.h: plain-C++ restatement of the reference's GuidedPathTracer
+// integrator (mitsuba/src/integrators/path/guided_path.cpp, "GP") for the scene
+// subset of the hot path: perspective camera, triangle meshes, diffuse (optionally
+// two-sided) BSDFs, area lights, box-filtered film.  Templated on the SD-tree
+// backend so that the same tracer runs either on the restated trees
+// (sdtree_port.h) or on the reference's own SD-tree code compiled verbatim
+// (oracle/sdtree_ref, built into oracle/_ref/).
+//
+// Deliberate, documented deviations from the reference (none changes the estimator):
+//   * sampler: the reference uses one SFMT stream per worker thread and is not
+//     reproducible (src/samplers/independent.cpp:41-59).  Here every path owns a
+//     PCG32 stream keyed by (seed, global pass, pixel, sample) and consumes numbers
+//     in the reference's order; the stochastic spatial filter draws its
+//     3 numbers per committed vertex from a second per-vertex stream.  The CUDA
+//     path uses the same generator, which is what makes path-level parity testable.
+//   * acceleration structure: a BVH instead of the SAH kd-tree (hit set identical;
+//     ties on t broken towards the lower triangle index).
+//   * film: a sample lands in exactly the pixel containing it with weight 1 (the
+//     reference's box filter has radius 0.5+1e-5: a 1e-5 sliver also touches the
+//     neighbour; weights cancel in every quantity we reproduce).
+#pragma once
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+#include "../include/ppg.h"
+
+namespace ppgo {
+
+// ------------------------------------------------------------------ small vector math
+struct F3 { float x, y, z; };
+static inline F3 f3(float x, float y, float z) { return F3{x, y, z}; }
+static inline F3 operator+(F3 a, F3 b) { return F3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline F3 operator-(F3 a, F3 b) { return F3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline F3 operator*(F3 a, float s) { return F3{a.x * s, a.y * s, a.z * s}; }
+static inline F3 operator*(F3 a, F3 b) { return F3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+static inline F3 operator-(F3 a) { return F3{-a.x, -a.y, -a.z}; }
+static inline float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline F3 cross(F3 a, F3 b) { return F3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+static inline float length(F3 a) { return std::sqrt(dot(a, a)); }
+static inline F3 normalize(F3 a) { return a * (1.0f / length(a)); }   // TVector3::operator/ multiplies by the reciprocal (core/vector.h)
+static inline float comp(const F3 &a, int i) { return (&a.x)[i]; }
+static inline bool is_zero(F3 a) { return a.x == 0 && a.y == 0 && a.z == 0; }
+static inline bool is_valid(F3 a) {   // Spectrum::isValid (core/spectrum.h): finite and non-negative
+    return std::isfinite(a.x) && std::isfinite(a.y) && std::isfinite(a.z) && a.x >= 0 && a.y >= 0 && a.z >= 0;
+}
+static inline float max3(F3 a) { return std::max(std::max(a.x, a.y), a.z); }
+
+static const float kPiT = 3.14159265358979323846f;    // M_PI (single-precision build)
+static const float kEpsilon = 1e-4f;                 // core/constants.h:28
+static const float kInvPi = 0.31830988618379067154f; // INV_PI
+
+// ------------------------------------------------------------------ PCG32 path sampler
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+struct Pcg32 {
+    uint64_t state, inc;
+    void seed(uint64_t initstate, uint64_t initseq) {
+        state = 0; inc = (initseq << 1) | 1u;
+        nextU32(); state += initstate; nextU32();
+    }
+    uint32_t nextU32() {
+        const uint64_t old = state;
+        state = old * 6364136223846793005ull + inc;
+        const uint32_t xs = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+        const uint32_t rot = (uint32_t) (old >> 59u);
+        return (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+    float next1D() { return (float) (nextU32() >> 8) * (1.0f / 16777216.0f); }
+};
+// path stream: key = (seed, global sample index)
+static inline void seed_path_rng(Pcg32 &r, uint64_t seed, uint64_t sampleIndex) {
+    r.seed(splitmix64(seed ^ splitmix64(sampleIndex)), sampleIndex);
+}
+// per-committed-vertex stream for the stochastic spatial filter
+static inline void seed_vertex_rng(Pcg32 &r, uint64_t seed, uint64_t sampleIndex, uint32_t vertexOrdinal) {
+    r.seed(splitmix64((seed + 0x5851F42D4C957F2Dull) ^ splitmix64(sampleIndex * 64 + vertexOrdinal)), sampleIndex * 64 + vertexOrdinal);
+}
+
+// ------------------------------------------------------------------ scene
+struct TriAccelP {   // Wald's projection test, restated from include/mitsuba/render/triaccel.h:60-158
+    int k; float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv;
+};
+static inline bool triaccel_load(TriAccelP &t, F3 A, F3 B, F3 C) {
+    static const int mod3[4] = {1, 2, 0, 1};
+    const F3 b = C - A, c = B - A, N = cross(c, b);
+    int k = 0;
+    for (int j = 0; j < 3; ++j) if (std::fabs(comp(N, j)) > std::fabs(comp(N, k))) k = j;
+    const int u = mod3[k], v = mod3[k + 1];
+    const float n_k = comp(N, k), denom = comp(b, u) * comp(c, v) - comp(b, v) * comp(c, u);
+    if (denom == 0) { t.k = 3; return false; }
+    t.k = k;
+    t.n_u = comp(N, u) / n_k; t.n_v = comp(N, v) / n_k; t.n_d = dot(A, N) / n_k;
+    t.b_nu = comp(b, u) / denom; t.b_nv = -comp(b, v) / denom;
+    t.a_u = comp(A, u); t.a_v = comp(A, v);
+    t.c_nu = comp(c, v) / denom; t.c_nv = -comp(c, u) / denom;
+    return true;
+}
+static inline bool triaccel_intersect(const TriAccelP &tr, F3 o, F3 d, float mint, float maxt, float &u, float &v, float &t) {
+    float o_u, o_v, o_k, d_u, d_v, d_k;
+    switch (tr.k) {
+        case 0: o_u = o.y; o_v = o.z; o_k = o.x; d_u = d.y; d_v = d.z; d_k = d.x; break;
+        case 1: o_u = o.z; o_v = o.x; o_k = o.y; d_u = d.z; d_v = d.x; d_k = d.y; break;
+        case 2: o_u = o.x; o_v = o.y; o_k = o.z; d_u = d.x; d_v = d.y; d_k = d.z; break;
+        default: return false;
+    }
+    t = (tr.n_d - o_u * tr.n_u - o_v * tr.n_v - o_k) / (d_u * tr.n_u + d_v * tr.n_v + d_k);
+    if (!(t >= mint && t <= maxt)) return false;   // NaN-safe form of "t < mint || t > maxt -> miss"
+    const float hu = o_u + t * d_u - tr.a_u;
+    const float hv = o_v + t * d_v - tr.a_v;
+    u = hv * tr.b_nu + hu * tr.b_nv;
+    v = hu * tr.c_nu + hv * tr.c_nv;
+    return u >= 0 && v >= 0 && u + v <= 1.0f;
+}
+
+struct BvhNode { float bmin[3], bmax[3]; uint32_t left, count; };   // count>0: leaf, left = first prim slot; else children left, left+1
+
+struct Scene {
+    std::vector<F3> P, N; std::vector<float> UV;
+    std::vector<uint32_t> idx, triShape;
+    std::vector<ppg_shape> shapes; std::vector<ppg_bsdf> bsdfs; std::vector<F3> radiance;
+    ppg_camera cam; F3 aabbMin, aabbMax;
+    std::vector<TriAccelP> accel; std::vector<BvhNode> bvh; std::vector<uint32_t> primOrder;
+    // camera derived (src/sensors/perspective.cpp:120-298)
+    F3 camO, camLeft, camUp, camDir; float tanX, tanY;
+
+    void load(const ppg_scene_desc &d) {
+        P.resize(d.n_vertices); N.resize(d.n_vertices); UV.assign(2 * (size_t) d.n_vertices, 0.f);
+        for (uint32_t i = 0; i < d.n_vertices; ++i) {
+            P[i] = f3(d.positions[3 * i], d.positions[3 * i + 1], d.positions[3 * i + 2]);
+            N[i] = d.normals ? f3(d.normals[3 * i], d.normals[3 * i + 1], d.normals[3 * i + 2]) : f3(0, 0, 0);
+            if (d.uvs) { UV[2 * i] = d.uvs[2 * i]; UV[2 * i + 1] = d.uvs[2 * i + 1]; }
+        }
+        idx.assign(d.indices, d.indices + 3 * (size_t) d.n_triangles);
+        triShape.assign(d.triangle_shape, d.triangle_shape + d.n_triangles);
+        shapes.assign(d.shapes, d.shapes + d.n_shapes);
+        bsdfs.assign(d.bsdfs, d.bsdfs + d.n_bsdfs);
+        radiance.resize(d.n_emitters);
+        for (uint32_t i = 0; i < d.n_emitters; ++i) radiance[i] = f3(d.area_radiance[3 * i], d.area_radiance[3 * i + 1], d.area_radiance[3 * i + 2]);
+        cam = d.camera;
+        aabbMin = f3(d.aabb_min[0], d.aabb_min[1], d.aabb_min[2]); aabbMax = f3(d.aabb_max[0], d.aabb_max[1], d.aabb_max[2]);
+        const float *m = cam.to_world;
+        camLeft = f3(m[0], m[4], m[8]); camUp = f3(m[1], m[5], m[9]); camDir = f3(m[2], m[6], m[10]); camO = f3(m[3], m[7], m[11]);
+        const float aspect = (float) cam.film_width / (float) cam.film_height;
+        tanX = std::tan(0.5f * cam.x_fov_deg * (kPiT / 180.0f));
+        tanY = tanX / aspect;
+        accel.resize(d.n_triangles);
+        for (uint32_t t = 0; t < d.n_triangles; ++t) triaccel_load(accel[t], P[idx[3 * t]], P[idx[3 * t + 1]], P[idx[3 * t + 2]]);
+        buildBvh();
+    }
+
+    // median-split BVH over triangle centroids (quality irrelevant for parity; hit set is what matters)
+    void buildBvh() {
+        const uint32_t nt = (uint32_t) triShape.size();
+        primOrder.resize(nt);
+        for (uint32_t i = 0; i < nt; ++i) primOrder[i] = i;
+        std::vector<F3> cen(nt), tmin(nt), tmax(nt);
+        for (uint32_t t = 0; t < nt; ++t) {
+            F3 a = P[idx[3 * t]], b = P[idx[3 * t + 1]], c = P[idx[3 * t + 2]];
+            tmin[t] = f3(std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z)));
+            tmax[t] = f3(std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)));
+            cen[t] = (tmin[t] + tmax[t]) * 0.5f;
+        }
+        bvh.clear(); bvh.reserve(2 * nt + 1); bvh.emplace_back();
+        struct Job { uint32_t node, first, count; };
+        std::vector<Job> jobs; jobs.push_back(Job{0, 0, nt});
+        while (!jobs.empty()) {
+            Job j = jobs.back(); jobs.pop_back();
+            F3 mn = f3(1e30f, 1e30f, 1e30f), mx = f3(-1e30f, -1e30f, -1e30f), cmn = mn, cmx = mx;
+            for (uint32_t i = j.first; i < j.first + j.count; ++i) {
+                const uint32_t t = primOrder[i];
+                mn = f3(std::min(mn.x, tmin[t].x), std::min(mn.y, tmin[t].y), std::min(mn.z, tmin[t].z));
+                mx = f3(std::max(mx.x, tmax[t].x), std::max(mx.y, tmax[t].y), std::max(mx.z, tmax[t].z));
+                cmn = f3(std::min(cmn.x, cen[t].x), std::min(cmn.y, cen[t].y), std::min(cmn.z, cen[t].z));
+                cmx = f3(std::max(cmx.x, cen[t].x), std::max(cmx.y, cen[t].y), std::max(cmx.z, cen[t].z));
+            }
+            BvhNode nd;
+            nd.bmin[0] = mn.x; nd.bmin[1] = mn.y; nd.bmin[2] = mn.z; nd.bmax[0] = mx.x; nd.bmax[1] = mx.y; nd.bmax[2] = mx.z;
+            const F3 ext = cmx - cmn;
+            int ax = 0; if (ext.y > comp(ext, ax)) ax = 1; if (ext.z > comp(ext, ax)) ax = 2;
+            if (j.count <= 2 || comp(ext, ax) <= 0) { nd.left = j.first; nd.count = j.count; bvh[j.node] = nd; continue; }
+            const uint32_t mid = j.first + j.count / 2;
+            std::nth_element(primOrder.begin() + j.first, primOrder.begin() + mid, primOrder.begin() + j.first + j.count,
+                             [&](uint32_t a, uint32_t b) { return comp(cen[a], ax) < comp(cen[b], ax) || (comp(cen[a], ax) == comp(cen[b], ax) && a < b); });
+            nd.left = (uint32_t) bvh.size(); nd.count = 0; bvh[j.node] = nd;
+            bvh.emplace_back(); bvh.emplace_back();
+            jobs.push_back(Job{nd.left, j.first, mid - j.first});
+            jobs.push_back(Job{nd.left + 1, mid, j.first + j.count - mid});
+        }
+    }
+
+    struct Hit { float t, u, v; uint32_t prim; };
+
+    // nearest hit in [mint, maxt]; ties on t go to the lower triangle index
+    bool intersect(F3 o, F3 d, float mint, float maxt, Hit &hit) const {
+        hit.t = std::numeric_limits<float>::infinity(); hit.prim = 0xFFFFFFFFu;
+        const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        uint32_t stack[64]; int sp = 0; stack[sp++] = 0;
+        while (sp) {
+            const BvhNode &n = bvh[stack[--sp]];
+            float t0 = mint, t1 = std::min(maxt, hit.t);
+            bool miss = false;
+            for (int a = 0; a < 3; ++a) {
+                float ta = (n.bmin[a] - comp(o, a)) * comp(inv, a), tb = (n.bmax[a] - comp(o, a)) * comp(inv, a);
+                if (ta > tb) std::swap(ta, tb);
+                // widen conservatively: degenerate (flat) boxes and NaNs from 0*inf must not cull
+                if (!(ta != ta)) t0 = std::max(t0, ta - std::fabs(ta) * 1e-6f);
+                if (!(tb != tb)) t1 = std::min(t1, tb + std::fabs(tb) * 1e-6f);
+                if (t0 > t1) { miss = true; break; }
+            }
+            if (miss) continue;
+            if (n.count) {
+                for (uint32_t i = n.left; i < n.left + n.count; ++i) {
+                    const uint32_t p = primOrder[i];
+                    float u, v, t;
+                    if (triaccel_intersect(accel[p], o, d, mint, maxt, u, v, t)) {
+                        if (t < hit.t || (t == hit.t && p < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = p; }
+                    }
+                }
+            } else { stack[sp++] = n.left; stack[sp++] = n.left + 1; }
+        }
+        return hit.prim != 0xFFFFFFFFu;
+    }
+};
+
+// Intersection record: the fields of render/shape.h:36 Intersection the path uses
+struct Its {
+    bool valid; float t; F3 p, geoN, shN, shS, shT, wi; uint32_t shape;
+    F3 toLocal(F3 v) const { return f3(dot(v, shS), dot(v, shT), dot(v, shN)); }
+    F3 toWorld(F3 v) const { return shS * v.x + shT * v.y + shN * v.z; }
+};
+
+// ShapeKDTree::rayIntersect incl. the adaptive epsilon (src/librender/skdtree.cpp:112-142)
+// + fillIntersectionRecord (include/mitsuba/render/skdtree.h:343-428) + computeShadingFrame (src/libcore/util.cpp:603-608)
+static inline bool ray_intersect(const Scene &sc, F3 o, F3 d, float mint, float maxt, Its &its) {
+    its.valid = false; its.t = std::numeric_limits<float>::infinity();
+    if (mint == kEpsilon)
+        mint *= std::max(std::max(std::max(std::fabs(o.x), std::fabs(o.y)), std::fabs(o.z)), kEpsilon);
+    Scene::Hit h;
+    if (!sc.intersect(o, d, mint, maxt, h)) return false;
+    its.valid = true; its.t = h.t;
+    const uint32_t i0 = sc.idx[3 * h.prim], i1 = sc.idx[3 * h.prim + 1], i2 = sc.idx[3 * h.prim + 2];
+    const F3 p0 = sc.P[i0], p1 = sc.P[i1], p2 = sc.P[i2];
+    const F3 b = f3(1 - h.u - h.v, h.u, h.v);
+    its.p = p0 * b.x + p1 * b.y + p2 * b.z;
+    const F3 side1 = p1 - p0, side2 = p2 - p0;
+    F3 faceN = cross(side1, side2);
+    const float len = length(faceN);
+    if (!is_zero(faceN)) faceN = faceN * (1.0f / len);   // Normal::operator/= (reciprocal multiply)
+    its.shape = sc.triShape[h.prim];
+    if (sc.shapes[its.shape].has_normals) {
+        its.shN = normalize(sc.N[i0] * b.x + sc.N[i1] * b.y + sc.N[i2] * b.z);
+        if (dot(faceN, its.shN) < 0) faceN = -faceN;
+    } else its.shN = faceN;
+    its.geoN = faceN;
+    const F3 dpdu = side1;   // no UV tangents for meshes without texture coordinates (skdtree.h:373-380)
+    its.shS = normalize(dpdu - its.shN * dot(its.shN, dpdu));
+    its.shT = cross(its.shN, its.shS);
+    its.wi = its.toLocal(-d);
+    return true;
+}
+
+// ------------------------------------------------------------------ BSDF: diffuse (+ twosided)
+// src/libcore/warp.cpp:81-102 then :43-52
+static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
+    const float r1 = 2.0f * sx - 1.0f, r2 = 2.0f * sy - 1.0f;
+    float phi, r;
+    if (r1 == 0 && r2 == 0) { r = phi = 0; }
+    else if (r1 * r1 > r2 * r2) { r = r1; phi = (kPiT / 4.0f) * (r2 / r1); }
+    else { r = r2; phi = (kPiT / 2.0f) - (r1 / r2) * (kPiT / 4.0f); }
+    const float px = r * std::cos(phi), py = r * std::sin(phi);
+    float z = std::sqrt(std::max(0.0f, 1.0f - px * px - py * py));   // math::safe_sqrt
+    if (z == 0) z = 1e-10f;
+    return f3(px, py, z);
+}
+struct BsdfSample { F3 wo; float eta; bool delta; };
+// all three return per src/bsdfs/diffuse.cpp:110-150; twosided per src/bsdfs/twosided.cpp:108-184
+static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo) {
+    if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
+    if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
+    return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * (kInvPi * wo.z);
+}
+static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo) {
+    if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
+    if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+    return kInvPi * wo.z;   // warp::squareToCosineHemispherePdf
+}
+static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfSample &s, float &pdf) {
+    bool flip = false;
+    if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; flip = true; } }
+    s.eta = 1.0f; s.delta = false; pdf = 0;
+    if (wi.z <= 0) return f3(0, 0, 0);
+    s.wo = square_to_cosine_hemisphere(sx, sy);
+    pdf = kInvPi * s.wo.z;
+    if (flip) s.wo.z = -s.wo.z;
+    return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+}
+
+// ------------------------------------------------------------------ the integrator
+struct CommitRec {   // GP:1713-1724 Vertex, minus the tree pointer (kept as backend leaf handle)
+    F3 o, d, voxel, throughput, bsdfVal, radiance; float woPdf, bsdfPdf, dTreePdf; bool isDelta;
+};
+
+template <class Backend> class Tracer {
+public:
+    ppg_params prm; Scene sc; Backend tree; int nthreads;
+    bool isBuilt = false, isFinalIter = false; int iter = 0; int passesRendered = 0;
+    int W, H;
+    std::vector<float> image, sqImage, film;     // W*H*4 (r,g,b,weight)
+    std::vector<std::vector<float>> images; std::vector<float> variances;
+    uint64_t totalVertices = 0, totalPaths = 0;
+    ppg_stats stats;
+    // optional per-path capture for parity tests
+    std::vector<float> *captureLi = nullptr; std::vector<int32_t> *captureDepth = nullptr;
+
+    Tracer(const ppg_params &p, const ppg_scene_desc &d, int threads)
+        : prm(p), tree(d.aabb_min, d.aabb_max), nthreads(threads) {
+        sc.load(d); W = d.camera.film_width; H = d.camera.film_height;
+        image.assign((size_t) W * H * 4, 0.f); sqImage = image; film = image;
+        std::memset(&stats, 0, sizeof(stats));
+    }
+
+    // src/sensors/perspective.cpp:271-298 written out for the lookAt camera (see DESIGN.md "camera")
+    void sampleRay(float px, float py, F3 &o, F3 &d, float &mint, float &maxt) const {
+        const float sx = px * (1.0f / (float) W), sy = py * (1.0f / (float) H);
+        const F3 nearP = f3((1.0f - 2.0f * sx) * sc.tanX, (1.0f - 2.0f * sy) * sc.tanY, 1.0f);
+        const F3 dl = normalize(nearP);
+        const float invZ = 1.0f / dl.z;
+        mint = sc.cam.near_clip * invZ; maxt = sc.cam.far_clip * invZ;
+        o = sc.camO;
+        d = sc.camLeft * dl.x + sc.camUp * dl.y + sc.camDir * dl.z;
+    }
+
+    // GP:1712-2157, surface branch (no media: README.md:5-7), nee = never
+    F3 Li(F3 o, F3 d, float mint, float maxt, Pcg32 &rng, uint64_t sampleIndex, int &depthOut, uint64_t &nVerticesTraced) {
+        typename Backend::Leaf *vLeaf[32]; CommitRec vtx[32]; int nVertices = 0;
+        F3 LiAcc = f3(0, 0, 0), throughput = f3(1, 1, 1); float eta = 1.0f;
+        bool scattered = false, emittedRadiance = true;   // rRec.type & EEmittedRadiance (ERadiance for sensor rays)
+        int depth = 1;
+        Its its; ray_intersect(sc, o, d, mint, maxt, its);
+        nVerticesTraced++;
+        auto recordRadiance = [&](F3 r) { LiAcc = LiAcc + r; for (int i = 0; i < nVertices; ++i) vtx[i].radiance = vtx[i].radiance + r; };   // GP:1791-1796
+        while (depth <= prm.max_depth || prm.max_depth < 0) {
+            if (!its.valid) break;   // no environment emitter in scope (GP:1902-1914)
+            const ppg_shape &shp = sc.shapes[its.shape];
+            if (shp.emitter >= 0 && emittedRadiance && (!prm.hide_emitters || scattered)) {   // GP:1917-1919; area.cpp:104-109
+                if (dot(its.shN, -d) > 0) recordRadiance(throughput * sc.radiance[shp.emitter]);
+            }
+            if (depth >= prm.max_depth && prm.max_depth != -1) break;                          // GP:1925
+            const float wiDotGeoN = -dot(its.geoN, d), wiDotShN = its.wi.z;
+            if (wiDotGeoN * wiDotShN < 0 && prm.strict_normals) break;                         // GP:1929-1932
+            const ppg_bsdf &bsdf = sc.bsdfs[shp.bsdf];
+            float voxel[3]; typename Backend::Leaf *leaf = tree.lookup(&its.p.x, voxel);       // GP:1942-1944 (diffuse is smooth)
+            float frac = prm.bsdf_sampling_fraction;
+            if (leaf && prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) frac = tree.bsdfSamplingFraction(leaf);   // GP:1946-1949
+            // ---- sampleMat, GP:1650-1691
+            float woPdf, bsdfPdf, dTreePdf; F3 bsdfWeight; BsdfSample bs;
+            float sx = rng.next1D(), sy = rng.next1D();
+            if (!isBuilt || !leaf) {
+                bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf);
+                woPdf = bsdfPdf; dTreePdf = 0;
+            } else {
+                F3 result;
+                bool zero = false;
+                if (sx < frac) {
+                    sx /= frac;
+                    result = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf);
+                    if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0; zero = true; }
+                    else result = result * bsdfPdf;
+                } else {
+                    float dw[3]; tree.sample(leaf, rng, dw);
+                    bs.wo = its.toLocal(f3(dw[0], dw[1], dw[2])); bs.eta = 1.0f; bs.delta = false;
+                    result = bsdf_eval(bsdf, its.wi, bs.wo);
+                }
+                if (zero) bsdfWeight = f3(0, 0, 0);
+                else {
+                    // pdfMat, GP:1693-1710
+                    bsdfPdf = bsdf_pdf(bsdf, its.wi, bs.wo);
+                    if (!std::isfinite(bsdfPdf)) { woPdf = 0; dTreePdf = 0; }
+                    else {
+                        const F3 wow = its.toWorld(bs.wo);
+                        dTreePdf = tree.pdf(leaf, &wow.x);
+                        woPdf = frac * bsdfPdf + (1 - frac) * dTreePdf;
+                    }
+                    bsdfWeight = (woPdf == 0) ? f3(0, 0, 0) : result * (1.0f / woPdf);   // Spectrum::operator/(Float) multiplies by the reciprocal
+                }
+            }
+            if (is_zero(bsdfWeight)) break;                                                     // GP:2024-2025
+            const F3 wo = its.toWorld(bs.wo);
+            const float woDotGeoN = dot(its.geoN, wo);
+            if (woDotGeoN * bs.wo.z <= 0 && prm.strict_normals) break;                          // GP:2028-2032
+            o = its.p; d = wo;
+            throughput = throughput * bsdfWeight; eta *= bs.eta;
+            // ---- next hit + emitter lookup, GP:2078-2091 (rayIntersectAndLookForEmitter, no null surfaces in scope)
+            F3 value = f3(0, 0, 0);
+            Its next; ray_intersect(sc, o, d, kEpsilon, std::numeric_limits<float>::infinity(), next);
+            nVerticesTraced++;
+            if (next.valid) {
+                const ppg_shape &ns = sc.shapes[next.shape];
+                if (ns.emitter >= 0 && dot(next.shN, -d) > 0) value = sc.radiance[ns.emitter];
+            }
+            const bool isDelta = bs.delta;
+            {
+                const float a = woPdf * woPdf;                       // miWeight(woPdf, 0), GP:2247-2250
+                const float weight = a / (a + 0.0f);
+                const F3 L = throughput * value * weight;
+                if (!is_zero(L)) recordRadiance(L);
+                if ((!isDelta || prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) && leaf && nVertices < 32 && !isFinalIter) {   // GP:2093-2110
+                    if (1 / woPdf > 0) {
+                        CommitRec &v = vtx[nVertices]; vLeaf[nVertices] = leaf;
+                        v.o = o; v.d = d; v.voxel = f3(voxel[0], voxel[1], voxel[2]); v.throughput = throughput;
+                        v.bsdfVal = bsdfWeight * woPdf; v.radiance = L; v.woPdf = woPdf; v.bsdfPdf = bsdfPdf; v.dTreePdf = dTreePdf; v.isDelta = isDelta;
+                        ++nVertices;
+                    }
+                }
+            }
+            its = next;
+            emittedRadiance = false;                                                            // GP:2121 ERadianceNoEmission
+            if (depth++ >= prm.rr_depth) {                                                      // GP:2123-2142
+                float successProb = 1.0f;
+                if (leaf && !isDelta) {
+                    if (!isBuilt) successProb = max3(throughput) * eta * eta;
+                    successProb = std::max(0.1f, std::min(successProb, 0.99f));
+                }
+                if (rng.next1D() >= successProb) break;
+                throughput = throughput * (1.0f / successProb);
+            }
+            scattered = true;
+        }
+        depthOut = depth;
+        if (nVertices > 0 && !isFinalIter) {                                                    // GP:2150-2154
+            const int loss = isBuilt ? prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE;
+            for (int i = 0; i < nVertices; ++i) commit(vLeaf[i], vtx[i], 1.0f, loss, sampleIndex, (uint32_t) i);
+        }
+        return LiAcc;
+    }
+
+    // Vertex::commit, GP:1730-1768
+    void commit(typename Backend::Leaf *leaf, const CommitRec &v, float statisticalWeight, int loss, uint64_t sampleIndex, uint32_t ordinal) {
+        if (!(v.woPdf > 0) || !is_valid(v.radiance) || !is_valid(v.bsdfVal)) return;
+        F3 local = f3(0, 0, 0);
+        if (v.throughput.x * v.woPdf > kEpsilon) local.x = v.radiance.x / v.throughput.x;
+        if (v.throughput.y * v.woPdf > kEpsilon) local.y = v.radiance.y / v.throughput.y;
+        if (v.throughput.z * v.woPdf > kEpsilon) local.z = v.radiance.z / v.throughput.z;
+        const F3 product = local * v.bsdfVal;
+        const float avgLocal = (local.x + local.y + local.z) * (1.0f / 3.0f);      // Spectrum::average(): sum * (1/N)
+        const float avgProduct = (product.x + product.y + product.z) * (1.0f / 3.0f);
+        float rnd[3] = {0, 0, 0};
+        if (prm.spatial_filter == PPG_SFILTER_STOCHASTIC) {
+            Pcg32 r; seed_vertex_rng(r, prm.seed, sampleIndex, ordinal);
+            rnd[0] = r.next1D(); rnd[1] = r.next1D(); rnd[2] = r.next1D();
+        }
+        tree.record(leaf, &v.o.x, &v.voxel.x, &v.d.x, avgLocal, avgProduct, v.woPdf, v.bsdfPdf, v.dTreePdf, statisticalWeight, v.isDelta,
+                    prm.spatial_filter, prm.directional_filter, loss, rnd);
+    }
+
+    // renderBlock (GP:1587-1641) over every 32x32 block of one pass, OpenMP over blocks like the LocalWorkers
+    void renderPass(int passGlobal) {
+        const int bs = 32, bx = (W + bs - 1) / bs, by = (H + bs - 1) / bs;
+        uint64_t verts = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : verts)
+        for (int blk = 0; blk < bx * by; ++blk) {
+            const int x0 = (blk % bx) * bs, y0 = (blk / bx) * bs;
+            for (int y = y0; y < std::min(y0 + bs, H); ++y)
+                for (int x = x0; x < std::min(x0 + bs, W); ++x)
+                    for (int j = 0; j < prm.spp_per_pass; ++j) {
+                        const uint64_t sampleIndex = (((uint64_t) passGlobal * H + y) * W + x) * prm.spp_per_pass + j;
+                        Pcg32 rng; seed_path_rng(rng, prm.seed, sampleIndex);
+                        const float jx = rng.next1D(), jy = rng.next1D();
+                        F3 o, d; float mint, maxt;
+                        sampleRay((float) x + jx, (float) y + jy, o, d, mint, maxt);
+                        int depth; uint64_t nv = 0;
+                        const F3 spec = Li(o, d, mint, maxt, rng, sampleIndex, depth, nv);
+                        verts += nv;
+                        if (captureLi) {
+                            const size_t li = ((size_t) y * W + x) * prm.spp_per_pass + j;
+                            (*captureLi)[3 * li] = spec.x; (*captureLi)[3 * li + 1] = spec.y; (*captureLi)[3 * li + 2] = spec.z;
+                            if (captureDepth) (*captureDepth)[li] = depth;
+                        }
+                        if (!is_valid(spec)) continue;                    // ImageBlock::put rejects invalid samples (imageblock.h:150-154)
+                        float *px = &image[((size_t) y * W + x) * 4], *sq = &sqImage[((size_t) y * W + x) * 4];
+                        px[0] += spec.x; px[1] += spec.y; px[2] += spec.z; px[3] += 1.0f;
+                        sq[0] += spec.x * spec.x; sq[1] += spec.y * spec.y; sq[2] += spec.z * spec.z; sq[3] += 1.0f;
+                    }
+        }
+        totalVertices += verts; totalPaths += (uint64_t) W * H * prm.spp_per_pass;
+    }
+
+    // performRenderPasses, GP:1210-1329 (scheduling elided)
+    bool performRenderPasses(float &variance, int numPasses, ppg_iteration_stats &st) {
+        std::fill(image.begin(), image.end(), 0.f); std::fill(sqImage.begin(), sqImage.end(), 0.f);
+        const auto t0 = std::chrono::steady_clock::now();
+        const uint64_t v0 = totalVertices, p0 = totalPaths;
+        int local = 0;
+        for (int i = 0; i < numPasses; ++i) {
+            renderPass(passesRendered);
+            ++passesRendered; ++local;
+            if (prm.budget_type == PPG_BUDGET_SECONDS && elapsed(startTime) > prm.budget) break;   // GP:1259-1262
+        }
+        for (size_t i = 0; i < film.size(); ++i) film[i] += image[i];                             // film->put(block), renderproc.cpp:143-151
+        if (prm.sample_combination == PPG_COMB_INVERSEVAR) images.push_back(image);              // GP:1292-1296
+        // variance estimate with the getPixel() quirk (GP:1300-1313)
+        const int N = local * prm.spp_per_pass;
+        variance = 0;
+        for (int x = 0; x < W; ++x) for (int y = 0; y < H; ++y) {
+            const float *px = &image[((size_t) y * W + x) * 4], *sq = &sqImage[((size_t) y * W + x) * 4];
+            const float iw = px[3] != 0 ? 1.0f / px[3] : 0.0f, isw = sq[3] != 0 ? 1.0f / sq[3] : 0.0f;
+            float lv[3];
+            for (int c = 0; c < 3; ++c) { const float pix = px[c] * iw; lv[c] = sq[c] * isw - pix * pix / (float) N; }
+            const float lum = lv[0] * 0.212671f + lv[1] * 0.715160f + lv[2] * 0.072169f;
+            variance += std::min(lum, 10000.0f);
+        }
+        variance /= (float) W * H * (N - 1);
+        if (prm.sample_combination == PPG_COMB_INVERSEVAR) variances.push_back(variance);
+        st.seconds += elapsed(t0); st.passes += local; st.variance = variance; st.total_passes = passesRendered;
+        st.vertices += totalVertices - v0; st.paths += totalPaths - p0;
+        return true;
+    }
+
+    std::chrono::steady_clock::time_point startTime;
+    static float elapsed(std::chrono::steady_clock::time_point s) {
+        return (float) std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - s).count() / 1000;
+    }
+
+    void resetSDTree() {   // GP:1108-1113
+        tree.refine((size_t) (std::sqrt(std::pow(2, iter) * prm.spp_per_pass / 4) * prm.s_tree_threshold), prm.sd_tree_max_memory);
+        tree.resetAll(20, prm.d_tree_threshold, nthreads);
+    }
+    void buildSDTree(ppg_iteration_stats &st) {   // GP:1115-1189
+        tree.buildAll(nthreads);
+        tree.statistics(st);
+        isBuilt = true;
+    }
+
+    void beginIterStats(ppg_iteration_stats &st, int passes) { std::memset(&st, 0, sizeof(st)); st.iteration = iter; (void) passes; }
+
+    // GP:1342-1426
+    bool renderSPP() {
+        const int nPasses = (int) std::ceil((size_t) prm.budget / (float) prm.spp_per_pass);
+        bool result = true; float currentVarAtEnd = std::numeric_limits<float>::infinity();
+        while (result && passesRendered < nPasses) {
+            const int sppRendered = passesRendered * prm.spp_per_pass;
+            int remainingPasses = nPasses - passesRendered;
+            int passesThisIteration = std::min(remainingPasses, 1 << iter);
+            if (remainingPasses - passesThisIteration < 2 * passesThisIteration) passesThisIteration = remainingPasses;
+            isFinalIter = passesThisIteration >= remainingPasses;
+            ppg_iteration_stats &st = stats.iterations[std::min(iter, PPG_MAX_ITERATIONS - 1)]; beginIterStats(st, passesThisIteration);
+            std::fill(film.begin(), film.end(), 0.f);
+            auto t0 = std::chrono::steady_clock::now(); resetSDTree(); st.reset_seconds = elapsed(t0);
+            float variance;
+            if (!performRenderPasses(variance, passesThisIteration, st)) { result = false; break; }
+            const float lastVarAtEnd = currentVarAtEnd;
+            currentVarAtEnd = passesThisIteration * variance / remainingPasses;
+            remainingPasses -= passesThisIteration;
+            if (prm.sample_combination == PPG_COMB_AUTOMATIC && remainingPasses > 0 &&
+                (remainingPasses < passesThisIteration || (sppRendered > 256 && currentVarAtEnd > lastVarAtEnd))) {
+                isFinalIter = true;
+                if (!performRenderPasses(variance, remainingPasses, st)) { result = false; break; }
+            }
+            st.is_final = isFinalIter;
+            t0 = std::chrono::steady_clock::now(); buildSDTree(st); st.build_seconds = elapsed(t0);
+            ++iter; stats.n_iterations = std::min(iter, PPG_MAX_ITERATIONS);
+        }
+        return result;
+    }
+
+    // GP:1434-1514
+    bool renderTime() {
+        const float nSeconds = prm.budget; bool result = true;
+        float currentVarAtEnd = std::numeric_limits<float>::infinity(), elapsedSeconds = 0;
+        while (result && elapsedSeconds < nSeconds) {
+            const int sppRendered = passesRendered * prm.spp_per_pass;
+            float remainingTime = nSeconds - elapsedSeconds;
+            const int passesThisIteration = 1 << iter;
+            ppg_iteration_stats &st = stats.iterations[std::min(iter, PPG_MAX_ITERATIONS - 1)]; beginIterStats(st, passesThisIteration);
+            const auto startIter = std::chrono::steady_clock::now();
+            std::fill(film.begin(), film.end(), 0.f);
+            resetSDTree(); st.reset_seconds = elapsed(startIter);
+            float variance;
+            if (!performRenderPasses(variance, passesThisIteration, st)) { result = false; break; }
+            const float secondsIter = elapsed(startIter);
+            const float lastVarAtEnd = currentVarAtEnd;
+            currentVarAtEnd = secondsIter * variance / remainingTime;
+            remainingTime -= secondsIter;
+            if (prm.sample_combination == PPG_COMB_AUTOMATIC && remainingTime > 0 &&
+                (remainingTime < secondsIter || (sppRendered > 256 && currentVarAtEnd > lastVarAtEnd))) {
+                isFinalIter = true;
+                do {
+                    if (!performRenderPasses(variance, passesThisIteration, st)) { result = false; break; }
+                    elapsedSeconds = elapsed(startTime);
+                } while (elapsedSeconds < nSeconds);
+            }
+            st.is_final = isFinalIter;
+            auto t0 = std::chrono::steady_clock::now(); buildSDTree(st); st.build_seconds = elapsed(t0);
+            ++iter; stats.n_iterations = std::min(iter, PPG_MAX_ITERATIONS);
+            elapsedSeconds = elapsed(startTime);
+        }
+        return result;
+    }
+
+    // GP:1516-1585; film develop = weight-normalised RGB (hdrfilm)
+    bool render(float *rgbOut) {
+        iter = 0; isFinalIter = false; passesRendered = 0; images.clear(); variances.clear();
+        startTime = std::chrono::steady_clock::now();
+        const bool ok = prm.budget_type == PPG_BUDGET_SPP ? renderSPP() : renderTime();
+        std::vector<float> out((size_t) W * H * 3, 0.f);
+        if (prm.sample_combination == PPG_COMB_INVERSEVAR) {   // GP:1567-1582
+            const size_t begin = images.size() - std::min(images.size(), (size_t) 4);
+            float totalWeight = 0;
+            for (size_t i = begin; i < variances.size(); ++i) totalWeight += 1.0f / variances[i];
+            for (size_t i = begin; i < images.size(); ++i) {
+                const float wgt = 1.0f / variances[i] / totalWeight;
+                for (size_t p = 0; p < (size_t) W * H; ++p) {
+                    const float *px = &images[i][p * 4]; const float iw = px[3] != 0 ? 1.0f / px[3] : 0.0f;
+                    for (int c = 0; c < 3; ++c) out[p * 3 + c] += px[c] * iw * wgt;
+                }
+            }
+        } else {
+            for (size_t p = 0; p < (size_t) W * H; ++p) {
+                const float *px = &film[p * 4]; const float iw = px[3] != 0 ? 1.0f / px[3] : 0.0f;
+                for (int c = 0; c < 3; ++c) out[p * 3 + c] = px[c] * iw;
+            }
+        }
+        if (rgbOut) std::memcpy(rgbOut, out.data(), out.size() * sizeof(float));
+        stats.total_passes = passesRendered; stats.total_paths = totalPaths; stats.total_vertices = totalVertices;
+        stats.render_seconds = elapsed(startTime);
+        stats.final_variance = stats.n_iterations ? stats.iterations[stats.n_iterations - 1].variance : 0;
+        return ok;
+    }
+};
+
+}  // namespace ppgo

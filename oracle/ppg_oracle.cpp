@@ -1,0 +1,187 @@
+// TEST INFRASTRUCTURE -- C API of the CPU oracle (see ppg_oracle.h).
+// Built twice by oracle/Makefile:
+//   oracle/libppg_oracle.so           restated SD-tree (sdtree_port.h)              -- "port"
+//   oracle/_ref/libppg_oracle_ref.so  reference SD-tree compiled verbatim (-DPPGO_BACKEND_REF,
+//                                     guided_path.cpp:25-1008 piped in ahead of this file) -- "reference" trees
+#ifdef PPGO_BACKEND_REF
+#include "sdtree_ref/ref_backend.h"
+typedef ppgo::RefBackend BackendT;
+#else
+#include "backend_port.h"
+typedef ppgo::PortBackend BackendT;
+#endif
+#include "ppg_oracle.h"
+
+#include <memory>
+
+using namespace ppgo;
+
+struct ppgo_handle {
+    std::unique_ptr<Tracer<BackendT>> tracer;   // when a scene is given
+    std::unique_ptr<BackendT> tree;             // tree-only handle
+    std::vector<float> capLi; std::vector<int32_t> capDepth; float *userLi = nullptr; int32_t *userDepth = nullptr;
+    BackendT &T() { return tracer ? tracer->tree : *tree; }
+};
+
+extern "C" {
+
+int ppgo_is_reference_backend(void) {
+#ifdef PPGO_BACKEND_REF
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+ppgo_handle *ppgo_create(const ppg_params *p, const ppg_scene_desc *scene, const float *aabb_min, const float *aabb_max, int nthreads) {
+    ppgo_handle *h = new ppgo_handle();
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    if (scene) h->tracer.reset(new Tracer<BackendT>(*p, *scene, nthreads));
+    else h->tree.reset(new BackendT(aabb_min, aabb_max));
+    return h;
+}
+void ppgo_destroy(ppgo_handle *h) { delete h; }
+
+int ppgo_set_capture(ppgo_handle *h, float *li, int32_t *depth) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    Tracer<BackendT> &t = *h->tracer;
+    const size_t n = (size_t) t.W * t.H * t.prm.spp_per_pass;
+    h->capLi.assign(3 * n, 0.f); h->capDepth.assign(n, 0);
+    h->userLi = li; h->userDepth = depth;
+    t.captureLi = &h->capLi; t.captureDepth = &h->capDepth;
+    return PPG_OK;
+}
+static void flush_capture(ppgo_handle *h) {
+    if (h->userLi) std::memcpy(h->userLi, h->capLi.data(), h->capLi.size() * sizeof(float));
+    if (h->userDepth) std::memcpy(h->userDepth, h->capDepth.data(), h->capDepth.size() * sizeof(int32_t));
+}
+
+int ppgo_render(ppgo_handle *h, float *rgb_out, ppg_stats *stats) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    const bool ok = h->tracer->render(rgb_out);
+    if (stats) *stats = h->tracer->stats;
+    flush_capture(h);
+    return ok ? PPG_OK : PPG_ERR_CANCELLED;
+}
+
+int ppgo_step_reset(ppgo_handle *h, int iter) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    Tracer<BackendT> &t = *h->tracer;
+    if (iter == 0) { t.passesRendered = 0; t.startTime = std::chrono::steady_clock::now(); }
+    t.iter = iter; std::fill(t.film.begin(), t.film.end(), 0.f);
+    t.resetSDTree();
+    return PPG_OK;
+}
+int ppgo_step_passes(ppgo_handle *h, int n_passes, int is_final, float *variance_out) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    Tracer<BackendT> &t = *h->tracer;
+    t.isFinalIter = is_final != 0;
+    ppg_iteration_stats st; std::memset(&st, 0, sizeof(st));
+    const ppg_budget_type keep = (ppg_budget_type) t.prm.budget_type; t.prm.budget_type = PPG_BUDGET_SPP;
+    float var = 0; t.performRenderPasses(var, n_passes, st);
+    t.prm.budget_type = keep;
+    if (variance_out) *variance_out = var;
+    flush_capture(h);
+    return PPG_OK;
+}
+int ppgo_step_build(ppgo_handle *h, ppg_iteration_stats *st) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    ppg_iteration_stats tmp; std::memset(&tmp, 0, sizeof(tmp));
+    h->tracer->buildSDTree(tmp);
+    if (st) *st = tmp;
+    return PPG_OK;
+}
+int ppgo_get_moment_images(ppgo_handle *h, float *sum_rgbw, float *sumsq_rgbw) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    if (sum_rgbw) std::memcpy(sum_rgbw, h->tracer->image.data(), h->tracer->image.size() * sizeof(float));
+    if (sumsq_rgbw) std::memcpy(sumsq_rgbw, h->tracer->sqImage.data(), h->tracer->sqImage.size() * sizeof(float));
+    return PPG_OK;
+}
+
+int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb) { h->T().refine((size_t) threshold, max_mb); return PPG_OK; }
+int ppgo_tree_reset(ppgo_handle *h, int max_depth, float threshold) { h->T().resetAll(max_depth, threshold, 1); return PPG_OK; }
+int ppgo_tree_build(ppgo_handle *h) { h->T().buildAll(1); return PPG_OK; }
+
+int ppgo_tree_record(ppgo_handle *h, size_t n, const float *o, const float *d, const float *radiance, const float *product,
+                     const float *wo_pdf, const float *bsdf_pdf, const float *dtree_pdf, const float *weight, const uint8_t *is_delta,
+                     const float *rnd, int sfilter, int dfilter, int loss) {
+    BackendT &T = h->T();
+    static const float zero3[3] = {0.5f, 0.5f, 0.5f};
+    for (size_t i = 0; i < n; ++i) {
+        float voxel[3]; BackendT::Leaf *leaf = T.lookup(o + 3 * i, voxel);
+        T.record(leaf, o + 3 * i, voxel, d + 3 * i, radiance[i], product ? product[i] : 0.f, wo_pdf[i], bsdf_pdf ? bsdf_pdf[i] : 0.f,
+                 dtree_pdf ? dtree_pdf[i] : 0.f, weight ? weight[i] : 1.0f, is_delta ? is_delta[i] != 0 : false, sfilter, dfilter, loss,
+                 rnd ? rnd + 3 * i : zero3);
+    }
+    return PPG_OK;
+}
+int ppgo_tree_lookup(ppgo_handle *h, size_t n, const float *p, uint32_t *leaf_out, float *size_out) {
+    BackendT &T = h->T();
+    for (size_t i = 0; i < n; ++i) {
+        float voxel[3]; BackendT::Leaf *leaf = T.lookup(p + 3 * i, voxel);
+        if (leaf_out) leaf_out[i] = (uint32_t) T.leafIndex(leaf);
+        if (size_out) { size_out[3 * i] = voxel[0]; size_out[3 * i + 1] = voxel[1]; size_out[3 * i + 2] = voxel[2]; }
+    }
+    return PPG_OK;
+}
+int ppgo_tree_pdf(ppgo_handle *h, size_t n, const uint32_t *leaf, const float *dir, float *pdf_out) {
+    BackendT &T = h->T();
+    for (size_t i = 0; i < n; ++i) pdf_out[i] = T.pdf(T.leafAt(leaf[i]), dir + 3 * i);
+    return PPG_OK;
+}
+int ppgo_tree_sample(ppgo_handle *h, size_t n, const uint32_t *leaf, const float *rnd, size_t rnd_stride, float *dir_out) {
+    BackendT &T = h->T();
+    for (size_t i = 0; i < n; ++i) T.sampleReplay(T.leafAt(leaf[i]), rnd + rnd_stride * i, rnd_stride, dir_out + 3 * i);
+    return PPG_OK;
+}
+int ppgo_tree_fraction(ppgo_handle *h, size_t n, const uint32_t *leaf, float *frac_out) {
+    BackendT &T = h->T();
+    for (size_t i = 0; i < n; ++i) frac_out[i] = T.bsdfSamplingFraction(T.leafAt(leaf[i]));
+    return PPG_OK;
+}
+int ppgo_tree_counts(ppgo_handle *h, uint64_t counts[4]) {
+    BackendT &T = h->T();
+    counts[0] = T.numNodes(); counts[1] = counts[2] = counts[3] = 0;
+    for (size_t i = 0; i < T.numNodes(); ++i) if (T.isLeaf(i)) { counts[1]++; counts[2] += T.treeSize(i, false); counts[3] += T.treeSize(i, true); }
+    return PPG_OK;
+}
+int ppgo_tree_export(ppgo_handle *h, int which, uint32_t *s_children, int32_t *s_axis, uint8_t *s_is_leaf,
+                     uint64_t *tree_first, uint32_t *tree_count, float *tree_sum, float *tree_weight, int32_t *tree_depth,
+                     float *sums, uint16_t *children, float *adam, float *aabb_min_max) {
+    BackendT &T = h->T();
+    const bool building = which != 0;
+    uint64_t off = 0;
+    for (size_t i = 0; i < T.numNodes(); ++i) {
+        const bool leaf = T.isLeaf(i);
+        if (s_children) { s_children[2 * i] = leaf ? 0 : T.child(i, 0); s_children[2 * i + 1] = leaf ? 0 : T.child(i, 1); }
+        if (s_axis) s_axis[i] = T.axis(i);
+        if (s_is_leaf) s_is_leaf[i] = leaf;
+        if (adam) T.adamState(i, adam + 6 * i);
+        if (!leaf) {
+            if (tree_first) tree_first[i] = off;
+            if (tree_count) tree_count[i] = 0;
+            if (tree_sum) tree_sum[i] = 0;
+            if (tree_weight) tree_weight[i] = 0;
+            if (tree_depth) tree_depth[i] = 0;
+            continue;
+        }
+        const size_t n = T.treeSize(i, building);
+        if (tree_first) tree_first[i] = off;
+        if (tree_count) tree_count[i] = (uint32_t) n;
+        if (tree_sum) tree_sum[i] = T.treeSum(i, building);
+        if (tree_weight) tree_weight[i] = T.treeWeight(i, building);
+        if (tree_depth) tree_depth[i] = T.treeDepth(i, building);
+        if (sums || children) {
+            for (size_t k = 0; k < n; ++k) {
+                float s[4]; uint16_t c[4]; T.treeNode(i, building, k, s, c);
+                if (sums) std::memcpy(sums + 4 * (off + k), s, sizeof(s));
+                if (children) std::memcpy(children + 4 * (off + k), c, sizeof(c));
+            }
+        }
+        off += n;
+    }
+    if (aabb_min_max) T.aabb(aabb_min_max, aabb_min_max + 3);
+    return PPG_OK;
+}
+
+}  // extern "C"

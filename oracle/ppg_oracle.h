@@ -1,0 +1,52 @@
+/* TEST INFRASTRUCTURE -- C API of the CPU oracle (libppg_oracle.so / _ref/libppg_oracle_ref.so).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it. */
+#ifndef PPG_ORACLE_H
+#define PPG_ORACLE_H
+#include "../include/ppg.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct ppgo_handle ppgo_handle;
+
+/* 1 if this library embeds the reference's verbatim SD-tree code, 0 for the restatement */
+int ppgo_is_reference_backend(void);
+
+/* full integrator (scene may be NULL for a tree-only handle; then aabb_min/max give the S-tree box) */
+ppgo_handle *ppgo_create(const ppg_params *p, const ppg_scene_desc *scene, const float *aabb_min, const float *aabb_max, int nthreads);
+void ppgo_destroy(ppgo_handle *h);
+int ppgo_render(ppgo_handle *h, float *rgb_out, ppg_stats *stats);
+/* capture per-sample radiance of the LAST pass rendered: li (W*H*spp*3), depth (W*H*spp) -- set before ppgo_render */
+int ppgo_set_capture(ppgo_handle *h, float *li, int32_t *depth);
+/* step-wise driving (tests): iteration k reset, n passes, build */
+int ppgo_step_reset(ppgo_handle *h, int iter);
+int ppgo_step_passes(ppgo_handle *h, int n_passes, int is_final, float *variance_out);
+int ppgo_step_build(ppgo_handle *h, ppg_iteration_stats *st);
+int ppgo_get_moment_images(ppgo_handle *h, float *sum_rgbw, float *sumsq_rgbw);
+
+/* ---- SD-tree level operations (work on the handle's tree) */
+int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb);
+int ppgo_tree_reset(ppgo_handle *h, int max_depth, float threshold);
+int ppgo_tree_build(ppgo_handle *h);
+/* Vertex::commit's record step for n records (sequential, deterministic order).
+ * arrays: o,voxel,d: 3n; radiance,product,wo_pdf,bsdf_pdf,dtree_pdf,weight: n; is_delta: n (u8); rnd: 3n */
+int ppgo_tree_record(ppgo_handle *h, size_t n, const float *o, const float *d, const float *radiance, const float *product,
+                     const float *wo_pdf, const float *bsdf_pdf, const float *dtree_pdf, const float *weight, const uint8_t *is_delta,
+                     const float *rnd, int sfilter, int dfilter, int loss);
+/* lookup: leaf node index + voxel size */
+int ppgo_tree_lookup(ppgo_handle *h, size_t n, const float *p, uint32_t *leaf_out, float *size_out);
+int ppgo_tree_pdf(ppgo_handle *h, size_t n, const uint32_t *leaf, const float *dir, float *pdf_out);
+int ppgo_tree_sample(ppgo_handle *h, size_t n, const uint32_t *leaf, const float *rnd, size_t rnd_stride, float *dir_out);
+int ppgo_tree_fraction(ppgo_handle *h, size_t n, const uint32_t *leaf, float *frac_out);
+/* counts[0]=S-tree nodes, [1]=leaves, [2]=total sampling quadtree nodes, [3]=total building quadtree nodes */
+int ppgo_tree_counts(ppgo_handle *h, uint64_t counts[4]);
+/* export: s_children 2*N u32 (0,0 for leaves), s_axis N i32, s_is_leaf N u8;
+ * per S-tree node i (valid for leaves): tree_first[which][i], tree_count, tree_sum, tree_weight, tree_depth;
+ * quadtree nodes concatenated in S-tree node order: sums 4 floats, children 4 u16. which: 0 sampling, 1 building.
+ * adam: 6 floats per S-tree node (iter, m, v, variable, batchAcc, batchGrad). Any pointer may be NULL. */
+int ppgo_tree_export(ppgo_handle *h, int which, uint32_t *s_children, int32_t *s_axis, uint8_t *s_is_leaf,
+                     uint64_t *tree_first, uint32_t *tree_count, float *tree_sum, float *tree_weight, int32_t *tree_depth,
+                     float *sums, uint16_t *children, float *adam, float *aabb_min_max);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,547 @@
+"""Minimal Mitsuba-0.5 scene loader -> flat arrays for ``ppg_set_scene``.
+
+Restates only what the bundled scenes of the reference need (SURVEY.md §2 #11,
+§7 step 2): it is a *host loader for the hot path*, not a scene graph.
+
+Reference behaviour followed (paths under /root/reference/mitsuba):
+  * <spectrum value="l:v,..."> -> zero-extended piecewise-linear spectrum,
+    convolved with the CIE 1931 matching functions, -> XYZ -> linear Rec.709
+    (src/librender/scenehandler.cpp:597-613, src/libcore/spectrum.cpp:172-191,
+    222-227, 630-686).  Single-valued emitter spectra are multiplied by D65
+    (scenehandler.cpp:575-593); <rgb> is taken verbatim.
+  * transforms compose left-to-right as ``T_new * T_so_far``
+    (scenehandler.cpp:348-441); lookAt builds (left, up, dir, origin) columns
+    (src/libcore/transform.cpp:191-214).
+  * OBJ: n-gons are fanned (src/shapes/obj.cpp:313-324), vertices merged per
+    (p, n, uv) key, missing normals replaced by angle-weighted smooth normals
+    (src/librender/trimesh.cpp:608-690) unless ``faceNormals``.
+  * perspective sensor: fovAxis resolution (src/librender/sensor.cpp:239-300).
+  * scene AABB = geometry AABB + sensor position + emitter AABBs
+    (src/librender/scene.cpp:387-413).
+  * shapes with an emitter and no BSDF get a black diffuse BSDF, shapes with
+    neither get 0.5 grey diffuse (src/librender/shape.cpp:48-72).
+"""
+from __future__ import annotations
+
+import math
+import os
+import re
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+_CIE_NPZ = os.path.join(_DATA_DIR, "cie1931.npz")
+_REF_SPECTRUM_CPP = "/root/reference/mitsuba/src/libcore/spectrum.cpp"
+
+BSDF_DIFFUSE = 0
+BSDF_NULL_BLACK = 1
+BSDF_FLAG_TWOSIDED = 1
+
+
+# --------------------------------------------------------------------------- CIE data
+
+def _parse_c_array(text: str, name: str) -> np.ndarray:
+    m = re.search(r"const\s+Float\s+" + name + r"\s*\[[^\]]*\]\s*=\s*\{(.*?)\};", text, re.S)
+    if not m:
+        raise RuntimeError(f"table {name} not found")
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    vals = [float(t.rstrip("fF")) for t in re.split(r"[,\s]+", body.strip()) if t]
+    return np.asarray(vals, dtype=np.float64)
+
+
+def extract_cie_tables(ref_cpp: str = _REF_SPECTRUM_CPP) -> dict:
+    """Read the CIE 1931 2-degree observer + D65 tables (standard colorimetric
+    data, 471 samples 360..830 nm) out of the reference tree.  Only used by
+    tools/make_fixtures.py to (re)generate ppg_b200/data/cie1931.npz."""
+    text = open(ref_cpp, "r", errors="replace").read()
+    out = {}
+    for key, name in (("x", "CIE_X_entries"), ("y", "CIE_Y_entries"), ("z", "CIE_Z_entries"), ("d65", "CIE_D65_entries")):
+        out[key] = _parse_c_array(text, name)
+    n = len(out["x"])
+    # CIE_wavelengths is 360..830 in 1 nm steps (spectrum.cpp: CIE_wavelengths[CIE_samples])
+    out["lambda"] = np.arange(360.0, 360.0 + n, 1.0)
+    # D65 is normalised so that it has unit luminance (spectrum.cpp staticInitialization)
+    return out
+
+
+_cie_cache = None
+
+
+def _cie():
+    global _cie_cache
+    if _cie_cache is None:
+        if os.path.exists(_CIE_NPZ):
+            d = np.load(_CIE_NPZ)
+            _cie_cache = {k: d[k] for k in d.files}
+        elif os.path.exists(_REF_SPECTRUM_CPP):
+            _cie_cache = extract_cie_tables()
+        else:
+            raise RuntimeError("CIE tables unavailable: run tools/make_fixtures.py where /root/reference exists")
+    return _cie_cache
+
+
+def _eval_reversed(l, v, x_mid, x):
+    """InterpolatedSpectrum::eval (src/libcore/spectrum.cpp:688-714) strictly inside a
+    knot interval.  NOTE the argument order of its lerp: ``math::lerp(t, fb, fa)`` --
+    the reference interpolates *mirrored* inside every interval (value fb at the left
+    knot side, fa at the right).  fromContinuousSpectrum integrates exactly this
+    function (Gauss-Lobatto over ProductSpectrum::eval), so the RGB values of coarse
+    spectra (the CBOX emitter: 100 nm knots) depend on the quirk; we reproduce it.
+    ``x_mid`` selects the interval, ``x`` is where the interval's line is evaluated."""
+    j = np.searchsorted(l, x_mid, side="right") - 1
+    inside = (x_mid > l[0]) & (x_mid < l[-1])
+    j = np.clip(j, 0, len(l) - 2)
+    a, b = l[j], l[j + 1]
+    t = (x - a) / (b - a)
+    val = (1.0 - t) * v[j + 1] + t * v[j]
+    return np.where(inside, val, 0.0)
+
+
+def _integrate_product(l1, v1, l2, v2, lo, hi):
+    """Integral over [lo,hi] of the product of two InterpolatedSpectrum::eval functions
+    (piecewise linear per knot interval, zero outside): Simpson per merged knot interval
+    is exact for the quadratic pieces."""
+    knots = np.unique(np.concatenate([l1, l2, [lo, hi]]))
+    knots = knots[(knots >= lo) & (knots <= hi)]
+    a, b = knots[:-1], knots[1:]
+    mid = 0.5 * (a + b)
+    fa = _eval_reversed(l1, v1, mid, a) * _eval_reversed(l2, v2, mid, a)
+    fm = _eval_reversed(l1, v1, mid, mid) * _eval_reversed(l2, v2, mid, mid)
+    fb = _eval_reversed(l1, v1, mid, b) * _eval_reversed(l2, v2, mid, b)
+    return float(np.sum((b - a) / 6.0 * (fa + 4.0 * fm + fb)))
+
+
+def spectrum_to_rgb(wavelengths, values) -> np.ndarray:
+    """InterpolatedSpectrum(...).zeroExtend() -> Spectrum::fromContinuousSpectrum
+    (RGB build) -> clampNegative."""
+    lam = np.asarray(wavelengths, dtype=np.float64)
+    val = np.asarray(values, dtype=np.float64)
+    if len(lam) < 2:
+        raise ValueError("InterpolatedSpectrum::zeroExtend() -- at least 2 entries are needed!")
+    spacing = float(np.mean(np.diff(lam)))
+    if val[0] != 0:
+        lam = np.concatenate([[lam[0] - spacing], lam]); val = np.concatenate([[0.0], val])
+    if val[-1] != 0:
+        lam = np.concatenate([lam, [lam[-1] + spacing]]); val = np.concatenate([val, [0.0]])
+    c = _cie()
+    cl = c["lambda"]
+    lo, hi = cl[0], cl[-1]
+    X = _integrate_product(lam, val, cl, c["x"], lo, hi)
+    Y = _integrate_product(lam, val, cl, c["y"], lo, hi)
+    Z = _integrate_product(lam, val, cl, c["z"], lo, hi)
+    ynorm = float(np.trapezoid(c["y"], cl))
+    X, Y, Z = X / ynorm, Y / ynorm, Z / ynorm
+    rgb = np.array([
+        3.240479 * X - 1.537150 * Y - 0.498535 * Z,
+        -0.969256 * X + 1.875991 * Y + 0.041556 * Z,
+        0.055648 * X - 0.204043 * Y + 1.057311 * Z,
+    ])
+    return np.maximum(rgb, 0.0).astype(np.float32)
+
+
+def d65_rgb() -> np.ndarray:
+    """Spectrum::getD65() in an RGB build is Spectrum(1.0f) (spectrum.cpp:163)."""
+    return np.ones(3, dtype=np.float32)
+
+
+# --------------------------------------------------------------------------- transforms
+
+def _translate(x, y, z):
+    m = np.eye(4); m[:3, 3] = (x, y, z); return m
+
+
+def _scale(x, y, z):
+    return np.diag([x, y, z, 1.0])
+
+
+def _rotate(axis, angle_deg):
+    """Transform::rotate(axis, angle) (src/libcore/transform.cpp) -- Rodrigues."""
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    s, c = math.sin(math.radians(angle_deg)), math.cos(math.radians(angle_deg))
+    x, y, z = a
+    m = np.eye(4)
+    m[0, 0] = x * x + (1 - x * x) * c; m[0, 1] = x * y * (1 - c) - z * s; m[0, 2] = x * z * (1 - c) + y * s
+    m[1, 0] = x * y * (1 - c) + z * s; m[1, 1] = y * y + (1 - y * y) * c; m[1, 2] = y * z * (1 - c) - x * s
+    m[2, 0] = x * z * (1 - c) - y * s; m[2, 1] = y * z * (1 - c) + x * s; m[2, 2] = z * z + (1 - z * z) * c
+    return m
+
+
+def _look_at(origin, target, up):
+    o = np.asarray(origin, dtype=np.float64); t = np.asarray(target, dtype=np.float64); u = np.asarray(up, dtype=np.float64)
+    d = t - o; d /= np.linalg.norm(d)
+    left = np.cross(u, d); left /= np.linalg.norm(left)
+    new_up = np.cross(d, left)
+    m = np.eye(4)
+    m[:3, 0] = left; m[:3, 1] = new_up; m[:3, 2] = d; m[:3, 3] = o
+    return m
+
+
+def _floats(s):
+    return [float(t) for t in re.split(r"[,\s]+", s.strip()) if t]
+
+
+def _parse_transform(node) -> np.ndarray:
+    m = np.eye(4)
+    for ch in node:
+        a = ch.attrib
+        if ch.tag == "translate":
+            t = _translate(float(a.get("x", 0)), float(a.get("y", 0)), float(a.get("z", 0)))
+        elif ch.tag == "rotate":
+            t = _rotate((float(a.get("x", 0)), float(a.get("y", 0)), float(a.get("z", 0))), float(a["angle"]))
+        elif ch.tag == "scale":
+            if "value" in a:
+                v = float(a["value"]); t = _scale(v, v, v)
+            else:
+                t = _scale(float(a.get("x", 1)), float(a.get("y", 1)), float(a.get("z", 1)))
+        elif ch.tag in ("lookAt", "lookat"):
+            up = _floats(a["up"]) if a.get("up") else [0, 1, 0]
+            t = _look_at(_floats(a["origin"]), _floats(a["target"]), up)
+        elif ch.tag == "matrix":
+            t = np.asarray(_floats(a["value"]), dtype=np.float64).reshape(4, 4)
+        else:
+            raise ValueError(f"unsupported transform element <{ch.tag}>")
+        m = t @ m
+    return m
+
+
+# --------------------------------------------------------------------------- meshes
+
+def _load_obj(path, to_world, face_normals=False, flip_normals=False):
+    """WavefrontOBJ -> one merged triangle mesh (the bundled OBJs hold one object each)."""
+    verts, norms, uvs, tris = [], [], [], []
+    with open(path, "r", errors="replace") as f:
+        for line in f:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == "v":
+                verts.append([float(tok[1]), float(tok[2]), float(tok[3])])
+            elif tok[0] == "vn":
+                norms.append([float(tok[1]), float(tok[2]), float(tok[3])])
+            elif tok[0] == "vt":
+                uvs.append([float(tok[1]), float(tok[2])])
+            elif tok[0] == "f":
+                corners = []
+                for s in tok[1:]:
+                    parts = s.split("/")
+                    p = int(parts[0]); uv = 0; n = 0
+                    if len(parts) == 2:
+                        uv = int(parts[1]) if parts[1] else 0
+                    elif len(parts) == 3:
+                        uv = int(parts[1]) if parts[1] else 0
+                        n = int(parts[2]) if parts[2] else 0
+                    corners.append((p, uv, n))
+                for i in range(1, len(corners) - 1):  # fan, like obj.cpp:313-324
+                    tris.append((corners[0], corners[i], corners[i + 1]))
+    verts = np.asarray(verts, dtype=np.float64).reshape(-1, 3)
+    norms = np.asarray(norms, dtype=np.float64).reshape(-1, 3)
+    uvs = np.asarray(uvs, dtype=np.float64).reshape(-1, 2)
+    M = to_world
+    # normals transform with the inverse transpose
+    Mn = np.linalg.inv(M[:3, :3]).T
+    key_to_idx = {}
+    P, N, UV, I = [], [], [], []
+    has_n = has_uv = False
+    for tri in tris:
+        idx = []
+        for (p, uv, n) in tri:
+            if p < 0: p += len(verts) + 1
+            if n < 0: n += len(norms) + 1
+            if uv < 0: uv += len(uvs) + 1
+            pw = (M[:3, :3] @ verts[p - 1] + M[:3, 3]).astype(np.float32)
+            if n != 0:
+                nw = Mn @ norms[n - 1]
+                l = np.linalg.norm(nw)
+                if l > 0: nw = nw / l
+                nw = nw.astype(np.float32); has_n = True
+            else:
+                nw = np.zeros(3, np.float32)
+            if uv != 0:
+                t = uvs[uv - 1].astype(np.float32).copy(); t[1] = 1 - t[1]  # flipTexCoords default true
+                has_uv = True
+            else:
+                t = np.zeros(2, np.float32)
+            key = (pw.tobytes(), nw.tobytes(), t.tobytes())
+            k = key_to_idx.get(key)
+            if k is None:
+                k = len(P); key_to_idx[key] = k
+                P.append(pw); N.append(nw); UV.append(t)
+            idx.append(k)
+        I.append(idx)
+    P = np.asarray(P, np.float32).reshape(-1, 3); N = np.asarray(N, np.float32).reshape(-1, 3)
+    UV = np.asarray(UV, np.float32).reshape(-1, 2); I = np.asarray(I, np.uint32).reshape(-1, 3)
+    if face_normals:
+        if flip_normals:
+            I = I[:, [1, 0, 2]]
+        return P, None, (UV if has_uv else None), I
+    if has_n:
+        if flip_normals: N = -N
+    else:
+        N = _smooth_normals(P, I)
+        if flip_normals: N = -N
+    return P, N, (UV if has_uv else None), I
+
+
+def _smooth_normals(P, I):
+    """Angle-weighted vertex normals (Thuermer & Wuethrich), trimesh.cpp:636-690."""
+    N = np.zeros((len(P), 3), np.float64)
+    Pd = P.astype(np.float64)
+    for tri in I:
+        for i in range(3):
+            v0, v1, v2 = Pd[tri[i]], Pd[tri[(i + 1) % 3]], Pd[tri[(i + 2) % 3]]
+            a, b = v1 - v0, v2 - v0
+            if i == 0:
+                n = np.cross(a, b); l = np.linalg.norm(n)
+                if l == 0:
+                    break
+                n = n / l
+            la, lb = np.linalg.norm(a), np.linalg.norm(b)
+            if la == 0 or lb == 0:
+                continue
+            ang = math.acos(max(-1.0, min(1.0, float(np.dot(a, b) / (la * lb)))))
+            N[tri[i]] += n * ang
+    l = np.linalg.norm(N, axis=1, keepdims=True)
+    N = np.where(l > 0, N / np.maximum(l, 1e-300), np.array([1.0, 0.0, 0.0]))
+    return N.astype(np.float32)
+
+
+def _rectangle(to_world):
+    """shapes/rectangle.cpp:125-148: unit square [-1,1]^2 in the xy-plane, normal +z."""
+    p = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float64)
+    P = (p @ to_world[:3, :3].T + to_world[:3, 3]).astype(np.float32)
+    n = np.linalg.inv(to_world[:3, :3]).T @ np.array([0, 0, 1.0]); n /= np.linalg.norm(n)
+    N = np.tile(n.astype(np.float32), (4, 1))
+    UV = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    I = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    return P, N, UV, I
+
+
+# --------------------------------------------------------------------------- scene
+
+@dataclass
+class SceneDesc:
+    positions: np.ndarray      # (V,3) f32
+    normals: np.ndarray        # (V,3) f32
+    uvs: np.ndarray            # (V,2) f32
+    indices: np.ndarray        # (T,3) u32
+    triangle_shape: np.ndarray  # (T,) u32
+    shapes: np.ndarray         # (S,8) u32/i32: first_tri, n_tris, bsdf, emitter, has_normals, has_uvs, 0, 0
+    bsdfs: np.ndarray          # (B,16) f32 view of ppg_bsdf (type/flags bit-cast)
+    area_radiance: np.ndarray  # (E,3) f32
+    cam_to_world: np.ndarray   # (4,4) f32
+    x_fov_deg: float
+    near_clip: float
+    far_clip: float
+    film_width: int
+    film_height: int
+    aabb_min: np.ndarray
+    aabb_max: np.ndarray
+    integrator: dict = field(default_factory=dict)  # XML name -> string value
+    bsdf_names: list = field(default_factory=list)
+
+    def with_film(self, w: int, h: int) -> "SceneDesc":
+        """Same scene, different film size (x fov re-resolved only when the aspect
+        changes the 'smaller' axis -- callers keep aspect)."""
+        import copy
+        s = copy.copy(self); s.film_width = int(w); s.film_height = int(h); return s
+
+    def save(self, path):
+        np.savez_compressed(
+            path, positions=self.positions, normals=self.normals, uvs=self.uvs, indices=self.indices,
+            triangle_shape=self.triangle_shape, shapes=self.shapes, bsdfs=self.bsdfs,
+            area_radiance=self.area_radiance, cam_to_world=self.cam_to_world,
+            cam=np.array([self.x_fov_deg, self.near_clip, self.far_clip, self.film_width, self.film_height], np.float64),
+            aabb=np.stack([self.aabb_min, self.aabb_max]).astype(np.float32),
+            integrator=np.array([f"{k}={v}" for k, v in self.integrator.items()]),
+            bsdf_names=np.array(self.bsdf_names))
+
+    @staticmethod
+    def load(path) -> "SceneDesc":
+        d = np.load(path, allow_pickle=False)
+        cam = d["cam"]
+        integ = dict(s.split("=", 1) for s in d["integrator"].tolist())
+        return SceneDesc(d["positions"], d["normals"], d["uvs"], d["indices"], d["triangle_shape"], d["shapes"],
+                         d["bsdfs"], d["area_radiance"], d["cam_to_world"], float(cam[0]), float(cam[1]), float(cam[2]),
+                         int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist())
+
+
+def _make_bsdf(type_, flags, refl):
+    b = np.zeros(16, np.float32)
+    b[:2] = np.array([type_, flags], np.uint32).view(np.float32)
+    b[2:5] = refl
+    return b
+
+
+def _prop_children(node):
+    out = {}
+    for ch in node:
+        if "name" in ch.attrib and ch.tag in ("string", "integer", "float", "boolean"):
+            out[ch.attrib["name"]] = ch.attrib["value"]
+    return out
+
+
+def _parse_color(node, is_emitter=False):
+    if node.tag == "rgb":
+        return np.asarray(_floats(node.attrib["value"]), np.float32)
+    if node.tag == "srgb":
+        v = np.asarray(_floats(node.attrib["value"]), np.float64)
+        lin = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+        return lin.astype(np.float32)
+    if node.tag == "spectrum":
+        val = node.attrib["value"]
+        if ":" in val:
+            pairs = [t.split(":") for t in re.split(r"[,\s]+", val.strip()) if t]
+            return spectrum_to_rgb([float(p[0]) for p in pairs], [float(p[1]) for p in pairs])
+        toks = _floats(val)
+        if len(toks) == 1:
+            return (d65_rgb() * toks[0]) if is_emitter else np.full(3, toks[0], np.float32)
+        if len(toks) == 3:
+            return np.asarray(toks, np.float32)
+    raise ValueError(f"unsupported colour element <{node.tag}>")
+
+
+def _parse_bsdf(node, bsdf_table, names, by_id):
+    typ = node.attrib["type"]
+    flags = 0
+    inner = node
+    if typ == "twosided":
+        flags |= BSDF_FLAG_TWOSIDED
+        inner = [c for c in node if c.tag == "bsdf"][0]
+        typ = inner.attrib["type"]
+    if typ != "diffuse":
+        raise NotImplementedError(f"BSDF '{typ}' is outside the round-1 hot-path scope (CBOX uses diffuse only)")
+    refl = np.full(3, 0.5, np.float32)  # diffuse.cpp default reflectance
+    for c in inner:
+        if c.attrib.get("name") in ("reflectance", "diffuseReflectance") and c.tag in ("rgb", "srgb", "spectrum"):
+            refl = _parse_color(c)
+    idx = len(bsdf_table)
+    bsdf_table.append(_make_bsdf(BSDF_DIFFUSE, flags, refl))
+    names.append(node.attrib.get("id", f"bsdf{idx}"))
+    if "id" in node.attrib:
+        by_id[node.attrib["id"]] = idx
+    return idx
+
+
+def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
+    root = ET.parse(path).getroot()
+    base = os.path.dirname(os.path.abspath(path))
+    integrator = {}
+    inode = root.find("integrator")
+    if inode is not None:
+        if inode.attrib.get("type") != "guided_path":
+            raise ValueError("only <integrator type=\"guided_path\"> is handled")
+        integrator = _prop_children(inode)
+
+    # sensor
+    snode = root.find("sensor")
+    if snode is None or snode.attrib.get("type") != "perspective":
+        raise NotImplementedError("only the perspective sensor is in scope")
+    sp = _prop_children(snode)
+    cam_to_world = np.eye(4)
+    for t in snode.findall("transform"):
+        if t.attrib.get("name") == "toWorld":
+            cam_to_world = _parse_transform(t)
+    fnode = snode.find("film")
+    fp = _prop_children(fnode) if fnode is not None else {}
+    W, H = int(fp.get("width", 768)), int(fp.get("height", 576))
+    if film_size is not None:
+        W, H = film_size
+    if fnode is not None:
+        rf = fnode.find("rfilter")
+        if rf is not None and rf.attrib.get("type") != "box":
+            raise NotImplementedError("only the box reconstruction filter is in scope (all bundled scenes use it)")
+    aspect = W / H
+    fov = float(sp.get("fov", 0) or 0)
+    if "fov" not in sp:
+        f = sp.get("focalLength", "50mm").rstrip("m")
+        fov_diag = 2 * 180 / math.pi * math.atan(math.sqrt(36 * 36 + 24 * 24) / (2 * float(f)))
+        diagonal = 2 * math.tan(0.5 * math.radians(fov_diag))
+        width = diagonal / math.sqrt(1.0 + 1.0 / (aspect * aspect))
+        xfov = math.degrees(2 * math.atan(width * 0.5))
+    else:
+        axis = sp.get("fovAxis", "x").lower()
+        if axis == "smaller":
+            axis = "y" if aspect > 1 else "x"
+        elif axis == "larger":
+            axis = "x" if aspect > 1 else "y"
+        if axis == "x":
+            xfov = fov
+        elif axis == "y":
+            xfov = math.degrees(2 * math.atan(math.tan(0.5 * math.radians(fov)) * aspect))
+        elif axis == "diagonal":
+            diagonal = 2 * math.tan(0.5 * math.radians(fov))
+            width = diagonal / math.sqrt(1.0 + 1.0 / (aspect * aspect))
+            xfov = math.degrees(2 * math.atan(width * 0.5))
+        else:
+            raise ValueError("The 'fovAxis' parameter must be set to one of 'smaller', 'larger', 'diagonal', 'x', or 'y'!")
+    near = float(sp.get("nearClip", 1e-2)); far = float(sp.get("farClip", 1e4))
+
+    bsdf_table, names, by_id = [], [], {}
+    for b in root.findall("bsdf"):
+        _parse_bsdf(b, bsdf_table, names, by_id)
+
+    P_all, N_all, UV_all, I_all, TS_all, shapes, radiance = [], [], [], [], [], [], []
+    voff = 0; toff = 0
+    black = grey = None
+    for sh in root.findall("shape"):
+        typ = sh.attrib["type"]
+        props = _prop_children(sh)
+        to_world = np.eye(4)
+        for t in sh.findall("transform"):
+            if t.attrib.get("name") == "toWorld":
+                to_world = _parse_transform(t)
+        if typ == "obj":
+            P, N, UV, I = _load_obj(os.path.join(base, props["filename"]), to_world,
+                                    props.get("faceNormals", "false") == "true", props.get("flipNormals", "false") == "true")
+        elif typ == "rectangle":
+            P, N, UV, I = _rectangle(to_world)
+        else:
+            raise NotImplementedError(f"shape '{typ}' is outside the round-1 scope")
+        bsdf_idx = None
+        ref = sh.find("ref")
+        if ref is not None:
+            bsdf_idx = by_id[ref.attrib["id"]]
+        bn = sh.find("bsdf")
+        if bn is not None:
+            bsdf_idx = _parse_bsdf(bn, bsdf_table, names, by_id)
+        em = sh.find("emitter")
+        em_idx = -1
+        if em is not None:
+            if em.attrib.get("type") != "area":
+                raise NotImplementedError("only area emitters on shapes")
+            rad = np.ones(3, np.float32)
+            for c in em:
+                if c.attrib.get("name") == "radiance":
+                    rad = _parse_color(c, is_emitter=True)
+            em_idx = len(radiance); radiance.append(rad)
+        if bsdf_idx is None:
+            if em_idx >= 0:
+                if black is None:
+                    black = len(bsdf_table); bsdf_table.append(_make_bsdf(BSDF_DIFFUSE, 0, np.zeros(3, np.float32))); names.append("__black")
+                bsdf_idx = black
+            else:
+                if grey is None:
+                    grey = len(bsdf_table); bsdf_table.append(_make_bsdf(BSDF_DIFFUSE, 0, np.full(3, 0.5, np.float32))); names.append("__grey")
+                bsdf_idx = grey
+        shapes.append([toff, len(I), bsdf_idx, em_idx, 0 if N is None else 1, 0 if UV is None else 1, 0, 0])
+        P_all.append(P)
+        N_all.append(N if N is not None else np.zeros_like(P))
+        UV_all.append(UV if UV is not None else np.zeros((len(P), 2), np.float32))
+        I_all.append(I + voff)
+        TS_all.append(np.full(len(I), len(shapes) - 1, np.uint32))
+        voff += len(P); toff += len(I)
+
+    P = np.concatenate(P_all).astype(np.float32)
+    aabb_min = P.min(axis=0).astype(np.float64); aabb_max = P.max(axis=0).astype(np.float64)
+    cam_pos = cam_to_world[:3, 3]
+    aabb_min = np.minimum(aabb_min, cam_pos); aabb_max = np.maximum(aabb_max, cam_pos)
+    return SceneDesc(
+        positions=P, normals=np.concatenate(N_all).astype(np.float32), uvs=np.concatenate(UV_all).astype(np.float32),
+        indices=np.concatenate(I_all).astype(np.uint32), triangle_shape=np.concatenate(TS_all).astype(np.uint32),
+        shapes=np.asarray(shapes, np.int64).astype(np.int32), bsdfs=np.asarray(bsdf_table, np.float32).reshape(-1, 16),
+        area_radiance=np.asarray(radiance, np.float32).reshape(-1, 3), cam_to_world=cam_to_world.astype(np.float32),
+        x_fov_deg=float(xfov), near_clip=near, far_clip=far, film_width=W, film_height=H,
+        aabb_min=aabb_min.astype(np.float32), aabb_max=aabb_max.astype(np.float32), integrator=integrator, bsdf_names=names)

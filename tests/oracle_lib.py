@@ -1,0 +1,238 @@
+"""Test-side ctypes wrapper of the CPU oracle (oracle/libppg_oracle.so and, when it was
+built, oracle/_ref/libppg_oracle_ref.so = same tracer on the reference's verbatim SD-tree).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from ppg_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PORT_SO = os.path.join(ROOT, "oracle", "libppg_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libppg_oracle_ref.so")
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+
+
+def _declare(lib):
+    H = C.c_void_p
+    f32p = C.POINTER(C.c_float); u32p = C.POINTER(C.c_uint32); u8p = C.POINTER(C.c_uint8); u16p = C.POINTER(C.c_uint16)
+    i32p = C.POINTER(C.c_int32); u64p = C.POINTER(C.c_uint64)
+    lib.ppgo_create.restype = H
+    lib.ppgo_create.argtypes = [C.POINTER(capi.PpgParams), C.POINTER(capi.PpgSceneDesc), f32p, f32p, C.c_int]
+    lib.ppgo_destroy.argtypes = [H]; lib.ppgo_destroy.restype = None
+    lib.ppgo_render.argtypes = [H, f32p, C.POINTER(capi.PpgStats)]
+    lib.ppgo_set_capture.argtypes = [H, f32p, i32p]
+    lib.ppgo_step_reset.argtypes = [H, C.c_int]
+    lib.ppgo_step_passes.argtypes = [H, C.c_int, C.c_int, f32p]
+    lib.ppgo_step_build.argtypes = [H, C.POINTER(capi.PpgIterationStats)]
+    lib.ppgo_get_moment_images.argtypes = [H, f32p, f32p]
+    lib.ppgo_tree_refine.argtypes = [H, C.c_uint64, C.c_int]
+    lib.ppgo_tree_reset.argtypes = [H, C.c_int, C.c_float]
+    lib.ppgo_tree_build.argtypes = [H]
+    lib.ppgo_tree_record.argtypes = [H, C.c_size_t, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, u8p, f32p, C.c_int, C.c_int, C.c_int]
+    lib.ppgo_tree_lookup.argtypes = [H, C.c_size_t, f32p, u32p, f32p]
+    lib.ppgo_tree_pdf.argtypes = [H, C.c_size_t, u32p, f32p, f32p]
+    lib.ppgo_tree_sample.argtypes = [H, C.c_size_t, u32p, f32p, C.c_size_t, f32p]
+    lib.ppgo_tree_fraction.argtypes = [H, C.c_size_t, u32p, f32p]
+    lib.ppgo_tree_counts.argtypes = [H, u64p]
+    lib.ppgo_tree_export.argtypes = [H, C.c_int, u32p, i32p, u8p, u64p, u32p, f32p, f32p, i32p, f32p, u16p, f32p, f32p]
+    return lib
+
+
+_libs = {}
+
+
+def load(kind="port"):
+    if kind not in _libs:
+        path = PORT_SO if kind == "port" else REF_SO
+        if not os.path.exists(path):
+            if kind == "port":
+                build()
+            else:
+                raise FileNotFoundError(path)
+        _libs[kind] = _declare(C.CDLL(path))
+    return _libs[kind]
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def default_params(**kw):
+    """Reference defaults (GP:1014-1085, integrator.cpp:190-225), restated on the test side."""
+    p = capi.PpgParams()
+    p.nee = 0; p.sample_combination = 1; p.spatial_filter = 0; p.directional_filter = 0; p.bsdf_sampling_fraction_loss = 0
+    p.sd_tree_max_memory = -1; p.s_tree_threshold = 12000; p.d_tree_threshold = 0.01; p.bsdf_sampling_fraction = 0.5
+    p.spp_per_pass = 4; p.budget_type = 1; p.budget = 300.0; p.dump_sd_tree = 0
+    p.max_depth = -1; p.rr_depth = 5; p.strict_normals = 0; p.hide_emitters = 0; p.seed = 1234
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+_ENUMS = {
+    "nee": {"never": 0, "kickstart": 1, "always": 2},
+    "sampleCombination": {"discard": 0, "automatic": 1, "inversevar": 2},
+    "spatialFilter": {"nearest": 0, "stochastic": 1, "box": 2},
+    "directionalFilter": {"nearest": 0, "box": 1},
+    "bsdfSamplingFractionLoss": {"none": 0, "kl": 1, "var": 2},
+    "budgetType": {"spp": 0, "seconds": 1},
+}
+_FIELDS = {
+    "nee": "nee", "sampleCombination": "sample_combination", "spatialFilter": "spatial_filter",
+    "directionalFilter": "directional_filter", "bsdfSamplingFractionLoss": "bsdf_sampling_fraction_loss",
+    "sdTreeMaxMemory": "sd_tree_max_memory", "sTreeThreshold": "s_tree_threshold", "dTreeThreshold": "d_tree_threshold",
+    "bsdfSamplingFraction": "bsdf_sampling_fraction", "sppPerPass": "spp_per_pass", "budgetType": "budget_type",
+    "budget": "budget", "dumpSDTree": "dump_sd_tree", "maxDepth": "max_depth", "rrDepth": "rr_depth",
+    "strictNormals": "strict_normals", "hideEmitters": "hide_emitters", "seed": "seed",
+}
+
+
+def params_from_xml(props: dict, **override):
+    """XML (name -> string) to ppg_params, on the test side (the product does this in C: ppg_params_set)."""
+    p = default_params()
+    allp = dict(props); allp.update({k: str(v) for k, v in override.items()})
+    for k, v in allp.items():
+        f = _FIELDS[k]
+        if k in _ENUMS:
+            setattr(p, f, _ENUMS[k][v])
+        elif v in ("true", "false"):
+            setattr(p, f, 1 if v == "true" else 0)
+        elif f in ("d_tree_threshold", "bsdf_sampling_fraction", "budget"):
+            setattr(p, f, float(v))
+        else:
+            setattr(p, f, int(float(v)))
+    return p
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Oracle:
+    def __init__(self, params, scene=None, aabb=None, nthreads=0, kind="port"):
+        self.lib = load(kind)
+        self.kind = kind
+        self.scene_arrays = capi.SceneArrays(scene) if scene is not None else None
+        self.params = params
+        if scene is not None:
+            self.W, self.H = scene.film_width, scene.film_height
+            self.h = self.lib.ppgo_create(C.byref(params), C.byref(self.scene_arrays.desc), None, None, nthreads)
+        else:
+            mn = np.asarray(aabb[0], np.float32); mx = np.asarray(aabb[1], np.float32)
+            self.h = self.lib.ppgo_create(C.byref(params), None, fptr(mn), fptr(mx), nthreads)
+
+    def close(self):
+        if self.h:
+            self.lib.ppgo_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, capture=False):
+        img = np.zeros((self.H, self.W, 3), np.float32)
+        st = capi.PpgStats()
+        cap = None
+        if capture:
+            n = self.W * self.H * self.params.spp_per_pass
+            self._capli = np.zeros((n, 3), np.float32); self._capd = np.zeros(n, np.int32)
+            self.lib.ppgo_set_capture(self.h, fptr(self._capli), self._capd.ctypes.data_as(C.POINTER(C.c_int32)))
+            cap = (self._capli, self._capd)
+        rc = self.lib.ppgo_render(self.h, fptr(img), C.byref(st))
+        assert rc == 0, rc
+        return (img, st.as_dict(), cap) if capture else (img, st.as_dict())
+
+    # ---- step-wise
+    def set_capture(self):
+        n = self.W * self.H * self.params.spp_per_pass
+        self._capli = np.zeros((n, 3), np.float32); self._capd = np.zeros(n, np.int32)
+        self.lib.ppgo_set_capture(self.h, fptr(self._capli), self._capd.ctypes.data_as(C.POINTER(C.c_int32)))
+        return self._capli, self._capd
+
+    def step_reset(self, it):
+        assert self.lib.ppgo_step_reset(self.h, it) == 0
+
+    def step_passes(self, n, is_final=False):
+        v = C.c_float(0)
+        assert self.lib.ppgo_step_passes(self.h, n, int(is_final), C.byref(v)) == 0
+        return v.value
+
+    def step_build(self):
+        st = capi.PpgIterationStats()
+        assert self.lib.ppgo_step_build(self.h, C.byref(st)) == 0
+        return st.as_dict()
+
+    def moment_images(self):
+        a = np.zeros((self.H, self.W, 4), np.float32); b = np.zeros_like(a)
+        self.lib.ppgo_get_moment_images(self.h, fptr(a), fptr(b))
+        return a, b
+
+    # ---- tree level
+    def refine(self, threshold, max_mb=-1):
+        self.lib.ppgo_tree_refine(self.h, int(threshold), max_mb)
+
+    def reset(self, max_depth=20, threshold=0.01):
+        self.lib.ppgo_tree_reset(self.h, max_depth, threshold)
+
+    def build(self):
+        self.lib.ppgo_tree_build(self.h)
+
+    def record(self, o, d, radiance, wo_pdf, product=None, bsdf_pdf=None, dtree_pdf=None, weight=None, is_delta=None, rnd=None,
+               sfilter=0, dfilter=0, loss=0):
+        n = len(radiance)
+        c = lambda a: None if a is None else fptr(np.ascontiguousarray(a, np.float32))
+        keep = [np.ascontiguousarray(x, np.float32) if x is not None else None for x in (o, d, radiance, product, wo_pdf, bsdf_pdf, dtree_pdf, weight, rnd)]
+        ptrs = [None if k is None else fptr(k) for k in keep]
+        dl = None
+        if is_delta is not None:
+            dl = np.ascontiguousarray(is_delta, np.uint8)
+        self.lib.ppgo_tree_record(self.h, n, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6], ptrs[7],
+                                  None if dl is None else dl.ctypes.data_as(C.POINTER(C.c_uint8)), ptrs[8], sfilter, dfilter, loss)
+
+    def lookup(self, p):
+        p = np.ascontiguousarray(p, np.float32); n = len(p)
+        leaf = np.zeros(n, np.uint32); size = np.zeros((n, 3), np.float32)
+        self.lib.ppgo_tree_lookup(self.h, n, fptr(p), leaf.ctypes.data_as(C.POINTER(C.c_uint32)), fptr(size))
+        return leaf, size
+
+    def pdf(self, leaf, d):
+        leaf = np.ascontiguousarray(leaf, np.uint32); d = np.ascontiguousarray(d, np.float32)
+        out = np.zeros(len(leaf), np.float32)
+        self.lib.ppgo_tree_pdf(self.h, len(leaf), leaf.ctypes.data_as(C.POINTER(C.c_uint32)), fptr(d), fptr(out))
+        return out
+
+    def sample(self, leaf, rnd):
+        leaf = np.ascontiguousarray(leaf, np.uint32); rnd = np.ascontiguousarray(rnd, np.float32)
+        out = np.zeros((len(leaf), 3), np.float32)
+        self.lib.ppgo_tree_sample(self.h, len(leaf), leaf.ctypes.data_as(C.POINTER(C.c_uint32)), fptr(rnd), rnd.shape[1], fptr(out))
+        return out
+
+    def fraction(self, leaf):
+        leaf = np.ascontiguousarray(leaf, np.uint32); out = np.zeros(len(leaf), np.float32)
+        self.lib.ppgo_tree_fraction(self.h, len(leaf), leaf.ctypes.data_as(C.POINTER(C.c_uint32)), fptr(out))
+        return out
+
+    def export(self, which=0):
+        cnt = (C.c_uint64 * 4)()
+        self.lib.ppgo_tree_counts(self.h, cnt)
+        N, nq = int(cnt[0]), int(cnt[2 + which])
+        e = dict(
+            s_children=np.zeros((N, 2), np.uint32), s_axis=np.zeros(N, np.int32), s_is_leaf=np.zeros(N, np.uint8),
+            tree_first=np.zeros(N, np.uint64), tree_count=np.zeros(N, np.uint32), tree_sum=np.zeros(N, np.float32),
+            tree_weight=np.zeros(N, np.float32), tree_depth=np.zeros(N, np.int32), sums=np.zeros((nq, 4), np.float32),
+            children=np.zeros((nq, 4), np.uint16), adam=np.zeros((N, 6), np.float32), aabb=np.zeros((2, 3), np.float32))
+        P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        self.lib.ppgo_tree_export(self.h, which, P(e["s_children"], C.c_uint32), P(e["s_axis"], C.c_int32), P(e["s_is_leaf"], C.c_uint8),
+                                  P(e["tree_first"], C.c_uint64), P(e["tree_count"], C.c_uint32), P(e["tree_sum"], C.c_float),
+                                  P(e["tree_weight"], C.c_float), P(e["tree_depth"], C.c_int32), P(e["sums"], C.c_float),
+                                  P(e["children"], C.c_uint16), P(e["adam"], C.c_float), P(e["aabb"], C.c_float))
+        e["n_leaves"] = int(cnt[1])
+        return e

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Regenerate the data fixtures that must travel to the GPU box (where
+/root/reference does not exist).  Run in the build container:
+
+    python tools/make_fixtures.py
+
+Writes
+  practical-path-guiding_b200/ppg_b200/data/cie1931.npz  CIE 1931 observer + D65 tables (standard colorimetric data)
+  scenes/cbox.npz            flat-array form of /root/reference/scenes/cbox/cbox.xml (our loader's output)
+  scenes/cbox-improved.npz   same for cbox-improved.xml
+  tests/golden/cbox_log_stats.json   known-answer statistics parsed from the logs embedded
+                                      in the reference's golden EXRs (hdrfilm attachLog)
+"""
+import json, os, re, struct, sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "practical-path-guiding_b200"))
+from ppg_b200 import scene as S  # noqa: E402
+
+REF = "/root/reference"
+
+
+def exr_attr(fn, want):
+    b = open(fn, "rb").read()
+    assert b[:4] == b"\x76\x2f\x31\x01"
+    p = 8
+    while b[p] != 0:
+        e = b.index(b"\0", p); name = b[p:e].decode(); p = e + 1
+        e = b.index(b"\0", p); p = e + 1
+        sz = struct.unpack("<i", b[p:p + 4])[0]; p += 4
+        if name == want:
+            return b[p:p + sz]
+        p += sz
+    return None
+
+
+def parse_log(log):
+    its = []
+    cur = None
+    triple = lambda s: [float(x) for x in re.findall(r"[-+0-9.einf]+", s.split("=")[1])]
+    for l in log.splitlines():
+        m = re.search(r"ITERATION (\d+), (\d+) passes", l)
+        if m:
+            cur = {"iteration": int(m.group(1)), "passes": int(m.group(2))}; its.append(cur); continue
+        m = re.search(r"([0-9.]+) seconds, Total passes: (\d+), Var: ([-0-9.einf]+)", l)
+        if m and cur is not None:
+            cur.update(seconds=float(m.group(1)), total_passes=int(m.group(2)), var=float(m.group(3)))
+        if cur is None:
+            continue
+        if "Depth  " in l: cur["depth"] = triple(l)
+        if "Mean radiance" in l: cur["mean_radiance"] = triple(l)
+        if "Node count" in l: cur["node_count"] = triple(l)
+        if "Stat. weight" in l: cur["stat_weight"] = triple(l)
+        m = re.search(r"FINAL (\d+) passes", l)
+        if m: cur["final_passes"] = int(m.group(1))
+    m = re.search(r"Render time: ([0-9.]+)s", log)
+    m2 = re.search(r"\((\d+)x(\d+), (\d+) cores", log)
+    return {"iterations": its, "render_time_s": float(m.group(1)) if m else None,
+            "width": int(m2.group(1)), "height": int(m2.group(2)), "cores": int(m2.group(3))}
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "scenes"), exist_ok=True)
+    cie = S.extract_cie_tables()
+    assert len(cie["x"]) == 471
+    np.savez_compressed(S._CIE_NPZ, **cie)
+    S._cie_cache = None
+    for name in ("cbox", "cbox-improved"):
+        sc = S.load_mitsuba_xml(f"{REF}/scenes/cbox/{name}.xml")
+        sc.save(os.path.join(ROOT, "scenes", f"{name}.npz"))
+        print(name, "tris", len(sc.indices), "verts", len(sc.positions), "bsdfs", sc.bsdf_names, sc.integrator)
+        print("  aabb", sc.aabb_min, sc.aabb_max, "xfov", sc.x_fov_deg)
+        print("  refl", sc.bsdfs[:, 2:5], "radiance", sc.area_radiance)
+    stats = {}
+    for name in ("cbox", "cbox-improved"):
+        log = exr_attr(f"{REF}/scenes/cbox/{name}.exr", "log").decode(errors="replace")
+        stats[name] = parse_log(log)
+    with open(os.path.join(ROOT, "tests", "golden", "cbox_log_stats.json"), "w") as f:
+        json.dump(stats, f, indent=1)
+    print(json.dumps(stats["cbox"]["iterations"][:2], indent=1))
+
+
+if __name__ == "__main__":
+    main()
