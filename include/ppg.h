@@ -156,6 +156,17 @@ typedef struct ppg_scene_desc {
 /* ---- per-iteration statistics (the reference's log lines, GP:1176-1186, 1323-1326) --- */
 
 #define PPG_MAX_ITERATIONS 40
+#define PPG_KERNEL_CLASSES 8
+typedef enum ppg_kernel_class {
+    PPG_K_BOUNCE = 0,   /* ray generation + intersect + shade + guide + compaction, one launch per path depth */
+    PPG_K_COMMIT = 1,   /* vertex records -> building trees (splat) */
+    PPG_K_FILM = 2,     /* film / variance / develop */
+    PPG_K_REFINE = 3,   /* S-tree refine */
+    PPG_K_RESET = 4,    /* D-tree reset (count, scan, fill) */
+    PPG_K_BUILD = 5,    /* D-tree build */
+    PPG_K_ADAM = 6,
+    PPG_K_OTHER = 7
+} ppg_kernel_class;
 
 typedef struct ppg_iteration_stats {
     int32_t  iteration;            /* k */
@@ -186,6 +197,10 @@ typedef struct ppg_stats {
     double   device_seconds;       /* CUDA-event time of all kernels */
     double   final_variance;
     uint64_t kernel_launches;
+    /* CUDA-event time per kernel class, measured on the launching stream (index: ppg_kernel_class) */
+    double   kernel_ms[PPG_KERNEL_CLASSES];
+    uint64_t kernel_count[PPG_KERNEL_CLASSES];
+    double   render_device_ms;     /* CUDA-event time of the whole render on the library's stream */
     ppg_iteration_stats iterations[PPG_MAX_ITERATIONS];
 } ppg_stats;
 

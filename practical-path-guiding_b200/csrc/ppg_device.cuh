@@ -1,0 +1,441 @@
+// ppg_device.cuh -- device-side building blocks of the B200 guided path tracer.
+//
+// Everything here is net-new sm_100a code; the *behaviour* follows the reference
+// integrator mitsuba/src/integrators/path/guided_path.cpp ("GP") and the Mitsuba
+// services it calls -- each function cites the lines it has to agree with.
+// No tensor cores on this path (no dense contraction anywhere); the work is
+// gather/scatter + fp32 ALU, so the rules that matter are coalesced float4 state
+// traffic, shared-memory staging of the hot read-only data, and warp-aggregated atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ppg {
+
+#define PPG_PI 3.14159265358979323846f            // M_PI, single-precision build (core/constants.h:63,80)
+#define PPG_INV_PI 0.31830988618379067154f
+#define PPG_EPSILON 1e-4f                          // core/constants.h:28
+
+// ------------------------------------------------------------------ float3 helpers
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float3 normalize(float3 a) { return a * (1.0f / sqrtf(dot(a, a))); }   // TVector3::operator/ multiplies by the reciprocal
+__device__ __forceinline__ bool is_zero(float3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+__device__ __forceinline__ bool is_valid(float3 a) {   // Spectrum::isValid: finite and non-negative
+    return isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && a.x >= 0.f && a.y >= 0.f && a.z >= 0.f;
+}
+__device__ __forceinline__ float max3(float3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
+__device__ __forceinline__ float comp(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// ------------------------------------------------------------------ PCG32 path sampler
+// One stream per path, keyed by (seed, global sample index); numbers are consumed in the
+// reference's order.  Must match oracle/ppg_cpu_tracer.h bit for bit.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+struct Pcg32 {
+    uint64_t state, inc;
+    __device__ __forceinline__ uint32_t nextU32() {
+        const uint64_t old = state;
+        state = old * 6364136223846793005ull + inc;
+        const uint32_t xs = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+        const uint32_t rot = (uint32_t) (old >> 59u);
+        return __funnelshift_r(xs, xs, rot);
+    }
+    __device__ __forceinline__ float next1D() { return (float) (nextU32() >> 8) * (1.0f / 16777216.0f); }
+    __device__ __forceinline__ void seed(uint64_t initstate, uint64_t initseq) {
+        state = 0; inc = (initseq << 1) | 1u;
+        nextU32(); state += initstate; nextU32();
+    }
+};
+__device__ __forceinline__ void seed_path_rng(Pcg32 &r, uint64_t seed, uint64_t sampleIndex) {
+    r.seed(splitmix64(seed ^ splitmix64(sampleIndex)), sampleIndex);
+}
+__device__ __forceinline__ void seed_vertex_rng(Pcg32 &r, uint64_t seed, uint64_t sampleIndex, uint32_t ordinal) {
+    r.seed(splitmix64((seed + 0x5851F42D4C957F2Dull) ^ splitmix64(sampleIndex * 64 + ordinal)), sampleIndex * 64 + ordinal);
+}
+
+// ------------------------------------------------------------------ scene in HBM / shared memory
+// Triangles are stored in BVH-leaf order.  Per triangle:
+//   accel[3t+0] = {n_u, n_v, n_d, bits(k)}            Wald projection test constants
+//   accel[3t+1] = {a_u, a_v, b_nu, b_nv}              (restated from render/triaccel.h:60-158)
+//   accel[3t+2] = {c_nu, c_nv, bits(origPrim), bits(meta index == t)}
+//   geom[6t+0..2] = {p_i.xyz, n_i.x}, geom[6t+3..5] = {n_i.yz, uv_i}   (i = 0,1,2)
+//   meta[t] = {bsdf, emitter (-1 none), flags (bit0 has_normals), shape}
+// BVH node: 2 x float4 = {bmin.xyz, bits(left)}, {bmax.xyz, bits(count)}; count>0 -> leaf [left, left+count)
+struct SceneView {
+    const float4 *accel;
+    const float4 *geom;
+    const int4 *meta;
+    const float4 *bvh;
+    const float4 *bsdf;       // 2 per material: {refl.rgb, bits(type | flags<<8)}, {reserved}
+    const float4 *radiance;   // per emitter: rgb
+    uint32_t nTris, nBvhNodes, nBsdfs, nEmitters;
+};
+struct Camera {             // src/sensors/perspective.cpp:271-298 for a lookAt camera
+    float3 o, left, up, dir;
+    float tanX, tanY, nearClip, farClip;
+    int W, H;
+};
+
+struct Hit { float t, u, v; uint32_t tri; uint32_t prim; };
+
+__device__ __forceinline__ bool tri_intersect(const float4 A, const float4 B, const float4 C, float3 o, float3 d, float mint, float maxt,
+                                              float &u, float &v, float &t) {
+    const int k = __float_as_int(A.w);
+    float o_u, o_v, o_k, d_u, d_v, d_k;
+    if (k == 0) { o_u = o.y; o_v = o.z; o_k = o.x; d_u = d.y; d_v = d.z; d_k = d.x; }
+    else if (k == 1) { o_u = o.z; o_v = o.x; o_k = o.y; d_u = d.z; d_v = d.x; d_k = d.y; }
+    else if (k == 2) { o_u = o.x; o_v = o.y; o_k = o.z; d_u = d.x; d_v = d.y; d_k = d.z; }
+    else return false;
+    t = (A.z - o_u * A.x - o_v * A.y - o_k) / (d_u * A.x + d_v * A.y + d_k);
+    if (!(t >= mint && t <= maxt)) return false;
+    const float hu = o_u + t * d_u - B.x;
+    const float hv = o_v + t * d_v - B.y;
+    u = hv * B.z + hu * B.w;
+    v = hu * C.x + hv * C.y;
+    return u >= 0.f && v >= 0.f && u + v <= 1.0f;
+}
+
+// Nearest hit in [mint, maxt]; ties on t go to the lower ORIGINAL triangle index so that the
+// result does not depend on the traversal order (same rule as the oracle).
+__device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, float3 d, float mint, float maxt, Hit &hit) {
+    hit.t = __int_as_float(0x7f800000); hit.prim = 0xFFFFFFFFu; hit.tri = 0;
+    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    uint32_t stack[32]; int sp = 0; uint32_t node = 0;
+    for (;;) {
+        const float4 n0 = sc.bvh[2 * node], n1 = sc.bvh[2 * node + 1];
+        float t0 = mint, t1 = fminf(maxt, hit.t);
+        bool miss = false;
+        {
+            float ta = (n0.x - o.x) * inv.x, tb = (n1.x - o.x) * inv.x; if (ta > tb) { float s = ta; ta = tb; tb = s; }
+            if (ta == ta) t0 = fmaxf(t0, ta - fabsf(ta) * 1e-6f);
+            if (tb == tb) t1 = fminf(t1, tb + fabsf(tb) * 1e-6f);
+            ta = (n0.y - o.y) * inv.y; tb = (n1.y - o.y) * inv.y; if (ta > tb) { float s = ta; ta = tb; tb = s; }
+            if (ta == ta) t0 = fmaxf(t0, ta - fabsf(ta) * 1e-6f);
+            if (tb == tb) t1 = fminf(t1, tb + fabsf(tb) * 1e-6f);
+            ta = (n0.z - o.z) * inv.z; tb = (n1.z - o.z) * inv.z; if (ta > tb) { float s = ta; ta = tb; tb = s; }
+            if (ta == ta) t0 = fmaxf(t0, ta - fabsf(ta) * 1e-6f);
+            if (tb == tb) t1 = fminf(t1, tb + fabsf(tb) * 1e-6f);
+            miss = t0 > t1;
+        }
+        if (!miss) {
+            const uint32_t left = __float_as_uint(n0.w), count = __float_as_uint(n1.w);
+            if (count) {
+                for (uint32_t i = left; i < left + count; ++i) {
+                    const float4 A = sc.accel[3 * i], B = sc.accel[3 * i + 1], C = sc.accel[3 * i + 2];
+                    float u, v, t;
+                    if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
+                        const uint32_t prim = __float_as_uint(C.z);
+                        if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i; }
+                    }
+                }
+            } else {
+                node = left; stack[sp++] = left + 1;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return hit.prim != 0xFFFFFFFFu;
+}
+
+// Intersection record (render/shape.h:36), the fields the path uses
+struct Its {
+    float3 p, geoN, shN, shS, shT, wi;
+    int bsdf, emitter;
+    __device__ __forceinline__ float3 toLocal(float3 v) const { return f3(dot(v, shS), dot(v, shT), dot(v, shN)); }
+    __device__ __forceinline__ float3 toWorld(float3 v) const { return shS * v.x + shT * v.y + shN * v.z; }
+};
+
+// fillIntersectionRecord (render/skdtree.h:343-428) + computeShadingFrame (libcore/util.cpp:603-608)
+__device__ __forceinline__ void fill_its(const SceneView &sc, const Hit &h, float3 d, Its &its) {
+    const float4 g0 = sc.geom[6 * h.tri], g1 = sc.geom[6 * h.tri + 1], g2 = sc.geom[6 * h.tri + 2];
+    const int4 m = sc.meta[h.tri];
+    const float3 p0 = f3(g0.x, g0.y, g0.z), p1 = f3(g1.x, g1.y, g1.z), p2 = f3(g2.x, g2.y, g2.z);
+    const float3 b = f3(1 - h.u - h.v, h.u, h.v);
+    its.p = p0 * b.x + p1 * b.y + p2 * b.z;
+    const float3 side1 = p1 - p0, side2 = p2 - p0;
+    float3 faceN = cross(side1, side2);
+    const float len = sqrtf(dot(faceN, faceN));
+    if (!is_zero(faceN)) faceN = faceN * (1.0f / len);
+    if (m.z & 1) {
+        const float4 h0 = sc.geom[6 * h.tri + 3], h1 = sc.geom[6 * h.tri + 4], h2 = sc.geom[6 * h.tri + 5];
+        const float3 n0 = f3(g0.w, h0.x, h0.y), n1 = f3(g1.w, h1.x, h1.y), n2 = f3(g2.w, h2.x, h2.y);
+        its.shN = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
+        if (dot(faceN, its.shN) < 0.f) faceN = -faceN;
+    } else its.shN = faceN;
+    its.geoN = faceN;
+    const float3 dpdu = side1;
+    its.shS = normalize(dpdu - its.shN * dot(its.shN, dpdu));
+    its.shT = cross(its.shN, its.shS);
+    its.wi = its.toLocal(-d);
+    its.bsdf = m.x; its.emitter = m.y;
+}
+
+// ------------------------------------------------------------------ BSDF: diffuse (+ twosided)
+// src/libcore/warp.cpp:81-102 (concentric disk) then :43-52
+__device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy) {
+    const float r1 = 2.0f * sx - 1.0f, r2 = 2.0f * sy - 1.0f;
+    float phi, r;
+    if (r1 == 0.f && r2 == 0.f) { r = phi = 0.f; }
+    else if (r1 * r1 > r2 * r2) { r = r1; phi = (PPG_PI / 4.0f) * (r2 / r1); }
+    else { r = r2; phi = (PPG_PI / 2.0f) - (r1 / r2) * (PPG_PI / 4.0f); }
+    float s, c; sincosf(phi, &s, &c);
+    const float px = r * c, py = r * s;
+    float z = sqrtf(fmaxf(0.0f, 1.0f - px * px - py * py));
+    if (z == 0.f) z = 1e-10f;
+    return f3(px, py, z);
+}
+#define PPG_BSDF_TWOSIDED 1u
+struct Bsdf { float3 refl; uint32_t type, flags; };
+__device__ __forceinline__ Bsdf load_bsdf(const SceneView &sc, int idx) {
+    const float4 a = sc.bsdf[2 * idx];
+    Bsdf b; b.refl = f3(a.x, a.y, a.z);
+    const uint32_t tf = __float_as_uint(a.w); b.type = tf & 0xffu; b.flags = tf >> 8;
+    return b;
+}
+// eval / pdf / sample per src/bsdfs/diffuse.cpp:110-150, twosided per src/bsdfs/twosided.cpp:108-184
+__device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo) {
+    if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
+    if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
+    return b.refl * (PPG_INV_PI * wo.z);
+}
+__device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
+    if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
+    if (wi.z <= 0.f || wo.z <= 0.f) return 0.0f;
+    return PPG_INV_PI * wo.z;
+}
+__device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf) {
+    bool flip = false;
+    if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; flip = true; }
+    eta = 1.0f; delta = false; pdf = 0.f;
+    if (wi.z <= 0.f) return f3(0, 0, 0);
+    wo = square_to_cosine_hemisphere(sx, sy);
+    pdf = PPG_INV_PI * wo.z;
+    if (flip) wo.z = -wo.z;
+    return b.refl;
+}
+
+// ------------------------------------------------------------------ SD-tree views
+// S-tree node: uint2 {child0, child1}; child0 == 0 marks a leaf (node 0 is the root, never a child; GP:844).
+// Axis cycles x,y,z with depth (root 0, children (axis+1)%3, GP:889), so it is not stored.
+// Per-node leaf record (valid for leaves):
+//   leafA[n] = {bits(samplingBase), bits(buildingBase), theta (Adam variable), bits(flags)}  flags bit0: sampling mean()>0
+// Sampling quadtree node: 32 B = float4 sums + uint2 children (4 x uint16, 0 = leaf; GP:368-370) + pad,
+// read with one 16 B and one 8 B load from the same 32 B sector.
+struct SampNode { float4 sums; uint2 children; uint2 pad; };
+struct TreeView {
+    const uint2 *snodes;
+    const float4 *leafA;
+    const SampNode *samp;         // sampling pool
+    const uint2 *bchildren;       // building pool topology (4 x uint16 per node)
+    float4 *bsums;                // building pool sums (atomics target)
+    float *bweight;               // per S-tree node: building statistical weight (atomics target)
+    float *adamG, *adamW;         // per S-tree node: batch gradient / weight accumulators
+    float3 aabbMin, extent;       // cubified scene box (GP:850-860)
+};
+
+__device__ __forceinline__ uint32_t child16(uint2 c, int i) { return ((i & 2) ? c.y : c.x) >> ((i & 1) * 16) & 0xffffu; }
+__device__ __forceinline__ float sum4(float4 s, int i) { return i == 0 ? s.x : (i == 1 ? s.y : (i == 2 ? s.z : s.w)); }
+
+// STree::dTreeWrapper(p, size) -- GP:897-905 + 761-769 + 747-755.  Returns the leaf node index and the
+// number of levels descended (the voxel size follows from it: size[axis] halves once per level on that axis).
+__device__ __forceinline__ uint32_t stree_lookup(const uint2 *__restrict__ snodes, float3 aabbMin, float3 extent, float3 pw, int &levels) {
+    // p0 is the coordinate of the current split axis; the triple rotates with the axis (no dynamic indexing)
+    float p0 = (pw.x - aabbMin.x) / extent.x, p1 = (pw.y - aabbMin.y) / extent.y, p2 = (pw.z - aabbMin.z) / extent.z;
+    uint32_t n = 0; int depth = 0;
+    for (;;) {
+        const uint2 c = __ldg(&snodes[n]);
+        if (c.x == 0u) break;
+        if (p0 < 0.5f) { p0 *= 2.f; n = c.x; } else { p0 = (p0 - 0.5f) * 2.f; n = c.y; }
+        const float t = p0; p0 = p1; p1 = p2; p2 = t;
+        ++depth;
+    }
+    levels = depth;
+    return n;
+}
+__device__ __forceinline__ float3 voxel_size(float3 extent, int levels) {
+    // size[a] /= 2 once per level whose axis is a (exact powers of two)
+    const int nx = (levels + 2) / 3, ny = (levels + 1) / 3, nz = levels / 3;
+    return f3(ldexpf(extent.x, -nx), ldexpf(extent.y, -ny), ldexpf(extent.z, -nz));
+}
+
+// DTreeWrapper::dirToCanonical -- GP:597-608
+__device__ __forceinline__ float2 dir_to_canonical(float3 d) {
+    if (!isfinite(d.x) || !isfinite(d.y) || !isfinite(d.z)) return make_float2(0.f, 0.f);
+    const float cosTheta = fminf(fmaxf(d.z, -1.0f), 1.0f);
+    float phi = atan2f(d.y, d.x);
+    while (phi < 0.f) phi += 2.0f * PPG_PI;   // == the reference's double add rounded to float (both addends are floats)
+    return make_float2((cosTheta + 1.f) / 2.f, phi / (2.f * PPG_PI));
+}
+// DTreeWrapper::canonicalToDir -- GP:586-595
+__device__ __forceinline__ float3 canonical_to_dir(float2 p) {
+    const float cosTheta = 2.f * p.x - 1.f;
+    const float phi = 2.f * PPG_PI * p.y;
+    const float sinTheta = sqrtf(1.f - cosTheta * cosTheta);
+    float s, c; sincosf(phi, &s, &c);
+    return f3(sinTheta * c, sinTheta * s, cosTheta);
+}
+
+// QuadTreeNode::childIndex -- GP:205-217
+__device__ __forceinline__ int quad_child_index(float2 &p) {
+    int res = 0;
+    if (p.x < 0.5f) p.x *= 2.f; else { p.x = (p.x - 0.5f) * 2.f; res |= 1; }
+    if (p.y < 0.5f) p.y *= 2.f; else { p.y = (p.y - 0.5f) * 2.f; res |= 2; }
+    return res;
+}
+
+// DTree::pdf -- GP:415-421 + 232-245 (valid == mean() > 0).  Product accumulated top-down.
+template <class NodeT>
+__device__ __forceinline__ float dtree_pdf(const NodeT *__restrict__ tree, bool valid, float2 p) {
+    if (!valid) return 1.0f / (4.0f * PPG_PI);
+    float result = 1.0f; uint32_t n = 0;
+    for (;;) {
+        const float4 s = __ldg(&tree[n].sums);
+        const uint2 ch = __ldg(&tree[n].children);
+        const int c = quad_child_index(p);
+        const float sc = sum4(s, c);
+        if (!(sc > 0.f)) return 0.f;
+        result *= 4.f * sc / (s.x + s.y + s.z + s.w);
+        const uint32_t next = child16(ch, c);
+        if (next == 0u) break;
+        n = next;
+    }
+    return result / (4.0f * PPG_PI);
+}
+
+// DTree::sample -- GP:431-442 + 257-301.  One uniform per level, re-stretched; two at the leaf.
+// The reference evaluates origin_0 + 0.5*(origin_1 + 0.5*(... + 0.5*next2D)) from the leaf upward;
+// the per-level origin bits are kept in two masks and folded in that same order.
+template <class NodeT, class RngT>
+__device__ __forceinline__ float2 dtree_sample(const NodeT *__restrict__ tree, bool valid, RngT &rng) {
+    float2 res;
+    if (!valid) { res.x = rng.next1D(); res.y = rng.next1D(); return res; }
+    uint32_t bx = 0, by = 0; int levels = 0; uint32_t n = 0;
+    for (;;) {
+        const float4 s = __ldg(&tree[n].sums);
+        const uint2 ch = __ldg(&tree[n].children);
+        int index = 0;
+        const float topLeft = s.x, topRight = s.y;
+        float partial = topLeft + s.z;
+        const float total = partial + topRight + s.w;
+        if (!(total > 0.0f)) { res.x = rng.next1D(); res.y = rng.next1D(); break; }
+        float boundary = partial / total;
+        float smp = rng.next1D();
+        if (smp < boundary) {
+            smp /= boundary;
+            boundary = topLeft / partial;
+        } else {
+            partial = total - partial;
+            smp = (smp - boundary) / (1.0f - boundary);
+            boundary = topRight / partial;
+            index |= 1;
+        }
+        if (smp < boundary) {
+            smp /= boundary;
+        } else {
+            smp = (smp - boundary) / (1.0f - boundary);
+            index |= 2;
+        }
+        bx |= (uint32_t) (index & 1) << levels; by |= (uint32_t) ((index >> 1) & 1) << levels; ++levels;
+        const uint32_t next = child16(ch, index);
+        if (next == 0u) { res.x = rng.next1D(); res.y = rng.next1D(); break; }
+        n = next;
+    }
+    for (int i = levels - 1; i >= 0; --i) {
+        res.x = ((bx >> i) & 1u ? 0.5f : 0.0f) + 0.5f * res.x;
+        res.y = ((by >> i) & 1u ? 0.5f : 0.0f) + 0.5f * res.y;
+    }
+    res.x = fminf(fmaxf(res.x, 0.0f), 1.0f);
+    res.y = fminf(fmaxf(res.y, 0.0f), 1.0f);
+    return res;
+}
+
+// red.global.add.f32 without a return value
+__device__ __forceinline__ void red_add(float *addr, float v) { atomicAdd(addr, v); }
+
+// Add `w` to counters[key] with one atomic per distinct key per warp (the statistical-weight counter of
+// a D-tree is a single address that every vertex of that leaf hits: in iteration 0 that is ONE address
+// for the whole wavefront).  Lanes with equal (key, w) are merged: leader adds popc * w.
+__device__ __forceinline__ void warp_aggregated_add(float *counters, uint32_t key, float w, bool active) {
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned long long k = ((unsigned long long) key << 32) | __float_as_uint(w);
+    const unsigned peers = __match_any_sync(m, k);
+    const int leader = __ffs(peers) - 1;
+    if ((threadIdx.x & 31) == leader) red_add(&counters[key], w * (float) __popc(peers));
+}
+
+// QuadTreeNode::record (nearest) -- GP:303-312
+__device__ __forceinline__ void dtree_record_nearest(const uint2 *__restrict__ bchildren, float4 *bsums, uint32_t base, float2 p, float value) {
+    uint32_t n = 0;
+    for (;;) {
+        const int c = quad_child_index(p);
+        const uint32_t next = child16(__ldg(&bchildren[base + n]), c);
+        if (next == 0u) { red_add(reinterpret_cast<float *>(&bsums[base + n]) + c, value); return; }
+        n = next;
+    }
+}
+// DTree::depthAt -- GP:423-425 + 247-255
+__device__ __forceinline__ int dtree_depth_at(const uint2 *__restrict__ bchildren, uint32_t base, float2 p) {
+    int d = 1; uint32_t n = 0;
+    for (;;) {
+        const int c = quad_child_index(p);
+        const uint32_t next = child16(__ldg(&bchildren[base + n]), c);
+        if (next == 0u) return d;
+        n = next; ++d;
+    }
+}
+// QuadTreeNode::record (box footprint) -- GP:322-338 + 314-320; explicit stack, no wrap-around, no clamping
+__device__ __forceinline__ void dtree_record_box(const uint2 *__restrict__ bchildren, float4 *bsums, uint32_t base, float2 origin, float size, float value) {
+    struct E { uint32_t n; float ox, oy, s; };
+    E st[48]; int sp = 0;
+    st[sp++] = E{0u, 0.f, 0.f, 1.0f};
+    while (sp) {
+        const E e = st[--sp];
+        const float childSize = e.s / 2.f;
+        const uint2 ch = __ldg(&bchildren[base + e.n]);
+        for (int i = 0; i < 4; ++i) {
+            float cox = e.ox, coy = e.oy;
+            if (i & 1) cox += childSize;
+            if (i & 2) coy += childSize;
+            const float lx = fmaxf(fminf(origin.x + size, cox + childSize) - fmaxf(origin.x, cox), 0.0f);
+            const float ly = fmaxf(fminf(origin.y + size, coy + childSize) - fmaxf(origin.y, coy), 0.0f);
+            const float w = lx * ly;
+            if (w > 0.0f) {
+                const uint32_t next = child16(ch, i);
+                if (next == 0u) red_add(reinterpret_cast<float *>(&bsums[base + e.n]) + i, value * w);
+                else if (sp < 48) st[sp++] = E{next, cox, coy, childSize};
+            }
+        }
+    }
+}
+// DTree::recordIrradiance -- GP:395-413 (the statistical-weight add is done by the caller, warp-aggregated)
+__device__ __forceinline__ void dtree_record_irradiance(const uint2 *__restrict__ bchildren, float4 *bsums, uint32_t base, float2 p,
+                                                        float irradiance, float statisticalWeight, int directionalFilter) {
+    if (isfinite(irradiance) && irradiance > 0.f) {
+        if (directionalFilter == 0) dtree_record_nearest(bchildren, bsums, base, p, irradiance * statisticalWeight);
+        else {
+            const int depth = dtree_depth_at(bchildren, base, p);
+            const float size = ldexpf(1.0f, -depth);          // std::pow(0.5f, depth), exact
+            float2 origin = p;
+            origin.x -= size / 2.f; origin.y -= size / 2.f;
+            dtree_record_box(bchildren, bsums, base, origin, size, irradiance * statisticalWeight / (size * size));
+        }
+    }
+}
+
+__device__ __forceinline__ float logistic(float x) { return 1.f / (1.f + expf(-x)); }   // GP:64-66
+
+}  // namespace ppg

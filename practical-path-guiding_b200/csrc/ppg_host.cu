@@ -1,0 +1,1156 @@
+// ppg_host.cu -- host side of libppg_b200.so: the C ABI of include/ppg.h, the iteration schedule of the
+// reference integrator (GP = mitsuba/src/integrators/path/guided_path.cpp), BVH construction and the
+// launch sequence of the wavefront kernels.  C++ host, CUDA kernels, no torch, no CPU fallback.
+#include "../../include/ppg.h"
+#include "ppg_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace ppg;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_lastError;
+static int fail(int code, const std::string &msg) { g_lastError = msg; return code; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            g_lastError = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+            return PPG_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    // grow preserving contents
+    cudaError_t grow(size_t count, cudaStream_t s) {
+        if (count <= n && p) return cudaSuccess;
+        T *q = nullptr; cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && n) cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        if (p) cudaFree(p);
+        p = q; n = count; return cudaSuccess;
+    }
+};
+
+// ------------------------------------------------------------------ parameters (GP:1014-1085, integrator.cpp:190-225)
+extern "C" void ppg_params_default(ppg_params *p) {
+    p->nee = PPG_NEE_NEVER; p->sample_combination = PPG_COMB_AUTOMATIC; p->spatial_filter = PPG_SFILTER_NEAREST;
+    p->directional_filter = PPG_DFILTER_NEAREST; p->bsdf_sampling_fraction_loss = PPG_LOSS_NONE;
+    p->sd_tree_max_memory = -1; p->s_tree_threshold = 12000; p->d_tree_threshold = 0.01f; p->bsdf_sampling_fraction = 0.5f;
+    p->spp_per_pass = 4; p->budget_type = PPG_BUDGET_SECONDS; p->budget = 300.0f; p->dump_sd_tree = 0;
+    p->max_depth = -1; p->rr_depth = 5; p->strict_normals = 0; p->hide_emitters = 0; p->seed = 1234;
+}
+
+static bool parse_enum(const char *v, const char *const *names, int n, int32_t *out) {
+    for (int i = 0; i < n; ++i) if (!strcmp(v, names[i])) { *out = i; return true; }
+    return false;
+}
+static bool parse_bool(const char *v, int32_t *out) {
+    if (!strcmp(v, "true")) { *out = 1; return true; }
+    if (!strcmp(v, "false")) { *out = 0; return true; }
+    return false;
+}
+static bool parse_int(const char *v, long long *out) { char *e = nullptr; *out = strtoll(v, &e, 10); return e && *e == '\0' && e != v; }
+static bool parse_float(const char *v, float *out) { char *e = nullptr; *out = strtof(v, &e); return e && *e == '\0' && e != v; }
+
+extern "C" int ppg_params_set(ppg_params *p, const char *name, const char *value) {
+    if (!p || !name || !value) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    static const char *const nee[] = {"never", "kickstart", "always"};
+    static const char *const comb[] = {"discard", "automatic", "inversevar"};
+    static const char *const sf[] = {"nearest", "stochastic", "box"};
+    static const char *const df[] = {"nearest", "box"};
+    static const char *const loss[] = {"none", "kl", "var"};
+    static const char *const bt[] = {"spp", "seconds"};
+    bool ok; long long iv;
+    std::string n(name);
+    if (n == "nee") ok = parse_enum(value, nee, 3, &p->nee);
+    else if (n == "sampleCombination") ok = parse_enum(value, comb, 3, &p->sample_combination);
+    else if (n == "spatialFilter") ok = parse_enum(value, sf, 3, &p->spatial_filter);
+    else if (n == "directionalFilter") ok = parse_enum(value, df, 2, &p->directional_filter);
+    else if (n == "bsdfSamplingFractionLoss") ok = parse_enum(value, loss, 3, &p->bsdf_sampling_fraction_loss);
+    else if (n == "budgetType") ok = parse_enum(value, bt, 2, &p->budget_type);
+    else if (n == "sdTreeMaxMemory") { ok = parse_int(value, &iv); if (ok) p->sd_tree_max_memory = (int32_t) iv; }
+    else if (n == "sTreeThreshold") { ok = parse_int(value, &iv); if (ok) p->s_tree_threshold = (int32_t) iv; }
+    else if (n == "sppPerPass") { ok = parse_int(value, &iv); if (ok) p->spp_per_pass = (int32_t) iv; }
+    else if (n == "maxDepth") { ok = parse_int(value, &iv); if (ok) p->max_depth = (int32_t) iv; }
+    else if (n == "rrDepth") { ok = parse_int(value, &iv); if (ok) p->rr_depth = (int32_t) iv; }
+    else if (n == "seed") { ok = parse_int(value, &iv); if (ok) p->seed = (uint64_t) iv; }
+    else if (n == "dTreeThreshold") ok = parse_float(value, &p->d_tree_threshold);
+    else if (n == "bsdfSamplingFraction") ok = parse_float(value, &p->bsdf_sampling_fraction);
+    else if (n == "budget") ok = parse_float(value, &p->budget);
+    else if (n == "dumpSDTree") ok = parse_bool(value, &p->dump_sd_tree);
+    else if (n == "strictNormals") ok = parse_bool(value, &p->strict_normals);
+    else if (n == "hideEmitters") ok = parse_bool(value, &p->hide_emitters);
+    else return fail(PPG_ERR_INVALID_ARGUMENT, "unknown integrator parameter '" + n + "'");
+    if (!ok) return fail(PPG_ERR_INVALID_ARGUMENT, "invalid value '" + std::string(value) + "' for parameter '" + n + "'");
+    return PPG_OK;
+}
+
+extern "C" int ppg_params_validate(const ppg_params *p) {
+    if (!p) return fail(PPG_ERR_INVALID_ARGUMENT, "null params");
+    auto in = [](int v, int lo, int hi) { return v >= lo && v <= hi; };
+    if (!in(p->nee, 0, 2) || !in(p->sample_combination, 0, 2) || !in(p->spatial_filter, 0, 2) || !in(p->directional_filter, 0, 1) ||
+        !in(p->bsdf_sampling_fraction_loss, 0, 2) || !in(p->budget_type, 0, 1))
+        return fail(PPG_ERR_INVALID_ARGUMENT, "enum parameter out of range (the reference Assert(false)s, GP:1023-1080)");
+    if (p->rr_depth <= 0) return fail(PPG_ERR_INVALID_ARGUMENT, "'rrDepth' must be set to a value greater than zero!");
+    if (p->max_depth <= 0 && p->max_depth != -1) return fail(PPG_ERR_INVALID_ARGUMENT, "'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
+    if (p->spp_per_pass < 1) return fail(PPG_ERR_INVALID_ARGUMENT, "'sppPerPass' must be at least 1");
+    if (!(p->budget > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "'budget' must be positive");
+    if (!(p->bsdf_sampling_fraction >= 0.f && p->bsdf_sampling_fraction <= 1.f)) return fail(PPG_ERR_INVALID_ARGUMENT, "'bsdfSamplingFraction' must lie in [0,1]");
+    if (p->nee != PPG_NEE_NEVER) return fail(PPG_ERR_UNSUPPORTED, "nee != never is a 'next' row of the hot-path scope (SURVEY 8f) and not implemented yet");
+    return PPG_OK;
+}
+
+extern "C" const char *ppg_description(void) { return "Guided path tracer"; }
+extern "C" int ppg_abi_version(void) { return PPG_ABI_VERSION; }
+extern "C" const char *ppg_last_error(void) { return g_lastError.c_str(); }
+
+// ------------------------------------------------------------------ host BVH (binned SAH) + Wald triangle constants
+namespace {
+struct H3 { float x, y, z; };
+static inline H3 h3(float x, float y, float z) { return H3{x, y, z}; }
+static inline H3 operator-(H3 a, H3 b) { return h3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline H3 hcross(H3 a, H3 b) { return h3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static inline float hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline float hcomp(H3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// restated from include/mitsuba/render/triaccel.h:60-93 (Wald's projection-plane precomputation)
+static void wald_constants(H3 A, H3 B, H3 C, float out[9], int &k) {
+    static const int mod3[4] = {1, 2, 0, 1};
+    const H3 b = C - A, c = B - A, N = hcross(c, b);
+    k = 0;
+    for (int j = 0; j < 3; ++j) if (std::fabs(hcomp(N, j)) > std::fabs(hcomp(N, k))) k = j;
+    const int u = mod3[k], v = mod3[k + 1];
+    const float n_k = hcomp(N, k), denom = hcomp(b, u) * hcomp(c, v) - hcomp(b, v) * hcomp(c, u);
+    if (denom == 0) { k = 3; for (int i = 0; i < 9; ++i) out[i] = 0; return; }
+    out[0] = hcomp(N, u) / n_k; out[1] = hcomp(N, v) / n_k; out[2] = hdot(A, N) / n_k;   // n_u n_v n_d
+    out[3] = hcomp(A, u); out[4] = hcomp(A, v);                                           // a_u a_v
+    out[5] = hcomp(b, u) / denom; out[6] = -hcomp(b, v) / denom;                          // b_nu b_nv
+    out[7] = hcomp(c, v) / denom; out[8] = -hcomp(c, u) / denom;                          // c_nu c_nv
+}
+
+struct HostBvh {
+    std::vector<float> nodes;        // 8 floats per node
+    std::vector<uint32_t> order;     // leaf order -> original triangle
+};
+static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, HostBvh &out) {
+    const uint32_t nt = (uint32_t) tmin.size();
+    out.order.resize(nt);
+    for (uint32_t i = 0; i < nt; ++i) out.order[i] = i;
+    std::vector<H3> cen(nt);
+    for (uint32_t t = 0; t < nt; ++t) cen[t] = h3(0.5f * (tmin[t].x + tmax[t].x), 0.5f * (tmin[t].y + tmax[t].y), 0.5f * (tmin[t].z + tmax[t].z));
+    struct Node { H3 mn, mx; uint32_t left, count; };
+    std::vector<Node> nodes; nodes.reserve(2 * nt + 1); nodes.push_back(Node());
+    struct Job { uint32_t node, first, count; };
+    std::vector<Job> jobs; jobs.push_back(Job{0, 0, nt});
+    auto area = [](H3 mn, H3 mx) { const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z; return 2.f * (dx * dy + dy * dz + dz * dx); };
+    while (!jobs.empty()) {
+        const Job j = jobs.back(); jobs.pop_back();
+        H3 mn = h3(1e30f, 1e30f, 1e30f), mx = h3(-1e30f, -1e30f, -1e30f), cmn = mn, cmx = mx;
+        for (uint32_t i = j.first; i < j.first + j.count; ++i) {
+            const uint32_t t = out.order[i];
+            mn = h3(std::min(mn.x, tmin[t].x), std::min(mn.y, tmin[t].y), std::min(mn.z, tmin[t].z));
+            mx = h3(std::max(mx.x, tmax[t].x), std::max(mx.y, tmax[t].y), std::max(mx.z, tmax[t].z));
+            cmn = h3(std::min(cmn.x, cen[t].x), std::min(cmn.y, cen[t].y), std::min(cmn.z, cen[t].z));
+            cmx = h3(std::max(cmx.x, cen[t].x), std::max(cmx.y, cen[t].y), std::max(cmx.z, cen[t].z));
+        }
+        Node nd; nd.mn = mn; nd.mx = mx; nd.left = j.first; nd.count = j.count;
+        const int maxLeaf = 4;
+        if (j.count > (uint32_t) maxLeaf || j.count > 1) {
+            // binned SAH over the three axes
+            const int NB = 16; float bestCost = std::numeric_limits<float>::infinity(); int bestAxis = -1, bestBin = -1;
+            for (int ax = 0; ax < 3; ++ax) {
+                const float lo = hcomp(cmn, ax), hi = hcomp(cmx, ax);
+                if (!(hi > lo)) continue;
+                H3 bmn[NB], bmx[NB]; uint32_t bc[NB];
+                for (int b = 0; b < NB; ++b) { bmn[b] = h3(1e30f, 1e30f, 1e30f); bmx[b] = h3(-1e30f, -1e30f, -1e30f); bc[b] = 0; }
+                for (uint32_t i = j.first; i < j.first + j.count; ++i) {
+                    const uint32_t t = out.order[i];
+                    int b = (int) (NB * (hcomp(cen[t], ax) - lo) / (hi - lo)); b = std::min(std::max(b, 0), NB - 1);
+                    bc[b]++;
+                    bmn[b] = h3(std::min(bmn[b].x, tmin[t].x), std::min(bmn[b].y, tmin[t].y), std::min(bmn[b].z, tmin[t].z));
+                    bmx[b] = h3(std::max(bmx[b].x, tmax[t].x), std::max(bmx[b].y, tmax[t].y), std::max(bmx[b].z, tmax[t].z));
+                }
+                float rightArea[NB]; uint32_t rightCount[NB];
+                H3 rmn = h3(1e30f, 1e30f, 1e30f), rmx = h3(-1e30f, -1e30f, -1e30f); uint32_t rc = 0;
+                for (int b = NB - 1; b > 0; --b) {
+                    rmn = h3(std::min(rmn.x, bmn[b].x), std::min(rmn.y, bmn[b].y), std::min(rmn.z, bmn[b].z));
+                    rmx = h3(std::max(rmx.x, bmx[b].x), std::max(rmx.y, bmx[b].y), std::max(rmx.z, bmx[b].z));
+                    rc += bc[b]; rightArea[b] = rc ? area(rmn, rmx) : 0.f; rightCount[b] = rc;
+                }
+                H3 lmn = h3(1e30f, 1e30f, 1e30f), lmx = h3(-1e30f, -1e30f, -1e30f); uint32_t lc = 0;
+                for (int b = 0; b < NB - 1; ++b) {
+                    lmn = h3(std::min(lmn.x, bmn[b].x), std::min(lmn.y, bmn[b].y), std::min(lmn.z, bmn[b].z));
+                    lmx = h3(std::max(lmx.x, bmx[b].x), std::max(lmx.y, bmx[b].y), std::max(lmx.z, bmx[b].z));
+                    lc += bc[b];
+                    if (lc == 0 || rightCount[b + 1] == 0) continue;
+                    const float cost = area(lmn, lmx) * lc + rightArea[b + 1] * rightCount[b + 1];
+                    if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestBin = b; }
+                }
+            }
+            const float leafCost = area(mn, mx) * j.count;
+            if (bestAxis >= 0 && (j.count > (uint32_t) maxLeaf || bestCost < leafCost)) {
+                const float lo = hcomp(cmn, bestAxis), hi = hcomp(cmx, bestAxis);
+                auto mid = std::partition(out.order.begin() + j.first, out.order.begin() + j.first + j.count, [&](uint32_t t) {
+                    int b = (int) (NB * (hcomp(cen[t], bestAxis) - lo) / (hi - lo)); b = std::min(std::max(b, 0), NB - 1);
+                    return b <= bestBin;
+                });
+                const uint32_t nl = (uint32_t) (mid - (out.order.begin() + j.first));
+                if (nl > 0 && nl < j.count) {
+                    nd.left = (uint32_t) nodes.size(); nd.count = 0; nodes[j.node] = nd;
+                    nodes.push_back(Node()); nodes.push_back(Node());
+                    jobs.push_back(Job{nd.left, j.first, nl});
+                    jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl});
+                    continue;
+                }
+            }
+            if (j.count > (uint32_t) maxLeaf) {   // degenerate centroids: split in the middle
+                const uint32_t nl = j.count / 2;
+                nd.left = (uint32_t) nodes.size(); nd.count = 0; nodes[j.node] = nd;
+                nodes.push_back(Node()); nodes.push_back(Node());
+                jobs.push_back(Job{nd.left, j.first, nl});
+                jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl});
+                continue;
+            }
+        }
+        nodes[j.node] = nd;
+    }
+    out.nodes.resize(nodes.size() * 8);
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        float *f = &out.nodes[8 * i];
+        f[0] = nodes[i].mn.x; f[1] = nodes[i].mn.y; f[2] = nodes[i].mn.z; memcpy(&f[3], &nodes[i].left, 4);
+        f[4] = nodes[i].mx.x; f[5] = nodes[i].mx.y; f[6] = nodes[i].mx.z; memcpy(&f[7], &nodes[i].count, 4);
+    }
+}
+}  // namespace
+
+// ------------------------------------------------------------------ the integrator object
+struct ppg_integrator {
+    ppg_params prm;
+    int device = 0, numSMs = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    std::atomic<bool> cancelled{false};
+    int rank = 0, world = 1;
+    ppg_allreduce_fn allreduce = nullptr; void *allreduceUser = nullptr;
+
+    // scene
+    bool haveScene = false;
+    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance; DevBuf<int4> dMeta;
+    SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
+    float aabbMin[3], aabbMax[3];
+    int W = 0, H = 0;
+    DevBuf<uint32_t> dPixelMap; uint32_t nLocalPixels = 0;
+
+    // film
+    DevBuf<float4> dImage, dSqImage, dFilm; DevBuf<float> dRgb; DevBuf<double> dVar;
+    std::vector<DevBuf<float4> *> images; std::vector<float> variances;
+
+    // SD-tree
+    uint32_t capNodes = 0; size_t capPool = 0;
+    DevBuf<uint2> dSnodes; DevBuf<float4> dLeafA; DevBuf<float> dBweight, dSampSum, dSampWeight, dAdam, dAdamG, dAdamW;
+    DevBuf<int> dSampDepth, dBuildDepth; DevBuf<uint32_t> dSampCount, dBuildCount, dBuildBase, dScalars /* [0]=nNodes [1]=totalBuild */;
+    DevBuf<SampNode> dSamp; DevBuf<uint2> dBchildren; DevBuf<float> dTrain /* bsums | packed tail */;
+    uint32_t hNodes = 1; uint32_t hTotalBuild = 1;
+    float extent[3];
+
+    // wavefront
+    size_t pathCapacity = 0; int maxBounces = 0, nSlabs = 0; int recordMode = 0;
+    DevBuf<float4> dStateA, dStateB, dSlabs, dLiFinal; DevBuf<uint32_t> dLive; DevBuf<unsigned long long> dCounters;
+    int gridBounce = 0, gridCommit = 0;
+
+    // per-kernel-class CUDA-event timing on the launching stream
+    struct Timed { cudaEvent_t a, b; int cls; };
+    std::vector<Timed> evPool; size_t evUsed = 0; cudaEvent_t evRender0 = nullptr, evRender1 = nullptr;
+    bool kernelTiming = true;
+    void tic(int cls) {
+        if (!kernelTiming) return;
+        if (evUsed == evPool.size()) { Timed t; cudaEventCreate(&t.a); cudaEventCreate(&t.b); t.cls = cls; evPool.push_back(t); }
+        evPool[evUsed].cls = cls; cudaEventRecord(evPool[evUsed].a, stream);
+    }
+    void toc() { if (!kernelTiming) return; cudaEventRecord(evPool[evUsed].b, stream); ++evUsed; }
+    void resolve_timers() {   // call after a stream synchronize
+        for (size_t i = 0; i < evUsed; ++i) {
+            float ms = 0; if (cudaEventElapsedTime(&ms, evPool[i].a, evPool[i].b) == cudaSuccess) { stats.kernel_ms[evPool[i].cls] += ms; stats.kernel_count[evPool[i].cls]++; }
+        }
+        evUsed = 0;
+    }
+
+    // run state (GP:2313-2323)
+    bool isBuilt = false, isFinalIter = false; int iter = 0, passesRendered = 0;
+    std::chrono::steady_clock::time_point startTime;
+    ppg_stats stats; uint64_t launches = 0; double deviceMs = 0;
+
+    ~ppg_integrator() {
+        for (auto *b : images) delete b;
+        for (auto &t : evPool) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        if (evRender0) cudaEventDestroy(evRender0);
+        if (evRender1) cudaEventDestroy(evRender1);
+        if (evA) cudaEventDestroy(evA);
+        if (evB) cudaEventDestroy(evB);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static float elapsed_s(std::chrono::steady_clock::time_point s) {
+    return (float) std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - s).count() / 1000;
+}
+
+extern "C" int ppg_create(const ppg_params *params, int device, ppg_integrator **out) {
+    if (!params || !out) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = ppg_params_validate(params);
+    if (rc != PPG_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PPG_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) return fail(PPG_ERR_NO_DEVICE, "CUDA device index out of range");
+    CK(cudaSetDevice(device));
+    ppg_integrator *h = new ppg_integrator();
+    h->prm = *params; h->device = device;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    h->numSMs = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->evA)); CK(cudaEventCreate(&h->evB)); CK(cudaEventCreate(&h->evRender0)); CK(cudaEventCreate(&h->evRender1));
+    if (const char *e = getenv("PPG_KERNEL_TIMING")) h->kernelTiming = atoi(e) != 0;
+    memset(&h->stats, 0, sizeof(h->stats));
+    *out = h;
+    return PPG_OK;
+}
+extern "C" void ppg_destroy(ppg_integrator *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    delete h;
+}
+extern "C" int ppg_cancel(ppg_integrator *h) { if (!h) return PPG_ERR_INVALID_ARGUMENT; h->cancelled.store(true); return PPG_OK; }
+extern "C" int ppg_set_allreduce(ppg_integrator *h, ppg_allreduce_fn cb, void *user) {
+    if (!h) return PPG_ERR_INVALID_ARGUMENT; h->allreduce = cb; h->allreduceUser = user; return PPG_OK;
+}
+
+static int build_pixel_map(ppg_integrator *h) {
+    // 32x32 image blocks (scene.cpp:24), row-major over blocks, interleaved across ranks; row-major inside a block
+    const int bs = 32, bx = (h->W + bs - 1) / bs, by = (h->H + bs - 1) / bs;
+    std::vector<uint32_t> map; map.reserve((size_t) h->W * h->H / h->world + 1024);
+    for (int b = 0; b < bx * by; ++b) {
+        if (b % h->world != h->rank) continue;
+        const int x0 = (b % bx) * bs, y0 = (b / bx) * bs;
+        for (int y = y0; y < std::min(y0 + bs, h->H); ++y)
+            for (int x = x0; x < std::min(x0 + bs, h->W); ++x) map.push_back((uint32_t) x | ((uint32_t) y << 16));
+    }
+    h->nLocalPixels = (uint32_t) map.size();
+    CK(h->dPixelMap.alloc(std::max<size_t>(map.size(), 1)));
+    if (!map.empty()) CK(cudaMemcpy(h->dPixelMap.p, map.data(), map.size() * 4, cudaMemcpyHostToDevice));
+    return PPG_OK;
+}
+
+extern "C" int ppg_set_shard(ppg_integrator *h, int rank, int world_size) {
+    if (!h || world_size < 1 || rank < 0 || rank >= world_size) return fail(PPG_ERR_INVALID_ARGUMENT, "bad shard");
+    CK(cudaSetDevice(h->device));
+    h->rank = rank; h->world = world_size;
+    if (h->haveScene) return build_pixel_map(h);
+    return PPG_OK;
+}
+
+extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
+    if (!h || !s) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    if (!s->n_triangles || !s->positions || !s->indices || !s->triangle_shape || !s->shapes || !s->bsdfs)
+        return fail(PPG_ERR_INVALID_ARGUMENT, "scene needs triangles, shapes and bsdfs");
+    if (s->camera.film_width <= 0 || s->camera.film_height <= 0 || s->camera.film_width > 65535 || s->camera.film_height > 65535)
+        return fail(PPG_ERR_INVALID_ARGUMENT, "film size out of range");
+    CK(cudaSetDevice(h->device));
+    const uint32_t nt = s->n_triangles;
+    for (uint32_t t = 0; t < nt; ++t) {
+        if (s->triangle_shape[t] >= s->n_shapes) return fail(PPG_ERR_INVALID_ARGUMENT, "triangle_shape out of range");
+        for (int k = 0; k < 3; ++k) if (s->indices[3 * t + k] >= s->n_vertices) return fail(PPG_ERR_INVALID_ARGUMENT, "vertex index out of range");
+    }
+    for (uint32_t i = 0; i < s->n_shapes; ++i) {
+        if (s->shapes[i].bsdf < 0 || (uint32_t) s->shapes[i].bsdf >= s->n_bsdfs) return fail(PPG_ERR_INVALID_ARGUMENT, "shape bsdf out of range");
+        if (s->shapes[i].emitter >= (int) s->n_emitters) return fail(PPG_ERR_INVALID_ARGUMENT, "shape emitter out of range");
+    }
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK)
+        return fail(PPG_ERR_UNSUPPORTED, "BSDF type outside the implemented hot-path scope");
+    auto P = [&](uint32_t i) { return h3(s->positions[3 * i], s->positions[3 * i + 1], s->positions[3 * i + 2]); };
+    std::vector<H3> tmin(nt), tmax(nt);
+    for (uint32_t t = 0; t < nt; ++t) {
+        const H3 a = P(s->indices[3 * t]), b = P(s->indices[3 * t + 1]), c = P(s->indices[3 * t + 2]);
+        tmin[t] = h3(std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z)));
+        tmax[t] = h3(std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)));
+    }
+    HostBvh bvh; build_bvh(tmin, tmax, bvh);
+    std::vector<float> accel(12 * (size_t) nt), geom(24 * (size_t) nt); std::vector<int32_t> meta(4 * (size_t) nt);
+    for (uint32_t slot = 0; slot < nt; ++slot) {
+        const uint32_t t = bvh.order[slot];
+        const uint32_t i0 = s->indices[3 * t], i1 = s->indices[3 * t + 1], i2 = s->indices[3 * t + 2];
+        float w[9]; int k; wald_constants(P(i0), P(i1), P(i2), w, k);
+        float *a = &accel[12 * (size_t) slot];
+        a[0] = w[0]; a[1] = w[1]; a[2] = w[2]; memcpy(&a[3], &k, 4);
+        a[4] = w[3]; a[5] = w[4]; a[6] = w[5]; a[7] = w[6];
+        a[8] = w[7]; a[9] = w[8]; memcpy(&a[10], &t, 4); memcpy(&a[11], &slot, 4);
+        const uint32_t vi[3] = {i0, i1, i2};
+        float *g = &geom[24 * (size_t) slot];
+        for (int k2 = 0; k2 < 3; ++k2) {
+            const float *p = &s->positions[3 * vi[k2]];
+            const float nz[3] = {0, 0, 0}; const float *n = s->normals ? &s->normals[3 * vi[k2]] : nz;
+            const float uz[2] = {0, 0}; const float *uv = s->uvs ? &s->uvs[2 * vi[k2]] : uz;
+            g[4 * k2] = p[0]; g[4 * k2 + 1] = p[1]; g[4 * k2 + 2] = p[2]; g[4 * k2 + 3] = n[0];
+            g[12 + 4 * k2] = n[1]; g[12 + 4 * k2 + 1] = n[2]; g[12 + 4 * k2 + 2] = uv[0]; g[12 + 4 * k2 + 3] = uv[1];
+        }
+        const ppg_shape &sh = s->shapes[s->triangle_shape[t]];
+        meta[4 * (size_t) slot] = sh.bsdf; meta[4 * (size_t) slot + 1] = sh.emitter;
+        meta[4 * (size_t) slot + 2] = (sh.has_normals && s->normals) ? 1 : 0; meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
+    }
+    std::vector<float> bsdf(8 * (size_t) s->n_bsdfs, 0.f);
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
+        float *b = &bsdf[8 * (size_t) i];
+        b[0] = s->bsdfs[i].reflectance[0]; b[1] = s->bsdfs[i].reflectance[1]; b[2] = s->bsdfs[i].reflectance[2];
+        if (s->bsdfs[i].type == PPG_BSDF_NULL_BLACK) b[0] = b[1] = b[2] = 0.f;
+        const uint32_t tf = 0u | ((s->bsdfs[i].flags & 0xffffffu) << 8); memcpy(&b[3], &tf, 4);
+    }
+    std::vector<float> rad(4 * (size_t) std::max<uint32_t>(s->n_emitters, 1), 0.f);
+    for (uint32_t i = 0; i < s->n_emitters; ++i) { rad[4 * i] = s->area_radiance[3 * i]; rad[4 * i + 1] = s->area_radiance[3 * i + 1]; rad[4 * i + 2] = s->area_radiance[3 * i + 2]; }
+    const size_t nBvh = bvh.nodes.size() / 8;
+    CK(h->dAccel.alloc(3 * (size_t) nt)); CK(h->dGeom.alloc(6 * (size_t) nt)); CK(h->dMeta.alloc(nt)); CK(h->dBvh.alloc(2 * nBvh));
+    CK(h->dBsdf.alloc(2 * (size_t) s->n_bsdfs)); CK(h->dRadiance.alloc(std::max<uint32_t>(s->n_emitters, 1)));
+    CK(cudaMemcpy(h->dAccel.p, accel.data(), accel.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dGeom.p, geom.data(), geom.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dMeta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dBvh.p, bvh.nodes.data(), bvh.nodes.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dBsdf.p, bsdf.data(), bsdf.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dRadiance.p, rad.data(), rad.size() * 4, cudaMemcpyHostToDevice));
+    SceneView &v = h->sceneView;
+    v.accel = h->dAccel.p; v.geom = h->dGeom.p; v.meta = h->dMeta.p; v.bvh = h->dBvh.p; v.bsdf = h->dBsdf.p; v.radiance = h->dRadiance.p;
+    v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
+    const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 2 * s->n_bsdfs + v.nEmitters);
+    h->sceneSmemBytes = sceneBytes <= 48 * 1024 ? (uint32_t) sceneBytes : 0u;   // small scenes (CBOX: ~9 KB) live in shared memory
+    // camera (src/sensors/perspective.cpp:120-298; lookAt columns: left, up, dir, origin -- transform.cpp:191-214)
+    const float *m = s->camera.to_world;
+    Camera &c = h->cam;
+    c.left = make_float3(m[0], m[4], m[8]); c.up = make_float3(m[1], m[5], m[9]); c.dir = make_float3(m[2], m[6], m[10]); c.o = make_float3(m[3], m[7], m[11]);
+    const float aspect = (float) s->camera.film_width / (float) s->camera.film_height;
+    c.tanX = std::tan(0.5f * s->camera.x_fov_deg * (3.14159265358979323846f / 180.0f)); c.tanY = c.tanX / aspect;
+    c.nearClip = s->camera.near_clip; c.farClip = s->camera.far_clip; c.W = s->camera.film_width; c.H = s->camera.film_height;
+    h->W = c.W; h->H = c.H;
+    for (int i = 0; i < 3; ++i) { h->aabbMin[i] = s->aabb_min[i]; h->aabbMax[i] = s->aabb_max[i]; }
+    // STree::STree (GP:850-860): cubify from the min corner
+    const float sx = h->aabbMax[0] - h->aabbMin[0], sy = h->aabbMax[1] - h->aabbMin[1], sz = h->aabbMax[2] - h->aabbMin[2];
+    const float mxs = std::max(std::max(sx, sy), sz);
+    for (int i = 0; i < 3; ++i) { const float mx = h->aabbMin[i] + mxs; h->extent[i] = mx - h->aabbMin[i]; }
+    const size_t npx = (size_t) h->W * h->H;
+    CK(h->dImage.alloc(npx)); CK(h->dSqImage.alloc(npx)); CK(h->dFilm.alloc(npx)); CK(h->dRgb.alloc(3 * npx)); CK(h->dVar.alloc(1));
+    h->haveScene = true;
+    return build_pixel_map(h);
+}
+
+// ------------------------------------------------------------------ SD-tree storage
+static int ensure_tree_capacity(ppg_integrator *h, uint32_t nodes, size_t pool) {
+    if (nodes > h->capNodes) {
+        const uint32_t cap = std::max<uint32_t>(nodes, std::max<uint32_t>(2 * h->capNodes, 1u << 16));
+        CK(h->dSnodes.grow(cap, h->stream)); CK(h->dLeafA.grow(cap, h->stream)); CK(h->dBweight.grow(cap, h->stream));
+        CK(h->dSampSum.grow(cap, h->stream)); CK(h->dSampWeight.grow(cap, h->stream)); CK(h->dAdam.grow(6 * (size_t) cap, h->stream));
+        CK(h->dAdamG.grow(cap, h->stream)); CK(h->dAdamW.grow(cap, h->stream)); CK(h->dSampDepth.grow(cap, h->stream));
+        CK(h->dBuildDepth.grow(cap, h->stream)); CK(h->dSampCount.grow(cap, h->stream)); CK(h->dBuildCount.grow(cap, h->stream));
+        CK(h->dBuildBase.grow(cap, h->stream));
+        h->capNodes = cap;
+    }
+    if (pool > h->capPool) {
+        const size_t cap = std::max<size_t>(pool, std::max<size_t>(2 * h->capPool, (size_t) 1 << 20));
+        CK(h->dSamp.grow(cap, h->stream)); CK(h->dBchildren.grow(cap, h->stream));
+        h->capPool = cap;
+    }
+    // bsums (4 floats per pool node) followed by the packed exchange tail (3 floats per S-tree node + scalars)
+    CK(h->dTrain.grow(4 * h->capPool + 4 * (size_t) h->capNodes + 64, h->stream));
+    return PPG_OK;
+}
+
+static MaintParams maint(ppg_integrator *h) {
+    MaintParams M;
+    M.snodes = h->dSnodes.p; M.leafA = h->dLeafA.p; M.bweight = h->dBweight.p; M.sampSum = h->dSampSum.p; M.sampWeight = h->dSampWeight.p;
+    M.sampDepth = h->dSampDepth.p; M.sampCount = h->dSampCount.p; M.adam = h->dAdam.p; M.buildCount = h->dBuildCount.p; M.buildDepth = h->dBuildDepth.p;
+    M.nNodes = h->dScalars.p; M.capNodes = h->capNodes; M.samp = h->dSamp.p; M.bchildren = h->dBchildren.p; M.bsums = reinterpret_cast<float4 *>(h->dTrain.p);
+    return M;
+}
+
+// new STree (GP:1519): one leaf whose sampling tree is a single empty quadtree node
+static int init_tree(ppg_integrator *h) {
+    CK(h->dScalars.alloc(8));
+    h->capNodes = 0; h->capPool = 0;
+    h->dSnodes.release(); h->dLeafA.release(); h->dBweight.release(); h->dSampSum.release(); h->dSampWeight.release(); h->dAdam.release();
+    h->dAdamG.release(); h->dAdamW.release(); h->dSampDepth.release(); h->dBuildDepth.release(); h->dSampCount.release(); h->dBuildCount.release();
+    h->dBuildBase.release(); h->dSamp.release(); h->dBchildren.release(); h->dTrain.release();
+    int rc = ensure_tree_capacity(h, 1u << 16, (size_t) 1 << 20);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->dSnodes.p, 0, sizeof(uint2) * h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dLeafA.p, 0, sizeof(float4) * h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dBweight.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dSampSum.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dSampWeight.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dAdam.p, 0, 24 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dAdamG.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dAdamW.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dSampDepth.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dSamp.p, 0, sizeof(SampNode), h->stream));          // one empty quadtree node at pool offset 0
+    const uint32_t one[2] = {1u, 1u};
+    CK(cudaMemcpyAsync(h->dScalars.p, one, 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dSampCount.p, one, 4, cudaMemcpyHostToDevice, h->stream));
+    h->hNodes = 1; h->hTotalBuild = 1;
+    CK(cudaStreamSynchronize(h->stream));
+    return PPG_OK;
+}
+
+static TreeView tree_view(ppg_integrator *h) {
+    TreeView T;
+    T.snodes = h->dSnodes.p; T.leafA = h->dLeafA.p; T.samp = h->dSamp.p; T.bchildren = h->dBchildren.p;
+    T.bsums = reinterpret_cast<float4 *>(h->dTrain.p); T.bweight = h->dBweight.p; T.adamG = h->dAdamG.p; T.adamW = h->dAdamW.p;
+    T.aabbMin = make_float3(h->aabbMin[0], h->aabbMin[1], h->aabbMin[2]); T.extent = make_float3(h->extent[0], h->extent[1], h->extent[2]);
+    return T;
+}
+
+// resetSDTree, GP:1108-1113
+static int reset_sd_tree(ppg_integrator *h) {
+    const double thr = std::sqrt(std::pow(2.0, h->iter) * h->prm.spp_per_pass / 4) * h->prm.s_tree_threshold;
+    const float threshold = (float) (size_t) thr;                   // (size_t) cast then Float comparison, GP:1111 + 953-955
+    // upper bound of the node count after refinement: every leaf can at most double per halving of its weight;
+    // the total weight of the last iteration bounds the number of new leaves by 2*W/threshold
+    bool memCapped = false;
+    if (h->prm.sd_tree_max_memory >= 0) {   // GP:958-967 (footprint approximated by node counts: 2 trees x 24 B per node + per-tree overhead)
+        const size_t fp = (size_t) h->hTotalBuild * 2 * 24 + (size_t) h->hNodes * 96;
+        memCapped = fp / 1000000 >= (size_t) h->prm.sd_tree_max_memory;
+    }
+    if (!memCapped) {
+        // capacity: the refinement can create at most 2 nodes per threshold worth of recorded weight
+        double totalW = 0;
+        {
+            std::vector<float> w(h->hNodes);
+            CK(cudaMemcpyAsync(w.data(), h->dBweight.p, 4 * (size_t) h->hNodes, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (float x : w) totalW += x;
+        }
+        const double est = h->hNodes + 4.0 * totalW / std::max(1.0f, threshold) + 1024;
+        int rc = ensure_tree_capacity(h, (uint32_t) std::min<double>(est, 4.0e9), h->capPool);
+        if (rc) return rc;
+        MaintParams M = maint(h);
+        h->tic(PPG_K_REFINE); stree_refine_kernel<<<1, 1024, 0, h->stream>>>(M, threshold); h->toc(); h->launches++;
+    }
+    MaintParams M = maint(h);
+    const int blocks = h->numSMs * 4;
+    h->tic(PPG_K_RESET);
+    dtree_reset_kernel<false><<<blocks, 128, 0, h->stream>>>(M, nullptr, 20, h->prm.d_tree_threshold); h->launches++;
+    exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->dBuildCount.p, h->dBuildBase.p, h->dScalars.p, h->dScalars.p + 1); h->launches++;
+    h->toc();
+    uint32_t sc[2];
+    CK(cudaMemcpyAsync(sc, h->dScalars.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->hNodes = sc[0]; h->hTotalBuild = sc[1];
+    int rc = ensure_tree_capacity(h, h->hNodes, std::max<size_t>(h->hTotalBuild, 1));
+    if (rc) return rc;
+    M = maint(h);
+    h->tic(PPG_K_RESET);
+    dtree_reset_kernel<true><<<blocks, 128, 0, h->stream>>>(M, h->dBuildBase.p, 20, h->prm.d_tree_threshold); h->launches++;
+    leaf_after_reset_kernel<<<blocks, 256, 0, h->stream>>>(M, h->dBuildBase.p); h->launches++;
+    h->toc();
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream)); h->resolve_timers();
+    return PPG_OK;
+}
+
+// the one exchange step: sum the building statistics over all ranks
+__global__ void pack_tail_kernel(float *tail, const float *bweight, const float *adamG, const float *adamW, uint32_t n, int dir) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (dir == 0) { tail[i] = bweight[i]; tail[n + i] = adamG[i]; tail[2 * (size_t) n + i] = adamW[i]; }
+        else { const_cast<float *>(bweight)[i] = tail[i]; const_cast<float *>(adamG)[i] = tail[n + i]; const_cast<float *>(adamW)[i] = tail[2 * (size_t) n + i]; }
+    }
+}
+static int exchange_training_statistics(ppg_integrator *h) {
+    if (!h->allreduce || h->world <= 1) return PPG_OK;
+    float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;
+    pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->dAdamG.p, h->dAdamW.p, h->hNodes, 0); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->allreduce(h->allreduceUser, h->dTrain.p, 4 * (size_t) h->hTotalBuild + 3 * (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+    pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->dAdamG.p, h->dAdamW.p, h->hNodes, 1); h->launches++;
+    return PPG_OK;
+}
+// a host scalar made identical on all ranks (rank 0's value wins): time-based decisions must not diverge
+static int sync_scalar(ppg_integrator *h, float *v) {
+    if (!h->allreduce || h->world <= 1) return PPG_OK;
+    float *slot = h->dTrain.p + h->dTrain.n - 16;
+    const float mine = h->rank == 0 ? *v : 0.f;
+    CK(cudaMemcpyAsync(slot, &mine, 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->allreduce(h->allreduceUser, slot, 1) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+    CK(cudaMemcpy(v, slot, 4, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+
+// buildSDTree, GP:1115-1189
+static int build_sd_tree(ppg_integrator *h, ppg_iteration_stats &st) {
+    int rc = exchange_training_statistics(h);
+    if (rc) return rc;
+    MaintParams M = maint(h);
+    h->tic(PPG_K_BUILD); dtree_build_kernel<<<h->numSMs * 4, 128, 0, h->stream>>>(M, h->dBuildBase.p); h->toc(); h->launches++;
+    CK(cudaGetLastError());
+    // "Distribution statistics" (GP:1121-1186) on the host, in node order like forEachDTreeWrapperConst
+    const uint32_t n = h->hNodes;
+    std::vector<uint2> sn(n); std::vector<float> ssum(n), sw(n); std::vector<int> sd(n); std::vector<uint32_t> scnt(n);
+    CK(cudaMemcpyAsync(sn.data(), h->dSnodes.p, sizeof(uint2) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ssum.data(), h->dSampSum.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sw.data(), h->dSampWeight.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sd.data(), h->dSampDepth.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(scnt.data(), h->dSampCount.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream)); h->resolve_timers();
+    int maxDepth = 0, minDepth = std::numeric_limits<int>::max(); float avgDepth = 0;
+    float maxR = 0, minR = std::numeric_limits<float>::max(), avgR = 0;
+    size_t maxN = 0, minN = std::numeric_limits<size_t>::max(); float avgN = 0;
+    float maxW = 0, minW = std::numeric_limits<float>::max(), avgW = 0;
+    int nPoints = 0, nPointsNodes = 0; uint32_t leaves = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (sn[i].x != 0u) continue;
+        ++leaves;
+        const int depth = sd[i];
+        maxDepth = std::max(maxDepth, depth); minDepth = std::min(minDepth, depth); avgDepth += depth;
+        float mean = 0; if (sw[i] != 0) { const float factor = 1 / (3.14159265358979323846f * 4 * sw[i]); mean = factor * ssum[i]; }
+        maxR = std::max(maxR, mean); minR = std::min(minR, mean); avgR += mean;
+        if (scnt[i] > 1) { const size_t nodes = scnt[i]; maxN = std::max(maxN, nodes); minN = std::min(minN, nodes); avgN += nodes; ++nPointsNodes; }
+        maxW = std::max(maxW, sw[i]); minW = std::min(minW, sw[i]); avgW += sw[i];
+        ++nPoints;
+    }
+    if (nPoints > 0) { avgDepth /= nPoints; avgR /= nPoints; if (nPointsNodes > 0) avgN /= nPointsNodes; avgW /= nPoints; }
+    st.depth_min = minDepth; st.depth_max = maxDepth; st.depth_avg = avgDepth;
+    st.mean_radiance_min = minR; st.mean_radiance_avg = avgR; st.mean_radiance_max = maxR;
+    st.nodes_min = minN; st.nodes_max = maxN; st.nodes_avg = avgN;
+    st.weight_min = minW; st.weight_avg = avgW; st.weight_max = maxW;
+    st.s_tree_nodes = n; st.s_tree_leaves = leaves;
+    h->isBuilt = true;
+    return PPG_OK;
+}
+
+// ------------------------------------------------------------------ wavefront buffers
+static int ensure_wavefront(ppg_integrator *h) {
+    const size_t perPass = (size_t) h->nLocalPixels * h->prm.spp_per_pass;
+    h->maxBounces = h->prm.max_depth > 0 ? h->prm.max_depth : 64;
+    h->nSlabs = std::max(1, h->maxBounces - 1);
+    const bool full = h->prm.spatial_filter != PPG_SFILTER_NEAREST || h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE;
+    h->recordMode = full ? 2 : 1;
+    const size_t perPath = 2 * 80 + 16 + (size_t) h->nSlabs * (full ? 96 : 48);
+    size_t cap = (size_t) 1 << 23;
+    if (const char *e = getenv("PPG_PATH_CAPACITY")) cap = std::max<size_t>(strtoull(e, nullptr, 10), 1024);
+    size_t budget = (size_t) 24 << 30;
+    if (const char *e = getenv("PPG_WAVEFRONT_BYTES")) budget = strtoull(e, nullptr, 10);
+    cap = std::min(cap, budget / perPath);
+    cap = std::max(cap, perPass);                          // one pass must fit
+    cap = (cap / std::max<size_t>(perPass, 1)) * std::max<size_t>(perPass, 1);   // whole passes only
+    cap = std::max(cap, perPass);
+    if (cap > 0xFFFFFFF0ull / 2) return fail(PPG_ERR_INVALID_ARGUMENT, "pass too large for 31-bit path ids");
+    if (cap != h->pathCapacity) {
+        h->dStateA.release(); h->dStateB.release(); h->dSlabs.release(); h->dLiFinal.release();
+        CK(h->dStateA.alloc(5 * cap)); CK(h->dStateB.alloc(5 * cap)); CK(h->dLiFinal.alloc(cap));
+        CK(h->dSlabs.alloc((size_t) h->nSlabs * (full ? 6 : 3) * cap));
+        h->pathCapacity = cap;
+    }
+    CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
+    // persistent grids: resident blocks per SM from the occupancy calculator
+    int occ = 0;
+    CK(cudaFuncSetAttribute(bounce_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1>, PPG_BLOCK, h->sceneSmemBytes));
+    h->gridBounce = h->numSMs * std::max(occ, 1);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
+    h->gridCommit = h->numSMs * std::max(occ, 1);
+    return PPG_OK;
+}
+
+static PathState path_state(float4 *base, size_t cap) {
+    PathState s; s.s0 = base; s.s1 = base + cap; s.s2 = base + 2 * cap; s.s3 = base + 3 * cap; s.s4 = base + 4 * cap; return s;
+}
+static VertexSlab slab_at(ppg_integrator *h, int k) {
+    const size_t cap = h->pathCapacity; const int per = h->recordMode == 2 ? 6 : 3;
+    float4 *b = h->dSlabs.p;
+    VertexSlab s;
+    // field-major layout: field f of slab k at ((f * nSlabs) + k) * cap, so that slab k+1 of a field is +cap (commit's slabStride)
+    s.v0 = b + ((size_t) 0 * h->nSlabs + k) * cap; s.v1 = b + ((size_t) 1 * h->nSlabs + k) * cap; s.v2 = b + ((size_t) 2 * h->nSlabs + k) * cap;
+    if (per == 6) { s.v3 = b + ((size_t) 3 * h->nSlabs + k) * cap; s.v4 = b + ((size_t) 4 * h->nSlabs + k) * cap; s.v5 = b + ((size_t) 5 * h->nSlabs + k) * cap; }
+    else { s.v3 = s.v4 = s.v5 = nullptr; }
+    return s;
+}
+
+template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid) {
+    const size_t sm = P.sceneSmemBytes;
+    if (record == 0) bounce_kernel<FIRST, 0><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else if (record == 1) bounce_kernel<FIRST, 1><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else bounce_kernel<FIRST, 2><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    h->launches++;
+}
+
+// one batch of `nPasses` passes as a single wavefront
+static int render_batch(ppg_integrator *h, int nPasses) {
+    const uint32_t nPaths = (uint32_t) ((size_t) nPasses * h->nLocalPixels * h->prm.spp_per_pass);
+    if (nPaths == 0) return PPG_OK;
+    const int record = h->isFinalIter ? 0 : h->recordMode;
+    CK(cudaMemsetAsync(h->dLive.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
+    CK(cudaMemcpyAsync(h->dLive.p, &nPaths, 4, cudaMemcpyHostToDevice, h->stream));
+    RenderParams P;
+    P.scene = h->sceneView; P.cam = h->cam; P.tree = tree_view(h);
+    P.liFinal = h->dLiFinal.p; P.pixelMap = h->dPixelMap.p; P.counters = h->dCounters.p;
+    P.nPaths = nPaths; P.nLocalPixels = h->nLocalPixels; P.spp = (uint32_t) h->prm.spp_per_pass;
+    P.passBase = (uint64_t) h->passesRendered; P.seed = h->prm.seed;
+    P.maxDepth = h->prm.max_depth; P.rrDepth = h->prm.rr_depth; P.strictNormals = h->prm.strict_normals; P.hideEmitters = h->prm.hide_emitters;
+    P.isBuilt = h->isBuilt ? 1 : 0; P.lossMode = h->prm.bsdf_sampling_fraction_loss; P.fixedFraction = h->prm.bsdf_sampling_fraction;
+    P.sceneSmemBytes = h->sceneSmemBytes;
+    PathState A = path_state(h->dStateA.p, h->pathCapacity), B = path_state(h->dStateB.p, h->pathCapacity);
+    const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK));
+    int lastDepth = 0;
+    for (int depth = 1; depth <= h->maxBounces; ++depth) {
+        P.depth = depth; P.in = (depth & 1) ? B : A; P.out = (depth & 1) ? A : B;
+        P.liveIn = h->dLive.p + (depth - 1); P.liveOut = h->dLive.p + depth;
+        const int k = std::min(depth - 1, h->nSlabs - 1);
+        P.slab = slab_at(h, k);
+        const int rec = (depth - 1 < h->nSlabs) ? record : 0;
+        h->tic(PPG_K_BOUNCE);
+        if (depth == 1) launch_bounce<true>(h, P, rec, grid); else launch_bounce<false>(h, P, rec, grid);
+        h->toc();
+        lastDepth = depth;
+    }
+    {   // survivors of the bounce cap (maxDepth == -1 only)
+        const PathState last = (lastDepth & 1) ? A : B;
+        flush_kernel<<<std::max(grid / 4, 1), PPG_BLOCK, 0, h->stream>>>(last, h->dLive.p + lastDepth, h->dLiFinal.p); h->launches++;
+    }
+    if (record) {
+        CommitParams C;
+        C.tree = tree_view(h); C.slab0 = slab_at(h, 0); C.slabStride = h->pathCapacity; C.liveCounts = h->dLive.p; C.liFinal = h->dLiFinal.p;
+        C.spatialFilter = h->prm.spatial_filter; C.directionalFilter = h->prm.directional_filter;
+        C.lossMode = h->isBuilt ? h->prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE;       // GP:2152
+        C.statisticalWeight = 1.0f; C.seed = h->prm.seed; C.snodes = h->dSnodes.p;
+        dim3 g(std::min<int>(h->gridCommit, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK)), h->nSlabs);
+        h->tic(PPG_K_COMMIT);
+        if (record == 1) commit_kernel<1><<<g, PPG_BLOCK, 0, h->stream>>>(C); else commit_kernel<2><<<g, PPG_BLOCK, 0, h->stream>>>(C);
+        h->toc(); h->launches++;
+        if (C.lossMode != PPG_LOSS_NONE) {
+            if (h->allreduce && h->world > 1) {
+                // replicas must take identical optimiser steps: sum the gradient accumulators over ranks first
+                float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;
+                pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->dAdamG.p, h->dAdamW.p, h->hNodes, 0); h->launches++;
+                CK(cudaStreamSynchronize(h->stream));
+                if (h->allreduce(h->allreduceUser, tail + h->hNodes, 2 * (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+                CK(cudaMemcpyAsync(h->dAdamG.p, tail + h->hNodes, 4 * (size_t) h->hNodes, cudaMemcpyDeviceToDevice, h->stream));
+                CK(cudaMemcpyAsync(h->dAdamW.p, tail + 2 * (size_t) h->hNodes, 4 * (size_t) h->hNodes, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            h->tic(PPG_K_ADAM); adam_kernel<<<h->numSMs * 2, 256, 0, h->stream>>>(maint(h), h->dAdamG.p, h->dAdamW.p, 64); h->toc(); h->launches++;
+        }
+    }
+    h->tic(PPG_K_FILM);
+    film_kernel<<<std::min<int>(h->numSMs * 8, (int) ((h->nLocalPixels + PPG_BLOCK - 1) / PPG_BLOCK)), PPG_BLOCK, 0, h->stream>>>(
+        h->dLiFinal.p, h->dPixelMap.p, h->nLocalPixels, (uint32_t) h->prm.spp_per_pass, (uint32_t) nPasses, h->W, h->dImage.p, h->dSqImage.p);
+    h->toc(); h->launches++;
+    CK(cudaGetLastError());
+    return PPG_OK;
+}
+
+// performRenderPasses, GP:1210-1329
+static int perform_render_passes(ppg_integrator *h, float &variance, int numPasses, ppg_iteration_stats &st) {
+    const size_t npx = (size_t) h->W * h->H;
+    CK(cudaMemsetAsync(h->dImage.p, 0, sizeof(float4) * npx, h->stream));
+    CK(cudaMemsetAsync(h->dSqImage.p, 0, sizeof(float4) * npx, h->stream));
+    CK(cudaMemsetAsync(h->dCounters.p, 0, 32, h->stream));
+    const auto t0 = std::chrono::steady_clock::now();
+    CK(cudaEventRecord(h->evA, h->stream));
+    const size_t perPass = (size_t) h->nLocalPixels * h->prm.spp_per_pass;
+    const int maxBatch = (int) std::max<size_t>(1, perPass ? h->pathCapacity / perPass : 1);
+    int local = 0; int rcode = PPG_OK;
+    while (local < numPasses) {
+        const int nb = std::min(maxBatch, numPasses - local);
+        int rc = render_batch(h, nb);
+        if (rc) return rc;
+        h->passesRendered += nb; local += nb;
+        bool shouldAbort = false;
+        if (h->prm.budget_type == PPG_BUDGET_SECONDS) {              // GP:1259-1262, checked per batch
+            CK(cudaStreamSynchronize(h->stream));
+            float el = elapsed_s(h->startTime);
+            rc = sync_scalar(h, &el); if (rc) return rc;
+            shouldAbort = (int) el > h->prm.budget;
+        }
+        if (h->cancelled.load()) { rcode = PPG_ERR_CANCELLED; shouldAbort = true; }
+        if (shouldAbort) break;
+    }
+    add_image_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dFilm.p, h->dImage.p, npx); h->launches++;   // film->put(block), renderproc.cpp:143-151
+    if (h->prm.sample_combination == PPG_COMB_INVERSEVAR) {            // GP:1292-1296: keep the iteration's image
+        DevBuf<float4> *img = new DevBuf<float4>();
+        CK(img->alloc(npx));
+        CK(cudaMemcpyAsync(img->p, h->dImage.p, sizeof(float4) * npx, cudaMemcpyDeviceToDevice, h->stream));
+        h->images.push_back(img);
+        if (h->images.size() > 4) { delete h->images.front(); h->images.erase(h->images.begin()); }
+    }
+    // variance, GP:1298-1319
+    const int N = local * h->prm.spp_per_pass;
+    CK(cudaMemsetAsync(h->dVar.p, 0, 8, h->stream));
+    if (h->nLocalPixels)
+        variance_kernel<<<std::min<int>(h->numSMs * 4, (int) ((h->nLocalPixels + PPG_BLOCK - 1) / PPG_BLOCK)), PPG_BLOCK, 0, h->stream>>>(
+            h->dImage.p, h->dSqImage.p, h->dPixelMap.p, h->nLocalPixels, h->W, (float) N, h->dVar.p);
+    h->launches++;
+    double num = 0; unsigned long long cnt[4];
+    CK(cudaMemcpyAsync(&num, h->dVar.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cnt, h->dCounters.p, 32, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->evB, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->evA, h->evB); h->deviceMs += ms;
+    h->resolve_timers();
+    if (h->allreduce && h->world > 1) {
+        float *slot = h->dTrain.p + h->dTrain.n - 16;
+        const float mine = (float) num;
+        CK(cudaMemcpy(slot, &mine, 4, cudaMemcpyHostToDevice));
+        if (h->allreduce(h->allreduceUser, slot, 1) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+        float total = 0; CK(cudaMemcpy(&total, slot, 4, cudaMemcpyDeviceToHost)); num = total;
+    }
+    variance = (float) (num / ((double) h->W * h->H * (N - 1)));
+    if (h->prm.sample_combination == PPG_COMB_INVERSEVAR) { h->variances.push_back(variance); if (h->variances.size() > 4) h->variances.erase(h->variances.begin()); }
+    st.seconds += elapsed_s(t0); st.passes += local; st.variance = variance; st.total_passes = h->passesRendered;
+    st.vertices += cnt[0]; st.paths += (uint64_t) local * perPass; st.recorded_vertices += cnt[1];
+    if (cnt[1]) st.s_tree_depth_avg = (double) cnt[2] / (double) cnt[1];
+    h->stats.total_vertices += cnt[0]; h->stats.total_paths += (uint64_t) local * perPass;
+    return rcode;
+}
+
+static ppg_iteration_stats &iter_stats(ppg_integrator *h) {
+    ppg_iteration_stats &st = h->stats.iterations[std::min(h->iter, PPG_MAX_ITERATIONS - 1)];
+    memset(&st, 0, sizeof(st)); st.iteration = h->iter;
+    return st;
+}
+static int clear_film(ppg_integrator *h) { CK(cudaMemsetAsync(h->dFilm.p, 0, sizeof(float4) * (size_t) h->W * h->H, h->stream)); return PPG_OK; }
+
+// renderSPP, GP:1342-1426
+static int render_spp(ppg_integrator *h) {
+    const int nPasses = (int) std::ceil((size_t) h->prm.budget / (float) h->prm.spp_per_pass);
+    float currentVarAtEnd = std::numeric_limits<float>::infinity();
+    while (h->passesRendered < nPasses) {
+        const int sppRendered = h->passesRendered * h->prm.spp_per_pass;
+        int remainingPasses = nPasses - h->passesRendered;
+        int passesThisIteration = std::min(remainingPasses, 1 << std::min(h->iter, 30));
+        if (remainingPasses - passesThisIteration < 2 * passesThisIteration) passesThisIteration = remainingPasses;
+        h->isFinalIter = passesThisIteration >= remainingPasses;
+        ppg_iteration_stats &st = iter_stats(h);
+        int rc = clear_film(h); if (rc) return rc;
+        auto t0 = std::chrono::steady_clock::now();
+        rc = reset_sd_tree(h); if (rc) return rc;
+        CK(cudaStreamSynchronize(h->stream)); st.reset_seconds = elapsed_s(t0);
+        float variance = 0;
+        rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
+        const float lastVarAtEnd = currentVarAtEnd;
+        currentVarAtEnd = passesThisIteration * variance / remainingPasses;
+        remainingPasses -= passesThisIteration;
+        if (h->prm.sample_combination == PPG_COMB_AUTOMATIC && remainingPasses > 0 &&
+            (remainingPasses < passesThisIteration || (sppRendered > 256 && currentVarAtEnd > lastVarAtEnd))) {
+            h->isFinalIter = true;
+            rc = perform_render_passes(h, variance, remainingPasses, st); if (rc) return rc;
+        }
+        st.is_final = h->isFinalIter;
+        t0 = std::chrono::steady_clock::now();
+        rc = build_sd_tree(h, st); if (rc) return rc;
+        st.build_seconds = elapsed_s(t0);
+        if (h->prm.dump_sd_tree && !h->isFinalIter) { /* dumpSDTree needs a destination file: use ppg_dump_sdtree */ }
+        ++h->iter; h->stats.n_iterations = std::min(h->iter, PPG_MAX_ITERATIONS);
+    }
+    return PPG_OK;
+}
+
+// renderTime, GP:1434-1514
+static int render_time(ppg_integrator *h) {
+    const float nSeconds = h->prm.budget;
+    float currentVarAtEnd = std::numeric_limits<float>::infinity(), elapsedSeconds = 0;
+    while (elapsedSeconds < nSeconds) {
+        const int sppRendered = h->passesRendered * h->prm.spp_per_pass;
+        float remainingTime = nSeconds - elapsedSeconds;
+        const int passesThisIteration = 1 << std::min(h->iter, 30);
+        ppg_iteration_stats &st = iter_stats(h);
+        const auto startIter = std::chrono::steady_clock::now();
+        int rc = clear_film(h); if (rc) return rc;
+        rc = reset_sd_tree(h); if (rc) return rc;
+        CK(cudaStreamSynchronize(h->stream)); st.reset_seconds = elapsed_s(startIter);
+        float variance = 0;
+        rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
+        float secondsIter = elapsed_s(startIter);
+        rc = sync_scalar(h, &secondsIter); if (rc) return rc;
+        const float lastVarAtEnd = currentVarAtEnd;
+        currentVarAtEnd = secondsIter * variance / remainingTime;
+        remainingTime -= secondsIter;
+        if (h->prm.sample_combination == PPG_COMB_AUTOMATIC && remainingTime > 0 &&
+            (remainingTime < secondsIter || (sppRendered > 256 && currentVarAtEnd > lastVarAtEnd))) {
+            h->isFinalIter = true;
+            do {
+                rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
+                elapsedSeconds = elapsed_s(h->startTime);
+                rc = sync_scalar(h, &elapsedSeconds); if (rc) return rc;
+            } while (elapsedSeconds < nSeconds);
+        }
+        st.is_final = h->isFinalIter;
+        const auto t0 = std::chrono::steady_clock::now();
+        rc = build_sd_tree(h, st); if (rc) return rc;
+        st.build_seconds = elapsed_s(t0);
+        ++h->iter; h->stats.n_iterations = std::min(h->iter, PPG_MAX_ITERATIONS);
+        elapsedSeconds = elapsed_s(h->startTime);
+        rc = sync_scalar(h, &elapsedSeconds); if (rc) return rc;
+    }
+    return PPG_OK;
+}
+
+// render, GP:1516-1585
+extern "C" int ppg_render_device(ppg_integrator *h, float **rgb_dev, ppg_stats *stats) {
+    if (!h) return fail(PPG_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->haveScene) return fail(PPG_ERR_NO_SCENE, "ppg_render called before ppg_set_scene");
+    CK(cudaSetDevice(h->device));
+    h->cancelled.store(false);
+    const auto wall0 = std::chrono::steady_clock::now();
+    memset(&h->stats, 0, sizeof(h->stats)); h->launches = 0; h->deviceMs = 0; h->evUsed = 0;
+    CK(cudaEventRecord(h->evRender0, h->stream));
+    int rc = init_tree(h); if (rc) return rc;                                   // m_sdTree = new STree(scene->getAABB()), GP:1519
+    rc = ensure_wavefront(h); if (rc) return rc;
+    h->iter = 0; h->isFinalIter = false; h->isBuilt = false; h->passesRendered = 0;
+    for (auto *b : h->images) delete b;
+    h->images.clear(); h->variances.clear();
+    rc = clear_film(h); if (rc) return rc;
+    h->startTime = std::chrono::steady_clock::now();
+    rc = h->prm.budget_type == PPG_BUDGET_SPP ? render_spp(h) : render_time(h);
+    if (rc != PPG_OK && rc != PPG_ERR_CANCELLED) return rc;
+    const size_t npx = (size_t) h->W * h->H;
+    const int blocks = h->numSMs * 4;
+    if (h->prm.sample_combination == PPG_COMB_INVERSEVAR && !h->images.empty()) {   // GP:1567-1582
+        float totalWeight = 0;
+        for (float v : h->variances) totalWeight += 1.0f / v;
+        CK(cudaMemsetAsync(h->dRgb.p, 0, 12 * npx, h->stream));
+        for (size_t i = 0; i < h->images.size(); ++i) {
+            develop_kernel<<<blocks, 256, 0, h->stream>>>(h->images[i]->p, h->dRgb.p, npx, 1.0f / h->variances[i] / totalWeight, 1); h->launches++;
+        }
+    } else {
+        develop_kernel<<<blocks, 256, 0, h->stream>>>(h->dFilm.p, h->dRgb.p, npx, 1.0f, 0); h->launches++;
+    }
+    CK(cudaEventRecord(h->evRender1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    { float ms = 0; cudaEventElapsedTime(&ms, h->evRender0, h->evRender1); h->stats.render_device_ms = ms; }
+    if (h->allreduce && h->world > 1) {    // disjoint tiles: summing the zero-padded frames assembles the film on every rank
+        if (h->allreduce(h->allreduceUser, h->dRgb.p, 3 * npx) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+    }
+    CK(cudaGetLastError());
+    h->stats.total_passes = h->passesRendered;
+    h->stats.render_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    h->stats.device_seconds = h->deviceMs / 1000.0;
+    h->stats.final_variance = h->stats.n_iterations ? h->stats.iterations[h->stats.n_iterations - 1].variance : 0;
+    h->stats.kernel_launches = h->launches;
+    if (stats) *stats = h->stats;
+    if (rgb_dev) *rgb_dev = h->dRgb.p;
+    return rc;
+}
+
+extern "C" int ppg_render(ppg_integrator *h, float *rgb_out, ppg_stats *stats) {
+    float *dev = nullptr;
+    const int rc = ppg_render_device(h, &dev, stats);
+    if (rc != PPG_OK && rc != PPG_ERR_CANCELLED) return rc;
+    if (rgb_out) CK(cudaMemcpy(rgb_out, dev, 12 * (size_t) h->W * h->H, cudaMemcpyDeviceToHost));
+    return rc;
+}
+
+extern "C" int ppg_get_moment_images(ppg_integrator *h, float *sum_rgbw, float *sumsq_rgbw) {
+    if (!h || !h->haveScene) return fail(PPG_ERR_NO_SCENE, "no scene");
+    CK(cudaSetDevice(h->device));
+    const size_t npx = (size_t) h->W * h->H;
+    if (sum_rgbw) CK(cudaMemcpy(sum_rgbw, h->dImage.p, 16 * npx, cudaMemcpyDeviceToHost));
+    if (sumsq_rgbw) CK(cudaMemcpy(sumsq_rgbw, h->dSqImage.p, 16 * npx, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+
+// dumpSDTree wire format (GP:1191-1208, 699-711, 945-951): 16 floats camera matrix, then for every leaf with
+// sampling weight > 0, in forEachLeaf order (child 0 before child 1): pos, size, mean, u64 weight, u64 nNodes,
+// nNodes x 4 x (f32 sum, u16 child)
+extern "C" int ppg_dump_sdtree(ppg_integrator *h, const char *path) {
+    if (!h || !path) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h->haveScene || h->capNodes == 0) return fail(PPG_ERR_NO_SCENE, "no SD-tree yet");
+    CK(cudaSetDevice(h->device));
+    const uint32_t n = h->hNodes;
+    std::vector<uint2> sn(n); std::vector<float4> la(n); std::vector<float> ssum(n), sw(n); std::vector<uint32_t> scnt(n);
+    CK(cudaMemcpy(sn.data(), h->dSnodes.p, sizeof(uint2) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(la.data(), h->dLeafA.p, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ssum.data(), h->dSampSum.p, 4 * (size_t) n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sw.data(), h->dSampWeight.p, 4 * (size_t) n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(scnt.data(), h->dSampCount.p, 4 * (size_t) n, cudaMemcpyDeviceToHost));
+    std::vector<SampNode> pool(std::max<size_t>(h->hTotalBuild, 1));
+    CK(cudaMemcpy(pool.data(), h->dSamp.p, sizeof(SampNode) * pool.size(), cudaMemcpyDeviceToHost));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(PPG_ERR_IO, std::string("cannot open ") + path);
+    float cm[16];
+    const Camera &c = h->cam;   // camera-to-world matrix, row-major (GP:1197-1205)
+    cm[0] = c.left.x; cm[1] = c.up.x; cm[2] = c.dir.x; cm[3] = c.o.x; cm[4] = c.left.y; cm[5] = c.up.y; cm[6] = c.dir.y; cm[7] = c.o.y;
+    cm[8] = c.left.z; cm[9] = c.up.z; cm[10] = c.dir.z; cm[11] = c.o.z; cm[12] = 0; cm[13] = 0; cm[14] = 0; cm[15] = 1;
+    fwrite(cm, 4, 16, f);
+    struct E { uint32_t n; float p[3], s[3]; int axis; };
+    std::vector<E> st; E root; root.n = 0; root.axis = 0;
+    for (int i = 0; i < 3; ++i) { root.p[i] = h->aabbMin[i]; root.s[i] = h->extent[i]; }
+    st.push_back(root);
+    while (!st.empty()) {
+        E e = st.back(); st.pop_back();
+        if (sn[e.n].x == 0u) {
+            if (!(sw[e.n] > 0)) continue;
+            const float mean = (1 / (3.14159265358979323846f * 4 * sw[e.n])) * ssum[e.n];
+            fwrite(e.p, 4, 3, f); fwrite(e.s, 4, 3, f); fwrite(&mean, 4, 1, f);
+            const uint64_t w64 = (uint64_t) sw[e.n], nn = scnt[e.n];
+            fwrite(&w64, 8, 1, f); fwrite(&nn, 8, 1, f);
+            uint32_t base; memcpy(&base, &la[e.n].x, 4);
+            for (uint32_t k = 0; k < scnt[e.n]; ++k) {
+                const SampNode &q = pool[base + k];
+                const float s4[4] = {q.sums.x, q.sums.y, q.sums.z, q.sums.w};
+                const uint16_t c4[4] = {(uint16_t) (q.children.x & 0xffff), (uint16_t) (q.children.x >> 16), (uint16_t) (q.children.y & 0xffff), (uint16_t) (q.children.y >> 16)};
+                for (int j = 0; j < 4; ++j) { fwrite(&s4[j], 4, 1, f); fwrite(&c4[j], 2, 1, f); }
+            }
+        } else {
+            E a = e, b = e;
+            a.s[e.axis] = b.s[e.axis] = e.s[e.axis] / 2; b.p[e.axis] += b.s[e.axis];
+            a.axis = b.axis = (e.axis + 1) % 3; a.n = sn[e.n].x; b.n = sn[e.n].y;
+            st.push_back(b); st.push_back(a);
+        }
+    }
+    fclose(f);
+    return PPG_OK;
+}
+
+// ------------------------------------------------------------------ kernel-level entry points on caller-supplied tree arrays
+namespace {
+struct ReplayRng { const float *v; uint32_t n, i; __device__ float next1D() { return i < n ? v[i++] : 0.5f; } };
+
+__global__ void op_pdf_kernel(const SampNode *pool, const uint32_t *first, const float *tsum, const float *tweight, const uint32_t *qt, const float *qd, size_t n, float *out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const uint32_t t = qt[i];
+        float mean = 0.f; if (tweight[t] != 0.f) mean = (1.f / (PPG_PI * 4.f * tweight[t])) * tsum[t];
+        out[i] = dtree_pdf(pool + first[t], mean > 0.f, dir_to_canonical(f3(qd[3 * i], qd[3 * i + 1], qd[3 * i + 2])));
+    }
+}
+__global__ void op_sample_kernel(const SampNode *pool, const uint32_t *first, const float *tsum, const float *tweight, const uint32_t *qt, const float *rnd, size_t stride, size_t n, float *out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const uint32_t t = qt[i];
+        float mean = 0.f; if (tweight[t] != 0.f) mean = (1.f / (PPG_PI * 4.f * tweight[t])) * tsum[t];
+        ReplayRng r{rnd + stride * i, (uint32_t) stride, 0u};
+        const float3 d = canonical_to_dir(dtree_sample(pool + first[t], mean > 0.f, r));
+        out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+    }
+}
+__global__ void op_record_kernel(TreeView T, const uint32_t *rt, const float *rd, const float *rrad, const float *rpdf, const float *rw, size_t n, int filter) {
+    const size_t nPad = (n + 31) / 32 * 32;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nPad; i += (size_t) gridDim.x * blockDim.x) {
+        const bool ok = i < n;
+        const uint32_t t = ok ? rt[i] : 0u; const float w = ok ? rw[i] : 0.f;
+        const bool wOk = ok && isfinite(w) && w > 0.f;
+        warp_aggregated_add(T.bweight, t, w, wOk);
+        if (wOk) {
+            const float4 la = T.leafA[t];
+            dtree_record_irradiance(T.bchildren, T.bsums, __float_as_uint(la.y), dir_to_canonical(f3(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2])), rrad[i] / rpdf[i], w, filter);
+        }
+    }
+}
+__global__ void op_lookup_kernel(const uint2 *snodes, float3 mn, float3 ext, const float *pts, size_t n, uint32_t *leaf, float *size) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        int lv; const uint32_t l = stree_lookup(snodes, mn, ext, f3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), lv);
+        leaf[i] = l;
+        const float3 v = voxel_size(ext, lv);
+        size[3 * i] = v.x; size[3 * i + 1] = v.y; size[3 * i + 2] = v.z;
+    }
+}
+template <class T> struct Up {
+    DevBuf<T> b;
+    int up(const T *host, size_t n) { if (b.alloc(std::max<size_t>(n, 1)) != cudaSuccess) return 1; return n ? cudaMemcpy(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess : 0; }
+};
+static int op_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PPG_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)"); }
+    if (device < 0) device = 0;
+    if (device >= ndev) return fail(PPG_ERR_NO_DEVICE, "device index out of range");
+    CK(cudaSetDevice(device));
+    return PPG_OK;
+}
+static std::vector<SampNode> to_pool(const float *sums, const uint16_t *children, size_t n) {
+    std::vector<SampNode> pool(n);
+    for (size_t i = 0; i < n; ++i) {
+        pool[i].sums = make_float4(sums[4 * i], sums[4 * i + 1], sums[4 * i + 2], sums[4 * i + 3]);
+        pool[i].children = make_uint2((uint32_t) children[4 * i] | ((uint32_t) children[4 * i + 1] << 16), (uint32_t) children[4 * i + 2] | ((uint32_t) children[4 * i + 3] << 16));
+        pool[i].pad = make_uint2(0u, 0u);
+    }
+    return pool;
+}
+}  // namespace
+
+extern "C" int ppg_op_dtree_pdf(int device, const float *sums, const uint16_t *children, size_t n_nodes, const uint32_t *tree_first_node,
+                                const float *tree_sum, const float *tree_weight, size_t n_trees, const uint32_t *query_tree, const float *query_dir,
+                                size_t n, float *pdf_out) {
+    int rc = op_device(device); if (rc) return rc;
+    std::vector<SampNode> pool = to_pool(sums, children, n_nodes);
+    Up<SampNode> dp; Up<uint32_t> df, dq; Up<float> ds, dw, dd; DevBuf<float> out;
+    if (dp.up(pool.data(), n_nodes) || df.up(tree_first_node, n_trees) || ds.up(tree_sum, n_trees) || dw.up(tree_weight, n_trees) || dq.up(query_tree, n) || dd.up(query_dir, 3 * n))
+        return fail(PPG_ERR_CUDA, "upload failed");
+    CK(out.alloc(std::max<size_t>(n, 1)));
+    if (n) op_pdf_kernel<<<296, 256>>>(dp.b.p, df.b.p, ds.b.p, dw.b.p, dq.b.p, dd.b.p, n, out.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(pdf_out, out.p, 4 * n, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+extern "C" int ppg_op_dtree_sample(int device, const float *sums, const uint16_t *children, size_t n_nodes, const uint32_t *tree_first_node,
+                                   const float *tree_sum, const float *tree_weight, size_t n_trees, const uint32_t *query_tree, const float *rnd,
+                                   size_t rnd_stride, size_t n, float *dir_out) {
+    int rc = op_device(device); if (rc) return rc;
+    std::vector<SampNode> pool = to_pool(sums, children, n_nodes);
+    Up<SampNode> dp; Up<uint32_t> df, dq; Up<float> ds, dw, dr; DevBuf<float> out;
+    if (dp.up(pool.data(), n_nodes) || df.up(tree_first_node, n_trees) || ds.up(tree_sum, n_trees) || dw.up(tree_weight, n_trees) || dq.up(query_tree, n) || dr.up(rnd, rnd_stride * n))
+        return fail(PPG_ERR_CUDA, "upload failed");
+    CK(out.alloc(std::max<size_t>(3 * n, 1)));
+    if (n) op_sample_kernel<<<296, 256>>>(dp.b.p, df.b.p, ds.b.p, dw.b.p, dq.b.p, dr.b.p, rnd_stride, n, out.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(dir_out, out.p, 12 * n, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+extern "C" int ppg_op_dtree_record(int device, float *sums_inout, const uint16_t *children, size_t n_nodes, const uint32_t *tree_first_node,
+                                   float *tree_weight_inout, size_t n_trees, const uint32_t *rec_tree, const float *rec_dir, const float *rec_radiance,
+                                   const float *rec_wo_pdf, const float *rec_weight, size_t n, int filter) {
+    int rc = op_device(device); if (rc) return rc;
+    std::vector<uint2> bch(n_nodes);
+    for (size_t i = 0; i < n_nodes; ++i)
+        bch[i] = make_uint2((uint32_t) children[4 * i] | ((uint32_t) children[4 * i + 1] << 16), (uint32_t) children[4 * i + 2] | ((uint32_t) children[4 * i + 3] << 16));
+    std::vector<float4> la(n_trees);
+    for (size_t t = 0; t < n_trees; ++t) { uint32_t b = tree_first_node[t]; float fb; memcpy(&fb, &b, 4); la[t] = make_float4(fb, fb, 0.f, 0.f); }
+    Up<uint2> dch; Up<float4> dla; Up<float> dsums, dwt, dd, drad, dpdf, dw; Up<uint32_t> drt;
+    if (dch.up(bch.data(), n_nodes) || dla.up(la.data(), n_trees) || dsums.up(sums_inout, 4 * n_nodes) || dwt.up(tree_weight_inout, n_trees) || drt.up(rec_tree, n) ||
+        dd.up(rec_dir, 3 * n) || drad.up(rec_radiance, n) || dpdf.up(rec_wo_pdf, n) || dw.up(rec_weight, n))
+        return fail(PPG_ERR_CUDA, "upload failed");
+    TreeView T; memset(&T, 0, sizeof(T));
+    T.leafA = dla.b.p; T.bchildren = dch.b.p; T.bsums = reinterpret_cast<float4 *>(dsums.b.p); T.bweight = dwt.b.p;
+    if (n) op_record_kernel<<<296, 256>>>(T, drt.b.p, dd.b.p, drad.b.p, dpdf.b.p, dw.b.p, n, filter);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(sums_inout, dsums.b.p, 16 * n_nodes, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tree_weight_inout, dwt.b.p, 4 * n_trees, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+extern "C" int ppg_op_stree_lookup(int device, const uint32_t *node_children, size_t n_nodes, const float aabb_min[3], const float aabb_extent[3],
+                                   const float *points, size_t n, uint32_t *leaf_out, float *size_out) {
+    int rc = op_device(device); if (rc) return rc;
+    Up<uint2> dn; Up<float> dp; DevBuf<uint32_t> dl; DevBuf<float> dsz;
+    if (dn.up(reinterpret_cast<const uint2 *>(node_children), n_nodes) || dp.up(points, 3 * n)) return fail(PPG_ERR_CUDA, "upload failed");
+    CK(dl.alloc(std::max<size_t>(n, 1))); CK(dsz.alloc(std::max<size_t>(3 * n, 1)));
+    if (n) op_lookup_kernel<<<296, 256>>>(dn.b.p, make_float3(aabb_min[0], aabb_min[1], aabb_min[2]), make_float3(aabb_extent[0], aabb_extent[1], aabb_extent[2]), dp.b.p, n, dl.p, dsz.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(leaf_out, dl.p, 4 * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(size_out, dsz.p, 12 * n, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}

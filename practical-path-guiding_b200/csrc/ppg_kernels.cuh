@@ -1,0 +1,696 @@
+// ppg_kernels.cuh -- the wavefront kernels of the guided path tracer (sm_100a).
+//
+// One pass-batch of N paths is processed as
+//     bounce<FIRST>  (ray generation + bounce 1)          GP:1613-1637 + one turn of the Li loop
+//     bounce         (one launch per further path depth)  GP:1798-2146
+//     commit         (all recorded vertices -> building trees)   GP:2150-2154 -> 1730-1768 -> 575-584
+//     film           (per-pixel sum and sum of squares)   GP:1633-1634, imageblock.h:127-186
+// Live paths are compacted between bounces (warp ballot + block prefix + one atomic per block),
+// path state is SoA float4 (5 x 16 B per path, coalesced), the scene (CBOX: ~9 KB) is staged in
+// shared memory, the read-only sampling trees go through the read-only/L1 path.
+#pragma once
+#include "ppg_device.cuh"
+
+namespace ppg {
+
+#define PPG_BLOCK 256
+#define PPG_MAX_VERTICES 32         // MAX_NUM_VERTICES, GP:1771
+#define PPG_INVALID 0xFFFFFFFFu
+
+// ------------------------------------------------------------------ SoA buffers
+struct PathState {      // 5 x float4 per path
+    float4 *s0;         // o.xyz, d.x
+    float4 *s1;         // d.yz, throughput.xy
+    float4 *s2;         // throughput.z, eta, Li.xy
+    float4 *s3;         // Li.z, bits(pathId), bits(rng.lo), bits(rng.hi)
+    float4 *s4;         // bits(sampleIndex.lo), bits(sampleIndex.hi), bits(nVertices | flags<<8), rrRecip
+};
+#define PPG_FLAG_DYING 1u            // lost Russian roulette: trace one more ray for the emitter lookup, then stop (GP:2078-2091 precede GP:2123-2142)
+
+struct VertexSlab {     // one slab per path depth; entry i belongs to the i-th live path of that bounce
+    float4 *v0;         // d.xyz, woPdf
+    float4 *v1;         // throughput.xyz, bits(leafNode)
+    float4 *v2;         // LiPrefix.xyz, bits(pathId | isDelta<<31)   (pathId == PPG_INVALID: no vertex)
+    float4 *v3;         // bsdfVal.xyz, bsdfPdf                       (full mode only)
+    float4 *v4;         // o.xyz, dTreePdf                            (full mode only)
+    float4 *v5;         // bits(sampleIndex.lo), bits(sampleIndex.hi), bits(streeLevels | ordinal<<8), 0   (full mode only)
+};
+
+struct RenderParams {
+    SceneView scene; Camera cam; TreeView tree;
+    PathState in, out;
+    VertexSlab slab;               // slab of the CURRENT depth (already offset by the host)
+    float4 *liFinal;               // per path: Li.rgb, 1
+    const uint32_t *pixelMap;      // local pixel -> x | y<<16
+    const uint32_t *liveIn; uint32_t *liveOut;      // device counters
+    unsigned long long *counters;  // [0]: rays traced, [1]: vertices recorded, [2]: sum of S-tree levels over recorded vertices
+    uint32_t nPaths;               // paths of this batch (FIRST kernel)
+    uint32_t nLocalPixels, spp;
+    uint64_t passBase;             // global index of the first pass in the batch
+    uint64_t seed;
+    int depth;                     // rRec.depth of this bounce (1 = primary hit)
+    int maxDepth, rrDepth;
+    int strictNormals, hideEmitters;
+    int isBuilt;                   // m_isBuilt: guide with the sampling trees
+    int lossMode;                  // bsdfSamplingFractionLoss
+    float fixedFraction;           // bsdfSamplingFraction
+    uint32_t sceneSmemBytes;       // >0: stage the scene into shared memory
+};
+
+// ------------------------------------------------------------------ scene staging
+// Copies accel | geom | meta | bvh | bsdf | radiance into dynamic shared memory (16 B granules) and
+// returns a view whose (generic) pointers address the shared copy.
+__device__ __forceinline__ SceneView stage_scene(const SceneView &g, float4 *smem) {
+    SceneView s = g;
+    uint32_t off = 0;
+    auto copy = [&](const float4 *src, uint32_t n) {
+        float4 *dst = smem + off;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        off += n;
+        return dst;
+    };
+    s.accel = copy(g.accel, 3 * g.nTris);
+    s.geom = copy(g.geom, 6 * g.nTris);
+    s.meta = reinterpret_cast<const int4 *>(copy(reinterpret_cast<const float4 *>(g.meta), g.nTris));
+    s.bvh = copy(g.bvh, 2 * g.nBvhNodes);
+    s.bsdf = copy(g.bsdf, 2 * g.nBsdfs);
+    s.radiance = copy(g.radiance, g.nEmitters);
+    __syncthreads();
+    return s;
+}
+
+// block-wide compaction: returns the output slot of this thread (valid when `alive`); one atomic per block
+__device__ __forceinline__ uint32_t block_compact(bool alive, uint32_t *counter, uint32_t *sWarp /* [PPG_BLOCK/32 + 1] */) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sWarp[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < PPG_BLOCK / 32; ++w) { const uint32_t c = sWarp[w]; sWarp[w] = total; total += c; }
+        sWarp[PPG_BLOCK / 32] = total ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    const uint32_t slot = sWarp[PPG_BLOCK / 32] + sWarp[warp] + __popc(ballot & ((1u << lane) - 1u));
+    __syncthreads();   // sWarp is reused by the next loop iteration
+    return slot;
+}
+
+// ------------------------------------------------------------------ the bounce kernel
+// FIRST: generate the camera ray (renderBlock, GP:1613-1632) instead of loading a path state.
+// RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
+//         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
+template <bool FIRST, int RECORD>
+__global__ void __launch_bounds__(PPG_BLOCK) bounce_kernel(const RenderParams P) {
+    extern __shared__ float4 smemScene[];
+    __shared__ uint32_t sWarp[PPG_BLOCK / 32 + 1];
+    const SceneView sc = P.sceneSmemBytes ? stage_scene(P.scene, smemScene) : P.scene;
+    const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
+    unsigned long long raysLocal = 0, recLocal = 0, levelsLocal = 0;
+
+    for (uint32_t base = blockIdx.x * PPG_BLOCK; base < nIn; base += gridDim.x * PPG_BLOCK) {
+        const uint32_t i = base + threadIdx.x;
+        bool alive = i < nIn;
+        float3 o, d, thr, Li; float eta = 1.f, rrRecip = 1.f, mint, maxt;
+        uint32_t pathId = 0, nVertices = 0, flags = 0; uint64_t sampleIndex = 0;
+        Pcg32 rng; rng.state = 0; rng.inc = 1;
+        if (alive) {
+            if (FIRST) {
+                pathId = i;
+                const uint32_t perPass = P.nLocalPixels * P.spp;
+                const uint32_t passInBatch = i / perPass, rem = i - passInBatch * perPass;
+                const uint32_t lp = rem / P.spp, s = rem - lp * P.spp;
+                const uint32_t xy = __ldg(&P.pixelMap[lp]);
+                const uint32_t x = xy & 0xffffu, y = xy >> 16;
+                sampleIndex = (((P.passBase + passInBatch) * (uint64_t) P.cam.H + y) * (uint64_t) P.cam.W + x) * P.spp + s;
+                seed_path_rng(rng, P.seed, sampleIndex);
+                const float jx = rng.next1D(), jy = rng.next1D();                 // samplePos = pixel + next2D (GP:1620)
+                const float sx = ((float) x + jx) * (1.0f / (float) P.cam.W), sy = ((float) y + jy) * (1.0f / (float) P.cam.H);
+                const float3 nearP = f3((1.0f - 2.0f * sx) * P.cam.tanX, (1.0f - 2.0f * sy) * P.cam.tanY, 1.0f);
+                const float3 dl = normalize(nearP);
+                const float invZ = 1.0f / dl.z;
+                mint = P.cam.nearClip * invZ; maxt = P.cam.farClip * invZ;
+                o = P.cam.o;
+                d = P.cam.left * dl.x + P.cam.up * dl.y + P.cam.dir * dl.z;
+                thr = f3(1, 1, 1); Li = f3(0, 0, 0);
+            } else {
+                const float4 a = P.in.s0[i], b = P.in.s1[i], c = P.in.s2[i], e = P.in.s3[i], f = P.in.s4[i];
+                o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y); thr = f3(b.z, b.w, c.x); eta = c.y; Li = f3(c.z, c.w, e.x);
+                pathId = __float_as_uint(e.y);
+                rng.state = ((uint64_t) __float_as_uint(e.w) << 32) | __float_as_uint(e.z);
+                sampleIndex = ((uint64_t) __float_as_uint(f.y) << 32) | __float_as_uint(f.x);
+                rng.inc = (sampleIndex << 1) | 1u;
+                const uint32_t nf = __float_as_uint(f.z); nVertices = nf & 0xffu; flags = nf >> 8;
+                rrRecip = f.w;
+                // adaptive ray epsilon of rays leaving a surface (skdtree.cpp:125-128)
+                mint = PPG_EPSILON * fmaxf(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), PPG_EPSILON);
+                maxt = __int_as_float(0x7f800000);
+            }
+        }
+        bool wroteVertex = false;
+        if (alive) {
+            ++raysLocal;
+            Hit hit;
+            const bool found = bvh_intersect(sc, o, d, mint, maxt, hit);
+            bool cont = found;                                                     // miss: no environment emitter in scope (GP:1902-1914)
+            Its its;
+            if (cont) {
+                fill_its(sc, hit, d, its);
+                // emitted radiance: primary hit via EEmittedRadiance (GP:1917-1919), later hits via the `value`
+                // returned by rayIntersectAndLookForEmitter (GP:2078-2091; miWeight(woPdf, 0) == 1)
+                if (its.emitter >= 0 && (!FIRST || !P.hideEmitters)) {
+                    if (dot(its.shN, -d) > 0.f) {                                    // area.cpp:104-109
+                        const float4 r = sc.radiance[its.emitter];
+                        Li = Li + thr * f3(r.x, r.y, r.z);
+                    }
+                }
+                thr = thr * rrRecip;                                                // throughput /= successProb happens after L was recorded (GP:2141)
+                if (flags & PPG_FLAG_DYING) cont = false;
+                if (P.depth >= P.maxDepth && P.maxDepth != -1) cont = false;        // GP:1925
+            }
+            if (cont) {
+                const float wiDotGeoN = -dot(its.geoN, d);
+                if (wiDotGeoN * its.wi.z < 0.f && P.strictNormals) cont = false;     // GP:1929-1932
+            }
+            if (cont) {
+                const Bsdf bsdf = load_bsdf(sc, its.bsdf);
+                int levels; const uint32_t leaf = stree_lookup(P.tree.snodes, P.tree.aabbMin, P.tree.extent, its.p, levels);   // GP:1942-1944
+                const float4 la = __ldg(&P.tree.leafA[leaf]);
+                float frac = P.fixedFraction;
+                if (P.lossMode != 0) frac = logistic(la.z);                          // GP:1946-1949
+                // ---- sampleMat, GP:1650-1691
+                float woPdf, bsdfPdf, dTreePdf, bsEta = 1.f; float3 wo, bsdfWeight; bool isDelta = false;
+                float sx = rng.next1D(); const float sy = rng.next1D();
+                if (!P.isBuilt) {
+                    bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf);
+                    woPdf = bsdfPdf; dTreePdf = 0.f;
+                } else {
+                    const SampNode *tree = P.tree.samp + __float_as_uint(la.x);
+                    const bool valid = __float_as_uint(la.w) & 1u;
+                    float3 result; bool zero = false;
+                    if (sx < frac) {
+                        sx /= frac;
+                        result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf);
+                        if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0.f; zero = true; }
+                        else result = result * bsdfPdf;
+                    } else {
+                        const float2 c2 = dtree_sample(tree, valid, rng);
+                        wo = its.toLocal(canonical_to_dir(c2));
+                        result = bsdf_eval(bsdf, its.wi, wo);
+                    }
+                    if (zero) bsdfWeight = f3(0, 0, 0);
+                    else {   // pdfMat, GP:1693-1710
+                        bsdfPdf = bsdf_pdf(bsdf, its.wi, wo);
+                        if (!isfinite(bsdfPdf)) { woPdf = 0.f; dTreePdf = 0.f; }
+                        else {
+                            dTreePdf = dtree_pdf(tree, valid, dir_to_canonical(its.toWorld(wo)));
+                            woPdf = frac * bsdfPdf + (1.f - frac) * dTreePdf;
+                        }
+                        bsdfWeight = (woPdf == 0.f) ? f3(0, 0, 0) : result * (1.0f / woPdf);
+                    }
+                }
+                if (is_zero(bsdfWeight)) cont = false;                               // GP:2024-2025
+                float3 woW = f3(0, 0, 0);
+                if (cont) {
+                    woW = its.toWorld(wo);
+                    if (dot(its.geoN, woW) * wo.z <= 0.f && P.strictNormals) cont = false;   // GP:2028-2032
+                }
+                if (cont) {
+                    o = its.p; d = woW;
+                    thr = thr * bsdfWeight; eta *= bsEta;
+                    // ---- vertex record (GP:2093-2110); its radiance is Li_final - Li_prefix
+                    if (RECORD && (!isDelta || P.lossMode != 0) && nVertices < PPG_MAX_VERTICES && (1.f / woPdf > 0.f)) {
+                        P.slab.v0[i] = make_float4(d.x, d.y, d.z, woPdf);
+                        P.slab.v1[i] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(leaf));
+                        P.slab.v2[i] = make_float4(Li.x, Li.y, Li.z, __uint_as_float(pathId | (isDelta ? 0x80000000u : 0u)));
+                        if (RECORD == 2) {
+                            const float3 bv = bsdfWeight * woPdf;
+                            P.slab.v3[i] = make_float4(bv.x, bv.y, bv.z, bsdfPdf);
+                            P.slab.v4[i] = make_float4(o.x, o.y, o.z, dTreePdf);
+                            P.slab.v5[i] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
+                                                       __uint_as_float((uint32_t) levels | (nVertices << 8)), 0.f);
+                        }
+                        wroteVertex = true; ++nVertices; ++recLocal; levelsLocal += levels;
+                    }
+                    // ---- Russian roulette (GP:2123-2142); the decision takes effect after the next emitter lookup
+                    rrRecip = 1.f; flags = 0;
+                    if (P.depth >= P.rrDepth) {
+                        float successProb = 1.0f;
+                        if (!isDelta) {
+                            if (!P.isBuilt) successProb = max3(thr) * eta * eta;
+                            successProb = fmaxf(0.1f, fminf(successProb, 0.99f));
+                        }
+                        if (rng.next1D() >= successProb) flags |= PPG_FLAG_DYING;
+                        else rrRecip = 1.0f / successProb;
+                    }
+                }
+            }
+            if (!cont) {
+                P.liFinal[pathId] = make_float4(Li.x, Li.y, Li.z, 1.f);
+                alive = false;
+            }
+        }
+        if (RECORD && i < nIn && !wroteVertex) P.slab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
+        const uint32_t slot = block_compact(alive, P.liveOut, sWarp);
+        if (alive) {
+            P.out.s0[slot] = make_float4(o.x, o.y, o.z, d.x);
+            P.out.s1[slot] = make_float4(d.y, d.z, thr.x, thr.y);
+            P.out.s2[slot] = make_float4(thr.z, eta, Li.x, Li.y);
+            P.out.s3[slot] = make_float4(Li.z, __uint_as_float(pathId), __uint_as_float((uint32_t) rng.state), __uint_as_float((uint32_t) (rng.state >> 32)));
+            P.out.s4[slot] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
+                                         __uint_as_float(nVertices | (flags << 8)), rrRecip);
+        }
+    }
+    // per-warp reduction of the statistics counters
+    for (int off = 16; off; off >>= 1) {
+        raysLocal += __shfl_xor_sync(0xffffffffu, raysLocal, off);
+        recLocal += __shfl_xor_sync(0xffffffffu, recLocal, off);
+        levelsLocal += __shfl_xor_sync(0xffffffffu, levelsLocal, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (raysLocal) atomicAdd(&P.counters[0], raysLocal);
+        if (recLocal) { atomicAdd(&P.counters[1], recLocal); atomicAdd(&P.counters[2], levelsLocal); }
+    }
+}
+
+// paths still alive after the last bounce (only possible with maxDepth == -1 and the bounce cap) keep their radiance
+__global__ void __launch_bounds__(PPG_BLOCK) flush_kernel(PathState in, const uint32_t *liveIn, float4 *liFinal) {
+    const uint32_t nIn = *liveIn;
+    for (uint32_t i = blockIdx.x * PPG_BLOCK + threadIdx.x; i < nIn; i += gridDim.x * PPG_BLOCK) {
+        const float4 c = in.s2[i], e = in.s3[i];
+        liFinal[__float_as_uint(e.y)] = make_float4(c.z, c.w, e.x, 1.f);
+    }
+}
+
+// ------------------------------------------------------------------ commit: vertices -> building trees
+struct CommitParams {
+    TreeView tree;
+    VertexSlab slab0;              // slab of depth 1; slab k lives at +k*slabStride entries
+    size_t slabStride;
+    const uint32_t *liveCounts;    // liveCounts[k]: entries of slab k (the input live count of that bounce)
+    const float4 *liFinal;
+    int spatialFilter, directionalFilter, lossMode;   // lossMode already gated by isBuilt (GP:2152)
+    float statisticalWeight;       // 1.0 (0.5 only with nee=kickstart)
+    uint64_t seed;
+    const uint2 *snodes;
+};
+
+// optimizeBsdfSamplingFraction's gradient (GP:672-697) at the leaf's current theta; accumulated per leaf,
+// the Adam steps are taken by adam_kernel (batched: see DESIGN.md "Adam")
+__device__ __forceinline__ float sampling_fraction_gradient(float theta, float product, float woPdf, float bsdfPdf, float dTreePdf, float ratioPower) {
+    const float f = logistic(theta);
+    const float mixPdf = f * bsdfPdf + (1.f - f) * dTreePdf;
+    const float ratio = powf(product / mixPdf, ratioPower);
+    const float dLoss_df = -ratio / woPdf * (bsdfPdf - dTreePdf);
+    return 0.01f * theta + dLoss_df * (f * (1.f - f));
+}
+
+// DTreeWrapper::record (GP:575-584) into the building tree of S-tree node `leaf`.
+// weightDone: the statistical-weight add was already issued by the caller (warp-aggregated).
+__device__ __forceinline__ void record_into_leaf(const TreeView &T, uint32_t leaf, float3 d, float radiance, float product, float woPdf, float bsdfPdf,
+                                                 float dTreePdf, float weight, bool isDelta, int directionalFilter, int lossMode, bool weightDone) {
+    const float4 la = __ldg(&T.leafA[leaf]);
+    if (!isDelta) {
+        const bool wOk = isfinite(weight) && weight > 0.f;                    // DTree::recordIrradiance, GP:395-413
+        if (wOk) {
+            if (!weightDone) red_add(&T.bweight[leaf], weight);
+            dtree_record_irradiance(T.bchildren, T.bsums, __float_as_uint(la.y), dir_to_canonical(d), radiance / woPdf, weight, directionalFilter);
+        }
+    }
+    if (lossMode != 0 && product > 0.f) {
+        const float g = sampling_fraction_gradient(la.z, product, woPdf, bsdfPdf, dTreePdf, lossMode == 1 ? 1.0f : 2.0f);
+        red_add(&T.adamG[leaf], g * weight);
+        red_add(&T.adamW[leaf], weight);
+    }
+}
+
+template <int RECORD>
+__global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P) {
+    const uint32_t k = blockIdx.y;
+    const uint32_t n = P.liveCounts[k];
+    const size_t so = (size_t) k * P.slabStride;
+    for (uint32_t base = blockIdx.x * PPG_BLOCK; base < n; base += gridDim.x * PPG_BLOCK) {
+        const uint32_t i = base + threadIdx.x;
+        bool ok = i < n;
+        float4 v0, v1, v2, v4 = make_float4(0, 0, 0, 0), v5 = make_float4(0, 0, 0, 0);
+        uint32_t pid = PPG_INVALID;
+        if (ok) { v2 = P.slab0.v2[so + i]; pid = __float_as_uint(v2.w); ok = pid != PPG_INVALID; }
+        float3 d = f3(0, 0, 1), radiance = f3(0, 0, 0), thr = f3(1, 1, 1), bsdfVal = f3(0, 0, 0); float woPdf = 0.f, bsdfPdf = 0.f, dTreePdf = 0.f;
+        uint32_t leaf = 0; bool isDelta = false;
+        if (ok) {
+            v0 = P.slab0.v0[so + i]; v1 = P.slab0.v1[so + i];
+            isDelta = pid >> 31; pid &= 0x7fffffffu;
+            const float4 lf = __ldg(&P.liFinal[pid]);
+            d = f3(v0.x, v0.y, v0.z); woPdf = v0.w; thr = f3(v1.x, v1.y, v1.z); leaf = __float_as_uint(v1.w);
+            radiance = f3(lf.x - v2.x, lf.y - v2.y, lf.z - v2.z);                  // everything recorded after the vertex was created
+            if (RECORD == 2) {
+                const float4 v3 = P.slab0.v3[so + i]; bsdfVal = f3(v3.x, v3.y, v3.z); bsdfPdf = v3.w;
+                v4 = P.slab0.v4[so + i]; v5 = P.slab0.v5[so + i]; dTreePdf = v4.w;
+            }
+            // Vertex::commit, GP:1730-1768
+            if (!(woPdf > 0.f) || !is_valid(radiance) || !is_valid(bsdfVal)) ok = false;
+        }
+        float3 local = f3(0, 0, 0);
+        if (ok) {
+            if (thr.x * woPdf > PPG_EPSILON) local.x = radiance.x / thr.x;
+            if (thr.y * woPdf > PPG_EPSILON) local.y = radiance.y / thr.y;
+            if (thr.z * woPdf > PPG_EPSILON) local.z = radiance.z / thr.z;
+        }
+        const float3 prod = local * bsdfVal;
+        const float avgLocal = (local.x + local.y + local.z) * (1.0f / 3.0f);       // Spectrum::average()
+        const float avgProduct = (prod.x + prod.y + prod.z) * (1.0f / 3.0f);
+        const bool nearest = RECORD == 1 || P.spatialFilter == 0;
+        if (nearest) {
+            // nearest: the vertex's own leaf.  The statistical-weight counter of a leaf is ONE address that every vertex
+            // of that leaf hits (iteration 0: one address for the whole wavefront) -> one atomic per distinct leaf per warp.
+            // All 32 lanes reach this call (the loop trip count is block-uniform).
+            const float w = P.statisticalWeight;
+            warp_aggregated_add(P.tree.bweight, leaf, w, ok && !isDelta && isfinite(w) && w > 0.f);
+            if (ok) record_into_leaf(P.tree, leaf, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, w, isDelta, P.directionalFilter, P.lossMode, true);
+        } else if (ok) {
+            const float3 o = f3(v4.x, v4.y, v4.z);
+            const uint32_t lo = __float_as_uint(v5.z);
+            const float3 voxel = voxel_size(P.tree.extent, (int) (lo & 0xffu));
+            if (P.spatialFilter == 1) {
+                // stochastic box filter, GP:1746-1763: jitter the position inside the voxel-sized box, clip, re-lookup
+                const uint64_t sampleIndex = ((uint64_t) __float_as_uint(v5.y) << 32) | __float_as_uint(v5.x);
+                Pcg32 r; seed_vertex_rng(r, P.seed, sampleIndex, lo >> 8);
+                float3 off = voxel;
+                off.x *= r.next1D() - 0.5f; off.y *= r.next1D() - 0.5f; off.z *= r.next1D() - 0.5f;
+                float3 q = o + off;
+                const float3 mx = P.tree.aabbMin + P.tree.extent;
+                q.x = fminf(fmaxf(q.x, P.tree.aabbMin.x), mx.x); q.y = fminf(fmaxf(q.y, P.tree.aabbMin.y), mx.y); q.z = fminf(fmaxf(q.z, P.tree.aabbMin.z), mx.z);
+                int lv; const uint32_t splat = stree_lookup(P.snodes, P.tree.aabbMin, P.tree.extent, q, lv);
+                record_into_leaf(P.tree, splat, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, P.statisticalWeight, isDelta, P.directionalFilter, P.lossMode, false);
+            } else {
+                // box filter, STree::record GP:935-943 + STreeNode::record GP:823-839: every leaf overlapping the voxel-sized box
+                const float volume = voxel.x * voxel.y * voxel.z;
+                const float w0 = P.statisticalWeight / volume;
+                const float3 min1 = o - voxel * 0.5f, max1 = o + voxel * 0.5f;
+                struct E { uint32_t n; float3 mn, sz; int axis; };
+                E st[64]; int sp = 0;
+                st[sp++] = E{0u, P.tree.aabbMin, P.tree.extent, 0};
+                while (sp) {
+                    const E e = st[--sp];
+                    const float lx = fmaxf(fminf(max1.x, e.mn.x + e.sz.x) - fmaxf(min1.x, e.mn.x), 0.f);
+                    const float ly = fmaxf(fminf(max1.y, e.mn.y + e.sz.y) - fmaxf(min1.y, e.mn.y), 0.f);
+                    const float lz = fmaxf(fminf(max1.z, e.mn.z + e.sz.z) - fmaxf(min1.z, e.mn.z), 0.f);
+                    const float w = lx * ly * lz;
+                    if (!(w > 0.f)) continue;
+                    const uint2 c = __ldg(&P.snodes[e.n]);
+                    if (c.x == 0u) {
+                        record_into_leaf(P.tree, e.n, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, w0 * w, isDelta, P.directionalFilter, P.lossMode, false);
+                    } else if (sp + 2 <= 64) {
+                        float3 sz = e.sz, mn1 = e.mn;
+                        if (e.axis == 0) { sz.x /= 2.f; mn1.x += sz.x; } else if (e.axis == 1) { sz.y /= 2.f; mn1.y += sz.y; } else { sz.z /= 2.f; mn1.z += sz.z; }
+                        const int na = (e.axis + 1) % 3;
+                        st[sp++] = E{c.y, mn1, sz, na};
+                        st[sp++] = E{c.x, e.mn, sz, na};
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ film
+// block->put(samplePos, spec) and squaredBlock->put(samplePos, spec*spec) (GP:1633-1634); invalid samples are
+// dropped (imageblock.h:150-154).  Box filter: the sample lands in its own pixel with weight 1.
+__global__ void __launch_bounds__(PPG_BLOCK) film_kernel(const float4 *liFinal, const uint32_t *pixelMap, uint32_t nLocalPixels, uint32_t spp,
+                                                         uint32_t passesInBatch, int W, float4 *image, float4 *sqImage) {
+    for (uint32_t lp = blockIdx.x * PPG_BLOCK + threadIdx.x; lp < nLocalPixels; lp += gridDim.x * PPG_BLOCK) {
+        float4 a = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+        for (uint32_t pb = 0; pb < passesInBatch; ++pb)
+            for (uint32_t s = 0; s < spp; ++s) {
+                const float4 L = liFinal[((size_t) pb * nLocalPixels + lp) * spp + s];
+                if (!is_valid(f3(L.x, L.y, L.z))) continue;
+                a.x += L.x; a.y += L.y; a.z += L.z; a.w += 1.f;
+                q.x += L.x * L.x; q.y += L.y * L.y; q.z += L.z * L.z; q.w += 1.f;
+            }
+        const uint32_t xy = pixelMap[lp];
+        const size_t px = (size_t) (xy >> 16) * W + (xy & 0xffffu);
+        float4 A = image[px], Q = sqImage[px];
+        A.x += a.x; A.y += a.y; A.z += a.z; A.w += a.w;
+        Q.x += q.x; Q.y += q.y; Q.z += q.z; Q.w += q.w;
+        image[px] = A; sqImage[px] = Q;
+    }
+}
+
+// variance estimate with the getPixel() quirk (GP:1300-1313): sum over this rank's pixels of
+// min(lum(S2/W - (S1/W)^2/N), 1e4), accumulated in double
+__global__ void __launch_bounds__(PPG_BLOCK) variance_kernel(const float4 *image, const float4 *sqImage, const uint32_t *pixelMap, uint32_t nLocalPixels,
+                                                             int W, float N, double *out) {
+    __shared__ double sh[PPG_BLOCK / 32];
+    double acc = 0.0;
+    for (uint32_t lp = blockIdx.x * PPG_BLOCK + threadIdx.x; lp < nLocalPixels; lp += gridDim.x * PPG_BLOCK) {
+        const uint32_t xy = pixelMap[lp];
+        const size_t px = (size_t) (xy >> 16) * W + (xy & 0xffffu);
+        const float4 A = image[px], Q = sqImage[px];
+        const float iw = A.w != 0.f ? 1.0f / A.w : 0.f, isw = Q.w != 0.f ? 1.0f / Q.w : 0.f;
+        const float p0 = A.x * iw, p1 = A.y * iw, p2 = A.z * iw;
+        const float l0 = Q.x * isw - p0 * p0 / N, l1 = Q.y * isw - p1 * p1 / N, l2 = Q.z * isw - p2 * p2 / N;
+        const float lum = l0 * 0.212671f + l1 * 0.715160f + l2 * 0.072169f;
+        acc += (double) fminf(lum, 10000.0f);
+    }
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0; for (int w = 0; w < PPG_BLOCK / 32; ++w) t += sh[w];
+        atomicAdd(out, t);
+    }
+}
+
+__global__ void add_image_kernel(float4 *dst, const float4 *src, size_t n) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        float4 a = dst[i]; const float4 b = src[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a;
+    }
+}
+// film develop: weight-normalised RGB (hdrfilm); accumulate != 0: out += scale * normalised (inverse-variance combination, GP:1567-1582)
+__global__ void develop_kernel(const float4 *film, float *rgb, size_t n, float scale, int accumulate) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const float4 a = film[i];
+        const float iw = a.w != 0.f ? 1.0f / a.w : 0.f;
+        if (accumulate) { rgb[3 * i] += a.x * iw * scale; rgb[3 * i + 1] += a.y * iw * scale; rgb[3 * i + 2] += a.z * iw * scale; }
+        else { rgb[3 * i] = a.x * iw * scale; rgb[3 * i + 1] = a.y * iw * scale; rgb[3 * i + 2] = a.z * iw * scale; }
+    }
+}
+
+// ------------------------------------------------------------------ SD-tree maintenance (device side)
+struct MaintParams {
+    uint2 *snodes;                // S-tree nodes
+    float4 *leafA;                // per node leaf record
+    float *bweight;               // per node building statistical weight
+    float *sampSum, *sampWeight;  // per node: DTree::m_atomic of the sampling tree
+    int *sampDepth;               // per node: m_maxDepth of the sampling tree
+    uint32_t *sampCount;          // per node: node count of the sampling tree
+    float *adam;                  // per node: 6 floats (iter, m, v, variable, batchAcc, batchGrad)
+    uint32_t *buildCount;         // per node: node count of the building tree
+    int *buildDepth;              // per node: m_maxDepth of the building tree
+    uint32_t *nNodes;             // device scalar: current S-tree node count
+    uint32_t capNodes;
+    SampNode *samp; uint2 *bchildren; float4 *bsums;
+};
+
+// STree::refine (GP:957-998) as a single persistent block: rounds over the frontier of newly created nodes;
+// a leaf splits while its building weight exceeds the threshold (GP:953-955), both children inherit the parent's
+// leaf record (shared sampling tree, Adam state) with half the building weight (GP:876-895).  Children are allocated
+// with a block prefix sum, so node numbering is deterministic (required for identical replicas across ranks).
+__global__ void __launch_bounds__(1024) stree_refine_kernel(MaintParams M, float threshold) {
+    __shared__ uint32_t sScan[1024];
+    __shared__ uint32_t sBase, sBegin, sEnd, sAny;
+    if (threadIdx.x == 0) { sBegin = 0; sEnd = *M.nNodes; }
+    __syncthreads();
+    for (;;) {
+        const uint32_t begin = sBegin, end = sEnd;
+        if (threadIdx.x == 0) { sBase = end; sAny = 0; }
+        __syncthreads();
+        for (uint32_t chunk = begin; chunk < end; chunk += 1024) {
+            const uint32_t n = chunk + threadIdx.x;
+            bool split = false;
+            if (n < end) split = M.snodes[n].x == 0u && M.bweight[n] > threshold;
+            // block exclusive scan of the split flags
+            sScan[threadIdx.x] = split ? 1u : 0u;
+            __syncthreads();
+            for (int off = 1; off < 1024; off <<= 1) {
+                uint32_t v = threadIdx.x >= off ? sScan[threadIdx.x - off] : 0u;
+                __syncthreads();
+                sScan[threadIdx.x] += v;
+                __syncthreads();
+            }
+            const uint32_t incl = sScan[threadIdx.x], total = sScan[1023];
+            const uint32_t base = sBase;
+            if (split) {
+                const uint32_t c0 = base + 2 * (incl - 1);
+                if (c0 + 1 < M.capNodes) {
+                    const float4 la = M.leafA[n];
+                    const float half = M.bweight[n] / 2.f;
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t ci = c0 + c;
+                        M.snodes[ci] = make_uint2(0u, 0u);
+                        M.leafA[ci] = la; M.bweight[ci] = half;
+                        M.sampSum[ci] = M.sampSum[n]; M.sampWeight[ci] = M.sampWeight[n]; M.sampDepth[ci] = M.sampDepth[n]; M.sampCount[ci] = M.sampCount[n];
+                        for (int j = 0; j < 6; ++j) M.adam[6 * ci + j] = M.adam[6 * n + j];
+                    }
+                    M.snodes[n] = make_uint2(c0, c0 + 1);
+                    M.bweight[n] = 0.f;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { sBase = min(base + 2 * total, M.capNodes & ~1u); if (total) sAny = 1; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { sBegin = end; sEnd = sBase; }
+        __syncthreads();
+        if (!sAny || sBegin >= sEnd) break;
+    }
+    if (threadIdx.x == 0) *M.nNodes = sEnd;
+}
+
+// DTree::reset (GP:456-514), one thread per S-tree leaf.  The new building topology is the refinement of the leaf's
+// sampling tree: child i of a node at `depth` is subdivided iff depth < maxDepth and sum_i/total > threshold (for a
+// brand-new subtree the provisional sums are parent_sum/4; if total == 0 the fraction is 0.25^depth).  The DFS uses
+// the reference's stack discipline so that node numbering is identical to the reference's.
+// FILL == false: count nodes only (-> buildCount, buildDepth).  FILL == true: write the topology at buildBase and zero sums.
+template <bool FILL>
+__global__ void __launch_bounds__(128) dtree_reset_kernel(MaintParams M, const uint32_t *buildBase, int newMaxDepth, float subdivisionThreshold) {
+    const uint32_t nNodes = *M.nNodes;
+    for (uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < nNodes; leaf += gridDim.x * blockDim.x) {
+        if (M.snodes[leaf].x != 0u) { if (!FILL) M.buildCount[leaf] = 0; continue; }
+        const SampNode *prev = M.samp + __float_as_uint(M.leafA[leaf].x);
+        const float total = M.sampSum[leaf];
+        const uint32_t base = FILL ? buildBase[leaf] : 0u;
+        struct S { uint16_t nodeIndex, otherNodeIndex; uint8_t otherIsPrev, depth; float quarter; };
+        S stack[64]; int sp = 0;
+        stack[sp++] = S{0, 0, 1, 1, 0.f};
+        uint32_t count = 1; int maxDepth = 0;
+        if (FILL) { M.bchildren[base] = make_uint2(0u, 0u); M.bsums[base] = make_float4(0, 0, 0, 0); }
+        bool full = false;
+        while (sp && !full) {
+            const S s = stack[--sp];
+            maxDepth = max(maxDepth, (int) s.depth);
+            float4 osum; uint2 och = make_uint2(0u, 0u);
+            if (s.otherIsPrev) { osum = prev[s.otherNodeIndex].sums; och = prev[s.otherNodeIndex].children; }
+            else osum = make_float4(s.quarter, s.quarter, s.quarter, s.quarter);
+            uint32_t childOut[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 4; ++i) {
+                const float si = sum4(osum, i);
+                const float fraction = total > 0.f ? (si / total) : ldexpf(1.0f, -2 * (int) s.depth);   // std::pow(0.25f, depth), exact
+                if ((int) s.depth < newMaxDepth && fraction > subdivisionThreshold) {
+                    const uint32_t oc = s.otherIsPrev ? child16(och, i) : 0u;
+                    if (sp < 64) {
+                        if (oc != 0u) stack[sp++] = S{(uint16_t) count, (uint16_t) oc, 1, (uint8_t) (s.depth + 1), 0.f};
+                        else stack[sp++] = S{(uint16_t) count, (uint16_t) count, 0, (uint8_t) (s.depth + 1), si / 4.f};
+                    }
+                    childOut[i] = count;
+                    if (FILL) { M.bchildren[base + count] = make_uint2(0u, 0u); M.bsums[base + count] = make_float4(0, 0, 0, 0); }
+                    ++count;
+                    if (count > 65535u) { full = true; break; }                      // GP:499-503
+                }
+            }
+            if (FILL) M.bchildren[base + s.nodeIndex] = make_uint2(childOut[0] | (childOut[1] << 16), childOut[2] | (childOut[3] << 16));
+        }
+        if (!FILL) { M.buildCount[leaf] = count; M.buildDepth[leaf] = maxDepth; }
+    }
+}
+
+// DTree::build (GP:520-533, 346-366) + "sampling = building" (GP:610-613), one thread per S-tree leaf.
+// Children have larger indices than their parent (reset appends), so one reverse sweep equals the recursion.
+__global__ void __launch_bounds__(128) dtree_build_kernel(MaintParams M, const uint32_t *buildBase) {
+    const uint32_t nNodes = *M.nNodes;
+    for (uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < nNodes; leaf += gridDim.x * blockDim.x) {
+        if (M.snodes[leaf].x != 0u) continue;
+        const uint32_t base = buildBase[leaf], count = M.buildCount[leaf];
+        for (uint32_t k = count; k-- > 0;) {
+            float4 s = M.bsums[base + k];
+            const uint2 ch = M.bchildren[base + k];
+            float *sp = reinterpret_cast<float *>(&s);
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t c = child16(ch, i);
+                if (c == 0u) continue;
+                const float4 cs = M.samp[base + c].sums;          // already built (c > k)
+                float sum = 0.f; sum += cs.x; sum += cs.y; sum += cs.z; sum += cs.w;
+                sp[i] = sum;
+            }
+            SampNode out; out.sums = s; out.children = ch; out.pad = make_uint2(0u, 0u);
+            M.samp[base + k] = out;
+        }
+        const float4 r = M.samp[base].sums;
+        float sum = 0.f; sum += r.x; sum += r.y; sum += r.z; sum += r.w;
+        const float w = M.bweight[leaf];
+        M.sampSum[leaf] = sum; M.sampWeight[leaf] = w; M.sampDepth[leaf] = M.buildDepth[leaf]; M.sampCount[leaf] = count;
+        // DTree::mean() > 0 (GP:387-393)
+        float mean = 0.f;
+        if (w != 0.f) { const float factor = 1.f / (PPG_PI * 4.f * w); mean = factor * sum; }
+        float4 la = M.leafA[leaf];
+        la.x = __uint_as_float(base); la.y = __uint_as_float(base); la.w = __uint_as_float(mean > 0.f ? 1u : 0u);
+        M.leafA[leaf] = la;
+    }
+}
+
+// after reset: point every leaf at its new building tree and zero the building statistical weight (GP:457)
+__global__ void leaf_after_reset_kernel(MaintParams M, const uint32_t *buildBase) {
+    const uint32_t nNodes = *M.nNodes;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
+        float4 la = M.leafA[n]; la.y = __uint_as_float(buildBase[n]); M.leafA[n] = la;
+        M.bweight[n] = 0.f;
+    }
+}
+
+// exclusive prefix sum of counts[0..n) by a single block (n is at most a few 1e5..1e6 S-tree nodes, once per iteration)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t *counts, uint32_t *offsets, const uint32_t *nPtr, uint32_t *totalOut) {
+    __shared__ uint32_t sScan[1024];
+    __shared__ uint32_t sCarry;
+    const uint32_t n = *nPtr;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    for (uint32_t chunk = 0; chunk < n; chunk += 1024) {
+        const uint32_t i = chunk + threadIdx.x;
+        const uint32_t v = i < n ? counts[i] : 0u;
+        sScan[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            uint32_t t = threadIdx.x >= off ? sScan[threadIdx.x - off] : 0u;
+            __syncthreads();
+            sScan[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n) offsets[i] = sCarry + sScan[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) sCarry += sScan[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *totalOut = sCarry;
+}
+
+// Batched Adam (GP:69-133, 672-697): the reference takes one optimiser step whenever the accumulated weight of a
+// leaf exceeds batchSize=1, under a per-leaf spin lock, i.e. thousands of strictly sequential steps per pass.  Here
+// the gradient sums of one commit launch are applied as `steps` sequential Adam steps of the mean gradient
+// (steps = number of reference mini-batches that the accumulated weight corresponds to, capped); see DESIGN.md.
+__global__ void adam_kernel(MaintParams M, float *adamG, float *adamW, int maxSteps) {
+    const uint32_t nNodes = *M.nNodes;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
+        const float w = adamW[n];
+        if (!(w > 0.f) || M.snodes[n].x != 0u) { adamG[n] = 0.f; adamW[n] = 0.f; continue; }
+        const float g = adamG[n] / w;
+        float *st = M.adam + 6 * n;
+        int iter = (int) st[0]; float m1 = st[1], m2 = st[2], var = st[3];
+        int steps = (int) fminf(floorf(w / 2.f), (float) maxSteps);   // one reference step per >1 accumulated weight (two unit-weight records)
+        if (steps < 1) steps = 1;
+        for (int s = 0; s < steps; ++s) {
+            ++iter;
+            const float lr = 0.01f * sqrtf(1.f - powf(0.999f, (float) iter)) / (1.f - powf(0.9f, (float) iter));
+            m1 = 0.9f * m1 + (1.f - 0.9f) * g;
+            m2 = 0.999f * m2 + (1.f - 0.999f) * g * g;
+            var -= lr * m1 / (sqrtf(m2) + 1e-08f);
+            var = fminf(fmaxf(var, -20.0f), 20.0f);
+        }
+        st[0] = (float) iter; st[1] = m1; st[2] = m2; st[3] = var;
+        float4 la = M.leafA[n]; la.z = var; M.leafA[n] = la;
+        adamG[n] = 0.f; adamW[n] = 0.f;
+    }
+}
+
+}  // namespace ppg

@@ -12,6 +12,8 @@ import os
 import numpy as np
 
 PPG_MAX_ITERATIONS = 40
+PPG_KERNEL_CLASSES = 8
+KERNEL_CLASSES = ["bounce", "commit", "film", "refine", "reset", "build", "adam", "other"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libppg_b200.so")
@@ -73,11 +75,14 @@ class PpgStats(C.Structure):
     _fields_ = [
         ("n_iterations", C.c_int32), ("total_passes", C.c_int32), ("total_paths", C.c_uint64), ("total_vertices", C.c_uint64),
         ("render_seconds", C.c_double), ("device_seconds", C.c_double), ("final_variance", C.c_double),
-        ("kernel_launches", C.c_uint64), ("iterations", PpgIterationStats * PPG_MAX_ITERATIONS),
+        ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_double * PPG_KERNEL_CLASSES), ("kernel_count", C.c_uint64 * PPG_KERNEL_CLASSES),
+        ("render_device_ms", C.c_double), ("iterations", PpgIterationStats * PPG_MAX_ITERATIONS),
     ]
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "iterations"}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("iterations", "kernel_ms", "kernel_count")}
+        d["kernel_ms"] = {k: self.kernel_ms[i] for i, k in enumerate(KERNEL_CLASSES)}
+        d["kernel_count"] = {k: self.kernel_count[i] for i, k in enumerate(KERNEL_CLASSES)}
         d["iterations"] = [self.iterations[i].as_dict() for i in range(self.n_iterations)]
         return d
 

@@ -1,0 +1,166 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libppg_b200.so) against the CPU oracle on the same
+seeded inputs.  Tolerances are stated per test.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from common import load_cbox, relmse
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(props, scene):
+    from ppg_b200.integrator import GuidedPathTracer
+    g = GuidedPathTracer(props)
+    g.set_scene(scene)
+    return g
+
+
+def test_unguided_single_pass_matches_oracle_per_pixel():
+    """budget = sppPerPass -> one final, unguided iteration; both sides use the same PCG32 streams, so the
+    per-pixel sums agree up to libm ulps (a few paths may flip a discrete decision).
+    Tolerance: >= 99.5 % of pixels within 1e-3 relative (+1e-4 abs); image mean within 1e-3 relative."""
+    sc = load_cbox(128)
+    props = dict(sc.integrator, budget="4")
+    g = _gpu(props, sc)
+    img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port")
+    ref, ost = o.render()
+    assert st["total_paths"] == ost["total_paths"] == 128 * 128 * 4
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 2e-4 * ost["total_vertices"]
+    close = np.isclose(img, ref, rtol=1e-3, atol=1e-4).all(axis=2)
+    assert close.mean() >= 0.995, close.mean()
+    assert abs(img.mean() - ref.mean()) <= 1e-3 * ref.mean()
+
+
+def test_iteration_statistics_match_oracle():
+    """CBOX 256^2, sppPerPass 4, budget 28 spp (passes 1+2+4), maxDepth 4 -- BASELINE.json configs[0].
+    Iteration 0 is unguided: same paths on both sides, so the recorded statistical weight agrees to 1e-4 and the
+    D-tree topology (85 nodes, depth 4) exactly.  Later iterations diverge through float-atomic ordering, so they are
+    compared statistically (weight 1 %, variance 10 %)."""
+    sc = load_cbox(256)
+    props = dict(sc.integrator, budget="28", maxDepth="4", rrDepth="10")
+    g = _gpu(props, sc)
+    img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port")
+    ref, ost = o.render()
+    assert st["n_iterations"] == ost["n_iterations"] == 3
+    gi, oi = st["iterations"], ost["iterations"]
+    assert [i["passes"] for i in gi] == [i["passes"] for i in oi] == [1, 2, 4]
+    assert gi[0]["nodes_min"] == gi[0]["nodes_max"] == 85 and gi[0]["depth_max"] == 4
+    assert abs(gi[0]["weight_avg"] - oi[0]["weight_avg"]) <= 1e-4 * oi[0]["weight_avg"]
+    assert abs(gi[0]["mean_radiance_avg"] - oi[0]["mean_radiance_avg"]) <= 2e-3 * oi[0]["mean_radiance_avg"]
+    assert abs(gi[0]["variance"] - oi[0]["variance"]) <= 1e-3 * oi[0]["variance"]
+    assert gi[1]["s_tree_leaves"] == oi[1]["s_tree_leaves"]
+    for k in (1, 2):
+        assert abs(gi[k]["weight_avg"] * gi[k]["s_tree_leaves"] - oi[k]["weight_avg"] * oi[k]["s_tree_leaves"]) <= 0.01 * oi[k]["weight_avg"] * oi[k]["s_tree_leaves"]
+        assert abs(gi[k]["variance"] - oi[k]["variance"]) <= 0.10 * oi[k]["variance"]
+    assert abs(img.mean() - ref.mean()) <= 0.02 * ref.mean()
+
+
+def test_known_answers_of_the_reference_log():
+    """The authors' render log embedded in scenes/cbox/cbox.exr pins iteration 0 of CBOX 512^2 / 4 spp per pass:
+    one D-tree of 85 nodes, stat. weight 4 349 763, mean radiance 0.135707 (tests/golden/cbox_log_stats.json).
+    Seeded Monte Carlo: weight within 0.3 %, mean radiance within 3 %, Var within 4 % (spread measured over oracle seeds)."""
+    import json, os
+    from common import ROOT
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "cbox_log_stats.json")))["cbox"]["iterations"]
+    sc = load_cbox(512)
+    props = dict(sc.integrator, budget="12")        # passes 1 + 2 (final)
+    g = _gpu(props, sc)
+    _, st = g.render()
+    it0 = st["iterations"][0]
+    assert it0["nodes_min"] == it0["nodes_max"] == int(gold[0]["node_count"][0]) == 85
+    assert abs(it0["weight_avg"] - gold[0]["stat_weight"][1]) <= 0.003 * gold[0]["stat_weight"][1]
+    assert abs(it0["mean_radiance_avg"] - gold[0]["mean_radiance"][1]) <= 0.03 * gold[0]["mean_radiance"][1]
+    assert abs(it0["variance"] - gold[0]["var"]) <= 0.04 * gold[0]["var"]
+    assert st["iterations"][1]["s_tree_leaves"] == 512    # 4.35 M / 2^9 < 12000: uniform refinement to 512 leaves
+
+
+def test_full_render_equal_spp_relmse_vs_oracle():
+    """Equal-spp image parity (BASELINE north_star: relMSE within 5 % of the reference algorithm's image):
+    both the CUDA render and the oracle render of CBOX 128^2 at 252 spp are compared with a converged 4032-spp-equivalent
+    reference built from oracle renders with other seeds; the two relMSEs must agree within 15 % (MC noise of the relMSE
+    itself at this size; the 5 % claim is made at bench size in bench.py)."""
+    sc = load_cbox(128)
+    props = dict(sc.integrator, budget="252")
+    refs = []
+    for seed in range(8):
+        o = O.Oracle(O.params_from_xml(props, seed=100 + seed), sc, kind="port")
+        refs.append(o.render()[0]); o.close()
+    ref = np.mean(refs, axis=0)
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port")
+    oimg, _ = o.render()
+    g = _gpu(props, sc)
+    gimg, _ = g.render()
+    ro, rg = relmse(oimg, ref), relmse(gimg, ref)
+    assert abs(rg - ro) <= 0.15 * ro, (rg, ro)
+
+
+def _trained_oracle():
+    sc = load_cbox(128)
+    props = dict(sc.integrator, budget="60")
+    o = O.Oracle(O.params_from_xml(props), sc, kind="ref" if O.have_ref() else "port")
+    o.render()
+    return o
+
+
+def test_op_dtree_pdf_and_sample_match_reference_trees():
+    """D-tree pdf / sample kernels on the oracle's trained CBOX trees (verbatim reference SD-tree code when
+    oracle/_ref is present).  pdf: relative 2e-6 (top-down product vs the reference's bottom-up product);
+    sample: replayed uniforms, direction within 2e-6 absolute."""
+    from ppg_b200 import integrator as I
+    o = _trained_oracle()
+    e = o.export(0)
+    leaves = np.nonzero(e["s_is_leaf"])[0].astype(np.uint32)
+    rng = np.random.default_rng(7)
+    n = 200000
+    ql = rng.choice(leaves, n).astype(np.uint32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    first = e["tree_first"].astype(np.uint32)
+    ref = o.pdf(ql, d)
+    got = I.op_dtree_pdf(e["sums"], e["children"], first, e["tree_sum"], e["tree_weight"], ql, d)
+    assert np.allclose(got, ref, rtol=2e-6, atol=1e-12), np.abs(got - ref).max()
+    rnd = rng.random((n, 24), dtype=np.float32)
+    refd = o.sample(ql, rnd)
+    gotd = I.op_dtree_sample(e["sums"], e["children"], first, e["tree_sum"], e["tree_weight"], ql, rnd)
+    assert np.abs(gotd - refd).max() <= 2e-6
+
+
+def test_op_stree_lookup_bit_exact():
+    """S-tree descent: leaf index and voxel size are integer / power-of-two work -> bit exact."""
+    from ppg_b200 import integrator as I
+    o = _trained_oracle()
+    e = o.export(0)
+    rng = np.random.default_rng(3)
+    mn, mx = e["aabb"]
+    pts = (mn + rng.random((100000, 3)) * (mx - mn)).astype(np.float32)
+    leaf, size = o.lookup(pts)
+    gl, gs = I.op_stree_lookup(e["s_children"], mn, mx - mn, pts)
+    assert np.array_equal(gl, leaf)
+    assert np.array_equal(gs, size)
+
+
+@pytest.mark.parametrize("dfilter", [0, 1])
+def test_op_dtree_record_matches_reference(dfilter):
+    """Splat kernels (nearest and box directional filter) into the building trees: atomics reorder the float
+    adds, so sums agree to 1e-5 relative of the per-tree total; statistical weights are integers -> exact."""
+    from ppg_b200 import integrator as I
+    o = _trained_oracle()
+    o.refine(2000); o.reset(20, 0.01)
+    e = o.export(1)
+    leaves = np.nonzero(e["s_is_leaf"])[0].astype(np.uint32)
+    rng = np.random.default_rng(11)
+    n = 100000
+    mn, mx = e["aabb"]
+    # positions inside the cornell box proper so that many leaves are hit
+    pos = (np.array([0, 0, 0]) + rng.random((n, 3)) * np.array([556, 548.8, 559.2])).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rad = rng.lognormal(0, 1, n).astype(np.float32); pdf = (0.05 + rng.random(n)).astype(np.float32); w = np.ones(n, np.float32)
+    leaf, _ = o.lookup(pos)
+    sums, tw = I.op_dtree_record(e["sums"], e["children"], e["tree_first"].astype(np.uint32), e["tree_weight"], leaf, d, rad, pdf, w, dfilter)
+    o.record(pos, d, rad, pdf, weight=w, dfilter=dfilter)
+    e2 = o.export(1)
+    assert np.array_equal(tw, e2["tree_weight"])
+    scale = np.abs(e2["sums"]).sum() / max(1, len(leaves))
+    assert np.abs(sums - e2["sums"]).max() <= 1e-5 * scale + 1e-3 * np.abs(e2["sums"]).max() * 1e-3
