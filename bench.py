@@ -264,9 +264,13 @@ def gpu_arm(args):
         "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "wall_ms_per_step": wall_ms / args.steps, "mpaths_per_s": paths / (dev_ms * 1e-3) / 1e6,
+        "wall_ms_per_step": wall_ms / args.steps, "kernel_ms_per_step": sum(sum(s["kernel_ms"].values()) for s in stats) / args.steps, "mpaths_per_s": paths / (dev_ms * 1e-3) / 1e6,
         "final_variance": stats[-1]["final_variance"], "iterations": stats[-1]["n_iterations"], "total_passes": stats[-1]["total_passes"],
     }
+    if args.verbose:
+        for it in stats[-1]["iterations"]:
+            print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in it.items() if k in ("iteration", "passes", "seconds", "reset_seconds", "build_seconds", "variance", "s_tree_leaves", "vertices", "nodes_avg", "depth_avg", "s_tree_depth_avg")}, file=sys.stderr)
+        print({"render_device_ms": stats[-1]["render_device_ms"], "render_seconds": stats[-1]["render_seconds"], "kernel_ms": stats[-1]["kernel_ms"]}, file=sys.stderr)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -284,6 +288,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=512)
     ap.add_argument("--cpu-budget", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

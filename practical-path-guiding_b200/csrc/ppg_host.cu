@@ -400,6 +400,17 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         tmax[t] = h3(std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)));
     }
     HostBvh bvh; build_bvh(tmin, tmax, bvh);
+    uint32_t kBegin[4] = {0, 0, 0, 0};
+    if (nt <= PPG_BRUTE_FORCE_TRIS) {
+        // brute-force layout: order the triangles by projection axis (degenerate k==3 triangles last, never tested)
+        std::vector<int> ks(nt);
+        for (uint32_t t = 0; t < nt; ++t) { float w[9]; wald_constants(P(s->indices[3 * t]), P(s->indices[3 * t + 1]), P(s->indices[3 * t + 2]), w, ks[t]); }
+        std::vector<uint32_t> order;
+        for (int k = 0; k < 3; ++k) { kBegin[k] = (uint32_t) order.size(); for (uint32_t t = 0; t < nt; ++t) if (ks[t] == k) order.push_back(t); }
+        kBegin[3] = (uint32_t) order.size();
+        for (uint32_t t = 0; t < nt; ++t) if (ks[t] == 3) order.push_back(t);
+        bvh.order = order;
+    }
     std::vector<float> accel(12 * (size_t) nt), geom(24 * (size_t) nt); std::vector<int32_t> meta(4 * (size_t) nt);
     for (uint32_t slot = 0; slot < nt; ++slot) {
         const uint32_t t = bvh.order[slot];
@@ -442,6 +453,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     CK(cudaMemcpy(h->dRadiance.p, rad.data(), rad.size() * 4, cudaMemcpyHostToDevice));
     SceneView &v = h->sceneView;
     v.accel = h->dAccel.p; v.geom = h->dGeom.p; v.meta = h->dMeta.p; v.bvh = h->dBvh.p; v.bsdf = h->dBsdf.p; v.radiance = h->dRadiance.p;
+    for (int k = 0; k < 4; ++k) v.kBegin[k] = kBegin[k];
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
     const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 2 * s->n_bsdfs + v.nEmitters);
     h->sceneSmemBytes = sceneBytes <= 48 * 1024 ? (uint32_t) sceneBytes : 0u;   // small scenes (CBOX: ~9 KB) live in shared memory
@@ -496,11 +508,8 @@ static MaintParams maint(ppg_integrator *h) {
 // new STree (GP:1519): one leaf whose sampling tree is a single empty quadtree node
 static int init_tree(ppg_integrator *h) {
     CK(h->dScalars.alloc(8));
-    h->capNodes = 0; h->capPool = 0;
-    h->dSnodes.release(); h->dLeafA.release(); h->dBweight.release(); h->dSampSum.release(); h->dSampWeight.release(); h->dAdam.release();
-    h->dAdamG.release(); h->dAdamW.release(); h->dSampDepth.release(); h->dBuildDepth.release(); h->dSampCount.release(); h->dBuildCount.release();
-    h->dBuildBase.release(); h->dSamp.release(); h->dBchildren.release(); h->dTrain.release();
-    int rc = ensure_tree_capacity(h, 1u << 16, (size_t) 1 << 20);
+    // buffers persist across renders (cudaMalloc/cudaFree are synchronous and slow): only their contents are reset
+    int rc = ensure_tree_capacity(h, std::max<uint32_t>(h->capNodes, 1u << 16), std::max<size_t>(h->capPool, (size_t) 1 << 20));
     if (rc) return rc;
     CK(cudaMemsetAsync(h->dSnodes.p, 0, sizeof(uint2) * h->capNodes, h->stream));
     CK(cudaMemsetAsync(h->dLeafA.p, 0, sizeof(float4) * h->capNodes, h->stream));

@@ -5,7 +5,7 @@
 //     bounce         (one launch per further path depth)  GP:1798-2146
 //     commit         (all recorded vertices -> building trees)   GP:2150-2154 -> 1730-1768 -> 575-584
 //     film           (per-pixel sum and sum of squares)   GP:1633-1634, imageblock.h:127-186
-// Live paths are compacted between bounces (warp ballot + block prefix + one atomic per block),
+// Live paths are compacted between bounces (warp ballot + prefix popcount + one atomic per warp),
 // path state is SoA float4 (5 x 16 B per path, coalesced), the scene (CBOX: ~9 KB) is staged in
 // shared memory, the read-only sampling trees go through the read-only/L1 path.
 #pragma once
@@ -79,22 +79,15 @@ __device__ __forceinline__ SceneView stage_scene(const SceneView &g, float4 *sme
     return s;
 }
 
-// block-wide compaction: returns the output slot of this thread (valid when `alive`); one atomic per block
-__device__ __forceinline__ uint32_t block_compact(bool alive, uint32_t *counter, uint32_t *sWarp /* [PPG_BLOCK/32 + 1] */) {
+// warp-wide compaction: returns the output slot of this lane (valid when `alive`); one atomic per warp and
+// no block barrier, so warps of a block never wait for each other inside the path loop.
+__device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) {
     const unsigned ballot = __ballot_sync(0xffffffffu, alive);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) sWarp[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int w = 0; w < PPG_BLOCK / 32; ++w) { const uint32_t c = sWarp[w]; sWarp[w] = total; total += c; }
-        sWarp[PPG_BLOCK / 32] = total ? atomicAdd(counter, total) : 0u;
-    }
-    __syncthreads();
-    const uint32_t slot = sWarp[PPG_BLOCK / 32] + sWarp[warp] + __popc(ballot & ((1u << lane) - 1u));
-    __syncthreads();   // sWarp is reused by the next loop iteration
-    return slot;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(counter, (uint32_t) __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(ballot & ((1u << lane) - 1u));
 }
 
 // ------------------------------------------------------------------ the bounce kernel
@@ -104,7 +97,6 @@ __device__ __forceinline__ uint32_t block_compact(bool alive, uint32_t *counter,
 template <bool FIRST, int RECORD>
 __global__ void __launch_bounds__(PPG_BLOCK) bounce_kernel(const RenderParams P) {
     extern __shared__ float4 smemScene[];
-    __shared__ uint32_t sWarp[PPG_BLOCK / 32 + 1];
     const SceneView sc = P.sceneSmemBytes ? stage_scene(P.scene, smemScene) : P.scene;
     const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
     unsigned long long raysLocal = 0, recLocal = 0, levelsLocal = 0;
@@ -252,7 +244,7 @@ __global__ void __launch_bounds__(PPG_BLOCK) bounce_kernel(const RenderParams P)
             }
         }
         if (RECORD && i < nIn && !wroteVertex) P.slab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
-        const uint32_t slot = block_compact(alive, P.liveOut, sWarp);
+        const uint32_t slot = warp_compact(alive, P.liveOut);
         if (alive) {
             P.out.s0[slot] = make_float4(o.x, o.y, o.z, d.x);
             P.out.s1[slot] = make_float4(d.y, d.z, thr.x, thr.y);

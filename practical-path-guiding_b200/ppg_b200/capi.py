@@ -16,7 +16,7 @@ PPG_KERNEL_CLASSES = 8
 KERNEL_CLASSES = ["bounce", "commit", "film", "refine", "reset", "build", "adam", "other"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libppg_b200.so")
+LIB_PATH = os.environ.get("PPG_B200_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libppg_b200.so")   # PPG_B200_LIB: A/B builds of the same CUDA sources
 
 
 class PpgParams(C.Structure):
