@@ -282,6 +282,7 @@ __device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx
 struct SampNode { float4 sums; uint2 children; uint2 pad; };
 struct TreeView {
     const uint2 *snodes;
+    const uint32_t *stable;       // S-tree prefix table (see stree_lookup), or nullptr
     const float4 *leafA;
     const SampNode *samp;         // sampling pool
     const uint2 *bchildren;       // building pool topology (4 x uint16 per node)
@@ -296,10 +297,31 @@ __device__ __forceinline__ float sum4(float4 s, int i) { return i == 0 ? s.x : (
 
 // STree::dTreeWrapper(p, size) -- GP:897-905 + 761-769 + 747-755.  Returns the leaf node index and the
 // number of levels descended (the voxel size follows from it: size[axis] halves once per level on that axis).
-__device__ __forceinline__ uint32_t stree_lookup(const uint2 *__restrict__ snodes, float3 aabbMin, float3 extent, float3 pw, int &levels) {
+//
+// The reference walks one node per level (~18 dependent loads on CBOX).  Because every split is at the midpoint and
+// the axes cycle x,y,z, the first 3*B levels of the walk are exactly the B leading binary digits of each normalised
+// coordinate (p < 0.5 ? 2p : 2p-1 is exact in fp32), so a prefix table indexed by the interleaved digits replaces them
+// with ONE load; the walk then continues from the table's node with the exact remainders 2^B*p - floor(2^B*p).
+// Table entry: node | levels<<24 | leaf<<31 (built by stree_table_kernel after every refine).
+#define PPG_STREE_TABLE_BITS 6                     // digits per axis -> 3*6 = 18 levels, 2^18 entries (1 MB, L2 resident)
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // bit i -> bit 3i (6 bits)
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8) | ((v & 32u) << 10);
+}
+__device__ __forceinline__ uint32_t stree_lookup(const uint2 *__restrict__ snodes, const uint32_t *__restrict__ table, float3 aabbMin, float3 extent,
+                                                 float3 pw, int &levels) {
     // p0 is the coordinate of the current split axis; the triple rotates with the axis (no dynamic indexing)
     float p0 = (pw.x - aabbMin.x) / extent.x, p1 = (pw.y - aabbMin.y) / extent.y, p2 = (pw.z - aabbMin.z) / extent.z;
     uint32_t n = 0; int depth = 0;
+    if (table) {
+        const float S = (float) (1 << PPG_STREE_TABLE_BITS), M = S - 1.0f;
+        // digits: clamp(floor(S*p), 0, S-1); p >= 1 keeps taking the upper child and p < 0 the lower one, exactly like the walk
+        const float f0 = fminf(fmaxf(floorf(p0 * S), 0.f), M), f1 = fminf(fmaxf(floorf(p1 * S), 0.f), M), f2 = fminf(fmaxf(floorf(p2 * S), 0.f), M);
+        const uint32_t key = (spread3((uint32_t) f0) << 2) | (spread3((uint32_t) f1) << 1) | spread3((uint32_t) f2);
+        const uint32_t e = __ldg(&table[key]);
+        n = e & 0x00ffffffu; depth = (int) ((e >> 24) & 0x7fu);
+        if (e >> 31) { levels = depth; return n; }
+        p0 = p0 * S - f0; p1 = p1 * S - f1; p2 = p2 * S - f2;       // exact remainders; depth == 3*BITS here, next axis is x again
+    }
     for (;;) {
         const uint2 c = __ldg(&snodes[n]);
         if (c.x == 0u) break;

@@ -270,6 +270,7 @@ struct ppg_integrator {
     uint32_t capNodes = 0; size_t capPool = 0;
     DevBuf<uint2> dSnodes; DevBuf<float4> dLeafA; DevBuf<float> dBweight, dSampSum, dSampWeight, dAdam, dAdamG, dAdamW;
     DevBuf<int> dSampDepth, dBuildDepth; DevBuf<uint32_t> dSampCount, dBuildCount, dBuildBase, dScalars /* [0]=nNodes [1]=totalBuild */;
+    DevBuf<uint32_t> dStable;
     DevBuf<SampNode> dSamp; DevBuf<uint2> dBchildren; DevBuf<float> dTrain /* bsums | packed tail */;
     uint32_t hNodes = 1; uint32_t hTotalBuild = 1;
     float extent[3];
@@ -531,7 +532,7 @@ static int init_tree(ppg_integrator *h) {
 
 static TreeView tree_view(ppg_integrator *h) {
     TreeView T;
-    T.snodes = h->dSnodes.p; T.leafA = h->dLeafA.p; T.samp = h->dSamp.p; T.bchildren = h->dBchildren.p;
+    T.snodes = h->dSnodes.p; T.stable = h->dStable.p; T.leafA = h->dLeafA.p; T.samp = h->dSamp.p; T.bchildren = h->dBchildren.p;
     T.bsums = reinterpret_cast<float4 *>(h->dTrain.p); T.bweight = h->dBweight.p; T.adamG = h->dAdamG.p; T.adamW = h->dAdamW.p;
     T.aabbMin = make_float3(h->aabbMin[0], h->aabbMin[1], h->aabbMin[2]); T.extent = make_float3(h->extent[0], h->extent[1], h->extent[2]);
     return T;
@@ -1071,9 +1072,9 @@ __global__ void op_record_kernel(TreeView T, const uint32_t *rt, const float *rd
         }
     }
 }
-__global__ void op_lookup_kernel(const uint2 *snodes, float3 mn, float3 ext, const float *pts, size_t n, uint32_t *leaf, float *size) {
+__global__ void op_lookup_kernel(const uint2 *snodes, const uint32_t *table, float3 mn, float3 ext, const float *pts, size_t n, uint32_t *leaf, float *size) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-        int lv; const uint32_t l = stree_lookup(snodes, mn, ext, f3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), lv);
+        int lv; const uint32_t l = stree_lookup(snodes, table, mn, ext, f3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), lv);
         leaf[i] = l;
         const float3 v = voxel_size(ext, lv);
         size[3 * i] = v.x; size[3 * i + 1] = v.y; size[3 * i + 2] = v.z;
@@ -1157,7 +1158,9 @@ extern "C" int ppg_op_stree_lookup(int device, const uint32_t *node_children, si
     Up<uint2> dn; Up<float> dp; DevBuf<uint32_t> dl; DevBuf<float> dsz;
     if (dn.up(reinterpret_cast<const uint2 *>(node_children), n_nodes) || dp.up(points, 3 * n)) return fail(PPG_ERR_CUDA, "upload failed");
     CK(dl.alloc(std::max<size_t>(n, 1))); CK(dsz.alloc(std::max<size_t>(3 * n, 1)));
-    if (n) op_lookup_kernel<<<296, 256>>>(dn.b.p, make_float3(aabb_min[0], aabb_min[1], aabb_min[2]), make_float3(aabb_extent[0], aabb_extent[1], aabb_extent[2]), dp.b.p, n, dl.p, dsz.p);
+    DevBuf<uint32_t> dt; CK(dt.alloc((size_t) 1 << (3 * PPG_STREE_TABLE_BITS)));
+    stree_table_kernel<<<296, 256>>>(dn.b.p, dt.p);     // the same prefix table the render kernels use
+    if (n) op_lookup_kernel<<<296, 256>>>(dn.b.p, dt.p, make_float3(aabb_min[0], aabb_min[1], aabb_min[2]), make_float3(aabb_extent[0], aabb_extent[1], aabb_extent[2]), dp.b.p, n, dl.p, dsz.p);
     CK(cudaGetLastError());
     CK(cudaMemcpy(leaf_out, dl.p, 4 * n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(size_out, dsz.p, 12 * n, cudaMemcpyDeviceToHost));

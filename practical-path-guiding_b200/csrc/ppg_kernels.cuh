@@ -13,7 +13,12 @@
 
 namespace ppg {
 
+#ifndef PPG_BLOCK
 #define PPG_BLOCK 256
+#endif
+#ifndef PPG_MIN_BLOCKS
+#define PPG_MIN_BLOCKS 4               // resident blocks per SM the bounce kernel is compiled for (register cap)
+#endif
 #define PPG_MAX_VERTICES 32         // MAX_NUM_VERTICES, GP:1771
 #define PPG_INVALID 0xFFFFFFFFu
 
@@ -95,7 +100,7 @@ __device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) 
 // RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
 //         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
 template <bool FIRST, int RECORD>
-__global__ void __launch_bounds__(PPG_BLOCK) bounce_kernel(const RenderParams P) {
+__global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
     extern __shared__ float4 smemScene[];
     const SceneView sc = P.sceneSmemBytes ? stage_scene(P.scene, smemScene) : P.scene;
     const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(PPG_BLOCK) bounce_kernel(const RenderParams P)
             }
             if (cont) {
                 const Bsdf bsdf = load_bsdf(sc, its.bsdf);
-                int levels; const uint32_t leaf = stree_lookup(P.tree.snodes, P.tree.aabbMin, P.tree.extent, its.p, levels);   // GP:1942-1944
+                int levels; const uint32_t leaf = stree_lookup(P.tree.snodes, P.tree.stable, P.tree.aabbMin, P.tree.extent, its.p, levels);   // GP:1942-1944
                 const float4 la = __ldg(&P.tree.leafA[leaf]);
                 float frac = P.fixedFraction;
                 if (P.lossMode != 0) frac = logistic(la.z);                          // GP:1946-1949
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P)
                 float3 q = o + off;
                 const float3 mx = P.tree.aabbMin + P.tree.extent;
                 q.x = fminf(fmaxf(q.x, P.tree.aabbMin.x), mx.x); q.y = fminf(fmaxf(q.y, P.tree.aabbMin.y), mx.y); q.z = fminf(fmaxf(q.z, P.tree.aabbMin.z), mx.z);
-                int lv; const uint32_t splat = stree_lookup(P.snodes, P.tree.aabbMin, P.tree.extent, q, lv);
+                int lv; const uint32_t splat = stree_lookup(P.snodes, P.tree.stable, P.tree.aabbMin, P.tree.extent, q, lv);
                 record_into_leaf(P.tree, splat, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, P.statisticalWeight, isDelta, P.directionalFilter, P.lossMode, false);
             } else {
                 // box filter, STree::record GP:935-943 + STreeNode::record GP:823-839: every leaf overlapping the voxel-sized box
@@ -539,6 +544,23 @@ __global__ void __launch_bounds__(1024) stree_refine_kernel(MaintParams M, float
         if (!sAny || sBegin >= sEnd) break;
     }
     if (threadIdx.x == 0) *M.nNodes = sEnd;
+}
+
+// Prefix table of the S-tree (see stree_lookup): entry `key` = where the walk stands after following the 3*BITS
+// interleaved digits of key (x digit first), or the leaf it ended in earlier.
+__global__ void stree_table_kernel(const uint2 *snodes, uint32_t *table) {
+    const uint32_t nKeys = 1u << (3 * PPG_STREE_TABLE_BITS);
+    for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < nKeys; key += gridDim.x * blockDim.x) {
+        uint32_t n = 0, depth = 0, leaf = 0;
+        for (int level = 0; level < 3 * PPG_STREE_TABLE_BITS; ++level) {
+            const uint2 c = snodes[n];
+            if (c.x == 0u) { leaf = 1; break; }
+            const uint32_t bit = (key >> (3 * PPG_STREE_TABLE_BITS - 1 - level)) & 1u;
+            n = bit ? c.y : c.x; ++depth;
+        }
+        if (!leaf && snodes[n].x == 0u) leaf = 1;
+        table[key] = n | (depth << 24) | (leaf << 31);
+    }
 }
 
 // DTree::reset (GP:456-514), one thread per S-tree leaf.  The new building topology is the refinement of the leaf's

@@ -1,0 +1,104 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol of include/ppg.h, parameter handling mirrors the
+reference constructor, the product path fails loudly without a GPU, and the scene loader reproduces Mitsuba's values."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import ROOT, gpu_available, load_cbox
+from ppg_b200 import capi, integrator as I
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    hdr = open(os.path.join(ROOT, "include", "ppg.h")).read()
+    declared = set(re.findall(r"^(?:int|void|const char \*)\s*\*?(ppg_[a-z_0-9]+)\s*\(", hdr, re.M))
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.ppg_description() == b"Guided path tracer"      # MTS_EXPORT_PLUGIN(GuidedPathTracer, "Guided path tracer"), GP:2422
+    assert lib.ppg_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    src = '#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu", sizeof(ppg_params), sizeof(ppg_bsdf), sizeof(ppg_shape), sizeof(ppg_scene_desc), sizeof(ppg_iteration_stats), sizeof(ppg_stats));}' % os.path.join(ROOT, "include", "ppg.h")
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["/usr/bin/gcc", os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
+        sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(capi.PpgParams), C.sizeof(capi.PpgBsdf), C.sizeof(capi.PpgShape), C.sizeof(capi.PpgSceneDesc), C.sizeof(capi.PpgIterationStats), C.sizeof(capi.PpgStats)]
+
+
+def test_parameter_defaults_are_the_references():
+    p = I.make_params()
+    # GP:1015-1084 and integrator.cpp:190-225
+    assert (p.nee, p.sample_combination, p.spatial_filter, p.directional_filter, p.bsdf_sampling_fraction_loss) == (0, 1, 0, 0, 0)
+    assert (p.sd_tree_max_memory, p.s_tree_threshold, p.spp_per_pass, p.budget_type, p.dump_sd_tree) == (-1, 12000, 4, 1, 0)
+    assert (p.d_tree_threshold, p.bsdf_sampling_fraction, p.budget) == (pytest.approx(0.01), 0.5, 300.0)
+    assert (p.max_depth, p.rr_depth, p.strict_normals, p.hide_emitters) == (-1, 5, 0, 0)
+
+
+@pytest.mark.parametrize("name,value", [("sampleCombination", "sometimes"), ("spatialFilter", "gauss"), ("directionalFilter", "stochastic"),
+                                        ("bsdfSamplingFractionLoss", "l2"), ("budgetType", "minutes"), ("nee", "maybe"), ("rrDepth", "0"),
+                                        ("maxDepth", "0"), ("maxDepth", "-2"), ("strictNormals", "yes"), ("notAParameter", "1")])
+def test_invalid_parameters_are_rejected_like_the_reference(name, value):
+    """Unknown enum strings Assert(false) in the reference (GP:1023,1034,1045,1054,1065,1080); rrDepth <= 0 and
+    maxDepth not in {-1, >0} Log(EError) (integrator.cpp:220-224)."""
+    with pytest.raises(I.PpgError) as e:
+        I.make_params({name: value})
+    assert e.value.code == -1
+
+
+def test_all_reference_parameter_strings_are_accepted():
+    for name, vals in {"sampleCombination": ["discard", "automatic", "inversevar"], "spatialFilter": ["nearest", "stochastic", "box"],
+                       "directionalFilter": ["nearest", "box"], "bsdfSamplingFractionLoss": ["none", "kl", "var"], "budgetType": ["spp", "seconds"]}.items():
+        for i, v in enumerate(vals):
+            I.make_params({name: v})
+    p = I.make_params(load_cbox(improved=True).integrator)
+    assert (p.sample_combination, p.bsdf_sampling_fraction_loss, p.spatial_filter, p.directional_filter, p.s_tree_threshold, p.spp_per_pass) == (2, 1, 1, 1, 4000, 1)
+    assert (p.max_depth, p.rr_depth, p.strict_normals, p.budget_type, p.budget) == (10, 10, 1, 0, 127.0)
+
+
+@pytest.mark.skipif(gpu_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a CUDA device -- it never routes through the oracle or any CPU code."""
+    with pytest.raises(I.PpgError) as e:
+        I.GuidedPathTracer({})
+    assert e.value.code == -2
+    with pytest.raises(I.PpgError) as e2:
+        I.op_stree_lookup(np.zeros((1, 2), np.uint32), [0, 0, 0], [1, 1, 1], np.zeros((1, 3), np.float32))
+    assert e2.value.code == -2
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "practical-path-guiding_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "ppg_device.cuh" and "oracle/ppg_cpu_tracer.h" in txt, os.path.join(dirpath, f)
+
+
+def test_cbox_rgb_values_match_mitsubas_spectrum_conversion():
+    """The CBOX spectra converted by our loader give the RGB triples Mitsuba 0.5 computes (its well-known cbox-rgb values);
+    this needs the reference's mirrored InterpolatedSpectrum::eval (spectrum.cpp:701-706), which the loader restates."""
+    sc = load_cbox()
+    refl = {n: sc.bsdfs[i, 2:5] for i, n in enumerate(sc.bsdf_names)}
+    assert np.allclose(refl["white"], [0.885809, 0.698859, 0.666422], atol=2e-4)
+    assert np.allclose(refl["red"], [0.570068, 0.0430135, 0.0443706], atol=2e-4)
+    assert np.allclose(refl["green"], [0.105421, 0.37798, 0.076425], atol=2e-4)
+    assert np.allclose(sc.area_radiance[0], [2 * 18.387, 2 * 10.9873, 2 * 2.75357], rtol=2e-4)
+    assert np.allclose(sc.aabb_min, [0, 0, -800]) and np.allclose(sc.aabb_max, [556, 548.8, 559.2])   # geometry + sensor position (scene.cpp:387-413)
+    assert len(sc.indices) == 36
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/scenes/cbox/cbox.xml"), reason="reference tree not present")
+def test_fixture_is_what_the_loader_produces_from_the_reference_xml():
+    from ppg_b200.scene import load_mitsuba_xml
+    a = load_mitsuba_xml("/root/reference/scenes/cbox/cbox.xml"); b = load_cbox()
+    for k in ("positions", "normals", "indices", "triangle_shape", "shapes", "bsdfs", "area_radiance", "cam_to_world", "aabb_min", "aabb_max"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.integrator == b.integrator and a.x_fov_deg == b.x_fov_deg

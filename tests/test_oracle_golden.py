@@ -1,0 +1,58 @@
+"""Pins the CPU oracle against the reference's own known answers: the per-iteration statistics of the authors'
+render logs embedded in the golden EXRs (tests/golden/cbox_log_stats.json, extracted by tools/make_fixtures.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from common import ROOT, load_cbox
+
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "cbox_log_stats.json")))
+
+
+def test_pass_schedule_matches_log():
+    """budget 127 spp at sppPerPass 4 -> 32 passes in iterations of 1, 2, 4, 8, 17 (GP:1365-1374; cbox.exr log)."""
+    sc = load_cbox(32)
+    o = O.Oracle(O.params_from_xml(sc.integrator), sc)
+    _, st = o.render()
+    assert [i["passes"] for i in st["iterations"]] == [i["passes"] for i in GOLD["cbox"]["iterations"]] == [1, 2, 4, 8, 17]
+    assert [i["total_passes"] for i in st["iterations"]] == [i["total_passes"] for i in GOLD["cbox"]["iterations"]]
+    assert st["iterations"][-1]["is_final"] == 1
+
+
+@pytest.mark.parametrize("kind", ["port"] + (["ref"] if O.have_ref() else []))
+def test_iteration0_known_answers(kind):
+    """CBOX 512^2, 4 spp: one D-tree of 85 nodes / depth 4; stat. weight 4 349 763, mean radiance 0.135707, Var 1.482526
+    in the reference's log.  Tolerances from the measured seed-to-seed spread of the oracle (weight +-0.1 %, mean +-1.5 %, Var +-2 %)."""
+    g = GOLD["cbox"]["iterations"][0]
+    sc = load_cbox(512)
+    o = O.Oracle(O.params_from_xml(sc.integrator), sc, kind=kind)
+    o.step_reset(0); var = o.step_passes(1); st = o.step_build()
+    assert st["nodes_min"] == st["nodes_max"] == 85 == int(g["node_count"][0])
+    assert st["depth_min"] == st["depth_max"] == 4 == int(g["depth"][0])
+    assert abs(st["weight_avg"] - g["stat_weight"][1]) <= 0.003 * g["stat_weight"][1]
+    assert abs(st["mean_radiance_avg"] - g["mean_radiance"][1]) <= 0.03 * g["mean_radiance"][1]
+    assert abs(var - g["var"]) <= 0.04 * g["var"]
+    # iteration 1 of the log: 512 leaves after refinement at threshold 12000, avg weight 7161.7 over 2 passes
+    o.step_reset(1)
+    e = o.export(0)
+    assert e["n_leaves"] == 512
+    o.step_passes(2); st1 = o.step_build()
+    g1 = GOLD["cbox"]["iterations"][1]
+    assert abs(st1["weight_avg"] - g1["stat_weight"][1]) <= 0.01 * g1["stat_weight"][1]
+    assert abs(st1["nodes_avg"] - g1["node_count"][1]) <= 4
+    assert abs(st1["mean_radiance_avg"] - g1["mean_radiance"][1]) <= 0.06 * g1["mean_radiance"][1]
+
+
+def test_improved_config_iteration0():
+    """cbox-improved.xml (inversevar / kl / stochastic / box / 4000 / sppPerPass 1): iteration 0 stat. weight 1 088 232,
+    mean radiance 0.136631 in the reference's log."""
+    g = GOLD["cbox-improved"]["iterations"][0]
+    sc = load_cbox(512, improved=True)
+    o = O.Oracle(O.params_from_xml(sc.integrator), sc)
+    o.step_reset(0); o.step_passes(1); st = o.step_build()
+    assert abs(st["weight_avg"] - g["stat_weight"][1]) <= 0.005 * g["stat_weight"][1]
+    assert abs(st["mean_radiance_avg"] - g["mean_radiance"][1]) <= 0.05 * g["mean_radiance"][1]
+    assert st["nodes_max"] == 85

@@ -1,0 +1,128 @@
+"""Pins the restated SD-tree (oracle/sdtree_port.h) against the reference's OWN SD-tree code compiled verbatim
+(oracle/_ref/libppg_oracle_ref.so, built from guided_path.cpp:25-1008 where /root/reference exists).
+Single-threaded, same record order -> every float must agree bit for bit."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+AABB = ([0.0, 0.0, -800.0], [556.0, 548.8, 559.2])
+
+
+def _records(n, seed):
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n, 3)) * np.array([556, 548.8, 559.2])).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rad = rng.lognormal(0, 1, n).astype(np.float32)
+    prod = (rad * rng.random(n)).astype(np.float32)
+    wo = (0.05 + rng.random(n)).astype(np.float32); bp = (0.05 + rng.random(n)).astype(np.float32); dp = (0.05 + rng.random(n)).astype(np.float32)
+    rnd = rng.random((n, 3)).astype(np.float32)
+    delta = (rng.random(n) < 0.05).astype(np.uint8)
+    return pos, d, rad, prod, wo, bp, dp, rnd, delta
+
+
+def _run(kind, sfilter, dfilter, loss, iters=3, n=6000):
+    o = O.Oracle(O.default_params(), aabb=AABB, kind=kind)
+    out = []
+    for it in range(iters):
+        o.refine(int(np.sqrt(2 ** it) * 300)); o.reset(20, 0.01)
+        pos, d, rad, prod, wo, bp, dp, rnd, delta = _records(n * 2 ** it, 100 + it)
+        o.record(pos, d, rad, wo, product=prod, bsdf_pdf=bp, dtree_pdf=dp, weight=np.ones(len(rad), np.float32), is_delta=delta, rnd=rnd,
+                 sfilter=sfilter, dfilter=dfilter, loss=loss if it > 0 else 0)
+        out.append(o.export(1))
+        o.build()
+        out.append(o.export(0))
+    return o, out
+
+
+@needs_ref
+@pytest.mark.parametrize("sfilter,dfilter,loss", [(0, 0, 0), (1, 1, 1), (2, 1, 2), (2, 0, 0)])
+def test_port_equals_verbatim_reference(sfilter, dfilter, loss):
+    op, a = _run("port", sfilter, dfilter, loss)
+    orf, b = _run("ref", sfilter, dfilter, loss)
+    for ea, eb in zip(a, b):
+        for k in ("s_children", "s_axis", "s_is_leaf", "tree_first", "tree_count", "tree_depth", "children"):
+            assert np.array_equal(ea[k], eb[k]), k
+        for k in ("tree_sum", "tree_weight", "sums", "adam", "aabb"):
+            assert np.array_equal(ea[k].view(np.uint32), eb[k].view(np.uint32)), k      # bit exact
+    # sample / pdf / lookup / sampling fraction on the trained trees
+    rng = np.random.default_rng(5)
+    e = a[-1]
+    leaves = np.nonzero(e["s_is_leaf"])[0].astype(np.uint32)
+    ql = rng.choice(leaves, 20000).astype(np.uint32)
+    d = rng.normal(size=(20000, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    assert np.array_equal(op.pdf(ql, d).view(np.uint32), orf.pdf(ql, d).view(np.uint32))
+    rnd = rng.random((20000, 48), dtype=np.float32)
+    assert np.array_equal(op.sample(ql, rnd).view(np.uint32), orf.sample(ql, rnd).view(np.uint32))
+    pts = (rng.random((20000, 3)) * np.array([556, 548.8, 1359.2]) + np.array([0, 0, -800])).astype(np.float32)
+    la, sa = op.lookup(pts); lb, sb = orf.lookup(pts)
+    assert np.array_equal(la, lb) and np.array_equal(sa, sb)
+    assert np.array_equal(op.fraction(leaves).view(np.uint32), orf.fraction(leaves).view(np.uint32))
+
+
+def test_initial_tree_is_uniform_depth_4():
+    """DTree::reset with total == 0 refines by 0.25^depth > 0.01 -> depth 4, 85 nodes (GP:484-487; log 'Node count = 85')."""
+    o = O.Oracle(O.default_params(), aabb=AABB)
+    o.reset(20, 0.01)
+    e = o.export(1)
+    assert e["tree_count"][0] == 85 and e["tree_depth"][0] == 4 and e["n_leaves"] == 1
+
+
+def test_empty_tree_pdf_is_uniform_and_sample_is_identity():
+    o = O.Oracle(O.default_params(), aabb=AABB)
+    o.reset(20, 0.01); o.build()
+    d = np.array([[0, 0, 1], [1, 0, 0], [0.6, 0, 0.8]], np.float32)
+    assert np.allclose(o.pdf(np.zeros(3, np.uint32), d), 1 / (4 * np.pi))
+    rnd = np.array([[0.25, 0.5] + [0] * 6], np.float32)
+    got = o.sample(np.zeros(1, np.uint32), rnd)[0]
+    ct = 2 * 0.25 - 1; st = np.sqrt(1 - ct * ct)
+    assert np.allclose(got, [st * np.cos(np.pi), st * np.sin(np.pi), ct], atol=1e-6)
+
+
+def test_refine_threshold_and_weight_halving():
+    """A leaf splits while its building weight exceeds the threshold; children get half (GP:953-955, 886-892)."""
+    o = O.Oracle(O.default_params(), aabb=AABB)
+    o.reset(20, 0.01)
+    n = 1000
+    pos, d, rad, prod, wo, *_ = _records(n, 1)
+    o.record(pos, d, rad, wo, weight=np.ones(n, np.float32))
+    o.build()
+    o.refine(100)       # 1000 -> 500 -> 250 -> 125 -> 62.5: 4 levels, 16 leaves
+    e = o.export(1)
+    assert e["n_leaves"] == 16
+    assert np.allclose(e["tree_weight"][e["s_is_leaf"] == 1], 62.5)
+
+
+def test_dtree_sample_matches_pdf_chi2():
+    """chi^2-style check in the spirit of the reference's test_chisquare.cpp: the histogram of D-tree samples
+    matches the integral of D-tree pdf over a 16x32 (cos theta, phi) grid."""
+    o = O.Oracle(O.default_params(), aabb=AABB)
+    o.reset(20, 0.01)
+    rng = np.random.default_rng(2)
+    n = 50000
+    d = rng.normal(size=(n, 3)); d[:, 2] = np.abs(d[:, 2]) * 2 + 0.5; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pos = np.tile(np.array([[100, 100, 100]], np.float32), (n, 1))
+    o.record(pos, d.astype(np.float32), rng.lognormal(0, 0.5, n).astype(np.float32), np.full(n, 0.3, np.float32), weight=np.ones(n, np.float32))
+    o.build(); o.reset(20, 0.01)
+    o.record(pos, d.astype(np.float32), rng.lognormal(0, 0.5, n).astype(np.float32), np.full(n, 0.3, np.float32), weight=np.ones(n, np.float32))
+    o.build()
+    m = 400000
+    s = o.sample(np.zeros(m, np.uint32), rng.random((m, 48), dtype=np.float32))
+    ct = np.clip(s[:, 2], -1, 1); phi = np.mod(np.arctan2(s[:, 1], s[:, 0]), 2 * np.pi)
+    H, _, _ = np.histogram2d((ct + 1) / 2, phi / (2 * np.pi), bins=[16, 32], range=[[0, 1], [0, 1]])
+    # expected: integrate pdf over each cell with a 8x8 midpoint rule (solid angle of a cell = 4 pi / (16*32))
+    g = (np.arange(8) + 0.5) / 8
+    exp = np.zeros((16, 32))
+    for i in range(16):
+        for j in range(32):
+            x = (i + g[:, None]) / 16 + 0 * g[None, :]; y = (j + g[None, :]) / 32 + 0 * g[:, None]
+            c = 2 * x - 1; sn = np.sqrt(1 - c * c); ph = 2 * np.pi * y
+            dirs = np.stack([sn * np.cos(ph), sn * np.sin(ph), c], -1).reshape(-1, 3).astype(np.float32)
+            exp[i, j] = o.pdf(np.zeros(64, np.uint32), dirs).mean() * 4 * np.pi / (16 * 32)
+    exp *= m
+    mask = exp > 5
+    chi2 = np.sum((H[mask] - exp[mask]) ** 2 / exp[mask])
+    dof = mask.sum() - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
+    assert abs(H[~mask].sum() - exp[~mask].sum()) < 0.01 * m
