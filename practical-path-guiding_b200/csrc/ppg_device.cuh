@@ -81,7 +81,12 @@ struct SceneView {
     const float4 *bsdf;       // 2 per material: {refl.rgb, bits(type | flags<<8)}, {reserved}
     const float4 *radiance;   // per emitter: rgb
     uint32_t nTris, nBvhNodes, nBsdfs, nEmitters;
-    uint32_t kBegin[4];       // brute-force layout (nTris <= PPG_BRUTE_FORCE_TRIS): triangles sorted by projection axis k; [3] also ends the k==3 (degenerate) tail
+    // brute-force layout (nTris <= PPG_BRUTE_FORCE_TRIS): coplanar triangle groups ordered by projection axis k.
+    //   groups[2q+0] = {n_u, n_v, n_d, bits(firstTri | count<<16)}   plane of the group's first triangle
+    //   groups[2q+1] = {umin, vmin, umax, vmax}                      padded bounds of the group in the projection plane
+    const float4 *groups;
+    uint32_t nGroups;
+    uint32_t kBegin[4];       // group ranges per k (k == 3: degenerate triangles, never tested)
 };
 struct Camera {             // src/sensors/perspective.cpp:271-298 for a lookAt camera
     float3 o, left, up, dir;
@@ -113,12 +118,13 @@ __device__ __forceinline__ bool tri_intersect(const float4 A, const float4 B, co
 __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, float3 d, float mint, float maxt, Hit &hit) {
     hit.t = __int_as_float(0x7f800000); hit.prim = 0xFFFFFFFFu; hit.tri = 0;
     if (sc.nTris <= PPG_BRUTE_FORCE_TRIS) {
-        // Tiny scenes (CBOX: 36 triangles, staged in shared memory): a BVH walk makes every lane of a warp reach its
-        // leaves at different times (measured: 2.5 of 32 lanes active in the triangle test).  Instead every triangle is
-        // visited in lock step (shared-memory broadcasts), grouped by projection axis k so that the component selection
-        // is a uniform branch.  A cheap conservative filter (approximate division, generous margins) rejects clear
-        // misses; only the 1-2 surviving candidates per ray run the exact reference test (IEEE division), so the
-        // hit set is identical to testing every triangle exactly.
+        // Tiny scenes (CBOX: 36 triangles in 18 coplanar groups, staged in shared memory).  A BVH walk makes every lane
+        // of a warp reach its leaves at different times (measured: 2.5 of 32 lanes active in the triangle test), so
+        // instead all lanes visit every coplanar group in lock step (shared-memory broadcasts; groups are ordered by
+        // projection axis k so that the component selection is a uniform branch).  Per group a cheap conservative
+        // filter -- approximate plane distance, hit point against the group's padded bounding rectangle -- rejects
+        // clear misses; only the triangles of surviving groups (1-2 per ray) run the exact reference test with its
+        // IEEE division, so the hit set is identical to testing every triangle exactly.
         const float tlo = mint * (1.0f - 1e-4f);
         float thi = maxt * (1.0f + 1e-4f);
 #pragma unroll 1
@@ -128,24 +134,26 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
             else if (g == 1) { o_u = o.z; o_v = o.x; o_k = o.y; d_u = d.z; d_v = d.x; d_k = d.y; }
             else { o_u = o.x; o_v = o.y; o_k = o.z; d_u = d.x; d_v = d.y; d_k = d.z; }
             const uint32_t end = sc.kBegin[g + 1];
-            for (uint32_t i = sc.kBegin[g]; i < end; ++i) {
-                const float4 A = sc.accel[3 * i];
-                const float num = A.z - o_u * A.x - o_v * A.y - o_k, den = d_u * A.x + d_v * A.y + d_k;
-                const float ta = __fdividef(num, den);
+            for (uint32_t q = sc.kBegin[g]; q < end; ++q) {
+                const float4 G0 = sc.groups[2 * q];
+                const float ta = __fdividef(G0.z - o_u * G0.x - o_v * G0.y - o_k, d_u * G0.x + d_v * G0.y + d_k);
                 if (ta >= tlo && ta <= thi) {
-                    const float4 B = sc.accel[3 * i + 1], C = sc.accel[3 * i + 2];
-                    const float hua = o_u + ta * d_u - B.x, hva = o_v + ta * d_v - B.y;
-                    const float ua = hva * B.z + hua * B.w, va = hua * C.x + hva * C.y;
-                    if (ua >= -0.01f && va >= -0.01f && ua + va <= 1.01f) {
-                        const float t = num / den;                                   // exact test, triaccel.h:147-157
-                        if (t >= mint && t <= maxt) {
-                            const float hu = o_u + t * d_u - B.x, hv = o_v + t * d_v - B.y;
-                            const float u = hv * B.z + hu * B.w, v = hu * C.x + hv * C.y;
-                            if (u >= 0.f && v >= 0.f && u + v <= 1.0f) {
-                                const uint32_t prim = __float_as_uint(C.z);
-                                if (t < hit.t || (t == hit.t && prim < hit.prim)) {
-                                    hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i;
-                                    thi = t * (1.0f + 1e-4f);
+                    const float4 G1 = sc.groups[2 * q + 1];
+                    const float pu = o_u + ta * d_u, pv = o_v + ta * d_v;
+                    if (pu >= G1.x && pv >= G1.y && pu <= G1.z && pv <= G1.w) {
+                        const uint32_t fc = __float_as_uint(G0.w), last = (fc & 0xffffu) + (fc >> 16);
+                        for (uint32_t i = fc & 0xffffu; i < last; ++i) {
+                            const float4 A = sc.accel[3 * i], B = sc.accel[3 * i + 1], C = sc.accel[3 * i + 2];
+                            const float t = (A.z - o_u * A.x - o_v * A.y - o_k) / (d_u * A.x + d_v * A.y + d_k);   // exact test, triaccel.h:147-157
+                            if (t >= mint && t <= maxt) {
+                                const float hu = o_u + t * d_u - B.x, hv = o_v + t * d_v - B.y;
+                                const float u = hv * B.z + hu * B.w, v = hu * C.x + hv * C.y;
+                                if (u >= 0.f && v >= 0.f && u + v <= 1.0f) {
+                                    const uint32_t prim = __float_as_uint(C.z);
+                                    if (t < hit.t || (t == hit.t && prim < hit.prim)) {
+                                        hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i;
+                                        thi = t * (1.0f + 1e-4f);
+                                    }
                                 }
                             }
                         }

@@ -256,7 +256,7 @@ struct ppg_integrator {
 
     // scene
     bool haveScene = false;
-    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance; DevBuf<int4> dMeta;
+    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups; DevBuf<int4> dMeta;
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
@@ -401,17 +401,47 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         tmax[t] = h3(std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)));
     }
     HostBvh bvh; build_bvh(tmin, tmax, bvh);
+    // brute-force layout for tiny scenes: coplanar groups ordered by projection axis (see bvh_intersect)
     uint32_t kBegin[4] = {0, 0, 0, 0};
+    std::vector<float> groups;
     if (nt <= PPG_BRUTE_FORCE_TRIS) {
-        // brute-force layout: order the triangles by projection axis (degenerate k==3 triangles last, never tested)
-        std::vector<int> ks(nt);
-        for (uint32_t t = 0; t < nt; ++t) { float w[9]; wald_constants(P(s->indices[3 * t]), P(s->indices[3 * t + 1]), P(s->indices[3 * t + 2]), w, ks[t]); }
-        std::vector<uint32_t> order;
-        for (int k = 0; k < 3; ++k) { kBegin[k] = (uint32_t) order.size(); for (uint32_t t = 0; t < nt; ++t) if (ks[t] == k) order.push_back(t); }
-        kBegin[3] = (uint32_t) order.size();
-        for (uint32_t t = 0; t < nt; ++t) if (ks[t] == 3) order.push_back(t);
+        struct Tri { int k; float w[9]; uint32_t t; };
+        std::vector<Tri> tris(nt);
+        for (uint32_t t = 0; t < nt; ++t) { tris[t].t = t; wald_constants(P(s->indices[3 * t]), P(s->indices[3 * t + 1]), P(s->indices[3 * t + 2]), tris[t].w, tris[t].k); }
+        static const int mod3[4] = {1, 2, 0, 1};
+        std::vector<uint32_t> order; std::vector<char> used(nt, 0);
+        for (int k = 0; k < 3; ++k) {
+            kBegin[k] = (uint32_t) (groups.size() / 8);
+            for (uint32_t a = 0; a < nt; ++a) {
+                if (used[a] || tris[a].k != k) continue;
+                // gather the triangles lying in (numerically) the same plane as `a`
+                std::vector<uint32_t> members;
+                for (uint32_t b = a; b < nt; ++b) {
+                    if (used[b] || tris[b].k != k) continue;
+                    const float *wa = tris[a].w, *wb = tris[b].w;
+                    const float scale = 1.0f + std::fabs(wa[2]);
+                    if (std::fabs(wa[0] - wb[0]) <= 1e-6f && std::fabs(wa[1] - wb[1]) <= 1e-6f && std::fabs(wa[2] - wb[2]) <= 1e-6f * scale) { members.push_back(b); used[b] = 1; }
+                }
+                float umin = 1e30f, vmin = 1e30f, umax = -1e30f, vmax = -1e30f;
+                for (uint32_t b : members)
+                    for (int c = 0; c < 3; ++c) {
+                        const H3 v = P(s->indices[3 * b + c]);
+                        umin = std::min(umin, hcomp(v, mod3[k])); umax = std::max(umax, hcomp(v, mod3[k]));
+                        vmin = std::min(vmin, hcomp(v, mod3[k + 1])); vmax = std::max(vmax, hcomp(v, mod3[k + 1]));
+                    }
+                const float pad = 0.01f * std::max(umax - umin, vmax - vmin) + 1e-3f * (1.0f + std::max(std::max(std::fabs(umin), std::fabs(umax)), std::max(std::fabs(vmin), std::fabs(vmax))));
+                const uint32_t fc = (uint32_t) order.size() | ((uint32_t) members.size() << 16);
+                float g[8] = {tris[a].w[0], tris[a].w[1], tris[a].w[2], 0.f, umin - pad, vmin - pad, umax + pad, vmax + pad};
+                memcpy(&g[3], &fc, 4);
+                groups.insert(groups.end(), g, g + 8);
+                for (uint32_t b : members) order.push_back(tris[b].t);
+            }
+        }
+        kBegin[3] = (uint32_t) (groups.size() / 8);
+        for (uint32_t t = 0; t < nt; ++t) if (tris[t].k == 3) order.push_back(t);
         bvh.order = order;
     }
+    if (groups.empty()) groups.assign(8, 0.f);
     std::vector<float> accel(12 * (size_t) nt), geom(24 * (size_t) nt); std::vector<int32_t> meta(4 * (size_t) nt);
     for (uint32_t slot = 0; slot < nt; ++slot) {
         const uint32_t t = bvh.order[slot];
@@ -454,9 +484,12 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     CK(cudaMemcpy(h->dRadiance.p, rad.data(), rad.size() * 4, cudaMemcpyHostToDevice));
     SceneView &v = h->sceneView;
     v.accel = h->dAccel.p; v.geom = h->dGeom.p; v.meta = h->dMeta.p; v.bvh = h->dBvh.p; v.bsdf = h->dBsdf.p; v.radiance = h->dRadiance.p;
+    CK(h->dGroups.alloc(groups.size() / 4));
+    CK(cudaMemcpy(h->dGroups.p, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice));
+    v.groups = h->dGroups.p; v.nGroups = (uint32_t) (groups.size() / 8);
     for (int k = 0; k < 4; ++k) v.kBegin[k] = kBegin[k];
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
-    const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 2 * s->n_bsdfs + v.nEmitters);
+    const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 2 * s->n_bsdfs + v.nEmitters + 2 * v.nGroups);
     h->sceneSmemBytes = sceneBytes <= 48 * 1024 ? (uint32_t) sceneBytes : 0u;   // small scenes (CBOX: ~9 KB) live in shared memory
     // camera (src/sensors/perspective.cpp:120-298; lookAt columns: left, up, dir, origin -- transform.cpp:191-214)
     const float *m = s->camera.to_world;

@@ -80,6 +80,7 @@ __device__ __forceinline__ SceneView stage_scene(const SceneView &g, float4 *sme
     s.bvh = copy(g.bvh, 2 * g.nBvhNodes);
     s.bsdf = copy(g.bsdf, 2 * g.nBsdfs);
     s.radiance = copy(g.radiance, g.nEmitters);
+    s.groups = copy(g.groups, 2 * g.nGroups);
     __syncthreads();
     return s;
 }
