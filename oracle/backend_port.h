@@ -80,6 +80,17 @@ struct PortBackend {
     }
     void aabb(float *mn, float *mx) const { mn[0] = t.amin.x; mn[1] = t.amin.y; mn[2] = t.amin.z; mx[0] = t.amax.x; mx[1] = t.amax.y; mx[2] = t.amax.z; }
 
+    // flat [building sums (4 per quadtree node) | building weight] per leaf in node order (the exchange buffer of SURVEY 8e)
+    size_t packSize() const { size_t n = 0; for (const auto &nd : t.nodes) if (nd.isLeaf) n += 4 * nd.dTree.building.nodes.size() + 1; return n; }
+    void packBuilding(float *buf, bool unpack) {
+        size_t o = 0;
+        for (auto &nd : t.nodes) {
+            if (!nd.isLeaf) continue;
+            for (auto &q : nd.dTree.building.nodes) for (int j = 0; j < 4; ++j) { if (unpack) q.sum[j] = buf[o]; else buf[o] = q.sum[j]; ++o; }
+            if (unpack) nd.dTree.building.weight = buf[o]; else buf[o] = nd.dTree.building.weight;
+            ++o;
+        }
+    }
     void statistics(ppg_iteration_stats &st) const;
 };
 

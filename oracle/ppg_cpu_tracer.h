@@ -321,6 +321,9 @@ public:
     std::vector<std::vector<float>> images; std::vector<float> variances;
     uint64_t totalVertices = 0, totalPaths = 0;
     ppg_stats stats;
+    // tile sharding for the 2-rank gloo test: this rank renders blocks with blk % world == rank and
+    // sums [building sums | building weights] over ranks before every build, the variance numerator and the film
+    int shardRank = 0, shardWorld = 1; ppg_allreduce_fn allreduce = nullptr; void *allreduceUser = nullptr;
     // optional per-path capture for parity tests
     std::vector<float> *captureLi = nullptr; std::vector<int32_t> *captureDepth = nullptr;
 
@@ -471,6 +474,7 @@ public:
         uint64_t verts = 0;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : verts)
         for (int blk = 0; blk < bx * by; ++blk) {
+            if (blk % shardWorld != shardRank) continue;
             const int x0 = (blk % bx) * bs, y0 = (blk / bx) * bs;
             for (int y = y0; y < std::min(y0 + bs, H); ++y)
                 for (int x = x0; x < std::min(x0 + bs, W); ++x)
@@ -494,7 +498,13 @@ public:
                         sq[0] += spec.x * spec.x; sq[1] += spec.y * spec.y; sq[2] += spec.z * spec.z; sq[3] += 1.0f;
                     }
         }
-        totalVertices += verts; totalPaths += (uint64_t) W * H * prm.spp_per_pass;
+        totalVertices += verts;
+        uint64_t px = 0;
+        for (int blk = 0; blk < bx * by; ++blk) if (blk % shardWorld == shardRank) {
+            const int x0 = (blk % bx) * bs, y0 = (blk / bx) * bs;
+            px += (uint64_t) (std::min(x0 + bs, W) - x0) * (std::min(y0 + bs, H) - y0);
+        }
+        totalPaths += px * prm.spp_per_pass;
     }
 
     // performRenderPasses, GP:1210-1329 (scheduling elided)
@@ -514,6 +524,7 @@ public:
         const int N = local * prm.spp_per_pass;
         variance = 0;
         for (int x = 0; x < W; ++x) for (int y = 0; y < H; ++y) {
+            if (shardWorld > 1 && ((y / 32) * ((W + 31) / 32) + x / 32) % shardWorld != shardRank) continue;
             const float *px = &image[((size_t) y * W + x) * 4], *sq = &sqImage[((size_t) y * W + x) * 4];
             const float iw = px[3] != 0 ? 1.0f / px[3] : 0.0f, isw = sq[3] != 0 ? 1.0f / sq[3] : 0.0f;
             float lv[3];
@@ -521,6 +532,7 @@ public:
             const float lum = lv[0] * 0.212671f + lv[1] * 0.715160f + lv[2] * 0.072169f;
             variance += std::min(lum, 10000.0f);
         }
+        if (allreduce && shardWorld > 1) allreduce(allreduceUser, &variance, 1);
         variance /= (float) W * H * (N - 1);
         if (prm.sample_combination == PPG_COMB_INVERSEVAR) variances.push_back(variance);
         st.seconds += elapsed(t0); st.passes += local; st.variance = variance; st.total_passes = passesRendered;
@@ -538,6 +550,12 @@ public:
         tree.resetAll(20, prm.d_tree_threshold, nthreads);
     }
     void buildSDTree(ppg_iteration_stats &st) {   // GP:1115-1189
+        if (allreduce && shardWorld > 1) {
+            std::vector<float> buf(tree.packSize());
+            tree.packBuilding(buf.data(), false);
+            allreduce(allreduceUser, buf.data(), buf.size());
+            tree.packBuilding(buf.data(), true);
+        }
         tree.buildAll(nthreads);
         tree.statistics(st);
         isBuilt = true;
@@ -632,6 +650,7 @@ public:
                 for (int c = 0; c < 3; ++c) out[p * 3 + c] = px[c] * iw;
             }
         }
+        if (allreduce && shardWorld > 1) allreduce(allreduceUser, out.data(), out.size());
         if (rgbOut) std::memcpy(rgbOut, out.data(), out.size() * sizeof(float));
         stats.total_passes = passesRendered; stats.total_paths = totalPaths; stats.total_vertices = totalVertices;
         stats.render_seconds = elapsed(startTime);

@@ -64,6 +64,15 @@ int ppgo_render(ppgo_handle *h, float *rgb_out, ppg_stats *stats) {
     return ok ? PPG_OK : PPG_ERR_CANCELLED;
 }
 
+int ppgo_set_shard(ppgo_handle *h, int rank, int world_size) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    h->tracer->shardRank = rank; h->tracer->shardWorld = world_size; return PPG_OK;
+}
+int ppgo_set_allreduce(ppgo_handle *h, ppg_allreduce_fn cb, void *user) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    h->tracer->allreduce = cb; h->tracer->allreduceUser = user; return PPG_OK;
+}
+
 int ppgo_step_reset(ppgo_handle *h, int iter) {
     if (!h->tracer) return PPG_ERR_NO_SCENE;
     Tracer<BackendT> &t = *h->tracer;

@@ -15,6 +15,9 @@ int ppgo_is_reference_backend(void);
 ppgo_handle *ppgo_create(const ppg_params *p, const ppg_scene_desc *scene, const float *aabb_min, const float *aabb_max, int nthreads);
 void ppgo_destroy(ppgo_handle *h);
 int ppgo_render(ppgo_handle *h, float *rgb_out, ppg_stats *stats);
+/* tile sharding + exchange callback with the product's semantics (ppg_set_shard / ppg_set_allreduce); the buffer is a HOST pointer here */
+int ppgo_set_shard(ppgo_handle *h, int rank, int world_size);
+int ppgo_set_allreduce(ppgo_handle *h, ppg_allreduce_fn cb, void *user);
 /* capture per-sample radiance of the LAST pass rendered: li (W*H*spp*3), depth (W*H*spp) -- set before ppgo_render */
 int ppgo_set_capture(ppgo_handle *h, float *li, int32_t *depth);
 /* step-wise driving (tests): iteration k reset, n passes, build */

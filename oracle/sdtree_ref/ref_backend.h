@@ -75,6 +75,16 @@ struct RefBackend {
         out6[0] = (float) s.iter; out6[1] = s.firstMoment; out6[2] = s.secondMoment; out6[3] = s.variable; out6[4] = s.batchAccumulation; out6[5] = s.batchGradient;
     }
     void aabb(float *mn, float *mx) const { const mitsuba::AABB &a = t->aabb(); for (int i = 0; i < 3; ++i) { mn[i] = a.min[i]; mx[i] = a.max[i]; } }
+    size_t packSize() const { size_t n = 0; for (const auto &nd : t->m_nodes) if (nd.isLeaf) n += 4 * nd.dTree.building.numNodes() + 1; return n; }
+    void packBuilding(float *buf, bool unpack) {
+        size_t o = 0;
+        for (auto &nd : t->m_nodes) {
+            if (!nd.isLeaf) continue;
+            for (auto &q : nd.dTree.building.m_nodes) for (int j = 0; j < 4; ++j) { if (unpack) q.setSum(j, buf[o]); else buf[o] = q.sum(j); ++o; }
+            if (unpack) nd.dTree.building.setStatisticalWeight(buf[o]); else buf[o] = nd.dTree.building.statisticalWeight();
+            ++o;
+        }
+    }
     void statistics(ppg_iteration_stats &st) const { backend_statistics(*this, st); }
 };
 

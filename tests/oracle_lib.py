@@ -27,6 +27,8 @@ def _declare(lib):
     lib.ppgo_destroy.argtypes = [H]; lib.ppgo_destroy.restype = None
     lib.ppgo_render.argtypes = [H, f32p, C.POINTER(capi.PpgStats)]
     lib.ppgo_set_capture.argtypes = [H, f32p, i32p]
+    lib.ppgo_set_shard.argtypes = [H, C.c_int, C.c_int]
+    lib.ppgo_set_allreduce.argtypes = [H, capi.ALLREDUCE_FN, C.c_void_p]
     lib.ppgo_step_reset.argtypes = [H, C.c_int]
     lib.ppgo_step_passes.argtypes = [H, C.c_int, C.c_int, f32p]
     lib.ppgo_step_build.argtypes = [H, C.POINTER(capi.PpgIterationStats)]
@@ -136,6 +138,18 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def set_shard(self, rank, world):
+        assert self.lib.ppgo_set_shard(self.h, rank, world) == 0
+
+    def set_allreduce(self, fn):
+        """fn(numpy float32 view) sums in place over ranks (host memory)."""
+        def _cb(user, ptr, n):
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(n,))
+            fn(a)
+            return 0
+        self._cb = capi.ALLREDUCE_FN(_cb)
+        assert self.lib.ppgo_set_allreduce(self.h, self._cb, None) == 0
 
     def render(self, capture=False):
         img = np.zeros((self.H, self.W, 3), np.float32)
