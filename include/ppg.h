@@ -253,6 +253,10 @@ int ppg_cancel(ppg_integrator *h);
 /* dumpSDTree wire format (GP:1191-1208, 699-711, 945-951), current sampling trees. */
 int ppg_dump_sdtree(ppg_integrator *h, const char *path);
 
+/* scene->getDestinationFile(): with dumpSDTree=true every non-final iteration writes "<destination>-NN.sdt"
+ * (NN = two-digit iteration index, GP:1191-1195, 1417-1419). NULL/"" disables the per-iteration dumps. */
+int ppg_set_destination(ppg_integrator *h, const char *destination);
+
 /* Copy the variance-estimate helper images (sum, sum of squares; W*H*4 floats
  * each: R,G,B,weight) of the last performRenderPasses to the host. Either may be NULL. */
 int ppg_get_moment_images(ppg_integrator *h, float *sum_rgbw, float *sumsq_rgbw);

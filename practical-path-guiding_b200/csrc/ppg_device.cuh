@@ -296,7 +296,6 @@ struct TreeView {
     const uint2 *bchildren;       // building pool topology (4 x uint16 per node)
     float4 *bsums;                // building pool sums (atomics target)
     float *bweight;               // per S-tree node: building statistical weight (atomics target)
-    float *adamG, *adamW;         // per S-tree node: batch gradient / weight accumulators
     float3 aabbMin, extent;       // cubified scene box (GP:850-860)
 };
 

@@ -251,6 +251,7 @@ struct ppg_integrator {
     cudaStream_t stream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::atomic<bool> cancelled{false};
+    std::string destination;
     int rank = 0, world = 1;
     ppg_allreduce_fn allreduce = nullptr; void *allreduceUser = nullptr;
 
@@ -268,7 +269,8 @@ struct ppg_integrator {
 
     // SD-tree
     uint32_t capNodes = 0; size_t capPool = 0;
-    DevBuf<uint2> dSnodes; DevBuf<float4> dLeafA; DevBuf<float> dBweight, dSampSum, dSampWeight, dAdam, dAdamG, dAdamW;
+    DevBuf<uint2> dSnodes; DevBuf<float4> dLeafA; DevBuf<float> dBweight, dSampSum, dSampWeight, dAdam, dAdamDelta, dAdamIterBefore;
+    DevBuf<uint32_t> dAdamCount, dAdamCursor, dAdamOffset; DevBuf<float4> dAdamRecA, dAdamSortA; DevBuf<float2> dAdamRecB, dAdamSortB; size_t adamCap = 0;
     DevBuf<int> dSampDepth, dBuildDepth; DevBuf<uint32_t> dSampCount, dBuildCount, dBuildBase, dScalars /* [0]=nNodes [1]=totalBuild */;
     DevBuf<uint32_t> dStable;
     DevBuf<SampNode> dSamp; DevBuf<uint2> dBchildren; DevBuf<float> dTrain /* bsums | packed tail */;
@@ -345,6 +347,9 @@ extern "C" void ppg_destroy(ppg_integrator *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     delete h;
+}
+extern "C" int ppg_set_destination(ppg_integrator *h, const char *destination) {
+    if (!h) return PPG_ERR_INVALID_ARGUMENT; h->destination = destination ? destination : ""; return PPG_OK;
 }
 extern "C" int ppg_cancel(ppg_integrator *h) { if (!h) return PPG_ERR_INVALID_ARGUMENT; h->cancelled.store(true); return PPG_OK; }
 extern "C" int ppg_set_allreduce(ppg_integrator *h, ppg_allreduce_fn cb, void *user) {
@@ -516,7 +521,12 @@ static int ensure_tree_capacity(ppg_integrator *h, uint32_t nodes, size_t pool) 
         const uint32_t cap = std::max<uint32_t>(nodes, std::max<uint32_t>(2 * h->capNodes, 1u << 16));
         CK(h->dSnodes.grow(cap, h->stream)); CK(h->dLeafA.grow(cap, h->stream)); CK(h->dBweight.grow(cap, h->stream));
         CK(h->dSampSum.grow(cap, h->stream)); CK(h->dSampWeight.grow(cap, h->stream)); CK(h->dAdam.grow(6 * (size_t) cap, h->stream));
-        CK(h->dAdamG.grow(cap, h->stream)); CK(h->dAdamW.grow(cap, h->stream)); CK(h->dSampDepth.grow(cap, h->stream));
+        CK(h->dAdamDelta.grow(cap, h->stream)); CK(h->dAdamIterBefore.grow(cap, h->stream)); CK(h->dSampDepth.grow(cap, h->stream));
+        {   // record-bucket bookkeeping must stay zero between commit launches: reallocate zeroed
+            h->dAdamCount.release(); h->dAdamCursor.release(); h->dAdamOffset.release();
+            CK(h->dAdamCount.alloc(cap)); CK(h->dAdamCursor.alloc(cap)); CK(h->dAdamOffset.alloc(cap));
+            CK(cudaMemsetAsync(h->dAdamCount.p, 0, 4 * (size_t) cap, h->stream)); CK(cudaMemsetAsync(h->dAdamCursor.p, 0, 4 * (size_t) cap, h->stream));
+        }
         CK(h->dBuildDepth.grow(cap, h->stream)); CK(h->dSampCount.grow(cap, h->stream)); CK(h->dBuildCount.grow(cap, h->stream));
         CK(h->dBuildBase.grow(cap, h->stream));
         h->capNodes = cap;
@@ -526,8 +536,8 @@ static int ensure_tree_capacity(ppg_integrator *h, uint32_t nodes, size_t pool) 
         CK(h->dSamp.grow(cap, h->stream)); CK(h->dBchildren.grow(cap, h->stream));
         h->capPool = cap;
     }
-    // bsums (4 floats per pool node) followed by the packed exchange tail (3 floats per S-tree node + scalars)
-    CK(h->dTrain.grow(4 * h->capPool + 4 * (size_t) h->capNodes + 64, h->stream));
+    // bsums (4 floats per pool node) followed by the packed exchange tail (building weights, or 6 Adam arrays; + scalars)
+    CK(h->dTrain.grow(4 * h->capPool + 6 * (size_t) h->capNodes + 64, h->stream));
     return PPG_OK;
 }
 
@@ -551,8 +561,8 @@ static int init_tree(ppg_integrator *h) {
     CK(cudaMemsetAsync(h->dSampSum.p, 0, 4 * (size_t) h->capNodes, h->stream));
     CK(cudaMemsetAsync(h->dSampWeight.p, 0, 4 * (size_t) h->capNodes, h->stream));
     CK(cudaMemsetAsync(h->dAdam.p, 0, 24 * (size_t) h->capNodes, h->stream));
-    CK(cudaMemsetAsync(h->dAdamG.p, 0, 4 * (size_t) h->capNodes, h->stream));
-    CK(cudaMemsetAsync(h->dAdamW.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dAdamCount.p, 0, 4 * (size_t) h->capNodes, h->stream));
+    CK(cudaMemsetAsync(h->dAdamCursor.p, 0, 4 * (size_t) h->capNodes, h->stream));
     CK(cudaMemsetAsync(h->dSampDepth.p, 0, 4 * (size_t) h->capNodes, h->stream));
     CK(cudaMemsetAsync(h->dSamp.p, 0, sizeof(SampNode), h->stream));          // one empty quadtree node at pool offset 0
     const uint32_t one[2] = {1u, 1u};
@@ -566,7 +576,7 @@ static int init_tree(ppg_integrator *h) {
 static TreeView tree_view(ppg_integrator *h) {
     TreeView T;
     T.snodes = h->dSnodes.p; T.stable = h->dStable.p; T.leafA = h->dLeafA.p; T.samp = h->dSamp.p; T.bchildren = h->dBchildren.p;
-    T.bsums = reinterpret_cast<float4 *>(h->dTrain.p); T.bweight = h->dBweight.p; T.adamG = h->dAdamG.p; T.adamW = h->dAdamW.p;
+    T.bsums = reinterpret_cast<float4 *>(h->dTrain.p); T.bweight = h->dBweight.p;
     T.aabbMin = make_float3(h->aabbMin[0], h->aabbMin[1], h->aabbMin[2]); T.extent = make_float3(h->extent[0], h->extent[1], h->extent[2]);
     return T;
 }
@@ -620,19 +630,18 @@ static int reset_sd_tree(ppg_integrator *h) {
 }
 
 // the one exchange step: sum the building statistics over all ranks
-__global__ void pack_tail_kernel(float *tail, const float *bweight, const float *adamG, const float *adamW, uint32_t n, int dir) {
+__global__ void pack_tail_kernel(float *tail, float *bweight, uint32_t n, int dir) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (dir == 0) { tail[i] = bweight[i]; tail[n + i] = adamG[i]; tail[2 * (size_t) n + i] = adamW[i]; }
-        else { const_cast<float *>(bweight)[i] = tail[i]; const_cast<float *>(adamG)[i] = tail[n + i]; const_cast<float *>(adamW)[i] = tail[2 * (size_t) n + i]; }
+        if (dir == 0) tail[i] = bweight[i]; else bweight[i] = tail[i];
     }
 }
 static int exchange_training_statistics(ppg_integrator *h) {
     if (!h->allreduce || h->world <= 1) return PPG_OK;
     float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;
-    pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->dAdamG.p, h->dAdamW.p, h->hNodes, 0); h->launches++;
+    pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->hNodes, 0); h->launches++;
     CK(cudaStreamSynchronize(h->stream));
-    if (h->allreduce(h->allreduceUser, h->dTrain.p, 4 * (size_t) h->hTotalBuild + 3 * (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
-    pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->dAdamG.p, h->dAdamW.p, h->hNodes, 1); h->launches++;
+    if (h->allreduce(h->allreduceUser, h->dTrain.p, 4 * (size_t) h->hTotalBuild + (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+    pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->hNodes, 1); h->launches++;
     return PPG_OK;
 }
 // a host scalar made identical on all ranks (rank 0's value wins): time-based decisions must not diverge
@@ -784,21 +793,42 @@ static int render_batch(ppg_integrator *h, int nPasses) {
         C.spatialFilter = h->prm.spatial_filter; C.directionalFilter = h->prm.directional_filter;
         C.lossMode = h->isBuilt ? h->prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE;       // GP:2152
         C.statisticalWeight = 1.0f; C.seed = h->prm.seed; C.snodes = h->dSnodes.p;
+        const bool useAdam = C.lossMode != PPG_LOSS_NONE;
+        if (useAdam) {
+            // one record per (vertex, leaf) pair; the spatial box filter touches several leaves per vertex (records beyond the capacity are dropped)
+            const size_t want = (size_t) nPaths * h->nSlabs * (h->prm.spatial_filter == PPG_SFILTER_BOX ? 2 : 1);
+            if (want > h->adamCap) {
+                h->dAdamRecA.release(); h->dAdamRecB.release(); h->dAdamSortA.release(); h->dAdamSortB.release();
+                CK(h->dAdamRecA.alloc(want)); CK(h->dAdamRecB.alloc(want)); CK(h->dAdamSortA.alloc(want)); CK(h->dAdamSortB.alloc(want));
+                h->adamCap = want;
+            }
+            CK(cudaMemsetAsync(h->dScalars.p + 3, 0, 4, h->stream));
+        }
+        C.adamRecA = h->dAdamRecA.p; C.adamRecB = h->dAdamRecB.p; C.adamTotal = h->dScalars.p + 3; C.adamCap = (uint32_t) std::min<size_t>(h->adamCap, 0xFFFFFFFFu);
         dim3 g(std::min<int>(h->gridCommit, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK)), h->nSlabs);
         h->tic(PPG_K_COMMIT);
         if (record == 1) commit_kernel<1><<<g, PPG_BLOCK, 0, h->stream>>>(C); else commit_kernel<2><<<g, PPG_BLOCK, 0, h->stream>>>(C);
         h->toc(); h->launches++;
-        if (C.lossMode != PPG_LOSS_NONE) {
-            if (h->allreduce && h->world > 1) {
-                // replicas must take identical optimiser steps: sum the gradient accumulators over ranks first
-                float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;
-                pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->dAdamG.p, h->dAdamW.p, h->hNodes, 0); h->launches++;
+        if (useAdam) {
+            // replay the sampling-fraction records leaf by leaf (see adam_seq_kernel)
+            MaintParams M = maint(h);
+            const bool multi = h->allreduce && h->world > 1;
+            float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;       // [6 x nNodes] exchange area (the building weights are packed there only at iteration end)
+            h->tic(PPG_K_ADAM);
+            adam_hist_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dAdamRecA.p, h->dScalars.p + 3, (uint32_t) h->adamCap, h->dAdamCount.p); h->launches++;
+            exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->dAdamCount.p, h->dAdamOffset.p, h->dScalars.p, h->dScalars.p + 4); h->launches++;
+            adam_scatter_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dAdamRecA.p, h->dAdamRecB.p, h->dScalars.p + 3, (uint32_t) h->adamCap, h->dAdamOffset.p,
+                                                                      h->dAdamCursor.p, h->dAdamSortA.p, h->dAdamSortB.p); h->launches++;
+            adam_seq_kernel<<<h->numSMs * 4, 128, 0, h->stream>>>(M, h->dAdamSortA.p, h->dAdamSortB.p, h->dAdamOffset.p, h->dAdamCount.p, h->dAdamCursor.p,
+                                                                  C.lossMode == PPG_LOSS_KL ? 1.0f : 2.0f, multi ? h->dAdamDelta.p : nullptr); h->launches++;
+            h->toc();
+            if (multi) {
+                // replicas replayed their own records from the common state: average them (parameter averaging) so that all ranks continue identically
+                adam_pack_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, tail, h->dAdamIterBefore.p, h->dAdamDelta.p, 1); h->launches++;
                 CK(cudaStreamSynchronize(h->stream));
-                if (h->allreduce(h->allreduceUser, tail + h->hNodes, 2 * (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
-                CK(cudaMemcpyAsync(h->dAdamG.p, tail + h->hNodes, 4 * (size_t) h->hNodes, cudaMemcpyDeviceToDevice, h->stream));
-                CK(cudaMemcpyAsync(h->dAdamW.p, tail + 2 * (size_t) h->hNodes, 4 * (size_t) h->hNodes, cudaMemcpyDeviceToDevice, h->stream));
+                if (h->allreduce(h->allreduceUser, tail, 6 * (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+                adam_merge_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, tail, h->dAdamIterBefore.p, 1.0f / (float) h->world); h->launches++;
             }
-            h->tic(PPG_K_ADAM); adam_kernel<<<h->numSMs * 2, 256, 0, h->stream>>>(maint(h), h->dAdamG.p, h->dAdamW.p, 64); h->toc(); h->launches++;
         }
     }
     h->tic(PPG_K_FILM);
@@ -821,7 +851,9 @@ static int perform_render_passes(ppg_integrator *h, float &variance, int numPass
     const int maxBatch = (int) std::max<size_t>(1, perPass ? h->pathCapacity / perPass : 1);
     int local = 0; int rcode = PPG_OK;
     while (local < numPasses) {
-        const int nb = std::min(maxBatch, numPasses - local);
+        int nb = std::min(maxBatch, numPasses - local);
+        // the sampling fraction is learned between pass-batches (theta is constant inside a wavefront): start with small batches
+        if (h->isBuilt && !h->isFinalIter && h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) nb = std::min(nb, std::max(1, local / 2));
         int rc = render_batch(h, nb);
         if (rc) return rc;
         h->passesRendered += nb; local += nb;
@@ -880,6 +912,12 @@ static ppg_iteration_stats &iter_stats(ppg_integrator *h) {
 }
 static int clear_film(ppg_integrator *h) { CK(cudaMemsetAsync(h->dFilm.p, 0, sizeof(float4) * (size_t) h->W * h->H, h->stream)); return PPG_OK; }
 
+static int dump_iteration(ppg_integrator *h) {      // dumpSDTree: "<dest>-NN.sdt", GP:1191-1195
+    if (h->destination.empty() || h->rank != 0) return PPG_OK;
+    char ext[32]; snprintf(ext, sizeof(ext), "-%02d.sdt", h->iter);
+    return ppg_dump_sdtree(h, (h->destination + ext).c_str());
+}
+
 // renderSPP, GP:1342-1426
 static int render_spp(ppg_integrator *h) {
     const int nPasses = (int) std::ceil((size_t) h->prm.budget / (float) h->prm.spp_per_pass);
@@ -909,7 +947,7 @@ static int render_spp(ppg_integrator *h) {
         t0 = std::chrono::steady_clock::now();
         rc = build_sd_tree(h, st); if (rc) return rc;
         st.build_seconds = elapsed_s(t0);
-        if (h->prm.dump_sd_tree && !h->isFinalIter) { /* dumpSDTree needs a destination file: use ppg_dump_sdtree */ }
+        if (h->prm.dump_sd_tree && !h->isFinalIter) { rc = dump_iteration(h); if (rc) return rc; }     // GP:1417-1419
         ++h->iter; h->stats.n_iterations = std::min(h->iter, PPG_MAX_ITERATIONS);
     }
     return PPG_OK;
@@ -948,6 +986,7 @@ static int render_time(ppg_integrator *h) {
         const auto t0 = std::chrono::steady_clock::now();
         rc = build_sd_tree(h, st); if (rc) return rc;
         st.build_seconds = elapsed_s(t0);
+        if (h->prm.dump_sd_tree && !h->isFinalIter) { rc = dump_iteration(h); if (rc) return rc; }     // GP:1504-1506
         ++h->iter; h->stats.n_iterations = std::min(h->iter, PPG_MAX_ITERATIONS);
         elapsedSeconds = elapsed_s(h->startTime);
         rc = sync_scalar(h, &elapsedSeconds); if (rc) return rc;

@@ -292,22 +292,18 @@ struct CommitParams {
     float statisticalWeight;       // 1.0 (0.5 only with nee=kickstart)
     uint64_t seed;
     const uint2 *snodes;
+    // sampling-fraction learning: one record per (vertex, leaf) pair, consumed by adam_seq_kernel
+    float4 *adamRecA;              // bits(leaf), product, woPdf, bsdfPdf
+    float2 *adamRecB;              // dTreePdf, statistical weight
+    uint32_t *adamTotal;           // device counter of appended records
+    uint32_t adamCap;
 };
-
-// optimizeBsdfSamplingFraction's gradient (GP:672-697) at the leaf's current theta; accumulated per leaf,
-// the Adam steps are taken by adam_kernel (batched: see DESIGN.md "Adam")
-__device__ __forceinline__ float sampling_fraction_gradient(float theta, float product, float woPdf, float bsdfPdf, float dTreePdf, float ratioPower) {
-    const float f = logistic(theta);
-    const float mixPdf = f * bsdfPdf + (1.f - f) * dTreePdf;
-    const float ratio = powf(product / mixPdf, ratioPower);
-    const float dLoss_df = -ratio / woPdf * (bsdfPdf - dTreePdf);
-    return 0.01f * theta + dLoss_df * (f * (1.f - f));
-}
 
 // DTreeWrapper::record (GP:575-584) into the building tree of S-tree node `leaf`.
 // weightDone: the statistical-weight add was already issued by the caller (warp-aggregated).
-__device__ __forceinline__ void record_into_leaf(const TreeView &T, uint32_t leaf, float3 d, float radiance, float product, float woPdf, float bsdfPdf,
+__device__ __forceinline__ void record_into_leaf(const CommitParams &C, uint32_t leaf, float3 d, float radiance, float product, float woPdf, float bsdfPdf,
                                                  float dTreePdf, float weight, bool isDelta, int directionalFilter, int lossMode, bool weightDone) {
+    const TreeView &T = C.tree;
     const float4 la = __ldg(&T.leafA[leaf]);
     if (!isDelta) {
         const bool wOk = isfinite(weight) && weight > 0.f;                    // DTree::recordIrradiance, GP:395-413
@@ -317,9 +313,18 @@ __device__ __forceinline__ void record_into_leaf(const TreeView &T, uint32_t lea
         }
     }
     if (lossMode != 0 && product > 0.f) {
-        const float g = sampling_fraction_gradient(la.z, product, woPdf, bsdfPdf, dTreePdf, lossMode == 1 ? 1.0f : 2.0f);
-        red_add(&T.adamG[leaf], g * weight);
-        red_add(&T.adamW[leaf], weight);
+        // optimizeBsdfSamplingFraction (GP:672-697) is order dependent: defer it to adam_seq_kernel, which replays the
+        // records of each leaf sequentially.  Opportunistic warp aggregation of the list cursor (one atomic per warp).
+        const unsigned m = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(C.adamTotal, (uint32_t) __popc(m));
+        base = __shfl_sync(m, base, leader);
+        const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
+        if (idx < C.adamCap) {
+            C.adamRecA[idx] = make_float4(__uint_as_float(leaf), product, woPdf, bsdfPdf);
+            C.adamRecB[idx] = make_float2(dTreePdf, weight);
+        }
     }
 }
 
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P)
             // All 32 lanes reach this call (the loop trip count is block-uniform).
             const float w = P.statisticalWeight;
             warp_aggregated_add(P.tree.bweight, leaf, w, ok && !isDelta && isfinite(w) && w > 0.f);
-            if (ok) record_into_leaf(P.tree, leaf, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, w, isDelta, P.directionalFilter, P.lossMode, true);
+            if (ok) record_into_leaf(P, leaf, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, w, isDelta, P.directionalFilter, P.lossMode, true);
         } else if (ok) {
             const float3 o = f3(v4.x, v4.y, v4.z);
             const uint32_t lo = __float_as_uint(v5.z);
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P)
                 const float3 mx = P.tree.aabbMin + P.tree.extent;
                 q.x = fminf(fmaxf(q.x, P.tree.aabbMin.x), mx.x); q.y = fminf(fmaxf(q.y, P.tree.aabbMin.y), mx.y); q.z = fminf(fmaxf(q.z, P.tree.aabbMin.z), mx.z);
                 int lv; const uint32_t splat = stree_lookup(P.snodes, P.tree.stable, P.tree.aabbMin, P.tree.extent, q, lv);
-                record_into_leaf(P.tree, splat, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, P.statisticalWeight, isDelta, P.directionalFilter, P.lossMode, false);
+                record_into_leaf(P, splat, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, P.statisticalWeight, isDelta, P.directionalFilter, P.lossMode, false);
             } else {
                 // box filter, STree::record GP:935-943 + STreeNode::record GP:823-839: every leaf overlapping the voxel-sized box
                 const float volume = voxel.x * voxel.y * voxel.z;
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P)
                     if (!(w > 0.f)) continue;
                     const uint2 c = __ldg(&P.snodes[e.n]);
                     if (c.x == 0u) {
-                        record_into_leaf(P.tree, e.n, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, w0 * w, isDelta, P.directionalFilter, P.lossMode, false);
+                        record_into_leaf(P, e.n, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, w0 * w, isDelta, P.directionalFilter, P.lossMode, false);
                     } else if (sp + 2 <= 64) {
                         float3 sz = e.sz, mn1 = e.mn;
                         if (e.axis == 0) { sz.x /= 2.f; mn1.x += sz.x; } else if (e.axis == 1) { sz.y /= 2.f; mn1.y += sz.y; } else { sz.z /= 2.f; mn1.z += sz.z; }
@@ -680,31 +685,108 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t *co
     if (threadIdx.x == 0) *totalOut = sCarry;
 }
 
-// Batched Adam (GP:69-133, 672-697): the reference takes one optimiser step whenever the accumulated weight of a
-// leaf exceeds batchSize=1, under a per-leaf spin lock, i.e. thousands of strictly sequential steps per pass.  Here
-// the gradient sums of one commit launch are applied as `steps` sequential Adam steps of the mean gradient
-// (steps = number of reference mini-batches that the accumulated weight corresponds to, capped); see DESIGN.md.
-__global__ void adam_kernel(MaintParams M, float *adamG, float *adamW, int maxSteps) {
+// ---- sampling-fraction learning (GP:69-133, 672-697) ----------------------------------------------------------------
+// The reference runs optimizeBsdfSamplingFraction under a per-leaf spin lock: every record updates the leaf's batch
+// accumulators at the CURRENT theta and takes an Adam step whenever the accumulated weight exceeds batchSize = 1.  That
+// is inherently sequential per leaf but independent across leaves, so the records of one commit launch are bucketed by
+// leaf (histogram -> scan -> scatter) and each leaf replays its bucket sequentially with the reference's exact arithmetic.
+// (The order inside a bucket is arbitrary -- as it is between the reference's worker threads.)
+
+// count records per leaf; lanes with the same leaf share one atomic
+__global__ void __launch_bounds__(256) adam_hist_kernel(const float4 *recA, const uint32_t *total, uint32_t cap, uint32_t *count) {
+    const uint32_t n = min(*total, cap);
+    const uint32_t nPad = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nPad; i += gridDim.x * blockDim.x) {
+        const bool ok = i < n;
+        const uint32_t leaf = ok ? __float_as_uint(recA[i].x) : 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(m, leaf);
+            if ((int) (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[leaf], (uint32_t) __popc(peers));
+        }
+    }
+}
+// move every record into its leaf's bucket
+__global__ void __launch_bounds__(256) adam_scatter_kernel(const float4 *recA, const float2 *recB, const uint32_t *total, uint32_t cap, const uint32_t *offset,
+                                                           uint32_t *cursor, float4 *outA, float2 *outB) {
+    const uint32_t n = min(*total, cap);
+    const uint32_t nPad = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nPad; i += gridDim.x * blockDim.x) {
+        const bool ok = i < n;
+        float4 a = make_float4(0, 0, 0, 0); float2 b = make_float2(0, 0);
+        if (ok) { a = recA[i]; b = recB[i]; }
+        const uint32_t leaf = __float_as_uint(a.x);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(m, leaf);
+            const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[leaf], (uint32_t) __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t pos = offset[leaf] + base + __popc(peers & ((1u << lane) - 1u));
+            outA[pos] = a; outB[pos] = b;
+        }
+    }
+}
+// one thread per leaf: AdamOptimizer::append / step exactly as GP:85-109, gradient as GP:672-697
+__global__ void __launch_bounds__(128) adam_seq_kernel(MaintParams M, const float4 *recA, const float2 *recB, const uint32_t *offset, uint32_t *count,
+                                                       uint32_t *cursor, float ratioPower, float *deltaIter) {
+    const uint32_t nNodes = *M.nNodes;
+    for (uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < nNodes; leaf += gridDim.x * blockDim.x) {
+        const uint32_t n = count[leaf];
+        count[leaf] = 0; cursor[leaf] = 0;              // ready for the next commit launch
+        if (deltaIter) deltaIter[leaf] = 0.f;
+        if (n == 0) continue;
+        float *st = M.adam + 6 * (size_t) leaf;
+        int iter = (int) st[0]; float m1 = st[1], m2 = st[2], variable = st[3], batchAcc = st[4], batchGrad = st[5];
+        const int iter0 = iter;
+        const uint32_t o = offset[leaf];
+        for (uint32_t k = 0; k < n; ++k) {
+            const float4 a = recA[o + k]; const float2 b = recB[o + k];
+            const float product = a.y, woPdf = a.z, bsdfPdf = a.w, dTreePdf = b.x, weight = b.y;
+            const float f = logistic(variable);
+            const float mixPdf = f * bsdfPdf + (1.f - f) * dTreePdf;
+            const float ratio = powf(product / mixPdf, ratioPower);
+            const float dLoss_df = -ratio / woPdf * (bsdfPdf - dTreePdf);
+            const float dLoss_dv = dLoss_df * (f * (1.f - f));
+            const float g = 0.01f * variable + dLoss_dv;
+            batchGrad += g * weight; batchAcc += weight;
+            if (batchAcc > 1.0f) {                      // batchSize = 1, GP:89
+                const float grad = batchGrad / batchAcc;
+                ++iter;
+                const float lr = 0.01f * sqrtf(1.f - powf(0.999f, (float) iter)) / (1.f - powf(0.9f, (float) iter));
+                m1 = 0.9f * m1 + (1.f - 0.9f) * grad;
+                m2 = 0.999f * m2 + (1.f - 0.999f) * grad * grad;
+                variable -= lr * m1 / (sqrtf(m2) + 1e-08f);
+                variable = fminf(fmaxf(variable, -20.0f), 20.0f);
+                batchGrad = 0.f; batchAcc = 0.f;
+            }
+        }
+        st[0] = (float) iter; st[1] = m1; st[2] = m2; st[3] = variable; st[4] = batchAcc; st[5] = batchGrad;
+        if (deltaIter) deltaIter[leaf] = (float) (iter - iter0);
+        float4 la = M.leafA[leaf]; la.z = variable; M.leafA[leaf] = la;
+    }
+}
+// N > 1 ranks: every rank replayed its own records from the common state; average the replicas (the exchange buffer holds
+// the SUM over ranks of [deltaIter | m1 | m2 | variable | batchAcc | batchGrad], 6 arrays of nNodes floats)
+__global__ void adam_merge_kernel(MaintParams M, const float *sum6, const float *iterBefore, float invWorld) {
     const uint32_t nNodes = *M.nNodes;
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
-        const float w = adamW[n];
-        if (!(w > 0.f) || M.snodes[n].x != 0u) { adamG[n] = 0.f; adamW[n] = 0.f; continue; }
-        const float g = adamG[n] / w;
-        float *st = M.adam + 6 * n;
-        int iter = (int) st[0]; float m1 = st[1], m2 = st[2], var = st[3];
-        int steps = (int) fminf(floorf(w / 2.f), (float) maxSteps);   // one reference step per >1 accumulated weight (two unit-weight records)
-        if (steps < 1) steps = 1;
-        for (int s = 0; s < steps; ++s) {
-            ++iter;
-            const float lr = 0.01f * sqrtf(1.f - powf(0.999f, (float) iter)) / (1.f - powf(0.9f, (float) iter));
-            m1 = 0.9f * m1 + (1.f - 0.9f) * g;
-            m2 = 0.999f * m2 + (1.f - 0.999f) * g * g;
-            var -= lr * m1 / (sqrtf(m2) + 1e-08f);
-            var = fminf(fmaxf(var, -20.0f), 20.0f);
-        }
-        st[0] = (float) iter; st[1] = m1; st[2] = m2; st[3] = var;
-        float4 la = M.leafA[n]; la.z = var; M.leafA[n] = la;
-        adamG[n] = 0.f; adamW[n] = 0.f;
+        float *st = M.adam + 6 * (size_t) n;
+        st[0] = iterBefore[n] + sum6[n];
+        st[1] = sum6[(size_t) nNodes + n] * invWorld; st[2] = sum6[2 * (size_t) nNodes + n] * invWorld; st[3] = sum6[3 * (size_t) nNodes + n] * invWorld;
+        st[4] = sum6[4 * (size_t) nNodes + n]; st[5] = sum6[5 * (size_t) nNodes + n];
+        float4 la = M.leafA[n]; la.z = st[3]; M.leafA[n] = la;
+    }
+}
+__global__ void adam_pack_kernel(MaintParams M, float *out6, float *iterBefore, const float *deltaIter, int stage) {
+    const uint32_t nNodes = *M.nNodes;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
+        const float *st = M.adam + 6 * (size_t) n;
+        if (stage == 0) { iterBefore[n] = st[0]; continue; }          // before the replay
+        out6[n] = deltaIter[n]; iterBefore[n] = st[0] - deltaIter[n];
+        out6[(size_t) nNodes + n] = st[1]; out6[2 * (size_t) nNodes + n] = st[2]; out6[3 * (size_t) nNodes + n] = st[3];
+        out6[4 * (size_t) nNodes + n] = st[4]; out6[5 * (size_t) nNodes + n] = st[5];
     }
 }
 

@@ -159,6 +159,7 @@ def load_library(path: str | None = None):
     lib.ppg_render_device.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(PpgStats)]
     lib.ppg_cancel.argtypes = [H]
     lib.ppg_dump_sdtree.argtypes = [H, C.c_char_p]
+    lib.ppg_set_destination.argtypes = [H, C.c_char_p]
     lib.ppg_get_moment_images.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     u16p = C.POINTER(C.c_uint16); u32p = C.POINTER(C.c_uint32); f32p = C.POINTER(C.c_float)
     lib.ppg_op_dtree_pdf.argtypes = [C.c_int, f32p, u16p, C.c_size_t, u32p, f32p, f32p, C.c_size_t, u32p, f32p, C.c_size_t, f32p]
@@ -173,6 +174,6 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "ppg_params_default", "ppg_params_set", "ppg_params_validate", "ppg_description", "ppg_abi_version", "ppg_create",
     "ppg_destroy", "ppg_set_scene", "ppg_set_shard", "ppg_set_allreduce", "ppg_render", "ppg_render_device", "ppg_cancel",
-    "ppg_dump_sdtree", "ppg_get_moment_images", "ppg_last_error", "ppg_op_dtree_pdf", "ppg_op_dtree_sample",
+    "ppg_dump_sdtree", "ppg_set_destination", "ppg_get_moment_images", "ppg_last_error", "ppg_op_dtree_pdf", "ppg_op_dtree_sample",
     "ppg_op_dtree_record", "ppg_op_stree_lookup",
 ]

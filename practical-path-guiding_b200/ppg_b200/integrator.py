@@ -108,6 +108,11 @@ class GuidedPathTracer:
     def cancel(self):
         self.lib.ppg_cancel(self._h)
 
+    def set_destination(self, destination: str):
+        """scene->getDestinationFile(): with dumpSDTree=true every non-final iteration writes <destination>-NN.sdt."""
+        _check(self.lib, self.lib.ppg_set_destination(self._h, destination.encode()))
+        return self
+
     def dump_sdtree(self, path: str):
         _check(self.lib, self.lib.ppg_dump_sdtree(self._h, path.encode()))
 
