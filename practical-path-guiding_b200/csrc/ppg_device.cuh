@@ -113,6 +113,24 @@ __device__ __forceinline__ bool tri_intersect(const float4 A, const float4 B, co
     return u >= 0.f && v >= 0.f && u + v <= 1.0f;
 }
 
+// exact Wald test (triaccel.h:95-158) of every triangle of coplanar group q, ray components already permuted for the group's axis
+__device__ __forceinline__ void tri_group_exact(const SceneView &sc, uint32_t q, float o_u, float o_v, float o_k, float d_u, float d_v, float d_k,
+                                                float mint, float maxt, Hit &hit) {
+    const uint32_t fc = __float_as_uint(sc.groups[2 * q].w), last = (fc & 0xffffu) + (fc >> 16);
+    for (uint32_t i = fc & 0xffffu; i < last; ++i) {
+        const float4 A = sc.accel[3 * i], B = sc.accel[3 * i + 1], C = sc.accel[3 * i + 2];
+        const float t = (A.z - o_u * A.x - o_v * A.y - o_k) / (d_u * A.x + d_v * A.y + d_k);
+        if (t >= mint && t <= maxt) {
+            const float hu = o_u + t * d_u - B.x, hv = o_v + t * d_v - B.y;
+            const float u = hv * B.z + hu * B.w, v = hu * C.x + hv * C.y;
+            if (u >= 0.f && v >= 0.f && u + v <= 1.0f) {
+                const uint32_t prim = __float_as_uint(C.z);
+                if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i; }
+            }
+        }
+    }
+}
+
 // Nearest hit in [mint, maxt]; ties on t go to the lower ORIGINAL triangle index so that the
 // result does not depend on the traversal order (same rule as the oracle).
 __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, float3 d, float mint, float maxt, Hit &hit) {
@@ -125,8 +143,13 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
         // filter -- approximate plane distance, hit point against the group's padded bounding rectangle -- rejects
         // clear misses; only the triangles of surviving groups (1-2 per ray) run the exact reference test with its
         // IEEE division, so the hit set is identical to testing every triangle exactly.
-        const float tlo = mint * (1.0f - 1e-4f);
-        float thi = maxt * (1.0f + 1e-4f);
+        // Pass 1 (converged): filter every group, remember the survivors in a bit mask (<= 32 groups; larger tiny scenes
+        // test survivors immediately).  Pass 2: every lane pops its candidates one at a time, so the expensive exact
+        // tests run with most lanes active instead of being scattered over the 18 filter iterations (measured: 3.2 of
+        // 32 lanes active and 36 % of all warp instructions when the exact test sat inside the filter loop).
+        const float tlo = mint * (1.0f - 1e-4f), thi = maxt * (1.0f + 1e-4f);
+        const bool deferred = sc.nGroups <= 32u;
+        uint32_t cand = 0, nearQ = 0xFFFFFFFFu; float nearT = __int_as_float(0x7f800000);
 #pragma unroll 1
         for (int g = 0; g < 3; ++g) {
             float o_u, o_v, o_k, d_u, d_v, d_k;
@@ -141,25 +164,29 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
                     const float4 G1 = sc.groups[2 * q + 1];
                     const float pu = o_u + ta * d_u, pv = o_v + ta * d_v;
                     if (pu >= G1.x && pv >= G1.y && pu <= G1.z && pv <= G1.w) {
-                        const uint32_t fc = __float_as_uint(G0.w), last = (fc & 0xffffu) + (fc >> 16);
-                        for (uint32_t i = fc & 0xffffu; i < last; ++i) {
-                            const float4 A = sc.accel[3 * i], B = sc.accel[3 * i + 1], C = sc.accel[3 * i + 2];
-                            const float t = (A.z - o_u * A.x - o_v * A.y - o_k) / (d_u * A.x + d_v * A.y + d_k);   // exact test, triaccel.h:147-157
-                            if (t >= mint && t <= maxt) {
-                                const float hu = o_u + t * d_u - B.x, hv = o_v + t * d_v - B.y;
-                                const float u = hv * B.z + hu * B.w, v = hu * C.x + hv * C.y;
-                                if (u >= 0.f && v >= 0.f && u + v <= 1.0f) {
-                                    const uint32_t prim = __float_as_uint(C.z);
-                                    if (t < hit.t || (t == hit.t && prim < hit.prim)) {
-                                        hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i;
-                                        thi = t * (1.0f + 1e-4f);
-                                    }
-                                }
-                            }
-                        }
+                        if (deferred) { cand |= 1u << q; if (ta < nearT) { nearT = ta; nearQ = q; } }
+                        else tri_group_exact(sc, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
                     }
                 }
             }
+        }
+        // Pass 2a (converged): every lane tests its NEAREST candidate group exactly -- almost always the true hit.
+        if (nearQ != 0xFFFFFFFFu) {
+            const uint32_t q = nearQ; cand &= ~(1u << q);
+            const int k = (q >= sc.kBegin[1]) + (q >= sc.kBegin[2]);
+            const float o_u = k == 0 ? o.y : (k == 1 ? o.z : o.x), o_v = k == 0 ? o.z : (k == 1 ? o.x : o.y), o_k = k == 0 ? o.x : (k == 1 ? o.y : o.z);
+            const float d_u = k == 0 ? d.y : (k == 1 ? d.z : d.x), d_v = k == 0 ? d.z : (k == 1 ? d.x : d.y), d_k = k == 0 ? d.x : (k == 1 ? d.y : d.z);
+            tri_group_exact(sc, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
+        }
+        // Pass 2b (rare): remaining candidates that are not clearly behind the hit found so far
+        while (cand) {
+            const uint32_t q = __ffs(cand) - 1; cand &= cand - 1u;
+            const int k = (q >= sc.kBegin[1]) + (q >= sc.kBegin[2]);
+            const float o_u = k == 0 ? o.y : (k == 1 ? o.z : o.x), o_v = k == 0 ? o.z : (k == 1 ? o.x : o.y), o_k = k == 0 ? o.x : (k == 1 ? o.y : o.z);
+            const float d_u = k == 0 ? d.y : (k == 1 ? d.z : d.x), d_v = k == 0 ? d.z : (k == 1 ? d.x : d.y), d_k = k == 0 ? d.x : (k == 1 ? d.y : d.z);
+            const float4 G0 = sc.groups[2 * q];
+            const float ta = __fdividef(G0.z - o_u * G0.x - o_v * G0.y - o_k, d_u * G0.x + d_v * G0.y + d_k);
+            if (ta <= hit.t * (1.0f + 1e-4f)) tri_group_exact(sc, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
         }
         return hit.prim != 0xFFFFFFFFu;
     }
