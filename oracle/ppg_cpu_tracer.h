@@ -134,6 +134,36 @@ struct Scene {
     std::vector<TriAccelP> accel; std::vector<BvhNode> bvh; std::vector<uint32_t> primOrder;
     // camera derived (src/sensors/perspective.cpp:120-298)
     F3 camO, camLeft, camUp, camDir; float tanX, tanY;
+    // emitter sampling (next event estimation): per emitter the area distribution over its triangles
+    // (TriMesh::prepareSamplingTable, src/librender/trimesh.cpp:388-403) and the discrete emitter choice (scene.cpp:357-381)
+    struct EmitterSampler { uint32_t firstTri, nTris; std::vector<float> cdf; float invArea; int shape; };
+    std::vector<EmitterSampler> emitterSamplers; std::vector<float> emitterCdf; float emitterNormalization = 0;
+
+    // DiscreteDistribution::sample (include/mitsuba/core/pmf.h:124-137)
+    static size_t cdfSample(const std::vector<float> &cdf, float v) {
+        const ptrdiff_t entry = std::lower_bound(cdf.begin(), cdf.end(), v) - cdf.begin();
+        size_t index = std::min(cdf.size() - 2, (size_t) std::max((ptrdiff_t) 0, entry - 1));
+        while (cdf[index + 1] - cdf[index] == 0 && index < cdf.size() - 1) ++index;
+        return index;
+    }
+    void buildEmitterSamplers() {
+        emitterSamplers.clear();
+        for (size_t e = 0; e < radiance.size(); ++e) {
+            EmitterSampler es; es.shape = -1; es.firstTri = es.nTris = 0; es.invArea = 0;
+            for (size_t sidx = 0; sidx < shapes.size(); ++sidx) if (shapes[sidx].emitter == (int) e) { es.shape = (int) sidx; es.firstTri = shapes[sidx].first_triangle; es.nTris = shapes[sidx].n_triangles; }
+            es.cdf.assign(1, 0.0f);
+            for (uint32_t t = es.firstTri; t < es.firstTri + es.nTris; ++t) {
+                const F3 p0 = P[idx[3 * t]], p1 = P[idx[3 * t + 1]], p2 = P[idx[3 * t + 2]];
+                es.cdf.push_back(es.cdf.back() + 0.5f * length(cross(p1 - p0, p2 - p0)));        // Triangle::surfaceArea (libcore/triangle.cpp:61-67)
+            }
+            const float sum = es.cdf.back();                                                     // DiscreteDistribution::normalize (pmf.h:101-114)
+            if (sum > 0) { const float nrm = 1.0f / sum; for (size_t i = 1; i < es.cdf.size(); ++i) es.cdf[i] *= nrm; es.cdf.back() = 1.0f; es.invArea = 1.0f / sum; }
+            emitterSamplers.push_back(es);
+        }
+        emitterCdf.assign(1, 0.0f);
+        for (size_t e = 0; e < emitterSamplers.size(); ++e) emitterCdf.push_back(emitterCdf.back() + 1.0f);     // getSamplingWeight() == 1
+        if (emitterCdf.back() > 0) { emitterNormalization = 1.0f / emitterCdf.back(); for (size_t i = 1; i < emitterCdf.size(); ++i) emitterCdf[i] *= emitterNormalization; emitterCdf.back() = 1.0f; }
+    }
 
     void load(const ppg_scene_desc &d) {
         P.resize(d.n_vertices); N.resize(d.n_vertices); UV.assign(2 * (size_t) d.n_vertices, 0.f);
@@ -158,6 +188,7 @@ struct Scene {
         accel.resize(d.n_triangles);
         for (uint32_t t = 0; t < d.n_triangles; ++t) triaccel_load(accel[t], P[idx[3 * t]], P[idx[3 * t + 1]], P[idx[3 * t + 2]]);
         buildBvh();
+        buildEmitterSamplers();
     }
 
     // median-split BVH over triangle centroids (quality irrelevant for parity; hit set is what matters)
@@ -271,6 +302,61 @@ static inline bool ray_intersect(const Scene &sc, F3 o, F3 d, float mint, float 
     return true;
 }
 
+// ------------------------------------------------------------------ next event estimation
+static const float kShadowEpsilon = 1e-3f;   // core/constants.h:29
+
+// Scene::evalTransmittance without media / null surfaces (src/librender/scene.cpp:619-679): 1 if unoccluded, else 0.
+// The shadow-ray query scales the epsilon WITHOUT the max(.., Epsilon) clamp (skdtree.cpp:154-158).
+static inline bool occluded(const Scene &sc, F3 p1, F3 d, float remaining) {
+    float mint = kEpsilon * std::max(std::max(std::fabs(p1.x), std::fabs(p1.y)), std::fabs(p1.z));
+    Scene::Hit h;
+    return sc.intersect(p1, d, mint, remaining * (1 - kShadowEpsilon), h);
+}
+
+struct DirectSample { F3 value, d, n; float dist, pdf; int emitter; };
+// Scene::sampleAttenuatedEmitterDirect (scene.cpp:876-897) -> AreaLight::sampleDirect (emitters/area.cpp:158-173)
+// -> Shape::sampleDirect (shape.cpp:102-115) -> TriMesh::samplePosition (trimesh.cpp:412-423) -> Triangle::sample (libcore/triangle.cpp:24-59)
+static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float sx, float sy, DirectSample &out) {
+    if (sc.emitterSamplers.empty()) return false;
+    const size_t ei = Scene::cdfSample(sc.emitterCdf, sx);
+    const float emPdf = sc.emitterCdf[ei + 1] - sc.emitterCdf[ei];
+    sx = (sx - sc.emitterCdf[ei]) / (sc.emitterCdf[ei + 1] - sc.emitterCdf[ei]);            // sampleReuse
+    const Scene::EmitterSampler &E = sc.emitterSamplers[ei];
+    if (E.nTris == 0) return false;
+    const size_t ti = Scene::cdfSample(E.cdf, sy);
+    sy = (sy - E.cdf[ti]) / (E.cdf[ti + 1] - E.cdf[ti]);
+    const uint32_t t = E.firstTri + (uint32_t) ti;
+    const F3 p0 = sc.P[sc.idx[3 * t]], p1 = sc.P[sc.idx[3 * t + 1]], p2 = sc.P[sc.idx[3 * t + 2]];
+    const float a = std::sqrt(std::max(0.0f, 1.0f - sx));                                      // warp::squareToUniformTriangle
+    const float bx = 1 - a, by = a * sy;
+    const F3 sideA = p1 - p0, sideB = p2 - p0;
+    const F3 p = p0 + (sideA * bx) + (sideB * by);
+    F3 n;
+    if (sc.shapes[E.shape].has_normals) n = normalize(sc.N[sc.idx[3 * t]] * (1.0f - bx - by) + sc.N[sc.idx[3 * t + 1]] * bx + sc.N[sc.idx[3 * t + 2]] * by);
+    else n = normalize(cross(sideA, sideB));
+    float pdf = E.invArea;
+    F3 d = p - ref;
+    const float distSquared = dot(d, d);
+    const float dist = std::sqrt(distSquared);
+    d = d * (1.0f / dist);
+    const float dp = std::fabs(dot(d, n));
+    pdf *= dp != 0 ? (distSquared / dp) : 0.0f;
+    out.d = d; out.n = n; out.dist = dist; out.emitter = (int) ei;
+    if (dot(d, refN) >= 0 && dot(d, n) < 0 && pdf != 0) out.value = sc.radiance[ei] * (1.0f / pdf);
+    else { out.pdf = 0; out.value = f3(0, 0, 0); return false; }
+    if (occluded(sc, ref, d, dist)) { out.pdf = pdf * emPdf; out.value = f3(0, 0, 0); return true; }
+    out.value = out.value * (1.0f / emPdf);          // value *= transmittance / emPdf
+    out.pdf = pdf * emPdf;
+    return true;
+}
+// Scene::pdfEmitterDirect (scene.cpp:949-952) for an emitter hit found by BSDF / guiding sampling (dRec.setQuery, records.inl:170-178)
+static inline float pdf_emitter_direct(const Scene &sc, int emitter, F3 refN, F3 d, F3 n, float dist) {
+    if (!(dot(d, refN) >= 0 && dot(d, n) < 0)) return 0.0f;                                    // AreaLight::pdfDirect (area.cpp:175-183)
+    const float pdfPos = sc.emitterSamplers[emitter].invArea;
+    return pdfPos * (dist * dist) / std::fabs(dot(d, n)) * (1.0f * sc.emitterNormalization);   // Shape::pdfDirect (shape.cpp:117-126) * pdfEmitterDiscrete
+}
+static inline float mi_weight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); }   // GP:2247-2250
+
 // ------------------------------------------------------------------ BSDF: diffuse (+ twosided)
 // src/libcore/warp.cpp:81-102 then :43-52
 static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
@@ -315,8 +401,9 @@ struct CommitRec {   // GP:1713-1724 Vertex, minus the tree pointer (kept as bac
 template <class Backend> class Tracer {
 public:
     ppg_params prm; Scene sc; Backend tree; int nthreads;
-    bool isBuilt = false, isFinalIter = false; int iter = 0; int passesRendered = 0;
+    bool isBuilt = false, isFinalIter = false, doNee = false; int iter = 0; int passesRendered = 0;
     int W, H;
+    bool doNeeWithSpp(int spp) const { return prm.nee == PPG_NEE_NEVER ? false : (prm.nee == PPG_NEE_KICKSTART ? spp < 128 : true); }   // GP:1331-1340
     std::vector<float> image, sqImage, film;     // W*H*4 (r,g,b,weight)
     std::vector<std::vector<float>> images; std::vector<float> variances;
     uint64_t totalVertices = 0, totalPaths = 0;
@@ -399,6 +486,38 @@ public:
                     bsdfWeight = (woPdf == 0) ? f3(0, 0, 0) : result * (1.0f / woPdf);   // Spectrum::operator/(Float) multiplies by the reciprocal
                 }
             }
+            // ---- luminaire sampling, GP:1964-2021 (DirectSamplingRecord dRec(its): refN = shading normal unless the BSDF is two-sided / transmissive, records.inl:160-164)
+            const F3 refN = (bsdf.flags & PPG_BSDF_FLAG_TWOSIDED) ? f3(0, 0, 0) : its.shN;
+            if (doNee) {
+                const float ex = rng.next1D(), ey = rng.next1D();
+                DirectSample ds;
+                if (sample_emitter_direct(sc, its.p, refN, ex, ey, ds) && !is_zero(ds.value)) {
+                    const F3 dl = its.toLocal(ds.d);
+                    const float woDotGeoN2 = dot(its.geoN, ds.d);
+                    if (!prm.strict_normals || woDotGeoN2 * dl.z > 0) {
+                        const F3 bsdfVal = bsdf_eval(bsdf, its.wi, dl);
+                        float nWoPdf = 0, nBsdfPdf = 0, nDTreePdf = 0;
+                        {   // pdfMat (emitter->isOnSurface() && measure == ESolidAngle always hold for area lights)
+                            if (!isBuilt || !leaf) { nWoPdf = nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl); }
+                            else {
+                                nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl);
+                                if (!std::isfinite(nBsdfPdf)) nWoPdf = 0;
+                                else { nDTreePdf = tree.pdf(leaf, &ds.d.x); nWoPdf = frac * nBsdfPdf + (1 - frac) * nDTreePdf; }
+                            }
+                        }
+                        const float weight = mi_weight(ds.pdf, nWoPdf);
+                        const F3 value = ds.value * bsdfVal;
+                        const F3 L = throughput * value * weight;
+                        if (!isFinalIter && prm.nee != PPG_NEE_ALWAYS && leaf) {               // GP:1999-2016: half-weight vertex for the sampled light direction
+                            CommitRec v; v.o = its.p; v.d = ds.d; v.voxel = f3(voxel[0], voxel[1], voxel[2]);
+                            v.throughput = throughput * bsdfVal * (1.0f / ds.pdf); v.bsdfVal = bsdfVal; v.radiance = L;
+                            v.woPdf = ds.pdf; v.bsdfPdf = nBsdfPdf; v.dTreePdf = nDTreePdf; v.isDelta = false;
+                            commit(leaf, v, 0.5f, isBuilt ? prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE, sampleIndex, 32u + (uint32_t) depth);
+                        }
+                        recordRadiance(L);
+                    }
+                }
+            }
             if (is_zero(bsdfWeight)) break;                                                     // GP:2024-2025
             const F3 wo = its.toWorld(bs.wo);
             const float woDotGeoN = dot(its.geoN, wo);
@@ -415,15 +534,17 @@ public:
             }
             const bool isDelta = bs.delta;
             {
-                const float a = woPdf * woPdf;                       // miWeight(woPdf, 0), GP:2247-2250
-                const float weight = a / (a + 0.0f);
+                float emitterPdf = 0;                                                            // GP:2084-2087
+                if (doNee && !isDelta && !is_zero(value)) emitterPdf = pdf_emitter_direct(sc, sc.shapes[next.shape].emitter, refN, d, next.shN, next.t);
+                const float weight = mi_weight(woPdf, emitterPdf);
                 const F3 L = throughput * value * weight;
                 if (!is_zero(L)) recordRadiance(L);
                 if ((!isDelta || prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) && leaf && nVertices < 32 && !isFinalIter) {   // GP:2093-2110
                     if (1 / woPdf > 0) {
                         CommitRec &v = vtx[nVertices]; vLeaf[nVertices] = leaf;
                         v.o = o; v.d = d; v.voxel = f3(voxel[0], voxel[1], voxel[2]); v.throughput = throughput;
-                        v.bsdfVal = bsdfWeight * woPdf; v.radiance = L; v.woPdf = woPdf; v.bsdfPdf = bsdfPdf; v.dTreePdf = dTreePdf; v.isDelta = isDelta;
+                        v.bsdfVal = bsdfWeight * woPdf; v.radiance = (prm.nee == PPG_NEE_ALWAYS) ? f3(0, 0, 0) : L;
+                        v.woPdf = woPdf; v.bsdfPdf = bsdfPdf; v.dTreePdf = dTreePdf; v.isDelta = isDelta;
                         ++nVertices;
                     }
                 }
@@ -444,7 +565,8 @@ public:
         depthOut = depth;
         if (nVertices > 0 && !isFinalIter) {                                                    // GP:2150-2154
             const int loss = isBuilt ? prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE;
-            for (int i = 0; i < nVertices; ++i) commit(vLeaf[i], vtx[i], 1.0f, loss, sampleIndex, (uint32_t) i);
+            const float w = (prm.nee == PPG_NEE_KICKSTART && doNee) ? 0.5f : 1.0f;               // GP:2152
+            for (int i = 0; i < nVertices; ++i) commit(vLeaf[i], vtx[i], w, loss, sampleIndex, (uint32_t) i);
         }
         return LiAcc;
     }
@@ -569,6 +691,7 @@ public:
         bool result = true; float currentVarAtEnd = std::numeric_limits<float>::infinity();
         while (result && passesRendered < nPasses) {
             const int sppRendered = passesRendered * prm.spp_per_pass;
+            doNee = doNeeWithSpp(sppRendered);                                                   // GP:1362
             int remainingPasses = nPasses - passesRendered;
             int passesThisIteration = std::min(remainingPasses, 1 << iter);
             if (remainingPasses - passesThisIteration < 2 * passesThisIteration) passesThisIteration = remainingPasses;
@@ -599,6 +722,7 @@ public:
         float currentVarAtEnd = std::numeric_limits<float>::infinity(), elapsedSeconds = 0;
         while (result && elapsedSeconds < nSeconds) {
             const int sppRendered = passesRendered * prm.spp_per_pass;
+            doNee = doNeeWithSpp(sppRendered);                                                   // GP:1452
             float remainingTime = nSeconds - elapsedSeconds;
             const int passesThisIteration = 1 << iter;
             ppg_iteration_stats &st = stats.iterations[std::min(iter, PPG_MAX_ITERATIONS - 1)]; beginIterStats(st, passesThisIteration);

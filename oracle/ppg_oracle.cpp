@@ -78,6 +78,7 @@ int ppgo_step_reset(ppgo_handle *h, int iter) {
     Tracer<BackendT> &t = *h->tracer;
     if (iter == 0) { t.passesRendered = 0; t.startTime = std::chrono::steady_clock::now(); }
     t.iter = iter; std::fill(t.film.begin(), t.film.end(), 0.f);
+    t.doNee = t.doNeeWithSpp(t.passesRendered * t.prm.spp_per_pass);
     t.resetSDTree();
     return PPG_OK;
 }

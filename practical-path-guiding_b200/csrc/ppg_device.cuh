@@ -86,6 +86,11 @@ struct SceneView {
     //   groups[2q+1] = {umin, vmin, umax, vmax}                      padded bounds of the group in the projection plane
     const float4 *groups;
     uint32_t nGroups;
+    // next event estimation (nee != never): discrete emitter choice + per-emitter triangle area distribution
+    //   emitterCdf[nEmitters+1]; emitterInfo[e] = {bits(firstTri into emitterGeom), bits(nTris), invArea, bits(cdfOffset into emitterTriCdf)}
+    //   emitterGeom: 6 float4 per emitter triangle in ORIGINAL order (same packing as geom); emitterFlags[e] bit0: has vertex normals
+    const float *emitterCdf; const float4 *emitterInfo; const float *emitterTriCdf; const float4 *emitterGeom; const uint32_t *emitterFlags;
+    float emitterNormalization;
     uint32_t kBegin[4];       // group ranges per k (k == 3: degenerate triangles, never tested)
 };
 struct Camera {             // src/sensors/perspective.cpp:271-298 for a lookAt camera
@@ -95,6 +100,37 @@ struct Camera {             // src/sensors/perspective.cpp:271-298 for a lookAt 
 };
 
 struct Hit { float t, u, v; uint32_t tri; uint32_t prim; };
+
+// Scene access.  Small scenes are staged into dynamic shared memory; the accessor indexes the extern __shared__ symbol
+// directly so that the compiler KNOWS the address space (a generic pointer that may hold either a shared or a global
+// address was once compiled to LDG and faulted).  SMEM == false reads HBM through the read-only path.
+extern __shared__ float4 ppg_scene_smem[];
+template <bool SMEM> struct SceneAccess {
+    const SceneView &g;
+    uint32_t oGeom, oMeta, oBvh, oBsdf, oRadiance, oGroups;      // float4 offsets of the staged sections (accel at 0)
+    __device__ __forceinline__ SceneAccess(const SceneView &v) : g(v) {
+        oGeom = 3 * v.nTris; oMeta = oGeom + 6 * v.nTris; oBvh = oMeta + v.nTris; oBsdf = oBvh + 2 * v.nBvhNodes;
+        oRadiance = oBsdf + 2 * v.nBsdfs; oGroups = oRadiance + v.nEmitters;
+    }
+    __device__ __forceinline__ float4 accel(uint32_t i) const { return SMEM ? ppg_scene_smem[i] : __ldg(&g.accel[i]); }
+    __device__ __forceinline__ float4 geom(uint32_t i) const { return SMEM ? ppg_scene_smem[oGeom + i] : __ldg(&g.geom[i]); }
+    __device__ __forceinline__ int4 meta(uint32_t i) const {
+        if (SMEM) { const float4 m = ppg_scene_smem[oMeta + i]; return make_int4(__float_as_int(m.x), __float_as_int(m.y), __float_as_int(m.z), __float_as_int(m.w)); }
+        return __ldg(&g.meta[i]);
+    }
+    __device__ __forceinline__ float4 bvh(uint32_t i) const { return SMEM ? ppg_scene_smem[oBvh + i] : __ldg(&g.bvh[i]); }
+    __device__ __forceinline__ float4 bsdf(uint32_t i) const { return SMEM ? ppg_scene_smem[oBsdf + i] : __ldg(&g.bsdf[i]); }
+    __device__ __forceinline__ float4 radiance(uint32_t i) const { return SMEM ? ppg_scene_smem[oRadiance + i] : __ldg(&g.radiance[i]); }
+    __device__ __forceinline__ float4 groups(uint32_t i) const { return SMEM ? ppg_scene_smem[oGroups + i] : __ldg(&g.groups[i]); }
+    // block-cooperative staging (call once, all threads): accel | geom | meta | bvh | bsdf | radiance | groups
+    __device__ __forceinline__ void stage() const {
+        if (!SMEM) return;
+        auto copy = [&](uint32_t off, const float4 *src, uint32_t n) { for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) ppg_scene_smem[off + i] = src[i]; };
+        copy(0, g.accel, 3 * g.nTris); copy(oGeom, g.geom, 6 * g.nTris); copy(oMeta, reinterpret_cast<const float4 *>(g.meta), g.nTris);
+        copy(oBvh, g.bvh, 2 * g.nBvhNodes); copy(oBsdf, g.bsdf, 2 * g.nBsdfs); copy(oRadiance, g.radiance, g.nEmitters); copy(oGroups, g.groups, 2 * g.nGroups);
+        __syncthreads();
+    }
+};
 
 __device__ __forceinline__ bool tri_intersect(const float4 A, const float4 B, const float4 C, float3 o, float3 d, float mint, float maxt,
                                               float &u, float &v, float &t) {
@@ -114,11 +150,12 @@ __device__ __forceinline__ bool tri_intersect(const float4 A, const float4 B, co
 }
 
 // exact Wald test (triaccel.h:95-158) of every triangle of coplanar group q, ray components already permuted for the group's axis
-__device__ __forceinline__ void tri_group_exact(const SceneView &sc, uint32_t q, float o_u, float o_v, float o_k, float d_u, float d_v, float d_k,
+template <class Acc>
+__device__ __forceinline__ void tri_group_exact(const Acc &A_, uint32_t q, float o_u, float o_v, float o_k, float d_u, float d_v, float d_k,
                                                 float mint, float maxt, Hit &hit) {
-    const uint32_t fc = __float_as_uint(sc.groups[2 * q].w), last = (fc & 0xffffu) + (fc >> 16);
+    const uint32_t fc = __float_as_uint(A_.groups(2 * q).w), last = (fc & 0xffffu) + (fc >> 16);
     for (uint32_t i = fc & 0xffffu; i < last; ++i) {
-        const float4 A = sc.accel[3 * i], B = sc.accel[3 * i + 1], C = sc.accel[3 * i + 2];
+        const float4 A = A_.accel(3 * i), B = A_.accel(3 * i + 1), C = A_.accel(3 * i + 2);
         const float t = (A.z - o_u * A.x - o_v * A.y - o_k) / (d_u * A.x + d_v * A.y + d_k);
         if (t >= mint && t <= maxt) {
             const float hu = o_u + t * d_u - B.x, hv = o_v + t * d_v - B.y;
@@ -133,9 +170,11 @@ __device__ __forceinline__ void tri_group_exact(const SceneView &sc, uint32_t q,
 
 // Nearest hit in [mint, maxt]; ties on t go to the lower ORIGINAL triangle index so that the
 // result does not depend on the traversal order (same rule as the oracle).
-__device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, float3 d, float mint, float maxt, Hit &hit) {
+template <class Acc>
+__device__ __forceinline__ bool bvh_intersect(const Acc &A_, float3 o, float3 d, float mint, float maxt, Hit &hit) {
+    const SceneView &sc = A_.g;
     hit.t = __int_as_float(0x7f800000); hit.prim = 0xFFFFFFFFu; hit.tri = 0;
-    if (sc.nTris <= PPG_BRUTE_FORCE_TRIS) {
+    if (sc.nGroups != 0u) {      // host sets nGroups only for tiny scenes (<= PPG_BRUTE_FORCE_TRIS triangles in <= 32 coplanar groups)
         // Tiny scenes (CBOX: 36 triangles in 18 coplanar groups, staged in shared memory).  A BVH walk makes every lane
         // of a warp reach its leaves at different times (measured: 2.5 of 32 lanes active in the triangle test), so
         // instead all lanes visit every coplanar group in lock step (shared-memory broadcasts; groups are ordered by
@@ -143,12 +182,10 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
         // filter -- approximate plane distance, hit point against the group's padded bounding rectangle -- rejects
         // clear misses; only the triangles of surviving groups (1-2 per ray) run the exact reference test with its
         // IEEE division, so the hit set is identical to testing every triangle exactly.
-        // Pass 1 (converged): filter every group, remember the survivors in a bit mask (<= 32 groups; larger tiny scenes
-        // test survivors immediately).  Pass 2: every lane pops its candidates one at a time, so the expensive exact
+        // Pass 1 (converged): filter every group, remember the survivors in a bit mask (<= 32 groups).  Pass 2: every lane pops its candidates one at a time, so the expensive exact
         // tests run with most lanes active instead of being scattered over the 18 filter iterations (measured: 3.2 of
         // 32 lanes active and 36 % of all warp instructions when the exact test sat inside the filter loop).
         const float tlo = mint * (1.0f - 1e-4f), thi = maxt * (1.0f + 1e-4f);
-        const bool deferred = sc.nGroups <= 32u;
         uint32_t cand = 0, nearQ = 0xFFFFFFFFu; float nearT = __int_as_float(0x7f800000);
 #pragma unroll 1
         for (int g = 0; g < 3; ++g) {
@@ -157,15 +194,15 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
             else if (g == 1) { o_u = o.z; o_v = o.x; o_k = o.y; d_u = d.z; d_v = d.x; d_k = d.y; }
             else { o_u = o.x; o_v = o.y; o_k = o.z; d_u = d.x; d_v = d.y; d_k = d.z; }
             const uint32_t end = sc.kBegin[g + 1];
+#pragma unroll 1
             for (uint32_t q = sc.kBegin[g]; q < end; ++q) {
-                const float4 G0 = sc.groups[2 * q];
+                const float4 G0 = A_.groups(2 * q);
                 const float ta = __fdividef(G0.z - o_u * G0.x - o_v * G0.y - o_k, d_u * G0.x + d_v * G0.y + d_k);
                 if (ta >= tlo && ta <= thi) {
-                    const float4 G1 = sc.groups[2 * q + 1];
+                    const float4 G1 = A_.groups(2 * q + 1);
                     const float pu = o_u + ta * d_u, pv = o_v + ta * d_v;
                     if (pu >= G1.x && pv >= G1.y && pu <= G1.z && pv <= G1.w) {
-                        if (deferred) { cand |= 1u << q; if (ta < nearT) { nearT = ta; nearQ = q; } }
-                        else tri_group_exact(sc, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
+                        cand |= 1u << q; if (ta < nearT) { nearT = ta; nearQ = q; }
                     }
                 }
             }
@@ -176,7 +213,7 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
             const int k = (q >= sc.kBegin[1]) + (q >= sc.kBegin[2]);
             const float o_u = k == 0 ? o.y : (k == 1 ? o.z : o.x), o_v = k == 0 ? o.z : (k == 1 ? o.x : o.y), o_k = k == 0 ? o.x : (k == 1 ? o.y : o.z);
             const float d_u = k == 0 ? d.y : (k == 1 ? d.z : d.x), d_v = k == 0 ? d.z : (k == 1 ? d.x : d.y), d_k = k == 0 ? d.x : (k == 1 ? d.y : d.z);
-            tri_group_exact(sc, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
+            tri_group_exact(A_, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
         }
         // Pass 2b (rare): remaining candidates that are not clearly behind the hit found so far
         while (cand) {
@@ -184,16 +221,16 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
             const int k = (q >= sc.kBegin[1]) + (q >= sc.kBegin[2]);
             const float o_u = k == 0 ? o.y : (k == 1 ? o.z : o.x), o_v = k == 0 ? o.z : (k == 1 ? o.x : o.y), o_k = k == 0 ? o.x : (k == 1 ? o.y : o.z);
             const float d_u = k == 0 ? d.y : (k == 1 ? d.z : d.x), d_v = k == 0 ? d.z : (k == 1 ? d.x : d.y), d_k = k == 0 ? d.x : (k == 1 ? d.y : d.z);
-            const float4 G0 = sc.groups[2 * q];
+            const float4 G0 = A_.groups(2 * q);
             const float ta = __fdividef(G0.z - o_u * G0.x - o_v * G0.y - o_k, d_u * G0.x + d_v * G0.y + d_k);
-            if (ta <= hit.t * (1.0f + 1e-4f)) tri_group_exact(sc, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
+            if (ta <= hit.t * (1.0f + 1e-4f)) tri_group_exact(A_, q, o_u, o_v, o_k, d_u, d_v, d_k, mint, maxt, hit);
         }
         return hit.prim != 0xFFFFFFFFu;
     }
     const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     uint32_t stack[32]; int sp = 0; uint32_t node = 0;
     for (;;) {
-        const float4 n0 = sc.bvh[2 * node], n1 = sc.bvh[2 * node + 1];
+        const float4 n0 = A_.bvh(2 * node), n1 = A_.bvh(2 * node + 1);
         float t0 = mint, t1 = fminf(maxt, hit.t);
         bool miss = false;
         {
@@ -212,7 +249,7 @@ __device__ __forceinline__ bool bvh_intersect(const SceneView &sc, float3 o, flo
             const uint32_t left = __float_as_uint(n0.w), count = __float_as_uint(n1.w);
             if (count) {
                 for (uint32_t i = left; i < left + count; ++i) {
-                    const float4 A = sc.accel[3 * i], B = sc.accel[3 * i + 1], C = sc.accel[3 * i + 2];
+                    const float4 A = A_.accel(3 * i), B = A_.accel(3 * i + 1), C = A_.accel(3 * i + 2);
                     float u, v, t;
                     if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
                         const uint32_t prim = __float_as_uint(C.z);
@@ -239,9 +276,10 @@ struct Its {
 };
 
 // fillIntersectionRecord (render/skdtree.h:343-428) + computeShadingFrame (libcore/util.cpp:603-608)
-__device__ __forceinline__ void fill_its(const SceneView &sc, const Hit &h, float3 d, Its &its) {
-    const float4 g0 = sc.geom[6 * h.tri], g1 = sc.geom[6 * h.tri + 1], g2 = sc.geom[6 * h.tri + 2];
-    const int4 m = sc.meta[h.tri];
+template <class Acc>
+__device__ __forceinline__ void fill_its(const Acc &A_, const Hit &h, float3 d, Its &its) {
+    const float4 g0 = A_.geom(6 * h.tri), g1 = A_.geom(6 * h.tri + 1), g2 = A_.geom(6 * h.tri + 2);
+    const int4 m = A_.meta(h.tri);
     const float3 p0 = f3(g0.x, g0.y, g0.z), p1 = f3(g1.x, g1.y, g1.z), p2 = f3(g2.x, g2.y, g2.z);
     const float3 b = f3(1 - h.u - h.v, h.u, h.v);
     its.p = p0 * b.x + p1 * b.y + p2 * b.z;
@@ -250,7 +288,7 @@ __device__ __forceinline__ void fill_its(const SceneView &sc, const Hit &h, floa
     const float len = sqrtf(dot(faceN, faceN));
     if (!is_zero(faceN)) faceN = faceN * (1.0f / len);
     if (m.z & 1) {
-        const float4 h0 = sc.geom[6 * h.tri + 3], h1 = sc.geom[6 * h.tri + 4], h2 = sc.geom[6 * h.tri + 5];
+        const float4 h0 = A_.geom(6 * h.tri + 3), h1 = A_.geom(6 * h.tri + 4), h2 = A_.geom(6 * h.tri + 5);
         const float3 n0 = f3(g0.w, h0.x, h0.y), n1 = f3(g1.w, h1.x, h1.y), n2 = f3(g2.w, h2.x, h2.y);
         its.shN = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
         if (dot(faceN, its.shN) < 0.f) faceN = -faceN;
@@ -279,8 +317,9 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 }
 #define PPG_BSDF_TWOSIDED 1u
 struct Bsdf { float3 refl; uint32_t type, flags; };
-__device__ __forceinline__ Bsdf load_bsdf(const SceneView &sc, int idx) {
-    const float4 a = sc.bsdf[2 * idx];
+template <class Acc>
+__device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
+    const float4 a = A_.bsdf(2 * idx);
     Bsdf b; b.refl = f3(a.x, a.y, a.z);
     const uint32_t tf = __float_as_uint(a.w); b.type = tf & 0xffu; b.flags = tf >> 8;
     return b;
@@ -538,5 +577,67 @@ __device__ __forceinline__ void dtree_record_irradiance(const uint2 *__restrict_
 }
 
 __device__ __forceinline__ float logistic(float x) { return 1.f / (1.f + expf(-x)); }   // GP:64-66
+
+// ------------------------------------------------------------------ next event estimation (GP:1964-2021)
+#define PPG_SHADOW_EPSILON 1e-3f
+__device__ __forceinline__ float mi_weight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); }   // GP:2247-2250
+
+// DiscreteDistribution::sample (include/mitsuba/core/pmf.h:124-137): lower_bound on the cdf, clamp, skip empty entries
+__device__ __forceinline__ uint32_t cdf_sample(const float *__restrict__ cdf, uint32_t size /* entries incl. leading 0 */, float v) {
+    uint32_t lo = 0, hi = size;                       // first index with cdf[idx] >= v
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cdf[mid] < v) lo = mid + 1; else hi = mid; }
+    int index = (int) lo - 1; if (index < 0) index = 0; if ((uint32_t) index > size - 2) index = (int) size - 2;
+    while (cdf[index + 1] - cdf[index] == 0.f && (uint32_t) index < size - 1) ++index;
+    return (uint32_t) index;
+}
+
+struct DirectSample { float3 value, d; float pdf; };
+// Scene::sampleAttenuatedEmitterDirect (scene.cpp:876-897) -> AreaLight::sampleDirect (area.cpp:158-173) -> Shape::sampleDirect
+// (shape.cpp:102-115) -> TriMesh::samplePosition (trimesh.cpp:412-423) -> Triangle::sample (libcore/triangle.cpp:24-59);
+// visibility (Scene::evalTransmittance, scene.cpp:619-679) is tested by the caller.  Returns false when the sample carries nothing.
+template <class Acc>
+__device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref, float3 refN, float sx, float sy, DirectSample &out, float &dist) {
+    const SceneView &sc = A_.g;        // the emitter tables stay in HBM (read-only path)
+    const uint32_t ei = cdf_sample(sc.emitterCdf, sc.nEmitters + 1, sx);
+    const float c0 = sc.emitterCdf[ei], c1 = sc.emitterCdf[ei + 1];
+    const float emPdf = c1 - c0;
+    sx = (sx - c0) / (c1 - c0);
+    const float4 info = sc.emitterInfo[ei];
+    const uint32_t first = __float_as_uint(info.x), nTris = __float_as_uint(info.y), cdfOff = __float_as_uint(info.w);
+    if (nTris == 0u) return false;
+    const float *tcdf = sc.emitterTriCdf + cdfOff;
+    const uint32_t ti = cdf_sample(tcdf, nTris + 1, sy);
+    sy = (sy - tcdf[ti]) / (tcdf[ti + 1] - tcdf[ti]);
+    const uint32_t t = first + ti;
+    const float4 g0 = sc.emitterGeom[6 * t], g1 = sc.emitterGeom[6 * t + 1], g2 = sc.emitterGeom[6 * t + 2];
+    const float3 p0 = f3(g0.x, g0.y, g0.z), p1 = f3(g1.x, g1.y, g1.z), p2 = f3(g2.x, g2.y, g2.z);
+    const float a = sqrtf(fmaxf(0.0f, 1.0f - sx));                                             // warp::squareToUniformTriangle
+    const float bx = 1.f - a, by = a * sy;
+    const float3 sideA = p1 - p0, sideB = p2 - p0;
+    const float3 p = p0 + (sideA * bx) + (sideB * by);
+    float3 n;
+    if (sc.emitterFlags[ei] & 1u) {
+        const float4 h0 = sc.emitterGeom[6 * t + 3], h1 = sc.emitterGeom[6 * t + 4], h2 = sc.emitterGeom[6 * t + 5];
+        n = normalize(f3(g0.w, h0.x, h0.y) * (1.0f - bx - by) + f3(g1.w, h1.x, h1.y) * bx + f3(g2.w, h2.x, h2.y) * by);
+    } else n = normalize(cross(sideA, sideB));
+    float pdf = info.z;
+    float3 d = p - ref;
+    const float distSquared = dot(d, d);
+    dist = sqrtf(distSquared);
+    d = d * (1.0f / dist);
+    const float dp = fabsf(dot(d, n));
+    pdf *= dp != 0.f ? (distSquared / dp) : 0.0f;
+    out.d = d;
+    if (!(dot(d, refN) >= 0.f && dot(d, n) < 0.f && pdf != 0.f)) return false;
+    const float4 r = A_.radiance(ei);
+    out.value = (f3(r.x, r.y, r.z) * (1.0f / pdf)) * (1.0f / emPdf);
+    out.pdf = pdf * emPdf;
+    return true;
+}
+// Scene::pdfEmitterDirect (scene.cpp:949-952) for an emitter hit found by BSDF / guiding sampling
+__device__ __forceinline__ float pdf_emitter_direct(const SceneView &sc, int emitter, float3 refN, float3 d, float3 n, float dist) {
+    if (!(dot(d, refN) >= 0.f && dot(d, n) < 0.f)) return 0.0f;
+    return sc.emitterInfo[emitter].z * (dist * dist) / fabsf(dot(d, n)) * (1.0f * sc.emitterNormalization);
+}
 
 }  // namespace ppg

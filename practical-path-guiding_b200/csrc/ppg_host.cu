@@ -117,7 +117,6 @@ extern "C" int ppg_params_validate(const ppg_params *p) {
     if (p->spp_per_pass < 1) return fail(PPG_ERR_INVALID_ARGUMENT, "'sppPerPass' must be at least 1");
     if (!(p->budget > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "'budget' must be positive");
     if (!(p->bsdf_sampling_fraction >= 0.f && p->bsdf_sampling_fraction <= 1.f)) return fail(PPG_ERR_INVALID_ARGUMENT, "'bsdfSamplingFraction' must lie in [0,1]");
-    if (p->nee != PPG_NEE_NEVER) return fail(PPG_ERR_UNSUPPORTED, "nee != never is a 'next' row of the hot-path scope (SURVEY 8f) and not implemented yet");
     return PPG_OK;
 }
 
@@ -257,7 +256,7 @@ struct ppg_integrator {
 
     // scene
     bool haveScene = false;
-    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups; DevBuf<int4> dMeta;
+    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom; DevBuf<float> dEmitterCdf, dEmitterTriCdf; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
@@ -278,7 +277,7 @@ struct ppg_integrator {
     float extent[3];
 
     // wavefront
-    size_t pathCapacity = 0; int maxBounces = 0, nSlabs = 0; int recordMode = 0;
+    size_t pathCapacity = 0; int maxBounces = 0, nSlabs = 0; int recordMode = 0; int stateVecs = 5, slabSets = 1;
     DevBuf<float4> dStateA, dStateB, dSlabs, dLiFinal; DevBuf<uint32_t> dLive; DevBuf<unsigned long long> dCounters;
     int gridBounce = 0, gridCommit = 0;
 
@@ -300,7 +299,8 @@ struct ppg_integrator {
     }
 
     // run state (GP:2313-2323)
-    bool isBuilt = false, isFinalIter = false; int iter = 0, passesRendered = 0;
+    bool isBuilt = false, isFinalIter = false, doNee = false; int iter = 0, passesRendered = 0; uint32_t nRealEmitters = 0;
+    bool useNee() const { return prm.nee != PPG_NEE_NEVER && nRealEmitters > 0; }
     std::chrono::steady_clock::time_point startTime;
     ppg_stats stats; uint64_t launches = 0; double deviceMs = 0;
 
@@ -444,8 +444,10 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         }
         kBegin[3] = (uint32_t) (groups.size() / 8);
         for (uint32_t t = 0; t < nt; ++t) if (tris[t].k == 3) order.push_back(t);
-        bvh.order = order;
+        if (groups.size() / 8 <= 32) bvh.order = order;       // the candidate mask of the lock-step test has 32 bits
+        else { groups.clear(); kBegin[0] = kBegin[1] = kBegin[2] = kBegin[3] = 0; }
     }
+    const bool bruteForce = !groups.empty();
     if (groups.empty()) groups.assign(8, 0.f);
     std::vector<float> accel(12 * (size_t) nt), geom(24 * (size_t) nt); std::vector<int32_t> meta(4 * (size_t) nt);
     for (uint32_t slot = 0; slot < nt; ++slot) {
@@ -491,8 +493,56 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     v.accel = h->dAccel.p; v.geom = h->dGeom.p; v.meta = h->dMeta.p; v.bvh = h->dBvh.p; v.bsdf = h->dBsdf.p; v.radiance = h->dRadiance.p;
     CK(h->dGroups.alloc(groups.size() / 4));
     CK(cudaMemcpy(h->dGroups.p, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice));
-    v.groups = h->dGroups.p; v.nGroups = (uint32_t) (groups.size() / 8);
+    v.groups = h->dGroups.p; v.nGroups = bruteForce ? (uint32_t) (groups.size() / 8) : 0u;
     for (int k = 0; k < 4; ++k) v.kBegin[k] = kBegin[k];
+    {   // emitter sampling tables for next event estimation (TriMesh::prepareSamplingTable trimesh.cpp:388-403; Scene::configure scene.cpp:357-381)
+        const uint32_t ne = std::max<uint32_t>(s->n_emitters, 1);
+        std::vector<float> ecdf(1, 0.f), tcdf, egeom; std::vector<float> einfo(4 * (size_t) ne, 0.f); std::vector<uint32_t> eflags(ne, 0u);
+        for (uint32_t e = 0; e < s->n_emitters; ++e) {
+            int shape = -1;
+            for (uint32_t si = 0; si < s->n_shapes; ++si) if (s->shapes[si].emitter == (int) e) shape = (int) si;
+            const uint32_t first = (uint32_t) (egeom.size() / 24), cdfOff = (uint32_t) tcdf.size();
+            uint32_t ntri = 0; float invArea = 0.f;
+            if (shape >= 0) {
+                const ppg_shape &sh = s->shapes[shape];
+                if ((uint64_t) sh.first_triangle + sh.n_triangles > nt) return fail(PPG_ERR_INVALID_ARGUMENT, "shape triangle range out of bounds");
+                ntri = sh.n_triangles; eflags[e] = (sh.has_normals && s->normals) ? 1u : 0u;
+                std::vector<float> c(1, 0.f);
+                for (uint32_t t = sh.first_triangle; t < sh.first_triangle + sh.n_triangles; ++t) {
+                    const uint32_t vi[3] = {s->indices[3 * t], s->indices[3 * t + 1], s->indices[3 * t + 2]};
+                    const H3 p0 = P(vi[0]), p1 = P(vi[1]), p2 = P(vi[2]);
+                    const H3 cr = hcross(p1 - p0, p2 - p0);
+                    c.push_back(c.back() + 0.5f * std::sqrt(hdot(cr, cr)));                       // Triangle::surfaceArea
+                    float g[24];
+                    for (int k2 = 0; k2 < 3; ++k2) {
+                        const float *p = &s->positions[3 * vi[k2]];
+                        const float nz[3] = {0, 0, 0}; const float *n = s->normals ? &s->normals[3 * vi[k2]] : nz;
+                        g[4 * k2] = p[0]; g[4 * k2 + 1] = p[1]; g[4 * k2 + 2] = p[2]; g[4 * k2 + 3] = n[0];
+                        g[12 + 4 * k2] = n[1]; g[12 + 4 * k2 + 1] = n[2]; g[12 + 4 * k2 + 2] = 0.f; g[12 + 4 * k2 + 3] = 0.f;
+                    }
+                    egeom.insert(egeom.end(), g, g + 24);
+                }
+                const float sum = c.back();                                                        // DiscreteDistribution::normalize
+                if (sum > 0) { const float nrm = 1.0f / sum; for (size_t i = 1; i < c.size(); ++i) c[i] *= nrm; c.back() = 1.0f; invArea = 1.0f / sum; }
+                tcdf.insert(tcdf.end(), c.begin(), c.end());
+            }
+            memcpy(&einfo[4 * e], &first, 4); memcpy(&einfo[4 * e + 1], &ntri, 4); einfo[4 * e + 2] = invArea; memcpy(&einfo[4 * e + 3], &cdfOff, 4);
+            ecdf.push_back(ecdf.back() + 1.0f);                                                    // getSamplingWeight() == 1
+        }
+        float norm = 0.f;
+        if (ecdf.back() > 0) { norm = 1.0f / ecdf.back(); for (size_t i = 1; i < ecdf.size(); ++i) ecdf[i] *= norm; ecdf.back() = 1.0f; }
+        if (ecdf.size() < 2) ecdf.push_back(1.0f);
+        if (tcdf.empty()) tcdf.assign(2, 0.f);
+        if (egeom.empty()) egeom.assign(24, 0.f);
+        CK(h->dEmitterCdf.alloc(ecdf.size())); CK(h->dEmitterInfo.alloc(ne)); CK(h->dEmitterTriCdf.alloc(tcdf.size())); CK(h->dEmitterGeom.alloc(egeom.size() / 4)); CK(h->dEmitterFlags.alloc(ne));
+        CK(cudaMemcpy(h->dEmitterCdf.p, ecdf.data(), ecdf.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->dEmitterInfo.p, einfo.data(), einfo.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->dEmitterTriCdf.p, tcdf.data(), tcdf.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->dEmitterGeom.p, egeom.data(), egeom.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->dEmitterFlags.p, eflags.data(), eflags.size() * 4, cudaMemcpyHostToDevice));
+        v.emitterCdf = h->dEmitterCdf.p; v.emitterInfo = h->dEmitterInfo.p; v.emitterTriCdf = h->dEmitterTriCdf.p; v.emitterGeom = h->dEmitterGeom.p; v.emitterFlags = h->dEmitterFlags.p;
+        v.emitterNormalization = norm; h->nRealEmitters = s->n_emitters;
+    }
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
     const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 2 * s->n_bsdfs + v.nEmitters + 2 * v.nGroups);
     h->sceneSmemBytes = sceneBytes <= 48 * 1024 ? (uint32_t) sceneBytes : 0u;   // small scenes (CBOX: ~9 KB) live in shared memory
@@ -703,9 +753,11 @@ static int ensure_wavefront(ppg_integrator *h) {
     const size_t perPass = (size_t) h->nLocalPixels * h->prm.spp_per_pass;
     h->maxBounces = h->prm.max_depth > 0 ? h->prm.max_depth : 64;
     h->nSlabs = std::max(1, h->maxBounces - 1);
-    const bool full = h->prm.spatial_filter != PPG_SFILTER_NEAREST || h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE;
+    const bool nee = h->useNee();
+    const bool full = nee || h->prm.spatial_filter != PPG_SFILTER_NEAREST || h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE;
     h->recordMode = full ? 2 : 1;
-    const size_t perPath = 2 * 80 + 16 + (size_t) h->nSlabs * (full ? 96 : 48);
+    const int stateVecs = nee ? 7 : 5, slabSets = nee ? 2 : 1;
+    const size_t perPath = 2 * 16 * (size_t) stateVecs + 16 + (size_t) h->nSlabs * (full ? 96 : 48) * slabSets;
     size_t cap = (size_t) 1 << 23;
     if (const char *e = getenv("PPG_PATH_CAPACITY")) cap = std::max<size_t>(strtoull(e, nullptr, 10), 1024);
     size_t budget = (size_t) 24 << 30;
@@ -714,30 +766,30 @@ static int ensure_wavefront(ppg_integrator *h) {
     cap = std::max(cap, perPass);                          // one pass must fit
     cap = (cap / std::max<size_t>(perPass, 1)) * std::max<size_t>(perPass, 1);   // whole passes only
     cap = std::max(cap, perPass);
-    if (cap > 0xFFFFFFF0ull / 2) return fail(PPG_ERR_INVALID_ARGUMENT, "pass too large for 31-bit path ids");
-    if (cap != h->pathCapacity) {
+    if (cap >= (1ull << 30)) return fail(PPG_ERR_INVALID_ARGUMENT, "pass too large for 30-bit path ids");
+    if (cap != h->pathCapacity || stateVecs != h->stateVecs || slabSets != h->slabSets) {
         h->dStateA.release(); h->dStateB.release(); h->dSlabs.release(); h->dLiFinal.release();
-        CK(h->dStateA.alloc(5 * cap)); CK(h->dStateB.alloc(5 * cap)); CK(h->dLiFinal.alloc(cap));
-        CK(h->dSlabs.alloc((size_t) h->nSlabs * (full ? 6 : 3) * cap));
-        h->pathCapacity = cap;
+        CK(h->dStateA.alloc(stateVecs * cap)); CK(h->dStateB.alloc(stateVecs * cap)); CK(h->dLiFinal.alloc(cap));
+        CK(h->dSlabs.alloc((size_t) h->nSlabs * (full ? 6 : 3) * cap * slabSets));
+        h->pathCapacity = cap; h->stateVecs = stateVecs; h->slabSets = slabSets;
     }
     CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
-    CK(cudaFuncSetAttribute(bounce_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1>, PPG_BLOCK, h->sceneSmemBytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true>, PPG_BLOCK, h->sceneSmemBytes));
     h->gridBounce = h->numSMs * std::max(occ, 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
     h->gridCommit = h->numSMs * std::max(occ, 1);
     return PPG_OK;
 }
 
-static PathState path_state(float4 *base, size_t cap) {
-    PathState s; s.s0 = base; s.s1 = base + cap; s.s2 = base + 2 * cap; s.s3 = base + 3 * cap; s.s4 = base + 4 * cap; return s;
+static PathState path_state(float4 *base, size_t cap, bool nee) {
+    PathState s; s.s0 = base; s.s1 = base + cap; s.s2 = base + 2 * cap; s.s3 = base + 3 * cap; s.s4 = base + 4 * cap;
+    s.s5 = nee ? base + 5 * cap : nullptr; s.s6 = nee ? base + 6 * cap : nullptr; return s;
 }
-static VertexSlab slab_at(ppg_integrator *h, int k) {
+static VertexSlab slab_at(ppg_integrator *h, int k, int set = 0) {
     const size_t cap = h->pathCapacity; const int per = h->recordMode == 2 ? 6 : 3;
-    float4 *b = h->dSlabs.p;
+    float4 *b = h->dSlabs.p + (size_t) set * h->nSlabs * per * cap;
     VertexSlab s;
     // field-major layout: field f of slab k at ((f * nSlabs) + k) * cap, so that slab k+1 of a field is +cap (commit's slabStride)
     s.v0 = b + ((size_t) 0 * h->nSlabs + k) * cap; s.v1 = b + ((size_t) 1 * h->nSlabs + k) * cap; s.v2 = b + ((size_t) 2 * h->nSlabs + k) * cap;
@@ -746,12 +798,18 @@ static VertexSlab slab_at(ppg_integrator *h, int k) {
     return s;
 }
 
-template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid) {
+template <bool FIRST, bool SMEM> static void launch_bounce2(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
     const size_t sm = P.sceneSmemBytes;
-    if (record == 0) bounce_kernel<FIRST, 0><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else if (record == 1) bounce_kernel<FIRST, 1><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else bounce_kernel<FIRST, 2><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    if (nee) {      // next event estimation always runs with full records
+        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+        else bounce_kernel<FIRST, 2, true, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else bounce_kernel<FIRST, 2, false, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
     h->launches++;
+}
+template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
+    if (P.sceneSmemBytes) launch_bounce2<FIRST, true>(h, P, record, grid, nee); else launch_bounce2<FIRST, false>(h, P, record, grid, nee);
 }
 
 // one batch of `nPasses` passes as a single wavefront
@@ -769,7 +827,9 @@ static int render_batch(ppg_integrator *h, int nPasses) {
     P.maxDepth = h->prm.max_depth; P.rrDepth = h->prm.rr_depth; P.strictNormals = h->prm.strict_normals; P.hideEmitters = h->prm.hide_emitters;
     P.isBuilt = h->isBuilt ? 1 : 0; P.lossMode = h->prm.bsdf_sampling_fraction_loss; P.fixedFraction = h->prm.bsdf_sampling_fraction;
     P.sceneSmemBytes = h->sceneSmemBytes;
-    PathState A = path_state(h->dStateA.p, h->pathCapacity), B = path_state(h->dStateB.p, h->pathCapacity);
+    const bool nee = h->useNee();                      // the NEE kernels also carry the MIS state when doNee is off (kickstart after 128 spp)
+    P.neeMode = h->prm.nee; P.doNee = (nee && h->doNee) ? 1 : 0; P.training = record != 0 ? 1 : 0;
+    PathState A = path_state(h->dStateA.p, h->pathCapacity, nee), B = path_state(h->dStateB.p, h->pathCapacity, nee);
     const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK));
     int lastDepth = 0;
     for (int depth = 1; depth <= h->maxBounces; ++depth) {
@@ -777,9 +837,10 @@ static int render_batch(ppg_integrator *h, int nPasses) {
         P.liveIn = h->dLive.p + (depth - 1); P.liveOut = h->dLive.p + depth;
         const int k = std::min(depth - 1, h->nSlabs - 1);
         P.slab = slab_at(h, k);
+        if (nee) { P.neeSlab = slab_at(h, k, 1); P.prevSlab = slab_at(h, std::max(k - 1, 0)); if (depth - 1 >= h->nSlabs) P.prevSlab = slab_at(h, h->nSlabs - 1); }
         const int rec = (depth - 1 < h->nSlabs) ? record : 0;
         h->tic(PPG_K_BOUNCE);
-        if (depth == 1) launch_bounce<true>(h, P, rec, grid); else launch_bounce<false>(h, P, rec, grid);
+        if (depth == 1) launch_bounce<true>(h, P, rec, grid, nee); else launch_bounce<false>(h, P, rec, grid, nee);
         h->toc();
         lastDepth = depth;
     }
@@ -792,11 +853,14 @@ static int render_batch(ppg_integrator *h, int nPasses) {
         C.tree = tree_view(h); C.slab0 = slab_at(h, 0); C.slabStride = h->pathCapacity; C.liveCounts = h->dLive.p; C.liFinal = h->dLiFinal.p;
         C.spatialFilter = h->prm.spatial_filter; C.directionalFilter = h->prm.directional_filter;
         C.lossMode = h->isBuilt ? h->prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE;       // GP:2152
-        C.statisticalWeight = 1.0f; C.seed = h->prm.seed; C.snodes = h->dSnodes.p;
+        C.statisticalWeight = (h->prm.nee == PPG_NEE_KICKSTART && h->doNee && nee) ? 0.5f : 1.0f;   // GP:2152
+        C.seed = h->prm.seed; C.snodes = h->dSnodes.p; C.nSlabs = (uint32_t) h->nSlabs;
+        const bool neeSlabs = nee && h->doNee && h->prm.nee != PPG_NEE_ALWAYS;
+        C.nee0 = neeSlabs ? slab_at(h, 0, 1) : C.slab0;
         const bool useAdam = C.lossMode != PPG_LOSS_NONE;
         if (useAdam) {
             // one record per (vertex, leaf) pair; the spatial box filter touches several leaves per vertex (records beyond the capacity are dropped)
-            const size_t want = (size_t) nPaths * h->nSlabs * (h->prm.spatial_filter == PPG_SFILTER_BOX ? 2 : 1);
+            const size_t want = (size_t) nPaths * h->nSlabs * (h->prm.spatial_filter == PPG_SFILTER_BOX ? 2 : 1) * (neeSlabs ? 2 : 1);
             if (want > h->adamCap) {
                 h->dAdamRecA.release(); h->dAdamRecB.release(); h->dAdamSortA.release(); h->dAdamSortB.release();
                 CK(h->dAdamRecA.alloc(want)); CK(h->dAdamRecB.alloc(want)); CK(h->dAdamSortA.alloc(want)); CK(h->dAdamSortB.alloc(want));
@@ -805,7 +869,7 @@ static int render_batch(ppg_integrator *h, int nPasses) {
             CK(cudaMemsetAsync(h->dScalars.p + 3, 0, 4, h->stream));
         }
         C.adamRecA = h->dAdamRecA.p; C.adamRecB = h->dAdamRecB.p; C.adamTotal = h->dScalars.p + 3; C.adamCap = (uint32_t) std::min<size_t>(h->adamCap, 0xFFFFFFFFu);
-        dim3 g(std::min<int>(h->gridCommit, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK)), h->nSlabs);
+        dim3 g(std::min<int>(h->gridCommit, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK)), h->nSlabs * (neeSlabs ? 2 : 1));
         h->tic(PPG_K_COMMIT);
         if (record == 1) commit_kernel<1><<<g, PPG_BLOCK, 0, h->stream>>>(C); else commit_kernel<2><<<g, PPG_BLOCK, 0, h->stream>>>(C);
         h->toc(); h->launches++;
@@ -924,6 +988,7 @@ static int render_spp(ppg_integrator *h) {
     float currentVarAtEnd = std::numeric_limits<float>::infinity();
     while (h->passesRendered < nPasses) {
         const int sppRendered = h->passesRendered * h->prm.spp_per_pass;
+        h->doNee = h->prm.nee == PPG_NEE_NEVER ? false : (h->prm.nee == PPG_NEE_KICKSTART ? sppRendered < 128 : true);   // doNeeWithSpp, GP:1331-1340, 1362
         int remainingPasses = nPasses - h->passesRendered;
         int passesThisIteration = std::min(remainingPasses, 1 << std::min(h->iter, 30));
         if (remainingPasses - passesThisIteration < 2 * passesThisIteration) passesThisIteration = remainingPasses;
@@ -959,6 +1024,7 @@ static int render_time(ppg_integrator *h) {
     float currentVarAtEnd = std::numeric_limits<float>::infinity(), elapsedSeconds = 0;
     while (elapsedSeconds < nSeconds) {
         const int sppRendered = h->passesRendered * h->prm.spp_per_pass;
+        h->doNee = h->prm.nee == PPG_NEE_NEVER ? false : (h->prm.nee == PPG_NEE_KICKSTART ? sppRendered < 128 : true);   // GP:1452
         float remainingTime = nSeconds - elapsedSeconds;
         const int passesThisIteration = 1 << std::min(h->iter, 30);
         ppg_iteration_stats &st = iter_stats(h);

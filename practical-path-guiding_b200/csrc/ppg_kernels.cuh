@@ -29,6 +29,8 @@ struct PathState {      // 5 x float4 per path
     float4 *s2;         // throughput.z, eta, Li.xy
     float4 *s3;         // Li.z, bits(pathId), bits(rng.lo), bits(rng.hi)
     float4 *s4;         // bits(sampleIndex.lo), bits(sampleIndex.hi), bits(nVertices | flags<<8), rrRecip
+    float4 *s5;         // NEE only: woPdf of the last sampled direction, refN.xyz of the vertex it left (GP:2084-2087)
+    float4 *s6;         // NEE only: bits(slab slot of the last vertex | isDelta<<31 | hasVertex<<30), 0, 0, 0
 };
 #define PPG_FLAG_DYING 1u            // lost Russian roulette: trace one more ray for the emitter lookup, then stop (GP:2078-2091 precede GP:2123-2142)
 
@@ -60,30 +62,11 @@ struct RenderParams {
     int lossMode;                  // bsdfSamplingFractionLoss
     float fixedFraction;           // bsdfSamplingFraction
     uint32_t sceneSmemBytes;       // >0: stage the scene into shared memory
+    int neeMode, doNee;            // m_nee, m_doNee (GP:1331-1340)
+    int training;                  // vertex records are being written in this iteration (the last bounce kernel itself runs with RECORD == 0)
+    VertexSlab neeSlab;            // half-weight vertices of the sampled light directions (GP:1999-2016), slab of the current depth
+    VertexSlab prevSlab;           // slab of depth-1 (nee == always: the vertex's radiance excludes the emitter hit that follows it, GP:2101)
 };
-
-// ------------------------------------------------------------------ scene staging
-// Copies accel | geom | meta | bvh | bsdf | radiance into dynamic shared memory (16 B granules) and
-// returns a view whose (generic) pointers address the shared copy.
-__device__ __forceinline__ SceneView stage_scene(const SceneView &g, float4 *smem) {
-    SceneView s = g;
-    uint32_t off = 0;
-    auto copy = [&](const float4 *src, uint32_t n) {
-        float4 *dst = smem + off;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-        off += n;
-        return dst;
-    };
-    s.accel = copy(g.accel, 3 * g.nTris);
-    s.geom = copy(g.geom, 6 * g.nTris);
-    s.meta = reinterpret_cast<const int4 *>(copy(reinterpret_cast<const float4 *>(g.meta), g.nTris));
-    s.bvh = copy(g.bvh, 2 * g.nBvhNodes);
-    s.bsdf = copy(g.bsdf, 2 * g.nBsdfs);
-    s.radiance = copy(g.radiance, g.nEmitters);
-    s.groups = copy(g.groups, 2 * g.nGroups);
-    __syncthreads();
-    return s;
-}
 
 // warp-wide compaction: returns the output slot of this lane (valid when `alive`); one atomic per warp and
 // no block barrier, so warps of a block never wait for each other inside the path loop.
@@ -100,10 +83,10 @@ __device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) 
 // FIRST: generate the camera ray (renderBlock, GP:1613-1632) instead of loading a path state.
 // RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
 //         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
-template <bool FIRST, int RECORD>
+template <bool FIRST, int RECORD, bool NEE, bool SMEM>
 __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
-    extern __shared__ float4 smemScene[];
-    const SceneView sc = P.sceneSmemBytes ? stage_scene(P.scene, smemScene) : P.scene;
+    const SceneAccess<SMEM> sc(P.scene);
+    sc.stage();
     const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
     unsigned long long raysLocal = 0, recLocal = 0, levelsLocal = 0;
 
@@ -111,6 +94,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
         const uint32_t i = base + threadIdx.x;
         bool alive = i < nIn;
         float3 o, d, thr, Li; float eta = 1.f, rrRecip = 1.f, mint, maxt;
+        float prevWoPdf = 0.f; float3 prevRefN = f3(0, 0, 0); uint32_t prevSlot = 0;      // NEE only
         uint32_t pathId = 0, nVertices = 0, flags = 0; uint64_t sampleIndex = 0;
         Pcg32 rng; rng.state = 0; rng.inc = 1;
         if (alive) {
@@ -141,12 +125,13 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                 rng.inc = (sampleIndex << 1) | 1u;
                 const uint32_t nf = __float_as_uint(f.z); nVertices = nf & 0xffu; flags = nf >> 8;
                 rrRecip = f.w;
+                if (NEE) { const float4 g5 = P.in.s5[i], g6 = P.in.s6[i]; prevWoPdf = g5.x; prevRefN = f3(g5.y, g5.z, g5.w); prevSlot = __float_as_uint(g6.x); }
                 // adaptive ray epsilon of rays leaving a surface (skdtree.cpp:125-128)
                 mint = PPG_EPSILON * fmaxf(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), PPG_EPSILON);
                 maxt = __int_as_float(0x7f800000);
             }
         }
-        bool wroteVertex = false;
+        bool wroteVertex = false, wroteNee = false;
         if (alive) {
             ++raysLocal;
             Hit hit;
@@ -157,11 +142,23 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                 fill_its(sc, hit, d, its);
                 // emitted radiance: primary hit via EEmittedRadiance (GP:1917-1919), later hits via the `value`
                 // returned by rayIntersectAndLookForEmitter (GP:2078-2091; miWeight(woPdf, 0) == 1)
+                float3 Lhit = f3(0, 0, 0);
                 if (its.emitter >= 0 && (!FIRST || !P.hideEmitters)) {
                     if (dot(its.shN, -d) > 0.f) {                                    // area.cpp:104-109
-                        const float4 r = sc.radiance[its.emitter];
-                        Li = Li + thr * f3(r.x, r.y, r.z);
+                        const float4 r = sc.radiance(its.emitter);
+                        Lhit = thr * f3(r.x, r.y, r.z);
+                        if (NEE && !FIRST && P.doNee && !(prevSlot >> 31)) {            // MIS against light sampling, GP:2084-2088
+                            const float emitterPdf = pdf_emitter_direct(sc.g, its.emitter, prevRefN, d, its.shN, hit.t);
+                            Lhit = Lhit * mi_weight(prevWoPdf, emitterPdf);
+                        }
+                        Li = Li + Lhit;
                     }
+                }
+                if (NEE && !FIRST && P.training && P.neeMode == 2 && ((prevSlot >> 30) & 1u)) {
+                    // nee == always: the vertex created at the previous bounce starts with radiance 0 instead of L (GP:2101):
+                    // move its radiance prefix past this emitter hit
+                    const uint32_t ps = prevSlot & 0x3fffffffu;
+                    float4 pv = P.prevSlab.v2[ps]; pv.x = Li.x; pv.y = Li.y; pv.z = Li.z; P.prevSlab.v2[ps] = pv;
                 }
                 thr = thr * rrRecip;                                                // throughput /= successProb happens after L was recorded (GP:2141)
                 if (flags & PPG_FLAG_DYING) cont = false;
@@ -208,6 +205,42 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                         bsdfWeight = (woPdf == 0.f) ? f3(0, 0, 0) : result * (1.0f / woPdf);
                     }
                 }
+                const float3 refN = (bsdf.flags & PPG_BSDF_TWOSIDED) ? f3(0, 0, 0) : its.shN;   // DirectSamplingRecord(its), records.inl:160-164
+                if (NEE && P.doNee) {
+                    // ---- luminaire sampling, GP:1964-2021
+                    const float ex = rng.next1D(), ey = rng.next1D();
+                    DirectSample ds; float dist;
+                    if (sample_emitter_direct(sc, its.p, refN, ex, ey, ds, dist)) {
+                        // Scene::evalTransmittance: shadow ray, epsilon scaled without the clamp (skdtree.cpp:154-158)
+                        const float smint = PPG_EPSILON * fmaxf(fmaxf(fabsf(its.p.x), fabsf(its.p.y)), fabsf(its.p.z));
+                        Hit sh; ++raysLocal;
+                        if (!bvh_intersect(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh)) {
+                            const float3 dl = its.toLocal(ds.d);
+                            if (!P.strictNormals || dot(its.geoN, ds.d) * dl.z > 0.f) {
+                                const float3 bsdfVal = bsdf_eval(bsdf, its.wi, dl);
+                                float nWoPdf = 0.f, nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl), nDTreePdf = 0.f;
+                                if (!P.isBuilt) nWoPdf = nBsdfPdf;
+                                else if (isfinite(nBsdfPdf)) {
+                                    nDTreePdf = dtree_pdf(P.tree.samp + __float_as_uint(la.x), __float_as_uint(la.w) & 1u, dir_to_canonical(ds.d));
+                                    nWoPdf = frac * nBsdfPdf + (1.f - frac) * nDTreePdf;
+                                }
+                                const float3 L = thr * (ds.value * bsdfVal) * mi_weight(ds.pdf, nWoPdf);
+                                if (RECORD && P.neeMode != 2) {                          // GP:1999-2016: half-weight vertex with a fixed radiance
+                                    const float3 tv = thr * bsdfVal * (1.0f / ds.pdf);
+                                    P.neeSlab.v0[i] = make_float4(ds.d.x, ds.d.y, ds.d.z, ds.pdf);
+                                    P.neeSlab.v1[i] = make_float4(tv.x, tv.y, tv.z, __uint_as_float(leaf));
+                                    P.neeSlab.v2[i] = make_float4(L.x, L.y, L.z, __uint_as_float(pathId | 0x40000000u));   // bit 30: absolute radiance
+                                    P.neeSlab.v3[i] = make_float4(bsdfVal.x, bsdfVal.y, bsdfVal.z, nBsdfPdf);
+                                    P.neeSlab.v4[i] = make_float4(its.p.x, its.p.y, its.p.z, nDTreePdf);
+                                    P.neeSlab.v5[i] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
+                                                                  __uint_as_float((uint32_t) levels | ((32u + (uint32_t) P.depth) << 8)), 0.f);
+                                    wroteNee = true;
+                                }
+                                Li = Li + L;                                             // recordRadiance(L)
+                            }
+                        }
+                    }
+                }
                 if (is_zero(bsdfWeight)) cont = false;                               // GP:2024-2025
                 float3 woW = f3(0, 0, 0);
                 if (cont) {
@@ -231,6 +264,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                         }
                         wroteVertex = true; ++nVertices; ++recLocal; levelsLocal += levels;
                     }
+                    if (NEE) { prevWoPdf = woPdf; prevRefN = refN; prevSlot = i | (isDelta ? 0x80000000u : 0u) | (wroteVertex ? 0x40000000u : 0u); }
                     // ---- Russian roulette (GP:2123-2142); the decision takes effect after the next emitter lookup
                     rrRecip = 1.f; flags = 0;
                     if (P.depth >= P.rrDepth) {
@@ -250,6 +284,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
             }
         }
         if (RECORD && i < nIn && !wroteVertex) P.slab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
+        if (NEE && RECORD && P.neeMode != 2 && i < nIn && !wroteNee) P.neeSlab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
         const uint32_t slot = warp_compact(alive, P.liveOut);
         if (alive) {
             P.out.s0[slot] = make_float4(o.x, o.y, o.z, d.x);
@@ -258,6 +293,10 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
             P.out.s3[slot] = make_float4(Li.z, __uint_as_float(pathId), __uint_as_float((uint32_t) rng.state), __uint_as_float((uint32_t) (rng.state >> 32)));
             P.out.s4[slot] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
                                          __uint_as_float(nVertices | (flags << 8)), rrRecip);
+            if (NEE) {
+                P.out.s5[slot] = make_float4(prevWoPdf, prevRefN.x, prevRefN.y, prevRefN.z);
+                P.out.s6[slot] = make_float4(__uint_as_float(prevSlot), 0.f, 0.f, 0.f);
+            }
         }
     }
     // per-warp reduction of the statistics counters
@@ -289,7 +328,9 @@ struct CommitParams {
     const uint32_t *liveCounts;    // liveCounts[k]: entries of slab k (the input live count of that bounce)
     const float4 *liFinal;
     int spatialFilter, directionalFilter, lossMode;   // lossMode already gated by isBuilt (GP:2152)
-    float statisticalWeight;       // 1.0 (0.5 only with nee=kickstart)
+    float statisticalWeight;       // 1.0; 0.5 while nee=kickstart samples lights (GP:2152)
+    VertexSlab nee0;               // NEE slabs (blockIdx.y >= nSlabs): fixed radiance, weight 0.5 (GP:2014)
+    uint32_t nSlabs;
     uint64_t seed;
     const uint2 *snodes;
     // sampling-fraction learning: one record per (vertex, leaf) pair, consumed by adam_seq_kernel
@@ -330,26 +371,31 @@ __device__ __forceinline__ void record_into_leaf(const CommitParams &C, uint32_t
 
 template <int RECORD>
 __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P) {
-    const uint32_t k = blockIdx.y;
+    const bool neeSlab = blockIdx.y >= P.nSlabs;
+    const uint32_t k = neeSlab ? blockIdx.y - P.nSlabs : blockIdx.y;
     const uint32_t n = P.liveCounts[k];
     const size_t so = (size_t) k * P.slabStride;
+    VertexSlab S;      // select field by field (values), never by address: kernel parameters live in the param space
+    S.v0 = neeSlab ? P.nee0.v0 : P.slab0.v0; S.v1 = neeSlab ? P.nee0.v1 : P.slab0.v1; S.v2 = neeSlab ? P.nee0.v2 : P.slab0.v2;
+    S.v3 = neeSlab ? P.nee0.v3 : P.slab0.v3; S.v4 = neeSlab ? P.nee0.v4 : P.slab0.v4; S.v5 = neeSlab ? P.nee0.v5 : P.slab0.v5;
+    const float vertexWeight = neeSlab ? 0.5f : P.statisticalWeight;
     for (uint32_t base = blockIdx.x * PPG_BLOCK; base < n; base += gridDim.x * PPG_BLOCK) {
         const uint32_t i = base + threadIdx.x;
         bool ok = i < n;
         float4 v0, v1, v2, v4 = make_float4(0, 0, 0, 0), v5 = make_float4(0, 0, 0, 0);
         uint32_t pid = PPG_INVALID;
-        if (ok) { v2 = P.slab0.v2[so + i]; pid = __float_as_uint(v2.w); ok = pid != PPG_INVALID; }
+        if (ok) { v2 = S.v2[so + i]; pid = __float_as_uint(v2.w); ok = pid != PPG_INVALID; }
         float3 d = f3(0, 0, 1), radiance = f3(0, 0, 0), thr = f3(1, 1, 1), bsdfVal = f3(0, 0, 0); float woPdf = 0.f, bsdfPdf = 0.f, dTreePdf = 0.f;
         uint32_t leaf = 0; bool isDelta = false;
         if (ok) {
-            v0 = P.slab0.v0[so + i]; v1 = P.slab0.v1[so + i];
-            isDelta = pid >> 31; pid &= 0x7fffffffu;
-            const float4 lf = __ldg(&P.liFinal[pid]);
+            v0 = S.v0[so + i]; v1 = S.v1[so + i];
+            isDelta = pid >> 31; const bool absolute = (pid >> 30) & 1u; pid &= 0x3fffffffu;
+            const float4 lf = absolute ? make_float4(v2.x * 2.f, v2.y * 2.f, v2.z * 2.f, 0.f) : __ldg(&P.liFinal[pid]);
             d = f3(v0.x, v0.y, v0.z); woPdf = v0.w; thr = f3(v1.x, v1.y, v1.z); leaf = __float_as_uint(v1.w);
             radiance = f3(lf.x - v2.x, lf.y - v2.y, lf.z - v2.z);                  // everything recorded after the vertex was created
             if (RECORD == 2) {
-                const float4 v3 = P.slab0.v3[so + i]; bsdfVal = f3(v3.x, v3.y, v3.z); bsdfPdf = v3.w;
-                v4 = P.slab0.v4[so + i]; v5 = P.slab0.v5[so + i]; dTreePdf = v4.w;
+                const float4 v3 = S.v3[so + i]; bsdfVal = f3(v3.x, v3.y, v3.z); bsdfPdf = v3.w;
+                v4 = S.v4[so + i]; v5 = S.v5[so + i]; dTreePdf = v4.w;
             }
             // Vertex::commit, GP:1730-1768
             if (!(woPdf > 0.f) || !is_valid(radiance) || !is_valid(bsdfVal)) ok = false;
@@ -368,7 +414,7 @@ __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P)
             // nearest: the vertex's own leaf.  The statistical-weight counter of a leaf is ONE address that every vertex
             // of that leaf hits (iteration 0: one address for the whole wavefront) -> one atomic per distinct leaf per warp.
             // All 32 lanes reach this call (the loop trip count is block-uniform).
-            const float w = P.statisticalWeight;
+            const float w = vertexWeight;
             warp_aggregated_add(P.tree.bweight, leaf, w, ok && !isDelta && isfinite(w) && w > 0.f);
             if (ok) record_into_leaf(P, leaf, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, w, isDelta, P.directionalFilter, P.lossMode, true);
         } else if (ok) {
@@ -385,11 +431,11 @@ __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P)
                 const float3 mx = P.tree.aabbMin + P.tree.extent;
                 q.x = fminf(fmaxf(q.x, P.tree.aabbMin.x), mx.x); q.y = fminf(fmaxf(q.y, P.tree.aabbMin.y), mx.y); q.z = fminf(fmaxf(q.z, P.tree.aabbMin.z), mx.z);
                 int lv; const uint32_t splat = stree_lookup(P.snodes, P.tree.stable, P.tree.aabbMin, P.tree.extent, q, lv);
-                record_into_leaf(P, splat, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, P.statisticalWeight, isDelta, P.directionalFilter, P.lossMode, false);
+                record_into_leaf(P, splat, d, avgLocal, avgProduct, woPdf, bsdfPdf, dTreePdf, vertexWeight, isDelta, P.directionalFilter, P.lossMode, false);
             } else {
                 // box filter, STree::record GP:935-943 + STreeNode::record GP:823-839: every leaf overlapping the voxel-sized box
                 const float volume = voxel.x * voxel.y * voxel.z;
-                const float w0 = P.statisticalWeight / volume;
+                const float w0 = vertexWeight / volume;
                 const float3 min1 = o - voxel * 0.5f, max1 = o + voxel * 0.5f;
                 struct E { uint32_t n; float3 mn, sz; int axis; };
                 E st[64]; int sp = 0;

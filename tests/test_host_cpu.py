@@ -42,7 +42,7 @@ def test_parameter_defaults_are_the_references():
 
 
 @pytest.mark.parametrize("name,value", [("sampleCombination", "sometimes"), ("spatialFilter", "gauss"), ("directionalFilter", "stochastic"),
-                                        ("bsdfSamplingFractionLoss", "l2"), ("budgetType", "minutes"), ("nee", "maybe"), ("rrDepth", "0"),
+                                        ("bsdfSamplingFractionLoss", "l2"), ("budgetType", "minutes"), ("nee", "sometimes"), ("rrDepth", "0"),
                                         ("maxDepth", "0"), ("maxDepth", "-2"), ("strictNormals", "yes"), ("notAParameter", "1")])
 def test_invalid_parameters_are_rejected_like_the_reference(name, value):
     """Unknown enum strings Assert(false) in the reference (GP:1023,1034,1045,1054,1065,1080); rrDepth <= 0 and
@@ -53,7 +53,7 @@ def test_invalid_parameters_are_rejected_like_the_reference(name, value):
 
 
 def test_all_reference_parameter_strings_are_accepted():
-    for name, vals in {"sampleCombination": ["discard", "automatic", "inversevar"], "spatialFilter": ["nearest", "stochastic", "box"],
+    for name, vals in {"nee": ["never", "kickstart", "always"], "sampleCombination": ["discard", "automatic", "inversevar"], "spatialFilter": ["nearest", "stochastic", "box"],
                        "directionalFilter": ["nearest", "box"], "bsdfSamplingFractionLoss": ["none", "kl", "var"], "budgetType": ["spp", "seconds"]}.items():
         for i, v in enumerate(vals):
             I.make_params({name: v})

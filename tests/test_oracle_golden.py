@@ -56,3 +56,18 @@ def test_improved_config_iteration0():
     assert abs(st["weight_avg"] - g["stat_weight"][1]) <= 0.005 * g["stat_weight"][1]
     assert abs(st["mean_radiance_avg"] - g["mean_radiance"][1]) <= 0.05 * g["mean_radiance"][1]
     assert st["nodes_max"] == 85
+
+
+def test_nee_modes_are_unbiased_against_each_other():
+    """nee = never / kickstart / always estimate the same image (GP:1964-2021 adds light sampling with MIS, it must not change
+    the expectation): image means agree within 1 % at 128 spp on 64^2, and light sampling lowers the variance."""
+    sc = load_cbox(64)
+    out = {}
+    for nee in ("never", "kickstart", "always"):
+        o = O.Oracle(O.params_from_xml(dict(sc.integrator, budget="252", nee=nee)), sc)
+        img, st = o.render()
+        out[nee] = (img.mean(), st["iterations"][-1]["variance"], st["iterations"][0]["variance"])
+    assert abs(out["kickstart"][0] - out["never"][0]) <= 0.015 * out["never"][0]
+    assert abs(out["always"][0] - out["never"][0]) <= 0.015 * out["never"][0]
+    assert out["always"][1] < 0.6 * out["never"][1]          # final iteration with light sampling
+    assert out["kickstart"][2] < 0.5 * out["never"][2]       # first iteration with light sampling

@@ -11,7 +11,7 @@ size = 128
 sc = load_cbox(size)
 variants = {"default": {}, "dbox": {"directionalFilter": "box"}, "stochastic": {"spatialFilter": "stochastic"}, "sbox": {"spatialFilter": "box"},
             "kl": {"bsdfSamplingFractionLoss": "kl"}, "var": {"bsdfSamplingFractionLoss": "var"}, "inversevar": {"sampleCombination": "inversevar"}, "spp1": {"sppPerPass": "1"},
-            "thr4000": {"sTreeThreshold": "4000"}}
+            "thr4000": {"sTreeThreshold": "4000"}, "kickstart": {"nee": "kickstart"}, "always": {"nee": "always"}}
 sel = sys.argv[1:] or list(variants)
 for name in sel:
     props = dict(sc.integrator, budget="60", **variants[name])
