@@ -106,7 +106,9 @@ int ppg_params_validate(const ppg_params *p);
 
 typedef enum ppg_bsdf_type {
     PPG_BSDF_DIFFUSE = 0,        /* src/bsdfs/diffuse.cpp:110-150 */
-    PPG_BSDF_NULL_BLACK = 1      /* shape with an emitter and no BSDF: black diffuse (src/librender/shape.cpp:48-72) */
+    PPG_BSDF_NULL_BLACK = 1,     /* shape with an emitter and no BSDF: black diffuse (src/librender/shape.cpp:48-72) */
+    PPG_BSDF_DIELECTRIC = 2,     /* src/bsdfs/dielectric.cpp:228-392: delta reflection + refraction, fresnelDielectricExt (libcore/util.cpp:651-683) */
+    PPG_BSDF_CONDUCTOR = 3       /* src/bsdfs/conductor.cpp:223-286: delta reflection, fresnelConductorExact per channel (libcore/util.cpp:740-765) */
 } ppg_bsdf_type;
 
 #define PPG_BSDF_FLAG_TWOSIDED 1u /* src/bsdfs/twosided.cpp:108-184 wrapping the model */
@@ -114,8 +116,11 @@ typedef enum ppg_bsdf_type {
 typedef struct ppg_bsdf {
     int32_t  type;            /* ppg_bsdf_type */
     uint32_t flags;
-    float    reflectance[3];  /* linear Rec.709 RGB (scenehandler.cpp:597-613, spectrum.cpp:172-227) */
-    float    reserved[11];    /* future models (alpha, eta, k, ...) */
+    float    reflectance[3];  /* diffuse: reflectance; dielectric / conductor: specularReflectance. Linear Rec.709 RGB (scenehandler.cpp:597-613) */
+    float    specular_transmittance[3];  /* dielectric */
+    float    eta[3];          /* dielectric: eta[0] = intIOR / extIOR; conductor: eta / extEta per channel */
+    float    k[3];            /* conductor: k / extEta per channel */
+    float    reserved[2];
 } ppg_bsdf;                   /* 64 bytes */
 
 typedef struct ppg_shape {

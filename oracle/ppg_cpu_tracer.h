@@ -371,13 +371,42 @@ static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
     return f3(px, py, z);
 }
 struct BsdfSample { F3 wo; float eta; bool delta; };
-// all three return per src/bsdfs/diffuse.cpp:110-150; twosided per src/bsdfs/twosided.cpp:108-184
+static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK; }       // type & ESmooth (bsdf.h:224-285)
+static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC; }
+
+// fresnelDielectricExt, src/libcore/util.cpp:651-683
+static inline float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
+    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    const float scale = (cosThetaI_ > 0) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    const float cosThetaI = std::fabs(cosThetaI_), cosThetaT = std::sqrt(cosThetaTSqr);
+    const float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    const float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+// fresnelConductorExact (scalar form applied per channel), src/libcore/util.cpp:715-738
+static inline float fresnel_conductor_exact(float cosThetaI, float eta, float k) {
+    const float cosThetaI2 = cosThetaI * cosThetaI, sinThetaI2 = 1 - cosThetaI2, sinThetaI4 = sinThetaI2 * sinThetaI2;
+    const float temp1 = eta * eta - k * k - sinThetaI2;
+    const float a2pb2 = std::sqrt(std::max(0.0f, temp1 * temp1 + k * k * eta * eta * 4));
+    const float a = std::sqrt(std::max(0.0f, (a2pb2 + temp1) * 0.5f));
+    const float term1 = a2pb2 + cosThetaI2, term2 = a * (2 * cosThetaI);
+    const float Rs2 = (term1 - term2) / (term1 + term2);
+    const float term3 = a2pb2 * cosThetaI2 + sinThetaI4, term4 = term2 * sinThetaI2;
+    const float Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
+    return 0.5f * (Rp2 + Rs2);
+}
+// eval / pdf with the solid-angle measure (delta models return 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
+// twosided per src/bsdfs/twosided.cpp:108-184
 static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo) {
+    if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
     return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * (kInvPi * wo.z);
 }
 static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo) {
+    if (!bsdf_has_smooth(b)) return 0.0f;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (wi.z <= 0 || wo.z <= 0) return 0.0f;
     return kInvPi * wo.z;   // warp::squareToCosineHemispherePdf
@@ -386,6 +415,23 @@ static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfS
     bool flip = false;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; flip = true; } }
     s.eta = 1.0f; s.delta = false; pdf = 0;
+    if (b.type == PPG_BSDF_DIELECTRIC) {
+        const float eta = b.eta[0], invEta = 1 / eta;
+        float cosThetaT; const float F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
+        s.delta = true;
+        if (sx <= F) { s.wo = f3(-wi.x, -wi.y, wi.z); s.eta = 1.0f; pdf = F; return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]); }
+        const float scale = -(cosThetaT < 0 ? invEta : eta);
+        s.wo = f3(scale * wi.x, scale * wi.y, cosThetaT); s.eta = cosThetaT < 0 ? eta : invEta; pdf = 1 - F;
+        const float factor = cosThetaT < 0 ? invEta : eta;      // ERadiance: solid angle compression
+        return f3(b.specular_transmittance[0], b.specular_transmittance[1], b.specular_transmittance[2]) * (factor * factor);
+    }
+    if (b.type == PPG_BSDF_CONDUCTOR) {
+        if (wi.z <= 0) return f3(0, 0, 0);
+        s.delta = true; s.wo = f3(-wi.x, -wi.y, wi.z); pdf = 1;
+        if (flip) s.wo.z = -s.wo.z;
+        return f3(b.reflectance[0] * fresnel_conductor_exact(wi.z, b.eta[0], b.k[0]), b.reflectance[1] * fresnel_conductor_exact(wi.z, b.eta[1], b.k[1]),
+                  b.reflectance[2] * fresnel_conductor_exact(wi.z, b.eta[2], b.k[2]));
+    }
     if (wi.z <= 0) return f3(0, 0, 0);
     s.wo = square_to_cosine_hemisphere(sx, sy);
     pdf = kInvPi * s.wo.z;
@@ -451,7 +497,8 @@ public:
             const float wiDotGeoN = -dot(its.geoN, d), wiDotShN = its.wi.z;
             if (wiDotGeoN * wiDotShN < 0 && prm.strict_normals) break;                         // GP:1929-1932
             const ppg_bsdf &bsdf = sc.bsdfs[shp.bsdf];
-            float voxel[3]; typename Backend::Leaf *leaf = tree.lookup(&its.p.x, voxel);       // GP:1942-1944 (diffuse is smooth)
+            float voxel[3] = {0, 0, 0}; typename Backend::Leaf *leaf = nullptr;
+            if (bsdf_has_smooth(bsdf)) leaf = tree.lookup(&its.p.x, voxel);                    // GP:1942-1944: only smooth BSDFs are guided
             float frac = prm.bsdf_sampling_fraction;
             if (leaf && prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) frac = tree.bsdfSamplingFraction(leaf);   // GP:1946-1949
             // ---- sampleMat, GP:1650-1691
@@ -487,8 +534,8 @@ public:
                 }
             }
             // ---- luminaire sampling, GP:1964-2021 (DirectSamplingRecord dRec(its): refN = shading normal unless the BSDF is two-sided / transmissive, records.inl:160-164)
-            const F3 refN = (bsdf.flags & PPG_BSDF_FLAG_TWOSIDED) ? f3(0, 0, 0) : its.shN;
-            if (doNee) {
+            const F3 refN = bsdf_has_transmission_or_backside(bsdf) ? f3(0, 0, 0) : its.shN;
+            if (doNee && bsdf_has_smooth(bsdf)) {                                               // GP:1967-1969
                 const float ex = rng.next1D(), ey = rng.next1D();
                 DirectSample ds;
                 if (sample_emitter_direct(sc, its.p, refN, ex, ey, ds) && !is_zero(ds.value)) {

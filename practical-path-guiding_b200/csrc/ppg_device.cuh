@@ -78,7 +78,7 @@ struct SceneView {
     const float4 *geom;
     const int4 *meta;
     const float4 *bvh;
-    const float4 *bsdf;       // 2 per material: {refl.rgb, bits(type | flags<<8)}, {reserved}
+    const float4 *bsdf;       // 4 per material, see load_bsdf
     const float4 *radiance;   // per emitter: rgb
     uint32_t nTris, nBvhNodes, nBsdfs, nEmitters;
     // brute-force layout (nTris <= PPG_BRUTE_FORCE_TRIS): coplanar triangle groups ordered by projection axis k.
@@ -110,7 +110,7 @@ template <bool SMEM> struct SceneAccess {
     uint32_t oGeom, oMeta, oBvh, oBsdf, oRadiance, oGroups;      // float4 offsets of the staged sections (accel at 0)
     __device__ __forceinline__ SceneAccess(const SceneView &v) : g(v) {
         oGeom = 3 * v.nTris; oMeta = oGeom + 6 * v.nTris; oBvh = oMeta + v.nTris; oBsdf = oBvh + 2 * v.nBvhNodes;
-        oRadiance = oBsdf + 2 * v.nBsdfs; oGroups = oRadiance + v.nEmitters;
+        oRadiance = oBsdf + 4 * v.nBsdfs; oGroups = oRadiance + v.nEmitters;
     }
     __device__ __forceinline__ float4 accel(uint32_t i) const { return SMEM ? ppg_scene_smem[i] : __ldg(&g.accel[i]); }
     __device__ __forceinline__ float4 geom(uint32_t i) const { return SMEM ? ppg_scene_smem[oGeom + i] : __ldg(&g.geom[i]); }
@@ -127,7 +127,7 @@ template <bool SMEM> struct SceneAccess {
         if (!SMEM) return;
         auto copy = [&](uint32_t off, const float4 *src, uint32_t n) { for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) ppg_scene_smem[off + i] = src[i]; };
         copy(0, g.accel, 3 * g.nTris); copy(oGeom, g.geom, 6 * g.nTris); copy(oMeta, reinterpret_cast<const float4 *>(g.meta), g.nTris);
-        copy(oBvh, g.bvh, 2 * g.nBvhNodes); copy(oBsdf, g.bsdf, 2 * g.nBsdfs); copy(oRadiance, g.radiance, g.nEmitters); copy(oGroups, g.groups, 2 * g.nGroups);
+        copy(oBvh, g.bvh, 2 * g.nBvhNodes); copy(oBsdf, g.bsdf, 4 * g.nBsdfs); copy(oRadiance, g.radiance, g.nEmitters); copy(oGroups, g.groups, 2 * g.nGroups);
         __syncthreads();
     }
 };
@@ -316,21 +316,60 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
     return f3(px, py, z);
 }
 #define PPG_BSDF_TWOSIDED 1u
-struct Bsdf { float3 refl; uint32_t type, flags; };
-template <class Acc>
+#define PPG_BSDF_T_DIFFUSE 0u
+#define PPG_BSDF_T_DIELECTRIC 2u
+#define PPG_BSDF_T_CONDUCTOR 3u
+// 4 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, 0}
+struct Bsdf { float3 refl, trans, etaRgb, k; float eta, invEta; uint32_t type, flags; };
+// DELTA == false: the scene holds diffuse BSDFs only (host-checked), the delta models compile away
+template <bool DELTA, class Acc>
 __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
-    const float4 a = A_.bsdf(2 * idx);
+    const float4 a = A_.bsdf(4 * idx);
     Bsdf b; b.refl = f3(a.x, a.y, a.z);
-    const uint32_t tf = __float_as_uint(a.w); b.type = tf & 0xffu; b.flags = tf >> 8;
+    const uint32_t tf = __float_as_uint(a.w); b.type = DELTA ? (tf & 0xffu) : PPG_BSDF_T_DIFFUSE; b.flags = tf >> 8;
+    b.trans = b.etaRgb = b.k = f3(0, 0, 0); b.eta = b.invEta = 1.f;
+    if (DELTA && b.type != PPG_BSDF_T_DIFFUSE) {
+        const float4 t = A_.bsdf(4 * idx + 1), e = A_.bsdf(4 * idx + 2), k = A_.bsdf(4 * idx + 3);
+        b.trans = f3(t.x, t.y, t.z); b.eta = t.w; b.etaRgb = f3(e.x, e.y, e.z); b.invEta = e.w; b.k = f3(k.x, k.y, k.z);
+    }
     return b;
 }
-// eval / pdf / sample per src/bsdfs/diffuse.cpp:110-150, twosided per src/bsdfs/twosided.cpp:108-184
+__device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE; }                 // type & ESmooth (bsdf.h:224-285)
+__device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC; }
+
+// fresnelDielectricExt, src/libcore/util.cpp:651-683
+__device__ __forceinline__ float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
+    if (eta == 1.f) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    const float scale = (cosThetaI_ > 0.f) ? 1.f / eta : eta, cosThetaTSqr = 1.f - (1.f - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    const float cosThetaI = fabsf(cosThetaI_), cosThetaT = sqrtf(cosThetaTSqr);
+    const float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    const float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0.f) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+// fresnelConductorExact, src/libcore/util.cpp:715-738 (per channel)
+__device__ __forceinline__ float fresnel_conductor_exact(float cosThetaI, float eta, float k) {
+    const float cosThetaI2 = cosThetaI * cosThetaI, sinThetaI2 = 1.f - cosThetaI2, sinThetaI4 = sinThetaI2 * sinThetaI2;
+    const float temp1 = eta * eta - k * k - sinThetaI2;
+    const float a2pb2 = sqrtf(fmaxf(0.0f, temp1 * temp1 + k * k * eta * eta * 4.f));
+    const float a = sqrtf(fmaxf(0.0f, (a2pb2 + temp1) * 0.5f));
+    const float term1 = a2pb2 + cosThetaI2, term2 = a * (2.f * cosThetaI);
+    const float Rs2 = (term1 - term2) / (term1 + term2);
+    const float term3 = a2pb2 * cosThetaI2 + sinThetaI4, term4 = term2 * sinThetaI2;
+    const float Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
+    return 0.5f * (Rp2 + Rs2);
+}
+// eval / pdf in the solid-angle measure (delta models: 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
+// twosided per src/bsdfs/twosided.cpp:108-184
 __device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo) {
+    if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
     return b.refl * (PPG_INV_PI * wo.z);
 }
 __device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
+    if (!bsdf_has_smooth(b)) return 0.0f;
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (wi.z <= 0.f || wo.z <= 0.f) return 0.0f;
     return PPG_INV_PI * wo.z;
@@ -339,6 +378,22 @@ __device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx
     bool flip = false;
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; flip = true; }
     eta = 1.0f; delta = false; pdf = 0.f;
+    if (b.type == PPG_BSDF_T_DIELECTRIC) {
+        float cosThetaT; const float F = fresnel_dielectric_ext(wi.z, cosThetaT, b.eta);
+        delta = true;
+        if (sx <= F) { wo = f3(-wi.x, -wi.y, wi.z); pdf = F; return b.refl; }
+        const float scale = -(cosThetaT < 0.f ? b.invEta : b.eta);
+        wo = f3(scale * wi.x, scale * wi.y, cosThetaT); eta = cosThetaT < 0.f ? b.eta : b.invEta; pdf = 1.f - F;
+        const float factor = cosThetaT < 0.f ? b.invEta : b.eta;
+        return b.trans * (factor * factor);
+    }
+    if (b.type == PPG_BSDF_T_CONDUCTOR) {
+        if (wi.z <= 0.f) return f3(0, 0, 0);
+        delta = true; wo = f3(-wi.x, -wi.y, wi.z); pdf = 1.f;
+        if (flip) wo.z = -wo.z;
+        return f3(b.refl.x * fresnel_conductor_exact(wi.z, b.etaRgb.x, b.k.x), b.refl.y * fresnel_conductor_exact(wi.z, b.etaRgb.y, b.k.y),
+                  b.refl.z * fresnel_conductor_exact(wi.z, b.etaRgb.z, b.k.z));
+    }
     if (wi.z <= 0.f) return f3(0, 0, 0);
     wo = square_to_cosine_hemisphere(sx, sy);
     pdf = PPG_INV_PI * wo.z;

@@ -299,7 +299,7 @@ struct ppg_integrator {
     }
 
     // run state (GP:2313-2323)
-    bool isBuilt = false, isFinalIter = false, doNee = false; int iter = 0, passesRendered = 0; uint32_t nRealEmitters = 0;
+    bool isBuilt = false, isFinalIter = false, doNee = false; int iter = 0, passesRendered = 0; uint32_t nRealEmitters = 0; bool hasDeltaBsdf = false;
     bool useNee() const { return prm.nee != PPG_NEE_NEVER && nRealEmitters > 0; }
     std::chrono::steady_clock::time_point startTime;
     ppg_stats stats; uint64_t launches = 0; double deviceMs = 0;
@@ -396,8 +396,13 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         if (s->shapes[i].bsdf < 0 || (uint32_t) s->shapes[i].bsdf >= s->n_bsdfs) return fail(PPG_ERR_INVALID_ARGUMENT, "shape bsdf out of range");
         if (s->shapes[i].emitter >= (int) s->n_emitters) return fail(PPG_ERR_INVALID_ARGUMENT, "shape emitter out of range");
     }
-    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK)
-        return fail(PPG_ERR_UNSUPPORTED, "BSDF type outside the implemented hot-path scope");
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
+        const int t = s->bsdfs[i].type;
+        if (t != PPG_BSDF_DIFFUSE && t != PPG_BSDF_NULL_BLACK && t != PPG_BSDF_DIELECTRIC && t != PPG_BSDF_CONDUCTOR)
+            return fail(PPG_ERR_UNSUPPORTED, "BSDF type outside the implemented hot-path scope");
+        if (t == PPG_BSDF_DIELECTRIC && !(s->bsdfs[i].eta[0] > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "dielectric needs eta > 0");
+        if (t == PPG_BSDF_DIELECTRIC && (s->bsdfs[i].flags & PPG_BSDF_FLAG_TWOSIDED)) return fail(PPG_ERR_INVALID_ARGUMENT, "twosided cannot wrap a transmissive BSDF (twosided.cpp)");
+    }
     auto P = [&](uint32_t i) { return h3(s->positions[3 * i], s->positions[3 * i + 1], s->positions[3 * i + 2]); };
     std::vector<H3> tmin(nt), tmax(nt);
     for (uint32_t t = 0; t < nt; ++t) {
@@ -471,18 +476,24 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         meta[4 * (size_t) slot] = sh.bsdf; meta[4 * (size_t) slot + 1] = sh.emitter;
         meta[4 * (size_t) slot + 2] = (sh.has_normals && s->normals) ? 1 : 0; meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
     }
-    std::vector<float> bsdf(8 * (size_t) s->n_bsdfs, 0.f);
+    h->hasDeltaBsdf = false;
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type == PPG_BSDF_DIELECTRIC || s->bsdfs[i].type == PPG_BSDF_CONDUCTOR) h->hasDeltaBsdf = true;
+    std::vector<float> bsdf(16 * (size_t) s->n_bsdfs, 0.f);
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
-        float *b = &bsdf[8 * (size_t) i];
-        b[0] = s->bsdfs[i].reflectance[0]; b[1] = s->bsdfs[i].reflectance[1]; b[2] = s->bsdfs[i].reflectance[2];
-        if (s->bsdfs[i].type == PPG_BSDF_NULL_BLACK) b[0] = b[1] = b[2] = 0.f;
-        const uint32_t tf = 0u | ((s->bsdfs[i].flags & 0xffffffu) << 8); memcpy(&b[3], &tf, 4);
+        float *b = &bsdf[16 * (size_t) i]; const ppg_bsdf &m = s->bsdfs[i];
+        b[0] = m.reflectance[0]; b[1] = m.reflectance[1]; b[2] = m.reflectance[2];
+        uint32_t type = (uint32_t) m.type;
+        if (m.type == PPG_BSDF_NULL_BLACK) { b[0] = b[1] = b[2] = 0.f; type = PPG_BSDF_DIFFUSE; }
+        const uint32_t tf = type | ((m.flags & 0xffffffu) << 8); memcpy(&b[3], &tf, 4);
+        b[4] = m.specular_transmittance[0]; b[5] = m.specular_transmittance[1]; b[6] = m.specular_transmittance[2]; b[7] = m.eta[0];
+        b[8] = m.eta[0]; b[9] = m.eta[1]; b[10] = m.eta[2]; b[11] = m.eta[0] != 0.f ? 1.0f / m.eta[0] : 0.f;
+        b[12] = m.k[0]; b[13] = m.k[1]; b[14] = m.k[2];
     }
     std::vector<float> rad(4 * (size_t) std::max<uint32_t>(s->n_emitters, 1), 0.f);
     for (uint32_t i = 0; i < s->n_emitters; ++i) { rad[4 * i] = s->area_radiance[3 * i]; rad[4 * i + 1] = s->area_radiance[3 * i + 1]; rad[4 * i + 2] = s->area_radiance[3 * i + 2]; }
     const size_t nBvh = bvh.nodes.size() / 8;
     CK(h->dAccel.alloc(3 * (size_t) nt)); CK(h->dGeom.alloc(6 * (size_t) nt)); CK(h->dMeta.alloc(nt)); CK(h->dBvh.alloc(2 * nBvh));
-    CK(h->dBsdf.alloc(2 * (size_t) s->n_bsdfs)); CK(h->dRadiance.alloc(std::max<uint32_t>(s->n_emitters, 1)));
+    CK(h->dBsdf.alloc(4 * (size_t) s->n_bsdfs)); CK(h->dRadiance.alloc(std::max<uint32_t>(s->n_emitters, 1)));
     CK(cudaMemcpy(h->dAccel.p, accel.data(), accel.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dGeom.p, geom.data(), geom.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dMeta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
@@ -544,7 +555,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         v.emitterNormalization = norm; h->nRealEmitters = s->n_emitters;
     }
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
-    const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 2 * s->n_bsdfs + v.nEmitters + 2 * v.nGroups);
+    const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 4 * s->n_bsdfs + v.nEmitters + 2 * std::max<uint32_t>(v.nGroups, 1));
     h->sceneSmemBytes = sceneBytes <= 48 * 1024 ? (uint32_t) sceneBytes : 0u;   // small scenes (CBOX: ~9 KB) live in shared memory
     // camera (src/sensors/perspective.cpp:120-298; lookAt columns: left, up, dir, origin -- transform.cpp:191-214)
     const float *m = s->camera.to_world;
@@ -776,7 +787,7 @@ static int ensure_wavefront(ppg_integrator *h) {
     CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true>, PPG_BLOCK, h->sceneSmemBytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BLOCK, h->sceneSmemBytes));
     h->gridBounce = h->numSMs * std::max(occ, 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
     h->gridCommit = h->numSMs * std::max(occ, 1);
@@ -798,18 +809,20 @@ static VertexSlab slab_at(ppg_integrator *h, int k, int set = 0) {
     return s;
 }
 
-template <bool FIRST, bool SMEM> static void launch_bounce2(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
+template <bool FIRST, bool SMEM, bool DELTA> static void launch_bounce3(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
     const size_t sm = P.sceneSmemBytes;
     if (nee) {      // next event estimation always runs with full records
-        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-        else bounce_kernel<FIRST, 2, true, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else bounce_kernel<FIRST, 2, false, SMEM><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+        else bounce_kernel<FIRST, 2, true, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else bounce_kernel<FIRST, 2, false, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
     h->launches++;
 }
 template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
-    if (P.sceneSmemBytes) launch_bounce2<FIRST, true>(h, P, record, grid, nee); else launch_bounce2<FIRST, false>(h, P, record, grid, nee);
+    // scene staged in shared memory or read from HBM; lean instantiation for scenes without delta BSDFs
+    if (P.sceneSmemBytes) { if (h->hasDeltaBsdf) launch_bounce3<FIRST, true, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, true, false>(h, P, record, grid, nee); }
+    else { if (h->hasDeltaBsdf) launch_bounce3<FIRST, false, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, false, false>(h, P, record, grid, nee); }
 }
 
 // one batch of `nPasses` passes as a single wavefront

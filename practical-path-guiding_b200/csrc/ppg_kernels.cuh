@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) 
 // FIRST: generate the camera ray (renderBlock, GP:1613-1632) instead of loading a path state.
 // RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
 //         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
-template <bool FIRST, int RECORD, bool NEE, bool SMEM>
+template <bool FIRST, int RECORD, bool NEE, bool SMEM, bool DELTA>
 __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
     const SceneAccess<SMEM> sc(P.scene);
     sc.stage();
@@ -169,15 +169,19 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                 if (wiDotGeoN * its.wi.z < 0.f && P.strictNormals) cont = false;     // GP:1929-1932
             }
             if (cont) {
-                const Bsdf bsdf = load_bsdf(sc, its.bsdf);
-                int levels; const uint32_t leaf = stree_lookup(P.tree.snodes, P.tree.stable, P.tree.aabbMin, P.tree.extent, its.p, levels);   // GP:1942-1944
-                const float4 la = __ldg(&P.tree.leafA[leaf]);
+                const Bsdf bsdf = load_bsdf<DELTA>(sc, its.bsdf);
+                const bool smooth = bsdf_has_smooth(bsdf);                           // only smooth BSDFs are guided (GP:1942-1944)
+                int levels = 0; uint32_t leaf = 0; float4 la = make_float4(0, 0, 0, 0);
+                if (smooth) {
+                    leaf = stree_lookup(P.tree.snodes, P.tree.stable, P.tree.aabbMin, P.tree.extent, its.p, levels);
+                    la = __ldg(&P.tree.leafA[leaf]);
+                }
                 float frac = P.fixedFraction;
-                if (P.lossMode != 0) frac = logistic(la.z);                          // GP:1946-1949
+                if (smooth && P.lossMode != 0) frac = logistic(la.z);                 // GP:1946-1949
                 // ---- sampleMat, GP:1650-1691
                 float woPdf, bsdfPdf, dTreePdf, bsEta = 1.f; float3 wo, bsdfWeight; bool isDelta = false;
                 float sx = rng.next1D(); const float sy = rng.next1D();
-                if (!P.isBuilt) {
+                if (!P.isBuilt || !smooth) {                                         // not built / no dTree / all-delta BSDF (GP:1654)
                     bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf);
                     woPdf = bsdfPdf; dTreePdf = 0.f;
                 } else {
@@ -205,15 +209,15 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                         bsdfWeight = (woPdf == 0.f) ? f3(0, 0, 0) : result * (1.0f / woPdf);
                     }
                 }
-                const float3 refN = (bsdf.flags & PPG_BSDF_TWOSIDED) ? f3(0, 0, 0) : its.shN;   // DirectSamplingRecord(its), records.inl:160-164
-                if (NEE && P.doNee) {
+                const float3 refN = bsdf_has_transmission_or_backside(bsdf) ? f3(0, 0, 0) : its.shN;   // DirectSamplingRecord(its), records.inl:160-164
+                if (NEE && P.doNee && smooth) {                                       // GP:1967-1969
                     // ---- luminaire sampling, GP:1964-2021
                     const float ex = rng.next1D(), ey = rng.next1D();
                     DirectSample ds; float dist;
                     if (sample_emitter_direct(sc, its.p, refN, ex, ey, ds, dist)) {
                         // Scene::evalTransmittance: shadow ray, epsilon scaled without the clamp (skdtree.cpp:154-158)
                         const float smint = PPG_EPSILON * fmaxf(fmaxf(fabsf(its.p.x), fabsf(its.p.y)), fabsf(its.p.z));
-                        Hit sh; ++raysLocal;
+                        Hit sh;      // (shadow rays are not path vertices: not counted in the samples metric)
                         if (!bvh_intersect(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh)) {
                             const float3 dl = its.toLocal(ds.d);
                             if (!P.strictNormals || dot(its.geoN, ds.d) * dl.z > 0.f) {
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                     o = its.p; d = woW;
                     thr = thr * bsdfWeight; eta *= bsEta;
                     // ---- vertex record (GP:2093-2110); its radiance is Li_final - Li_prefix
-                    if (RECORD && (!isDelta || P.lossMode != 0) && nVertices < PPG_MAX_VERTICES && (1.f / woPdf > 0.f)) {
+                    if (RECORD && smooth && (!isDelta || P.lossMode != 0) && nVertices < PPG_MAX_VERTICES && (1.f / woPdf > 0.f)) {
                         P.slab.v0[i] = make_float4(d.x, d.y, d.z, woPdf);
                         P.slab.v1[i] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(leaf));
                         P.slab.v2[i] = make_float4(Li.x, Li.y, Li.z, __uint_as_float(pathId | (isDelta ? 0x80000000u : 0u)));
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                     rrRecip = 1.f; flags = 0;
                     if (P.depth >= P.rrDepth) {
                         float successProb = 1.0f;
-                        if (!isDelta) {
+                        if (smooth && !isDelta) {
                             if (!P.isBuilt) successProb = max3(thr) * eta * eta;
                             successProb = fmaxf(0.1f, fminf(successProb, 0.99f));
                         }

@@ -1,0 +1,83 @@
+"""Procedural scenes (no assets needed).
+
+``torus_scene`` is a STAND-IN for the reference's TORUS benchmark scene, which is not bundled with the reference
+("available for download on the Mitsuba website", /root/reference/README.md:63-65) and cannot be fetched here: a diffuse
+torus inside a glass cube on a diffuse floor, lit by a small area light -- i.e. every light path to the torus is
+specular-diffuse-specular (SDS), the caustic case path guiding was designed for.  It is NOT the original asset.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .scene import BSDF_CONDUCTOR, BSDF_DIELECTRIC, BSDF_DIFFUSE, SceneDesc, _look_at, _make_bsdf
+
+
+def _quad(p0, p1, p2, p3):
+    return np.array([p0, p1, p2, p3], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+
+
+def _box(lo, hi):
+    x0, y0, z0 = lo; x1, y1, z1 = hi
+    faces = [((x0, y0, z0), (x0, y1, z0), (x1, y1, z0), (x1, y0, z0)), ((x0, y0, z1), (x1, y0, z1), (x1, y1, z1), (x0, y1, z1)),
+             ((x0, y0, z0), (x0, y0, z1), (x0, y1, z1), (x0, y1, z0)), ((x1, y0, z0), (x1, y1, z0), (x1, y1, z1), (x1, y0, z1)),
+             ((x0, y0, z0), (x1, y0, z0), (x1, y0, z1), (x0, y0, z1)), ((x0, y1, z0), (x0, y1, z1), (x1, y1, z1), (x1, y1, z0))]
+    P, I = [], []
+    for f in faces:
+        p, i = _quad(*f)
+        I.append(i + 4 * len(P)); P.append(p)
+    return np.concatenate(P), np.concatenate(I)
+
+
+def _torus(R, r, nu, nv, center):
+    u = np.linspace(0, 2 * np.pi, nu, endpoint=False); v = np.linspace(0, 2 * np.pi, nv, endpoint=False)
+    U, V = np.meshgrid(u, v, indexing="ij")
+    P = np.stack([(R + r * np.cos(V)) * np.cos(U), r * np.sin(V), (R + r * np.cos(V)) * np.sin(U)], -1).reshape(-1, 3)
+    N = np.stack([np.cos(V) * np.cos(U), np.sin(V), np.cos(V) * np.sin(U)], -1).reshape(-1, 3)
+    idx = lambda i, j: (i % nu) * nv + (j % nv)
+    I = []
+    for i in range(nu):
+        for j in range(nv):
+            a, b, c, d = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+            I += [(a, c, b), (a, d, c)]          # outward-facing winding
+    return (P + np.array(center)).astype(np.float32), N.astype(np.float32), np.array(I, np.uint32)
+
+
+def torus_scene(size=256, nu=48, nv=24) -> SceneDesc:
+    meshes = []   # (P, N or None, I, bsdf, emitter)
+    bsdfs = [_make_bsdf(BSDF_DIFFUSE, 0, (0.7, 0.7, 0.7)), _make_bsdf(BSDF_DIFFUSE, 0, (0.8, 0.25, 0.15)),
+             _make_bsdf(BSDF_DIELECTRIC, 0, (1, 1, 1), (1, 1, 1), (1.5046 / 1.000277,) * 3), _make_bsdf(BSDF_DIFFUSE, 0, (0, 0, 0))]
+    names = ["floor", "torus", "glass", "__black"]
+    P, I = _quad((-6, -1.001, -6), (-6, -1.001, 6), (6, -1.001, 6), (6, -1.001, -6)); meshes.append((P, None, I, 0, -1))
+    P, N, I = _torus(0.6, 0.22, nu, nv, (0, -0.3, 0)); meshes.append((P, N, I, 1, -1))
+    P, I = _box((-1, -1, -1), (1, 1, 1)); meshes.append((P, None, I, 2, -1))
+    P, I = _quad((-0.15, 3.0, -0.15), (0.15, 3.0, -0.15), (0.15, 3.0, 0.15), (-0.15, 3.0, 0.15)); meshes.append((P, None, I, 3, 0))   # faces down (-y)
+    Ps, Ns, Is, TS, shapes = [], [], [], [], []
+    voff = toff = 0
+    for k, (P, N, I, b, e) in enumerate(meshes):
+        shapes.append([toff, len(I), b, e, 0 if N is None else 1, 0, 0, 0])
+        Ps.append(P); Ns.append(N if N is not None else np.zeros_like(P)); Is.append(I + voff); TS.append(np.full(len(I), k, np.uint32))
+        voff += len(P); toff += len(I)
+    P = np.concatenate(Ps).astype(np.float32)
+    cam = _look_at((2.6, 1.9, 3.4), (0, -0.2, 0), (0, 1, 0))
+    mn = np.minimum(P.min(0), cam[:3, 3]); mx = np.maximum(P.max(0), cam[:3, 3])
+    integ = {"strictNormals": "true", "maxDepth": "12", "rrDepth": "12", "budgetType": "spp", "budget": "127", "sTreeThreshold": "4000", "sppPerPass": "1"}
+    return SceneDesc(positions=P, normals=np.concatenate(Ns).astype(np.float32), uvs=np.zeros((len(P), 2), np.float32),
+                     indices=np.concatenate(Is).astype(np.uint32), triangle_shape=np.concatenate(TS).astype(np.uint32),
+                     shapes=np.asarray(shapes, np.int32), bsdfs=np.asarray(bsdfs, np.float32), area_radiance=np.array([[400.0, 400.0, 380.0]], np.float32),
+                     cam_to_world=cam.astype(np.float32), x_fov_deg=35.0, near_clip=0.1, far_clip=100.0, film_width=size, film_height=size,
+                     aabb_min=mn.astype(np.float32), aabb_max=mx.astype(np.float32), integrator=integ, bsdf_names=names)
+
+
+def cbox_glass_mirror(cbox: SceneDesc) -> SceneDesc:
+    """CBOX with a glass small box (dielectric, bk7 in air) and a mirror large box (conductor, material=none)."""
+    import copy
+    sc = copy.copy(cbox)
+    nb = len(sc.bsdfs)
+    sc.bsdfs = np.concatenate([sc.bsdfs, np.stack([_make_bsdf(BSDF_DIELECTRIC, 0, (1, 1, 1), (1, 1, 1), (1.5046 / 1.000277,) * 3),
+                                                   _make_bsdf(BSDF_CONDUCTOR, 0, (0.95, 0.95, 0.95), (0, 0, 0), (0, 0, 0), (1, 1, 1))])]).astype(np.float32)
+    sc.bsdf_names = list(sc.bsdf_names) + ["glass", "mirror"]
+    shapes = sc.shapes.copy()
+    shapes[6, 2] = nb          # cbox_smallbox
+    shapes[7, 2] = nb + 1      # cbox_largebox
+    sc.shapes = shapes
+    return sc

@@ -31,7 +31,8 @@ class PpgParams(C.Structure):
 
 
 class PpgBsdf(C.Structure):
-    _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("reflectance", C.c_float * 3), ("reserved", C.c_float * 11)]
+    _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("reflectance", C.c_float * 3), ("specular_transmittance", C.c_float * 3),
+                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("reserved", C.c_float * 2)]
 
 
 class PpgShape(C.Structure):

@@ -37,7 +37,22 @@ _REF_SPECTRUM_CPP = "/root/reference/mitsuba/src/libcore/spectrum.cpp"
 
 BSDF_DIFFUSE = 0
 BSDF_NULL_BLACK = 1
+BSDF_DIELECTRIC = 2
+BSDF_CONDUCTOR = 3
 BSDF_FLAG_TWOSIDED = 1
+
+# a few entries of Mitsuba's named indices of refraction (src/bsdfs/ior.h); defaults: intIOR "bk7", extIOR "air"
+_IOR = {"vacuum": 1.0, "air": 1.000277, "water": 1.3330, "bk7": 1.5046, "diamond": 2.419, "pyrex": 1.470, "acrylic glass": 1.49,
+        "polypropylene": 1.49, "sodium chloride": 1.544, "amber": 1.55, "pet": 1.5750, "helium": 1.000036, "hydrogen": 1.000132, "water ice": 1.31}
+
+
+def _lookup_ior(v, default):
+    if v is None:
+        v = default
+    try:
+        return float(v)
+    except ValueError:
+        return _IOR[v.lower()]
 
 
 # --------------------------------------------------------------------------- CIE data
@@ -368,10 +383,11 @@ class SceneDesc:
                          int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist())
 
 
-def _make_bsdf(type_, flags, refl):
+def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0)):
+    """One ppg_bsdf (include/ppg.h) as 16 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], reserved[2]."""
     b = np.zeros(16, np.float32)
     b[:2] = np.array([type_, flags], np.uint32).view(np.float32)
-    b[2:5] = refl
+    b[2:5] = refl; b[5:8] = trans; b[8:11] = eta; b[11:14] = k
     return b
 
 
@@ -411,14 +427,35 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         flags |= BSDF_FLAG_TWOSIDED
         inner = [c for c in node if c.tag == "bsdf"][0]
         typ = inner.attrib["type"]
-    if typ != "diffuse":
-        raise NotImplementedError(f"BSDF '{typ}' is outside the round-1 hot-path scope (CBOX uses diffuse only)")
-    refl = np.full(3, 0.5, np.float32)  # diffuse.cpp default reflectance
-    for c in inner:
-        if c.attrib.get("name") in ("reflectance", "diffuseReflectance") and c.tag in ("rgb", "srgb", "spectrum"):
-            refl = _parse_color(c)
+    colors = {c.attrib.get("name"): c for c in inner if c.tag in ("rgb", "srgb", "spectrum")}
+    props = _prop_children(inner)
+    if typ == "diffuse":
+        refl = np.full(3, 0.5, np.float32)  # diffuse.cpp default reflectance
+        for nm in ("reflectance", "diffuseReflectance"):
+            if nm in colors:
+                refl = _parse_color(colors[nm])
+        entry = _make_bsdf(BSDF_DIFFUSE, flags, refl)
+    elif typ == "dielectric":           # src/bsdfs/dielectric.cpp:157-190
+        if flags & BSDF_FLAG_TWOSIDED:
+            raise ValueError("twosided cannot wrap a transmissive BSDF")
+        eta = _lookup_ior(props.get("intIOR"), "bk7") / _lookup_ior(props.get("extIOR"), "air")
+        sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
+        st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
+        entry = _make_bsdf(BSDF_DIELECTRIC, flags, sr, st, (eta, eta, eta))
+    elif typ == "conductor":            # src/bsdfs/conductor.cpp:152-176
+        ext = _lookup_ior(props.get("extEta"), "air")
+        if "eta" in colors and "k" in colors:
+            eta, k = _parse_color(colors["eta"]), _parse_color(colors["k"])
+        elif props.get("material", "Cu").lower() == "none":
+            eta, k = np.zeros(3, np.float32), np.ones(3, np.float32)
+        else:
+            raise NotImplementedError("conductor: named materials need Mitsuba's data/ior/*.spd files; give eta/k or material=none")
+        sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
+        entry = _make_bsdf(BSDF_CONDUCTOR, flags, sr, (0, 0, 0), eta / ext, k / ext)
+    else:
+        raise NotImplementedError(f"BSDF '{typ}' is not implemented yet (hot-path scope so far: diffuse, dielectric, conductor, twosided)")
     idx = len(bsdf_table)
-    bsdf_table.append(_make_bsdf(BSDF_DIFFUSE, flags, refl))
+    bsdf_table.append(entry)
     names.append(node.attrib.get("id", f"bsdf{idx}"))
     if "id" in node.attrib:
         by_id[node.attrib["id"]] = idx

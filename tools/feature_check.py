@@ -11,10 +11,11 @@ size = 128
 sc = load_cbox(size)
 variants = {"default": {}, "dbox": {"directionalFilter": "box"}, "stochastic": {"spatialFilter": "stochastic"}, "sbox": {"spatialFilter": "box"},
             "kl": {"bsdfSamplingFractionLoss": "kl"}, "var": {"bsdfSamplingFractionLoss": "var"}, "inversevar": {"sampleCombination": "inversevar"}, "spp1": {"sppPerPass": "1"},
-            "thr4000": {"sTreeThreshold": "4000"}, "kickstart": {"nee": "kickstart"}, "always": {"nee": "always"}}
+            "thr4000": {"sTreeThreshold": "4000"}, "kickstart": {"nee": "kickstart"}, "always": {"nee": "always"}, "combo": {"nee": "kickstart", "spatialFilter": "stochastic", "directionalFilter": "box", "budget": "300"},
+            "kick_stoch": {"nee": "kickstart", "spatialFilter": "stochastic"}, "kick_dbox": {"nee": "kickstart", "directionalFilter": "box"}, "kick300": {"nee": "kickstart", "budget": "300"}}
 sel = sys.argv[1:] or list(variants)
 for name in sel:
-    props = dict(sc.integrator, budget="60", **variants[name])
+    props = dict(dict(sc.integrator, budget="60"), **variants[name])
     o = O.Oracle(O.params_from_xml(props), sc, kind="port"); oi, ost = o.render()
     g = GuidedPathTracer(props); g.set_scene(sc); gi, gst = g.render()
     ow = [round(i["weight_avg"] * i["s_tree_leaves"]) for i in ost["iterations"]]; gw = [round(i["weight_avg"] * i["s_tree_leaves"]) for i in gst["iterations"]]
