@@ -108,8 +108,12 @@ typedef enum ppg_bsdf_type {
     PPG_BSDF_DIFFUSE = 0,        /* src/bsdfs/diffuse.cpp:110-150 */
     PPG_BSDF_NULL_BLACK = 1,     /* shape with an emitter and no BSDF: black diffuse (src/librender/shape.cpp:48-72) */
     PPG_BSDF_DIELECTRIC = 2,     /* src/bsdfs/dielectric.cpp:228-392: delta reflection + refraction, fresnelDielectricExt (libcore/util.cpp:651-683) */
-    PPG_BSDF_CONDUCTOR = 3       /* src/bsdfs/conductor.cpp:223-286: delta reflection, fresnelConductorExact per channel (libcore/util.cpp:740-765) */
+    PPG_BSDF_CONDUCTOR = 3,      /* src/bsdfs/conductor.cpp:223-286: delta reflection, fresnelConductorExact per channel (libcore/util.cpp:740-765) */
+    PPG_BSDF_ROUGHCONDUCTOR = 4  /* src/bsdfs/roughconductor.cpp:257-416 with MicrofacetDistribution (src/bsdfs/microfacet.h): Beckmann or GGX,
+                                    visible-normal sampling; glossy => guided */
 } ppg_bsdf_type;
+
+typedef enum ppg_microfacet { PPG_MICROFACET_BECKMANN = 0, PPG_MICROFACET_GGX = 1 } ppg_microfacet;   /* microfacet.h:47-60 */
 
 #define PPG_BSDF_FLAG_TWOSIDED 1u /* src/bsdfs/twosided.cpp:108-184 wrapping the model */
 
@@ -120,7 +124,8 @@ typedef struct ppg_bsdf {
     float    specular_transmittance[3];  /* dielectric */
     float    eta[3];          /* dielectric: eta[0] = intIOR / extIOR; conductor: eta / extEta per channel */
     float    k[3];            /* conductor: k / extEta per channel */
-    float    reserved[2];
+    float    alpha;           /* rough models: isotropic roughness (clamped to >= 1e-4 like microfacet.h:63) */
+    int32_t  distribution;    /* rough models: ppg_microfacet */
 } ppg_bsdf;                   /* 64 bytes */
 
 typedef struct ppg_shape {

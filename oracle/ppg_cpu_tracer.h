@@ -371,7 +371,7 @@ static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
     return f3(px, py, z);
 }
 struct BsdfSample { F3 wo; float eta; bool delta; };
-static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK; }       // type & ESmooth (bsdf.h:224-285)
+static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK || b.type == PPG_BSDF_ROUGHCONDUCTOR; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
 static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
@@ -397,17 +397,164 @@ static inline float fresnel_conductor_exact(float cosThetaI, float eta, float k)
     const float Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
     return 0.5f * (Rp2 + Rs2);
 }
+// ---- MicrofacetDistribution (isotropic, Beckmann / GGX, visible-normal sampling), restated from src/bsdfs/microfacet.h
+static inline float mts_erfinv(float x) {       // math::erfinv, src/libcore/math.cpp:25-53 (Giles)
+    float w = -std::log((1.0f - x) * (1.0f + x)), p;
+    if (w < 5.0f) {
+        w = w - 2.5f; p = 2.81022636e-08f; p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w;
+        p = 0.00021858087f + p * w; p = -0.00125372503f + p * w; p = -0.00417768164f + p * w; p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+    } else {
+        w = std::sqrt(w) - 3.0f; p = -0.000200214257f; p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w;
+        p = 0.00573950773f + p * w; p = -0.0076224613f + p * w; p = 0.00943887047f + p * w; p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+    }
+    return p * x;
+}
+static inline float mts_erf(float x) {          // math::erf, src/libcore/math.cpp:55-72 (A&S 7.1.26)
+    const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f, p = 0.3275911f;
+    const float sign = std::copysign(1.0f, x); x = std::fabs(x);
+    const float t = 1.0f / (1.0f + p * x);
+    const float y = 1.0f - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * std::exp(-x * x);
+    return sign * y;
+}
+static inline float mts_hypot2(float a, float b) {   // math::hypot2, src/libcore/math.cpp:74-86
+    float r;
+    if (std::fabs(a) > std::fabs(b)) { r = b / a; r = std::fabs(a) * std::sqrt(1.0f + r * r); }
+    else if (b != 0.0f) { r = a / b; r = std::fabs(b) * std::sqrt(1.0f + r * r); }
+    else r = 0.0f;
+    return r;
+}
+struct Microfacet {
+    int type; float alpha;
+    Microfacet(int t, float a) : type(t), alpha(std::max(a, 1e-4f)) {}                    // microfacet.h:60-67
+    float eval(F3 m) const {                                                              // microfacet.h:191-236
+        if (m.z <= 0) return 0.0f;
+        const float cosTheta2 = m.z * m.z;
+        const float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+        float result;
+        if (type == PPG_MICROFACET_BECKMANN) result = std::exp(-beckmannExponent) / (kPiT * alpha * alpha * cosTheta2 * cosTheta2);
+        else { const float root = (1.0f + beckmannExponent) * cosTheta2; result = 1.0f / (kPiT * alpha * alpha * root * root); }
+        if (result * m.z < 1e-20f) result = 0;
+        return result;
+    }
+    float smithG1(F3 v, F3 m) const {                                                     // microfacet.h:477-517
+        if (dot(v, m) * v.z <= 0) return 0.0f;
+        const float temp = 1 - v.z * v.z;
+        const float tanTheta = std::fabs(temp <= 0.0f ? 0.0f : std::sqrt(temp) / v.z);   // Frame::tanTheta
+        if (tanTheta == 0.0f) return 1.0f;
+        if (type == PPG_MICROFACET_BECKMANN) {
+            const float a = 1.0f / (alpha * tanTheta);
+            if (a >= 1.6f) return 1.0f;
+            const float aSqr = a * a;
+            return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+        }
+        const float root = alpha * tanTheta;
+        return 2.0f / (1.0f + mts_hypot2(1.0f, root));
+    }
+    float pdfVisible(F3 wi, F3 m) const {                                                 // microfacet.h:462-466
+        if (wi.z == 0) return 0.0f;
+        return smithG1(wi, m) * std::fabs(dot(wi, m)) * eval(m) / std::fabs(wi.z);
+    }
+    void sampleVisible11(float thetaI, float sx, float sy, float &slopeX, float &slopeY) const {   // microfacet.h:573-690
+        const float SQRT_PI_INV = 1 / std::sqrt(kPiT);
+        if (type == PPG_MICROFACET_BECKMANN) {
+            if (thetaI < 1e-4f) { const float r = std::sqrt(-std::log(1.0f - sx)); const float ph = 2 * kPiT * sy; slopeX = r * std::cos(ph); slopeY = r * std::sin(ph); return; }
+            const float tanThetaI = std::tan(thetaI), cotThetaI = 1 / tanThetaI;
+            float a = -1, c = mts_erf(cotThetaI);
+            const float sample_x = std::max(sx, 1e-6f);
+            const float fit = 1 + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
+            float b = c - (1 + c) * std::pow(1 - sample_x, fit);
+            const float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * std::exp(-cotThetaI * cotThetaI));
+            int it = 0;
+            while (++it < 10) {
+                if (!(b >= a && b <= c)) b = 0.5f * (a + c);
+                const float invErf = mts_erfinv(b);
+                const float value = normalization * (1 + b + SQRT_PI_INV * tanThetaI * std::exp(-invErf * invErf)) - sample_x;
+                const float derivative = normalization * (1 - invErf * tanThetaI);
+                if (std::fabs(value) < 1e-5f) break;
+                if (value > 0) c = b; else a = b;
+                b -= value / derivative;
+            }
+            slopeX = mts_erfinv(b);
+            slopeY = mts_erfinv(2.0f * std::max(sy, 1e-6f) - 1.0f);
+            return;
+        }
+        if (thetaI < 1e-4f) { const float r = std::sqrt(std::max(0.0f, sx / (1 - sx))); const float ph = 2 * kPiT * sy; slopeX = r * std::cos(ph); slopeY = r * std::sin(ph); return; }
+        const float tanThetaI = std::tan(thetaI), a = 1 / tanThetaI;
+        const float G1 = 2.0f / (1.0f + std::sqrt(std::max(0.0f, 1.0f + 1.0f / (a * a))));
+        float A = 2.0f * sx / G1 - 1.0f;
+        if (std::fabs(A) == 1) A -= std::copysign(1.0f, A) * kEpsilon;
+        const float tmp = 1.0f / (A * A - 1.0f), B = tanThetaI;
+        const float D = std::sqrt(std::max(0.0f, B * B * tmp * tmp - (A * A - B * B) * tmp));
+        const float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+        slopeX = (A < 0.0f || slope_x_2 > 1.0f / tanThetaI) ? slope_x_1 : slope_x_2;
+        float S;
+        if (sy > 0.5f) { S = 1.0f; sy = 2.0f * (sy - 0.5f); } else { S = -1.0f; sy = 2.0f * (0.5f - sy); }
+        const float z = (sy * (sy * (sy * (-0.365728915865723f) + 0.790235037209296f) - 0.424965825137544f) + 0.000152998850436920f) /
+                        (sy * (sy * (sy * (sy * 0.169507819808272f - 0.397203533833404f) - 0.232500544458471f) + 1.0f) - 0.539825872510702f);
+        slopeY = S * z * std::sqrt(1.0f + slopeX * slopeX);
+    }
+    F3 sampleVisible(F3 _wi, float sx, float sy) const {                                  // microfacet.h:421-459
+        const F3 wi = normalize(f3(alpha * _wi.x, alpha * _wi.y, _wi.z));
+        float theta = 0, phi = 0;
+        if (wi.z < 0.99999f) { theta = std::acos(wi.z); phi = std::atan2(wi.y, wi.x); }
+        const float sinPhi = std::sin(phi), cosPhi = std::cos(phi);
+        float slx, sly; sampleVisible11(theta, sx, sy, slx, sly);
+        float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;
+        rx *= alpha; ry *= alpha;
+        const float normalization = 1.0f / std::sqrt(rx * rx + ry * ry + 1.0f);
+        return f3(-rx * normalization, -ry * normalization, normalization);
+    }
+};
+static inline F3 fresnel_conductor_rgb(float c, const ppg_bsdf &b) {
+    return f3(b.reflectance[0] * fresnel_conductor_exact(c, b.eta[0], b.k[0]), b.reflectance[1] * fresnel_conductor_exact(c, b.eta[1], b.k[1]),
+              b.reflectance[2] * fresnel_conductor_exact(c, b.eta[2], b.k[2]));
+}
+// roughconductor.cpp:257-283 (eval), :285-312 (pdf), :355-404 (sample)
+static inline F3 roughconductor_eval(const ppg_bsdf &b, F3 wi, F3 wo) {
+    if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
+    const F3 H = normalize(wo + wi);
+    const Microfacet distr(b.distribution, b.alpha);
+    const float D = distr.eval(H);
+    if (D == 0) return f3(0, 0, 0);
+    const F3 F = fresnel_conductor_rgb(dot(wi, H), b);
+    const float G = distr.smithG1(wi, H) * distr.smithG1(wo, H);
+    const float model = D * G / (4.0f * wi.z);
+    return F * model;
+}
+static inline float roughconductor_pdf(const ppg_bsdf &b, F3 wi, F3 wo) {
+    if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+    const F3 H = normalize(wo + wi);
+    const Microfacet distr(b.distribution, b.alpha);
+    return distr.eval(H) * distr.smithG1(wi, H) / (4.0f * wi.z);
+}
+static inline F3 roughconductor_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, F3 &wo, float &pdf) {
+    pdf = 0;
+    if (wi.z < 0) return f3(0, 0, 0);
+    const Microfacet distr(b.distribution, b.alpha);
+    const F3 m = distr.sampleVisible(wi, sx, sy);
+    pdf = distr.pdfVisible(wi, m);
+    if (pdf == 0) return f3(0, 0, 0);
+    wo = m * (2 * dot(wi, m)) - wi;                       // reflect(wi, m) = 2 * dot(wi, m) * Vector(m) - wi
+    if (wo.z <= 0) return f3(0, 0, 0);
+    const F3 F = fresnel_conductor_rgb(dot(wi, m), b);
+    const float weight = distr.smithG1(wo, m);
+    pdf /= 4.0f * dot(wo, m);
+    return F * weight;
+}
+
 // eval / pdf with the solid-angle measure (delta models return 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
 // twosided per src/bsdfs/twosided.cpp:108-184
 static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo) {
     if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
+    if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
     if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
     return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * (kInvPi * wo.z);
 }
 static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo) {
     if (!bsdf_has_smooth(b)) return 0.0f;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
+    if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
     if (wi.z <= 0 || wo.z <= 0) return 0.0f;
     return kInvPi * wo.z;   // warp::squareToCosineHemispherePdf
 }
@@ -431,6 +578,11 @@ static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfS
         if (flip) s.wo.z = -s.wo.z;
         return f3(b.reflectance[0] * fresnel_conductor_exact(wi.z, b.eta[0], b.k[0]), b.reflectance[1] * fresnel_conductor_exact(wi.z, b.eta[1], b.k[1]),
                   b.reflectance[2] * fresnel_conductor_exact(wi.z, b.eta[2], b.k[2]));
+    }
+    if (b.type == PPG_BSDF_ROUGHCONDUCTOR) {
+        const F3 w = roughconductor_sample(b, wi, sx, sy, s.wo, pdf);
+        if (flip) s.wo.z = -s.wo.z;
+        return w;
     }
     if (wi.z <= 0) return f3(0, 0, 0);
     s.wo = square_to_cosine_hemisphere(sx, sy);

@@ -319,22 +319,24 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 #define PPG_BSDF_T_DIFFUSE 0u
 #define PPG_BSDF_T_DIELECTRIC 2u
 #define PPG_BSDF_T_CONDUCTOR 3u
-// 4 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, 0}
-struct Bsdf { float3 refl, trans, etaRgb, k; float eta, invEta; uint32_t type, flags; };
+#define PPG_BSDF_T_ROUGHCONDUCTOR 4u
+// 4 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)}
+struct Bsdf { float3 refl, trans, etaRgb, k; float eta, invEta, alpha; uint32_t type, flags; int distr; };
 // DELTA == false: the scene holds diffuse BSDFs only (host-checked), the delta models compile away
 template <bool DELTA, class Acc>
 __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
     const float4 a = A_.bsdf(4 * idx);
     Bsdf b; b.refl = f3(a.x, a.y, a.z);
     const uint32_t tf = __float_as_uint(a.w); b.type = DELTA ? (tf & 0xffu) : PPG_BSDF_T_DIFFUSE; b.flags = tf >> 8;
-    b.trans = b.etaRgb = b.k = f3(0, 0, 0); b.eta = b.invEta = 1.f;
+    b.trans = b.etaRgb = b.k = f3(0, 0, 0); b.eta = b.invEta = 1.f; b.alpha = 0.1f; b.distr = 1;
     if (DELTA && b.type != PPG_BSDF_T_DIFFUSE) {
         const float4 t = A_.bsdf(4 * idx + 1), e = A_.bsdf(4 * idx + 2), k = A_.bsdf(4 * idx + 3);
         b.trans = f3(t.x, t.y, t.z); b.eta = t.w; b.etaRgb = f3(e.x, e.y, e.z); b.invEta = e.w; b.k = f3(k.x, k.y, k.z);
+        b.alpha = fabsf(k.w); b.distr = k.w < 0.f ? 0 : 1;
     }
     return b;
 }
-__device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE; }                 // type & ESmooth (bsdf.h:224-285)
+__device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE || b.type == PPG_BSDF_T_ROUGHCONDUCTOR; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
 __device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
@@ -360,17 +362,154 @@ __device__ __forceinline__ float fresnel_conductor_exact(float cosThetaI, float 
     const float Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
     return 0.5f * (Rp2 + Rs2);
 }
+// ---- MicrofacetDistribution (isotropic Beckmann / GGX, visible-normal sampling), src/bsdfs/microfacet.h
+__device__ __forceinline__ float mts_erfinv(float x) {       // math::erfinv, src/libcore/math.cpp:25-53
+    float w = -logf((1.0f - x) * (1.0f + x)), p;
+    if (w < 5.0f) {
+        w = w - 2.5f; p = 2.81022636e-08f; p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w;
+        p = 0.00021858087f + p * w; p = -0.00125372503f + p * w; p = -0.00417768164f + p * w; p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+    } else {
+        w = sqrtf(w) - 3.0f; p = -0.000200214257f; p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w;
+        p = 0.00573950773f + p * w; p = -0.0076224613f + p * w; p = 0.00943887047f + p * w; p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+    }
+    return p * x;
+}
+__device__ __forceinline__ float mts_erf(float x) {          // math::erf, src/libcore/math.cpp:55-72
+    const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f, p = 0.3275911f;
+    const float sign = copysignf(1.0f, x); x = fabsf(x);
+    const float t = 1.0f / (1.0f + p * x);
+    const float y = 1.0f - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * expf(-x * x);
+    return sign * y;
+}
+__device__ __forceinline__ float mts_hypot2(float a, float b) {   // math::hypot2, src/libcore/math.cpp:74-86
+    float r;
+    if (fabsf(a) > fabsf(b)) { r = b / a; r = fabsf(a) * sqrtf(1.0f + r * r); }
+    else if (b != 0.0f) { r = a / b; r = fabsf(b) * sqrtf(1.0f + r * r); }
+    else r = 0.0f;
+    return r;
+}
+__device__ __forceinline__ float mf_eval(int type, float alpha, float3 m) {                      // microfacet.h:191-236
+    if (m.z <= 0.f) return 0.0f;
+    const float cosTheta2 = m.z * m.z;
+    const float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+    float result;
+    if (type == 0) result = expf(-beckmannExponent) / (PPG_PI * alpha * alpha * cosTheta2 * cosTheta2);
+    else { const float root = (1.0f + beckmannExponent) * cosTheta2; result = 1.0f / (PPG_PI * alpha * alpha * root * root); }
+    if (result * m.z < 1e-20f) result = 0.f;
+    return result;
+}
+__device__ __forceinline__ float mf_smithG1(int type, float alpha, float3 v, float3 m) {         // microfacet.h:477-517
+    if (dot(v, m) * v.z <= 0.f) return 0.0f;
+    const float temp = 1.f - v.z * v.z;
+    const float tanTheta = fabsf(temp <= 0.0f ? 0.0f : sqrtf(temp) / v.z);
+    if (tanTheta == 0.0f) return 1.0f;
+    if (type == 0) {
+        const float a = 1.0f / (alpha * tanTheta);
+        if (a >= 1.6f) return 1.0f;
+        const float aSqr = a * a;
+        return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+    }
+    return 2.0f / (1.0f + mts_hypot2(1.0f, alpha * tanTheta));
+}
+__device__ __forceinline__ float mf_pdfVisible(int type, float alpha, float3 wi, float3 m) {     // microfacet.h:462-466
+    if (wi.z == 0.f) return 0.0f;
+    return mf_smithG1(type, alpha, wi, m) * fabsf(dot(wi, m)) * mf_eval(type, alpha, m) / fabsf(wi.z);
+}
+__device__ __forceinline__ void mf_sampleVisible11(int type, float thetaI, float sx, float sy, float &slopeX, float &slopeY) {   // microfacet.h:573-690
+    const float SQRT_PI_INV = 1.f / sqrtf(PPG_PI);
+    if (type == 0) {
+        if (thetaI < 1e-4f) { const float r = sqrtf(-logf(1.0f - sx)); float s, c; sincosf(2.f * PPG_PI * sy, &s, &c); slopeX = r * c; slopeY = r * s; return; }
+        const float tanThetaI = tanf(thetaI), cotThetaI = 1.f / tanThetaI;
+        float a = -1.f, c = mts_erf(cotThetaI);
+        const float sample_x = fmaxf(sx, 1e-6f);
+        const float fit = 1.f + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
+        float b = c - (1.f + c) * powf(1.f - sample_x, fit);
+        const float normalization = 1.f / (1.f + c + SQRT_PI_INV * tanThetaI * expf(-cotThetaI * cotThetaI));
+        int it = 0;
+        while (++it < 10) {
+            if (!(b >= a && b <= c)) b = 0.5f * (a + c);
+            const float invErf = mts_erfinv(b);
+            const float value = normalization * (1.f + b + SQRT_PI_INV * tanThetaI * expf(-invErf * invErf)) - sample_x;
+            const float derivative = normalization * (1.f - invErf * tanThetaI);
+            if (fabsf(value) < 1e-5f) break;
+            if (value > 0.f) c = b; else a = b;
+            b -= value / derivative;
+        }
+        slopeX = mts_erfinv(b);
+        slopeY = mts_erfinv(2.0f * fmaxf(sy, 1e-6f) - 1.0f);
+        return;
+    }
+    if (thetaI < 1e-4f) { const float r = sqrtf(fmaxf(0.0f, sx / (1.f - sx))); float s, c; sincosf(2.f * PPG_PI * sy, &s, &c); slopeX = r * c; slopeY = r * s; return; }
+    const float tanThetaI = tanf(thetaI), a = 1.f / tanThetaI;
+    const float G1 = 2.0f / (1.0f + sqrtf(fmaxf(0.0f, 1.0f + 1.0f / (a * a))));
+    float A = 2.0f * sx / G1 - 1.0f;
+    if (fabsf(A) == 1.f) A -= copysignf(1.0f, A) * PPG_EPSILON;
+    const float tmp = 1.0f / (A * A - 1.0f), B = tanThetaI;
+    const float D = sqrtf(fmaxf(0.0f, B * B * tmp * tmp - (A * A - B * B) * tmp));
+    const float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+    slopeX = (A < 0.0f || slope_x_2 > 1.0f / tanThetaI) ? slope_x_1 : slope_x_2;
+    float S;
+    if (sy > 0.5f) { S = 1.0f; sy = 2.0f * (sy - 0.5f); } else { S = -1.0f; sy = 2.0f * (0.5f - sy); }
+    const float z = (sy * (sy * (sy * (-0.365728915865723f) + 0.790235037209296f) - 0.424965825137544f) + 0.000152998850436920f) /
+                    (sy * (sy * (sy * (sy * 0.169507819808272f - 0.397203533833404f) - 0.232500544458471f) + 1.0f) - 0.539825872510702f);
+    slopeY = S * z * sqrtf(1.0f + slopeX * slopeX);
+}
+__device__ __forceinline__ float3 mf_sampleVisible(int type, float alpha, float3 _wi, float sx, float sy) {   // microfacet.h:421-459
+    const float3 wi = normalize(f3(alpha * _wi.x, alpha * _wi.y, _wi.z));
+    float theta = 0.f, phi = 0.f;
+    if (wi.z < 0.99999f) { theta = acosf(wi.z); phi = atan2f(wi.y, wi.x); }
+    float sinPhi, cosPhi; sincosf(phi, &sinPhi, &cosPhi);
+    float slx, sly; mf_sampleVisible11(type, theta, sx, sy, slx, sly);
+    float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;
+    rx *= alpha; ry *= alpha;
+    const float normalization = 1.0f / sqrtf(rx * rx + ry * ry + 1.0f);
+    return f3(-rx * normalization, -ry * normalization, normalization);
+}
+__device__ __forceinline__ float3 fresnel_conductor_rgb(float c, const Bsdf &b) {
+    return f3(b.refl.x * fresnel_conductor_exact(c, b.etaRgb.x, b.k.x), b.refl.y * fresnel_conductor_exact(c, b.etaRgb.y, b.k.y), b.refl.z * fresnel_conductor_exact(c, b.etaRgb.z, b.k.z));
+}
+// roughconductor.cpp:257-283 (eval), :285-312 (pdf), :355-404 (sample)
+__device__ __forceinline__ float3 roughconductor_eval(const Bsdf &b, float3 wi, float3 wo) {
+    if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
+    const float3 H = normalize(wo + wi);
+    const float D = mf_eval(b.distr, b.alpha, H);
+    if (D == 0.f) return f3(0, 0, 0);
+    const float3 F = fresnel_conductor_rgb(dot(wi, H), b);
+    const float G = mf_smithG1(b.distr, b.alpha, wi, H) * mf_smithG1(b.distr, b.alpha, wo, H);
+    return F * (D * G / (4.0f * wi.z));
+}
+__device__ __forceinline__ float roughconductor_pdf(const Bsdf &b, float3 wi, float3 wo) {
+    if (wi.z <= 0.f || wo.z <= 0.f) return 0.0f;
+    const float3 H = normalize(wo + wi);
+    return mf_eval(b.distr, b.alpha, H) * mf_smithG1(b.distr, b.alpha, wi, H) / (4.0f * wi.z);
+}
+__device__ __forceinline__ float3 roughconductor_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &pdf) {
+    pdf = 0.f;
+    if (wi.z < 0.f) return f3(0, 0, 0);
+    const float3 m = mf_sampleVisible(b.distr, b.alpha, wi, sx, sy);
+    pdf = mf_pdfVisible(b.distr, b.alpha, wi, m);
+    if (pdf == 0.f) return f3(0, 0, 0);
+    wo = m * (2.f * dot(wi, m)) - wi;
+    if (wo.z <= 0.f) return f3(0, 0, 0);
+    const float3 F = fresnel_conductor_rgb(dot(wi, m), b);
+    const float weight = mf_smithG1(b.distr, b.alpha, wo, m);
+    pdf /= 4.0f * dot(wo, m);
+    return F * weight;
+}
+
 // eval / pdf in the solid-angle measure (delta models: 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
 // twosided per src/bsdfs/twosided.cpp:108-184
 __device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo) {
     if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
+    if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
     if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
     return b.refl * (PPG_INV_PI * wo.z);
 }
 __device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
     if (!bsdf_has_smooth(b)) return 0.0f;
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
+    if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
     if (wi.z <= 0.f || wo.z <= 0.f) return 0.0f;
     return PPG_INV_PI * wo.z;
 }
@@ -393,6 +532,11 @@ __device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx
         if (flip) wo.z = -wo.z;
         return f3(b.refl.x * fresnel_conductor_exact(wi.z, b.etaRgb.x, b.k.x), b.refl.y * fresnel_conductor_exact(wi.z, b.etaRgb.y, b.k.y),
                   b.refl.z * fresnel_conductor_exact(wi.z, b.etaRgb.z, b.k.z));
+    }
+    if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) {
+        const float3 w = roughconductor_sample(b, wi, sx, sy, wo, pdf);
+        if (flip) wo.z = -wo.z;
+        return w;
     }
     if (wi.z <= 0.f) return f3(0, 0, 0);
     wo = square_to_cosine_hemisphere(sx, sy);

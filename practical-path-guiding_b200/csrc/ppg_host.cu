@@ -398,7 +398,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     }
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
         const int t = s->bsdfs[i].type;
-        if (t != PPG_BSDF_DIFFUSE && t != PPG_BSDF_NULL_BLACK && t != PPG_BSDF_DIELECTRIC && t != PPG_BSDF_CONDUCTOR)
+        if (t != PPG_BSDF_DIFFUSE && t != PPG_BSDF_NULL_BLACK && t != PPG_BSDF_DIELECTRIC && t != PPG_BSDF_CONDUCTOR && t != PPG_BSDF_ROUGHCONDUCTOR)
             return fail(PPG_ERR_UNSUPPORTED, "BSDF type outside the implemented hot-path scope");
         if (t == PPG_BSDF_DIELECTRIC && !(s->bsdfs[i].eta[0] > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "dielectric needs eta > 0");
         if (t == PPG_BSDF_DIELECTRIC && (s->bsdfs[i].flags & PPG_BSDF_FLAG_TWOSIDED)) return fail(PPG_ERR_INVALID_ARGUMENT, "twosided cannot wrap a transmissive BSDF (twosided.cpp)");
@@ -477,7 +477,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         meta[4 * (size_t) slot + 2] = (sh.has_normals && s->normals) ? 1 : 0; meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
     }
     h->hasDeltaBsdf = false;
-    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type == PPG_BSDF_DIELECTRIC || s->bsdfs[i].type == PPG_BSDF_CONDUCTOR) h->hasDeltaBsdf = true;
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) h->hasDeltaBsdf = true;   // any non-diffuse model
     std::vector<float> bsdf(16 * (size_t) s->n_bsdfs, 0.f);
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
         float *b = &bsdf[16 * (size_t) i]; const ppg_bsdf &m = s->bsdfs[i];
@@ -488,6 +488,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         b[4] = m.specular_transmittance[0]; b[5] = m.specular_transmittance[1]; b[6] = m.specular_transmittance[2]; b[7] = m.eta[0];
         b[8] = m.eta[0]; b[9] = m.eta[1]; b[10] = m.eta[2]; b[11] = m.eta[0] != 0.f ? 1.0f / m.eta[0] : 0.f;
         b[12] = m.k[0]; b[13] = m.k[1]; b[14] = m.k[2];
+        b[15] = std::max(m.alpha, 1e-4f) * (m.distribution == PPG_MICROFACET_BECKMANN ? -1.0f : 1.0f);   // microfacet.h:63 clamp; sign encodes the distribution
     }
     std::vector<float> rad(4 * (size_t) std::max<uint32_t>(s->n_emitters, 1), 0.f);
     for (uint32_t i = 0; i < s->n_emitters; ++i) { rad[4 * i] = s->area_radiance[3 * i]; rad[4 * i + 1] = s->area_radiance[3 * i + 1]; rad[4 * i + 2] = s->area_radiance[3 * i + 2]; }

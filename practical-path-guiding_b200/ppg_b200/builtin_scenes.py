@@ -81,3 +81,19 @@ def cbox_glass_mirror(cbox: SceneDesc) -> SceneDesc:
     shapes[7, 2] = nb + 1      # cbox_largebox
     sc.shapes = shapes
     return sc
+
+
+def cbox_rough_metal(cbox: SceneDesc) -> SceneDesc:
+    """CBOX whose boxes are rough conductors: the small box GGX alpha 0.1 with the eta/k of spaceship.xml's "RoughAluminium",
+    the large box Beckmann alpha 0.3 -- glossy BSDFs are guided (ESmooth) and take part in light sampling."""
+    import copy
+    from .scene import BSDF_ROUGHCONDUCTOR
+    sc = copy.copy(cbox)
+    nb = len(sc.bsdfs)
+    sc.bsdfs = np.concatenate([sc.bsdfs, np.stack([
+        _make_bsdf(BSDF_ROUGHCONDUCTOR, 0, (0.578596,) * 3, (0, 0, 0), (1.65746, 0.880369, 0.521229), (9.22387, 6.26952, 4.837), 0.1, 1),
+        _make_bsdf(BSDF_ROUGHCONDUCTOR, 0, (1, 1, 1), (0, 0, 0), (0.2, 0.92, 1.1), (3.9, 2.45, 2.14), 0.3, 0)])]).astype(np.float32)
+    sc.bsdf_names = list(sc.bsdf_names) + ["rough_aluminium_ggx", "rough_gold_beckmann"]
+    shapes = sc.shapes.copy(); shapes[6, 2] = nb; shapes[7, 2] = nb + 1
+    sc.shapes = shapes
+    return sc

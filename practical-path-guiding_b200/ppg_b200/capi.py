@@ -32,7 +32,7 @@ class PpgParams(C.Structure):
 
 class PpgBsdf(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("reflectance", C.c_float * 3), ("specular_transmittance", C.c_float * 3),
-                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("reserved", C.c_float * 2)]
+                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("alpha", C.c_float), ("distribution", C.c_int32)]
 
 
 class PpgShape(C.Structure):

@@ -39,6 +39,7 @@ BSDF_DIFFUSE = 0
 BSDF_NULL_BLACK = 1
 BSDF_DIELECTRIC = 2
 BSDF_CONDUCTOR = 3
+BSDF_ROUGHCONDUCTOR = 4
 BSDF_FLAG_TWOSIDED = 1
 
 # a few entries of Mitsuba's named indices of refraction (src/bsdfs/ior.h); defaults: intIOR "bk7", extIOR "air"
@@ -383,11 +384,12 @@ class SceneDesc:
                          int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist())
 
 
-def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0)):
-    """One ppg_bsdf (include/ppg.h) as 16 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], reserved[2]."""
+def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0), alpha=0.1, distribution=0):
+    """One ppg_bsdf (include/ppg.h) as 16 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], alpha, distribution (int bits)."""
     b = np.zeros(16, np.float32)
     b[:2] = np.array([type_, flags], np.uint32).view(np.float32)
-    b[2:5] = refl; b[5:8] = trans; b[8:11] = eta; b[11:14] = k
+    b[2:5] = refl; b[5:8] = trans; b[8:11] = eta; b[11:14] = k; b[14] = alpha
+    b[15:16] = np.array([distribution], np.int32).view(np.float32)
     return b
 
 
@@ -442,6 +444,21 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
         entry = _make_bsdf(BSDF_DIELECTRIC, flags, sr, st, (eta, eta, eta))
+    elif typ == "roughconductor":       # src/bsdfs/roughconductor.cpp:190-222
+        ext = _lookup_ior(props.get("extEta"), "air")
+        if "eta" in colors and "k" in colors:
+            eta, k = _parse_color(colors["eta"]), _parse_color(colors["k"])
+        elif props.get("material", "Cu").lower() == "none":
+            eta, k = np.zeros(3, np.float32), np.ones(3, np.float32)
+        else:
+            raise NotImplementedError("roughconductor: named materials need Mitsuba's data/ior/*.spd files; give eta/k or material=none")
+        if "alphaU" in props or "alphaV" in props:
+            raise NotImplementedError("anisotropic roughness")
+        distr = props.get("distribution", "beckmann").lower()
+        if distr not in ("beckmann", "ggx"):
+            raise NotImplementedError(f"microfacet distribution '{distr}'")
+        sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
+        entry = _make_bsdf(BSDF_ROUGHCONDUCTOR, flags, sr, (0, 0, 0), eta / ext, k / ext, float(props.get("alpha", 0.1)), 1 if distr == "ggx" else 0)
     elif typ == "conductor":            # src/bsdfs/conductor.cpp:152-176
         ext = _lookup_ior(props.get("extEta"), "air")
         if "eta" in colors and "k" in colors:

@@ -33,6 +33,8 @@ def _declare(lib):
     lib.ppgo_step_passes.argtypes = [H, C.c_int, C.c_int, f32p]
     lib.ppgo_step_build.argtypes = [H, C.POINTER(capi.PpgIterationStats)]
     lib.ppgo_get_moment_images.argtypes = [H, f32p, f32p]
+    lib.ppgo_bsdf_eval_pdf.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p]
+    lib.ppgo_bsdf_sample.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p, u8p]
     lib.ppgo_tree_refine.argtypes = [H, C.c_uint64, C.c_int]
     lib.ppgo_tree_reset.argtypes = [H, C.c_int, C.c_float]
     lib.ppgo_tree_build.argtypes = [H]
@@ -250,3 +252,25 @@ class Oracle:
                                   P(e["children"], C.c_uint16), P(e["adam"], C.c_float), P(e["aabb"], C.c_float))
         e["n_leaves"] = int(cnt[1])
         return e
+
+
+def make_bsdf(type=0, flags=0, reflectance=(0.5, 0.5, 0.5), transmittance=(1, 1, 1), eta=(1.5, 1.5, 1.5), k=(0, 0, 0), alpha=0.1, distribution=1):
+    b = capi.PpgBsdf()
+    b.type = type; b.flags = flags; b.alpha = alpha; b.distribution = distribution
+    for i in range(3):
+        b.reflectance[i] = reflectance[i]; b.specular_transmittance[i] = transmittance[i]; b.eta[i] = eta[i]; b.k[i] = k[i]
+    return b
+
+
+def bsdf_eval_pdf(b, wi, wo, kind="port"):
+    lib = load(kind); wi = np.ascontiguousarray(wi, np.float32); wo = np.ascontiguousarray(wo, np.float32)
+    ev = np.zeros_like(wi); pdf = np.zeros(len(wi), np.float32)
+    lib.ppgo_bsdf_eval_pdf(C.byref(b), len(wi), fptr(wi), fptr(wo), fptr(ev), fptr(pdf))
+    return ev, pdf
+
+
+def bsdf_sample(b, wi, smp, kind="port"):
+    lib = load(kind); wi = np.ascontiguousarray(wi, np.float32); smp = np.ascontiguousarray(smp, np.float32)
+    wo = np.zeros_like(wi); w = np.zeros_like(wi); pdf = np.zeros(len(wi), np.float32); d = np.zeros(len(wi), np.uint8)
+    lib.ppgo_bsdf_sample(C.byref(b), len(wi), fptr(wi), fptr(smp), fptr(wo), fptr(w), fptr(pdf), d.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return wo, w, pdf, d

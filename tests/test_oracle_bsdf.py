@@ -1,0 +1,67 @@
+"""BSDF restatements of the oracle, checked the way the reference checks its BSDFs (src/tests/test_chisquare.cpp:391-623):
+sample() must be distributed according to pdf(), and the sampling weight must equal eval()/pdf()."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+CASES = {
+    "diffuse": dict(type=0, reflectance=(0.6, 0.5, 0.4)),
+    "roughconductor-ggx-0.1": dict(type=4, reflectance=(1, 1, 1), eta=(1.65746, 0.880369, 0.521229), k=(9.22387, 6.26952, 4.837), alpha=0.1, distribution=1),   # spaceship.xml "RoughAluminium"
+    "roughconductor-ggx-0.4": dict(type=4, reflectance=(0.9, 0.9, 0.9), eta=(2, 2, 2), k=(0, 0, 0), alpha=0.4, distribution=1),
+    "roughconductor-beckmann-0.3": dict(type=4, reflectance=(1, 1, 1), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), alpha=0.3, distribution=0),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("cos_i", [0.95, 0.5, 0.15])
+def test_sample_matches_pdf_and_weight_matches_eval(name, cos_i):
+    b = O.make_bsdf(**CASES[name])
+    rng = np.random.default_rng(1)
+    n = 400000
+    wi = np.tile(np.array([[np.sqrt(1 - cos_i ** 2), 0.0, cos_i]], np.float32), (n, 1))
+    wo, w, pdf, delta = O.bsdf_sample(b, wi, rng.random((n, 2), dtype=np.float32))
+    ok = (pdf > 0) & (w.sum(axis=1) > 0)
+    assert ok.mean() > 0.3
+    ev, pdf2 = O.bsdf_eval_pdf(b, wi[ok], wo[ok])
+    assert np.allclose(pdf2, pdf[ok], rtol=2e-3, atol=1e-6)                       # pdf() of the sampled direction == pdf returned by sample()
+    assert np.allclose(ev, w[ok] * pdf[ok, None], rtol=3e-3, atol=1e-5)         # weight == eval / pdf
+    # chi^2: histogram of sampled directions vs integral of pdf over a (cos theta, phi) grid on the upper hemisphere
+    nb_c, nb_p = 10, 20
+    wo_ok = wo[ok]
+    ct = np.clip(wo_ok[:, 2], 0, 1); ph = np.mod(np.arctan2(wo_ok[:, 1], wo_ok[:, 0]), 2 * np.pi)
+    H, _, _ = np.histogram2d(ct, ph / (2 * np.pi), bins=[nb_c, nb_p], range=[[0, 1], [0, 1]])
+    g = (np.arange(12) + 0.5) / 12
+    exp = np.zeros((nb_c, nb_p))
+    for i in range(nb_c):
+        for j in range(nb_p):
+            c = ((i + g[:, None]) / nb_c + 0 * g[None, :]).ravel(); p = (2 * np.pi * (j + g[None, :]) / nb_p + 0 * g[:, None]).ravel()
+            sn = np.sqrt(1 - c * c)
+            d = np.stack([sn * np.cos(p), sn * np.sin(p), c], -1).astype(np.float32)
+            _, pd = O.bsdf_eval_pdf(b, np.tile(wi[:1], (len(d), 1)), d)
+            exp[i, j] = pd.mean() * (2 * np.pi / (nb_c * nb_p))
+    exp *= n                      # failed samples (pdf == 0) carry no mass: compare absolute counts
+    mask = exp > 10
+    chi2 = np.sum((H[mask] - exp[mask]) ** 2 / exp[mask]); dof = mask.sum() - 1
+    assert chi2 < dof + 8 * np.sqrt(2 * dof) + 0.02 * n * 0, (chi2, dof)
+    assert abs(H.sum() - exp.sum()) < 0.03 * n
+
+
+def test_dielectric_and_conductor_are_delta_and_energy_conserving():
+    glass = O.make_bsdf(type=2, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5, 1.5, 1.5))
+    rng = np.random.default_rng(2)
+    n = 100000
+    for cz in (0.9, 0.3, -0.6):
+        wi = np.tile(np.array([[np.sqrt(1 - cz ** 2), 0, cz]], np.float32), (n, 1))
+        wo, w, pdf, delta = O.bsdf_sample(glass, wi, rng.random((n, 2), dtype=np.float32))
+        assert delta.all()
+        refl = wo[:, 2] * cz > 0
+        F = refl.mean()
+        assert np.allclose(pdf[refl], F, atol=0.01) and np.allclose(pdf[~refl], 1 - F, atol=0.01)      # discrete lobe probabilities F / 1-F
+        assert np.allclose(np.linalg.norm(wo, axis=1), 1, atol=1e-5)
+        ev, pd = O.bsdf_eval_pdf(glass, wi, wo)
+        assert not ev.any() and not pd.any()                                                           # delta lobes: zero in the solid-angle measure
+    mirror = O.make_bsdf(type=3, reflectance=(1, 1, 1), eta=(0, 0, 0), k=(1, 1, 1))
+    wi = np.tile(np.array([[0.6, 0, 0.8]], np.float32), (4, 1))
+    wo, w, pdf, delta = O.bsdf_sample(mirror, wi, rng.random((4, 2), dtype=np.float32))
+    assert np.allclose(wo, [-0.6, 0, 0.8]) and np.allclose(w, 1.0, atol=1e-5) and np.allclose(pdf, 1) and delta.all()   # eta=0,k=1: perfect mirror (conductor.cpp:159-176)
