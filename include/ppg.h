@@ -109,24 +109,35 @@ typedef enum ppg_bsdf_type {
     PPG_BSDF_NULL_BLACK = 1,     /* shape with an emitter and no BSDF: black diffuse (src/librender/shape.cpp:48-72) */
     PPG_BSDF_DIELECTRIC = 2,     /* src/bsdfs/dielectric.cpp:228-392: delta reflection + refraction, fresnelDielectricExt (libcore/util.cpp:651-683) */
     PPG_BSDF_CONDUCTOR = 3,      /* src/bsdfs/conductor.cpp:223-286: delta reflection, fresnelConductorExact per channel (libcore/util.cpp:740-765) */
-    PPG_BSDF_ROUGHCONDUCTOR = 4  /* src/bsdfs/roughconductor.cpp:257-416 with MicrofacetDistribution (src/bsdfs/microfacet.h): Beckmann or GGX,
+    PPG_BSDF_ROUGHCONDUCTOR = 4, /* src/bsdfs/roughconductor.cpp:257-416 with MicrofacetDistribution (src/bsdfs/microfacet.h): Beckmann or GGX,
                                     visible-normal sampling; glossy => guided */
+    PPG_BSDF_ROUGHDIELECTRIC = 6,/* src/bsdfs/roughdielectric.cpp:270-600: rough refractive interface (reflectance = specularReflectance,
+                                    specular_transmittance, eta[0] = intIOR/extIOR, alpha, distribution); draws one extra path-sampler number */
+    PPG_BSDF_ROUGHPLASTIC = 5    /* src/bsdfs/roughplastic.cpp:326-507: rough dielectric coat over a diffuse base; the rough transmittance
+                                    (src/bsdfs/rtrans.h) is passed as a per-material 100-entry table + scalars */
 } ppg_bsdf_type;
 
 typedef enum ppg_microfacet { PPG_MICROFACET_BECKMANN = 0, PPG_MICROFACET_GGX = 1 } ppg_microfacet;   /* microfacet.h:47-60 */
 
 #define PPG_BSDF_FLAG_TWOSIDED 1u /* src/bsdfs/twosided.cpp:108-184 wrapping the model */
+#define PPG_BSDF_FLAG_NONLINEAR 2u /* roughplastic "nonlinear" (roughplastic.cpp:366-369) */
+#define PPG_BSDF_TABLE_SIZE 100   /* theta samples of the rough-transmittance tables (data/microfacet/*.dat) */
 
 typedef struct ppg_bsdf {
     int32_t  type;            /* ppg_bsdf_type */
     uint32_t flags;
-    float    reflectance[3];  /* diffuse: reflectance; dielectric / conductor: specularReflectance. Linear Rec.709 RGB (scenehandler.cpp:597-613) */
+    float    reflectance[3];  /* diffuse / roughplastic: diffuse reflectance; dielectric / conductor: specularReflectance. Linear Rec.709 RGB (scenehandler.cpp:597-613) */
     float    specular_transmittance[3];  /* dielectric */
     float    eta[3];          /* dielectric: eta[0] = intIOR / extIOR; conductor: eta / extEta per channel */
     float    k[3];            /* conductor: k / extEta per channel */
     float    alpha;           /* rough models: isotropic roughness (clamped to >= 1e-4 like microfacet.h:63) */
     int32_t  distribution;    /* rough models: ppg_microfacet */
-} ppg_bsdf;                   /* 64 bytes */
+    float    specular_reflectance[3];   /* roughplastic */
+    float    fdr_int;         /* roughplastic: 1 - internal diffuse rough transmittance (Fdr of roughplastic.cpp:364) */
+    float    specular_sampling_weight;  /* roughplastic: sAvg / (dAvg + sAvg) (roughplastic.cpp:269-272) */
+    int32_t  table;           /* roughplastic: index into ppg_scene_desc.bsdf_tables (external rough transmittance over cos(theta)^(1/4)) */
+    float    reserved[2];
+} ppg_bsdf;                   /* 96 bytes */
 
 typedef struct ppg_shape {
     uint32_t first_triangle;  /* triangles of a shape are contiguous */
@@ -159,6 +170,8 @@ typedef struct ppg_scene_desc {
     const ppg_shape *shapes;
     const ppg_bsdf  *bsdfs;
     const float    *area_radiance;  /* 3*n_emitters: area-light radiance RGB (src/emitters/area.cpp:104-109) */
+    const float    *bsdf_tables;    /* n_bsdf_tables * PPG_BSDF_TABLE_SIZE floats, may be NULL */
+    uint32_t        n_bsdf_tables;
     ppg_camera camera;
     float aabb_min[3], aabb_max[3]; /* Scene::getAABB(): kd-tree AABB + sensor + emitter AABBs (librender/scene.cpp:387-413) */
 } ppg_scene_desc;

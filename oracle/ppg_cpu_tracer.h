@@ -129,7 +129,7 @@ struct BvhNode { float bmin[3], bmax[3]; uint32_t left, count; };   // count>0: 
 struct Scene {
     std::vector<F3> P, N; std::vector<float> UV;
     std::vector<uint32_t> idx, triShape;
-    std::vector<ppg_shape> shapes; std::vector<ppg_bsdf> bsdfs; std::vector<F3> radiance;
+    std::vector<ppg_shape> shapes; std::vector<ppg_bsdf> bsdfs; std::vector<F3> radiance; std::vector<float> tables;
     ppg_camera cam; F3 aabbMin, aabbMax;
     std::vector<TriAccelP> accel; std::vector<BvhNode> bvh; std::vector<uint32_t> primOrder;
     // camera derived (src/sensors/perspective.cpp:120-298)
@@ -176,6 +176,8 @@ struct Scene {
         triShape.assign(d.triangle_shape, d.triangle_shape + d.n_triangles);
         shapes.assign(d.shapes, d.shapes + d.n_shapes);
         bsdfs.assign(d.bsdfs, d.bsdfs + d.n_bsdfs);
+        tables.clear();
+        if (d.bsdf_tables && d.n_bsdf_tables) tables.assign(d.bsdf_tables, d.bsdf_tables + (size_t)d.n_bsdf_tables * PPG_BSDF_TABLE_SIZE);
         radiance.resize(d.n_emitters);
         for (uint32_t i = 0; i < d.n_emitters; ++i) radiance[i] = f3(d.area_radiance[3 * i], d.area_radiance[3 * i + 1], d.area_radiance[3 * i + 2]);
         cam = d.camera;
@@ -371,8 +373,8 @@ static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
     return f3(px, py, z);
 }
 struct BsdfSample { F3 wo; float eta; bool delta; };
-static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK || b.type == PPG_BSDF_ROUGHCONDUCTOR; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
-static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC; }
+static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK || b.type == PPG_BSDF_ROUGHCONDUCTOR || b.type == PPG_BSDF_ROUGHPLASTIC || b.type == PPG_BSDF_ROUGHDIELECTRIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
+static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC || b.type == PPG_BSDF_ROUGHDIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
 static inline float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
@@ -542,23 +544,175 @@ static inline F3 roughconductor_sample(const ppg_bsdf &b, F3 wi, float sx, float
     return F * weight;
 }
 
+// ---- roughplastic (src/bsdfs/roughplastic.cpp). The external rough transmittance of the material (constant eta, alpha) is the 1-D table
+// RoughTransmittance::eval reads once alpha and eta are fixed (src/bsdfs/rtrans.h:183-193, 233), interpolated by evalCubicInterp1D
+// (src/libcore/spline.cpp:23-60) over cos(theta)^(1/4).
+static inline float rough_transmittance(const float *values, float cosTheta) {
+    if (!(cosTheta >= 0)) return 0.0f;
+    const float x = std::pow(std::fabs(cosTheta), 0.25f);
+    const size_t size = PPG_BSDF_TABLE_SIZE;
+    float result = 0.0f;
+    if (x >= 0.0f && x <= 1.0f) {
+        float t = ((x - 0.0f) * (size - 1)) / (1.0f - 0.0f);
+        const size_t k = std::max((size_t)0, std::min((size_t)t, size - 2));
+        const float f0 = values[k], f1 = values[k + 1];
+        const float d0 = k > 0 ? 0.5f * (values[k + 1] - values[k - 1]) : values[k + 1] - values[k];
+        const float d1 = k + 2 < size ? 0.5f * (values[k + 2] - values[k]) : values[k + 1] - values[k];
+        t = t - (float)k;
+        const float t2 = t * t, t3 = t2 * t;
+        result = (2 * t3 - 3 * t2 + 1) * f0 + (-2 * t3 + 3 * t2) * f1 + (t3 - 2 * t2 + t) * d0 + (t3 - t2) * d1;
+    }
+    return std::min(1.0f, std::max(0.0f, result));
+}
+static inline float roughplastic_prob_specular(const ppg_bsdf &b, const float *lut, float cosThetaI) {   // roughplastic.cpp:403-409 = :446-452
+    float probSpecular = 1 - rough_transmittance(lut, cosThetaI);
+    return (probSpecular * b.specular_sampling_weight) / (probSpecular * b.specular_sampling_weight + (1 - probSpecular) * (1 - b.specular_sampling_weight));
+}
+static inline F3 roughplastic_eval(const ppg_bsdf &b, const float *lut, F3 wi, F3 wo) {                  // roughplastic.cpp:326-380
+    if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
+    const Microfacet distr(b.distribution, b.alpha);
+    const F3 H = normalize(wo + wi);
+    const float D = distr.eval(H);
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, b.eta[0]);
+    const float G = distr.smithG1(wi, H) * distr.smithG1(wo, H);
+    const float value = F * D * G / (4.0f * wi.z);
+    F3 result = f3(b.specular_reflectance[0], b.specular_reflectance[1], b.specular_reflectance[2]) * value;
+    F3 diff = f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+    const float T12 = rough_transmittance(lut, wi.z), T21 = rough_transmittance(lut, wo.z), Fdr = b.fdr_int;
+    if (b.flags & PPG_BSDF_FLAG_NONLINEAR) diff = f3(diff.x / (1.0f - diff.x * Fdr), diff.y / (1.0f - diff.y * Fdr), diff.z / (1.0f - diff.z * Fdr));
+    else diff = diff * (1.0f / (1 - Fdr));                   // Spectrum /= Float multiplies by the reciprocal (core/spectrum.h:447-456)
+    const float invEta2 = 1 / (b.eta[0] * b.eta[0]);
+    return result + diff * (kInvPi * wo.z * T12 * T21 * invEta2);
+}
+static inline float roughplastic_pdf(const ppg_bsdf &b, const float *lut, F3 wi, F3 wo) {                // roughplastic.cpp:382-430
+    if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+    const Microfacet distr(b.distribution, b.alpha);
+    const F3 H = normalize(wo + wi);
+    const float probSpecular = roughplastic_prob_specular(b, lut, wi.z), probDiffuse = 1 - probSpecular;
+    const float dwh_dwo = 1.0f / (4.0f * dot(wo, H));
+    const float prob = distr.pdfVisible(wi, H);
+    float result = prob * dwh_dwo * probSpecular;
+    result += probDiffuse * (kInvPi * wo.z);
+    return result;
+}
+static inline F3 roughplastic_sample(const ppg_bsdf &b, const float *lut, F3 wi, float sx, float sy, F3 &wo, float &pdf) {   // roughplastic.cpp:432-497
+    pdf = 0;
+    if (wi.z <= 0) return f3(0, 0, 0);
+    bool choseSpecular = true;
+    const Microfacet distr(b.distribution, b.alpha);
+    const float probSpecular = roughplastic_prob_specular(b, lut, wi.z);
+    if (sy < probSpecular) sy /= probSpecular;
+    else { sy = (sy - probSpecular) / (1 - probSpecular); choseSpecular = false; }
+    if (choseSpecular) {
+        const F3 m = distr.sampleVisible(wi, sx, sy);
+        wo = m * (2 * dot(wi, m)) - wi;
+        if (wo.z <= 0) return f3(0, 0, 0);
+    } else wo = square_to_cosine_hemisphere(sx, sy);
+    pdf = roughplastic_pdf(b, lut, wi, wo);
+    if (pdf == 0) return f3(0, 0, 0);
+    return roughplastic_eval(b, lut, wi, wo) * (1.0f / pdf);  // Spectrum / Float, core/spectrum.h:415-425
+}
+// ---- roughdielectric (src/bsdfs/roughdielectric.cpp), visible-normal sampling (m_sampleVisible, the default: no Walter alpha scaling).
+// sample() draws ONE extra number from the path's sampler to choose reflection / refraction (EUsesSampler, :536-543).
+static inline float mts_signum(float v) { return std::copysign(1.0f, v); }                             // core/math.h:269-278
+static inline F3 roughdielectric_eval(const ppg_bsdf &b, F3 wi, F3 wo) {                                 // roughdielectric.cpp:270-350
+    if (wi.z == 0) return f3(0, 0, 0);
+    const float m_eta = b.eta[0], m_invEta = 1 / m_eta;
+    const bool reflect = wi.z * wo.z > 0;
+    F3 H;
+    if (reflect) H = normalize(wo + wi);
+    else { const float eta = wi.z > 0 ? m_eta : m_invEta; H = normalize(wi + wo * eta); }
+    H = H * mts_signum(H.z);
+    const Microfacet distr(b.distribution, b.alpha);
+    const float D = distr.eval(H);
+    if (D == 0) return f3(0, 0, 0);
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, m_eta);
+    const float G = distr.smithG1(wi, H) * distr.smithG1(wo, H);
+    if (reflect) {
+        const float value = F * D * G / (4.0f * std::fabs(wi.z));
+        return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * value;
+    }
+    const float eta = wi.z > 0.0f ? m_eta : m_invEta;
+    const float sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+    const float value = ((1 - F) * D * G * eta * eta * dot(wi, H) * dot(wo, H)) / (wi.z * sqrtDenom * sqrtDenom);
+    const float factor = wi.z > 0 ? m_invEta : m_eta;                                                    // ERadiance
+    return f3(b.specular_transmittance[0], b.specular_transmittance[1], b.specular_transmittance[2]) * std::fabs(value * factor * factor);
+}
+static inline float roughdielectric_pdf(const ppg_bsdf &b, F3 wi, F3 wo) {                               // roughdielectric.cpp:352-422
+    const float m_eta = b.eta[0], m_invEta = 1 / m_eta;
+    const bool reflect = wi.z * wo.z > 0;
+    F3 H; float dwh_dwo;
+    if (reflect) { H = normalize(wo + wi); dwh_dwo = 1.0f / (4.0f * dot(wo, H)); }
+    else {
+        const float eta = wi.z > 0 ? m_eta : m_invEta;
+        H = normalize(wi + wo * eta);
+        const float sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+        dwh_dwo = (eta * eta * dot(wo, H)) / (sqrtDenom * sqrtDenom);
+    }
+    H = H * mts_signum(H.z);
+    const Microfacet distr(b.distribution, b.alpha);
+    float prob = distr.pdfVisible(wi * mts_signum(wi.z), H);
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, m_eta);
+    prob *= reflect ? F : (1 - F);
+    return std::fabs(prob * dwh_dwo);
+}
+static inline F3 roughdielectric_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, float su, F3 &wo, float &etaOut, float &pdf) {   // roughdielectric.cpp:502-600
+    pdf = 0;
+    const float m_eta = b.eta[0], m_invEta = 1 / m_eta;
+    const Microfacet distr(b.distribution, b.alpha);
+    const F3 wiUp = wi * mts_signum(wi.z);
+    const F3 m = distr.sampleVisible(wiUp, sx, sy);
+    const float microfacetPDF = distr.pdfVisible(wiUp, m);
+    if (microfacetPDF == 0) return f3(0, 0, 0);
+    pdf = microfacetPDF;
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, m), cosThetaT, m_eta);
+    F3 weight = f3(1, 1, 1);
+    bool sampleReflection = true;
+    if (su > F) { sampleReflection = false; pdf *= 1 - F; } else pdf *= F;
+    float dwh_dwo;
+    if (sampleReflection) {
+        wo = m * (2 * dot(wi, m)) - wi; etaOut = 1.0f;
+        if (wi.z * wo.z <= 0) return f3(0, 0, 0);
+        weight = weight * f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+        dwh_dwo = 1.0f / (4.0f * dot(wo, m));
+    } else {
+        if (cosThetaT == 0) return f3(0, 0, 0);
+        { const float eta = cosThetaT < 0 ? 1 / m_eta : m_eta; wo = m * (dot(wi, m) * eta + cosThetaT) - wi * eta; }   // refract(wi, m, eta, cosThetaT), util.cpp:767-772
+        etaOut = cosThetaT < 0 ? m_eta : m_invEta;
+        if (wi.z * wo.z >= 0) return f3(0, 0, 0);
+        const float factor = cosThetaT < 0 ? m_invEta : m_eta;
+        weight = weight * (f3(b.specular_transmittance[0], b.specular_transmittance[1], b.specular_transmittance[2]) * (factor * factor));
+        const float sqrtDenom = dot(wi, m) + etaOut * dot(wo, m);
+        dwh_dwo = (etaOut * etaOut * dot(wo, m)) / (sqrtDenom * sqrtDenom);
+    }
+    weight = weight * distr.smithG1(wo, m);
+    pdf *= std::fabs(dwh_dwo);
+    return weight;
+}
+static inline const float *bsdf_table(const ppg_bsdf &b, const float *tables) { return tables ? tables + (size_t)b.table * PPG_BSDF_TABLE_SIZE : nullptr; }
+
 // eval / pdf with the solid-angle measure (delta models return 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
 // twosided per src/bsdfs/twosided.cpp:108-184
-static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo) {
+static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables = nullptr) {
     if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
+    if (b.type == PPG_BSDF_ROUGHDIELECTRIC) return roughdielectric_eval(b, wi, wo);
+    if (b.type == PPG_BSDF_ROUGHPLASTIC) return roughplastic_eval(b, bsdf_table(b, tables), wi, wo);
     if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
     return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * (kInvPi * wo.z);
 }
-static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo) {
+static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables = nullptr) {
     if (!bsdf_has_smooth(b)) return 0.0f;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
+    if (b.type == PPG_BSDF_ROUGHDIELECTRIC) return roughdielectric_pdf(b, wi, wo);
+    if (b.type == PPG_BSDF_ROUGHPLASTIC) return roughplastic_pdf(b, bsdf_table(b, tables), wi, wo);
     if (wi.z <= 0 || wo.z <= 0) return 0.0f;
     return kInvPi * wo.z;   // warp::squareToCosineHemispherePdf
 }
-static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfSample &s, float &pdf) {
+// `rng`: the path's sampler, consumed only by models that draw from it themselves (roughdielectric)
+static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfSample &s, float &pdf, const float *tables = nullptr, Pcg32 *rng = nullptr) {
     bool flip = false;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; flip = true; } }
     s.eta = 1.0f; s.delta = false; pdf = 0;
@@ -581,6 +735,12 @@ static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfS
     }
     if (b.type == PPG_BSDF_ROUGHCONDUCTOR) {
         const F3 w = roughconductor_sample(b, wi, sx, sy, s.wo, pdf);
+        if (flip) s.wo.z = -s.wo.z;
+        return w;
+    }
+    if (b.type == PPG_BSDF_ROUGHDIELECTRIC) return roughdielectric_sample(b, wi, sx, sy, rng ? rng->next1D() : 0.5f, s.wo, s.eta, pdf);
+    if (b.type == PPG_BSDF_ROUGHPLASTIC) {
+        const F3 w = roughplastic_sample(b, bsdf_table(b, tables), wi, sx, sy, s.wo, pdf);
         if (flip) s.wo.z = -s.wo.z;
         return w;
     }
@@ -657,25 +817,25 @@ public:
             float woPdf, bsdfPdf, dTreePdf; F3 bsdfWeight; BsdfSample bs;
             float sx = rng.next1D(), sy = rng.next1D();
             if (!isBuilt || !leaf) {
-                bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf);
+                bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf, sc.tables.data(), &rng);
                 woPdf = bsdfPdf; dTreePdf = 0;
             } else {
                 F3 result;
                 bool zero = false;
                 if (sx < frac) {
                     sx /= frac;
-                    result = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf);
+                    result = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf, sc.tables.data(), &rng);
                     if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0; zero = true; }
                     else result = result * bsdfPdf;
                 } else {
                     float dw[3]; tree.sample(leaf, rng, dw);
                     bs.wo = its.toLocal(f3(dw[0], dw[1], dw[2])); bs.eta = 1.0f; bs.delta = false;
-                    result = bsdf_eval(bsdf, its.wi, bs.wo);
+                    result = bsdf_eval(bsdf, its.wi, bs.wo, sc.tables.data());
                 }
                 if (zero) bsdfWeight = f3(0, 0, 0);
                 else {
                     // pdfMat, GP:1693-1710
-                    bsdfPdf = bsdf_pdf(bsdf, its.wi, bs.wo);
+                    bsdfPdf = bsdf_pdf(bsdf, its.wi, bs.wo, sc.tables.data());
                     if (!std::isfinite(bsdfPdf)) { woPdf = 0; dTreePdf = 0; }
                     else {
                         const F3 wow = its.toWorld(bs.wo);
@@ -694,12 +854,12 @@ public:
                     const F3 dl = its.toLocal(ds.d);
                     const float woDotGeoN2 = dot(its.geoN, ds.d);
                     if (!prm.strict_normals || woDotGeoN2 * dl.z > 0) {
-                        const F3 bsdfVal = bsdf_eval(bsdf, its.wi, dl);
+                        const F3 bsdfVal = bsdf_eval(bsdf, its.wi, dl, sc.tables.data());
                         float nWoPdf = 0, nBsdfPdf = 0, nDTreePdf = 0;
                         {   // pdfMat (emitter->isOnSurface() && measure == ESolidAngle always hold for area lights)
-                            if (!isBuilt || !leaf) { nWoPdf = nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl); }
+                            if (!isBuilt || !leaf) { nWoPdf = nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl, sc.tables.data()); }
                             else {
-                                nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl);
+                                nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl, sc.tables.data());
                                 if (!std::isfinite(nBsdfPdf)) nWoPdf = 0;
                                 else { nDTreePdf = tree.pdf(leaf, &ds.d.x); nWoPdf = frac * nBsdfPdf + (1 - frac) * nDTreePdf; }
                             }

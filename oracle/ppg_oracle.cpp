@@ -108,18 +108,19 @@ int ppgo_get_moment_images(ppgo_handle *h, float *sum_rgbw, float *sumsq_rgbw) {
     return PPG_OK;
 }
 
-int ppgo_bsdf_eval_pdf(const ppg_bsdf *b, size_t n, const float *wi, const float *wo, float *eval_out, float *pdf_out) {
+int ppgo_bsdf_eval_pdf(const ppg_bsdf *b, size_t n, const float *wi, const float *wo, float *eval_out, float *pdf_out, const float *tables) {
     for (size_t i = 0; i < n; ++i) {
         const F3 a = f3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c = f3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
-        const F3 e = bsdf_eval(*b, a, c);
-        eval_out[3 * i] = e.x; eval_out[3 * i + 1] = e.y; eval_out[3 * i + 2] = e.z; pdf_out[i] = bsdf_pdf(*b, a, c);
+        const F3 e = bsdf_eval(*b, a, c, tables);
+        eval_out[3 * i] = e.x; eval_out[3 * i + 1] = e.y; eval_out[3 * i + 2] = e.z; pdf_out[i] = bsdf_pdf(*b, a, c, tables);
     }
     return PPG_OK;
 }
-int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *sample, float *wo_out, float *weight_out, float *pdf_out, uint8_t *delta_out) {
+int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *sample, float *wo_out, float *weight_out, float *pdf_out, uint8_t *delta_out, const float *tables) {
     for (size_t i = 0; i < n; ++i) {
         BsdfSample bs; bs.wo = f3(0, 0, 0); float pdf = 0;
-        const F3 w = bsdf_sample(*b, f3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sample[2 * i], sample[2 * i + 1], bs, pdf);
+        Pcg32 extra; extra.seed(splitmix64(i), i);                      // the model's own draws from the path sampler (roughdielectric)
+        const F3 w = bsdf_sample(*b, f3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sample[2 * i], sample[2 * i + 1], bs, pdf, tables, &extra);
         wo_out[3 * i] = bs.wo.x; wo_out[3 * i + 1] = bs.wo.y; wo_out[3 * i + 2] = bs.wo.z;
         weight_out[3 * i] = w.x; weight_out[3 * i + 1] = w.y; weight_out[3 * i + 2] = w.z; pdf_out[i] = pdf; if (delta_out) delta_out[i] = bs.delta;
     }

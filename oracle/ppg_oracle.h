@@ -28,8 +28,8 @@ int ppgo_get_moment_images(ppgo_handle *h, float *sum_rgbw, float *sumsq_rgbw);
 
 /* ---- BSDF level (no handle): n queries on one material; wi/wo local frames (3n floats), sample = 2n uniforms.
  * eval_out 3n (f * cos), pdf_out n, and for sampling: wo_out 3n, weight_out 3n (f * cos / pdf), pdf_out n, delta_out n (u8) */
-int ppgo_bsdf_eval_pdf(const ppg_bsdf *b, size_t n, const float *wi, const float *wo, float *eval_out, float *pdf_out);
-int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *sample, float *wo_out, float *weight_out, float *pdf_out, uint8_t *delta_out);
+int ppgo_bsdf_eval_pdf(const ppg_bsdf *b, size_t n, const float *wi, const float *wo, float *eval_out, float *pdf_out, const float *tables /* may be NULL */);
+int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *sample, float *wo_out, float *weight_out, float *pdf_out, uint8_t *delta_out, const float *tables);
 
 /* ---- SD-tree level operations (work on the handle's tree) */
 int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb);

@@ -73,12 +73,15 @@ __device__ __forceinline__ void seed_vertex_rng(Pcg32 &r, uint64_t seed, uint64_
 //   geom[6t+0..2] = {p_i.xyz, n_i.x}, geom[6t+3..5] = {n_i.yz, uv_i}   (i = 0,1,2)
 //   meta[t] = {bsdf, emitter (-1 none), flags (bit0 has_normals), shape}
 // BVH node: 2 x float4 = {bmin.xyz, bits(left)}, {bmax.xyz, bits(count)}; count>0 -> leaf [left, left+count)
+#define PPG_BSDF_F4 6      // float4 per material, see load_bsdf
+#define PPG_BSDF_LUT 100   // PPG_BSDF_TABLE_SIZE
 struct SceneView {
     const float4 *accel;
     const float4 *geom;
     const int4 *meta;
     const float4 *bvh;
-    const float4 *bsdf;       // 4 per material, see load_bsdf
+    const float4 *bsdf;       // PPG_BSDF_F4 per material, see load_bsdf
+    const float *bsdfTables;  // roughplastic: PPG_BSDF_LUT floats per table (external rough transmittance), read through L1/L2
     const float4 *radiance;   // per emitter: rgb
     uint32_t nTris, nBvhNodes, nBsdfs, nEmitters;
     // brute-force layout (nTris <= PPG_BRUTE_FORCE_TRIS): coplanar triangle groups ordered by projection axis k.
@@ -110,7 +113,7 @@ template <bool SMEM> struct SceneAccess {
     uint32_t oGeom, oMeta, oBvh, oBsdf, oRadiance, oGroups;      // float4 offsets of the staged sections (accel at 0)
     __device__ __forceinline__ SceneAccess(const SceneView &v) : g(v) {
         oGeom = 3 * v.nTris; oMeta = oGeom + 6 * v.nTris; oBvh = oMeta + v.nTris; oBsdf = oBvh + 2 * v.nBvhNodes;
-        oRadiance = oBsdf + 4 * v.nBsdfs; oGroups = oRadiance + v.nEmitters;
+        oRadiance = oBsdf + PPG_BSDF_F4 * v.nBsdfs; oGroups = oRadiance + v.nEmitters;
     }
     __device__ __forceinline__ float4 accel(uint32_t i) const { return SMEM ? ppg_scene_smem[i] : __ldg(&g.accel[i]); }
     __device__ __forceinline__ float4 geom(uint32_t i) const { return SMEM ? ppg_scene_smem[oGeom + i] : __ldg(&g.geom[i]); }
@@ -127,7 +130,7 @@ template <bool SMEM> struct SceneAccess {
         if (!SMEM) return;
         auto copy = [&](uint32_t off, const float4 *src, uint32_t n) { for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) ppg_scene_smem[off + i] = src[i]; };
         copy(0, g.accel, 3 * g.nTris); copy(oGeom, g.geom, 6 * g.nTris); copy(oMeta, reinterpret_cast<const float4 *>(g.meta), g.nTris);
-        copy(oBvh, g.bvh, 2 * g.nBvhNodes); copy(oBsdf, g.bsdf, 4 * g.nBsdfs); copy(oRadiance, g.radiance, g.nEmitters); copy(oGroups, g.groups, 2 * g.nGroups);
+        copy(oBvh, g.bvh, 2 * g.nBvhNodes); copy(oBsdf, g.bsdf, PPG_BSDF_F4 * g.nBsdfs); copy(oRadiance, g.radiance, g.nEmitters); copy(oGroups, g.groups, 2 * g.nGroups);
         __syncthreads();
     }
 };
@@ -320,24 +323,32 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 #define PPG_BSDF_T_DIELECTRIC 2u
 #define PPG_BSDF_T_CONDUCTOR 3u
 #define PPG_BSDF_T_ROUGHCONDUCTOR 4u
-// 4 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)}
-struct Bsdf { float3 refl, trans, etaRgb, k; float eta, invEta, alpha; uint32_t type, flags; int distr; };
+#define PPG_BSDF_T_ROUGHPLASTIC 5u
+#define PPG_BSDF_T_ROUGHDIELECTRIC 6u
+#define PPG_BSDF_NONLINEAR 2u
+// 6 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)},
+// {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), -, -}
+struct Bsdf { float3 refl, trans, etaRgb, k, specRefl; float eta, invEta, alpha, fdrInt, ssw; uint32_t type, flags; int distr; const float *lut; };
 // DELTA == false: the scene holds diffuse BSDFs only (host-checked), the delta models compile away
 template <bool DELTA, class Acc>
 __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
-    const float4 a = A_.bsdf(4 * idx);
+    const float4 a = A_.bsdf(PPG_BSDF_F4 * idx);
     Bsdf b; b.refl = f3(a.x, a.y, a.z);
     const uint32_t tf = __float_as_uint(a.w); b.type = DELTA ? (tf & 0xffu) : PPG_BSDF_T_DIFFUSE; b.flags = tf >> 8;
-    b.trans = b.etaRgb = b.k = f3(0, 0, 0); b.eta = b.invEta = 1.f; b.alpha = 0.1f; b.distr = 1;
+    b.trans = b.etaRgb = b.k = b.specRefl = f3(0, 0, 0); b.eta = b.invEta = 1.f; b.alpha = 0.1f; b.distr = 1; b.fdrInt = b.ssw = 0.f; b.lut = nullptr;
     if (DELTA && b.type != PPG_BSDF_T_DIFFUSE) {
-        const float4 t = A_.bsdf(4 * idx + 1), e = A_.bsdf(4 * idx + 2), k = A_.bsdf(4 * idx + 3);
+        const float4 t = A_.bsdf(PPG_BSDF_F4 * idx + 1), e = A_.bsdf(PPG_BSDF_F4 * idx + 2), k = A_.bsdf(PPG_BSDF_F4 * idx + 3);
         b.trans = f3(t.x, t.y, t.z); b.eta = t.w; b.etaRgb = f3(e.x, e.y, e.z); b.invEta = e.w; b.k = f3(k.x, k.y, k.z);
         b.alpha = fabsf(k.w); b.distr = k.w < 0.f ? 0 : 1;
+        if (b.type == PPG_BSDF_T_ROUGHPLASTIC) {
+            const float4 s = A_.bsdf(PPG_BSDF_F4 * idx + 4), w = A_.bsdf(PPG_BSDF_F4 * idx + 5);
+            b.specRefl = f3(s.x, s.y, s.z); b.fdrInt = s.w; b.ssw = w.x; b.lut = A_.g.bsdfTables + (size_t) __float_as_uint(w.y) * PPG_BSDF_LUT;
+        }
     }
     return b;
 }
-__device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE || b.type == PPG_BSDF_T_ROUGHCONDUCTOR; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
-__device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC; }
+__device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE || b.type == PPG_BSDF_T_ROUGHCONDUCTOR || b.type == PPG_BSDF_T_ROUGHPLASTIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
+__device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
 __device__ __forceinline__ float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
@@ -497,12 +508,151 @@ __device__ __forceinline__ float3 roughconductor_sample(const Bsdf &b, float3 wi
     return F * weight;
 }
 
+// ---- roughplastic (src/bsdfs/roughplastic.cpp).  RoughTransmittance::eval with alpha and eta fixed (src/bsdfs/rtrans.h:183-193, 233):
+// evalCubicInterp1D (src/libcore/spline.cpp:23-60) of the material's table over cos(theta)^(1/4), clamped to [0,1].
+__device__ __forceinline__ float rough_transmittance(const float *__restrict__ values, float cosTheta) {
+    if (!(cosTheta >= 0.f)) return 0.0f;
+    const float x = powf(fabsf(cosTheta), 0.25f);
+    const int size = PPG_BSDF_LUT;
+    float result = 0.0f;
+    if (x >= 0.0f && x <= 1.0f) {
+        float t = ((x - 0.0f) * (float) (size - 1)) / (1.0f - 0.0f);
+        const int k = max(0, min((int) t, size - 2));
+        const float f0 = __ldg(&values[k]), f1 = __ldg(&values[k + 1]);
+        const float d0 = k > 0 ? 0.5f * (f1 - __ldg(&values[k - 1])) : f1 - f0;
+        const float d1 = k + 2 < size ? 0.5f * (__ldg(&values[k + 2]) - f0) : f1 - f0;
+        t = t - (float) k;
+        const float t2 = t * t, t3 = t2 * t;
+        result = (2.f * t3 - 3.f * t2 + 1.f) * f0 + (-2.f * t3 + 3.f * t2) * f1 + (t3 - 2.f * t2 + t) * d0 + (t3 - t2) * d1;
+    }
+    return fminf(1.0f, fmaxf(0.0f, result));
+}
+__device__ __forceinline__ float roughplastic_prob_specular(const Bsdf &b, float cosThetaI) {   // roughplastic.cpp:403-409 = :446-452
+    const float probSpecular = 1.f - rough_transmittance(b.lut, cosThetaI);
+    return (probSpecular * b.ssw) / (probSpecular * b.ssw + (1.f - probSpecular) * (1.f - b.ssw));
+}
+__device__ __forceinline__ float3 roughplastic_eval(const Bsdf &b, float3 wi, float3 wo) {     // roughplastic.cpp:326-380
+    if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
+    const float3 H = normalize(wo + wi);
+    const float D = mf_eval(b.distr, b.alpha, H);
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, b.eta);
+    const float G = mf_smithG1(b.distr, b.alpha, wi, H) * mf_smithG1(b.distr, b.alpha, wo, H);
+    const float value = F * D * G / (4.0f * wi.z);
+    const float3 result = b.specRefl * value;
+    float3 diff = b.refl;
+    const float T12 = rough_transmittance(b.lut, wi.z), T21 = rough_transmittance(b.lut, wo.z), Fdr = b.fdrInt;
+    if (b.flags & PPG_BSDF_NONLINEAR) diff = f3(diff.x / (1.0f - diff.x * Fdr), diff.y / (1.0f - diff.y * Fdr), diff.z / (1.0f - diff.z * Fdr));
+    else diff = diff * (1.0f / (1.f - Fdr));                   // Spectrum /= Float multiplies by the reciprocal (core/spectrum.h:447-456)
+    const float invEta2 = 1.f / (b.eta * b.eta);
+    return result + diff * (PPG_INV_PI * wo.z * T12 * T21 * invEta2);
+}
+__device__ __forceinline__ float roughplastic_pdf(const Bsdf &b, float3 wi, float3 wo) {       // roughplastic.cpp:382-430
+    if (wi.z <= 0.f || wo.z <= 0.f) return 0.0f;
+    const float3 H = normalize(wo + wi);
+    const float probSpecular = roughplastic_prob_specular(b, wi.z), probDiffuse = 1.f - probSpecular;
+    const float dwh_dwo = 1.0f / (4.0f * dot(wo, H));
+    const float prob = mf_pdfVisible(b.distr, b.alpha, wi, H);
+    float result = prob * dwh_dwo * probSpecular;
+    result += probDiffuse * (PPG_INV_PI * wo.z);
+    return result;
+}
+__device__ __forceinline__ float3 roughplastic_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &pdf) {   // roughplastic.cpp:432-497
+    pdf = 0.f;
+    if (wi.z <= 0.f) return f3(0, 0, 0);
+    bool choseSpecular = true;
+    const float probSpecular = roughplastic_prob_specular(b, wi.z);
+    if (sy < probSpecular) sy /= probSpecular;
+    else { sy = (sy - probSpecular) / (1.f - probSpecular); choseSpecular = false; }
+    if (choseSpecular) {
+        const float3 m = mf_sampleVisible(b.distr, b.alpha, wi, sx, sy);
+        wo = m * (2.f * dot(wi, m)) - wi;
+        if (wo.z <= 0.f) return f3(0, 0, 0);
+    } else wo = square_to_cosine_hemisphere(sx, sy);
+    pdf = roughplastic_pdf(b, wi, wo);
+    if (pdf == 0.f) return f3(0, 0, 0);
+    return roughplastic_eval(b, wi, wo) * (1.0f / pdf);       // Spectrum / Float, core/spectrum.h:415-425
+}
+
+// ---- roughdielectric (src/bsdfs/roughdielectric.cpp), visible-normal sampling.  sample() takes ONE extra number `su` of the path's
+// sampler to choose reflection / refraction (EUsesSampler, :536-543).
+__device__ __forceinline__ float mts_signum(float v) { return copysignf(1.0f, v); }                     // core/math.h:269-278
+__device__ __forceinline__ float3 roughdielectric_eval(const Bsdf &b, float3 wi, float3 wo) {            // roughdielectric.cpp:270-350
+    if (wi.z == 0.f) return f3(0, 0, 0);
+    const bool reflect = wi.z * wo.z > 0.f;
+    float3 H;
+    if (reflect) H = normalize(wo + wi);
+    else { const float eta = wi.z > 0.f ? b.eta : b.invEta; H = normalize(wi + wo * eta); }
+    H = H * mts_signum(H.z);
+    const float D = mf_eval(b.distr, b.alpha, H);
+    if (D == 0.f) return f3(0, 0, 0);
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, b.eta);
+    const float G = mf_smithG1(b.distr, b.alpha, wi, H) * mf_smithG1(b.distr, b.alpha, wo, H);
+    if (reflect) {
+        const float value = F * D * G / (4.0f * fabsf(wi.z));
+        return b.refl * value;
+    }
+    const float eta = wi.z > 0.0f ? b.eta : b.invEta;
+    const float sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+    const float value = ((1.f - F) * D * G * eta * eta * dot(wi, H) * dot(wo, H)) / (wi.z * sqrtDenom * sqrtDenom);
+    const float factor = wi.z > 0.f ? b.invEta : b.eta;                                                  // ERadiance
+    return b.trans * fabsf(value * factor * factor);
+}
+__device__ __forceinline__ float roughdielectric_pdf(const Bsdf &b, float3 wi, float3 wo) {              // roughdielectric.cpp:352-422
+    const bool reflect = wi.z * wo.z > 0.f;
+    float3 H; float dwh_dwo;
+    if (reflect) { H = normalize(wo + wi); dwh_dwo = 1.0f / (4.0f * dot(wo, H)); }
+    else {
+        const float eta = wi.z > 0.f ? b.eta : b.invEta;
+        H = normalize(wi + wo * eta);
+        const float sqrtDenom = dot(wi, H) + eta * dot(wo, H);
+        dwh_dwo = (eta * eta * dot(wo, H)) / (sqrtDenom * sqrtDenom);
+    }
+    H = H * mts_signum(H.z);
+    float prob = mf_pdfVisible(b.distr, b.alpha, wi * mts_signum(wi.z), H);
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, H), cosThetaT, b.eta);
+    prob *= reflect ? F : (1.f - F);
+    return fabsf(prob * dwh_dwo);
+}
+__device__ __forceinline__ float3 roughdielectric_sample(const Bsdf &b, float3 wi, float sx, float sy, float su, float3 &wo, float &etaOut, float &pdf) {   // :502-600
+    pdf = 0.f;
+    const float3 wiUp = wi * mts_signum(wi.z);
+    const float3 m = mf_sampleVisible(b.distr, b.alpha, wiUp, sx, sy);
+    const float microfacetPDF = mf_pdfVisible(b.distr, b.alpha, wiUp, m);
+    if (microfacetPDF == 0.f) return f3(0, 0, 0);
+    pdf = microfacetPDF;
+    float cosThetaT; const float F = fresnel_dielectric_ext(dot(wi, m), cosThetaT, b.eta);
+    float3 weight = f3(1, 1, 1);
+    bool sampleReflection = true;
+    if (su > F) { sampleReflection = false; pdf *= 1.f - F; } else pdf *= F;
+    float dwh_dwo;
+    if (sampleReflection) {
+        wo = m * (2.f * dot(wi, m)) - wi; etaOut = 1.0f;
+        if (wi.z * wo.z <= 0.f) return f3(0, 0, 0);
+        weight = weight * b.refl;
+        dwh_dwo = 1.0f / (4.0f * dot(wo, m));
+    } else {
+        if (cosThetaT == 0.f) return f3(0, 0, 0);
+        { const float eta = cosThetaT < 0.f ? 1.f / b.eta : b.eta; wo = m * (dot(wi, m) * eta + cosThetaT) - wi * eta; }   // refract(), util.cpp:767-772
+        etaOut = cosThetaT < 0.f ? b.eta : b.invEta;
+        if (wi.z * wo.z >= 0.f) return f3(0, 0, 0);
+        const float factor = cosThetaT < 0.f ? b.invEta : b.eta;
+        weight = weight * (b.trans * (factor * factor));
+        const float sqrtDenom = dot(wi, m) + etaOut * dot(wo, m);
+        dwh_dwo = (etaOut * etaOut * dot(wo, m)) / (sqrtDenom * sqrtDenom);
+    }
+    weight = weight * mf_smithG1(b.distr, b.alpha, wo, m);
+    pdf *= fabsf(dwh_dwo);
+    return weight;
+}
+
 // eval / pdf in the solid-angle measure (delta models: 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
 // twosided per src/bsdfs/twosided.cpp:108-184
 __device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo) {
     if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
+    if (b.type == PPG_BSDF_T_ROUGHDIELECTRIC) return roughdielectric_eval(b, wi, wo);
+    if (b.type == PPG_BSDF_T_ROUGHPLASTIC) return roughplastic_eval(b, wi, wo);
     if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
     return b.refl * (PPG_INV_PI * wo.z);
 }
@@ -510,10 +660,13 @@ __device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
     if (!bsdf_has_smooth(b)) return 0.0f;
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
+    if (b.type == PPG_BSDF_T_ROUGHDIELECTRIC) return roughdielectric_pdf(b, wi, wo);
+    if (b.type == PPG_BSDF_T_ROUGHPLASTIC) return roughplastic_pdf(b, wi, wo);
     if (wi.z <= 0.f || wo.z <= 0.f) return 0.0f;
     return PPG_INV_PI * wo.z;
 }
-__device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf) {
+// `rng`: the path's sampler, consumed only by models that draw from it themselves (roughdielectric)
+__device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf, Pcg32 &rng) {
     bool flip = false;
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; flip = true; }
     eta = 1.0f; delta = false; pdf = 0.f;
@@ -535,6 +688,12 @@ __device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx
     }
     if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) {
         const float3 w = roughconductor_sample(b, wi, sx, sy, wo, pdf);
+        if (flip) wo.z = -wo.z;
+        return w;
+    }
+    if (b.type == PPG_BSDF_T_ROUGHDIELECTRIC) { const float su = rng.next1D(); return roughdielectric_sample(b, wi, sx, sy, su, wo, eta, pdf); }
+    if (b.type == PPG_BSDF_T_ROUGHPLASTIC) {
+        const float3 w = roughplastic_sample(b, wi, sx, sy, wo, pdf);
         if (flip) wo.z = -wo.z;
         return w;
     }

@@ -256,7 +256,7 @@ struct ppg_integrator {
 
     // scene
     bool haveScene = false;
-    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom; DevBuf<float> dEmitterCdf, dEmitterTriCdf; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
+    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom; DevBuf<float> dEmitterCdf, dEmitterTriCdf, dBsdfTables; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
@@ -398,10 +398,12 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     }
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
         const int t = s->bsdfs[i].type;
-        if (t != PPG_BSDF_DIFFUSE && t != PPG_BSDF_NULL_BLACK && t != PPG_BSDF_DIELECTRIC && t != PPG_BSDF_CONDUCTOR && t != PPG_BSDF_ROUGHCONDUCTOR)
+        if (t != PPG_BSDF_DIFFUSE && t != PPG_BSDF_NULL_BLACK && t != PPG_BSDF_DIELECTRIC && t != PPG_BSDF_CONDUCTOR && t != PPG_BSDF_ROUGHCONDUCTOR && t != PPG_BSDF_ROUGHPLASTIC && t != PPG_BSDF_ROUGHDIELECTRIC)
             return fail(PPG_ERR_UNSUPPORTED, "BSDF type outside the implemented hot-path scope");
-        if (t == PPG_BSDF_DIELECTRIC && !(s->bsdfs[i].eta[0] > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "dielectric needs eta > 0");
-        if (t == PPG_BSDF_DIELECTRIC && (s->bsdfs[i].flags & PPG_BSDF_FLAG_TWOSIDED)) return fail(PPG_ERR_INVALID_ARGUMENT, "twosided cannot wrap a transmissive BSDF (twosided.cpp)");
+        if (t == PPG_BSDF_ROUGHPLASTIC && (!s->bsdf_tables || s->bsdfs[i].table < 0 || (uint32_t) s->bsdfs[i].table >= s->n_bsdf_tables))
+            return fail(PPG_ERR_INVALID_ARGUMENT, "roughplastic needs its rough-transmittance table (ppg_scene_desc.bsdf_tables)");
+        if ((t == PPG_BSDF_DIELECTRIC || t == PPG_BSDF_ROUGHDIELECTRIC) && !(s->bsdfs[i].eta[0] > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "dielectric needs eta > 0");
+        if ((t == PPG_BSDF_DIELECTRIC || t == PPG_BSDF_ROUGHDIELECTRIC) && (s->bsdfs[i].flags & PPG_BSDF_FLAG_TWOSIDED)) return fail(PPG_ERR_INVALID_ARGUMENT, "twosided cannot wrap a transmissive BSDF (twosided.cpp)");
     }
     auto P = [&](uint32_t i) { return h3(s->positions[3 * i], s->positions[3 * i + 1], s->positions[3 * i + 2]); };
     std::vector<H3> tmin(nt), tmax(nt);
@@ -478,9 +480,9 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     }
     h->hasDeltaBsdf = false;
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) h->hasDeltaBsdf = true;   // any non-diffuse model
-    std::vector<float> bsdf(16 * (size_t) s->n_bsdfs, 0.f);
+    std::vector<float> bsdf(4 * PPG_BSDF_F4 * (size_t) s->n_bsdfs, 0.f);
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
-        float *b = &bsdf[16 * (size_t) i]; const ppg_bsdf &m = s->bsdfs[i];
+        float *b = &bsdf[4 * PPG_BSDF_F4 * (size_t) i]; const ppg_bsdf &m = s->bsdfs[i];
         b[0] = m.reflectance[0]; b[1] = m.reflectance[1]; b[2] = m.reflectance[2];
         uint32_t type = (uint32_t) m.type;
         if (m.type == PPG_BSDF_NULL_BLACK) { b[0] = b[1] = b[2] = 0.f; type = PPG_BSDF_DIFFUSE; }
@@ -489,12 +491,17 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         b[8] = m.eta[0]; b[9] = m.eta[1]; b[10] = m.eta[2]; b[11] = m.eta[0] != 0.f ? 1.0f / m.eta[0] : 0.f;
         b[12] = m.k[0]; b[13] = m.k[1]; b[14] = m.k[2];
         b[15] = std::max(m.alpha, 1e-4f) * (m.distribution == PPG_MICROFACET_BECKMANN ? -1.0f : 1.0f);   // microfacet.h:63 clamp; sign encodes the distribution
+        b[16] = m.specular_reflectance[0]; b[17] = m.specular_reflectance[1]; b[18] = m.specular_reflectance[2]; b[19] = m.fdr_int;
+        b[20] = m.specular_sampling_weight; const uint32_t tab = (uint32_t) std::max(m.table, 0); memcpy(&b[21], &tab, 4);
     }
     std::vector<float> rad(4 * (size_t) std::max<uint32_t>(s->n_emitters, 1), 0.f);
     for (uint32_t i = 0; i < s->n_emitters; ++i) { rad[4 * i] = s->area_radiance[3 * i]; rad[4 * i + 1] = s->area_radiance[3 * i + 1]; rad[4 * i + 2] = s->area_radiance[3 * i + 2]; }
     const size_t nBvh = bvh.nodes.size() / 8;
     CK(h->dAccel.alloc(3 * (size_t) nt)); CK(h->dGeom.alloc(6 * (size_t) nt)); CK(h->dMeta.alloc(nt)); CK(h->dBvh.alloc(2 * nBvh));
-    CK(h->dBsdf.alloc(4 * (size_t) s->n_bsdfs)); CK(h->dRadiance.alloc(std::max<uint32_t>(s->n_emitters, 1)));
+    CK(h->dBsdf.alloc(PPG_BSDF_F4 * (size_t) s->n_bsdfs));
+    CK(h->dBsdfTables.alloc(std::max<size_t>((size_t) s->n_bsdf_tables * PPG_BSDF_TABLE_SIZE, 1)));
+    if (s->n_bsdf_tables) { CK(cudaMemcpy(h->dBsdfTables.p, s->bsdf_tables, (size_t) s->n_bsdf_tables * PPG_BSDF_TABLE_SIZE * 4, cudaMemcpyHostToDevice)); }
+    CK(h->dRadiance.alloc(std::max<uint32_t>(s->n_emitters, 1)));
     CK(cudaMemcpy(h->dAccel.p, accel.data(), accel.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dGeom.p, geom.data(), geom.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dMeta.p, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
@@ -502,7 +509,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     CK(cudaMemcpy(h->dBsdf.p, bsdf.data(), bsdf.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dRadiance.p, rad.data(), rad.size() * 4, cudaMemcpyHostToDevice));
     SceneView &v = h->sceneView;
-    v.accel = h->dAccel.p; v.geom = h->dGeom.p; v.meta = h->dMeta.p; v.bvh = h->dBvh.p; v.bsdf = h->dBsdf.p; v.radiance = h->dRadiance.p;
+    v.accel = h->dAccel.p; v.geom = h->dGeom.p; v.meta = h->dMeta.p; v.bvh = h->dBvh.p; v.bsdf = h->dBsdf.p; v.bsdfTables = h->dBsdfTables.p; v.radiance = h->dRadiance.p;
     CK(h->dGroups.alloc(groups.size() / 4));
     CK(cudaMemcpy(h->dGroups.p, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice));
     v.groups = h->dGroups.p; v.nGroups = bruteForce ? (uint32_t) (groups.size() / 8) : 0u;
@@ -556,7 +563,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         v.emitterNormalization = norm; h->nRealEmitters = s->n_emitters;
     }
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
-    const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + 4 * s->n_bsdfs + v.nEmitters + 2 * std::max<uint32_t>(v.nGroups, 1));
+    const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + PPG_BSDF_F4 * s->n_bsdfs + v.nEmitters + 2 * std::max<uint32_t>(v.nGroups, 1));
     h->sceneSmemBytes = sceneBytes <= 48 * 1024 ? (uint32_t) sceneBytes : 0u;   // small scenes (CBOX: ~9 KB) live in shared memory
     // camera (src/sensors/perspective.cpp:120-298; lookAt columns: left, up, dir, origin -- transform.cpp:191-214)
     const float *m = s->camera.to_world;
@@ -788,7 +795,9 @@ static int ensure_wavefront(ppg_integrator *h) {
     CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BLOCK, h->sceneSmemBytes));
+    if (!h->hasDeltaBsdf) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BLOCK, h->sceneSmemBytes));
+    else if (h->sceneSmemBytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, true, true>, PPG_BLOCK, h->sceneSmemBytes));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, false, true>, PPG_BLOCK, 0));
     h->gridBounce = h->numSMs * std::max(occ, 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
     h->gridCommit = h->numSMs * std::max(occ, 1);

@@ -19,6 +19,9 @@ namespace ppg {
 #ifndef PPG_MIN_BLOCKS
 #define PPG_MIN_BLOCKS 4               // resident blocks per SM the bounce kernel is compiled for (register cap)
 #endif
+#ifndef PPG_MIN_BLOCKS_GLOSSY
+#define PPG_MIN_BLOCKS_GLOSSY 3        // same for scenes with non-diffuse BSDFs (DELTA variants: microfacet code needs more registers)
+#endif
 #define PPG_MAX_VERTICES 32         // MAX_NUM_VERTICES, GP:1771
 #define PPG_INVALID 0xFFFFFFFFu
 
@@ -84,7 +87,7 @@ __device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) 
 // RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
 //         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
 template <bool FIRST, int RECORD, bool NEE, bool SMEM, bool DELTA>
-__global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
+__global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
     const SceneAccess<SMEM> sc(P.scene);
     sc.stage();
     const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                 float woPdf, bsdfPdf, dTreePdf, bsEta = 1.f; float3 wo, bsdfWeight; bool isDelta = false;
                 float sx = rng.next1D(); const float sy = rng.next1D();
                 if (!P.isBuilt || !smooth) {                                         // not built / no dTree / all-delta BSDF (GP:1654)
-                    bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf);
+                    bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng);
                     woPdf = bsdfPdf; dTreePdf = 0.f;
                 } else {
                     const SampNode *tree = P.tree.samp + __float_as_uint(la.x);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, PPG_MIN_BLOCKS) bounce_kernel(const
                     float3 result; bool zero = false;
                     if (sx < frac) {
                         sx /= frac;
-                        result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf);
+                        result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng);
                         if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0.f; zero = true; }
                         else result = result * bsdfPdf;
                     } else {

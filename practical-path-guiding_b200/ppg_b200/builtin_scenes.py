@@ -73,12 +73,28 @@ def cbox_glass_mirror(cbox: SceneDesc) -> SceneDesc:
     import copy
     sc = copy.copy(cbox)
     nb = len(sc.bsdfs)
-    sc.bsdfs = np.concatenate([sc.bsdfs, np.stack([_make_bsdf(BSDF_DIELECTRIC, 0, (1, 1, 1), (1, 1, 1), (1.5046 / 1.000277,) * 3),
+    sc.bsdfs = np.concatenate([_pad_bsdfs(sc.bsdfs), np.stack([_make_bsdf(BSDF_DIELECTRIC, 0, (1, 1, 1), (1, 1, 1), (1.5046 / 1.000277,) * 3),
                                                    _make_bsdf(BSDF_CONDUCTOR, 0, (0.95, 0.95, 0.95), (0, 0, 0), (0, 0, 0), (1, 1, 1))])]).astype(np.float32)
     sc.bsdf_names = list(sc.bsdf_names) + ["glass", "mirror"]
     shapes = sc.shapes.copy()
     shapes[6, 2] = nb          # cbox_smallbox
     shapes[7, 2] = nb + 1      # cbox_largebox
+    sc.shapes = shapes
+    return sc
+
+
+def cbox_rough_glass(cbox: SceneDesc) -> SceneDesc:
+    """CBOX whose small box is frosted glass (roughdielectric GGX alpha 0.15, eta 1.5) and whose large box is a lightly rough
+    glass (Beckmann alpha 0.05, tinted transmittance): glossy transmission is ESmooth, i.e. guided, recorded and light-sampled."""
+    import copy
+    from .scene import BSDF_ROUGHDIELECTRIC
+    sc = copy.copy(cbox)
+    nb = len(sc.bsdfs)
+    sc.bsdfs = np.concatenate([_pad_bsdfs(sc.bsdfs), np.stack([
+        _make_bsdf(BSDF_ROUGHDIELECTRIC, 0, (1, 1, 1), (1, 1, 1), (1.5,) * 3, (0, 0, 0), 0.15, 1),
+        _make_bsdf(BSDF_ROUGHDIELECTRIC, 0, (1, 1, 1), (0.8, 0.95, 0.9), (1.33,) * 3, (0, 0, 0), 0.05, 0)])]).astype(np.float32)
+    sc.bsdf_names = list(sc.bsdf_names) + ["frosted_glass_ggx", "rough_water_beckmann"]
+    shapes = sc.shapes.copy(); shapes[6, 2] = nb; shapes[7, 2] = nb + 1
     sc.shapes = shapes
     return sc
 
@@ -90,10 +106,34 @@ def cbox_rough_metal(cbox: SceneDesc) -> SceneDesc:
     from .scene import BSDF_ROUGHCONDUCTOR
     sc = copy.copy(cbox)
     nb = len(sc.bsdfs)
-    sc.bsdfs = np.concatenate([sc.bsdfs, np.stack([
+    sc.bsdfs = np.concatenate([_pad_bsdfs(sc.bsdfs), np.stack([
         _make_bsdf(BSDF_ROUGHCONDUCTOR, 0, (0.578596,) * 3, (0, 0, 0), (1.65746, 0.880369, 0.521229), (9.22387, 6.26952, 4.837), 0.1, 1),
         _make_bsdf(BSDF_ROUGHCONDUCTOR, 0, (1, 1, 1), (0, 0, 0), (0.2, 0.92, 1.1), (3.9, 2.45, 2.14), 0.3, 0)])]).astype(np.float32)
     sc.bsdf_names = list(sc.bsdf_names) + ["rough_aluminium_ggx", "rough_gold_beckmann"]
+    shapes = sc.shapes.copy(); shapes[6, 2] = nb; shapes[7, 2] = nb + 1
+    sc.shapes = shapes
+    return sc
+
+
+def _pad_bsdfs(b):
+    b = np.asarray(b, np.float32)
+    return b if b.shape[1] >= 24 else np.concatenate([b, np.zeros((len(b), 24 - b.shape[1]), np.float32)], axis=1)
+
+
+def cbox_rough_plastic(cbox: SceneDesc) -> SceneDesc:
+    """CBOX whose boxes are rough plastics (needs the reference's data/microfacet tables at build time):
+    the small box like spaceship.xml's "PinkLeather" (Beckmann 0.4, nonlinear), the large box GGX alpha 0.2, linear."""
+    import copy
+    from .scene import make_roughplastic
+    sc = copy.copy(cbox)
+    tables = []
+    extra = [make_roughplastic(0, (0.256, 0.013, 0.08), (1, 1, 1), 1.5 / 1.000277, 0.4, 0, True, tables),
+             make_roughplastic(0, (0.1, 0.3, 0.6), (1, 1, 1), 1.5 / 1.000277, 0.2, 1, False, tables)]
+    base = _pad_bsdfs(sc.bsdfs)
+    nb = len(base)
+    sc.bsdfs = np.concatenate([base, np.stack(extra)]).astype(np.float32)
+    sc.bsdf_tables = np.asarray(tables, np.float32)
+    sc.bsdf_names = list(sc.bsdf_names) + ["pink_leather_beckmann", "blue_plastic_ggx"]
     shapes = sc.shapes.copy(); shapes[6, 2] = nb; shapes[7, 2] = nb + 1
     sc.shapes = shapes
     return sc

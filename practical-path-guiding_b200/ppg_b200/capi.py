@@ -32,7 +32,8 @@ class PpgParams(C.Structure):
 
 class PpgBsdf(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("reflectance", C.c_float * 3), ("specular_transmittance", C.c_float * 3),
-                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("alpha", C.c_float), ("distribution", C.c_int32)]
+                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("alpha", C.c_float), ("distribution", C.c_int32),
+                ("specular_reflectance", C.c_float * 3), ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("table", C.c_int32), ("reserved", C.c_float * 2)]
 
 
 class PpgShape(C.Structure):
@@ -52,6 +53,7 @@ class PpgSceneDesc(C.Structure):
         ("positions", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("uvs", C.POINTER(C.c_float)),
         ("indices", C.POINTER(C.c_uint32)), ("triangle_shape", C.POINTER(C.c_uint32)),
         ("shapes", C.POINTER(PpgShape)), ("bsdfs", C.POINTER(PpgBsdf)), ("area_radiance", C.POINTER(C.c_float)),
+        ("bsdf_tables", C.POINTER(C.c_float)), ("n_bsdf_tables", C.c_uint32),
         ("camera", PpgCamera), ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3),
     ]
 
@@ -109,7 +111,12 @@ class SceneArrays:
         self.indices = np.ascontiguousarray(scene.indices, np.uint32)
         self.triangle_shape = np.ascontiguousarray(scene.triangle_shape, np.uint32)
         self.shapes = np.ascontiguousarray(scene.shapes, np.int32)          # (S,8) == ppg_shape
-        self.bsdfs = np.ascontiguousarray(scene.bsdfs, np.float32)          # (B,16) == ppg_bsdf
+        b = np.asarray(scene.bsdfs, np.float32)
+        if b.shape[1] < 24:                                                   # fixtures written before the struct grew to 96 bytes
+            b = np.concatenate([b, np.zeros((len(b), 24 - b.shape[1]), np.float32)], axis=1)
+        self.bsdfs = np.ascontiguousarray(b, np.float32)                    # (B,24) == ppg_bsdf
+        tables = getattr(scene, "bsdf_tables", None)
+        self.tables = np.ascontiguousarray(tables if tables is not None and len(tables) else np.zeros((0, 100)), np.float32)
         self.radiance = np.ascontiguousarray(scene.area_radiance, np.float32)
         d = PpgSceneDesc()
         d.n_vertices = len(self.positions); d.n_triangles = len(self.indices); d.n_shapes = len(self.shapes)
@@ -119,6 +126,8 @@ class SceneArrays:
         d.shapes = self.shapes.ctypes.data_as(C.POINTER(PpgShape))
         d.bsdfs = self.bsdfs.ctypes.data_as(C.POINTER(PpgBsdf))
         d.area_radiance = _fp(self.radiance)
+        d.bsdf_tables = _fp(self.tables) if len(self.tables) else None
+        d.n_bsdf_tables = len(self.tables)
         cam = PpgCamera()
         m = np.ascontiguousarray(scene.cam_to_world, np.float32).reshape(16)
         for i in range(16):

@@ -40,6 +40,9 @@ BSDF_NULL_BLACK = 1
 BSDF_DIELECTRIC = 2
 BSDF_CONDUCTOR = 3
 BSDF_ROUGHCONDUCTOR = 4
+BSDF_ROUGHPLASTIC = 5
+BSDF_ROUGHDIELECTRIC = 6
+BSDF_FLAG_NONLINEAR = 2
 BSDF_FLAG_TWOSIDED = 1
 
 # a few entries of Mitsuba's named indices of refraction (src/bsdfs/ior.h); defaults: intIOR "bk7", extIOR "air"
@@ -345,7 +348,7 @@ class SceneDesc:
     indices: np.ndarray        # (T,3) u32
     triangle_shape: np.ndarray  # (T,) u32
     shapes: np.ndarray         # (S,8) u32/i32: first_tri, n_tris, bsdf, emitter, has_normals, has_uvs, 0, 0
-    bsdfs: np.ndarray          # (B,16) f32 view of ppg_bsdf (type/flags bit-cast)
+    bsdfs: np.ndarray          # (B,24) f32 view of ppg_bsdf (type/flags bit-cast)
     area_radiance: np.ndarray  # (E,3) f32
     cam_to_world: np.ndarray   # (4,4) f32
     x_fov_deg: float
@@ -357,6 +360,7 @@ class SceneDesc:
     aabb_max: np.ndarray
     integrator: dict = field(default_factory=dict)  # XML name -> string value
     bsdf_names: list = field(default_factory=list)
+    bsdf_tables: np.ndarray = None   # (T,100) f32 rough-transmittance tables referenced by roughplastic materials
 
     def with_film(self, w: int, h: int) -> "SceneDesc":
         """Same scene, different film size (x fov re-resolved only when the aspect
@@ -372,7 +376,7 @@ class SceneDesc:
             cam=np.array([self.x_fov_deg, self.near_clip, self.far_clip, self.film_width, self.film_height], np.float64),
             aabb=np.stack([self.aabb_min, self.aabb_max]).astype(np.float32),
             integrator=np.array([f"{k}={v}" for k, v in self.integrator.items()]),
-            bsdf_names=np.array(self.bsdf_names))
+            bsdf_names=np.array(self.bsdf_names), bsdf_tables=(self.bsdf_tables if self.bsdf_tables is not None else np.zeros((0, 100), np.float32)))
 
     @staticmethod
     def load(path) -> "SceneDesc":
@@ -381,15 +385,29 @@ class SceneDesc:
         integ = dict(s.split("=", 1) for s in d["integrator"].tolist())
         return SceneDesc(d["positions"], d["normals"], d["uvs"], d["indices"], d["triangle_shape"], d["shapes"],
                          d["bsdfs"], d["area_radiance"], d["cam_to_world"], float(cam[0]), float(cam[1]), float(cam[2]),
-                         int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist())
+                         int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist(),
+                         d["bsdf_tables"] if "bsdf_tables" in d.files else None)
 
 
 def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0), alpha=0.1, distribution=0):
     """One ppg_bsdf (include/ppg.h) as 16 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], alpha, distribution (int bits)."""
-    b = np.zeros(16, np.float32)
+    b = np.zeros(24, np.float32)
     b[:2] = np.array([type_, flags], np.uint32).view(np.float32)
     b[2:5] = refl; b[5:8] = trans; b[8:11] = eta; b[11:14] = k; b[14] = alpha
     b[15:16] = np.array([distribution], np.int32).view(np.float32)
+    return b
+
+
+def make_roughplastic(flags, diffuse, specular, eta, alpha, distribution, nonlinear, tables):
+    """ppg_bsdf for roughplastic (src/bsdfs/roughplastic.cpp:190-290); appends its rough-transmittance table to `tables`."""
+    from . import rtrans
+    lut, fdr = rtrans.reduce_for_material("ggx" if distribution == 1 else "beckmann", eta, alpha)
+    lum = lambda c: 0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2]
+    d_avg, s_avg = lum(diffuse), lum(specular)
+    b = _make_bsdf(BSDF_ROUGHPLASTIC, flags | (BSDF_FLAG_NONLINEAR if nonlinear else 0), diffuse, (0, 0, 0), (eta, eta, eta), (0, 0, 0), alpha, distribution)
+    b[16:19] = specular; b[19] = fdr; b[20] = s_avg / (d_avg + s_avg)
+    b[21:22] = np.array([len(tables)], np.int32).view(np.float32)
+    tables.append(lut)
     return b
 
 
@@ -421,6 +439,9 @@ def _parse_color(node, is_emitter=False):
     raise ValueError(f"unsupported colour element <{node.tag}>")
 
 
+_TABLES = []      # rough-transmittance tables collected while parsing one scene
+
+
 def _parse_bsdf(node, bsdf_table, names, by_id):
     typ = node.attrib["type"]
     flags = 0
@@ -444,6 +465,24 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
         entry = _make_bsdf(BSDF_DIELECTRIC, flags, sr, st, (eta, eta, eta))
+    elif typ == "roughdielectric":      # src/bsdfs/roughdielectric.cpp:183-210
+        if flags & BSDF_FLAG_TWOSIDED:
+            raise ValueError("twosided cannot wrap a transmissive BSDF")
+        eta = _lookup_ior(props.get("intIOR"), "bk7") / _lookup_ior(props.get("extIOR"), "air")
+        distr = props.get("distribution", "beckmann").lower()
+        if distr not in ("beckmann", "ggx"):
+            raise NotImplementedError(f"microfacet distribution '{distr}'")
+        sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
+        st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
+        entry = _make_bsdf(BSDF_ROUGHDIELECTRIC, flags, sr, st, (eta, eta, eta), (0, 0, 0), float(props.get("alpha", 0.1)), 1 if distr == "ggx" else 0)
+    elif typ == "roughplastic":         # src/bsdfs/roughplastic.cpp:190-232
+        eta = _lookup_ior(props.get("intIOR"), "polypropylene") / _lookup_ior(props.get("extIOR"), "air")
+        distr = props.get("distribution", "beckmann").lower()
+        if distr not in ("beckmann", "ggx"):
+            raise NotImplementedError(f"microfacet distribution '{distr}'")
+        dr = _parse_color(colors["diffuseReflectance"]) if "diffuseReflectance" in colors else np.full(3, 0.5, np.float32)
+        sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
+        entry = make_roughplastic(flags, dr, sr, eta, float(props.get("alpha", 0.1)), 1 if distr == "ggx" else 0, props.get("nonlinear", "false") == "true", _TABLES)
     elif typ == "roughconductor":       # src/bsdfs/roughconductor.cpp:190-222
         ext = _lookup_ior(props.get("extEta"), "air")
         if "eta" in colors and "k" in colors:
@@ -482,6 +521,7 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
 def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
     root = ET.parse(path).getroot()
     base = os.path.dirname(os.path.abspath(path))
+    del _TABLES[:]
     integrator = {}
     inode = root.find("integrator")
     if inode is not None:
@@ -595,7 +635,8 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
     return SceneDesc(
         positions=P, normals=np.concatenate(N_all).astype(np.float32), uvs=np.concatenate(UV_all).astype(np.float32),
         indices=np.concatenate(I_all).astype(np.uint32), triangle_shape=np.concatenate(TS_all).astype(np.uint32),
-        shapes=np.asarray(shapes, np.int64).astype(np.int32), bsdfs=np.asarray(bsdf_table, np.float32).reshape(-1, 16),
+        shapes=np.asarray(shapes, np.int64).astype(np.int32), bsdfs=np.asarray(bsdf_table, np.float32).reshape(-1, 24),
+        bsdf_tables=np.asarray(_TABLES, np.float32).reshape(-1, 100),
         area_radiance=np.asarray(radiance, np.float32).reshape(-1, 3), cam_to_world=cam_to_world.astype(np.float32),
         x_fov_deg=float(xfov), near_clip=near, far_clip=far, film_width=W, film_height=H,
         aabb_min=aabb_min.astype(np.float32), aabb_max=aabb_max.astype(np.float32), integrator=integrator, bsdf_names=names)

@@ -13,6 +13,13 @@ def load_cbox(size=None, improved=False):
     return sc
 
 
+def load_fixture_scene(name, size=None):
+    """scenes/<name>.npz written by tools/make_fixtures.py."""
+    from ppg_b200.scene import SceneDesc
+    sc = SceneDesc.load(os.path.join(ROOT, "scenes", name + ".npz"))
+    return sc.with_film(size, size) if size is not None else sc
+
+
 def relmse(img, ref):
     img = np.asarray(img, np.float64); ref = np.asarray(ref, np.float64)
     return float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-3)))

@@ -33,8 +33,8 @@ def _declare(lib):
     lib.ppgo_step_passes.argtypes = [H, C.c_int, C.c_int, f32p]
     lib.ppgo_step_build.argtypes = [H, C.POINTER(capi.PpgIterationStats)]
     lib.ppgo_get_moment_images.argtypes = [H, f32p, f32p]
-    lib.ppgo_bsdf_eval_pdf.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p]
-    lib.ppgo_bsdf_sample.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p, u8p]
+    lib.ppgo_bsdf_eval_pdf.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p]
+    lib.ppgo_bsdf_sample.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p, u8p, f32p]
     lib.ppgo_tree_refine.argtypes = [H, C.c_uint64, C.c_int]
     lib.ppgo_tree_reset.argtypes = [H, C.c_int, C.c_float]
     lib.ppgo_tree_build.argtypes = [H]
@@ -262,15 +262,32 @@ def make_bsdf(type=0, flags=0, reflectance=(0.5, 0.5, 0.5), transmittance=(1, 1,
     return b
 
 
-def bsdf_eval_pdf(b, wi, wo, kind="port"):
+def bsdf_from_row(row):
+    """ppg_bsdf from one row of SceneDesc.bsdfs."""
+    b = capi.PpgBsdf()
+    raw = np.ascontiguousarray(row, np.float32).tobytes()
+    C.memmove(C.byref(b), raw, min(len(raw), C.sizeof(b)))
+    return b
+
+
+def _tab(tables):
+    if tables is None:
+        return None, None
+    t = np.ascontiguousarray(tables, np.float32)
+    return t, fptr(t)
+
+
+def bsdf_eval_pdf(b, wi, wo, kind="port", tables=None):
     lib = load(kind); wi = np.ascontiguousarray(wi, np.float32); wo = np.ascontiguousarray(wo, np.float32)
     ev = np.zeros_like(wi); pdf = np.zeros(len(wi), np.float32)
-    lib.ppgo_bsdf_eval_pdf(C.byref(b), len(wi), fptr(wi), fptr(wo), fptr(ev), fptr(pdf))
+    keep, tp = _tab(tables)
+    lib.ppgo_bsdf_eval_pdf(C.byref(b), len(wi), fptr(wi), fptr(wo), fptr(ev), fptr(pdf), tp)
     return ev, pdf
 
 
-def bsdf_sample(b, wi, smp, kind="port"):
+def bsdf_sample(b, wi, smp, kind="port", tables=None):
     lib = load(kind); wi = np.ascontiguousarray(wi, np.float32); smp = np.ascontiguousarray(smp, np.float32)
     wo = np.zeros_like(wi); w = np.zeros_like(wi); pdf = np.zeros(len(wi), np.float32); d = np.zeros(len(wi), np.uint8)
-    lib.ppgo_bsdf_sample(C.byref(b), len(wi), fptr(wi), fptr(smp), fptr(wo), fptr(w), fptr(pdf), d.ctypes.data_as(C.POINTER(C.c_uint8)))
+    keep, tp = _tab(tables)
+    lib.ppgo_bsdf_sample(C.byref(b), len(wi), fptr(wi), fptr(smp), fptr(wo), fptr(w), fptr(pdf), d.ctypes.data_as(C.POINTER(C.c_uint8)), tp)
     return wo, w, pdf, d

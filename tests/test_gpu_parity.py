@@ -306,3 +306,38 @@ def test_rough_conductor_matches_oracle(extra):
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
         assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-3)
         assert np.isclose(a["variance"], b["variance"], rtol=2e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(spatialFilter="stochastic", directionalFilter="box", sampleCombination="inversevar")])
+def test_rough_plastic_matches_oracle(extra):
+    """CBOX with rough-plastic boxes (roughplastic.cpp: microfacet coat with dielectric Fresnel over a diffuse base attenuated by the
+    tabulated rough transmittance, linear and nonlinear variants; Beckmann 0.4 like spaceship.xml's leather and GGX 0.2).
+    Same tolerance as the other microfacet model (device libm differs from glibc by ulps)."""
+    from common import load_fixture_scene
+    sc = load_fixture_scene("cbox-plastic", 128)
+    props = dict(dict(sc.integrator, budget="60"), **extra)
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert relmse(img, ref) <= 1e-4, relmse(img, ref)
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 1e-3 * ost["total_vertices"]
+    for a, b in zip(st["iterations"], ost["iterations"]):
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
+        assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(bsdfSamplingFractionLoss="none", spatialFilter="box")])
+def test_rough_dielectric_matches_oracle(extra):
+    """CBOX with rough-glass boxes (roughdielectric.cpp: glossy reflection + glossy transmission, one extra path-sampler draw per
+    sample for the lobe choice, eta tracking for Russian roulette)."""
+    from ppg_b200.builtin_scenes import cbox_rough_glass
+    sc = cbox_rough_glass(load_cbox(128))
+    props = dict(dict(sc.integrator, budget="60"), **extra)
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert relmse(img, ref) <= 1e-4, relmse(img, ref)
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 1e-3 * ost["total_vertices"]
+    for a, b in zip(st["iterations"], ost["iterations"]):
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
+        assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-3)

@@ -8,6 +8,8 @@ Writes
   practical-path-guiding_b200/ppg_b200/data/cie1931.npz  CIE 1931 observer + D65 tables (standard colorimetric data)
   scenes/cbox.npz            flat-array form of /root/reference/scenes/cbox/cbox.xml (our loader's output)
   scenes/cbox-improved.npz   same for cbox-improved.xml
+  scenes/cbox-plastic.npz    CBOX with rough-plastic boxes; carries the per-material rough-transmittance tables reduced from
+                             /root/reference/mitsuba/data/microfacet/{beckmann,ggx}.dat (ppg_b200/rtrans.py)
   tests/golden/cbox_log_stats.json   known-answer statistics parsed from the logs embedded
                                       in the reference's golden EXRs (hdrfilm attachLog)
 """
@@ -60,7 +62,16 @@ def parse_log(log):
             "width": int(m2.group(1)), "height": int(m2.group(2)), "cores": int(m2.group(3))}
 
 
+def plastic():
+    from ppg_b200.builtin_scenes import cbox_rough_plastic
+    sc = cbox_rough_plastic(S.SceneDesc.load(os.path.join(ROOT, "scenes", "cbox.npz")))
+    sc.save(os.path.join(ROOT, "scenes", "cbox-plastic.npz"))
+    print("cbox-plastic", sc.bsdf_names[-2:], "fdr", sc.bsdfs[-2:, 19], "ssw", sc.bsdfs[-2:, 20], "T(1)", sc.bsdf_tables[:, -1], "T(0)", sc.bsdf_tables[:, 0])
+
+
 def main():
+    if sys.argv[1:] == ["plastic"]:
+        return plastic()
     os.makedirs(os.path.join(ROOT, "scenes"), exist_ok=True)
     cie = S.extract_cie_tables()
     assert len(cie["x"]) == 471
@@ -79,6 +90,7 @@ def main():
     with open(os.path.join(ROOT, "tests", "golden", "cbox_log_stats.json"), "w") as f:
         json.dump(stats, f, indent=1)
     print(json.dumps(stats["cbox"]["iterations"][:2], indent=1))
+    plastic()
 
 
 if __name__ == "__main__":
