@@ -149,6 +149,15 @@ typedef struct ppg_shape {
     uint32_t reserved[2];
 } ppg_shape;                  /* 32 bytes */
 
+/* Analytic sphere (src/shapes/sphere.cpp); its ppg_shape has n_triangles == 0.  The object-to-world transform is restricted to
+ * translation + uniform scale (all the bundled scenes need), so local coordinates are p - center. */
+typedef struct ppg_sphere {
+    float   center[3];
+    float   radius;
+    int32_t shape;         /* index into ppg_scene_desc.shapes (BSDF / emitter of the sphere) */
+    int32_t flip_normals;  /* "flipNormals": normals point inwards */
+} ppg_sphere;
+
 typedef struct ppg_camera {   /* src/sensors/perspective.cpp:120-298 + librender/sensor.cpp:239-300 */
     float to_world[16];       /* row-major 4x4 camera-to-world (lookAt: columns left, up, dir, origin) */
     float x_fov_deg;          /* horizontal field of view after fovAxis resolution */
@@ -172,6 +181,8 @@ typedef struct ppg_scene_desc {
     const float    *area_radiance;  /* 3*n_emitters: area-light radiance RGB (src/emitters/area.cpp:104-109) */
     const float    *bsdf_tables;    /* n_bsdf_tables * PPG_BSDF_TABLE_SIZE floats, may be NULL */
     uint32_t        n_bsdf_tables;
+    uint32_t        n_spheres;
+    const ppg_sphere *spheres;      /* may be NULL */
     ppg_camera camera;
     float aabb_min[3], aabb_max[3]; /* Scene::getAABB(): kd-tree AABB + sensor + emitter AABBs (librender/scene.cpp:387-413) */
 } ppg_scene_desc;

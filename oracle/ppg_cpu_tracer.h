@@ -56,6 +56,12 @@ static inline float max3(F3 a) { return std::max(std::max(a.x, a.y), a.z); }
 static const float kPiT = 3.14159265358979323846f;    // M_PI (single-precision build)
 static const float kEpsilon = 1e-4f;                 // core/constants.h:28
 static const float kInvPi = 0.31830988618379067154f; // INV_PI
+// coordinateSystem(a, b, c), src/libcore/util.cpp:592-601
+static inline void coordinate_system(F3 a, F3 &b, F3 &c) {
+    if (std::fabs(a.x) > std::fabs(a.y)) { const float invLen = 1.0f / std::sqrt(a.x * a.x + a.z * a.z); c = f3(a.z * invLen, 0.0f, -a.x * invLen); }
+    else { const float invLen = 1.0f / std::sqrt(a.y * a.y + a.z * a.z); c = f3(0.0f, a.z * invLen, -a.y * invLen); }
+    b = cross(c, a);
+}
 
 // ------------------------------------------------------------------ PCG32 path sampler
 static inline uint64_t splitmix64(uint64_t x) {
@@ -130,13 +136,14 @@ struct Scene {
     std::vector<F3> P, N; std::vector<float> UV;
     std::vector<uint32_t> idx, triShape;
     std::vector<ppg_shape> shapes; std::vector<ppg_bsdf> bsdfs; std::vector<F3> radiance; std::vector<float> tables;
+    std::vector<ppg_sphere> spheres;
     ppg_camera cam; F3 aabbMin, aabbMax;
     std::vector<TriAccelP> accel; std::vector<BvhNode> bvh; std::vector<uint32_t> primOrder;
     // camera derived (src/sensors/perspective.cpp:120-298)
     F3 camO, camLeft, camUp, camDir; float tanX, tanY;
     // emitter sampling (next event estimation): per emitter the area distribution over its triangles
     // (TriMesh::prepareSamplingTable, src/librender/trimesh.cpp:388-403) and the discrete emitter choice (scene.cpp:357-381)
-    struct EmitterSampler { uint32_t firstTri, nTris; std::vector<float> cdf; float invArea; int shape; };
+    struct EmitterSampler { uint32_t firstTri, nTris; std::vector<float> cdf; float invArea; int shape; int sphere; };
     std::vector<EmitterSampler> emitterSamplers; std::vector<float> emitterCdf; float emitterNormalization = 0;
 
     // DiscreteDistribution::sample (include/mitsuba/core/pmf.h:124-137)
@@ -149,7 +156,7 @@ struct Scene {
     void buildEmitterSamplers() {
         emitterSamplers.clear();
         for (size_t e = 0; e < radiance.size(); ++e) {
-            EmitterSampler es; es.shape = -1; es.firstTri = es.nTris = 0; es.invArea = 0;
+            EmitterSampler es; es.shape = -1; es.firstTri = es.nTris = 0; es.invArea = 0; es.sphere = -1;
             for (size_t sidx = 0; sidx < shapes.size(); ++sidx) if (shapes[sidx].emitter == (int) e) { es.shape = (int) sidx; es.firstTri = shapes[sidx].first_triangle; es.nTris = shapes[sidx].n_triangles; }
             es.cdf.assign(1, 0.0f);
             for (uint32_t t = es.firstTri; t < es.firstTri + es.nTris; ++t) {
@@ -158,6 +165,9 @@ struct Scene {
             }
             const float sum = es.cdf.back();                                                     // DiscreteDistribution::normalize (pmf.h:101-114)
             if (sum > 0) { const float nrm = 1.0f / sum; for (size_t i = 1; i < es.cdf.size(); ++i) es.cdf[i] *= nrm; es.cdf.back() = 1.0f; es.invArea = 1.0f / sum; }
+            for (size_t k = 0; k < spheres.size(); ++k) if (spheres[k].shape == es.shape) {          // sphere.cpp:128: m_invSurfaceArea
+                es.sphere = (int) k; es.invArea = 1 / (4 * kPiT * spheres[k].radius * spheres[k].radius);
+            }
             emitterSamplers.push_back(es);
         }
         emitterCdf.assign(1, 0.0f);
@@ -178,6 +188,8 @@ struct Scene {
         bsdfs.assign(d.bsdfs, d.bsdfs + d.n_bsdfs);
         tables.clear();
         if (d.bsdf_tables && d.n_bsdf_tables) tables.assign(d.bsdf_tables, d.bsdf_tables + (size_t)d.n_bsdf_tables * PPG_BSDF_TABLE_SIZE);
+        spheres.clear();
+        if (d.spheres && d.n_spheres) spheres.assign(d.spheres, d.spheres + d.n_spheres);
         radiance.resize(d.n_emitters);
         for (uint32_t i = 0; i < d.n_emitters; ++i) radiance[i] = f3(d.area_radiance[3 * i], d.area_radiance[3 * i + 1], d.area_radiance[3 * i + 2]);
         cam = d.camera;
@@ -233,11 +245,45 @@ struct Scene {
         }
     }
 
-    struct Hit { float t, u, v; uint32_t prim; };
+    struct Hit { float t, u, v; uint32_t prim; };   // prim: triangle index, or kSphereBit | sphere index
+    static const uint32_t kSphereBit = 0x80000000u;
+
+    // Sphere::rayIntersect (src/shapes/sphere.cpp:163-187) with solveQuadraticDouble (src/libcore/util.cpp:487-525): double precision
+    static bool sphereIntersect(const ppg_sphere &sp, F3 ro, F3 rd, float mint, float maxt, float &t) {
+        const double ox = (double) ro.x - (double) sp.center[0], oy = (double) ro.y - (double) sp.center[1], oz = (double) ro.z - (double) sp.center[2];
+        const double dx = rd.x, dy = rd.y, dz = rd.z;
+        const double A = dx * dx + dy * dy + dz * dz;
+        const double B = 2 * (ox * dx + oy * dy + oz * dz);
+        const double C = (ox * ox + oy * oy + oz * oz) - (double) (sp.radius * sp.radius);        // m_radius*m_radius is a float product
+        double nearT, farT;
+        if (A == 0) { if (B != 0) nearT = farT = -C / B; else return false; }
+        else {
+            const double discrim = B * B - 4.0f * A * C;
+            if (discrim < 0) return false;
+            const double sqrtDiscrim = std::sqrt(discrim);
+            const double temp = B < 0 ? -0.5f * (B - sqrtDiscrim) : -0.5f * (B + sqrtDiscrim);
+            nearT = temp / A; farT = C / temp;
+            if (nearT > farT) std::swap(nearT, farT);
+        }
+        if (!(nearT <= maxt && farT >= mint)) return false;
+        if (nearT < mint) { if (farT > maxt) return false; t = (float) farT; }
+        else t = (float) nearT;
+        return true;
+    }
 
     // nearest hit in [mint, maxt]; ties on t go to the lower triangle index
     bool intersect(F3 o, F3 d, float mint, float maxt, Hit &hit) const {
+        const bool any = intersectTriangles(o, d, mint, maxt, hit);
+        bool sph = false;
+        for (size_t k = 0; k < spheres.size(); ++k) {
+            float t;
+            if (sphereIntersect(spheres[k], o, d, mint, maxt, t) && t < hit.t) { hit.t = t; hit.u = hit.v = 0; hit.prim = kSphereBit | (uint32_t) k; sph = true; }
+        }
+        return any || sph;
+    }
+    bool intersectTriangles(F3 o, F3 d, float mint, float maxt, Hit &hit) const {
         hit.t = std::numeric_limits<float>::infinity(); hit.prim = 0xFFFFFFFFu;
+        if (triShape.empty()) return false;
         const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         uint32_t stack[64]; int sp = 0; stack[sp++] = 0;
         while (sp) {
@@ -283,6 +329,22 @@ static inline bool ray_intersect(const Scene &sc, F3 o, F3 d, float mint, float 
     Scene::Hit h;
     if (!sc.intersect(o, d, mint, maxt, h)) return false;
     its.valid = true; its.t = h.t;
+    if (h.prim & Scene::kSphereBit) {          // Sphere::fillIntersectionRecord (src/shapes/sphere.cpp:209-255), identity rotation
+        const ppg_sphere &sp = sc.spheres[h.prim & ~Scene::kSphereBit];
+        const F3 c = f3(sp.center[0], sp.center[1], sp.center[2]);
+        its.p = o + d * h.t;
+        its.p = c + normalize(its.p - c) * sp.radius;        // re-projection (single precision)
+        const F3 local = its.p - c;
+        const F3 dpdu = f3(-local.y, local.x, 0) * (2 * kPiT);
+        its.geoN = normalize(its.p - c);
+        if (sp.flip_normals) its.geoN = its.geoN * -1.0f;
+        its.shN = its.geoN;
+        its.shape = (uint32_t) sp.shape;
+        its.shS = normalize(dpdu - its.shN * dot(its.shN, dpdu));
+        its.shT = cross(its.shN, its.shS);
+        its.wi = its.toLocal(-d);
+        return true;
+    }
     const uint32_t i0 = sc.idx[3 * h.prim], i1 = sc.idx[3 * h.prim + 1], i2 = sc.idx[3 * h.prim + 2];
     const F3 p0 = sc.P[i0], p1 = sc.P[i1], p2 = sc.P[i2];
     const F3 b = f3(1 - h.u - h.v, h.u, h.v);
@@ -324,6 +386,54 @@ static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float
     const float emPdf = sc.emitterCdf[ei + 1] - sc.emitterCdf[ei];
     sx = (sx - sc.emitterCdf[ei]) / (sc.emitterCdf[ei + 1] - sc.emitterCdf[ei]);            // sampleReuse
     const Scene::EmitterSampler &E = sc.emitterSamplers[ei];
+    if (E.sphere >= 0) {                     // Sphere::sampleDirect, src/shapes/sphere.cpp:286-355
+        const ppg_sphere &sp = sc.spheres[E.sphere];
+        const F3 c = f3(sp.center[0], sp.center[1], sp.center[2]);
+        const F3 refToCenter = c - ref;
+        const float refDist2 = dot(refToCenter, refToCenter);
+        const float invRefDist = 1.0f / std::sqrt(refDist2);
+        const float sinAlpha = sp.radius * invRefDist;
+        F3 d, n; float pdf, dist;
+        if (sinAlpha < 1 - kEpsilon) {       // outside: uniform cone
+            const float cosAlpha = std::sqrt(std::max(0.0f, 1.0f - sinAlpha * sinAlpha));
+            const F3 fn = refToCenter * invRefDist; F3 fs, ft; coordinate_system(fn, fs, ft);
+            const float cosTheta = (1 - sx) + sx * cosAlpha, sinTheta = std::sqrt(std::max(0.0f, 1.0f - cosTheta * cosTheta));
+            float sinPhi, cosPhi; sincosf(2.0f * kPiT * sy, &sinPhi, &cosPhi);
+            const F3 lv = f3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta);
+            d = fs * lv.x + ft * lv.y + fn * lv.z;
+            pdf = (0.5f * kInvPi) / (1 - cosAlpha);                                            // INV_TWOPI / (1-cosCutoff)
+            const float projDist = dot(refToCenter, d);
+            const float baseT = refDist2 / projDist;
+            const F3 query = ref + d * baseT;
+            const F3 queryToCenter = c - query;
+            const float queryDist2 = dot(queryToCenter, queryToCenter), queryProjDist = dot(queryToCenter, d);
+            const float A = 1.0f, B = -2 * queryProjDist, C = queryDist2 - sp.radius * sp.radius;
+            float nearT;
+            { const float discrim = B * B - 4.0f * A * C;                                       // solveQuadratic, util.cpp:447-485
+              if (discrim < 0) nearT = queryProjDist;
+              else { const float sq = std::sqrt(discrim); const float temp = B < 0 ? -0.5f * (B - sq) : -0.5f * (B + sq); float x0 = temp / A, x1 = C / temp; if (x0 > x1) std::swap(x0, x1); nearT = x0; } }
+            dist = baseT + nearT;
+            n = normalize(d * nearT - queryToCenter);
+        } else {                             // inside: uniform sphere
+            const float z = 1.0f - 2.0f * sy, r = std::sqrt(std::max(0.0f, 1.0f - z * z));
+            float sinPhi, cosPhi; sincosf(2.0f * kPiT * sx, &sinPhi, &cosPhi);
+            const F3 v = f3(r * cosPhi, r * sinPhi, z);
+            const F3 p = c + v * sp.radius;
+            n = v; d = p - ref;
+            const float dist2 = dot(d, d);
+            dist = std::sqrt(dist2);
+            d = d * (1.0f / dist);                                                              // Vector /= Float: reciprocal multiply
+            pdf = E.invArea * dist2 / std::fabs(dot(d, n));
+        }
+        if (sp.flip_normals) n = n * -1.0f;
+        out.d = d; out.n = n; out.dist = dist; out.emitter = (int) ei;
+        if (dot(d, refN) >= 0 && dot(d, n) < 0 && pdf != 0) out.value = sc.radiance[ei] * (1.0f / pdf);
+        else { out.pdf = 0; out.value = f3(0, 0, 0); return false; }
+        if (occluded(sc, ref, d, dist)) { out.pdf = pdf * emPdf; out.value = f3(0, 0, 0); return true; }
+        out.value = out.value * (1.0f / emPdf);
+        out.pdf = pdf * emPdf;
+        return true;
+    }
     if (E.nTris == 0) return false;
     const size_t ti = Scene::cdfSample(E.cdf, sy);
     sy = (sy - E.cdf[ti]) / (E.cdf[ti + 1] - E.cdf[ti]);
@@ -352,8 +462,18 @@ static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float
     return true;
 }
 // Scene::pdfEmitterDirect (scene.cpp:949-952) for an emitter hit found by BSDF / guiding sampling (dRec.setQuery, records.inl:170-178)
-static inline float pdf_emitter_direct(const Scene &sc, int emitter, F3 refN, F3 d, F3 n, float dist) {
+static inline float pdf_emitter_direct(const Scene &sc, int emitter, F3 ref, F3 refN, F3 d, F3 n, float dist) {
     if (!(dot(d, refN) >= 0 && dot(d, n) < 0)) return 0.0f;                                    // AreaLight::pdfDirect (area.cpp:175-183)
+    if (sc.emitterSamplers[emitter].sphere >= 0) {                                             // Sphere::pdfDirect, sphere.cpp:357-392
+        const ppg_sphere &sp = sc.spheres[sc.emitterSamplers[emitter].sphere];
+        const F3 refToCenter = f3(sp.center[0], sp.center[1], sp.center[2]) - ref;
+        const float invRefDist = 1.0f / length(refToCenter);
+        const float sinAlpha = sp.radius * invRefDist;
+        float pdfSA;
+        if (sinAlpha < 1 - kEpsilon) { const float cosAlpha = std::sqrt(std::max(0.0f, 1 - sinAlpha * sinAlpha)); pdfSA = (0.5f * kInvPi) / (1 - cosAlpha); }
+        else pdfSA = sc.emitterSamplers[emitter].invArea * dist * dist / std::fabs(dot(d, n));
+        return pdfSA * (1.0f * sc.emitterNormalization);
+    }
     const float pdfPos = sc.emitterSamplers[emitter].invArea;
     return pdfPos * (dist * dist) / std::fabs(dot(d, n)) * (1.0f * sc.emitterNormalization);   // Shape::pdfDirect (shape.cpp:117-126) * pdfEmitterDiscrete
 }
@@ -894,7 +1014,7 @@ public:
             const bool isDelta = bs.delta;
             {
                 float emitterPdf = 0;                                                            // GP:2084-2087
-                if (doNee && !isDelta && !is_zero(value)) emitterPdf = pdf_emitter_direct(sc, sc.shapes[next.shape].emitter, refN, d, next.shN, next.t);
+                if (doNee && !isDelta && !is_zero(value)) emitterPdf = pdf_emitter_direct(sc, sc.shapes[next.shape].emitter, its.p, refN, d, next.shN, next.t);
                 const float weight = mi_weight(woPdf, emitterPdf);
                 const F3 L = throughput * value * weight;
                 if (!is_zero(L)) recordRadiance(L);

@@ -81,6 +81,8 @@ struct SceneView {
     const int4 *meta;
     const float4 *bvh;
     const float4 *bsdf;       // PPG_BSDF_F4 per material, see load_bsdf
+    const float4 *spheres;    // analytic spheres (sphere.cpp): [2k] = {center.xyz, radius}, [2k+1] = {bits(bsdf), bits(emitter), bits(flipNormals), -}
+    uint32_t nSpheres;
     const float *bsdfTables;  // roughplastic: PPG_BSDF_LUT floats per table (external rough transmittance), read through L1/L2
     const float4 *radiance;   // per emitter: rgb
     uint32_t nTris, nBvhNodes, nBsdfs, nEmitters;
@@ -171,12 +173,49 @@ __device__ __forceinline__ void tri_group_exact(const Acc &A_, uint32_t q, float
     }
 }
 
+#define PPG_SPHERE_BIT 0x80000000u
+#define PPG_BVH_STACK 64          // the host builder refuses deeper trees
+// Sphere::rayIntersect (src/shapes/sphere.cpp:163-187) with solveQuadraticDouble (src/libcore/util.cpp:487-525): double precision like the reference
+__device__ __forceinline__ bool sphere_intersect(float4 cr, float3 ro, float3 rd, float mint, float maxt, float &t) {
+    const double ox = (double) ro.x - (double) cr.x, oy = (double) ro.y - (double) cr.y, oz = (double) ro.z - (double) cr.z;
+    const double dx = rd.x, dy = rd.y, dz = rd.z;
+    const double A = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double B = __dmul_rn(2.0, __dadd_rn(__dadd_rn(__dmul_rn(ox, dx), __dmul_rn(oy, dy)), __dmul_rn(oz, dz)));
+    const double C = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(ox, ox), __dmul_rn(oy, oy)), __dmul_rn(oz, oz)), (double) (cr.w * cr.w));
+    double nearT, farT;
+    if (A == 0.0) { if (B != 0.0) nearT = farT = -C / B; else return false; }
+    else {
+        const double discrim = __dsub_rn(__dmul_rn(B, B), __dmul_rn(__dmul_rn(4.0, A), C));
+        if (discrim < 0.0) return false;
+        const double sqrtDiscrim = sqrt(discrim);
+        const double temp = B < 0.0 ? __dmul_rn(-0.5, __dsub_rn(B, sqrtDiscrim)) : __dmul_rn(-0.5, __dadd_rn(B, sqrtDiscrim));
+        nearT = temp / A; farT = C / temp;
+        if (nearT > farT) { const double s = nearT; nearT = farT; farT = s; }
+    }
+    if (!(nearT <= (double) maxt && farT >= (double) mint)) return false;
+    if (nearT < (double) mint) { if (farT > (double) maxt) return false; t = (float) farT; }
+    else t = (float) nearT;
+    return true;
+}
+template <class Acc> __device__ __forceinline__ bool tri_scene_intersect(const Acc &A_, float3 o, float3 d, float mint, float maxt, Hit &hit);
+
 // Nearest hit in [mint, maxt]; ties on t go to the lower ORIGINAL triangle index so that the
-// result does not depend on the traversal order (same rule as the oracle).
+// result does not depend on the traversal order (same rule as the oracle).  Spheres are tested after the triangles.
 template <class Acc>
 __device__ __forceinline__ bool bvh_intersect(const Acc &A_, float3 o, float3 d, float mint, float maxt, Hit &hit) {
+    bool found = tri_scene_intersect(A_, o, d, mint, maxt, hit);
+    const SceneView &sc = A_.g;
+    for (uint32_t k = 0; k < sc.nSpheres; ++k) {
+        float t;
+        if (sphere_intersect(__ldg(&sc.spheres[2 * k]), o, d, mint, maxt, t) && t < hit.t) { hit.t = t; hit.u = hit.v = 0.f; hit.prim = PPG_SPHERE_BIT | k; hit.tri = 0; found = true; }
+    }
+    return found;
+}
+template <class Acc>
+__device__ __forceinline__ bool tri_scene_intersect(const Acc &A_, float3 o, float3 d, float mint, float maxt, Hit &hit) {
     const SceneView &sc = A_.g;
     hit.t = __int_as_float(0x7f800000); hit.prim = 0xFFFFFFFFu; hit.tri = 0;
+    if (sc.nTris == 0u) return false;
     if (sc.nGroups != 0u) {      // host sets nGroups only for tiny scenes (<= PPG_BRUTE_FORCE_TRIS triangles in <= 32 coplanar groups)
         // Tiny scenes (CBOX: 36 triangles in 18 coplanar groups, staged in shared memory).  A BVH walk makes every lane
         // of a warp reach its leaves at different times (measured: 2.5 of 32 lanes active in the triangle test), so
@@ -231,7 +270,7 @@ __device__ __forceinline__ bool bvh_intersect(const Acc &A_, float3 o, float3 d,
         return hit.prim != 0xFFFFFFFFu;
     }
     const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    uint32_t stack[32]; int sp = 0; uint32_t node = 0;
+    uint32_t stack[PPG_BVH_STACK]; int sp = 0; uint32_t node = 0;
     for (;;) {
         const float4 n0 = A_.bvh(2 * node), n1 = A_.bvh(2 * node + 1);
         float t0 = mint, t1 = fminf(maxt, hit.t);
@@ -280,7 +319,24 @@ struct Its {
 
 // fillIntersectionRecord (render/skdtree.h:343-428) + computeShadingFrame (libcore/util.cpp:603-608)
 template <class Acc>
-__device__ __forceinline__ void fill_its(const Acc &A_, const Hit &h, float3 d, Its &its) {
+__device__ __forceinline__ void fill_its(const Acc &A_, const Hit &h, float3 o, float3 d, Its &its) {
+    if (h.prim & PPG_SPHERE_BIT) {        // Sphere::fillIntersectionRecord (src/shapes/sphere.cpp:209-255), identity rotation
+        const uint32_t k = h.prim & ~PPG_SPHERE_BIT;
+        const float4 cr = __ldg(&A_.g.spheres[2 * k]), mt = __ldg(&A_.g.spheres[2 * k + 1]);
+        const float3 c = f3(cr.x, cr.y, cr.z);
+        its.p = o + d * h.t;
+        its.p = c + normalize(its.p - c) * cr.w;
+        const float3 local = its.p - c;
+        const float3 dpdu = f3(-local.y, local.x, 0.f) * (2.f * PPG_PI);
+        its.geoN = normalize(its.p - c);
+        if (__float_as_uint(mt.z)) its.geoN = its.geoN * -1.0f;
+        its.shN = its.geoN;
+        its.shS = normalize(dpdu - its.shN * dot(its.shN, dpdu));
+        its.shT = cross(its.shN, its.shS);
+        its.wi = its.toLocal(-d);
+        its.bsdf = __float_as_int(mt.x); its.emitter = __float_as_int(mt.y);
+        return;
+    }
     const float4 g0 = A_.geom(6 * h.tri), g1 = A_.geom(6 * h.tri + 1), g2 = A_.geom(6 * h.tri + 2);
     const int4 m = A_.meta(h.tri);
     const float3 p0 = f3(g0.x, g0.y, g0.z), p1 = f3(g1.x, g1.y, g1.z), p2 = f3(g2.x, g2.y, g2.z);
@@ -950,6 +1006,12 @@ __device__ __forceinline__ uint32_t cdf_sample(const float *__restrict__ cdf, ui
 }
 
 struct DirectSample { float3 value, d; float pdf; };
+// coordinateSystem(a, b, c), src/libcore/util.cpp:592-601
+__device__ __forceinline__ void coordinate_system(float3 a, float3 &b, float3 &c) {
+    if (fabsf(a.x) > fabsf(a.y)) { const float invLen = 1.0f / sqrtf(a.x * a.x + a.z * a.z); c = f3(a.z * invLen, 0.0f, -a.x * invLen); }
+    else { const float invLen = 1.0f / sqrtf(a.y * a.y + a.z * a.z); c = f3(0.0f, a.z * invLen, -a.y * invLen); }
+    b = cross(c, a);
+}
 // Scene::sampleAttenuatedEmitterDirect (scene.cpp:876-897) -> AreaLight::sampleDirect (area.cpp:158-173) -> Shape::sampleDirect
 // (shape.cpp:102-115) -> TriMesh::samplePosition (trimesh.cpp:412-423) -> Triangle::sample (libcore/triangle.cpp:24-59);
 // visibility (Scene::evalTransmittance, scene.cpp:619-679) is tested by the caller.  Returns false when the sample carries nothing.
@@ -962,6 +1024,54 @@ __device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref,
     sx = (sx - c0) / (c1 - c0);
     const float4 info = sc.emitterInfo[ei];
     const uint32_t first = __float_as_uint(info.x), nTris = __float_as_uint(info.y), cdfOff = __float_as_uint(info.w);
+    if (first & PPG_SPHERE_BIT) {          // Sphere::sampleDirect, src/shapes/sphere.cpp:286-355
+        const uint32_t k = first & ~PPG_SPHERE_BIT;
+        const float4 cr = __ldg(&sc.spheres[2 * k]), mt = __ldg(&sc.spheres[2 * k + 1]);
+        const float3 c = f3(cr.x, cr.y, cr.z);
+        const float3 refToCenter = c - ref;
+        const float refDist2 = dot(refToCenter, refToCenter);
+        const float invRefDist = 1.0f / sqrtf(refDist2);
+        const float sinAlpha = cr.w * invRefDist;
+        float3 d, n; float pdf;
+        if (sinAlpha < 1.f - PPG_EPSILON) {   // outside: uniform cone
+            const float cosAlpha = sqrtf(fmaxf(0.0f, 1.0f - sinAlpha * sinAlpha));
+            const float3 fn = refToCenter * invRefDist; float3 fs, ft; coordinate_system(fn, fs, ft);
+            const float cosTheta = (1.f - sx) + sx * cosAlpha, sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
+            float sinPhi, cosPhi; sincosf(2.0f * PPG_PI * sy, &sinPhi, &cosPhi);
+            const float3 lv = f3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta);
+            d = fs * lv.x + ft * lv.y + fn * lv.z;
+            pdf = (0.5f * PPG_INV_PI) / (1.f - cosAlpha);
+            const float projDist = dot(refToCenter, d);
+            const float baseT = refDist2 / projDist;
+            const float3 query = ref + d * baseT;
+            const float3 queryToCenter = c - query;
+            const float queryDist2 = dot(queryToCenter, queryToCenter), queryProjDist = dot(queryToCenter, d);
+            const float A = 1.0f, B = -2.f * queryProjDist, C = queryDist2 - cr.w * cr.w;
+            float nearT;
+            { const float discrim = B * B - 4.0f * A * C;                                       // solveQuadratic, util.cpp:447-485
+              if (discrim < 0.f) nearT = queryProjDist;
+              else { const float sq = sqrtf(discrim); const float temp = B < 0.f ? -0.5f * (B - sq) : -0.5f * (B + sq); float x0 = temp / A, x1 = C / temp; if (x0 > x1) { const float s_ = x0; x0 = x1; x1 = s_; } nearT = x0; } }
+            dist = baseT + nearT;
+            n = normalize(d * nearT - queryToCenter);
+        } else {                             // inside: uniform sphere
+            const float z = 1.0f - 2.0f * sy, r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+            float sinPhi, cosPhi; sincosf(2.0f * PPG_PI * sx, &sinPhi, &cosPhi);
+            const float3 v = f3(r * cosPhi, r * sinPhi, z);
+            const float3 p = c + v * cr.w;
+            n = v; d = p - ref;
+            const float dist2 = dot(d, d);
+            dist = sqrtf(dist2);
+            d = d * (1.0f / dist);
+            pdf = info.z * dist2 / fabsf(dot(d, n));
+        }
+        if (__float_as_uint(mt.z)) n = n * -1.0f;
+        out.d = d;
+        if (!(dot(d, refN) >= 0.f && dot(d, n) < 0.f && pdf != 0.f)) return false;
+        const float4 r = A_.radiance(ei);
+        out.value = (f3(r.x, r.y, r.z) * (1.0f / pdf)) * (1.0f / emPdf);
+        out.pdf = pdf * emPdf;
+        return true;
+    }
     if (nTris == 0u) return false;
     const float *tcdf = sc.emitterTriCdf + cdfOff;
     const uint32_t ti = cdf_sample(tcdf, nTris + 1, sy);
@@ -993,8 +1103,19 @@ __device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref,
     return true;
 }
 // Scene::pdfEmitterDirect (scene.cpp:949-952) for an emitter hit found by BSDF / guiding sampling
-__device__ __forceinline__ float pdf_emitter_direct(const SceneView &sc, int emitter, float3 refN, float3 d, float3 n, float dist) {
+__device__ __forceinline__ float pdf_emitter_direct(const SceneView &sc, int emitter, float3 ref, float3 refN, float3 d, float3 n, float dist) {
     if (!(dot(d, refN) >= 0.f && dot(d, n) < 0.f)) return 0.0f;
+    const float4 info = sc.emitterInfo[emitter];
+    if (__float_as_uint(info.x) & PPG_SPHERE_BIT) {                                            // Sphere::pdfDirect, sphere.cpp:357-392
+        const float4 cr = __ldg(&sc.spheres[2 * (__float_as_uint(info.x) & ~PPG_SPHERE_BIT)]);
+        const float3 refToCenter = f3(cr.x, cr.y, cr.z) - ref;
+        const float invRefDist = 1.0f / sqrtf(dot(refToCenter, refToCenter));
+        const float sinAlpha = cr.w * invRefDist;
+        float pdfSA;
+        if (sinAlpha < 1.f - PPG_EPSILON) { const float cosAlpha = sqrtf(fmaxf(0.0f, 1.f - sinAlpha * sinAlpha)); pdfSA = (0.5f * PPG_INV_PI) / (1.f - cosAlpha); }
+        else pdfSA = info.z * dist * dist / fabsf(dot(d, n));
+        return pdfSA * (1.0f * sc.emitterNormalization);
+    }
     return sc.emitterInfo[emitter].z * (dist * dist) / fabsf(dot(d, n)) * (1.0f * sc.emitterNormalization);
 }
 

@@ -151,6 +151,7 @@ static void wald_constants(H3 A, H3 B, H3 C, float out[9], int &k) {
 struct HostBvh {
     std::vector<float> nodes;        // 8 floats per node
     std::vector<uint32_t> order;     // leaf order -> original triangle
+    int maxDepth = 0;                // the device walk keeps one stack entry per level (PPG_BVH_STACK)
 };
 static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, HostBvh &out) {
     const uint32_t nt = (uint32_t) tmin.size();
@@ -160,11 +161,12 @@ static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, 
     for (uint32_t t = 0; t < nt; ++t) cen[t] = h3(0.5f * (tmin[t].x + tmax[t].x), 0.5f * (tmin[t].y + tmax[t].y), 0.5f * (tmin[t].z + tmax[t].z));
     struct Node { H3 mn, mx; uint32_t left, count; };
     std::vector<Node> nodes; nodes.reserve(2 * nt + 1); nodes.push_back(Node());
-    struct Job { uint32_t node, first, count; };
-    std::vector<Job> jobs; jobs.push_back(Job{0, 0, nt});
+    struct Job { uint32_t node, first, count; int depth; };
+    std::vector<Job> jobs; jobs.push_back(Job{0, 0, nt, 0});
     auto area = [](H3 mn, H3 mx) { const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z; return 2.f * (dx * dy + dy * dz + dz * dx); };
     while (!jobs.empty()) {
         const Job j = jobs.back(); jobs.pop_back();
+        out.maxDepth = std::max(out.maxDepth, j.depth);
         H3 mn = h3(1e30f, 1e30f, 1e30f), mx = h3(-1e30f, -1e30f, -1e30f), cmn = mn, cmx = mx;
         for (uint32_t i = j.first; i < j.first + j.count; ++i) {
             const uint32_t t = out.order[i];
@@ -218,8 +220,8 @@ static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, 
                 if (nl > 0 && nl < j.count) {
                     nd.left = (uint32_t) nodes.size(); nd.count = 0; nodes[j.node] = nd;
                     nodes.push_back(Node()); nodes.push_back(Node());
-                    jobs.push_back(Job{nd.left, j.first, nl});
-                    jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl});
+                    jobs.push_back(Job{nd.left, j.first, nl, j.depth + 1});
+                    jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl, j.depth + 1});
                     continue;
                 }
             }
@@ -227,8 +229,8 @@ static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, 
                 const uint32_t nl = j.count / 2;
                 nd.left = (uint32_t) nodes.size(); nd.count = 0; nodes[j.node] = nd;
                 nodes.push_back(Node()); nodes.push_back(Node());
-                jobs.push_back(Job{nd.left, j.first, nl});
-                jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl});
+                jobs.push_back(Job{nd.left, j.first, nl, j.depth + 1});
+                jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl, j.depth + 1});
                 continue;
             }
         }
@@ -256,7 +258,7 @@ struct ppg_integrator {
 
     // scene
     bool haveScene = false;
-    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom; DevBuf<float> dEmitterCdf, dEmitterTriCdf, dBsdfTables; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
+    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom, dSpheres; DevBuf<float> dEmitterCdf, dEmitterTriCdf, dBsdfTables; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
@@ -413,6 +415,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         tmax[t] = h3(std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)));
     }
     HostBvh bvh; build_bvh(tmin, tmax, bvh);
+    if (bvh.maxDepth >= PPG_BVH_STACK) return fail(PPG_ERR_UNSUPPORTED, "BVH deeper than the device traversal stack");
     // brute-force layout for tiny scenes: coplanar groups ordered by projection axis (see bvh_intersect)
     uint32_t kBegin[4] = {0, 0, 0, 0};
     std::vector<float> groups;
@@ -522,6 +525,15 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
             for (uint32_t si = 0; si < s->n_shapes; ++si) if (s->shapes[si].emitter == (int) e) shape = (int) si;
             const uint32_t first = (uint32_t) (egeom.size() / 24), cdfOff = (uint32_t) tcdf.size();
             uint32_t ntri = 0; float invArea = 0.f;
+            int sphere = -1;
+            for (uint32_t k = 0; k < s->n_spheres; ++k) if (shape >= 0 && s->spheres[k].shape == shape) sphere = (int) k;
+            if (sphere >= 0) {                                                                      // sphere.cpp:128: m_invSurfaceArea
+                const uint32_t tag = PPG_SPHERE_BIT | (uint32_t) sphere; const float r = s->spheres[sphere].radius;
+                invArea = 1 / (4 * 3.14159265358979323846f * r * r);
+                memcpy(&einfo[4 * e], &tag, 4); memcpy(&einfo[4 * e + 1], &ntri, 4); einfo[4 * e + 2] = invArea; memcpy(&einfo[4 * e + 3], &cdfOff, 4);
+                ecdf.push_back(ecdf.back() + 1.0f);
+                continue;
+            }
             if (shape >= 0) {
                 const ppg_shape &sh = s->shapes[shape];
                 if ((uint64_t) sh.first_triangle + sh.n_triangles > nt) return fail(PPG_ERR_INVALID_ARGUMENT, "shape triangle range out of bounds");
@@ -561,6 +573,20 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         CK(cudaMemcpy(h->dEmitterFlags.p, eflags.data(), eflags.size() * 4, cudaMemcpyHostToDevice));
         v.emitterCdf = h->dEmitterCdf.p; v.emitterInfo = h->dEmitterInfo.p; v.emitterTriCdf = h->dEmitterTriCdf.p; v.emitterGeom = h->dEmitterGeom.p; v.emitterFlags = h->dEmitterFlags.p;
         v.emitterNormalization = norm; h->nRealEmitters = s->n_emitters;
+    }
+    {   // analytic spheres
+        std::vector<float> sph(8 * (size_t) std::max<uint32_t>(s->n_spheres, 1), 0.f);
+        for (uint32_t k = 0; k < s->n_spheres; ++k) {
+            const ppg_sphere &sp = s->spheres[k];
+            if (sp.shape < 0 || (uint32_t) sp.shape >= s->n_shapes || !(sp.radius > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "sphere: bad shape index or radius");
+            float *o = &sph[8 * (size_t) k];
+            o[0] = sp.center[0]; o[1] = sp.center[1]; o[2] = sp.center[2]; o[3] = sp.radius;
+            const int32_t bs = s->shapes[sp.shape].bsdf, em = s->shapes[sp.shape].emitter; const uint32_t fl = sp.flip_normals ? 1u : 0u;
+            memcpy(&o[4], &bs, 4); memcpy(&o[5], &em, 4); memcpy(&o[6], &fl, 4);
+        }
+        CK(h->dSpheres.alloc(sph.size() / 4));
+        CK(cudaMemcpy(h->dSpheres.p, sph.data(), sph.size() * 4, cudaMemcpyHostToDevice));
+        v.spheres = h->dSpheres.p; v.nSpheres = s->n_spheres;
     }
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
     const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + PPG_BSDF_F4 * s->n_bsdfs + v.nEmitters + 2 * std::max<uint32_t>(v.nGroups, 1));

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
             bool cont = found;                                                     // miss: no environment emitter in scope (GP:1902-1914)
             Its its;
             if (cont) {
-                fill_its(sc, hit, d, its);
+                fill_its(sc, hit, o, d, its);
                 // emitted radiance: primary hit via EEmittedRadiance (GP:1917-1919), later hits via the `value`
                 // returned by rayIntersectAndLookForEmitter (GP:2078-2091; miWeight(woPdf, 0) == 1)
                 float3 Lhit = f3(0, 0, 0);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                         const float4 r = sc.radiance(its.emitter);
                         Lhit = thr * f3(r.x, r.y, r.z);
                         if (NEE && !FIRST && P.doNee && !(prevSlot >> 31)) {            // MIS against light sampling, GP:2084-2088
-                            const float emitterPdf = pdf_emitter_direct(sc.g, its.emitter, prevRefN, d, its.shN, hit.t);
+                            const float emitterPdf = pdf_emitter_direct(sc.g, its.emitter, o, prevRefN, d, its.shN, hit.t);
                             Lhit = Lhit * mi_weight(prevWoPdf, emitterPdf);
                         }
                         Li = Li + Lhit;

@@ -99,6 +99,27 @@ def cbox_rough_glass(cbox: SceneDesc) -> SceneDesc:
     return sc
 
 
+def cbox_with_analytic_spheres(cbox: SceneDesc) -> SceneDesc:
+    """CBOX plus three analytic spheres (src/shapes/sphere.cpp): a white diffuse ball on the floor, a small emitting ball (light
+    sampling from outside: uniform cone) and a huge inward-facing emitting shell around everything like spaceship.xml's
+    (light sampling from inside: uniform sphere).  The scene box grows to the shell (Sphere::getAABB)."""
+    import copy
+    from .scene import make_sphere, BSDF_DIFFUSE
+    sc = copy.copy(cbox)
+    ns, ne = len(sc.shapes), len(sc.area_radiance)
+    base = _pad_bsdfs(sc.bsdfs); nb = len(base)
+    sc.bsdfs = np.concatenate([base, _make_bsdf(BSDF_DIFFUSE, 0, (0, 0, 0))[None]]).astype(np.float32)        # emitters without a BSDF are black (shape.cpp)
+    sc.bsdf_names = list(sc.bsdf_names) + ["__black"]
+    nt = len(sc.indices)
+    sc.shapes = np.concatenate([sc.shapes, np.array([[nt, 0, 1, -1, 0, 0, 0, 0], [nt, 0, nb, ne, 0, 0, 0, 0], [nt, 0, nb, ne + 1, 0, 0, 0, 0]], np.int32)])
+    sc.area_radiance = np.concatenate([sc.area_radiance, np.array([[12.0, 10.0, 6.0], [0.08, 0.1, 0.14]], np.float32)])
+    sc.spheres = np.stack([make_sphere((420.0, 60.0, 120.0), 60.0, ns), make_sphere((150.0, 400.0, 250.0), 25.0, ns + 1),
+                           make_sphere((278.0, 273.0, -100.0), 1500.0, ns + 2, True)])
+    sc.aabb_min = np.minimum(sc.aabb_min, np.float32([278, 273, -100]) - np.float32(1500)).astype(np.float32)
+    sc.aabb_max = np.maximum(sc.aabb_max, np.float32([278, 273, -100]) + np.float32(1500)).astype(np.float32)
+    return sc
+
+
 def cbox_rough_metal(cbox: SceneDesc) -> SceneDesc:
     """CBOX whose boxes are rough conductors: the small box GGX alpha 0.1 with the eta/k of spaceship.xml's "RoughAluminium",
     the large box Beckmann alpha 0.3 -- glossy BSDFs are guided (ESmooth) and take part in light sampling."""

@@ -41,6 +41,10 @@ class PpgShape(C.Structure):
                 ("has_normals", C.c_uint32), ("has_uvs", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
+class PpgSphere(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("radius", C.c_float), ("shape", C.c_int32), ("flip_normals", C.c_int32)]
+
+
 class PpgCamera(C.Structure):
     _fields_ = [("to_world", C.c_float * 16), ("x_fov_deg", C.c_float), ("near_clip", C.c_float), ("far_clip", C.c_float),
                 ("film_width", C.c_int32), ("film_height", C.c_int32)]
@@ -54,6 +58,7 @@ class PpgSceneDesc(C.Structure):
         ("indices", C.POINTER(C.c_uint32)), ("triangle_shape", C.POINTER(C.c_uint32)),
         ("shapes", C.POINTER(PpgShape)), ("bsdfs", C.POINTER(PpgBsdf)), ("area_radiance", C.POINTER(C.c_float)),
         ("bsdf_tables", C.POINTER(C.c_float)), ("n_bsdf_tables", C.c_uint32),
+        ("n_spheres", C.c_uint32), ("spheres", C.POINTER(PpgSphere)),
         ("camera", PpgCamera), ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3),
     ]
 
@@ -118,6 +123,8 @@ class SceneArrays:
         tables = getattr(scene, "bsdf_tables", None)
         self.tables = np.ascontiguousarray(tables if tables is not None and len(tables) else np.zeros((0, 100)), np.float32)
         self.radiance = np.ascontiguousarray(scene.area_radiance, np.float32)
+        sph = getattr(scene, "spheres", None)
+        self.spheres = np.ascontiguousarray(sph if sph is not None and len(sph) else np.zeros((0, 6)), np.float32)   # (K,6) == ppg_sphere
         d = PpgSceneDesc()
         d.n_vertices = len(self.positions); d.n_triangles = len(self.indices); d.n_shapes = len(self.shapes)
         d.n_bsdfs = len(self.bsdfs); d.n_emitters = len(self.radiance)
@@ -128,6 +135,8 @@ class SceneArrays:
         d.area_radiance = _fp(self.radiance)
         d.bsdf_tables = _fp(self.tables) if len(self.tables) else None
         d.n_bsdf_tables = len(self.tables)
+        d.n_spheres = len(self.spheres)
+        d.spheres = self.spheres.ctypes.data_as(C.POINTER(PpgSphere)) if len(self.spheres) else None
         cam = PpgCamera()
         m = np.ascontiguousarray(scene.cam_to_world, np.float32).reshape(16)
         for i in range(16):

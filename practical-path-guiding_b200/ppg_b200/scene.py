@@ -361,6 +361,7 @@ class SceneDesc:
     integrator: dict = field(default_factory=dict)  # XML name -> string value
     bsdf_names: list = field(default_factory=list)
     bsdf_tables: np.ndarray = None   # (T,100) f32 rough-transmittance tables referenced by roughplastic materials
+    spheres: np.ndarray = None       # (K,6) f32 view of ppg_sphere: center[3], radius, shape (int bits), flip_normals (int bits)
 
     def with_film(self, w: int, h: int) -> "SceneDesc":
         """Same scene, different film size (x fov re-resolved only when the aspect
@@ -376,7 +377,8 @@ class SceneDesc:
             cam=np.array([self.x_fov_deg, self.near_clip, self.far_clip, self.film_width, self.film_height], np.float64),
             aabb=np.stack([self.aabb_min, self.aabb_max]).astype(np.float32),
             integrator=np.array([f"{k}={v}" for k, v in self.integrator.items()]),
-            bsdf_names=np.array(self.bsdf_names), bsdf_tables=(self.bsdf_tables if self.bsdf_tables is not None else np.zeros((0, 100), np.float32)))
+            bsdf_names=np.array(self.bsdf_names), bsdf_tables=(self.bsdf_tables if self.bsdf_tables is not None else np.zeros((0, 100), np.float32)),
+            spheres=(self.spheres if self.spheres is not None else np.zeros((0, 6), np.float32)))
 
     @staticmethod
     def load(path) -> "SceneDesc":
@@ -386,7 +388,15 @@ class SceneDesc:
         return SceneDesc(d["positions"], d["normals"], d["uvs"], d["indices"], d["triangle_shape"], d["shapes"],
                          d["bsdfs"], d["area_radiance"], d["cam_to_world"], float(cam[0]), float(cam[1]), float(cam[2]),
                          int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist(),
-                         d["bsdf_tables"] if "bsdf_tables" in d.files else None)
+                         d["bsdf_tables"] if "bsdf_tables" in d.files else None, d["spheres"] if "spheres" in d.files else None)
+
+
+def make_sphere(center, radius, shape, flip_normals=False):
+    """One ppg_sphere (include/ppg.h) as 6 floats."""
+    r = np.zeros(6, np.float32)
+    r[:3] = center; r[3] = radius
+    r[4:6] = np.array([shape, 1 if flip_normals else 0], np.int32).view(np.float32)
+    return r
 
 
 def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0), alpha=0.1, distribution=0):
@@ -580,6 +590,7 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
     P_all, N_all, UV_all, I_all, TS_all, shapes, radiance = [], [], [], [], [], [], []
     voff = 0; toff = 0
     black = grey = None
+    sphere_list = []
     for sh in root.findall("shape"):
         typ = sh.attrib["type"]
         props = _prop_children(sh)
@@ -592,6 +603,18 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
                                     props.get("faceNormals", "false") == "true", props.get("flipNormals", "false") == "true")
         elif typ == "rectangle":
             P, N, UV, I = _rectangle(to_world)
+        elif typ == "sphere":           # src/shapes/sphere.cpp:107-132: toWorld's scale folds into the radius
+            ctr = np.zeros(3)
+            for c in sh.findall("point"):
+                if c.attrib.get("name") == "center":
+                    ctr = np.array([float(c.attrib.get(k, 0)) for k in "xyz"])
+            radius = float(props.get("radius", 1.0)) * np.linalg.norm(to_world[:3, 0])
+            rot = to_world[:3, :3] / np.linalg.norm(to_world[:3, 0])
+            if not np.allclose(rot, np.eye(3), atol=1e-6):
+                raise NotImplementedError("sphere: toWorld must be translation + uniform scale")
+            center = to_world[:3, :3] @ ctr + to_world[:3, 3]
+            sphere_list.append([center, radius, len(shapes), props.get("flipNormals", "false") == "true"])
+            P = np.zeros((0, 3), np.float32); N = None; UV = None; I = np.zeros((0, 3), np.uint32)
         else:
             raise NotImplementedError(f"shape '{typ}' is outside the round-1 scope")
         bsdf_idx = None
@@ -632,11 +655,14 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
     aabb_min = P.min(axis=0).astype(np.float64); aabb_max = P.max(axis=0).astype(np.float64)
     cam_pos = cam_to_world[:3, 3]
     aabb_min = np.minimum(aabb_min, cam_pos); aabb_max = np.maximum(aabb_max, cam_pos)
+    for c, r, _, _ in sphere_list:         # Sphere::getAABB, sphere.cpp:152-157
+        aabb_min = np.minimum(aabb_min, np.float32(c) - np.float32(r)); aabb_max = np.maximum(aabb_max, np.float32(c) + np.float32(r))
     return SceneDesc(
         positions=P, normals=np.concatenate(N_all).astype(np.float32), uvs=np.concatenate(UV_all).astype(np.float32),
         indices=np.concatenate(I_all).astype(np.uint32), triangle_shape=np.concatenate(TS_all).astype(np.uint32),
         shapes=np.asarray(shapes, np.int64).astype(np.int32), bsdfs=np.asarray(bsdf_table, np.float32).reshape(-1, 24),
         bsdf_tables=np.asarray(_TABLES, np.float32).reshape(-1, 100),
+        spheres=np.asarray([make_sphere(c, r, si, fl) for c, r, si, fl in sphere_list], np.float32).reshape(-1, 6),
         area_radiance=np.asarray(radiance, np.float32).reshape(-1, 3), cam_to_world=cam_to_world.astype(np.float32),
         x_fov_deg=float(xfov), near_clip=near, far_clip=far, film_width=W, film_height=H,
         aabb_min=aabb_min.astype(np.float32), aabb_max=aabb_max.astype(np.float32), integrator=integrator, bsdf_names=names)

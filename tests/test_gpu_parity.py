@@ -341,3 +341,54 @@ def test_rough_dielectric_matches_oracle(extra):
     for a, b in zip(st["iterations"], ost["iterations"]):
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
         assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(nee="kickstart", spatialFilter="stochastic", directionalFilter="box")])
+def test_analytic_spheres_match_oracle(extra):
+    """CBOX + analytic spheres (sphere.cpp): double-precision ray/sphere quadratic, re-projected hit point, frame from dpdu;
+    emitting spheres sampled by uniform cone (reference point outside) and uniform sphere (inside the inward-facing shell)."""
+    from ppg_b200.builtin_scenes import cbox_with_analytic_spheres
+    sc = cbox_with_analytic_spheres(load_cbox(128))
+    props = dict(dict(sc.integrator, budget="60"), **extra)
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert relmse(img, ref) <= 1e-4, relmse(img, ref)
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 1e-3 * ost["total_vertices"]
+    for a, b in zip(st["iterations"], ost["iterations"]):
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
+        assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-3)
+
+
+@pytest.mark.gpu
+def test_spaceship_matches_oracle():
+    """BASELINE config 4's scene (spaceship-improved.xml: 457 560 triangles through the BVH walk, twosided rough plastics / conductors,
+    GGX glass with alpha 0.01, rectangle emitters, the radius-100 emitting shell), at 160x90 and 31 spp.  Deterministic options
+    (no sampling-fraction loss, nearest filters) so that the comparison with the multi-threaded oracle is sample by sample."""
+    from common import load_fixture_scene
+    sc = load_fixture_scene("spaceship-improved").with_film(160, 90)
+    props = dict(sc.integrator, budget="31", bsdfSamplingFractionLoss="none", spatialFilter="nearest", directionalFilter="nearest")
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert np.isfinite(img).all()
+    assert relmse(img, ref) <= 1e-3, relmse(img, ref)
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 2e-3 * ost["total_vertices"]
+    for a, b in zip(st["iterations"], ost["iterations"]):
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 2
+        assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=2e-3)
+
+
+@pytest.mark.gpu
+def test_spaceship_improved_settings_statistics():
+    """Same scene with the XML's own settings (inversevar / stochastic / box / kl): the Adam replay order differs from the
+    multi-threaded oracle's, so the comparison is statistical -- image mean, per-iteration tree statistics."""
+    from common import load_fixture_scene
+    sc = load_fixture_scene("spaceship-improved").with_film(160, 90)
+    props = dict(sc.integrator, budget="63")
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert np.isfinite(img).all()
+    assert abs(img.mean() - ref.mean()) <= 0.03 * ref.mean(), (img.mean(), ref.mean())
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 0.02 * ost["total_vertices"]
+    for a, b in list(zip(st["iterations"], ost["iterations"]))[:-1]:
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= max(2, 0.05 * b["s_tree_leaves"])

@@ -10,6 +10,7 @@ Writes
   scenes/cbox-improved.npz   same for cbox-improved.xml
   scenes/cbox-plastic.npz    CBOX with rough-plastic boxes; carries the per-material rough-transmittance tables reduced from
                              /root/reference/mitsuba/data/microfacet/{beckmann,ggx}.dat (ppg_b200/rtrans.py)
+  scenes/spaceship-improved.npz   flat-array form of /root/reference/scenes/spaceship/spaceship-improved.xml (457 560 triangles + 1 sphere)
   tests/golden/cbox_log_stats.json   known-answer statistics parsed from the logs embedded
                                       in the reference's golden EXRs (hdrfilm attachLog)
 """
@@ -69,9 +70,17 @@ def plastic():
     print("cbox-plastic", sc.bsdf_names[-2:], "fdr", sc.bsdfs[-2:, 19], "ssw", sc.bsdfs[-2:, 20], "T(1)", sc.bsdf_tables[:, -1], "T(0)", sc.bsdf_tables[:, 0])
 
 
+def spaceship():
+    sc = S.load_mitsuba_xml(f"{REF}/scenes/spaceship/spaceship-improved.xml")
+    sc.save(os.path.join(ROOT, "scenes", "spaceship-improved.npz"))
+    print("spaceship", "tris", len(sc.indices), "spheres", sc.spheres, "bsdfs", sc.bsdf_names, sc.integrator)
+
+
 def main():
     if sys.argv[1:] == ["plastic"]:
         return plastic()
+    if sys.argv[1:] == ["spaceship"]:
+        return spaceship()
     os.makedirs(os.path.join(ROOT, "scenes"), exist_ok=True)
     cie = S.extract_cie_tables()
     assert len(cie["x"]) == 471
@@ -91,6 +100,7 @@ def main():
         json.dump(stats, f, indent=1)
     print(json.dumps(stats["cbox"]["iterations"][:2], indent=1))
     plastic()
+    spaceship()
 
 
 if __name__ == "__main__":

@@ -42,4 +42,4 @@ for lib in a.libs.split(","):
             ms = st["render_device_ms"]; v = st["total_vertices"] / ms / 1e3
             best = max(best or 0, v)
         km = st.get("kernel_ms", [])
-        print(f"{lib:40s} {sn:10s} {best:9.1f} Msamples/s  ms {ms:8.1f}  kernel_ms {[round(x, 1) for x in km]}", flush=True)
+        print(f"{lib:40s} {sn:10s} {best:9.1f} Msamples/s  ms {ms:8.1f}  kernel_ms {km}", flush=True)
