@@ -197,13 +197,78 @@ __device__ __forceinline__ bool sphere_intersect(float4 cr, float3 ro, float3 rd
     else t = (float) nearT;
     return true;
 }
+// Not inlined: the walk's two stacks and its registers stay out of the callers' frames (the tiny-scene path of the bounce
+// kernel never calls it and keeps its register allocation).
+template <class Acc>
+__device__ __noinline__ bool bvh_walk(const Acc &A_, float3 o, float3 d, float mint, float maxt, Hit &hit) {
+    // BVH walk, near child first.  A node is 2 float4 {min.xyz, bits(left)}, {max.xyz, bits(count)}; siblings are adjacent, so one
+    // 64-byte fetch brings both children's boxes.  The far child is pushed with its entry distance and skipped on pop when
+    // a closer hit has been found since.  The slab test is widened by 1 ulp-ish factors so that flat boxes and NaNs (0 * inf)
+    // never cull; results do not depend on the visiting order (ties on t go to the lower original triangle index).
+    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    auto slab = [&](const float4 n0, const float4 n1, float &tEntry) -> bool {
+        // fmaxf / fminf drop NaN operands (0 * inf when the ray lies in a box plane); widening once after the reductions equals
+        // widening every axis because x -> x -+ |x| * 1e-6 is monotone
+        float ta = (n0.x - o.x) * inv.x, tb = (n1.x - o.x) * inv.x; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
+        float nearMax = fmaxf(__int_as_float(0xff800000), ta), farMin = fminf(__int_as_float(0x7f800000), tb);
+        ta = (n0.y - o.y) * inv.y; tb = (n1.y - o.y) * inv.y; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
+        nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
+        ta = (n0.z - o.z) * inv.z; tb = (n1.z - o.z) * inv.z; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
+        nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
+        const float t0 = fmaxf(mint, nearMax - fabsf(nearMax) * 1e-6f), t1 = fminf(fminf(maxt, hit.t), farMin + fabsf(farMin) * 1e-6f);
+        tEntry = t0;
+        return t0 <= t1;
+    };
+    uint32_t stackN[PPG_BVH_STACK]; float stackT[PPG_BVH_STACK]; int sp = 0;
+    uint32_t left, count;      // the current node: children left, left+1 (count == 0) or leaf slots [left, left+count)
+    {
+        const float4 r0 = A_.bvh(0), r1 = A_.bvh(1);
+        float te;
+        if (!slab(r0, r1, te)) return false;
+        left = __float_as_uint(r0.w); count = __float_as_uint(r1.w);
+    }
+    for (;;) {
+        if (count) {
+            for (uint32_t i = left; i < left + count; ++i) {
+                const float4 A = A_.accel(3 * i), B = A_.accel(3 * i + 1), C = A_.accel(3 * i + 2);
+                float u, v, t;
+                if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
+                    const uint32_t prim = __float_as_uint(C.z);
+                    if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i; }
+                }
+            }
+        } else {
+            const float4 a0 = A_.bvh(2 * left), a1 = A_.bvh(2 * left + 1), b0 = A_.bvh(2 * left + 2), b1 = A_.bvh(2 * left + 3);
+            float ta, tb;
+            const bool ha = slab(a0, a1, ta), hb = slab(b0, b1, tb);
+            if (ha && hb) {
+                const bool aFirst = ta <= tb;
+                const float4 f0 = aFirst ? b0 : a0, f1 = aFirst ? b1 : a1, n0 = aFirst ? a0 : b0, n1 = aFirst ? a1 : b1;
+                stackN[sp] = __float_as_uint(f0.w) | (__float_as_uint(f1.w) << 28); stackT[sp] = aFirst ? tb : ta; ++sp;
+                left = __float_as_uint(n0.w); count = __float_as_uint(n1.w);
+                continue;
+            }
+            if (ha) { left = __float_as_uint(a0.w); count = __float_as_uint(a1.w); continue; }
+            if (hb) { left = __float_as_uint(b0.w); count = __float_as_uint(b1.w); continue; }
+        }
+        bool popped = false;
+        while (sp > 0) {
+            --sp;
+            if (stackT[sp] <= hit.t) { left = stackN[sp] & 0x0fffffffu; count = stackN[sp] >> 28; popped = true; break; }
+        }
+        if (!popped) break;
+    }
+    return hit.prim != 0xFFFFFFFFu;
+}
 template <class Acc> __device__ __forceinline__ bool tri_scene_intersect(const Acc &A_, float3 o, float3 d, float mint, float maxt, Hit &hit);
 
 // Nearest hit in [mint, maxt]; ties on t go to the lower ORIGINAL triangle index so that the
 // result does not depend on the traversal order (same rule as the oracle).  Spheres are tested after the triangles.
-template <class Acc>
+// SPHERES == false: the scene holds triangles only (host-checked; the sphere code compiles away).
+template <bool SPHERES, class Acc>
 __device__ __forceinline__ bool bvh_intersect(const Acc &A_, float3 o, float3 d, float mint, float maxt, Hit &hit) {
     bool found = tri_scene_intersect(A_, o, d, mint, maxt, hit);
+    if (!SPHERES) return found;
     const SceneView &sc = A_.g;
     for (uint32_t k = 0; k < sc.nSpheres; ++k) {
         float t;
@@ -269,44 +334,7 @@ __device__ __forceinline__ bool tri_scene_intersect(const Acc &A_, float3 o, flo
         }
         return hit.prim != 0xFFFFFFFFu;
     }
-    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    uint32_t stack[PPG_BVH_STACK]; int sp = 0; uint32_t node = 0;
-    for (;;) {
-        const float4 n0 = A_.bvh(2 * node), n1 = A_.bvh(2 * node + 1);
-        float t0 = mint, t1 = fminf(maxt, hit.t);
-        bool miss = false;
-        {
-            float ta = (n0.x - o.x) * inv.x, tb = (n1.x - o.x) * inv.x; if (ta > tb) { float s = ta; ta = tb; tb = s; }
-            if (ta == ta) t0 = fmaxf(t0, ta - fabsf(ta) * 1e-6f);
-            if (tb == tb) t1 = fminf(t1, tb + fabsf(tb) * 1e-6f);
-            ta = (n0.y - o.y) * inv.y; tb = (n1.y - o.y) * inv.y; if (ta > tb) { float s = ta; ta = tb; tb = s; }
-            if (ta == ta) t0 = fmaxf(t0, ta - fabsf(ta) * 1e-6f);
-            if (tb == tb) t1 = fminf(t1, tb + fabsf(tb) * 1e-6f);
-            ta = (n0.z - o.z) * inv.z; tb = (n1.z - o.z) * inv.z; if (ta > tb) { float s = ta; ta = tb; tb = s; }
-            if (ta == ta) t0 = fmaxf(t0, ta - fabsf(ta) * 1e-6f);
-            if (tb == tb) t1 = fminf(t1, tb + fabsf(tb) * 1e-6f);
-            miss = t0 > t1;
-        }
-        if (!miss) {
-            const uint32_t left = __float_as_uint(n0.w), count = __float_as_uint(n1.w);
-            if (count) {
-                for (uint32_t i = left; i < left + count; ++i) {
-                    const float4 A = A_.accel(3 * i), B = A_.accel(3 * i + 1), C = A_.accel(3 * i + 2);
-                    float u, v, t;
-                    if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
-                        const uint32_t prim = __float_as_uint(C.z);
-                        if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i; }
-                    }
-                }
-            } else {
-                node = left; stack[sp++] = left + 1;
-                continue;
-            }
-        }
-        if (sp == 0) break;
-        node = stack[--sp];
-    }
-    return hit.prim != 0xFFFFFFFFu;
+    return bvh_walk(A_, o, d, mint, maxt, hit);
 }
 
 // Intersection record (render/shape.h:36), the fields the path uses
@@ -318,9 +346,9 @@ struct Its {
 };
 
 // fillIntersectionRecord (render/skdtree.h:343-428) + computeShadingFrame (libcore/util.cpp:603-608)
-template <class Acc>
+template <bool SPHERES, class Acc>
 __device__ __forceinline__ void fill_its(const Acc &A_, const Hit &h, float3 o, float3 d, Its &its) {
-    if (h.prim & PPG_SPHERE_BIT) {        // Sphere::fillIntersectionRecord (src/shapes/sphere.cpp:209-255), identity rotation
+    if (SPHERES && (h.prim & PPG_SPHERE_BIT)) {        // Sphere::fillIntersectionRecord (src/shapes/sphere.cpp:209-255), identity rotation
         const uint32_t k = h.prim & ~PPG_SPHERE_BIT;
         const float4 cr = __ldg(&A_.g.spheres[2 * k]), mt = __ldg(&A_.g.spheres[2 * k + 1]);
         const float3 c = f3(cr.x, cr.y, cr.z);
@@ -1015,7 +1043,7 @@ __device__ __forceinline__ void coordinate_system(float3 a, float3 &b, float3 &c
 // Scene::sampleAttenuatedEmitterDirect (scene.cpp:876-897) -> AreaLight::sampleDirect (area.cpp:158-173) -> Shape::sampleDirect
 // (shape.cpp:102-115) -> TriMesh::samplePosition (trimesh.cpp:412-423) -> Triangle::sample (libcore/triangle.cpp:24-59);
 // visibility (Scene::evalTransmittance, scene.cpp:619-679) is tested by the caller.  Returns false when the sample carries nothing.
-template <class Acc>
+template <bool SPHERES, class Acc>
 __device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref, float3 refN, float sx, float sy, DirectSample &out, float &dist) {
     const SceneView &sc = A_.g;        // the emitter tables stay in HBM (read-only path)
     const uint32_t ei = cdf_sample(sc.emitterCdf, sc.nEmitters + 1, sx);
@@ -1024,7 +1052,7 @@ __device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref,
     sx = (sx - c0) / (c1 - c0);
     const float4 info = sc.emitterInfo[ei];
     const uint32_t first = __float_as_uint(info.x), nTris = __float_as_uint(info.y), cdfOff = __float_as_uint(info.w);
-    if (first & PPG_SPHERE_BIT) {          // Sphere::sampleDirect, src/shapes/sphere.cpp:286-355
+    if (SPHERES && (first & PPG_SPHERE_BIT)) {          // Sphere::sampleDirect, src/shapes/sphere.cpp:286-355
         const uint32_t k = first & ~PPG_SPHERE_BIT;
         const float4 cr = __ldg(&sc.spheres[2 * k]), mt = __ldg(&sc.spheres[2 * k + 1]);
         const float3 c = f3(cr.x, cr.y, cr.z);
@@ -1103,10 +1131,11 @@ __device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref,
     return true;
 }
 // Scene::pdfEmitterDirect (scene.cpp:949-952) for an emitter hit found by BSDF / guiding sampling
+template <bool SPHERES>
 __device__ __forceinline__ float pdf_emitter_direct(const SceneView &sc, int emitter, float3 ref, float3 refN, float3 d, float3 n, float dist) {
     if (!(dot(d, refN) >= 0.f && dot(d, n) < 0.f)) return 0.0f;
     const float4 info = sc.emitterInfo[emitter];
-    if (__float_as_uint(info.x) & PPG_SPHERE_BIT) {                                            // Sphere::pdfDirect, sphere.cpp:357-392
+    if (SPHERES && (__float_as_uint(info.x) & PPG_SPHERE_BIT)) {                                            // Sphere::pdfDirect, sphere.cpp:357-392
         const float4 cr = __ldg(&sc.spheres[2 * (__float_as_uint(info.x) & ~PPG_SPHERE_BIT)]);
         const float3 refToCenter = f3(cr.x, cr.y, cr.z) - ref;
         const float invRefDist = 1.0f / sqrtf(dot(refToCenter, refToCenter));

@@ -20,7 +20,7 @@ namespace ppg {
 #define PPG_MIN_BLOCKS 4               // resident blocks per SM the bounce kernel is compiled for (register cap)
 #endif
 #ifndef PPG_MIN_BLOCKS_GLOSSY
-#define PPG_MIN_BLOCKS_GLOSSY 3        // same for scenes with non-diffuse BSDFs (DELTA variants: microfacet code needs more registers)
+#define PPG_MIN_BLOCKS_GLOSSY 4        // same for scenes with non-diffuse BSDFs (DELTA variants; measured on the rough CBOX variants: 4 > 3 > 2)
 #endif
 #define PPG_MAX_VERTICES 32         // MAX_NUM_VERTICES, GP:1771
 #define PPG_INVALID 0xFFFFFFFFu
@@ -138,11 +138,11 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
         if (alive) {
             ++raysLocal;
             Hit hit;
-            const bool found = bvh_intersect(sc, o, d, mint, maxt, hit);
+            const bool found = bvh_intersect<DELTA>(sc, o, d, mint, maxt, hit);
             bool cont = found;                                                     // miss: no environment emitter in scope (GP:1902-1914)
             Its its;
             if (cont) {
-                fill_its(sc, hit, o, d, its);
+                fill_its<DELTA>(sc, hit, o, d, its);
                 // emitted radiance: primary hit via EEmittedRadiance (GP:1917-1919), later hits via the `value`
                 // returned by rayIntersectAndLookForEmitter (GP:2078-2091; miWeight(woPdf, 0) == 1)
                 float3 Lhit = f3(0, 0, 0);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                         const float4 r = sc.radiance(its.emitter);
                         Lhit = thr * f3(r.x, r.y, r.z);
                         if (NEE && !FIRST && P.doNee && !(prevSlot >> 31)) {            // MIS against light sampling, GP:2084-2088
-                            const float emitterPdf = pdf_emitter_direct(sc.g, its.emitter, o, prevRefN, d, its.shN, hit.t);
+                            const float emitterPdf = pdf_emitter_direct<DELTA>(sc.g, its.emitter, o, prevRefN, d, its.shN, hit.t);
                             Lhit = Lhit * mi_weight(prevWoPdf, emitterPdf);
                         }
                         Li = Li + Lhit;
@@ -217,11 +217,11 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                     // ---- luminaire sampling, GP:1964-2021
                     const float ex = rng.next1D(), ey = rng.next1D();
                     DirectSample ds; float dist;
-                    if (sample_emitter_direct(sc, its.p, refN, ex, ey, ds, dist)) {
+                    if (sample_emitter_direct<DELTA>(sc, its.p, refN, ex, ey, ds, dist)) {
                         // Scene::evalTransmittance: shadow ray, epsilon scaled without the clamp (skdtree.cpp:154-158)
                         const float smint = PPG_EPSILON * fmaxf(fmaxf(fabsf(its.p.x), fabsf(its.p.y)), fabsf(its.p.z));
                         Hit sh;      // (shadow rays are not path vertices: not counted in the samples metric)
-                        if (!bvh_intersect(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh)) {
+                        if (!bvh_intersect<DELTA>(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh)) {
                             const float3 dl = its.toLocal(ds.d);
                             if (!P.strictNormals || dot(its.geoN, ds.d) * dl.z > 0.f) {
                                 const float3 bsdfVal = bsdf_eval(bsdf, its.wi, dl);
@@ -794,20 +794,24 @@ __global__ void __launch_bounds__(128) adam_seq_kernel(MaintParams M, const floa
         int iter = (int) st[0]; float m1 = st[1], m2 = st[2], variable = st[3], batchAcc = st[4], batchGrad = st[5];
         const int iter0 = iter;
         const uint32_t o = offset[leaf];
+        // beta^iter as running double-precision products (the reference evaluates std::pow(float, int) in double, GP:98-99);
+        // a pow() per step would sit on the per-leaf sequential chain
+        double b1pow = pow((double) 0.9f, (double) iter), b2pow = pow((double) 0.999f, (double) iter);
         for (uint32_t k = 0; k < n; ++k) {
             const float4 a = recA[o + k]; const float2 b = recB[o + k];
             const float product = a.y, woPdf = a.z, bsdfPdf = a.w, dTreePdf = b.x, weight = b.y;
             const float f = logistic(variable);
             const float mixPdf = f * bsdfPdf + (1.f - f) * dTreePdf;
-            const float ratio = powf(product / mixPdf, ratioPower);
+            const float r_ = product / mixPdf;
+            const float ratio = ratioPower == 1.f ? r_ : (ratioPower == 2.f ? r_ * r_ : powf(r_, ratioPower));
             const float dLoss_df = -ratio / woPdf * (bsdfPdf - dTreePdf);
             const float dLoss_dv = dLoss_df * (f * (1.f - f));
             const float g = 0.01f * variable + dLoss_dv;
             batchGrad += g * weight; batchAcc += weight;
             if (batchAcc > 1.0f) {                      // batchSize = 1, GP:89
                 const float grad = batchGrad / batchAcc;
-                ++iter;
-                const float lr = 0.01f * sqrtf(1.f - powf(0.999f, (float) iter)) / (1.f - powf(0.9f, (float) iter));
+                ++iter; b1pow *= (double) 0.9f; b2pow *= (double) 0.999f;
+                const float lr = 0.01f * sqrtf(1.f - (float) b2pow) / (1.f - (float) b1pow);
                 m1 = 0.9f * m1 + (1.f - 0.9f) * grad;
                 m2 = 0.999f * m2 + (1.f - 0.999f) * grad * grad;
                 variable -= lr * m1 / (sqrtf(m2) + 1e-08f);

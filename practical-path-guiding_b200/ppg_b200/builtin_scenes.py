@@ -113,7 +113,7 @@ def cbox_with_analytic_spheres(cbox: SceneDesc) -> SceneDesc:
     nt = len(sc.indices)
     sc.shapes = np.concatenate([sc.shapes, np.array([[nt, 0, 1, -1, 0, 0, 0, 0], [nt, 0, nb, ne, 0, 0, 0, 0], [nt, 0, nb, ne + 1, 0, 0, 0, 0]], np.int32)])
     sc.area_radiance = np.concatenate([sc.area_radiance, np.array([[12.0, 10.0, 6.0], [0.08, 0.1, 0.14]], np.float32)])
-    sc.spheres = np.stack([make_sphere((420.0, 60.0, 120.0), 60.0, ns), make_sphere((150.0, 400.0, 250.0), 25.0, ns + 1),
+    sc.spheres = np.stack([make_sphere((415.0, 60.0, 135.0), 60.0, ns), make_sphere((150.0, 400.0, 250.0), 25.0, ns + 1),
                            make_sphere((278.0, 273.0, -100.0), 1500.0, ns + 2, True)])
     sc.aabb_min = np.minimum(sc.aabb_min, np.float32([278, 273, -100]) - np.float32(1500)).astype(np.float32)
     sc.aabb_max = np.maximum(sc.aabb_max, np.float32([278, 273, -100]) + np.float32(1500)).astype(np.float32)

@@ -13,11 +13,11 @@ def load_cbox(size=None, improved=False):
     return sc
 
 
-def load_fixture_scene(name, size=None):
+def load_fixture_scene(name, size=None):  # size None or 0: the XML film size
     """scenes/<name>.npz written by tools/make_fixtures.py."""
     from ppg_b200.scene import SceneDesc
     sc = SceneDesc.load(os.path.join(ROOT, "scenes", name + ".npz"))
-    return sc.with_film(size, size) if size is not None else sc
+    return sc.with_film(size, size) if size else sc
 
 
 def relmse(img, ref):

@@ -14,7 +14,7 @@ from common import load_cbox, load_fixture_scene
 
 def scene(name):
     from ppg_b200 import builtin_scenes as B
-    if name == "diffuse": return load_cbox(a.size)
+    if name == "diffuse": return load_cbox(a.size or None)
     if name == "plastic": return load_fixture_scene("cbox-plastic", a.size)
     if name == "metal": return B.cbox_rough_metal(load_cbox(a.size))
     if name == "glass": return B.cbox_rough_glass(load_cbox(a.size))
