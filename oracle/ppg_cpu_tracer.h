@@ -493,7 +493,7 @@ static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
     return f3(px, py, z);
 }
 struct BsdfSample { F3 wo; float eta; bool delta; };
-static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK || b.type == PPG_BSDF_ROUGHCONDUCTOR || b.type == PPG_BSDF_ROUGHPLASTIC || b.type == PPG_BSDF_ROUGHDIELECTRIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
+static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK || b.type == PPG_BSDF_ROUGHCONDUCTOR || b.type == PPG_BSDF_ROUGHPLASTIC || b.type == PPG_BSDF_ROUGHDIELECTRIC || b.type == PPG_BSDF_PLASTIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
 static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC || b.type == PPG_BSDF_ROUGHDIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
@@ -809,6 +809,41 @@ static inline F3 roughdielectric_sample(const ppg_bsdf &b, F3 wi, float sx, floa
     pdf *= std::fabs(dwh_dwo);
     return weight;
 }
+// ---- plastic (src/bsdfs/plastic.cpp): delta reflection off the coat + diffuse base; eval / pdf in the solid-angle measure see the diffuse part only
+static inline F3 plastic_diffuse(const ppg_bsdf &b) {                                                    // plastic.cpp:266-271
+    F3 diff = f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+    if (b.flags & PPG_BSDF_FLAG_NONLINEAR) return f3(diff.x / (1.0f - diff.x * b.fdr_int), diff.y / (1.0f - diff.y * b.fdr_int), diff.z / (1.0f - diff.z * b.fdr_int));
+    return diff * (1.0f / (1 - b.fdr_int));
+}
+static inline float plastic_prob_specular(const ppg_bsdf &b, float Fi) {                                 // plastic.cpp:292-294
+    return (Fi * b.specular_sampling_weight) / (Fi * b.specular_sampling_weight + (1 - Fi) * (1 - b.specular_sampling_weight));
+}
+static inline F3 plastic_eval(const ppg_bsdf &b, F3 wi, F3 wo) {                                         // plastic.cpp:245-278
+    if (wo.z <= 0 || wi.z <= 0) return f3(0, 0, 0);
+    float ct; const float Fi = fresnel_dielectric_ext(wi.z, ct, b.eta[0]), Fo = fresnel_dielectric_ext(wo.z, ct, b.eta[0]);
+    const float invEta2 = 1 / (b.eta[0] * b.eta[0]);
+    return plastic_diffuse(b) * ((kInvPi * wo.z) * invEta2 * (1 - Fi) * (1 - Fo));
+}
+static inline float plastic_pdf(const ppg_bsdf &b, F3 wi, F3 wo) {                                       // plastic.cpp:280-308
+    if (wo.z <= 0 || wi.z <= 0) return 0.0f;
+    float ct; const float Fi = fresnel_dielectric_ext(wi.z, ct, b.eta[0]);
+    return (kInvPi * wo.z) * (1 - plastic_prob_specular(b, Fi));
+}
+static inline F3 plastic_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, F3 &wo, bool &delta, float &pdf) {   // plastic.cpp:374-441
+    pdf = 0; delta = false;
+    if (wi.z <= 0) return f3(0, 0, 0);
+    float ct; const float Fi = fresnel_dielectric_ext(wi.z, ct, b.eta[0]);
+    const float probSpecular = plastic_prob_specular(b, Fi);
+    if (sx < probSpecular) {
+        delta = true; wo = f3(-wi.x, -wi.y, wi.z); pdf = probSpecular;
+        return (f3(b.specular_reflectance[0], b.specular_reflectance[1], b.specular_reflectance[2]) * Fi) * (1.0f / probSpecular);
+    }
+    wo = square_to_cosine_hemisphere((sx - probSpecular) / (1 - probSpecular), sy);
+    const float Fo = fresnel_dielectric_ext(wo.z, ct, b.eta[0]);
+    const float invEta2 = 1 / (b.eta[0] * b.eta[0]);
+    pdf = (1 - probSpecular) * (kInvPi * wo.z);
+    return plastic_diffuse(b) * (invEta2 * (1 - Fi) * (1 - Fo) / (1 - probSpecular));
+}
 static inline const float *bsdf_table(const ppg_bsdf &b, const float *tables) { return tables ? tables + (size_t)b.table * PPG_BSDF_TABLE_SIZE : nullptr; }
 
 // eval / pdf with the solid-angle measure (delta models return 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
@@ -818,6 +853,7 @@ static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables 
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
     if (b.type == PPG_BSDF_ROUGHDIELECTRIC) return roughdielectric_eval(b, wi, wo);
+    if (b.type == PPG_BSDF_PLASTIC) return plastic_eval(b, wi, wo);
     if (b.type == PPG_BSDF_ROUGHPLASTIC) return roughplastic_eval(b, bsdf_table(b, tables), wi, wo);
     if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
     return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * (kInvPi * wo.z);
@@ -827,6 +863,7 @@ static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo, const float *table
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
     if (b.type == PPG_BSDF_ROUGHDIELECTRIC) return roughdielectric_pdf(b, wi, wo);
+    if (b.type == PPG_BSDF_PLASTIC) return plastic_pdf(b, wi, wo);
     if (b.type == PPG_BSDF_ROUGHPLASTIC) return roughplastic_pdf(b, bsdf_table(b, tables), wi, wo);
     if (wi.z <= 0 || wo.z <= 0) return 0.0f;
     return kInvPi * wo.z;   // warp::squareToCosineHemispherePdf
@@ -859,6 +896,11 @@ static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfS
         return w;
     }
     if (b.type == PPG_BSDF_ROUGHDIELECTRIC) return roughdielectric_sample(b, wi, sx, sy, rng ? rng->next1D() : 0.5f, s.wo, s.eta, pdf);
+    if (b.type == PPG_BSDF_PLASTIC) {
+        const F3 w = plastic_sample(b, wi, sx, sy, s.wo, s.delta, pdf);
+        if (flip) s.wo.z = -s.wo.z;
+        return w;
+    }
     if (b.type == PPG_BSDF_ROUGHPLASTIC) {
         const F3 w = roughplastic_sample(b, bsdf_table(b, tables), wi, sx, sy, s.wo, pdf);
         if (flip) s.wo.z = -s.wo.z;
@@ -941,11 +983,12 @@ public:
                 woPdf = bsdfPdf; dTreePdf = 0;
             } else {
                 F3 result;
-                bool zero = false;
+                bool zero = false, deltaEarly = false;
                 if (sx < frac) {
                     sx /= frac;
                     result = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf, sc.tables.data(), &rng);
                     if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0; zero = true; }
+                    else if (bs.delta) { dTreePdf = 0; woPdf = bsdfPdf * frac; result = result * (1.0f / frac); deltaEarly = true; }   // GP:1670-1676
                     else result = result * bsdfPdf;
                 } else {
                     float dw[3]; tree.sample(leaf, rng, dw);
@@ -953,6 +996,7 @@ public:
                     result = bsdf_eval(bsdf, its.wi, bs.wo, sc.tables.data());
                 }
                 if (zero) bsdfWeight = f3(0, 0, 0);
+                else if (deltaEarly) bsdfWeight = result;
                 else {
                     // pdfMat, GP:1693-1710
                     bsdfPdf = bsdf_pdf(bsdf, its.wi, bs.wo, sc.tables.data());

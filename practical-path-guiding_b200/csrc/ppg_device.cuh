@@ -409,6 +409,7 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 #define PPG_BSDF_T_ROUGHCONDUCTOR 4u
 #define PPG_BSDF_T_ROUGHPLASTIC 5u
 #define PPG_BSDF_T_ROUGHDIELECTRIC 6u
+#define PPG_BSDF_T_PLASTIC 7u
 #define PPG_BSDF_NONLINEAR 2u
 // 6 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)},
 // {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), -, -}
@@ -424,14 +425,14 @@ __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
         const float4 t = A_.bsdf(PPG_BSDF_F4 * idx + 1), e = A_.bsdf(PPG_BSDF_F4 * idx + 2), k = A_.bsdf(PPG_BSDF_F4 * idx + 3);
         b.trans = f3(t.x, t.y, t.z); b.eta = t.w; b.etaRgb = f3(e.x, e.y, e.z); b.invEta = e.w; b.k = f3(k.x, k.y, k.z);
         b.alpha = fabsf(k.w); b.distr = k.w < 0.f ? 0 : 1;
-        if (b.type == PPG_BSDF_T_ROUGHPLASTIC) {
+        if (b.type == PPG_BSDF_T_ROUGHPLASTIC || b.type == PPG_BSDF_T_PLASTIC) {
             const float4 s = A_.bsdf(PPG_BSDF_F4 * idx + 4), w = A_.bsdf(PPG_BSDF_F4 * idx + 5);
             b.specRefl = f3(s.x, s.y, s.z); b.fdrInt = s.w; b.ssw = w.x; b.lut = A_.g.bsdfTables + (size_t) __float_as_uint(w.y) * PPG_BSDF_LUT;
         }
     }
     return b;
 }
-__device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE || b.type == PPG_BSDF_T_ROUGHCONDUCTOR || b.type == PPG_BSDF_T_ROUGHPLASTIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
+__device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE || b.type == PPG_BSDF_T_ROUGHCONDUCTOR || b.type == PPG_BSDF_T_ROUGHPLASTIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC || b.type == PPG_BSDF_T_PLASTIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
 __device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
@@ -657,6 +658,41 @@ __device__ __forceinline__ float3 roughplastic_sample(const Bsdf &b, float3 wi, 
     return roughplastic_eval(b, wi, wo) * (1.0f / pdf);       // Spectrum / Float, core/spectrum.h:415-425
 }
 
+// ---- plastic (src/bsdfs/plastic.cpp): delta reflection off the coat + diffuse base; eval / pdf in the solid-angle measure see the diffuse part only
+__device__ __forceinline__ float3 plastic_diffuse(const Bsdf &b) {                                       // plastic.cpp:266-271
+    const float3 diff = b.refl;
+    if (b.flags & PPG_BSDF_NONLINEAR) return f3(diff.x / (1.0f - diff.x * b.fdrInt), diff.y / (1.0f - diff.y * b.fdrInt), diff.z / (1.0f - diff.z * b.fdrInt));
+    return diff * (1.0f / (1.f - b.fdrInt));
+}
+__device__ __forceinline__ float plastic_prob_specular(const Bsdf &b, float Fi) {                        // plastic.cpp:292-294
+    return (Fi * b.ssw) / (Fi * b.ssw + (1.f - Fi) * (1.f - b.ssw));
+}
+__device__ __forceinline__ float3 plastic_eval(const Bsdf &b, float3 wi, float3 wo) {                    // plastic.cpp:245-278
+    if (wo.z <= 0.f || wi.z <= 0.f) return f3(0, 0, 0);
+    float ct; const float Fi = fresnel_dielectric_ext(wi.z, ct, b.eta), Fo = fresnel_dielectric_ext(wo.z, ct, b.eta);
+    const float invEta2 = 1.f / (b.eta * b.eta);
+    return plastic_diffuse(b) * ((PPG_INV_PI * wo.z) * invEta2 * (1.f - Fi) * (1.f - Fo));
+}
+__device__ __forceinline__ float plastic_pdf(const Bsdf &b, float3 wi, float3 wo) {                      // plastic.cpp:280-308
+    if (wo.z <= 0.f || wi.z <= 0.f) return 0.0f;
+    float ct; const float Fi = fresnel_dielectric_ext(wi.z, ct, b.eta);
+    return (PPG_INV_PI * wo.z) * (1.f - plastic_prob_specular(b, Fi));
+}
+__device__ __forceinline__ float3 plastic_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, bool &delta, float &pdf) {   // plastic.cpp:374-441
+    pdf = 0.f; delta = false;
+    if (wi.z <= 0.f) return f3(0, 0, 0);
+    float ct; const float Fi = fresnel_dielectric_ext(wi.z, ct, b.eta);
+    const float probSpecular = plastic_prob_specular(b, Fi);
+    if (sx < probSpecular) {
+        delta = true; wo = f3(-wi.x, -wi.y, wi.z); pdf = probSpecular;
+        return (b.specRefl * Fi) * (1.0f / probSpecular);
+    }
+    wo = square_to_cosine_hemisphere((sx - probSpecular) / (1.f - probSpecular), sy);
+    const float Fo = fresnel_dielectric_ext(wo.z, ct, b.eta);
+    const float invEta2 = 1.f / (b.eta * b.eta);
+    pdf = (1.f - probSpecular) * (PPG_INV_PI * wo.z);
+    return plastic_diffuse(b) * (invEta2 * (1.f - Fi) * (1.f - Fo) / (1.f - probSpecular));
+}
 // ---- roughdielectric (src/bsdfs/roughdielectric.cpp), visible-normal sampling.  sample() takes ONE extra number `su` of the path's
 // sampler to choose reflection / refraction (EUsesSampler, :536-543).
 __device__ __forceinline__ float mts_signum(float v) { return copysignf(1.0f, v); }                     // core/math.h:269-278
@@ -736,6 +772,7 @@ __device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo)
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
     if (b.type == PPG_BSDF_T_ROUGHDIELECTRIC) return roughdielectric_eval(b, wi, wo);
+    if (b.type == PPG_BSDF_T_PLASTIC) return plastic_eval(b, wi, wo);
     if (b.type == PPG_BSDF_T_ROUGHPLASTIC) return roughplastic_eval(b, wi, wo);
     if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
     return b.refl * (PPG_INV_PI * wo.z);
@@ -745,6 +782,7 @@ __device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
     if (b.type == PPG_BSDF_T_ROUGHDIELECTRIC) return roughdielectric_pdf(b, wi, wo);
+    if (b.type == PPG_BSDF_T_PLASTIC) return plastic_pdf(b, wi, wo);
     if (b.type == PPG_BSDF_T_ROUGHPLASTIC) return roughplastic_pdf(b, wi, wo);
     if (wi.z <= 0.f || wo.z <= 0.f) return 0.0f;
     return PPG_INV_PI * wo.z;
@@ -776,6 +814,11 @@ __device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx
         return w;
     }
     if (b.type == PPG_BSDF_T_ROUGHDIELECTRIC) { const float su = rng.next1D(); return roughdielectric_sample(b, wi, sx, sy, su, wo, eta, pdf); }
+    if (b.type == PPG_BSDF_T_PLASTIC) {
+        const float3 w = plastic_sample(b, wi, sx, sy, wo, delta, pdf);
+        if (flip) wo.z = -wo.z;
+        return w;
+    }
     if (b.type == PPG_BSDF_T_ROUGHPLASTIC) {
         const float3 w = roughplastic_sample(b, wi, sx, sy, wo, pdf);
         if (flip) wo.z = -wo.z;

@@ -190,11 +190,12 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                 } else {
                     const SampNode *tree = P.tree.samp + __float_as_uint(la.x);
                     const bool valid = __float_as_uint(la.w) & 1u;
-                    float3 result; bool zero = false;
+                    float3 result; bool zero = false, deltaEarly = false;
                     if (sx < frac) {
                         sx /= frac;
                         result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng);
                         if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0.f; zero = true; }
+                        else if (DELTA && isDelta) { dTreePdf = 0.f; woPdf = bsdfPdf * frac; result = result * (1.0f / frac); deltaEarly = true; }   // GP:1670-1676
                         else result = result * bsdfPdf;
                     } else {
                         const float2 c2 = dtree_sample(tree, valid, rng);
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                         result = bsdf_eval(bsdf, its.wi, wo);
                     }
                     if (zero) bsdfWeight = f3(0, 0, 0);
+                    else if (deltaEarly) bsdfWeight = result;
                     else {   // pdfMat, GP:1693-1710
                         bsdfPdf = bsdf_pdf(bsdf, its.wi, wo);
                         if (!isfinite(bsdfPdf)) { woPdf = 0.f; dTreePdf = 0.f; }

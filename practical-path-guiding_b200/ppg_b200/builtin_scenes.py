@@ -120,6 +120,22 @@ def cbox_with_analytic_spheres(cbox: SceneDesc) -> SceneDesc:
     return sc
 
 
+def cbox_smooth_plastic(cbox: SceneDesc) -> SceneDesc:
+    """CBOX whose boxes are smooth plastics (plastic.cpp): a delta coat reflection mixed with a diffuse base, so a guided vertex can
+    return a delta sample (GP:1670-1676).  Small box nonlinear red, large box linear blue; the floor becomes a glossy dark plastic."""
+    import copy
+    from .scene import make_plastic
+    sc = copy.copy(cbox)
+    base = _pad_bsdfs(sc.bsdfs); nb = len(base)
+    sc.bsdfs = np.concatenate([base, np.stack([make_plastic(0, (0.6, 0.1, 0.08), (1, 1, 1), 1.49 / 1.000277, True),
+                                               make_plastic(0, (0.1, 0.25, 0.6), (0.9, 0.9, 0.9), 1.9, False),
+                                               make_plastic(0, (0.2, 0.2, 0.2), (1, 1, 1), 1.5, False)])]).astype(np.float32)
+    sc.bsdf_names = list(sc.bsdf_names) + ["red_plastic_nonlinear", "blue_plastic", "dark_floor_plastic"]
+    shapes = sc.shapes.copy(); shapes[6, 2] = nb; shapes[7, 2] = nb + 1; shapes[1, 2] = nb + 2
+    sc.shapes = shapes
+    return sc
+
+
 def cbox_rough_metal(cbox: SceneDesc) -> SceneDesc:
     """CBOX whose boxes are rough conductors: the small box GGX alpha 0.1 with the eta/k of spaceship.xml's "RoughAluminium",
     the large box Beckmann alpha 0.3 -- glossy BSDFs are guided (ESmooth) and take part in light sampling."""

@@ -42,6 +42,7 @@ BSDF_CONDUCTOR = 3
 BSDF_ROUGHCONDUCTOR = 4
 BSDF_ROUGHPLASTIC = 5
 BSDF_ROUGHDIELECTRIC = 6
+BSDF_PLASTIC = 7
 BSDF_FLAG_NONLINEAR = 2
 BSDF_FLAG_TWOSIDED = 1
 
@@ -408,6 +409,34 @@ def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0), 
     return b
 
 
+def fresnel_diffuse_reflectance(eta: float) -> float:
+    """fresnelDiffuseReflectance(eta, fast=false) (src/libcore/util.cpp:807-862): integral over xi in [0,1] of
+    fresnelDielectricExt(sqrt(xi), eta).  The reference integrates adaptively (Gauss-Lobatto, relative error 1e-5); here a fixed
+    composite Simpson rule in double precision after the substitution xi = c^2 (smooth integrand) -- same value to ~1e-7."""
+    n = 1 << 14
+    c = np.linspace(0.0, 1.0, n + 1)
+    scale = np.where(c > 0, 1.0 / eta, eta)
+    ct2 = 1.0 - (1.0 - c * c) * scale * scale
+    tir = ct2 <= 0
+    ct = np.sqrt(np.where(tir, 0.0, ct2))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rs = (c - eta * ct) / (c + eta * ct); rp = (eta * c - ct) / (eta * c + ct)
+        F = np.where(tir, 1.0, 0.5 * (rs * rs + rp * rp))
+    F = np.where(np.isfinite(F), F, 1.0)
+    f = F * 2.0 * c                                   # d(xi) = 2 c dc
+    w = np.ones(n + 1); w[1:-1:2] = 4; w[2:-1:2] = 2
+    return float(np.sum(f * w) / (3.0 * n))
+
+
+def make_plastic(flags, diffuse, specular, eta, nonlinear):
+    """ppg_bsdf for the smooth plastic (src/bsdfs/plastic.cpp:185-212)."""
+    lum = lambda c: 0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2]
+    d_avg, s_avg = lum(diffuse), lum(specular)
+    b = _make_bsdf(BSDF_PLASTIC, flags | (BSDF_FLAG_NONLINEAR if nonlinear else 0), diffuse, (0, 0, 0), (eta, eta, eta))
+    b[16:19] = specular; b[19] = fresnel_diffuse_reflectance(1.0 / eta); b[20] = s_avg / (d_avg + s_avg)
+    return b
+
+
 def make_roughplastic(flags, diffuse, specular, eta, alpha, distribution, nonlinear, tables):
     """ppg_bsdf for roughplastic (src/bsdfs/roughplastic.cpp:190-290); appends its rough-transmittance table to `tables`."""
     from . import rtrans
@@ -485,6 +514,11 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
         entry = _make_bsdf(BSDF_ROUGHDIELECTRIC, flags, sr, st, (eta, eta, eta), (0, 0, 0), float(props.get("alpha", 0.1)), 1 if distr == "ggx" else 0)
+    elif typ == "plastic":              # src/bsdfs/plastic.cpp:143-163
+        eta = _lookup_ior(props.get("intIOR"), "polypropylene") / _lookup_ior(props.get("extIOR"), "air")
+        dr = _parse_color(colors["diffuseReflectance"]) if "diffuseReflectance" in colors else np.full(3, 0.5, np.float32)
+        sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
+        entry = make_plastic(flags, dr, sr, eta, props.get("nonlinear", "false") == "true")
     elif typ == "roughplastic":         # src/bsdfs/roughplastic.cpp:190-232
         eta = _lookup_ior(props.get("intIOR"), "polypropylene") / _lookup_ior(props.get("extIOR"), "air")
         distr = props.get("distribution", "beckmann").lower()

@@ -392,3 +392,19 @@ def test_spaceship_improved_settings_statistics():
     assert abs(st["total_vertices"] - ost["total_vertices"]) <= 0.02 * ost["total_vertices"]
     for a, b in list(zip(st["iterations"], ost["iterations"]))[:-1]:
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= max(4, 0.15 * b["s_tree_leaves"])   # splits near the threshold flip
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(bsdfSamplingFractionLoss="none", bsdfSamplingFraction="0.3")])
+def test_smooth_plastic_matches_oracle(extra):
+    """CBOX with smooth-plastic boxes and floor (plastic.cpp): a delta coat reflection mixed with a diffuse base.  A guided vertex
+    whose BSDF sample lands on the delta lobe returns early with woPdf = bsdfPdf * fraction and weight / fraction (GP:1670-1676)."""
+    from ppg_b200.builtin_scenes import cbox_smooth_plastic
+    sc = cbox_smooth_plastic(load_cbox(128))
+    props = dict(dict(sc.integrator, budget="60"), **extra)
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert relmse(img, ref) <= 1e-5, relmse(img, ref)
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 1e-4 * ost["total_vertices"]
+    for a, b in zip(st["iterations"], ost["iterations"]):
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
+        assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-4)

@@ -26,14 +26,22 @@ def _roughplastic(distribution, alpha, nonlinear, diffuse=(0.256, 0.013, 0.08)):
     return O.bsdf_from_row(row), np.asarray(tables, np.float32)
 
 
+def _plastic(nonlinear, eta):
+    from ppg_b200.scene import make_plastic
+    return O.bsdf_from_row(make_plastic(0, (0.6, 0.3, 0.2), (1, 1, 1), eta, nonlinear)), None
+
+
+SMOOTH_PLASTIC = {"plastic-1.49-nonlinear": (True, 1.49), "plastic-1.9": (False, 1.9)}
 PLASTIC = {"roughplastic-beckmann-0.4-nonlinear": (0, 0.4, True), "roughplastic-ggx-0.2": (1, 0.2, False), "roughplastic-beckmann-0.1": (0, 0.1, False)}
 
 
-@pytest.mark.parametrize("name", list(CASES) + list(PLASTIC))
+@pytest.mark.parametrize("name", list(CASES) + list(PLASTIC) + list(SMOOTH_PLASTIC))
 @pytest.mark.parametrize("cos_i", [0.95, 0.5, 0.15])
 def test_sample_matches_pdf_and_weight_matches_eval(name, cos_i):
     tables = None
-    if name in PLASTIC:
+    if name in SMOOTH_PLASTIC:
+        b, tables = _plastic(*SMOOTH_PLASTIC[name])
+    elif name in PLASTIC:
         b, tables = _roughplastic(*PLASTIC[name])
     else:
         kw = dict(CASES[name])
@@ -49,8 +57,12 @@ def _chi2(b, tables, cos_i):
     n = 400000
     wi = np.tile(np.array([[np.sqrt(1 - cos_i ** 2), 0.0, cos_i]], np.float32), (n, 1))
     wo, w, pdf, delta = O.bsdf_sample(b, wi, rng.random((n, 2), dtype=np.float32), tables=tables)
-    ok = (pdf > 0) & (w.sum(axis=1) > 0)
-    assert ok.mean() > 0.3
+    ok = (pdf > 0) & (w.sum(axis=1) > 0) & (delta == 0)         # the smooth part (plastic's coat reflection is a delta lobe)
+    assert ok.mean() > 0.2
+    if delta.any():       # plastic.cpp:330-340: mirror direction, probability probSpecular, weight specularReflectance * Fi / probSpecular
+        dl = delta != 0
+        assert np.allclose(wo[dl], wi[dl] * np.float32([-1, -1, 1]), atol=1e-6)
+        assert abs(dl.mean() - pdf[dl][0]) < 0.01 and np.allclose(pdf[dl], pdf[dl][0])
     ev, pdf2 = O.bsdf_eval_pdf(b, wi[ok], wo[ok], tables=tables)
     assert np.allclose(pdf2, pdf[ok], rtol=2e-3, atol=1e-6)                       # pdf() of the sampled direction == pdf returned by sample()
     assert np.allclose(ev, w[ok] * pdf[ok, None], rtol=3e-3, atol=1e-5)         # weight == eval / pdf
