@@ -414,14 +414,14 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 // 6 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)},
 // {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), -, -}
 struct Bsdf { float3 refl, trans, etaRgb, k, specRefl; float eta, invEta, alpha, fdrInt, ssw; uint32_t type, flags; int distr; const float *lut; };
-// DELTA == false: the scene holds diffuse BSDFs only (host-checked), the delta models compile away
-template <bool DELTA, class Acc>
+// FULL == false: the scene holds diffuse BSDFs and triangles only (host-checked); every other model compiles away
+template <bool FULL, class Acc>
 __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
     const float4 a = A_.bsdf(PPG_BSDF_F4 * idx);
     Bsdf b; b.refl = f3(a.x, a.y, a.z);
-    const uint32_t tf = __float_as_uint(a.w); b.type = DELTA ? (tf & 0xffu) : PPG_BSDF_T_DIFFUSE; b.flags = tf >> 8;
+    const uint32_t tf = __float_as_uint(a.w); b.type = FULL ? (tf & 0xffu) : PPG_BSDF_T_DIFFUSE; b.flags = tf >> 8;
     b.trans = b.etaRgb = b.k = b.specRefl = f3(0, 0, 0); b.eta = b.invEta = 1.f; b.alpha = 0.1f; b.distr = 1; b.fdrInt = b.ssw = 0.f; b.lut = nullptr;
-    if (DELTA && b.type != PPG_BSDF_T_DIFFUSE) {
+    if (FULL && b.type != PPG_BSDF_T_DIFFUSE) {
         const float4 t = A_.bsdf(PPG_BSDF_F4 * idx + 1), e = A_.bsdf(PPG_BSDF_F4 * idx + 2), k = A_.bsdf(PPG_BSDF_F4 * idx + 3);
         b.trans = f3(t.x, t.y, t.z); b.eta = t.w; b.etaRgb = f3(e.x, e.y, e.z); b.invEta = e.w; b.k = f3(k.x, k.y, k.z);
         b.alpha = fabsf(k.w); b.distr = k.w < 0.f ? 0 : 1;

@@ -301,7 +301,7 @@ struct ppg_integrator {
     }
 
     // run state (GP:2313-2323)
-    bool isBuilt = false, isFinalIter = false, doNee = false; int iter = 0, passesRendered = 0; uint32_t nRealEmitters = 0; bool hasDeltaBsdf = false;
+    bool isBuilt = false, isFinalIter = false, doNee = false; int iter = 0, passesRendered = 0; uint32_t nRealEmitters = 0; bool fullFeature = false;
     bool useNee() const { return prm.nee != PPG_NEE_NEVER && nRealEmitters > 0; }
     std::chrono::steady_clock::time_point startTime;
     ppg_stats stats; uint64_t launches = 0; double deviceMs = 0;
@@ -481,9 +481,9 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         meta[4 * (size_t) slot] = sh.bsdf; meta[4 * (size_t) slot + 1] = sh.emitter;
         meta[4 * (size_t) slot + 2] = (sh.has_normals && s->normals) ? 1 : 0; meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
     }
-    h->hasDeltaBsdf = false;
-    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) h->hasDeltaBsdf = true;   // any non-diffuse model
-    if (s->n_spheres) h->hasDeltaBsdf = true;                                            // ... or analytic spheres: the full-feature kernel variants
+    h->fullFeature = false;
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) h->fullFeature = true;   // any non-diffuse model
+    if (s->n_spheres) h->fullFeature = true;                                            // ... or analytic spheres: the full-feature kernel variants
     std::vector<float> bsdf(4 * PPG_BSDF_F4 * (size_t) s->n_bsdfs, 0.f);
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
         float *b = &bsdf[4 * PPG_BSDF_F4 * (size_t) i]; const ppg_bsdf &m = s->bsdfs[i];
@@ -822,7 +822,7 @@ static int ensure_wavefront(ppg_integrator *h) {
     CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
-    if (!h->hasDeltaBsdf) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BLOCK, h->sceneSmemBytes));
+    if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BLOCK, h->sceneSmemBytes));
     else if (h->sceneSmemBytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, true, true>, PPG_BLOCK, h->sceneSmemBytes));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, false, true>, PPG_BLOCK, 0));
     h->gridBounce = h->numSMs * std::max(occ, 1);
@@ -846,20 +846,20 @@ static VertexSlab slab_at(ppg_integrator *h, int k, int set = 0) {
     return s;
 }
 
-template <bool FIRST, bool SMEM, bool DELTA> static void launch_bounce3(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
+template <bool FIRST, bool SMEM, bool FULL> static void launch_bounce3(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
     const size_t sm = P.sceneSmemBytes;
     if (nee) {      // next event estimation always runs with full records
-        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-        else bounce_kernel<FIRST, 2, true, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else bounce_kernel<FIRST, 2, false, SMEM, DELTA><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+        else bounce_kernel<FIRST, 2, true, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+    else bounce_kernel<FIRST, 2, false, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
     h->launches++;
 }
 template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
     // scene staged in shared memory or read from HBM; lean instantiation for scenes without delta BSDFs
-    if (P.sceneSmemBytes) { if (h->hasDeltaBsdf) launch_bounce3<FIRST, true, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, true, false>(h, P, record, grid, nee); }
-    else { if (h->hasDeltaBsdf) launch_bounce3<FIRST, false, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, false, false>(h, P, record, grid, nee); }
+    if (P.sceneSmemBytes) { if (h->fullFeature) launch_bounce3<FIRST, true, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, true, false>(h, P, record, grid, nee); }
+    else { if (h->fullFeature) launch_bounce3<FIRST, false, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, false, false>(h, P, record, grid, nee); }
 }
 
 // one batch of `nPasses` passes as a single wavefront

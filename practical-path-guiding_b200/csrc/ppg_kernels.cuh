@@ -20,7 +20,7 @@ namespace ppg {
 #define PPG_MIN_BLOCKS 4               // resident blocks per SM the bounce kernel is compiled for (register cap)
 #endif
 #ifndef PPG_MIN_BLOCKS_GLOSSY
-#define PPG_MIN_BLOCKS_GLOSSY 4        // same for scenes with non-diffuse BSDFs (DELTA variants; measured on the rough CBOX variants: 4 > 3 > 2)
+#define PPG_MIN_BLOCKS_GLOSSY 4        // same for scenes with non-diffuse BSDFs (FULL variants; measured on the rough CBOX variants: 4 > 3 > 2)
 #endif
 #define PPG_MAX_VERTICES 32         // MAX_NUM_VERTICES, GP:1771
 #define PPG_INVALID 0xFFFFFFFFu
@@ -86,8 +86,8 @@ __device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) 
 // FIRST: generate the camera ray (renderBlock, GP:1613-1632) instead of loading a path state.
 // RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
 //         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
-template <bool FIRST, int RECORD, bool NEE, bool SMEM, bool DELTA>
-__global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
+template <bool FIRST, int RECORD, bool NEE, bool SMEM, bool FULL>
+__global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
     const SceneAccess<SMEM> sc(P.scene);
     sc.stage();
     const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
@@ -138,11 +138,11 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
         if (alive) {
             ++raysLocal;
             Hit hit;
-            const bool found = bvh_intersect<DELTA>(sc, o, d, mint, maxt, hit);
+            const bool found = bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
             bool cont = found;                                                     // miss: no environment emitter in scope (GP:1902-1914)
             Its its;
             if (cont) {
-                fill_its<DELTA>(sc, hit, o, d, its);
+                fill_its<FULL>(sc, hit, o, d, its);
                 // emitted radiance: primary hit via EEmittedRadiance (GP:1917-1919), later hits via the `value`
                 // returned by rayIntersectAndLookForEmitter (GP:2078-2091; miWeight(woPdf, 0) == 1)
                 float3 Lhit = f3(0, 0, 0);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                         const float4 r = sc.radiance(its.emitter);
                         Lhit = thr * f3(r.x, r.y, r.z);
                         if (NEE && !FIRST && P.doNee && !(prevSlot >> 31)) {            // MIS against light sampling, GP:2084-2088
-                            const float emitterPdf = pdf_emitter_direct<DELTA>(sc.g, its.emitter, o, prevRefN, d, its.shN, hit.t);
+                            const float emitterPdf = pdf_emitter_direct<FULL>(sc.g, its.emitter, o, prevRefN, d, its.shN, hit.t);
                             Lhit = Lhit * mi_weight(prevWoPdf, emitterPdf);
                         }
                         Li = Li + Lhit;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                 if (wiDotGeoN * its.wi.z < 0.f && P.strictNormals) cont = false;     // GP:1929-1932
             }
             if (cont) {
-                const Bsdf bsdf = load_bsdf<DELTA>(sc, its.bsdf);
+                const Bsdf bsdf = load_bsdf<FULL>(sc, its.bsdf);
                 const bool smooth = bsdf_has_smooth(bsdf);                           // only smooth BSDFs are guided (GP:1942-1944)
                 int levels = 0; uint32_t leaf = 0; float4 la = make_float4(0, 0, 0, 0);
                 if (smooth) {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                         sx /= frac;
                         result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng);
                         if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0.f; zero = true; }
-                        else if (DELTA && isDelta) { dTreePdf = 0.f; woPdf = bsdfPdf * frac; result = result * (1.0f / frac); deltaEarly = true; }   // GP:1670-1676
+                        else if (FULL && isDelta) { dTreePdf = 0.f; woPdf = bsdfPdf * frac; result = result * (1.0f / frac); deltaEarly = true; }   // GP:1670-1676
                         else result = result * bsdfPdf;
                     } else {
                         const float2 c2 = dtree_sample(tree, valid, rng);
@@ -219,11 +219,11 @@ __global__ void __launch_bounds__(PPG_BLOCK, DELTA ? PPG_MIN_BLOCKS_GLOSSY : PPG
                     // ---- luminaire sampling, GP:1964-2021
                     const float ex = rng.next1D(), ey = rng.next1D();
                     DirectSample ds; float dist;
-                    if (sample_emitter_direct<DELTA>(sc, its.p, refN, ex, ey, ds, dist)) {
+                    if (sample_emitter_direct<FULL>(sc, its.p, refN, ex, ey, ds, dist)) {
                         // Scene::evalTransmittance: shadow ray, epsilon scaled without the clamp (skdtree.cpp:154-158)
                         const float smint = PPG_EPSILON * fmaxf(fmaxf(fabsf(its.p.x), fabsf(its.p.y)), fabsf(its.p.z));
                         Hit sh;      // (shadow rays are not path vertices: not counted in the samples metric)
-                        if (!bvh_intersect<DELTA>(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh)) {
+                        if (!bvh_intersect<FULL>(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh)) {
                             const float3 dl = its.toLocal(ds.d);
                             if (!P.strictNormals || dot(its.geoN, ds.d) * dl.z > 0.f) {
                                 const float3 bsdfVal = bsdf_eval(bsdf, its.wi, dl);
