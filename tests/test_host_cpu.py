@@ -23,13 +23,14 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    src = '#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu", sizeof(ppg_params), sizeof(ppg_bsdf), sizeof(ppg_shape), sizeof(ppg_scene_desc), sizeof(ppg_iteration_stats), sizeof(ppg_stats));}' % os.path.join(ROOT, "include", "ppg.h")
+    src = '#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu", sizeof(ppg_params), sizeof(ppg_bsdf), sizeof(ppg_shape), sizeof(ppg_scene_desc), sizeof(ppg_iteration_stats), sizeof(ppg_stats), sizeof(ppg_sphere));}' % os.path.join(ROOT, "include", "ppg.h")
     import subprocess, tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.run(["/usr/bin/gcc", os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
         sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [C.sizeof(capi.PpgParams), C.sizeof(capi.PpgBsdf), C.sizeof(capi.PpgShape), C.sizeof(capi.PpgSceneDesc), C.sizeof(capi.PpgIterationStats), C.sizeof(capi.PpgStats)]
+    assert sizes == [C.sizeof(capi.PpgParams), C.sizeof(capi.PpgBsdf), C.sizeof(capi.PpgShape), C.sizeof(capi.PpgSceneDesc), C.sizeof(capi.PpgIterationStats), C.sizeof(capi.PpgStats), C.sizeof(capi.PpgSphere)]
+    assert C.sizeof(capi.PpgBsdf) == 96 and C.sizeof(capi.PpgSphere) == 24
 
 
 def test_parameter_defaults_are_the_references():
@@ -102,3 +103,54 @@ def test_fixture_is_what_the_loader_produces_from_the_reference_xml():
     for k in ("positions", "normals", "indices", "triangle_shape", "shapes", "bsdfs", "area_radiance", "cam_to_world", "aabb_min", "aabb_max"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert a.integrator == b.integrator and a.x_fov_deg == b.x_fov_deg
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/scenes/spaceship/spaceship-improved.xml"), reason="reference tree not present")
+def test_spaceship_fixture_is_what_the_loader_produces_from_the_reference_xml():
+    """spaceship-improved.xml exercises the whole loader: matrix transforms, OBJ meshes with faceNormals, rectangles, a sphere with
+    flipNormals, twosided wrappers, roughconductor / roughplastic (reduced transmittance tables) / roughdielectric, named and referenced BSDFs."""
+    from ppg_b200.scene import load_mitsuba_xml, SceneDesc
+    a = load_mitsuba_xml("/root/reference/scenes/spaceship/spaceship-improved.xml")
+    b = SceneDesc.load(os.path.join(ROOT, "scenes", "spaceship-improved.npz"))
+    for k in ("positions", "normals", "indices", "triangle_shape", "shapes", "bsdfs", "bsdf_tables", "spheres", "area_radiance", "cam_to_world", "aabb_min", "aabb_max"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert len(a.indices) == 457560 and len(a.spheres) == 1 and a.spheres[0, 3] == 100.0
+    types = a.bsdfs[:, 0].view(np.uint32)
+    assert sorted(set(types.tolist())) == [0, 4, 5, 6]                      # diffuse, roughconductor, roughplastic, roughdielectric
+    assert a.integrator["bsdfSamplingFractionLoss"] == "kl" and a.integrator["sppPerPass"] == "1"
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/mitsuba/data/microfacet/beckmann.dat"), reason="reference tree not present")
+def test_rough_transmittance_reduction_has_the_physical_limits():
+    """rtrans.py (= RoughTransmittance::setEta/setAlpha/evalDiffuse): at low roughness the table tends to 1 - Fresnel; the diffuse
+    internal reflectance matches fresnelDiffuseReflectance(1/eta) (both integrate the same quantity for a smooth interface)."""
+    from ppg_b200 import rtrans
+    from ppg_b200.scene import fresnel_diffuse_reflectance
+    lut, fdr = rtrans.reduce_for_material("beckmann", 1.5, 0.02)
+    assert lut.shape == (100,) and lut.dtype == np.float32
+    c = ((np.arange(100) / 99.0) ** 4)[70:]                                  # table abscissa is cos(theta)^(1/4); cos > 0.25 (roughness matters at grazing angles)
+    ct = np.sqrt(1 - (1 - c * c) / 2.25)
+    F = 0.5 * (((c - 1.5 * ct) / (c + 1.5 * ct)) ** 2 + ((1.5 * c - ct) / (1.5 * c + ct)) ** 2)
+    assert np.allclose(lut[70:], 1 - F, atol=0.01)
+    assert abs(fdr - fresnel_diffuse_reflectance(1 / 1.5)) < 0.01
+    lut2, fdr2 = rtrans.reduce_for_material("ggx", 1.5, 0.4)
+    assert np.all(np.diff(lut2[10:]) > -1e-3) and 0.5 < fdr2 < 0.65           # transmittance grows towards normal incidence
+
+
+def test_fresnel_diffuse_reflectance_matches_the_published_fits():
+    """src/libcore/util.cpp:822-853 quotes two fits of the same integral with <= 0.1 % error for eta in [1, 2]."""
+    from ppg_b200.scene import fresnel_diffuse_reflectance as fdr
+    for eta in (1.1, 1.33, 1.5, 1.9):
+        ie = 1 / eta
+        fit_gt1 = 0.919317 - 3.4793 * ie + 6.75335 * ie ** 2 - 7.80989 * ie ** 3 + 4.98554 * ie ** 4 - 1.36881 * ie ** 5
+        fit_lt1 = -1.4399 * ie * ie + 0.7099 * ie + 0.6681 + 0.0636 / ie
+        assert abs(fdr(eta) - fit_gt1) < 2e-3 * max(fit_gt1, 0.05) + 2e-4
+        assert abs(fdr(ie) - fit_lt1) < 6e-3 * fit_lt1
+
+
+def test_unsupported_scene_content_is_refused_not_substituted():
+    from ppg_b200.scene import load_mitsuba_xml
+    if not os.path.exists("/root/reference/scenes/kitchen/kitchen.xml"):
+        pytest.skip("reference tree not present")
+    with pytest.raises(NotImplementedError):
+        load_mitsuba_xml("/root/reference/scenes/kitchen/kitchen.xml")
