@@ -148,6 +148,7 @@ static void wald_constants(H3 A, H3 B, H3 C, float out[9], int &k) {
     out[7] = hcomp(c, v) / denom; out[8] = -hcomp(c, u) / denom;                          // c_nu c_nv
 }
 
+static int bvh_env_int(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }   // tuning experiments only
 struct HostBvh {
     std::vector<float> nodes;        // 8 floats per node
     std::vector<uint32_t> order;     // leaf order -> original triangle
@@ -176,7 +177,7 @@ static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, 
             cmx = h3(std::max(cmx.x, cen[t].x), std::max(cmx.y, cen[t].y), std::max(cmx.z, cen[t].z));
         }
         Node nd; nd.mn = mn; nd.mx = mx; nd.left = j.first; nd.count = j.count;
-        const int maxLeaf = 4;
+        static const int maxLeaf = std::min(std::max(bvh_env_int("PPG_BVH_LEAF", 4), 1), 15);   // <= 15: the device stack packs the count in 4 bits
         if (j.count > (uint32_t) maxLeaf || j.count > 1) {
             // binned SAH over the three axes
             const int NB = 16; float bestCost = std::numeric_limits<float>::infinity(); int bestAxis = -1, bestBin = -1;
@@ -209,7 +210,9 @@ static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, 
                     if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestBin = b; }
                 }
             }
-            const float leafCost = area(mn, mx) * j.count;
+            // SAH with a traversal term: splitting pays when Ct * A + A_L N_L + A_R N_R < A * N (intersection cost 1)
+            static const float Ct = (float) bvh_env_int("PPG_BVH_CT_X10", 10) * 0.1f;
+            const float leafCost = area(mn, mx) * ((float) j.count - Ct);
             if (bestAxis >= 0 && (j.count > (uint32_t) maxLeaf || bestCost < leafCost)) {
                 const float lo = hcomp(cmn, bestAxis), hi = hcomp(cmx, bestAxis);
                 auto mid = std::partition(out.order.begin() + j.first, out.order.begin() + j.first + j.count, [&](uint32_t t) {

@@ -42,4 +42,6 @@ for lib in a.libs.split(","):
             ms = st["render_device_ms"]; v = st["total_vertices"] / ms / 1e3
             best = max(best or 0, v)
         km = st.get("kernel_ms", [])
-        print(f"{lib:40s} {sn:10s} {best:9.1f} Msamples/s  ms {ms:8.1f}  kernel_ms {km}", flush=True)
+        kb = km.get("bounce", 0.0) if isinstance(km, dict) else 0.0
+        print(f"{lib:40s} {sn:10s} {best:9.1f} Msamples/s  ms {ms:8.1f}  bounce_ms {kb:8.1f} ({st['total_vertices'] / max(kb, 1e-9) / 1e3:7.1f} Msamples/s of bounce-kernel time) "
+              f"commit {km.get('commit', 0):.1f} adam {km.get('adam', 0):.1f}", flush=True)

@@ -1,18 +1,23 @@
 #!/usr/bin/env python
 """Turn gpurun_out ncu artefacts into the small text summaries committed under profiles/.
-  summarize_profile.py launches <launches.csv> <out.md> "<title>"
+  summarize_profile.py launches <launches.csv> <out.md> "<title>"      (csv may also hold dram__bytes_{read,write}.sum: then
+                                                                        profiles/ncu_traffic.json is written next to <out.md>)
   summarize_profile.py kernel <report.ncu-rep> <mangled-substring> <out.md> "<title>"
 """
 import csv, collections, os, re, subprocess, sys
 
 def launches(path, out, title):
     lines = [l for l in open(path) if not l.startswith("==")]
-    tot = collections.defaultdict(float); cnt = collections.Counter()
+    tot = collections.defaultdict(float); cnt = collections.Counter(); dram = collections.defaultdict(float)
     for row in csv.DictReader(lines):
         name = re.sub(r"\(.*", "", row["Kernel Name"])
         try: v = float(row["Metric Value"].replace(",", ""))
         except Exception: continue
         u = row["Metric Unit"]
+        if row["Metric Name"].startswith("dram__bytes"):
+            dram[name] += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            continue
+        if row["Metric Name"] != "gpu__time_duration.sum": continue
         v = v / 1e6 if u == "ns" else v / 1e3 if u.startswith("us") else v * 1e3 if u in ("s", "second") else v
         tot[name] += v; cnt[name] += 1
     T = sum(tot.values())
@@ -21,6 +26,15 @@ def launches(path, out, title):
         f.write(f"launches captured: {sum(cnt.values())}, total {T:.1f} ms\n\n| kernel | launches | total ms | share | avg ms |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
             f.write(f"| `{k.strip()}` | {cnt[k]} | {v:.3f} | {v / T:.4f} | {v / cnt[k]:.4f} |\n")
+        if dram:
+            import json
+            f.write("\nDRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per launch:\n\n| kernel | launches | total GB | avg MB / launch |\n|---|---:|---:|---:|\n")
+            for k, v in sorted(dram.items(), key=lambda x: -x[1]):
+                f.write(f"| `{k.strip()}` | {cnt[k]} | {v / 1e9:.2f} | {v / max(cnt[k], 1) / 1e6:.1f} |\n")
+            bn = sum(c for k, c in cnt.items() if "bounce_kernel" in k); bb = sum(v for k, v in dram.items() if "bounce_kernel" in k)
+            json.dump({"bounce_dram_bytes_per_launch": bb / max(bn, 1), "bounce_launches": bn, "source": os.path.basename(out),
+                       "note": "average over every bounce_kernel launch of one bench step (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum)"},
+                      open(os.path.join(os.path.dirname(os.path.abspath(out)), "ncu_traffic.json"), "w"), indent=1)
 
 def kernel(rep, fn, out, title):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
