@@ -116,6 +116,9 @@ typedef enum ppg_bsdf_type {
     PPG_BSDF_PLASTIC = 7,        /* src/bsdfs/plastic.cpp:245-441: smooth dielectric coat (delta reflection) over a diffuse base; reflectance = diffuse,
                                     specular_reflectance, eta[0], fdr_int = fresnelDiffuseReflectance(1/eta), specular_sampling_weight,
                                     PPG_BSDF_FLAG_NONLINEAR.  Mixed delta + smooth: exercises GP:1672-1676 */
+    PPG_BSDF_THINDIELECTRIC = 8, /* src/bsdfs/thindielectric.cpp:153-306: delta reflection + index-matched (ENull) transmission with the internal
+                                    reflections folded in; reflectance = specularReflectance, specular_transmittance, eta[0].  Null transitions
+                                    are looked through by the emitter lookup (GP:2184-2245) and by light sampling (scene.cpp:619-679) */
     PPG_BSDF_ROUGHPLASTIC = 5    /* src/bsdfs/roughplastic.cpp:326-507: rough dielectric coat over a diffuse base; the rough transmittance
                                     (src/bsdfs/rtrans.h) is passed as a per-material 100-entry table + scalars */
 } ppg_bsdf_type;

@@ -247,6 +247,19 @@ struct Scene {
 
     struct Hit { float t, u, v; uint32_t prim; };   // prim: triangle index, or kSphereBit | sphere index
     static const uint32_t kSphereBit = 0x80000000u;
+    uint32_t hitShape(const Hit &h) const { return (h.prim & kSphereBit) ? (uint32_t) spheres[h.prim & ~kSphereBit].shape : triShape[h.prim]; }
+    // the normal ShapeKDTree::rayIntersect(ray, t, shape, n, uv) reports (skdtree.cpp:165-175: plain face normal; spheres: geoFrame.n)
+    F3 hitGeoNormal(const Hit &h, F3 ro, F3 rd) const {
+        if (h.prim & kSphereBit) {
+            const ppg_sphere &sp = spheres[h.prim & ~kSphereBit];
+            const F3 c = f3(sp.center[0], sp.center[1], sp.center[2]);
+            F3 p = ro + rd * h.t; p = c + normalize(p - c) * sp.radius;
+            F3 n = normalize(p - c); if (sp.flip_normals) n = n * -1.0f;
+            return n;
+        }
+        const F3 p0 = P[idx[3 * h.prim]], p1 = P[idx[3 * h.prim + 1]], p2 = P[idx[3 * h.prim + 2]];
+        return normalize(cross(p1 - p0, p2 - p0));
+    }
 
     // Sphere::rayIntersect (src/shapes/sphere.cpp:163-187) with solveQuadraticDouble (src/libcore/util.cpp:487-525): double precision
     static bool sphereIntersect(const ppg_sphere &sp, F3 ro, F3 rd, float mint, float maxt, float &t) {
@@ -376,11 +389,36 @@ static inline bool occluded(const Scene &sc, F3 p1, F3 d, float remaining) {
     Scene::Hit h;
     return sc.intersect(p1, d, mint, remaining * (1 - kShadowEpsilon), h);
 }
+static inline bool bsdf_has_null(const ppg_bsdf &b);
+static inline F3 bsdf_eval_null(const ppg_bsdf &b, float cosThetaI);
+// Scene::evalTransmittance with index-matched surfaces (scene.cpp:619-679, p1 and p2 on surfaces): a null surface multiplies its
+// straight-through transmittance (evaluated in the GEOMETRIC frame, :650-655) and the ray continues behind it, at most
+// maxInteractions times (maxDepth - depth - 1; negative = unlimited); anything else blocks.
+static inline F3 eval_transmittance(const Scene &sc, F3 p1, F3 d, float remaining, int maxInteractions) {
+    const float lengthFactor = 1 - kShadowEpsilon;
+    F3 ro = p1, transmittance = f3(1, 1, 1);
+    int interactions = 0;
+    float maxt = remaining * lengthFactor;
+    while (remaining > 0) {
+        const float mint = kEpsilon * std::max(std::max(std::fabs(ro.x), std::fabs(ro.y)), std::fabs(ro.z));
+        Scene::Hit h;
+        const bool surface = sc.intersect(ro, d, mint, maxt, h);
+        if (!surface) break;
+        const ppg_bsdf &b = sc.bsdfs[sc.shapes[sc.hitShape(h)].bsdf];
+        if (interactions == maxInteractions || !bsdf_has_null(b)) return f3(0, 0, 0);
+        const F3 n = sc.hitGeoNormal(h, ro, d);
+        transmittance = transmittance * bsdf_eval_null(b, -dot(n, d));
+        if (is_zero(transmittance)) break;
+        if (++interactions > 100) break;
+        ro = ro + d * h.t; remaining -= h.t; maxt = remaining * lengthFactor;
+    }
+    return transmittance;
+}
 
 struct DirectSample { F3 value, d, n; float dist, pdf; int emitter; };
 // Scene::sampleAttenuatedEmitterDirect (scene.cpp:876-897) -> AreaLight::sampleDirect (emitters/area.cpp:158-173)
 // -> Shape::sampleDirect (shape.cpp:102-115) -> TriMesh::samplePosition (trimesh.cpp:412-423) -> Triangle::sample (libcore/triangle.cpp:24-59)
-static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float sx, float sy, DirectSample &out) {
+static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float sx, float sy, DirectSample &out, int maxInteractions = 0) {
     if (sc.emitterSamplers.empty()) return false;
     const size_t ei = Scene::cdfSample(sc.emitterCdf, sx);
     const float emPdf = sc.emitterCdf[ei + 1] - sc.emitterCdf[ei];
@@ -429,7 +467,7 @@ static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float
         out.d = d; out.n = n; out.dist = dist; out.emitter = (int) ei;
         if (dot(d, refN) >= 0 && dot(d, n) < 0 && pdf != 0) out.value = sc.radiance[ei] * (1.0f / pdf);
         else { out.pdf = 0; out.value = f3(0, 0, 0); return false; }
-        if (occluded(sc, ref, d, dist)) { out.pdf = pdf * emPdf; out.value = f3(0, 0, 0); return true; }
+        out.value = out.value * eval_transmittance(sc, ref, d, dist, maxInteractions);          // value *= evalTransmittance(...), scene.cpp:886-889
         out.value = out.value * (1.0f / emPdf);
         out.pdf = pdf * emPdf;
         return true;
@@ -456,7 +494,7 @@ static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float
     out.d = d; out.n = n; out.dist = dist; out.emitter = (int) ei;
     if (dot(d, refN) >= 0 && dot(d, n) < 0 && pdf != 0) out.value = sc.radiance[ei] * (1.0f / pdf);
     else { out.pdf = 0; out.value = f3(0, 0, 0); return false; }
-    if (occluded(sc, ref, d, dist)) { out.pdf = pdf * emPdf; out.value = f3(0, 0, 0); return true; }
+    out.value = out.value * eval_transmittance(sc, ref, d, dist, maxInteractions);
     out.value = out.value * (1.0f / emPdf);          // value *= transmittance / emPdf
     out.pdf = pdf * emPdf;
     return true;
@@ -492,9 +530,10 @@ static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
     if (z == 0) z = 1e-10f;
     return f3(px, py, z);
 }
-struct BsdfSample { F3 wo; float eta; bool delta; };
+struct BsdfSample { F3 wo; float eta; bool delta; bool null = false; };   // null: sampledType == ENull (index-matched transition)
+static inline bool bsdf_has_null(const ppg_bsdf &b) { return b.type == PPG_BSDF_THINDIELECTRIC; }                              // type & ENull
 static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK || b.type == PPG_BSDF_ROUGHCONDUCTOR || b.type == PPG_BSDF_ROUGHPLASTIC || b.type == PPG_BSDF_ROUGHDIELECTRIC || b.type == PPG_BSDF_PLASTIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
-static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC || b.type == PPG_BSDF_ROUGHDIELECTRIC; }
+static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC || b.type == PPG_BSDF_ROUGHDIELECTRIC || b.type == PPG_BSDF_THINDIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
 static inline float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
@@ -518,6 +557,18 @@ static inline float fresnel_conductor_exact(float cosThetaI, float eta, float k)
     const float term3 = a2pb2 * cosThetaI2 + sinThetaI4, term4 = term2 * sinThetaI2;
     const float Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
     return 0.5f * (Rp2 + Rs2);
+}
+// ---- thindielectric (src/bsdfs/thindielectric.cpp): R' = R + T R T + T R^3 T + ... (:160-165)
+static inline float thindielectric_reflectance(float cosThetaI, float eta) {
+    float ct; float R = fresnel_dielectric_ext(std::fabs(cosThetaI), ct, eta); const float T = 1 - R;
+    if (R < 1) R += T * T * R / (1 - R * R);
+    return R;
+}
+// bsdf->eval(bRec, EDiscrete) with typeMask == ENull and wo == -wi (thindielectric.cpp:153-176): what a straight-through ray keeps
+static inline F3 bsdf_eval_null(const ppg_bsdf &b, float cosThetaI) {
+    if (b.type != PPG_BSDF_THINDIELECTRIC) return f3(0, 0, 0);
+    const float R = thindielectric_reflectance(cosThetaI, b.eta[0]);
+    return f3(b.specular_transmittance[0], b.specular_transmittance[1], b.specular_transmittance[2]) * (1 - R);
 }
 // ---- MicrofacetDistribution (isotropic, Beckmann / GGX, visible-normal sampling), restated from src/bsdfs/microfacet.h
 static inline float mts_erfinv(float x) {       // math::erfinv, src/libcore/math.cpp:25-53 (Giles)
@@ -872,7 +923,7 @@ static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo, const float *table
 static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfSample &s, float &pdf, const float *tables = nullptr, Pcg32 *rng = nullptr) {
     bool flip = false;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; flip = true; } }
-    s.eta = 1.0f; s.delta = false; pdf = 0;
+    s.eta = 1.0f; s.delta = false; s.null = false; pdf = 0;
     if (b.type == PPG_BSDF_DIELECTRIC) {
         const float eta = b.eta[0], invEta = 1 / eta;
         float cosThetaT; const float F = fresnel_dielectric_ext(wi.z, cosThetaT, eta);
@@ -882,6 +933,13 @@ static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfS
         s.wo = f3(scale * wi.x, scale * wi.y, cosThetaT); s.eta = cosThetaT < 0 ? eta : invEta; pdf = 1 - F;
         const float factor = cosThetaT < 0 ? invEta : eta;      // ERadiance: solid angle compression
         return f3(b.specular_transmittance[0], b.specular_transmittance[1], b.specular_transmittance[2]) * (factor * factor);
+    }
+    if (b.type == PPG_BSDF_THINDIELECTRIC) {                                                   // thindielectric.cpp:206-240
+        const float R = thindielectric_reflectance(wi.z, b.eta[0]);
+        s.delta = true; s.eta = 1.0f;
+        if (sx <= R) { s.wo = f3(-wi.x, -wi.y, wi.z); pdf = R; return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]); }
+        s.null = true; s.wo = f3(-wi.x, -wi.y, -wi.z); pdf = 1 - R;
+        return f3(b.specular_transmittance[0], b.specular_transmittance[1], b.specular_transmittance[2]);
     }
     if (b.type == PPG_BSDF_CONDUCTOR) {
         if (wi.z <= 0) return f3(0, 0, 0);
@@ -1014,7 +1072,7 @@ public:
             if (doNee && bsdf_has_smooth(bsdf)) {                                               // GP:1967-1969
                 const float ex = rng.next1D(), ey = rng.next1D();
                 DirectSample ds;
-                if (sample_emitter_direct(sc, its.p, refN, ex, ey, ds) && !is_zero(ds.value)) {
+                if (sample_emitter_direct(sc, its.p, refN, ex, ey, ds, prm.max_depth - depth - 1) && !is_zero(ds.value)) {     // interactions, GP:1970
                     const F3 dl = its.toLocal(ds.d);
                     const float woDotGeoN2 = dot(its.geoN, ds.d);
                     if (!prm.strict_normals || woDotGeoN2 * dl.z > 0) {
@@ -1047,18 +1105,47 @@ public:
             if (woDotGeoN * bs.wo.z <= 0 && prm.strict_normals) break;                          // GP:2028-2032
             o = its.p; d = wo;
             throughput = throughput * bsdfWeight; eta *= bs.eta;
-            // ---- next hit + emitter lookup, GP:2078-2091 (rayIntersectAndLookForEmitter, no null surfaces in scope)
+            if (bs.null) {                                                                      // index-matched transition, GP:2044-2075
+                // (smooth/null hybrids such as `mask` are not in scope, so no vertex is recorded here: leaf == nullptr for thindielectric)
+                emittedRadiance = !scattered;                                                   // ERadiance : ERadianceNoEmission
+                ray_intersect(sc, o, d, kEpsilon, std::numeric_limits<float>::infinity(), its);
+                nVerticesTraced++;
+                depth++;
+                continue;                                                                       // no Russian roulette, `scattered` unchanged
+            }
+            // ---- next hit + emitter lookup, GP:2078-2091 -> rayIntersectAndLookForEmitter GP:2184-2245: the emitter is looked for THROUGH
+            // index-matched surfaces (at most maxDepth - depth - 1 of them), the path itself continues at the first hit
             F3 value = f3(0, 0, 0);
             Its next; ray_intersect(sc, o, d, kEpsilon, std::numeric_limits<float>::infinity(), next);
             nVerticesTraced++;
-            if (next.valid) {
-                const ppg_shape &ns = sc.shapes[next.shape];
-                if (ns.emitter >= 0 && dot(next.shN, -d) > 0) value = sc.radiance[ns.emitter];
+            int qEmitter = -1; F3 qN = f3(0, 0, 0); float qDist = 0;                            // dRec.setQuery(ray, *its), records.inl:170-178
+            {
+                const Its *cur = &next; Its its2; F3 ro = o, transmittance = f3(1, 1, 1);
+                int interactions = 0; const int maxInteractions = prm.max_depth - depth - 1;
+                bool surface, lost = false;
+                while (true) {
+                    surface = cur->valid;
+                    if (surface && (interactions == maxInteractions || !bsdf_has_null(sc.bsdfs[sc.shapes[cur->shape].bsdf]) || sc.shapes[cur->shape].emitter >= 0)) break;
+                    if (!surface) break;
+                    if (is_zero(transmittance)) { lost = true; break; }
+                    const F3 wol = cur->toLocal(d);
+                    transmittance = transmittance * bsdf_eval_null(sc.bsdfs[sc.shapes[cur->shape].bsdf], -wol.z);   // bRec(its, -wo, wo), typeMask ENull, EDiscrete
+                    ro = ro + d * cur->t;
+                    ray_intersect(sc, ro, d, kEpsilon, std::numeric_limits<float>::infinity(), its2); cur = &its2;
+                    if (++interactions > 100) { lost = true; break; }
+                }
+                if (!lost && surface) {
+                    const ppg_shape &ns = sc.shapes[cur->shape];
+                    if (ns.emitter >= 0) {
+                        qEmitter = ns.emitter; qN = cur->shN; qDist = cur->t;                   // dist: the last segment only (quirk of setQuery after ray.o moved)
+                        if (dot(cur->shN, -d) > 0) value = transmittance * sc.radiance[ns.emitter];
+                    }
+                }
             }
             const bool isDelta = bs.delta;
             {
                 float emitterPdf = 0;                                                            // GP:2084-2087
-                if (doNee && !isDelta && !is_zero(value)) emitterPdf = pdf_emitter_direct(sc, sc.shapes[next.shape].emitter, its.p, refN, d, next.shN, next.t);
+                if (doNee && !isDelta && !is_zero(value)) emitterPdf = pdf_emitter_direct(sc, qEmitter, its.p, refN, d, qN, qDist);
                 const float weight = mi_weight(woPdf, emitterPdf);
                 const F3 L = throughput * value * weight;
                 if (!is_zero(L)) recordRadiance(L);

@@ -410,6 +410,7 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 #define PPG_BSDF_T_ROUGHPLASTIC 5u
 #define PPG_BSDF_T_ROUGHDIELECTRIC 6u
 #define PPG_BSDF_T_PLASTIC 7u
+#define PPG_BSDF_T_THINDIELECTRIC 8u
 #define PPG_BSDF_NONLINEAR 2u
 // 6 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)},
 // {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), -, -}
@@ -433,7 +434,8 @@ __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
     return b;
 }
 __device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE || b.type == PPG_BSDF_T_ROUGHCONDUCTOR || b.type == PPG_BSDF_T_ROUGHPLASTIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC || b.type == PPG_BSDF_T_PLASTIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
-__device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC; }
+__device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC || b.type == PPG_BSDF_T_THINDIELECTRIC; }
+__device__ __forceinline__ bool bsdf_has_null(const Bsdf &b) { return b.type == PPG_BSDF_T_THINDIELECTRIC; }                     // type & ENull
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
 __device__ __forceinline__ float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
@@ -658,6 +660,17 @@ __device__ __forceinline__ float3 roughplastic_sample(const Bsdf &b, float3 wi, 
     return roughplastic_eval(b, wi, wo) * (1.0f / pdf);       // Spectrum / Float, core/spectrum.h:415-425
 }
 
+// ---- thindielectric (src/bsdfs/thindielectric.cpp): R' = R + T R T + T R^3 T + ... (:160-165)
+__device__ __forceinline__ float thindielectric_reflectance(float cosThetaI, float eta) {
+    float ct; float R = fresnel_dielectric_ext(fabsf(cosThetaI), ct, eta); const float T = 1.f - R;
+    if (R < 1.f) R += T * T * R / (1.f - R * R);
+    return R;
+}
+// bsdf->eval(bRec, EDiscrete) with typeMask == ENull and wo == -wi (thindielectric.cpp:153-176): what a straight-through ray keeps
+__device__ __forceinline__ float3 bsdf_eval_null(const Bsdf &b, float cosThetaI) {
+    if (b.type != PPG_BSDF_T_THINDIELECTRIC) return f3(0, 0, 0);
+    return b.trans * (1.f - thindielectric_reflectance(cosThetaI, b.eta));
+}
 // ---- plastic (src/bsdfs/plastic.cpp): delta reflection off the coat + diffuse base; eval / pdf in the solid-angle measure see the diffuse part only
 __device__ __forceinline__ float3 plastic_diffuse(const Bsdf &b) {                                       // plastic.cpp:266-271
     const float3 diff = b.refl;
@@ -788,7 +801,16 @@ __device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
     return PPG_INV_PI * wo.z;
 }
 // `rng`: the path's sampler, consumed only by models that draw from it themselves (roughdielectric)
-__device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf, Pcg32 &rng) {
+// isNull: sampledType == ENull (index-matched transition straight through the surface)
+__device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf, Pcg32 &rng, bool &isNull) {
+    isNull = false;
+    if (b.type == PPG_BSDF_T_THINDIELECTRIC) {                                                 // thindielectric.cpp:206-240
+        const float R = thindielectric_reflectance(wi.z, b.eta);
+        delta = true; eta = 1.0f;
+        if (sx <= R) { wo = f3(-wi.x, -wi.y, wi.z); pdf = R; return b.refl; }
+        isNull = true; wo = f3(-wi.x, -wi.y, -wi.z); pdf = 1.f - R;
+        return b.trans;
+    }
     bool flip = false;
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; flip = true; }
     eta = 1.0f; delta = false; pdf = 0.f;
@@ -1074,6 +1096,78 @@ __device__ __forceinline__ uint32_t cdf_sample(const float *__restrict__ cdf, ui
     int index = (int) lo - 1; if (index < 0) index = 0; if ((uint32_t) index > size - 2) index = (int) size - 2;
     while (cdf[index + 1] - cdf[index] == 0.f && (uint32_t) index < size - 1) ++index;
     return (uint32_t) index;
+}
+
+// The normal ShapeKDTree::rayIntersect(ray, t, shape, n, uv) reports (skdtree.cpp:165-175: plain face normal; spheres: geoFrame.n)
+template <class Acc>
+__device__ __forceinline__ float3 hit_geo_normal(const Acc &A_, const Hit &h, float3 ro, float3 rd) {
+    if (h.prim & PPG_SPHERE_BIT) {
+        const uint32_t k = h.prim & ~PPG_SPHERE_BIT;
+        const float4 cr = __ldg(&A_.g.spheres[2 * k]), mt = __ldg(&A_.g.spheres[2 * k + 1]);
+        const float3 c = f3(cr.x, cr.y, cr.z);
+        float3 p = ro + rd * h.t; p = c + normalize(p - c) * cr.w;
+        float3 n = normalize(p - c); if (__float_as_uint(mt.z)) n = n * -1.0f;
+        return n;
+    }
+    const float4 g0 = A_.geom(6 * h.tri), g1 = A_.geom(6 * h.tri + 1), g2 = A_.geom(6 * h.tri + 2);
+    const float3 p0 = f3(g0.x, g0.y, g0.z), p1 = f3(g1.x, g1.y, g1.z), p2 = f3(g2.x, g2.y, g2.z);
+    return normalize(cross(p1 - p0, p2 - p0));
+}
+template <class Acc> __device__ __forceinline__ int hit_bsdf(const Acc &A_, const Hit &h) {
+    return (h.prim & PPG_SPHERE_BIT) ? __float_as_int(__ldg(&A_.g.spheres[2 * (h.prim & ~PPG_SPHERE_BIT) + 1]).x) : A_.meta(h.tri).x;
+}
+// Scene::evalTransmittance with index-matched surfaces (scene.cpp:619-679, both end points on surfaces): a null surface multiplies its
+// straight-through transmittance (evaluated in the GEOMETRIC frame, :650-655) and the ray continues behind it, at most maxInteractions
+// times (negative = unlimited); anything else blocks.  Full-feature variants only; not inlined (rare path, keeps the callers' registers).
+template <class Acc>
+__device__ __noinline__ float3 eval_transmittance(const Acc &A_, float3 p1, float3 d, float remaining, int maxInteractions) {
+    const float lengthFactor = 1.f - PPG_SHADOW_EPSILON;
+    float3 ro = p1, transmittance = f3(1, 1, 1);
+    int interactions = 0;
+    float maxt = remaining * lengthFactor;
+    while (remaining > 0.f) {
+        const float mint = PPG_EPSILON * fmaxf(fmaxf(fabsf(ro.x), fabsf(ro.y)), fabsf(ro.z));
+        Hit h;
+        if (!bvh_intersect<true>(A_, ro, d, mint, maxt, h)) break;
+        const Bsdf b = load_bsdf<true>(A_, hit_bsdf(A_, h));
+        if (interactions == maxInteractions || !bsdf_has_null(b)) return f3(0, 0, 0);
+        const float3 n = hit_geo_normal(A_, h, ro, d);
+        transmittance = transmittance * bsdf_eval_null(b, -dot(n, d));
+        if (is_zero(transmittance)) break;
+        if (++interactions > 100) break;
+        ro = ro + d * h.t; remaining -= h.t; maxt = remaining * lengthFactor;
+    }
+    return transmittance;
+}
+// rayIntersectAndLookForEmitter (GP:2184-2245) behind a first hit on an index-matched, non-emitting surface: follow the ray through up to
+// maxInteractions null surfaces; returns transmittance * Le of the emitter found (0 if none / blocked) and the query the light-sampling
+// pdf needs (emitter, shading normal, distance of the LAST segment -- dRec.setQuery after ray.o has moved, a reference quirk kept).
+template <class Acc>
+__device__ __noinline__ float3 look_through(const Acc &A_, float3 o, float3 d, const Its &first, float firstT, int maxInteractions,
+                                            int &qEmitter, float3 &qN, float &qDist) {
+    qEmitter = -1; qN = f3(0, 0, 0); qDist = 0.f;
+    float3 ro = o, transmittance = f3(1, 1, 1);
+    Its cur = first; float curT = firstT; bool surface = true;
+    int interactions = 0;
+    for (;;) {
+        if (surface) {
+            const Bsdf b = load_bsdf<true>(A_, cur.bsdf);
+            if (interactions == maxInteractions || !bsdf_has_null(b) || cur.emitter >= 0) break;
+            if (is_zero(transmittance)) return f3(0, 0, 0);
+            transmittance = transmittance * bsdf_eval_null(b, -dot(d, cur.shN));            // bRec(its, -wo, wo) in the shading frame
+        } else break;
+        ro = ro + d * curT;
+        const float mint = PPG_EPSILON * fmaxf(fmaxf(fmaxf(fabsf(ro.x), fabsf(ro.y)), fabsf(ro.z)), PPG_EPSILON);
+        Hit h;
+        surface = bvh_intersect<true>(A_, ro, d, mint, __int_as_float(0x7f800000), h);
+        if (surface) { fill_its<true>(A_, h, ro, d, cur); curT = h.t; }
+        if (++interactions > 100) return f3(0, 0, 0);
+    }
+    if (!surface || cur.emitter < 0) return f3(0, 0, 0);
+    qEmitter = cur.emitter; qN = cur.shN; qDist = curT;
+    if (!(dot(cur.shN, -d) > 0.f)) return f3(0, 0, 0);
+    const float4 r = A_.radiance(cur.emitter);
+    return transmittance * f3(r.x, r.y, r.z);
 }
 
 struct DirectSample { float3 value, d; float pdf; };

@@ -35,6 +35,8 @@ struct PathState {      // 5 x float4 per path
     float4 *s5;         // NEE only: woPdf of the last sampled direction, refN.xyz of the vertex it left (GP:2084-2087)
     float4 *s6;         // NEE only: bits(slab slot of the last vertex | isDelta<<31 | hasVertex<<30), 0, 0, 0
 };
+#define PPG_FLAG_NULL 2u             // the ray arrived through an index-matched (ENull) transition: plain intersection, no emitter lookup / MIS (GP:2070-2074)
+#define PPG_FLAG_UNSCATTERED 4u      // `scattered` is still false (camera ray that has only crossed null surfaces so far)
 #define PPG_FLAG_DYING 1u            // lost Russian roulette: trace one more ray for the emitter lookup, then stop (GP:2078-2091 precede GP:2123-2142)
 
 struct VertexSlab {     // one slab per path depth; entry i belongs to the i-th live path of that bounce
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_
                 maxt = __int_as_float(0x7f800000);
             }
         }
-        bool wroteVertex = false, wroteNee = false;
+        bool wroteVertex = false, wroteNee = false, unscattered = FIRST;
         if (alive) {
             ++raysLocal;
             Hit hit;
@@ -146,7 +148,25 @@ __global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_
                 // emitted radiance: primary hit via EEmittedRadiance (GP:1917-1919), later hits via the `value`
                 // returned by rayIntersectAndLookForEmitter (GP:2078-2091; miWeight(woPdf, 0) == 1)
                 float3 Lhit = f3(0, 0, 0);
-                if (its.emitter >= 0 && (!FIRST || !P.hideEmitters)) {
+                const bool viaNull = FULL && !FIRST && (flags & PPG_FLAG_NULL);
+                unscattered = FIRST || (FULL && (flags & PPG_FLAG_UNSCATTERED));
+                if (FULL && viaNull) {
+                    // after a null transition the hit is an ordinary path vertex: emitted radiance only while ERadiance is still
+                    // requested, i.e. the path has not scattered yet (GP:2070-2071, 1917-1919)
+                    if (its.emitter >= 0 && unscattered && !P.hideEmitters && dot(its.shN, -d) > 0.f) {
+                        const float4 r = sc.radiance(its.emitter);
+                        Li = Li + thr * f3(r.x, r.y, r.z);
+                    }
+                } else if (FULL && !FIRST && its.emitter < 0 && bsdf_has_null(load_bsdf<FULL>(sc, its.bsdf))) {
+                    // first hit on an index-matched surface: the emitter lookup continues behind it (GP:2184-2245)
+                    int qEmitter; float3 qN; float qDist;
+                    const float3 value = look_through(sc, o, d, its, hit.t, P.maxDepth - P.depth, qEmitter, qN, qDist);
+                    if (!is_zero(value)) {
+                        Lhit = thr * value;
+                        if (NEE && P.doNee && !(prevSlot >> 31)) Lhit = Lhit * mi_weight(prevWoPdf, pdf_emitter_direct<FULL>(sc.g, qEmitter, o, prevRefN, d, qN, qDist));
+                        Li = Li + Lhit;
+                    }
+                } else if (its.emitter >= 0 && (!FIRST || !P.hideEmitters)) {
                     if (dot(its.shN, -d) > 0.f) {                                    // area.cpp:104-109
                         const float4 r = sc.radiance(its.emitter);
                         Lhit = thr * f3(r.x, r.y, r.z);
@@ -182,10 +202,10 @@ __global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_
                 float frac = P.fixedFraction;
                 if (smooth && P.lossMode != 0) frac = logistic(la.z);                 // GP:1946-1949
                 // ---- sampleMat, GP:1650-1691
-                float woPdf, bsdfPdf, dTreePdf, bsEta = 1.f; float3 wo, bsdfWeight; bool isDelta = false;
+                float woPdf, bsdfPdf, dTreePdf, bsEta = 1.f; float3 wo, bsdfWeight; bool isDelta = false, isNull = false;
                 float sx = rng.next1D(); const float sy = rng.next1D();
                 if (!P.isBuilt || !smooth) {                                         // not built / no dTree / all-delta BSDF (GP:1654)
-                    bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng);
+                    bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng, isNull);
                     woPdf = bsdfPdf; dTreePdf = 0.f;
                 } else {
                     const SampNode *tree = P.tree.samp + __float_as_uint(la.x);
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_
                     float3 result; bool zero = false, deltaEarly = false;
                     if (sx < frac) {
                         sx /= frac;
-                        result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng);
+                        result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng, isNull);
                         if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0.f; zero = true; }
                         else if (FULL && isDelta) { dTreePdf = 0.f; woPdf = bsdfPdf * frac; result = result * (1.0f / frac); deltaEarly = true; }   // GP:1670-1676
                         else result = result * bsdfPdf;
@@ -223,7 +243,12 @@ __global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_
                         // Scene::evalTransmittance: shadow ray, epsilon scaled without the clamp (skdtree.cpp:154-158)
                         const float smint = PPG_EPSILON * fmaxf(fmaxf(fabsf(its.p.x), fabsf(its.p.y)), fabsf(its.p.z));
                         Hit sh;      // (shadow rays are not path vertices: not counted in the samples metric)
-                        if (!bvh_intersect<FULL>(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh)) {
+                        bool visible;
+                        if (FULL) {  // index-matched surfaces attenuate instead of blocking (Scene::evalTransmittance, interactions = maxDepth - depth - 1, GP:1970)
+                            const float3 T = eval_transmittance(sc, its.p, ds.d, dist, P.maxDepth - P.depth - 1);
+                            ds.value = ds.value * T; visible = !is_zero(ds.value);
+                        } else visible = !bvh_intersect<FULL>(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh);
+                        if (visible) {
                             const float3 dl = its.toLocal(ds.d);
                             if (!P.strictNormals || dot(its.geoN, ds.d) * dl.z > 0.f) {
                                 const float3 bsdfVal = bsdf_eval(bsdf, its.wi, dl);
@@ -276,7 +301,8 @@ __global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_
                     if (NEE) { prevWoPdf = woPdf; prevRefN = refN; prevSlot = i | (isDelta ? 0x80000000u : 0u) | (wroteVertex ? 0x40000000u : 0u); }
                     // ---- Russian roulette (GP:2123-2142); the decision takes effect after the next emitter lookup
                     rrRecip = 1.f; flags = 0;
-                    if (P.depth >= P.rrDepth) {
+                    if (FULL && isNull) flags = PPG_FLAG_NULL | (unscattered ? PPG_FLAG_UNSCATTERED : 0u);   // GP:2044-2075: no roulette, `scattered` unchanged
+                    else if (P.depth >= P.rrDepth) {
                         float successProb = 1.0f;
                         if (smooth && !isDelta) {
                             if (!P.isBuilt) successProb = max3(thr) * eta * eta;

@@ -136,6 +136,31 @@ def cbox_smooth_plastic(cbox: SceneDesc) -> SceneDesc:
     return sc
 
 
+def cbox_thin_glass(cbox: SceneDesc) -> SceneDesc:
+    """CBOX with two thin-dielectric panes (thindielectric.cpp): a horizontal one under the ceiling light, so that ALL direct light
+    reaches the room through an index-matched (ENull) surface -- light sampling multiplies the pane's transmittance
+    (Scene::evalTransmittance) and the emitter lookup after BSDF sampling looks through it (GP:2184-2245) -- and a tilted, tinted
+    one in front of the boxes that the camera looks through (null transition on the primary ray: `scattered` stays false)."""
+    import copy
+    from .scene import BSDF_THINDIELECTRIC
+    sc = copy.copy(cbox)
+    base = _pad_bsdfs(sc.bsdfs); nb = len(base)
+    sc.bsdfs = np.concatenate([base, np.stack([_make_bsdf(BSDF_THINDIELECTRIC, 0, (1, 1, 1), (1, 1, 1), (1.5046 / 1.000277,) * 3),
+                                               _make_bsdf(BSDF_THINDIELECTRIC, 0, (1, 1, 1), (0.7, 0.9, 0.95), (1.33,) * 3)])]).astype(np.float32)
+    sc.bsdf_names = list(sc.bsdf_names) + ["thin_glass", "thin_tinted"]
+    quads = [np.float32([[0.5, 500, 0.5], [555.5, 500, 0.5], [555.5, 500, 558.7], [0.5, 500, 558.7]]),
+             np.float32([[60, 20, 40], [500, 20, 60], [500, 430, 150], [60, 430, 130]])]
+    nv, nt, ns = len(sc.positions), len(sc.indices), len(sc.shapes)
+    P = np.concatenate(quads)
+    sc.positions = np.concatenate([sc.positions, P]); sc.normals = np.concatenate([sc.normals, np.zeros_like(P)])
+    sc.uvs = np.concatenate([sc.uvs, np.zeros((len(P), 2), np.float32)])
+    tris = np.uint32([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]]) + nv
+    sc.indices = np.concatenate([sc.indices, tris]).astype(np.uint32)
+    sc.triangle_shape = np.concatenate([sc.triangle_shape, np.uint32([ns, ns, ns + 1, ns + 1])])
+    sc.shapes = np.concatenate([sc.shapes, np.array([[nt, 2, nb, -1, 0, 0, 0, 0], [nt + 2, 2, nb + 1, -1, 0, 0, 0, 0]], np.int32)])
+    return sc
+
+
 def cbox_rough_metal(cbox: SceneDesc) -> SceneDesc:
     """CBOX whose boxes are rough conductors: the small box GGX alpha 0.1 with the eta/k of spaceship.xml's "RoughAluminium",
     the large box Beckmann alpha 0.3 -- glossy BSDFs are guided (ESmooth) and take part in light sampling."""

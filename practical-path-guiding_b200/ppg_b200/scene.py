@@ -43,6 +43,7 @@ BSDF_ROUGHCONDUCTOR = 4
 BSDF_ROUGHPLASTIC = 5
 BSDF_ROUGHDIELECTRIC = 6
 BSDF_PLASTIC = 7
+BSDF_THINDIELECTRIC = 8
 BSDF_FLAG_NONLINEAR = 2
 BSDF_FLAG_TWOSIDED = 1
 
@@ -504,6 +505,13 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
         entry = _make_bsdf(BSDF_DIELECTRIC, flags, sr, st, (eta, eta, eta))
+    elif typ == "thindielectric":       # src/bsdfs/thindielectric.cpp:88-104
+        if flags & BSDF_FLAG_TWOSIDED:
+            raise ValueError("twosided cannot wrap a transmissive BSDF")
+        eta = _lookup_ior(props.get("intIOR"), "bk7") / _lookup_ior(props.get("extIOR"), "air")
+        sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
+        st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
+        entry = _make_bsdf(BSDF_THINDIELECTRIC, flags, sr, st, (eta, eta, eta))
     elif typ == "roughdielectric":      # src/bsdfs/roughdielectric.cpp:183-210
         if flags & BSDF_FLAG_TWOSIDED:
             raise ValueError("twosided cannot wrap a transmissive BSDF")

@@ -408,3 +408,21 @@ def test_smooth_plastic_matches_oracle(extra):
     for a, b in zip(st["iterations"], ost["iterations"]):
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
         assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(hideEmitters="true", nee="kickstart"), dict(maxDepth="4", nee="always")])
+def test_thin_dielectric_null_transitions_match_oracle(extra):
+    """CBOX with thin-dielectric panes (thindielectric.cpp): index-matched (ENull) transitions.  Covers the null branch of Li
+    (GP:2044-2075: no roulette, `scattered` unchanged, emitted radiance only while unscattered), the emitter lookup THROUGH null
+    surfaces (rayIntersectAndLookForEmitter GP:2184-2245, incl. its last-segment distance quirk in the MIS pdf) and the attenuated
+    shadow rays of light sampling (Scene::evalTransmittance scene.cpp:619-679) with their interaction budget (maxDepth 4)."""
+    from ppg_b200.builtin_scenes import cbox_thin_glass
+    sc = cbox_thin_glass(load_cbox(128))
+    props = dict(dict(sc.integrator, budget="60"), **extra)
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert relmse(img, ref) <= 1e-5, relmse(img, ref)
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 1e-4 * ost["total_vertices"]
+    for a, b in zip(st["iterations"], ost["iterations"]):
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
+        assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-4)

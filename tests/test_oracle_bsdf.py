@@ -109,3 +109,35 @@ def test_dielectric_and_conductor_are_delta_and_energy_conserving():
     wi = np.tile(np.array([[0.6, 0, 0.8]], np.float32), (4, 1))
     wo, w, pdf, delta = O.bsdf_sample(mirror, wi, rng.random((4, 2), dtype=np.float32))
     assert np.allclose(wo, [-0.6, 0, 0.8]) and np.allclose(w, 1.0, atol=1e-5) and np.allclose(pdf, 1) and delta.all()   # eta=0,k=1: perfect mirror (conductor.cpp:159-176)
+
+
+def test_thin_dielectric_folds_internal_reflections_and_transmits_straight():
+    """thindielectric.cpp:206-240: reflection with probability R' = R + T^2 R / (1 - R^2), else the ray goes straight through (ENull)."""
+    b = O.make_bsdf(type=8, reflectance=(1, 1, 1), transmittance=(0.8, 0.9, 1.0), eta=(1.5, 1.5, 1.5))
+    rng = np.random.default_rng(3)
+    n = 200000
+    for cz in (0.9, 0.2, -0.5):
+        wi = np.tile(np.array([[np.sqrt(1 - cz ** 2), 0, cz]], np.float32), (n, 1))
+        wo, w, pdf, delta = O.bsdf_sample(b, wi, rng.random((n, 2), dtype=np.float32))
+        assert delta.all()
+        refl = wo[:, 2] * cz > 0
+        c = abs(cz); ct = np.sqrt(1 - (1 - c * c) / 2.25)
+        R = 0.5 * (((c - 1.5 * ct) / (c + 1.5 * ct)) ** 2 + ((1.5 * c - ct) / (1.5 * c + ct)) ** 2); Rp = R + (1 - R) ** 2 * R / (1 - R * R)
+        assert abs(refl.mean() - Rp) < 0.005 and np.allclose(pdf[refl], Rp, atol=1e-5) and np.allclose(pdf[~refl], 1 - Rp, atol=1e-5)
+        assert np.allclose(wo[~refl], -wi[~refl], atol=1e-7) and np.allclose(wo[refl], wi[refl] * np.float32([-1, -1, 1]), atol=1e-7)
+        assert np.allclose(w[~refl], [0.8, 0.9, 1.0]) and np.allclose(w[refl], 1.0)
+
+
+def test_oracle_looks_through_null_surfaces_consistently():
+    """With every light path crossing an index-matched pane, BSDF sampling alone (nee=never: emitter lookup through the pane) and the
+    plain CBOX bracket the result; light sampling adds the reference's known excess (MIS pdf from the last segment only, GP:2236 +
+    records.inl:170-178) -- both facts pinned here so that a change of either code path is noticed."""
+    from common import load_cbox
+    from ppg_b200.builtin_scenes import cbox_thin_glass
+    base = load_cbox(48); sc = cbox_thin_glass(base)
+    mean = {}
+    for name, scene, nee in (("plain", base, "never"), ("never", sc, "never"), ("always", sc, "always")):
+        o = O.Oracle(O.params_from_xml(dict(scene.integrator, budget="252", nee=nee)), scene, kind="port"); img, st = o.render()
+        assert np.isfinite(img).all(); mean[name] = float(img.mean())
+    assert 0.85 * mean["plain"] < mean["never"] < mean["plain"]
+    assert 1.1 * mean["never"] < mean["always"] < 1.6 * mean["never"]
