@@ -127,6 +127,7 @@ typedef enum ppg_microfacet { PPG_MICROFACET_BECKMANN = 0, PPG_MICROFACET_GGX = 
 
 #define PPG_BSDF_FLAG_TWOSIDED 1u /* src/bsdfs/twosided.cpp:108-184 wrapping the model */
 #define PPG_BSDF_FLAG_NONLINEAR 2u /* roughplastic "nonlinear" (roughplastic.cpp:366-369) */
+#define PPG_BSDF_FLAG_MASK 4u     /* src/bsdfs/mask.cpp:113-220 wrapping the (possibly twosided) model: constant `opacity`; a smooth/null hybrid */
 #define PPG_BSDF_TABLE_SIZE 100   /* theta samples of the rough-transmittance tables (data/microfacet/*.dat) */
 
 typedef struct ppg_bsdf {
@@ -142,8 +143,9 @@ typedef struct ppg_bsdf {
     float    fdr_int;         /* roughplastic: 1 - internal diffuse rough transmittance (Fdr of roughplastic.cpp:364) */
     float    specular_sampling_weight;  /* roughplastic: sAvg / (dAvg + sAvg) (roughplastic.cpp:269-272) */
     int32_t  table;           /* roughplastic: index into ppg_scene_desc.bsdf_tables (external rough transmittance over cos(theta)^(1/4)) */
-    float    reserved[2];
-} ppg_bsdf;                   /* 96 bytes */
+    float    opacity[3];      /* PPG_BSDF_FLAG_MASK: linear RGB opacity (mask.cpp:63-66) */
+    float    reserved[3];
+} ppg_bsdf;                   /* 112 bytes */
 
 typedef struct ppg_shape {
     uint32_t first_triangle;  /* triangles of a shape are contiguous */

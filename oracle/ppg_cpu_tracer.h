@@ -531,9 +531,9 @@ static inline F3 square_to_cosine_hemisphere(float sx, float sy) {
     return f3(px, py, z);
 }
 struct BsdfSample { F3 wo; float eta; bool delta; bool null = false; };   // null: sampledType == ENull (index-matched transition)
-static inline bool bsdf_has_null(const ppg_bsdf &b) { return b.type == PPG_BSDF_THINDIELECTRIC; }                              // type & ENull
+static inline bool bsdf_has_null(const ppg_bsdf &b) { return b.type == PPG_BSDF_THINDIELECTRIC || (b.flags & PPG_BSDF_FLAG_MASK); }                              // type & ENull
 static inline bool bsdf_has_smooth(const ppg_bsdf &b) { return b.type == PPG_BSDF_DIFFUSE || b.type == PPG_BSDF_NULL_BLACK || b.type == PPG_BSDF_ROUGHCONDUCTOR || b.type == PPG_BSDF_ROUGHPLASTIC || b.type == PPG_BSDF_ROUGHDIELECTRIC || b.type == PPG_BSDF_PLASTIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
-static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & PPG_BSDF_FLAG_TWOSIDED) || b.type == PPG_BSDF_DIELECTRIC || b.type == PPG_BSDF_ROUGHDIELECTRIC || b.type == PPG_BSDF_THINDIELECTRIC; }
+static inline bool bsdf_has_transmission_or_backside(const ppg_bsdf &b) { return (b.flags & (PPG_BSDF_FLAG_TWOSIDED | PPG_BSDF_FLAG_MASK)) || b.type == PPG_BSDF_DIELECTRIC || b.type == PPG_BSDF_ROUGHDIELECTRIC || b.type == PPG_BSDF_THINDIELECTRIC; }
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
 static inline float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
@@ -566,6 +566,7 @@ static inline float thindielectric_reflectance(float cosThetaI, float eta) {
 }
 // bsdf->eval(bRec, EDiscrete) with typeMask == ENull and wo == -wi (thindielectric.cpp:153-176): what a straight-through ray keeps
 static inline F3 bsdf_eval_null(const ppg_bsdf &b, float cosThetaI) {
+    if (b.flags & PPG_BSDF_FLAG_MASK) return f3(1 - b.opacity[0], 1 - b.opacity[1], 1 - b.opacity[2]);   // mask.cpp:118-119: Spectrum(1) - opacity
     if (b.type != PPG_BSDF_THINDIELECTRIC) return f3(0, 0, 0);
     const float R = thindielectric_reflectance(cosThetaI, b.eta[0]);
     return f3(b.specular_transmittance[0], b.specular_transmittance[1], b.specular_transmittance[2]) * (1 - R);
@@ -899,7 +900,7 @@ static inline const float *bsdf_table(const ppg_bsdf &b, const float *tables) { 
 
 // eval / pdf with the solid-angle measure (delta models return 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
 // twosided per src/bsdfs/twosided.cpp:108-184
-static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables = nullptr) {
+static inline F3 bsdf_eval_inner(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables) {
     if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
@@ -909,7 +910,7 @@ static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables 
     if (wi.z <= 0 || wo.z <= 0) return f3(0, 0, 0);
     return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]) * (kInvPi * wo.z);
 }
-static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables = nullptr) {
+static inline float bsdf_pdf_inner(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables) {
     if (!bsdf_has_smooth(b)) return 0.0f;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; wo.z = -wo.z; } }
     if (b.type == PPG_BSDF_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
@@ -920,7 +921,7 @@ static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo, const float *table
     return kInvPi * wo.z;   // warp::squareToCosineHemispherePdf
 }
 // `rng`: the path's sampler, consumed only by models that draw from it themselves (roughdielectric)
-static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfSample &s, float &pdf, const float *tables = nullptr, Pcg32 *rng = nullptr) {
+static inline F3 bsdf_sample_inner(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfSample &s, float &pdf, const float *tables, Pcg32 *rng) {
     bool flip = false;
     if (b.flags & PPG_BSDF_FLAG_TWOSIDED) { if (wi.z < 0) { wi.z = -wi.z; flip = true; } }
     s.eta = 1.0f; s.delta = false; s.null = false; pdf = 0;
@@ -969,6 +970,34 @@ static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfS
     pdf = kInvPi * s.wo.z;
     if (flip) s.wo.z = -s.wo.z;
     return f3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+}
+
+// ---- mask (src/bsdfs/mask.cpp:113-220), the outermost wrapper: nested model scaled by the opacity, or a straight-through null transition
+static inline F3 mask_opacity(const ppg_bsdf &b) { return f3(b.opacity[0], b.opacity[1], b.opacity[2]); }
+static inline float mask_prob(const ppg_bsdf &b) { return b.opacity[0] * 0.212671f + b.opacity[1] * 0.715160f + b.opacity[2] * 0.072169f; }   // getLuminance, spectrum.h:725-727
+static inline F3 bsdf_eval(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables = nullptr) {
+    if (b.flags & PPG_BSDF_FLAG_MASK) return bsdf_eval_inner(b, wi, wo, tables) * mask_opacity(b);
+    return bsdf_eval_inner(b, wi, wo, tables);
+}
+static inline float bsdf_pdf(const ppg_bsdf &b, F3 wi, F3 wo, const float *tables = nullptr) {
+    if (b.flags & PPG_BSDF_FLAG_MASK) return bsdf_pdf_inner(b, wi, wo, tables) * mask_prob(b);
+    return bsdf_pdf_inner(b, wi, wo, tables);
+}
+// `rng`: the path's sampler, consumed only by models that draw from it themselves (roughdielectric)
+static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfSample &s, float &pdf, const float *tables = nullptr, Pcg32 *rng = nullptr) {
+    if (b.flags & PPG_BSDF_FLAG_MASK) {                                                       // mask.cpp:186-207
+        const F3 opacity = mask_opacity(b); const float prob = mask_prob(b);
+        if (sx < prob) {
+            sx /= prob;
+            F3 result = (bsdf_sample_inner(b, wi, sx, sy, s, pdf, tables, rng) * opacity) * (1.0f / prob);
+            pdf *= prob;
+            return result;
+        }
+        s.wo = f3(-wi.x, -wi.y, -wi.z); s.eta = 1.0f; s.delta = true; s.null = true;
+        pdf = 1 - prob;
+        return (f3(1, 1, 1) - opacity) * (1.0f / pdf);
+    }
+    return bsdf_sample_inner(b, wi, sx, sy, s, pdf, tables, rng);
 }
 
 // ------------------------------------------------------------------ the integrator
@@ -1106,7 +1135,16 @@ public:
             o = its.p; d = wo;
             throughput = throughput * bsdfWeight; eta *= bs.eta;
             if (bs.null) {                                                                      // index-matched transition, GP:2044-2075
-                // (smooth/null hybrids such as `mask` are not in scope, so no vertex is recorded here: leaf == nullptr for thindielectric)
+                // smooth/null hybrids (mask): the null transition is recorded as a delta vertex for the sampling-fraction optimisation
+                if (prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE && leaf && nVertices < 32 && !isFinalIter) {   // GP:2049-2066
+                    if (1 / woPdf > 0) {
+                        CommitRec &v = vtx[nVertices]; vLeaf[nVertices] = leaf;
+                        v.o = o; v.d = d; v.voxel = f3(voxel[0], voxel[1], voxel[2]); v.throughput = throughput;
+                        v.bsdfVal = bsdfWeight * woPdf; v.radiance = f3(0, 0, 0);
+                        v.woPdf = woPdf; v.bsdfPdf = bsdfPdf; v.dTreePdf = dTreePdf; v.isDelta = true;
+                        ++nVertices;
+                    }
+                }
                 emittedRadiance = !scattered;                                                   // ERadiance : ERadianceNoEmission
                 ray_intersect(sc, o, d, kEpsilon, std::numeric_limits<float>::infinity(), its);
                 nVerticesTraced++;

@@ -73,7 +73,7 @@ __device__ __forceinline__ void seed_vertex_rng(Pcg32 &r, uint64_t seed, uint64_
 //   geom[6t+0..2] = {p_i.xyz, n_i.x}, geom[6t+3..5] = {n_i.yz, uv_i}   (i = 0,1,2)
 //   meta[t] = {bsdf, emitter (-1 none), flags (bit0 has_normals), shape}
 // BVH node: 2 x float4 = {bmin.xyz, bits(left)}, {bmax.xyz, bits(count)}; count>0 -> leaf [left, left+count)
-#define PPG_BSDF_F4 6      // float4 per material, see load_bsdf
+#define PPG_BSDF_F4 7      // float4 per material, see load_bsdf
 #define PPG_BSDF_LUT 100   // PPG_BSDF_TABLE_SIZE
 struct SceneView {
     const float4 *accel;
@@ -412,9 +412,10 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 #define PPG_BSDF_T_PLASTIC 7u
 #define PPG_BSDF_T_THINDIELECTRIC 8u
 #define PPG_BSDF_NONLINEAR 2u
+#define PPG_BSDF_MASK 4u
 // 6 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)},
-// {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), -, -}
-struct Bsdf { float3 refl, trans, etaRgb, k, specRefl; float eta, invEta, alpha, fdrInt, ssw; uint32_t type, flags; int distr; const float *lut; };
+// {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), -, -}, {opacity.rgb, luminance(opacity)} (mask flag)
+struct Bsdf { float3 refl, trans, etaRgb, k, specRefl, opacity; float eta, invEta, alpha, fdrInt, ssw, maskProb; uint32_t type, flags; int distr; const float *lut; };
 // FULL == false: the scene holds diffuse BSDFs and triangles only (host-checked); every other model compiles away
 template <bool FULL, class Acc>
 __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
@@ -422,6 +423,9 @@ __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
     Bsdf b; b.refl = f3(a.x, a.y, a.z);
     const uint32_t tf = __float_as_uint(a.w); b.type = FULL ? (tf & 0xffu) : PPG_BSDF_T_DIFFUSE; b.flags = tf >> 8;
     b.trans = b.etaRgb = b.k = b.specRefl = f3(0, 0, 0); b.eta = b.invEta = 1.f; b.alpha = 0.1f; b.distr = 1; b.fdrInt = b.ssw = 0.f; b.lut = nullptr;
+    b.opacity = f3(1, 1, 1); b.maskProb = 1.f;
+    if (FULL && (b.flags & PPG_BSDF_MASK)) { const float4 m = A_.bsdf(PPG_BSDF_F4 * idx + 6); b.opacity = f3(m.x, m.y, m.z); b.maskProb = m.w; }
+    if (!FULL) b.flags &= PPG_BSDF_TWOSIDED;
     if (FULL && b.type != PPG_BSDF_T_DIFFUSE) {
         const float4 t = A_.bsdf(PPG_BSDF_F4 * idx + 1), e = A_.bsdf(PPG_BSDF_F4 * idx + 2), k = A_.bsdf(PPG_BSDF_F4 * idx + 3);
         b.trans = f3(t.x, t.y, t.z); b.eta = t.w; b.etaRgb = f3(e.x, e.y, e.z); b.invEta = e.w; b.k = f3(k.x, k.y, k.z);
@@ -434,8 +438,8 @@ __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
     return b;
 }
 __device__ __forceinline__ bool bsdf_has_smooth(const Bsdf &b) { return b.type == PPG_BSDF_T_DIFFUSE || b.type == PPG_BSDF_T_ROUGHCONDUCTOR || b.type == PPG_BSDF_T_ROUGHPLASTIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC || b.type == PPG_BSDF_T_PLASTIC; }   // type & ESmooth = diffuse | glossy (bsdf.h:224-285)
-__device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & PPG_BSDF_TWOSIDED) || b.type == PPG_BSDF_T_DIELECTRIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC || b.type == PPG_BSDF_T_THINDIELECTRIC; }
-__device__ __forceinline__ bool bsdf_has_null(const Bsdf &b) { return b.type == PPG_BSDF_T_THINDIELECTRIC; }                     // type & ENull
+__device__ __forceinline__ bool bsdf_has_transmission_or_backside(const Bsdf &b) { return (b.flags & (PPG_BSDF_TWOSIDED | PPG_BSDF_MASK)) || b.type == PPG_BSDF_T_DIELECTRIC || b.type == PPG_BSDF_T_ROUGHDIELECTRIC || b.type == PPG_BSDF_T_THINDIELECTRIC; }
+__device__ __forceinline__ bool bsdf_has_null(const Bsdf &b) { return b.type == PPG_BSDF_T_THINDIELECTRIC || (b.flags & PPG_BSDF_MASK); }                     // type & ENull
 
 // fresnelDielectricExt, src/libcore/util.cpp:651-683
 __device__ __forceinline__ float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
@@ -668,6 +672,7 @@ __device__ __forceinline__ float thindielectric_reflectance(float cosThetaI, flo
 }
 // bsdf->eval(bRec, EDiscrete) with typeMask == ENull and wo == -wi (thindielectric.cpp:153-176): what a straight-through ray keeps
 __device__ __forceinline__ float3 bsdf_eval_null(const Bsdf &b, float cosThetaI) {
+    if (b.flags & PPG_BSDF_MASK) return f3(1.f - b.opacity.x, 1.f - b.opacity.y, 1.f - b.opacity.z);       // mask.cpp:118-119
     if (b.type != PPG_BSDF_T_THINDIELECTRIC) return f3(0, 0, 0);
     return b.trans * (1.f - thindielectric_reflectance(cosThetaI, b.eta));
 }
@@ -780,7 +785,7 @@ __device__ __forceinline__ float3 roughdielectric_sample(const Bsdf &b, float3 w
 
 // eval / pdf in the solid-angle measure (delta models: 0); sample per src/bsdfs/{diffuse.cpp:110-150, dielectric.cpp:277-334, conductor.cpp:262-277};
 // twosided per src/bsdfs/twosided.cpp:108-184
-__device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo) {
+__device__ __forceinline__ float3 bsdf_eval_inner(const Bsdf &b, float3 wi, float3 wo) {
     if (!bsdf_has_smooth(b)) return f3(0, 0, 0);
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_eval(b, wi, wo);
@@ -790,7 +795,7 @@ __device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo)
     if (wi.z <= 0.f || wo.z <= 0.f) return f3(0, 0, 0);
     return b.refl * (PPG_INV_PI * wo.z);
 }
-__device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
+__device__ __forceinline__ float bsdf_pdf_inner(const Bsdf &b, float3 wi, float3 wo) {
     if (!bsdf_has_smooth(b)) return 0.0f;
     if ((b.flags & PPG_BSDF_TWOSIDED) && wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     if (b.type == PPG_BSDF_T_ROUGHCONDUCTOR) return roughconductor_pdf(b, wi, wo);
@@ -802,7 +807,7 @@ __device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
 }
 // `rng`: the path's sampler, consumed only by models that draw from it themselves (roughdielectric)
 // isNull: sampledType == ENull (index-matched transition straight through the surface)
-__device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf, Pcg32 &rng, bool &isNull) {
+__device__ __forceinline__ float3 bsdf_sample_inner(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf, Pcg32 &rng, bool &isNull) {
     isNull = false;
     if (b.type == PPG_BSDF_T_THINDIELECTRIC) {                                                 // thindielectric.cpp:206-240
         const float R = thindielectric_reflectance(wi.z, b.eta);
@@ -851,6 +856,30 @@ __device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx
     pdf = PPG_INV_PI * wo.z;
     if (flip) wo.z = -wo.z;
     return b.refl;
+}
+
+// ---- mask (src/bsdfs/mask.cpp:113-220), the outermost wrapper: nested model scaled by the opacity, or a straight-through null transition
+__device__ __forceinline__ float3 bsdf_eval(const Bsdf &b, float3 wi, float3 wo) {
+    const float3 v = bsdf_eval_inner(b, wi, wo);
+    return (b.flags & PPG_BSDF_MASK) ? v * b.opacity : v;
+}
+__device__ __forceinline__ float bsdf_pdf(const Bsdf &b, float3 wi, float3 wo) {
+    const float p = bsdf_pdf_inner(b, wi, wo);
+    return (b.flags & PPG_BSDF_MASK) ? p * b.maskProb : p;
+}
+__device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx, float sy, float3 &wo, float &eta, bool &delta, float &pdf, Pcg32 &rng, bool &isNull) {
+    const bool mask = b.flags & PPG_BSDF_MASK;                                                // mask.cpp:186-207
+    if (mask) {
+        if (!(sx < b.maskProb)) {
+            wo = f3(-wi.x, -wi.y, -wi.z); eta = 1.0f; delta = true; isNull = true;
+            pdf = 1.f - b.maskProb;
+            return f3(1.f - b.opacity.x, 1.f - b.opacity.y, 1.f - b.opacity.z) * (1.0f / pdf);
+        }
+        sx /= b.maskProb;
+    }
+    float3 result = bsdf_sample_inner(b, wi, sx, sy, wo, eta, delta, pdf, rng, isNull);
+    if (mask) { result = (result * b.opacity) * (1.0f / b.maskProb); pdf *= b.maskProb; }
+    return result;
 }
 
 // ------------------------------------------------------------------ SD-tree views

@@ -415,6 +415,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         const int t = s->bsdfs[i].type;
         if (t != PPG_BSDF_DIFFUSE && t != PPG_BSDF_NULL_BLACK && t != PPG_BSDF_DIELECTRIC && t != PPG_BSDF_CONDUCTOR && t != PPG_BSDF_ROUGHCONDUCTOR && t != PPG_BSDF_ROUGHPLASTIC && t != PPG_BSDF_ROUGHDIELECTRIC && t != PPG_BSDF_PLASTIC && t != PPG_BSDF_THINDIELECTRIC)
             return fail(PPG_ERR_UNSUPPORTED, "BSDF type outside the implemented hot-path scope");
+        if ((s->bsdfs[i].flags & PPG_BSDF_FLAG_MASK) && t == PPG_BSDF_THINDIELECTRIC) return fail(PPG_ERR_UNSUPPORTED, "mask around another null-type BSDF");
         if (t == PPG_BSDF_ROUGHPLASTIC && (!s->bsdf_tables || s->bsdfs[i].table < 0 || (uint32_t) s->bsdfs[i].table >= s->n_bsdf_tables))
             return fail(PPG_ERR_INVALID_ARGUMENT, "roughplastic needs its rough-transmittance table (ppg_scene_desc.bsdf_tables)");
         if ((t == PPG_BSDF_DIELECTRIC || t == PPG_BSDF_ROUGHDIELECTRIC || t == PPG_BSDF_THINDIELECTRIC) && !(s->bsdfs[i].eta[0] > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "dielectric needs eta > 0");
@@ -495,7 +496,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         meta[4 * (size_t) slot + 2] = (sh.has_normals && s->normals) ? 1 : 0; meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
     }
     h->fullFeature = false;
-    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if (s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) h->fullFeature = true;   // any non-diffuse model
+    for (uint32_t i = 0; i < s->n_bsdfs; ++i) if ((s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) || (s->bsdfs[i].flags & ~PPG_BSDF_FLAG_TWOSIDED)) h->fullFeature = true;   // any non-diffuse model or wrapper other than twosided
     if (s->n_spheres) h->fullFeature = true;                                            // ... or analytic spheres: the full-feature kernel variants
     std::vector<float> bsdf(4 * PPG_BSDF_F4 * (size_t) s->n_bsdfs, 0.f);
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
@@ -510,6 +511,8 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         b[15] = std::max(m.alpha, 1e-4f) * (m.distribution == PPG_MICROFACET_BECKMANN ? -1.0f : 1.0f);   // microfacet.h:63 clamp; sign encodes the distribution
         b[16] = m.specular_reflectance[0]; b[17] = m.specular_reflectance[1]; b[18] = m.specular_reflectance[2]; b[19] = m.fdr_int;
         b[20] = m.specular_sampling_weight; const uint32_t tab = (uint32_t) std::max(m.table, 0); memcpy(&b[21], &tab, 4);
+        b[24] = m.opacity[0]; b[25] = m.opacity[1]; b[26] = m.opacity[2];
+        b[27] = m.opacity[0] * 0.212671f + m.opacity[1] * 0.715160f + m.opacity[2] * 0.072169f;                // getLuminance (spectrum.h:725-727)
     }
     std::vector<float> rad(4 * (size_t) std::max<uint32_t>(s->n_emitters, 1), 0.f);
     for (uint32_t i = 0; i < s->n_emitters; ++i) { rad[4 * i] = s->area_radiance[3 * i]; rad[4 * i + 1] = s->area_radiance[3 * i + 1]; rad[4 * i + 2] = s->area_radiance[3 * i + 2]; }

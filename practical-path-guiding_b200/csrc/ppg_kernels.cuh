@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_
                         }
                         wroteVertex = true; ++nVertices; ++recLocal; levelsLocal += levels;
                     }
-                    if (NEE) { prevWoPdf = woPdf; prevRefN = refN; prevSlot = i | (isDelta ? 0x80000000u : 0u) | (wroteVertex ? 0x40000000u : 0u); }
+                    if (NEE) { prevWoPdf = woPdf; prevRefN = refN; prevSlot = i | (isDelta ? 0x80000000u : 0u) | ((wroteVertex && !(FULL && isNull)) ? 0x40000000u : 0u); }   // a null vertex starts at radiance 0: nothing to move (GP:2058)
                     // ---- Russian roulette (GP:2123-2142); the decision takes effect after the next emitter lookup
                     rrRecip = 1.f; flags = 0;
                     if (FULL && isNull) flags = PPG_FLAG_NULL | (unscattered ? PPG_FLAG_UNSCATTERED : 0u);   // GP:2044-2075: no roulette, `scattered` unchanged

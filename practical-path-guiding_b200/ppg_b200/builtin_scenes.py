@@ -161,6 +161,21 @@ def cbox_thin_glass(cbox: SceneDesc) -> SceneDesc:
     return sc
 
 
+def cbox_blinds(cbox: SceneDesc) -> SceneDesc:
+    """CBOX with two `mask` panes like kitchen.xml's "Blinds" (mask.cpp: constant opacity around a twosided diffuse BSDF), in the places
+    of cbox_thin_glass's panes.  A mask is a smooth/null hybrid: guided, light-sampled, looked through by the emitter lookup and
+    shadow rays, and with a sampling-fraction loss its null transitions are recorded as delta vertices (GP:2049-2066)."""
+    from .scene import BSDF_FLAG_MASK, BSDF_FLAG_TWOSIDED, BSDF_DIFFUSE
+    sc = cbox_thin_glass(cbox)
+    b = sc.bsdfs.copy()
+    blinds = _make_bsdf(BSDF_DIFFUSE, BSDF_FLAG_MASK | BSDF_FLAG_TWOSIDED, (0.612066, 0.499505, 0.378676)); blinds[22:25] = (0.612066,) * 3
+    veil = _make_bsdf(BSDF_DIFFUSE, BSDF_FLAG_MASK | BSDF_FLAG_TWOSIDED, (0.2, 0.5, 0.7)); veil[22:25] = (0.3, 0.5, 0.8)
+    b[-2] = blinds; b[-1] = veil
+    sc.bsdfs = b
+    sc.bsdf_names = list(sc.bsdf_names[:-2]) + ["blinds", "veil"]
+    return sc
+
+
 def cbox_rough_metal(cbox: SceneDesc) -> SceneDesc:
     """CBOX whose boxes are rough conductors: the small box GGX alpha 0.1 with the eta/k of spaceship.xml's "RoughAluminium",
     the large box Beckmann alpha 0.3 -- glossy BSDFs are guided (ESmooth) and take part in light sampling."""
@@ -179,7 +194,7 @@ def cbox_rough_metal(cbox: SceneDesc) -> SceneDesc:
 
 def _pad_bsdfs(b):
     b = np.asarray(b, np.float32)
-    return b if b.shape[1] >= 24 else np.concatenate([b, np.zeros((len(b), 24 - b.shape[1]), np.float32)], axis=1)
+    return b if b.shape[1] >= 28 else np.concatenate([b, np.zeros((len(b), 28 - b.shape[1]), np.float32)], axis=1)
 
 
 def cbox_rough_plastic(cbox: SceneDesc) -> SceneDesc:

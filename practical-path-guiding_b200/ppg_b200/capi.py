@@ -33,7 +33,7 @@ class PpgParams(C.Structure):
 class PpgBsdf(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("reflectance", C.c_float * 3), ("specular_transmittance", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3), ("alpha", C.c_float), ("distribution", C.c_int32),
-                ("specular_reflectance", C.c_float * 3), ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("table", C.c_int32), ("reserved", C.c_float * 2)]
+                ("specular_reflectance", C.c_float * 3), ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("table", C.c_int32), ("opacity", C.c_float * 3), ("reserved", C.c_float * 3)]
 
 
 class PpgShape(C.Structure):
@@ -117,9 +117,9 @@ class SceneArrays:
         self.triangle_shape = np.ascontiguousarray(scene.triangle_shape, np.uint32)
         self.shapes = np.ascontiguousarray(scene.shapes, np.int32)          # (S,8) == ppg_shape
         b = np.asarray(scene.bsdfs, np.float32)
-        if b.shape[1] < 24:                                                   # fixtures written before the struct grew to 96 bytes
-            b = np.concatenate([b, np.zeros((len(b), 24 - b.shape[1]), np.float32)], axis=1)
-        self.bsdfs = np.ascontiguousarray(b, np.float32)                    # (B,24) == ppg_bsdf
+        if b.shape[1] < 28:                                                   # arrays written before the struct grew to 112 bytes
+            b = np.concatenate([b, np.zeros((len(b), 28 - b.shape[1]), np.float32)], axis=1)
+        self.bsdfs = np.ascontiguousarray(b, np.float32)                    # (B,28) == ppg_bsdf
         tables = getattr(scene, "bsdf_tables", None)
         self.tables = np.ascontiguousarray(tables if tables is not None and len(tables) else np.zeros((0, 100)), np.float32)
         self.radiance = np.ascontiguousarray(scene.area_radiance, np.float32)

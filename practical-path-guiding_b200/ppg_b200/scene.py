@@ -45,6 +45,7 @@ BSDF_ROUGHDIELECTRIC = 6
 BSDF_PLASTIC = 7
 BSDF_THINDIELECTRIC = 8
 BSDF_FLAG_NONLINEAR = 2
+BSDF_FLAG_MASK = 4
 BSDF_FLAG_TWOSIDED = 1
 
 # a few entries of Mitsuba's named indices of refraction (src/bsdfs/ior.h); defaults: intIOR "bk7", extIOR "air"
@@ -350,7 +351,7 @@ class SceneDesc:
     indices: np.ndarray        # (T,3) u32
     triangle_shape: np.ndarray  # (T,) u32
     shapes: np.ndarray         # (S,8) u32/i32: first_tri, n_tris, bsdf, emitter, has_normals, has_uvs, 0, 0
-    bsdfs: np.ndarray          # (B,24) f32 view of ppg_bsdf (type/flags bit-cast)
+    bsdfs: np.ndarray          # (B,28) f32 view of ppg_bsdf (type/flags bit-cast)
     area_radiance: np.ndarray  # (E,3) f32
     cam_to_world: np.ndarray   # (4,4) f32
     x_fov_deg: float
@@ -403,7 +404,7 @@ def make_sphere(center, radius, shape, flip_normals=False):
 
 def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0), alpha=0.1, distribution=0):
     """One ppg_bsdf (include/ppg.h) as 16 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], alpha, distribution (int bits)."""
-    b = np.zeros(24, np.float32)
+    b = np.zeros(28, np.float32)
     b[:2] = np.array([type_, flags], np.uint32).view(np.float32)
     b[2:5] = refl; b[5:8] = trans; b[8:11] = eta; b[11:14] = k; b[14] = alpha
     b[15:16] = np.array([distribution], np.int32).view(np.float32)
@@ -486,6 +487,19 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
     typ = node.attrib["type"]
     flags = 0
     inner = node
+    id_node = node
+    opacity = None
+    if typ == "mask":                   # src/bsdfs/mask.cpp:63-66: constant opacity around a nested BSDF
+        if any(c.tag == "texture" for c in node):
+            raise NotImplementedError("mask: textured opacity is out of scope (bitmap textures)")
+        opacity = np.full(3, 0.5, np.float32)
+        for c in node:
+            if c.tag in ("rgb", "srgb", "spectrum") and c.attrib.get("name") == "opacity":
+                opacity = _parse_color(c)
+        flags |= BSDF_FLAG_MASK
+        inner = [c for c in node if c.tag == "bsdf"][0]
+        node = inner
+        typ = inner.attrib["type"]
     if typ == "twosided":
         flags |= BSDF_FLAG_TWOSIDED
         inner = [c for c in node if c.tag == "bsdf"][0]
@@ -562,11 +576,15 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         entry = _make_bsdf(BSDF_CONDUCTOR, flags, sr, (0, 0, 0), eta / ext, k / ext)
     else:
         raise NotImplementedError(f"BSDF '{typ}' is not implemented yet (hot-path scope so far: diffuse, dielectric, conductor, twosided)")
+    if opacity is not None:
+        if int(entry[:1].view(np.uint32)[0]) in (BSDF_THINDIELECTRIC,):
+            raise NotImplementedError("mask around another null-type BSDF")
+        entry[22:25] = opacity
     idx = len(bsdf_table)
     bsdf_table.append(entry)
-    names.append(node.attrib.get("id", f"bsdf{idx}"))
-    if "id" in node.attrib:
-        by_id[node.attrib["id"]] = idx
+    names.append(id_node.attrib.get("id", f"bsdf{idx}"))
+    if "id" in id_node.attrib:
+        by_id[id_node.attrib["id"]] = idx
     return idx
 
 
@@ -702,7 +720,7 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
     return SceneDesc(
         positions=P, normals=np.concatenate(N_all).astype(np.float32), uvs=np.concatenate(UV_all).astype(np.float32),
         indices=np.concatenate(I_all).astype(np.uint32), triangle_shape=np.concatenate(TS_all).astype(np.uint32),
-        shapes=np.asarray(shapes, np.int64).astype(np.int32), bsdfs=np.asarray(bsdf_table, np.float32).reshape(-1, 24),
+        shapes=np.asarray(shapes, np.int64).astype(np.int32), bsdfs=np.asarray(bsdf_table, np.float32).reshape(-1, 28),
         bsdf_tables=np.asarray(_TABLES, np.float32).reshape(-1, 100),
         spheres=np.asarray([make_sphere(c, r, si, fl) for c, r, si, fl in sphere_list], np.float32).reshape(-1, 6),
         area_radiance=np.asarray(radiance, np.float32).reshape(-1, 3), cam_to_world=cam_to_world.astype(np.float32),

@@ -426,3 +426,34 @@ def test_thin_dielectric_null_transitions_match_oracle(extra):
     for a, b in zip(st["iterations"], ost["iterations"]):
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
         assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(nee="kickstart", spatialFilter="box")])
+def test_mask_smooth_null_hybrid_matches_oracle(extra):
+    """CBOX with `mask` panes (mask.cpp, kitchen.xml's "Blinds"): nested diffuse lobe scaled by the opacity, else a null transition;
+    guided vertices can return the null sample (delta early-out of sampleMat), light sampling and the emitter lookup see 1 - opacity."""
+    from ppg_b200.builtin_scenes import cbox_blinds
+    sc = cbox_blinds(load_cbox(128))
+    props = dict(dict(sc.integrator, budget="60"), **extra)
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert relmse(img, ref) <= 1e-5, relmse(img, ref)
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 1e-4 * ost["total_vertices"]
+    for a, b in zip(st["iterations"], ost["iterations"]):
+        assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1
+        assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-4)
+
+
+def test_mask_null_transitions_feed_the_sampling_fraction_optimiser():
+    """With a loss, null transitions of a smooth/null hybrid are recorded as delta vertices (GP:2049-2066).  Adam replay order differs
+    from the multi-threaded oracle's, so the check is statistical: image mean, vertex count and per-iteration variance track the oracle."""
+    from ppg_b200.builtin_scenes import cbox_blinds
+    sc = cbox_blinds(load_cbox(128))
+    props = dict(sc.integrator, budget="124", bsdfSamplingFractionLoss="kl")
+    g = _gpu(props, sc); img, st = g.render()
+    o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
+    assert abs(img.mean() - ref.mean()) <= 0.02 * ref.mean(), (img.mean(), ref.mean())
+    assert abs(st["total_vertices"] - ost["total_vertices"]) <= 0.01 * ost["total_vertices"]
+    for k in (2, 3, 4):
+        a, b = st["iterations"][k], ost["iterations"][k]
+        assert abs(a["variance"] - b["variance"]) <= 0.15 * b["variance"], (k, a["variance"], b["variance"])
