@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
         subprocess.run(["/usr/bin/gcc", os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
         sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(capi.PpgParams), C.sizeof(capi.PpgBsdf), C.sizeof(capi.PpgShape), C.sizeof(capi.PpgSceneDesc), C.sizeof(capi.PpgIterationStats), C.sizeof(capi.PpgStats), C.sizeof(capi.PpgSphere)]
-    assert C.sizeof(capi.PpgBsdf) == 96 and C.sizeof(capi.PpgSphere) == 24
+    assert C.sizeof(capi.PpgBsdf) == 112 and C.sizeof(capi.PpgSphere) == 24
 
 
 def test_parameter_defaults_are_the_references():
