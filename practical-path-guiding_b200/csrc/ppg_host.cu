@@ -283,7 +283,7 @@ struct ppg_integrator {
 
     // wavefront
     size_t pathCapacity = 0; int maxBounces = 0, nSlabs = 0; int recordMode = 0; int stateVecs = 5, slabSets = 1;
-    DevBuf<float4> dStateA, dStateB, dSlabs, dLiFinal; DevBuf<uint32_t> dLive; DevBuf<unsigned long long> dCounters;
+    DevBuf<float4> dStateA, dStateB, dSlabs, dLiFinal; DevBuf<uint32_t> dLive, dWork; DevBuf<unsigned long long> dCounters;
     int gridBounce = 0, gridCommit = 0;
 
     // per-kernel-class CUDA-event timing on the launching stream
@@ -835,14 +835,14 @@ static int ensure_wavefront(ppg_integrator *h) {
         CK(h->dSlabs.alloc((size_t) h->nSlabs * (full ? 6 : 3) * cap * slabSets));
         h->pathCapacity = cap; h->stateVecs = stateVecs; h->slabSets = slabSets;
     }
-    CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
+    CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dWork.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
-    if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BLOCK, h->sceneSmemBytes));
-    else if (h->sceneSmemBytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, true, true>, PPG_BLOCK, h->sceneSmemBytes));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, false, true>, PPG_BLOCK, 0));
-    // 4 grid-stride blocks per resident slot: finer tail balancing (+1.7 % on CBOX 1024^2 against exactly one block per slot)
-    h->gridBounce = h->numSMs * std::max(occ, 1) * std::max(env_int("PPG_GRID_MULT", 4), 1);
+    if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
+    else if (h->sceneSmemBytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, true, true>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, false, true>, PPG_BOUNCE_BLOCK, 0));
+    // one block per resident slot; warps claim their work dynamically (bounce_kernel)
+    h->gridBounce = h->numSMs * std::max(occ, 1) * std::max(env_int("PPG_GRID_MULT", 1), 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
     h->gridCommit = h->numSMs * std::max(occ, 1);
     return PPG_OK;
@@ -872,11 +872,11 @@ template <bool FIRST, bool SMEM, bool FULL> static void launch_bounce3(ppg_integ
     carveout(bounce_kernel<FIRST, 0, true, SMEM, FULL>); carveout(bounce_kernel<FIRST, 2, true, SMEM, FULL>); carveout(bounce_kernel<FIRST, 0, false, SMEM, FULL>);
     carveout(bounce_kernel<FIRST, 1, false, SMEM, FULL>); carveout(bounce_kernel<FIRST, 2, false, SMEM, FULL>);
     if (nee) {      // next event estimation always runs with full records
-        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-        else bounce_kernel<FIRST, 2, true, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
-    else bounce_kernel<FIRST, 2, false, SMEM, FULL><<<grid, PPG_BLOCK, sm, h->stream>>>(P);
+        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
+        else bounce_kernel<FIRST, 2, true, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
+    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
+    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
+    else bounce_kernel<FIRST, 2, false, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
     h->launches++;
 }
 template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
@@ -891,6 +891,7 @@ static int render_batch(ppg_integrator *h, int nPasses) {
     if (nPaths == 0) return PPG_OK;
     const int record = h->isFinalIter ? 0 : h->recordMode;
     CK(cudaMemsetAsync(h->dLive.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
+    CK(cudaMemsetAsync(h->dWork.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
     CK(cudaMemcpyAsync(h->dLive.p, &nPaths, 4, cudaMemcpyHostToDevice, h->stream));
     RenderParams P;
     P.scene = h->sceneView; P.cam = h->cam; P.tree = tree_view(h);
@@ -903,11 +904,11 @@ static int render_batch(ppg_integrator *h, int nPasses) {
     const bool nee = h->useNee();                      // the NEE kernels also carry the MIS state when doNee is off (kickstart after 128 spp)
     P.neeMode = h->prm.nee; P.doNee = (nee && h->doNee) ? 1 : 0; P.training = record != 0 ? 1 : 0;
     PathState A = path_state(h->dStateA.p, h->pathCapacity, nee), B = path_state(h->dStateB.p, h->pathCapacity, nee);
-    const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK));
+    const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + PPG_BOUNCE_BLOCK - 1) / PPG_BOUNCE_BLOCK));
     int lastDepth = 0;
     for (int depth = 1; depth <= h->maxBounces; ++depth) {
         P.depth = depth; P.in = (depth & 1) ? B : A; P.out = (depth & 1) ? A : B;
-        P.liveIn = h->dLive.p + (depth - 1); P.liveOut = h->dLive.p + depth;
+        P.liveIn = h->dLive.p + (depth - 1); P.liveOut = h->dLive.p + depth; P.work = h->dWork.p + depth;
         const int k = std::min(depth - 1, h->nSlabs - 1);
         P.slab = slab_at(h, k);
         if (nee) { P.neeSlab = slab_at(h, k, 1); P.prevSlab = slab_at(h, std::max(k - 1, 0)); if (depth - 1 >= h->nSlabs) P.prevSlab = slab_at(h, h->nSlabs - 1); }

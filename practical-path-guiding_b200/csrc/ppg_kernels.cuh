@@ -16,11 +16,18 @@ namespace ppg {
 #ifndef PPG_BLOCK
 #define PPG_BLOCK 256
 #endif
+#ifndef PPG_BOUNCE_BLOCK
+#define PPG_BOUNCE_BLOCK 1024          // threads per block of the bounce kernel: one block per SM stages the scene once (measured 256x4 -> 5589, 512x2 -> 5643,
+#endif                                 // 1024x1 -> 5676 Msamples/s on CBOX 1024^2)
 #ifndef PPG_MIN_BLOCKS
-#define PPG_MIN_BLOCKS 4               // resident blocks per SM the bounce kernel is compiled for (register cap)
+#define PPG_MIN_BLOCKS 1               // resident blocks per SM the bounce kernel is compiled for: 1024 threads x 64 registers = the whole register file
+#endif
+#ifndef PPG_CLAIM
+#define PPG_CLAIM 1u                   // groups of 32 paths a warp claims per atomic (measured on CBOX 1024^2: 1 -> 5585, 4 -> 5385, 16 -> 4819 Msamples/s:
+                                       // running warps then sweep ONE contiguous window of the SoA path state)
 #endif
 #ifndef PPG_MIN_BLOCKS_GLOSSY
-#define PPG_MIN_BLOCKS_GLOSSY 4        // same for scenes with non-diffuse BSDFs (FULL variants; measured on the rough CBOX variants: 4 > 3 > 2)
+#define PPG_MIN_BLOCKS_GLOSSY 1        // same for the full-feature variants (64 registers beat 80 and 128 on the rough CBOX variants)
 #endif
 #define PPG_MAX_VERTICES 32         // MAX_NUM_VERTICES, GP:1771
 #define PPG_INVALID 0xFFFFFFFFu
@@ -55,6 +62,7 @@ struct RenderParams {
     float4 *liFinal;               // per path: Li.rgb, 1
     const uint32_t *pixelMap;      // local pixel -> x | y<<16
     const uint32_t *liveIn; uint32_t *liveOut;      // device counters
+    uint32_t *work;                                 // dynamic scheduling: next unclaimed input index of this launch (zeroed by the host), or nullptr
     unsigned long long *counters;  // [0]: rays traced, [1]: vertices recorded, [2]: sum of S-tree levels over recorded vertices
     uint32_t nPaths;               // paths of this batch (FIRST kernel)
     uint32_t nLocalPixels, spp;
@@ -89,14 +97,25 @@ __device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) 
 // RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
 //         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
 template <bool FIRST, int RECORD, bool NEE, bool SMEM, bool FULL>
-__global__ void __launch_bounds__(PPG_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
+__global__ void __launch_bounds__(PPG_BOUNCE_BLOCK, FULL ? PPG_MIN_BLOCKS_GLOSSY : PPG_MIN_BLOCKS) bounce_kernel(const RenderParams P) {
     const SceneAccess<SMEM> sc(P.scene);
     sc.stage();
     const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
     unsigned long long raysLocal = 0, recLocal = 0, levelsLocal = 0;
 
-    for (uint32_t base = blockIdx.x * PPG_BLOCK; base < nIn; base += gridDim.x * PPG_BLOCK) {
-        const uint32_t i = base + threadIdx.x;
+    // Work distribution: every warp claims PPG_CLAIM consecutive groups of 32 paths at a time from a launch-wide counter, so exactly one
+    // block per resident slot is launched (the scene is staged once per slot) and the tail still balances.  No block barrier in the loop.
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t claimBase = 0, claimLeft = 0;
+    for (;;) {
+        if (claimLeft == 0) {
+            if (lane == 0) claimBase = atomicAdd(P.work, 32u * PPG_CLAIM);
+            claimBase = __shfl_sync(0xffffffffu, claimBase, 0);
+            claimLeft = PPG_CLAIM;
+        }
+        if (claimBase >= nIn) break;
+        const uint32_t i = claimBase + lane;
+        claimBase += 32u; --claimLeft;
         bool alive = i < nIn;
         float3 o, d, thr, Li; float eta = 1.f, rrRecip = 1.f, mint, maxt;
         float prevWoPdf = 0.f; float3 prevRefN = f3(0, 0, 0); uint32_t prevSlot = 0;      // NEE only
