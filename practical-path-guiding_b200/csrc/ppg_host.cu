@@ -838,9 +838,13 @@ static int ensure_wavefront(ppg_integrator *h) {
     CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dWork.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
-    if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
-    else if (h->sceneSmemBytes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, true, true>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, false, true>, PPG_BOUNCE_BLOCK, 0));
+    if (h->sceneSmemBytes) {
+        if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, true, true>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
+    } else {
+        if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, false, false>, PPG_BOUNCE_BLOCK_HBM, 0));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, false, true>, PPG_BOUNCE_BLOCK_HBM, 0));
+    }
     // one block per resident slot; warps claim their work dynamically (bounce_kernel)
     h->gridBounce = h->numSMs * std::max(occ, 1) * std::max(env_int("PPG_GRID_MULT", 1), 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
@@ -872,11 +876,11 @@ template <bool FIRST, bool SMEM, bool FULL> static void launch_bounce3(ppg_integ
     carveout(bounce_kernel<FIRST, 0, true, SMEM, FULL>); carveout(bounce_kernel<FIRST, 2, true, SMEM, FULL>); carveout(bounce_kernel<FIRST, 0, false, SMEM, FULL>);
     carveout(bounce_kernel<FIRST, 1, false, SMEM, FULL>); carveout(bounce_kernel<FIRST, 2, false, SMEM, FULL>);
     if (nee) {      // next event estimation always runs with full records
-        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
-        else bounce_kernel<FIRST, 2, true, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
-    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
-    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
-    else bounce_kernel<FIRST, 2, false, SMEM, FULL><<<grid, PPG_BOUNCE_BLOCK, sm, h->stream>>>(P);
+        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
+        else bounce_kernel<FIRST, 2, true, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
+    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
+    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
+    else bounce_kernel<FIRST, 2, false, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
     h->launches++;
 }
 template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
@@ -904,7 +908,8 @@ static int render_batch(ppg_integrator *h, int nPasses) {
     const bool nee = h->useNee();                      // the NEE kernels also carry the MIS state when doNee is off (kickstart after 128 spp)
     P.neeMode = h->prm.nee; P.doNee = (nee && h->doNee) ? 1 : 0; P.training = record != 0 ? 1 : 0;
     PathState A = path_state(h->dStateA.p, h->pathCapacity, nee), B = path_state(h->dStateB.p, h->pathCapacity, nee);
-    const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + PPG_BOUNCE_BLOCK - 1) / PPG_BOUNCE_BLOCK));
+    const int bb = h->sceneSmemBytes ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM;
+    const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + bb - 1) / bb));
     int lastDepth = 0;
     for (int depth = 1; depth <= h->maxBounces; ++depth) {
         P.depth = depth; P.in = (depth & 1) ? B : A; P.out = (depth & 1) ? A : B;

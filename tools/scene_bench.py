@@ -12,13 +12,20 @@ a = ap.parse_args()
 from common import load_cbox, load_fixture_scene
 
 
+def SceneDesc_load(name):
+    from ppg_b200.scene import SceneDesc
+    return SceneDesc.load(name)
+
+
 def scene(name):
     from ppg_b200 import builtin_scenes as B
     if name == "diffuse": return load_cbox(a.size or None)
-    if name == "plastic": return load_fixture_scene("cbox-plastic", a.size)
-    if name == "metal": return B.cbox_rough_metal(load_cbox(a.size))
-    if name == "glass": return B.cbox_rough_glass(load_cbox(a.size))
-    if name == "mirror": return B.cbox_glass_mirror(load_cbox(a.size))
+    if name == "plastic": return load_fixture_scene("cbox-plastic", a.size or 512)
+    if name == "metal": return B.cbox_rough_metal(load_cbox(a.size or 512))
+    if name == "glass": return B.cbox_rough_glass(load_cbox(a.size or 512))
+    if name == "mirror": return B.cbox_glass_mirror(load_cbox(a.size or 512))
+    if name == "blinds": return B.cbox_blinds(load_cbox(a.size or 512))
+    if name.endswith(".npz") and a.size: return SceneDesc_load(name).with_film(a.size, a.size)
     from ppg_b200.scene import SceneDesc
     return SceneDesc.load(name)
 
