@@ -71,3 +71,35 @@ def test_nee_modes_are_unbiased_against_each_other():
     assert abs(out["always"][0] - out["never"][0]) <= 0.015 * out["never"][0]
     assert out["always"][1] < 0.6 * out["never"][1]          # final iteration with light sampling
     assert out["kickstart"][2] < 0.5 * out["never"][2]       # first iteration with light sampling
+
+
+@pytest.mark.parametrize("kind", ["port"] + (["ref"] if O.have_ref() else []))
+def test_spaceship_known_answers(kind):
+    """The authors' own render of scenes/spaceship/spaceship-improved.xml (640x360; log embedded in spaceship-improved.exr) pins the
+    oracle on everything CBOX does not touch: twosided rough plastics / conductors, GGX glass, rectangle lights, the emitting sphere
+    shell, the kd-tree-vs-BVH hit set on 457 560 triangles, and the improved settings (inversevar / stochastic / box / kl, threshold
+    4000, sppPerPass 1).  Known answers of the first four iterations (log: measured here):
+      iteration 0: one D-tree of 85 nodes, depth 4; stat. weight 462 239 (461 233), mean radiance 0.121996 (0.121637)
+      iteration 1: Var 0.097601 (0.1008), avg weight 2866.96 (2911.4), max 129 329 (130 859)
+      iteration 2: Var 0.039882 (0.0416), avg weight 3042.78 (3088.9); depth avg 5.066667 = 2432/480 -> 480 leaves (480)
+      iteration 3: Var 0.017979 (0.0190), avg weight 3766.68 (3801.8); depth avg 5.118454 = 4105/802 -> 802 leaves (802)
+    Tolerances: counts 0.6 %, means 2 %, averages of later iterations 4 %, the (heavy-tailed) variance estimate 15 %."""
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "spaceship_log_stats.json")))["spaceship-improved"]
+    assert (gold["width"], gold["height"]) == (640, 360)
+    from common import load_fixture_scene
+    sc = load_fixture_scene("spaceship-improved")
+    o = O.Oracle(O.params_from_xml(dict(sc.integrator, budget="31")), sc, kind=kind)
+    _, st = o.render()
+    it, g = st["iterations"], gold["iterations"]
+    assert [i["passes"] for i in it] == [i["passes"] for i in g[:5]] == [1, 2, 4, 8, 16]
+    assert it[0]["nodes_min"] == it[0]["nodes_max"] == 85 == int(g[0]["node_count"][0]) and it[0]["depth_max"] == 4 == int(g[0]["depth"][0])
+    assert abs(it[0]["weight_avg"] - g[0]["stat_weight"][1]) <= 0.006 * g[0]["stat_weight"][1]
+    assert abs(it[0]["mean_radiance_avg"] - g[0]["mean_radiance"][1]) <= 0.02 * g[0]["mean_radiance"][1]
+    for k in (1, 2, 3):
+        assert abs(it[k]["variance"] - g[k]["var"]) <= 0.15 * g[k]["var"], (k, it[k]["variance"], g[k]["var"])
+        assert abs(it[k]["weight_avg"] - g[k]["stat_weight"][1]) <= 0.04 * g[k]["stat_weight"][1], (k, it[k]["weight_avg"])
+        assert abs(it[k]["weight_max"] - g[k]["stat_weight"][2]) <= 0.12 * g[k]["stat_weight"][2]      # an extreme statistic: +-6 % run to run
+        assert abs(it[k]["nodes_avg"] - g[k]["node_count"][1]) <= 4
+        assert abs(it[k]["depth_avg"] - g[k]["depth"][1]) <= 0.2
+    # the log's average depths are exact fractions of the leaf count: 5.066667 = 2432/480, 5.118454 = 4105/802
+    assert abs(it[2]["s_tree_leaves"] - 480) <= 40 and abs(it[3]["s_tree_leaves"] - 802) <= 60       # run-to-run spread of the oracle: 480-496, 790-830

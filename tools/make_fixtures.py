@@ -11,6 +11,7 @@ Writes
   scenes/cbox-plastic.npz    CBOX with rough-plastic boxes; carries the per-material rough-transmittance tables reduced from
                              /root/reference/mitsuba/data/microfacet/{beckmann,ggx}.dat (ppg_b200/rtrans.py)
   scenes/spaceship-improved.npz   flat-array form of /root/reference/scenes/spaceship/spaceship-improved.xml (457 560 triangles + 1 sphere)
+  tests/golden/spaceship_log_stats.json   the same for spaceship-improved.exr (first six iterations)
   tests/golden/cbox_log_stats.json   known-answer statistics parsed from the logs embedded
                                       in the reference's golden EXRs (hdrfilm attachLog)
 """
@@ -76,7 +77,19 @@ def spaceship():
     print("spaceship", "tris", len(sc.indices), "spheres", sc.spheres, "bsdfs", sc.bsdf_names, sc.integrator)
 
 
+def spaceship_log():
+    """Known answers of the authors' own render of spaceship-improved.xml (640x360, log embedded in the golden EXR)."""
+    log = exr_attr(f"{REF}/scenes/spaceship/spaceship-improved.exr", "log").decode(errors="replace")
+    st = parse_log(log)
+    st["iterations"] = st["iterations"][:6]
+    with open(os.path.join(ROOT, "tests", "golden", "spaceship_log_stats.json"), "w") as f:
+        json.dump({"spaceship-improved": st}, f, indent=1)
+    print("spaceship log:", [(i["passes"], i.get("var"), i["stat_weight"][1]) for i in st["iterations"]])
+
+
 def main():
+    if sys.argv[1:] == ["spaceship_log"]:
+        return spaceship_log()
     if sys.argv[1:] == ["plastic"]:
         return plastic()
     if sys.argv[1:] == ["spaceship"]:
@@ -98,6 +111,7 @@ def main():
         stats[name] = parse_log(log)
     with open(os.path.join(ROOT, "tests", "golden", "cbox_log_stats.json"), "w") as f:
         json.dump(stats, f, indent=1)
+    spaceship_log()
     print(json.dumps(stats["cbox"]["iterations"][:2], indent=1))
     plastic()
     spaceship()
