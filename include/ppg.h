@@ -111,16 +111,16 @@ typedef enum ppg_bsdf_type {
     PPG_BSDF_CONDUCTOR = 3,      /* src/bsdfs/conductor.cpp:223-286: delta reflection, fresnelConductorExact per channel (libcore/util.cpp:740-765) */
     PPG_BSDF_ROUGHCONDUCTOR = 4, /* src/bsdfs/roughconductor.cpp:257-416 with MicrofacetDistribution (src/bsdfs/microfacet.h): Beckmann or GGX,
                                     visible-normal sampling; glossy => guided */
+    PPG_BSDF_ROUGHPLASTIC = 5,   /* src/bsdfs/roughplastic.cpp:326-507: rough dielectric coat over a diffuse base; the rough transmittance
+                                    (src/bsdfs/rtrans.h) is passed as a per-material 100-entry table + scalars */
     PPG_BSDF_ROUGHDIELECTRIC = 6,/* src/bsdfs/roughdielectric.cpp:270-600: rough refractive interface (reflectance = specularReflectance,
                                     specular_transmittance, eta[0] = intIOR/extIOR, alpha, distribution); draws one extra path-sampler number */
     PPG_BSDF_PLASTIC = 7,        /* src/bsdfs/plastic.cpp:245-441: smooth dielectric coat (delta reflection) over a diffuse base; reflectance = diffuse,
                                     specular_reflectance, eta[0], fdr_int = fresnelDiffuseReflectance(1/eta), specular_sampling_weight,
                                     PPG_BSDF_FLAG_NONLINEAR.  Mixed delta + smooth: exercises GP:1672-1676 */
-    PPG_BSDF_THINDIELECTRIC = 8, /* src/bsdfs/thindielectric.cpp:153-306: delta reflection + index-matched (ENull) transmission with the internal
+    PPG_BSDF_THINDIELECTRIC = 8  /* src/bsdfs/thindielectric.cpp:153-306: delta reflection + index-matched (ENull) transmission with the internal
                                     reflections folded in; reflectance = specularReflectance, specular_transmittance, eta[0].  Null transitions
                                     are looked through by the emitter lookup (GP:2184-2245) and by light sampling (scene.cpp:619-679) */
-    PPG_BSDF_ROUGHPLASTIC = 5    /* src/bsdfs/roughplastic.cpp:326-507: rough dielectric coat over a diffuse base; the rough transmittance
-                                    (src/bsdfs/rtrans.h) is passed as a per-material 100-entry table + scalars */
 } ppg_bsdf_type;
 
 typedef enum ppg_microfacet { PPG_MICROFACET_BECKMANN = 0, PPG_MICROFACET_GGX = 1 } ppg_microfacet;   /* microfacet.h:47-60 */
