@@ -85,6 +85,13 @@ def spaceship_log():
     with open(os.path.join(ROOT, "tests", "golden", "spaceship_log_stats.json"), "w") as f:
         json.dump({"spaceship-improved": st}, f, indent=1)
     print("spaceship log:", [(i["passes"], i.get("var"), i["stat_weight"][1]) for i in st["iterations"]])
+    # the golden image itself, box-downsampled 4x4 to 160x90 RGB (float16, ~86 KB): image-level known answer for the GPU test
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import cv2
+    im = cv2.imread(f"{REF}/scenes/spaceship/spaceship-improved.exr", cv2.IMREAD_UNCHANGED)[..., :3][..., ::-1].astype(np.float64)
+    small = im.reshape(90, 4, 160, 4, 3).mean(axis=(1, 3))
+    np.save(os.path.join(ROOT, "tests", "golden", "spaceship_improved_160x90.npy"), small.astype(np.float16))
+    print("spaceship golden image mean rgb", im.mean(axis=(0, 1)))
 
 
 def main():
