@@ -1,9 +1,13 @@
 // TEST INFRASTRUCTURE -- CPU oracle, never shipped, never on the product path.
 //
 // ppg_cpu_tracer.h: plain-C++ restatement of the reference's GuidedPathTracer
-// integrator (mitsuba/src/integrators/path/guided_path.cpp, "GP") for the scene
-// subset of the hot path: perspective camera, triangle meshes, diffuse (optionally
-// two-sided) BSDFs, area lights, box-filtered film.  Templated on the SD-tree
+// integrator (mitsuba/src/integrators/path/guided_path.cpp, "GP") and of the Mitsuba
+// services its loop calls: perspective camera, triangle meshes and analytic spheres,
+// the BSDF models diffuse / dielectric / conductor / roughconductor / roughplastic /
+// roughdielectric / plastic / thindielectric with the twosided and mask wrappers,
+// index-matched (null) transitions, area lights on meshes and spheres with light
+// sampling, box-filtered film.  Pinned against the authors' render logs and images
+// of CBOX and SPACESHIP (tests/test_oracle_golden.py).  Templated on the SD-tree
 // backend so that the same tracer runs either on the restated trees
 // (sdtree_port.h) or on the reference's own SD-tree code compiled verbatim
 // (oracle/sdtree_ref, built into oracle/_ref/).
