@@ -265,7 +265,7 @@ struct ppg_integrator {
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
-    DevBuf<uint32_t> dPixelMap; uint32_t nLocalPixels = 0;
+    DevBuf<uint32_t> dPixelMap; uint32_t nLocalPixels = 0, minLocalPixels = 0;
 
     // film
     DevBuf<float4> dImage, dSqImage, dFilm; DevBuf<float> dRgb; DevBuf<double> dVar;
@@ -382,6 +382,12 @@ static int build_pixel_map(ppg_integrator *h) {
             for (int x = x0; x < std::min(x0 + bs, h->W); ++x) map.push_back((uint32_t) x | ((uint32_t) y << 16));
     }
     h->nLocalPixels = (uint32_t) map.size();
+    h->minLocalPixels = 0xffffffffu;                      // smallest share of any rank: decisions every rank must take alike
+    for (int r = 0; r < h->world; ++r) {
+        uint64_t c = 0;
+        for (int b = r; b < bx * by; b += h->world) { const int x0 = (b % bx) * bs, y0 = (b / bx) * bs; c += (uint64_t) (std::min(x0 + bs, h->W) - x0) * (std::min(y0 + bs, h->H) - y0); }
+        h->minLocalPixels = std::min<uint32_t>(h->minLocalPixels, (uint32_t) c);
+    }
     CK(h->dPixelMap.alloc(std::max<size_t>(map.size(), 1)));
     if (!map.empty()) CK(cudaMemcpy(h->dPixelMap.p, map.data(), map.size() * 4, cudaMemcpyHostToDevice));
     return PPG_OK;
@@ -890,8 +896,9 @@ template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderP
 }
 
 // one batch of `nPasses` passes as a single wavefront
-static int render_batch(ppg_integrator *h, int nPasses) {
-    const uint32_t nPaths = (uint32_t) ((size_t) nPasses * h->nLocalPixels * h->prm.spp_per_pass);
+// one batch of `nPasses` passes as a single wavefront, over this rank's pixels [pixel0, pixel0 + pixelCount) of the pixel map
+static int render_batch(ppg_integrator *h, int nPasses, uint32_t pixel0, uint32_t pixelCount) {
+    const uint32_t nPaths = (uint32_t) ((size_t) nPasses * pixelCount * h->prm.spp_per_pass);
     if (nPaths == 0) return PPG_OK;
     const int record = h->isFinalIter ? 0 : h->recordMode;
     CK(cudaMemsetAsync(h->dLive.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
@@ -899,8 +906,8 @@ static int render_batch(ppg_integrator *h, int nPasses) {
     CK(cudaMemcpyAsync(h->dLive.p, &nPaths, 4, cudaMemcpyHostToDevice, h->stream));
     RenderParams P;
     P.scene = h->sceneView; P.cam = h->cam; P.tree = tree_view(h);
-    P.liFinal = h->dLiFinal.p; P.pixelMap = h->dPixelMap.p; P.counters = h->dCounters.p;
-    P.nPaths = nPaths; P.nLocalPixels = h->nLocalPixels; P.spp = (uint32_t) h->prm.spp_per_pass;
+    P.liFinal = h->dLiFinal.p; P.pixelMap = h->dPixelMap.p + pixel0; P.counters = h->dCounters.p;
+    P.nPaths = nPaths; P.nLocalPixels = pixelCount; P.spp = (uint32_t) h->prm.spp_per_pass;
     P.passBase = (uint64_t) h->passesRendered; P.seed = h->prm.seed;
     P.maxDepth = h->prm.max_depth; P.rrDepth = h->prm.rr_depth; P.strictNormals = h->prm.strict_normals; P.hideEmitters = h->prm.hide_emitters;
     P.isBuilt = h->isBuilt ? 1 : 0; P.lossMode = h->prm.bsdf_sampling_fraction_loss; P.fixedFraction = h->prm.bsdf_sampling_fraction;
@@ -975,8 +982,8 @@ static int render_batch(ppg_integrator *h, int nPasses) {
         }
     }
     h->tic(PPG_K_FILM);
-    film_kernel<<<std::min<int>(h->numSMs * 8, (int) ((h->nLocalPixels + PPG_BLOCK - 1) / PPG_BLOCK)), PPG_BLOCK, 0, h->stream>>>(
-        h->dLiFinal.p, h->dPixelMap.p, h->nLocalPixels, (uint32_t) h->prm.spp_per_pass, (uint32_t) nPasses, h->W, h->dImage.p, h->dSqImage.p);
+    film_kernel<<<std::min<int>(h->numSMs * 8, (int) ((pixelCount + PPG_BLOCK - 1) / PPG_BLOCK)), PPG_BLOCK, 0, h->stream>>>(
+        h->dLiFinal.p, h->dPixelMap.p + pixel0, pixelCount, (uint32_t) h->prm.spp_per_pass, (uint32_t) nPasses, h->W, h->dImage.p, h->dSqImage.p);
     h->toc(); h->launches++;
     CK(cudaGetLastError());
     return PPG_OK;
@@ -997,7 +1004,20 @@ static int perform_render_passes(ppg_integrator *h, float &variance, int numPass
         int nb = std::min(maxBatch, numPasses - local);
         // the sampling fraction is learned between pass-batches (theta is constant inside a wavefront): start with small batches
         if (h->isBuilt && !h->isFinalIter && h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) nb = std::min(nb, std::max(1, local / 2));
-        int rc = render_batch(h, nb);
+        // ... and split the first passes of the iteration into pixel sub-batches: the reference updates theta after every ~2 records
+        // WHILE a pass runs (GP:672-697), so its first guided pass already adapts; one wavefront per pass would render it with stale
+        // fractions (visible against the authors' SPACESHIP log as -5 % recorded vertices in iteration 1).  8 / 4 / 2 stripes of
+        // the block-ordered pixel map for passes 0 / 1 / 2; every rank makes the same number of calls (Adam replicas are averaged per call).
+        int rc = PPG_OK;
+        static const int subMax = std::max(env_int("PPG_LOSS_SUBBATCH", 8), 1);
+        const bool learning = h->isBuilt && !h->isFinalIter && h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE;
+        const int K = (learning && nb == 1 && local < 3) ? std::max(subMax >> local, 1) : 1;
+        if (K > 1 && h->minLocalPixels >= (uint32_t) K * 1024u) {
+            for (int k = 0; k < K && !rc; ++k) {
+                const uint32_t p0 = (uint32_t) ((uint64_t) h->nLocalPixels * k / K), p1 = (uint32_t) ((uint64_t) h->nLocalPixels * (k + 1) / K);
+                rc = render_batch(h, 1, p0, p1 - p0);
+            }
+        } else rc = render_batch(h, nb, 0, h->nLocalPixels);
         if (rc) return rc;
         h->passesRendered += nb; local += nb;
         bool shouldAbort = false;
