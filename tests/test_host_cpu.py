@@ -154,3 +154,47 @@ def test_unsupported_scene_content_is_refused_not_substituted():
         pytest.skip("reference tree not present")
     with pytest.raises(NotImplementedError):
         load_mitsuba_xml("/root/reference/scenes/kitchen/kitchen.xml")
+
+
+def test_loader_parses_every_supported_bsdf_and_shape(tmp_path):
+    """One synthetic Mitsuba XML with every BSDF plugin / wrapper / shape the hot path implements: the loader must fill ppg_bsdf rows
+    (type, flags, parameters) and ppg_sphere entries as the C ABI documents them."""
+    from ppg_b200 import scene as S
+    xml = """<scene version="0.5.0">
+      <integrator type="guided_path"><string name="budgetType" value="spp"/><float name="budget" value="8"/><string name="nee" value="always"/></integrator>
+      <sensor type="perspective"><float name="fov" value="40"/>
+        <transform name="toWorld"><lookat origin="0, 1, -5" target="0, 1, 0" up="0, 1, 0"/></transform>
+        <film type="hdrfilm"><integer name="width" value="64"/><integer name="height" value="48"/><rfilter type="box"/></film></sensor>
+      <bsdf type="diffuse" id="d"><rgb name="reflectance" value="0.1, 0.2, 0.3"/></bsdf>
+      <bsdf type="twosided" id="rc"><bsdf type="roughconductor"><float name="alpha" value="0.2"/><string name="distribution" value="ggx"/>
+        <rgb name="eta" value="1.5, 1.0, 0.5"/><rgb name="k" value="3, 2, 1"/><float name="extEta" value="1"/></bsdf></bsdf>
+      <bsdf type="dielectric" id="g"><float name="intIOR" value="1.5"/><float name="extIOR" value="1"/></bsdf>
+      <bsdf type="thindielectric" id="tg"><float name="intIOR" value="1.33"/><float name="extIOR" value="1"/></bsdf>
+      <bsdf type="roughdielectric" id="rg"><float name="alpha" value="0.05"/><string name="distribution" value="beckmann"/><float name="intIOR" value="1.5"/><float name="extIOR" value="1"/></bsdf>
+      <bsdf type="plastic" id="p"><rgb name="diffuseReflectance" value="0.5, 0.1, 0.1"/><float name="intIOR" value="1.5"/><float name="extIOR" value="1"/><boolean name="nonlinear" value="true"/></bsdf>
+      <bsdf type="mask" id="m"><rgb name="opacity" value="0.6, 0.6, 0.6"/><bsdf type="twosided"><bsdf type="diffuse"><rgb name="reflectance" value="0.6, 0.5, 0.4"/></bsdf></bsdf></bsdf>
+      <bsdf type="conductor" id="c"><string name="material" value="none"/></bsdf>
+      <shape type="rectangle"><transform name="toWorld"><scale x="2" y="2"/><translate x="0" y="3" z="0"/></transform><ref id="d"/>
+        <emitter type="area"><rgb name="radiance" value="5, 5, 5"/></emitter></shape>
+      <shape type="rectangle"><ref id="m"/></shape>
+      <shape type="sphere"><point name="center" x="1" y="1" z="0"/><float name="radius" value="0.5"/><ref id="g"/></shape>
+      <shape type="sphere"><boolean name="flipNormals" value="true"/><transform name="toWorld"><scale value="50"/></transform>
+        <emitter type="area"><rgb name="radiance" value="0.1, 0.1, 0.1"/></emitter></shape>
+    </scene>"""
+    p = tmp_path / "scene.xml"; p.write_text(xml)
+    sc = S.load_mitsuba_xml(str(p))
+    row = {n: sc.bsdfs[i] for i, n in enumerate(sc.bsdf_names)}
+    ty = lambda n: int(row[n][:1].view(np.uint32)[0]); fl = lambda n: int(row[n][1:2].view(np.uint32)[0])
+    assert sc.bsdfs.shape[1] == 28
+    assert (ty("d"), ty("rc"), ty("g"), ty("tg"), ty("rg"), ty("p"), ty("m"), ty("c")) == (0, 4, 2, 8, 6, 7, 0, 3)
+    assert fl("rc") == S.BSDF_FLAG_TWOSIDED and fl("m") == (S.BSDF_FLAG_MASK | S.BSDF_FLAG_TWOSIDED) and fl("p") == S.BSDF_FLAG_NONLINEAR
+    assert np.allclose(row["m"][22:25], 0.6) and np.allclose(row["m"][2:5], [0.6, 0.5, 0.4])
+    assert np.allclose(row["rc"][8:11], [1.5, 1.0, 0.5]) and np.allclose(row["rc"][11:14], [3, 2, 1]) and np.isclose(row["rc"][14], 0.2) and int(row["rc"][15:16].view(np.int32)[0]) == 1
+    assert np.isclose(row["rg"][14], 0.05) and int(row["rg"][15:16].view(np.int32)[0]) == 0 and np.isclose(row["tg"][8], 1.33)
+    assert np.isclose(row["p"][19], S.fresnel_diffuse_reflectance(1 / 1.5)) and 0 < row["p"][20] < 1
+    assert len(sc.indices) == 4 and sc.spheres.shape == (2, 6)
+    assert np.allclose(sc.spheres[0, :4], [1, 1, 0, 0.5]) and np.allclose(sc.spheres[1, :4], [0, 0, 0, 50])
+    assert sc.spheres[:, 5].view(np.int32).tolist() == [0, 1]                    # flipNormals
+    assert sc.spheres[:, 4].view(np.int32).tolist() == [2, 3] and sc.shapes[3, 3] == 1 and sc.shapes[0, 3] == 0     # shape / emitter indices
+    assert np.allclose(sc.aabb_min, -50) and np.allclose(sc.aabb_max, 50) and sc.integrator["nee"] == "always"
+    assert (sc.film_width, sc.film_height) == (64, 48)
