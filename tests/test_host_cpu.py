@@ -198,3 +198,7 @@ def test_loader_parses_every_supported_bsdf_and_shape(tmp_path):
     assert sc.spheres[:, 4].view(np.int32).tolist() == [2, 3] and sc.shapes[3, 3] == 1 and sc.shapes[0, 3] == 0     # shape / emitter indices
     assert np.allclose(sc.aabb_min, -50) and np.allclose(sc.aabb_max, 50) and sc.integrator["nee"] == "always"
     assert (sc.film_width, sc.film_height) == (64, 48)
+    # and the oracle renders it (all models on one path: light sampling of both emitters through the mask, the glass sphere, the shell)
+    import oracle_lib as O
+    o = O.Oracle(O.params_from_xml(sc.integrator), sc, kind="port"); img, st = o.render()
+    assert img.shape == (48, 64, 3) and np.isfinite(img).all() and img.mean() > 0.01 and st["total_paths"] == 64 * 48 * 8
