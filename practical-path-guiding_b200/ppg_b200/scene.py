@@ -403,7 +403,8 @@ def make_sphere(center, radius, shape, flip_normals=False):
 
 
 def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0), alpha=0.1, distribution=0):
-    """One ppg_bsdf (include/ppg.h) as 16 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], alpha, distribution (int bits)."""
+    """One ppg_bsdf (include/ppg.h) as 28 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], alpha, distribution (int bits),
+    specular_reflectance[3], fdr_int, specular_sampling_weight, table (int bits), opacity[3], reserved[3]; the trailing fields stay 0 here."""
     b = np.zeros(28, np.float32)
     b[:2] = np.array([type_, flags], np.uint32).view(np.float32)
     b[2:5] = refl; b[5:8] = trans; b[8:11] = eta; b[11:14] = k; b[14] = alpha
