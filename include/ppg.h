@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PPG_ABI_VERSION 1
+#define PPG_ABI_VERSION 2   /* 2: bitmap textures, bumpmap, environment map */
 
 typedef enum ppg_status {
     PPG_OK = 0,
@@ -128,6 +128,8 @@ typedef enum ppg_microfacet { PPG_MICROFACET_BECKMANN = 0, PPG_MICROFACET_GGX = 
 #define PPG_BSDF_FLAG_TWOSIDED 1u /* src/bsdfs/twosided.cpp:108-184 wrapping the model */
 #define PPG_BSDF_FLAG_NONLINEAR 2u /* roughplastic "nonlinear" (roughplastic.cpp:366-369) */
 #define PPG_BSDF_FLAG_MASK 4u     /* src/bsdfs/mask.cpp:113-220 wrapping the (possibly twosided) model: constant `opacity`; a smooth/null hybrid */
+#define PPG_BSDF_FLAG_BUMPMAP 8u  /* src/bsdfs/bumpmap.cpp:161-238 wrapping everything above: the shading frame is perturbed by the gradient of the
+                                     displacement texture `bump_texture` (Frame getFrame(its), :139-159) */
 #define PPG_BSDF_TABLE_SIZE 100   /* theta samples of the rough-transmittance tables (data/microfacet/*.dat) */
 
 typedef struct ppg_bsdf {
@@ -144,8 +146,37 @@ typedef struct ppg_bsdf {
     float    specular_sampling_weight;  /* roughplastic: sAvg / (dAvg + sAvg) (roughplastic.cpp:269-272) */
     int32_t  table;           /* roughplastic: index into ppg_scene_desc.bsdf_tables (external rough transmittance over cos(theta)^(1/4)) */
     float    opacity[3];      /* PPG_BSDF_FLAG_MASK: linear RGB opacity (mask.cpp:63-66) */
-    float    reserved[3];
+    uint32_t reflectance_texture;   /* 1 + index into ppg_scene_desc.textures of the bitmap that replaces `reflectance` (diffuse "reflectance",
+                                       roughplastic / plastic "diffuseReflectance"); 0 = the constant above.  For roughplastic / plastic the
+                                       caller sets specular_sampling_weight from the texture's average (roughplastic.cpp:269-272) */
+    uint32_t bump_texture;          /* PPG_BSDF_FLAG_BUMPMAP: 1 + index of the displacement texture */
+    uint32_t reserved;
 } ppg_bsdf;                   /* 112 bytes */
+
+/* Bitmap texture (src/textures/bitmap.cpp).  The integrator fetches BSDFs without ray differentials (GP:1934 its.getBSDF() ->
+ * hasUVPartials stays false, render/skdtree.h:417), so every lookup is the bilinear one at MIP level 0 (bitmap.cpp:431-453,
+ * render/mipmap.h:575-596) whatever `filterType` says; only level 0 is passed.  Texels are IEEE half floats like the reference's
+ * storage (bitmap.cpp:178-183), linear RGB (3 channels) or luminance (1 channel), row-major, row 0 first as decoded from the file. */
+typedef enum ppg_wrap { PPG_WRAP_REPEAT = 0, PPG_WRAP_CLAMP = 1, PPG_WRAP_MIRROR = 2 } ppg_wrap;   /* mipmap.h:503-563 */
+typedef struct ppg_texture {
+    uint32_t width, height;
+    uint32_t channels;        /* 1 or 3 */
+    uint32_t wrap_u, wrap_v;  /* ppg_wrap */
+    float    uv_scale[2];     /* Texture2D: uv' = uv * scale + offset (librender/texture.cpp:81-121) */
+    float    uv_offset[2];
+    uint32_t reserved;
+    uint64_t first_texel;     /* offset (in uint16 elements) of texel (0,0) in ppg_scene_desc.texels */
+} ppg_texture;                /* 48 bytes */
+
+/* Environment emitter (src/emitters/envmap.cpp; `sunsky` is baked into one on the host, src/emitters/sunsky.cpp:122-225):
+ * lat-long RGB map in half precision, looked up bilinearly (u repeats, v clamps) with u = atan2(v.x, -v.z) / 2pi,
+ * v = acos(v.y) / pi for v = world_to_env * d (envmap.cpp:380-410); evaluated when a ray leaves the scene (GP:1902-1914, 2228-2243). */
+typedef struct ppg_envmap {
+    uint32_t width, height;   /* 0 x 0: the scene has no environment emitter */
+    const uint16_t *texels;   /* width * height * 3 half floats */
+    float    scale;           /* envmap "scale" */
+    float    world_to_env[9]; /* row-major linear part of the inverse emitter-to-world transform */
+} ppg_envmap;
 
 typedef struct ppg_shape {
     uint32_t first_triangle;  /* triangles of a shape are contiguous */
@@ -193,6 +224,13 @@ typedef struct ppg_scene_desc {
     const ppg_sphere *spheres;      /* may be NULL */
     ppg_camera camera;
     float aabb_min[3], aabb_max[3]; /* Scene::getAABB(): kd-tree AABB + sensor + emitter AABBs (librender/scene.cpp:387-413) */
+    /* ABI 2 */
+    uint32_t n_textures;
+    uint32_t reserved;
+    const ppg_texture *textures;    /* may be NULL */
+    const uint16_t *texels;         /* half floats of all textures */
+    uint64_t n_texels;              /* length of texels (bounds check) */
+    ppg_envmap envmap;
 } ppg_scene_desc;
 
 /* ---- per-iteration statistics (the reference's log lines, GP:1176-1186, 1323-1326) --- */

@@ -4,9 +4,10 @@
 // integrator (mitsuba/src/integrators/path/guided_path.cpp, "GP") and of the Mitsuba
 // services its loop calls: perspective camera, triangle meshes and analytic spheres,
 // the BSDF models diffuse / dielectric / conductor / roughconductor / roughplastic /
-// roughdielectric / plastic / thindielectric with the twosided and mask wrappers,
-// index-matched (null) transitions, area lights on meshes and spheres with light
-// sampling, box-filtered film.  Pinned against the authors' render logs and images
+// roughdielectric / plastic / thindielectric with the twosided, mask and bumpmap
+// wrappers, bilinear bitmap textures, index-matched (null) transitions, area lights on
+// meshes and spheres with light sampling, a lat-long environment emitter (sunsky is
+// baked into one on the host), box-filtered film.  Pinned against the authors' render logs and images
 // of CBOX and SPACESHIP (tests/test_oracle_golden.py).  Templated on the SD-tree
 // backend so that the same tracer runs either on the restated trees
 // (sdtree_port.h) or on the reference's own SD-tree code compiled verbatim
@@ -134,6 +135,7 @@ static inline bool triaccel_intersect(const TriAccelP &tr, F3 o, F3 d, float min
     return u >= 0 && v >= 0 && u + v <= 1.0f;
 }
 
+static const float kInvPiS = 0.31830988618379067154f; // INV_PI
 struct BvhNode { float bmin[3], bmax[3]; uint32_t left, count; };   // count>0: leaf, left = first prim slot; else children left, left+1
 
 struct Scene {
@@ -149,6 +151,77 @@ struct Scene {
     // (TriMesh::prepareSamplingTable, src/librender/trimesh.cpp:388-403) and the discrete emitter choice (scene.cpp:357-381)
     struct EmitterSampler { uint32_t firstTri, nTris; std::vector<float> cdf; float invArea; int shape; int sphere; };
     std::vector<EmitterSampler> emitterSamplers; std::vector<float> emitterCdf; float emitterNormalization = 0;
+    // bitmap textures (level 0, half precision like the reference's storage) and the environment map
+    std::vector<ppg_texture> textures; std::vector<uint16_t> texels;
+    uint32_t envW = 0, envH = 0; std::vector<uint16_t> envTexels; float envScale = 1.0f; float worldToEnv[9];
+
+    static float halfToFloat(uint16_t h) {
+        const uint32_t sgn = (uint32_t) (h >> 15) << 31, e = (h >> 10) & 31u, m = h & 1023u;
+        uint32_t bits;
+        if (e == 0) {
+            if (m == 0) bits = sgn;
+            else { int sh = 0; uint32_t mm = m; while (!(mm & 1024u)) { mm <<= 1; ++sh; } bits = sgn | ((uint32_t) (113 - sh) << 23) | ((mm & 1023u) << 13); }
+        } else if (e == 31) bits = sgn | 0x7f800000u | (m << 13);
+        else bits = sgn | ((e + 112u) << 23) | (m << 13);
+        float f; std::memcpy(&f, &bits, 4); return f;
+    }
+    static int wrapIndex(int x, int size, uint32_t mode) {            // TMIPMap::evalTexel boundary handling, render/mipmap.h:503-563
+        if (x >= 0 && x < size) return x;
+        if (mode == PPG_WRAP_REPEAT) { int r = x % size; return r < 0 ? r + size : r; }          // math::modulo
+        if (mode == PPG_WRAP_CLAMP) return std::min(std::max(x, 0), size - 1);
+        int r = x % (2 * size); if (r < 0) r += 2 * size;                                        // mirror
+        return r >= size ? 2 * size - r - 1 : r;
+    }
+    static F3 texel(const uint16_t *base, uint32_t W, uint32_t Hh, uint32_t channels, uint32_t wu, uint32_t wv, int x, int y) {
+        x = wrapIndex(x, (int) W, wu); y = wrapIndex(y, (int) Hh, wv);
+        const uint16_t *px = base + ((size_t) y * W + (size_t) x) * channels;
+        if (channels == 1) { const float v = halfToFloat(px[0]); return f3(v, v, v); }
+        return f3(halfToFloat(px[0]), halfToFloat(px[1]), halfToFloat(px[2]));
+    }
+    // TMIPMap::evalBilinear(0, uv), render/mipmap.h:575-596
+    static F3 bilinear(const uint16_t *base, uint32_t W, uint32_t Hh, uint32_t channels, uint32_t wu, uint32_t wv, float uu, float vv) {
+        if (!std::isfinite(uu) || !std::isfinite(vv)) return f3(0, 0, 0);
+        const float u = uu * (float) W - 0.5f, v = vv * (float) Hh - 0.5f;
+        const int xPos = (int) std::floor(u), yPos = (int) std::floor(v);
+        const float dx1 = u - (float) xPos, dx2 = 1.0f - dx1, dy1 = v - (float) yPos, dy2 = 1.0f - dy1;
+        return texel(base, W, Hh, channels, wu, wv, xPos, yPos) * dx2 * dy2 + texel(base, W, Hh, channels, wu, wv, xPos, yPos + 1) * dx2 * dy1
+             + texel(base, W, Hh, channels, wu, wv, xPos + 1, yPos) * dx1 * dy2 + texel(base, W, Hh, channels, wu, wv, xPos + 1, yPos + 1) * dx1 * dy1;
+    }
+    // Texture2D::eval(its) without UV partials (librender/texture.cpp:112-121) -> BitmapTexture::eval(uv) (textures/bitmap.cpp:431-453)
+    F3 evalTexture(uint32_t idx, float u, float v) const {
+        const ppg_texture &t = textures[idx];
+        return bilinear(texels.data() + t.first_texel, t.width, t.height, t.channels, t.wrap_u, t.wrap_v, u * t.uv_scale[0] + t.uv_offset[0], v * t.uv_scale[1] + t.uv_offset[1]);
+    }
+    // Texture2D::evalGradient(its) (texture.cpp:123-130) -> BitmapTexture::evalGradient(uv) (bitmap.cpp:455-479) -> evalGradientBilinear (mipmap.h:601-626);
+    // returns the luminances BumpMap::getFrame uses (bumpmap.cpp:141-144)
+    void evalTextureGradientLum(uint32_t idx, float u_, float v_, float &dDu, float &dDv) const {
+        const ppg_texture &t = textures[idx];
+        const float uu = u_ * t.uv_scale[0] + t.uv_offset[0], vv = v_ * t.uv_scale[1] + t.uv_offset[1];
+        F3 g0 = f3(0, 0, 0), g1 = f3(0, 0, 0);
+        if (std::isfinite(uu) && std::isfinite(vv)) {
+            const uint16_t *base = texels.data() + t.first_texel;
+            const float u = uu * (float) t.width - 0.5f, v = vv * (float) t.height - 0.5f;
+            const int xPos = (int) std::floor(u), yPos = (int) std::floor(v);
+            const float dx = u - (float) xPos, dy = v - (float) yPos;
+            const F3 p00 = texel(base, t.width, t.height, t.channels, t.wrap_u, t.wrap_v, xPos, yPos), p10 = texel(base, t.width, t.height, t.channels, t.wrap_u, t.wrap_v, xPos + 1, yPos),
+                     p01 = texel(base, t.width, t.height, t.channels, t.wrap_u, t.wrap_v, xPos, yPos + 1), p11 = texel(base, t.width, t.height, t.channels, t.wrap_u, t.wrap_v, xPos + 1, yPos + 1);
+            const F3 tmp = p01 + p10 - p11;
+            g0 = (p10 + p00 * (dy - 1) - tmp * dy) * (float) t.width;
+            g1 = (p01 + p00 * (dx - 1) - tmp * dx) * (float) t.height;
+        }
+        g0 = g0 * t.uv_scale[0]; g1 = g1 * t.uv_scale[1];
+        dDu = g0.x * 0.212671f + g0.y * 0.715160f + g0.z * 0.072169f;
+        dDv = g1.x * 0.212671f + g1.y * 0.715160f + g1.z * 0.072169f;
+    }
+    bool hasEnvironment() const { return envW != 0; }
+    // EnvironmentMap::evalEnvironment without ray differentials (src/emitters/envmap.cpp:380-410): u repeats, v clamps (:176-178)
+    F3 evalEnvironment(F3 d) const {
+        const F3 v = f3(worldToEnv[0] * d.x + worldToEnv[1] * d.y + worldToEnv[2] * d.z, worldToEnv[3] * d.x + worldToEnv[4] * d.y + worldToEnv[5] * d.z,
+                        worldToEnv[6] * d.x + worldToEnv[7] * d.y + worldToEnv[8] * d.z);
+        const float uu = std::atan2(v.x, -v.z) * 0.15915494309189533577f;                  // INV_TWOPI
+        const float vv = std::acos(std::min(1.0f, std::max(-1.0f, v.y))) * kInvPiS;          // math::safe_acos * INV_PI
+        return bilinear(envTexels.data(), envW, envH, 3, PPG_WRAP_REPEAT, PPG_WRAP_CLAMP, uu, vv) * envScale;
+    }
 
     // DiscreteDistribution::sample (include/mitsuba/core/pmf.h:124-137)
     static size_t cdfSample(const std::vector<float> &cdf, float v) {
@@ -196,6 +269,11 @@ struct Scene {
         if (d.spheres && d.n_spheres) spheres.assign(d.spheres, d.spheres + d.n_spheres);
         radiance.resize(d.n_emitters);
         for (uint32_t i = 0; i < d.n_emitters; ++i) radiance[i] = f3(d.area_radiance[3 * i], d.area_radiance[3 * i + 1], d.area_radiance[3 * i + 2]);
+        textures.clear(); texels.clear();
+        if (d.textures && d.n_textures) { textures.assign(d.textures, d.textures + d.n_textures); texels.assign(d.texels, d.texels + d.n_texels); }
+        envW = d.envmap.width; envH = d.envmap.height; envTexels.clear();
+        if (envW && envH && d.envmap.texels) { envTexels.assign(d.envmap.texels, d.envmap.texels + (size_t) envW * envH * 3); envScale = d.envmap.scale; std::memcpy(worldToEnv, d.envmap.world_to_env, sizeof(worldToEnv)); }
+        else envW = envH = 0;
         cam = d.camera;
         aabbMin = f3(d.aabb_min[0], d.aabb_min[1], d.aabb_min[2]); aabbMax = f3(d.aabb_max[0], d.aabb_max[1], d.aabb_max[2]);
         const float *m = cam.to_world;
@@ -333,6 +411,7 @@ struct Scene {
 // Intersection record: the fields of render/shape.h:36 Intersection the path uses
 struct Its {
     bool valid; float t; F3 p, geoN, shN, shS, shT, wi; uint32_t shape;
+    float uvU = 0, uvV = 0; uint32_t prim = 0xFFFFFFFFu; F3 bary;      // texture coordinates (skdtree.h:398-405) and the triangle hit (for the UV tangents)
     F3 toLocal(F3 v) const { return f3(dot(v, shS), dot(v, shT), dot(v, shN)); }
     F3 toWorld(F3 v) const { return shS * v.x + shT * v.y + shN * v.z; }
 };
@@ -360,6 +439,7 @@ static inline bool ray_intersect(const Scene &sc, F3 o, F3 d, float mint, float 
         its.shS = normalize(dpdu - its.shN * dot(its.shN, dpdu));
         its.shT = cross(its.shN, its.shS);
         its.wi = its.toLocal(-d);
+        its.prim = h.prim; its.uvU = its.uvV = 0;      // (textured / bump-mapped spheres are refused by the loader)
         return true;
     }
     const uint32_t i0 = sc.idx[3 * h.prim], i1 = sc.idx[3 * h.prim + 1], i2 = sc.idx[3 * h.prim + 2];
@@ -371,12 +451,19 @@ static inline bool ray_intersect(const Scene &sc, F3 o, F3 d, float mint, float 
     const float len = length(faceN);
     if (!is_zero(faceN)) faceN = faceN * (1.0f / len);   // Normal::operator/= (reciprocal multiply)
     its.shape = sc.triShape[h.prim];
+    its.prim = h.prim; its.bary = b;
+    if (sc.shapes[its.shape].has_uvs) {            // its.uv = t0 * b.x + t1 * b.y + t2 * b.z (skdtree.h:398-403)
+        its.uvU = sc.UV[2 * i0] * b.x + sc.UV[2 * i1] * b.y + sc.UV[2 * i2] * b.z;
+        its.uvV = sc.UV[2 * i0 + 1] * b.x + sc.UV[2 * i1 + 1] * b.y + sc.UV[2 * i2 + 1] * b.z;
+    } else { its.uvU = b.y; its.uvV = b.z; }
     if (sc.shapes[its.shape].has_normals) {
         its.shN = normalize(sc.N[i0] * b.x + sc.N[i1] * b.y + sc.N[i2] * b.z);
         if (dot(faceN, its.shN) < 0) faceN = -faceN;
     } else its.shN = faceN;
     its.geoN = faceN;
-    const F3 dpdu = side1;   // no UV tangents for meshes without texture coordinates (skdtree.h:373-380)
+    // dpdu = side1 also for meshes WITH texture coordinates, where the reference uses the UV tangent (skdtree.h:373-380, trimesh.cpp:385): the two
+    // frames differ by a rotation about n, which no isotropic BSDF can observe; the bumpmap wrapper, which can, computes the UV tangents itself
+    const F3 dpdu = side1;
     its.shS = normalize(dpdu - its.shN * dot(its.shN, dpdu));
     its.shT = cross(its.shN, its.shS);
     its.wi = its.toLocal(-d);
@@ -1004,6 +1091,67 @@ static inline F3 bsdf_sample(const ppg_bsdf &b, F3 wi, float sx, float sy, BsdfS
     return bsdf_sample_inner(b, wi, sx, sy, s, pdf, tables, rng);
 }
 
+// ---- the BSDF at a hit: textured parameters looked up at its.uv (Texture2D::eval, librender/texture.cpp:112-121), and the bumpmap wrapper
+// (src/bsdfs/bumpmap.cpp): BumpMap::getFrame :139-159, eval :161-175, pdf :177-193, sample :214-236
+struct HitBsdf {
+    ppg_bsdf b; bool bump = false; F3 bs, bt, bn;          // perturbed frame (world space)
+    F3 toPerturbed(const Its &its, F3 wLocal) const { const F3 w = its.toWorld(wLocal); return f3(dot(w, bs), dot(w, bt), dot(w, bn)); }
+    F3 fromPerturbed(const Its &its, F3 wP) const { return its.toLocal(bs * wP.x + bt * wP.y + bn * wP.z); }
+};
+// per-triangle UV tangents, TriMesh::computeUVTangents (src/librender/trimesh.cpp:683-743); meshes without texture coordinates: the two edges
+static inline void uv_tangents(const Scene &sc, const Its &its, F3 &dpdu, F3 &dpdv) {
+    const uint32_t i0 = sc.idx[3 * its.prim], i1 = sc.idx[3 * its.prim + 1], i2 = sc.idx[3 * its.prim + 2];
+    const F3 dP1 = sc.P[i1] - sc.P[i0], dP2 = sc.P[i2] - sc.P[i0];
+    if (!sc.shapes[its.shape].has_uvs) { dpdu = dP1; dpdv = dP2; return; }
+    const float du1 = sc.UV[2 * i1] - sc.UV[2 * i0], dv1 = sc.UV[2 * i1 + 1] - sc.UV[2 * i0 + 1], du2 = sc.UV[2 * i2] - sc.UV[2 * i0], dv2 = sc.UV[2 * i2 + 1] - sc.UV[2 * i0 + 1];
+    const F3 n = cross(dP1, dP2); const float len = length(n);
+    if (len == 0) { dpdu = dpdv = f3(0, 0, 0); return; }
+    const float determinant = du1 * dv2 - dv1 * du2;
+    if (determinant == 0) { coordinate_system(n * (1.0f / len), dpdu, dpdv); return; }
+    const float invDet = 1.0f / determinant;
+    dpdu = (dP1 * dv2 - dP2 * dv1) * invDet;
+    dpdv = (dP1 * (-du2) + dP2 * du1) * invDet;
+}
+static inline void resolve_bsdf(const Scene &sc, const Its &its, int index, HitBsdf &hb) {
+    hb.b = sc.bsdfs[index]; hb.bump = false;
+    if (hb.b.reflectance_texture) {
+        const F3 c = sc.evalTexture(hb.b.reflectance_texture - 1, its.uvU, its.uvV);
+        hb.b.reflectance[0] = c.x; hb.b.reflectance[1] = c.y; hb.b.reflectance[2] = c.z;
+    }
+    if ((hb.b.flags & PPG_BSDF_FLAG_BUMPMAP) && hb.b.bump_texture && !(its.prim & Scene::kSphereBit)) {
+        float dDispDu, dDispDv; sc.evalTextureGradientLum(hb.b.bump_texture - 1, its.uvU, its.uvV, dDispDu, dDispDv);
+        F3 dpdu0, dpdv0; uv_tangents(sc, its, dpdu0, dpdv0);
+        const F3 dpdu = dpdu0 + its.shN * (dDispDu - dot(its.shN, dpdu0)), dpdv = dpdv0 + its.shN * (dDispDv - dot(its.shN, dpdv0));
+        hb.bn = normalize(cross(dpdu, dpdv));
+        hb.bs = normalize(dpdu - hb.bn * dot(hb.bn, dpdu));
+        hb.bt = cross(hb.bn, hb.bs);
+        if (dot(hb.bn, its.geoN) < 0) hb.bn = hb.bn * -1.0f;
+        hb.bump = true;
+    }
+}
+static inline F3 hit_eval(const HitBsdf &hb, const Its &its, F3 wi, F3 wo, const float *tables) {
+    if (!hb.bump) return bsdf_eval(hb.b, wi, wo, tables);
+    const F3 pwi = hb.toPerturbed(its, wi), pwo = hb.toPerturbed(its, wo);
+    if (wo.z * pwo.z <= 0) return f3(0, 0, 0);
+    return bsdf_eval(hb.b, pwi, pwo, tables);
+}
+static inline float hit_pdf(const HitBsdf &hb, const Its &its, F3 wi, F3 wo, const float *tables) {
+    if (!hb.bump) return bsdf_pdf(hb.b, wi, wo, tables);
+    const F3 pwi = hb.toPerturbed(its, wi), pwo = hb.toPerturbed(its, wo);
+    if (wo.z * pwo.z <= 0) return 0.0f;
+    return bsdf_pdf(hb.b, pwi, pwo, tables);
+}
+static inline F3 hit_sample(const HitBsdf &hb, const Its &its, F3 wi, float sx, float sy, BsdfSample &s, float &pdf, const float *tables, Pcg32 *rng) {
+    if (!hb.bump) return bsdf_sample(hb.b, wi, sx, sy, s, pdf, tables, rng);
+    F3 result = bsdf_sample(hb.b, hb.toPerturbed(its, wi), sx, sy, s, pdf, tables, rng);
+    if (!is_zero(result)) {
+        const F3 pwo = s.wo;
+        s.wo = hb.fromPerturbed(its, pwo);
+        if (s.wo.z * pwo.z <= 0) return f3(0, 0, 0);
+    }
+    return result;
+}
+
 // ------------------------------------------------------------------ the integrator
 struct CommitRec {   // GP:1713-1724 Vertex, minus the tree pointer (kept as backend leaf handle)
     F3 o, d, voxel, throughput, bsdfVal, radiance; float woPdf, bsdfPdf, dTreePdf; bool isDelta;
@@ -1053,7 +1201,10 @@ public:
         nVerticesTraced++;
         auto recordRadiance = [&](F3 r) { LiAcc = LiAcc + r; for (int i = 0; i < nVertices; ++i) vtx[i].radiance = vtx[i].radiance + r; };   // GP:1791-1796
         while (depth <= prm.max_depth || prm.max_depth < 0) {
-            if (!its.valid) break;   // no environment emitter in scope (GP:1902-1914)
+            if (!its.valid) {                                                                    // GP:1902-1914: attenuated radiance of the environment emitter
+                if (sc.hasEnvironment() && emittedRadiance && (!prm.hide_emitters || scattered)) recordRadiance(throughput * sc.evalEnvironment(d));
+                break;
+            }
             const ppg_shape &shp = sc.shapes[its.shape];
             if (shp.emitter >= 0 && emittedRadiance && (!prm.hide_emitters || scattered)) {   // GP:1917-1919; area.cpp:104-109
                 if (dot(its.shN, -d) > 0) recordRadiance(throughput * sc.radiance[shp.emitter]);
@@ -1061,7 +1212,8 @@ public:
             if (depth >= prm.max_depth && prm.max_depth != -1) break;                          // GP:1925
             const float wiDotGeoN = -dot(its.geoN, d), wiDotShN = its.wi.z;
             if (wiDotGeoN * wiDotShN < 0 && prm.strict_normals) break;                         // GP:1929-1932
-            const ppg_bsdf &bsdf = sc.bsdfs[shp.bsdf];
+            HitBsdf hb; resolve_bsdf(sc, its, shp.bsdf, hb);                                    // its.getBSDF() (GP:1934): no ray differentials
+            const ppg_bsdf &bsdf = hb.b;
             float voxel[3] = {0, 0, 0}; typename Backend::Leaf *leaf = nullptr;
             if (bsdf_has_smooth(bsdf)) leaf = tree.lookup(&its.p.x, voxel);                    // GP:1942-1944: only smooth BSDFs are guided
             float frac = prm.bsdf_sampling_fraction;
@@ -1070,27 +1222,27 @@ public:
             float woPdf, bsdfPdf, dTreePdf; F3 bsdfWeight; BsdfSample bs;
             float sx = rng.next1D(), sy = rng.next1D();
             if (!isBuilt || !leaf) {
-                bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf, sc.tables.data(), &rng);
+                bsdfWeight = hit_sample(hb, its, its.wi, sx, sy, bs, bsdfPdf, sc.tables.data(), &rng);
                 woPdf = bsdfPdf; dTreePdf = 0;
             } else {
                 F3 result;
                 bool zero = false, deltaEarly = false;
                 if (sx < frac) {
                     sx /= frac;
-                    result = bsdf_sample(bsdf, its.wi, sx, sy, bs, bsdfPdf, sc.tables.data(), &rng);
+                    result = hit_sample(hb, its, its.wi, sx, sy, bs, bsdfPdf, sc.tables.data(), &rng);
                     if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0; zero = true; }
                     else if (bs.delta) { dTreePdf = 0; woPdf = bsdfPdf * frac; result = result * (1.0f / frac); deltaEarly = true; }   // GP:1670-1676
                     else result = result * bsdfPdf;
                 } else {
                     float dw[3]; tree.sample(leaf, rng, dw);
                     bs.wo = its.toLocal(f3(dw[0], dw[1], dw[2])); bs.eta = 1.0f; bs.delta = false;
-                    result = bsdf_eval(bsdf, its.wi, bs.wo, sc.tables.data());
+                    result = hit_eval(hb, its, its.wi, bs.wo, sc.tables.data());
                 }
                 if (zero) bsdfWeight = f3(0, 0, 0);
                 else if (deltaEarly) bsdfWeight = result;
                 else {
                     // pdfMat, GP:1693-1710
-                    bsdfPdf = bsdf_pdf(bsdf, its.wi, bs.wo, sc.tables.data());
+                    bsdfPdf = hit_pdf(hb, its, its.wi, bs.wo, sc.tables.data());
                     if (!std::isfinite(bsdfPdf)) { woPdf = 0; dTreePdf = 0; }
                     else {
                         const F3 wow = its.toWorld(bs.wo);
@@ -1109,12 +1261,12 @@ public:
                     const F3 dl = its.toLocal(ds.d);
                     const float woDotGeoN2 = dot(its.geoN, ds.d);
                     if (!prm.strict_normals || woDotGeoN2 * dl.z > 0) {
-                        const F3 bsdfVal = bsdf_eval(bsdf, its.wi, dl, sc.tables.data());
+                        const F3 bsdfVal = hit_eval(hb, its, its.wi, dl, sc.tables.data());
                         float nWoPdf = 0, nBsdfPdf = 0, nDTreePdf = 0;
                         {   // pdfMat (emitter->isOnSurface() && measure == ESolidAngle always hold for area lights)
-                            if (!isBuilt || !leaf) { nWoPdf = nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl, sc.tables.data()); }
+                            if (!isBuilt || !leaf) { nWoPdf = nBsdfPdf = hit_pdf(hb, its, its.wi, dl, sc.tables.data()); }
                             else {
-                                nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl, sc.tables.data());
+                                nBsdfPdf = hit_pdf(hb, its, its.wi, dl, sc.tables.data());
                                 if (!std::isfinite(nBsdfPdf)) nWoPdf = 0;
                                 else { nDTreePdf = tree.pdf(leaf, &ds.d.x); nWoPdf = frac * nBsdfPdf + (1 - frac) * nDTreePdf; }
                             }
@@ -1182,6 +1334,11 @@ public:
                         qEmitter = ns.emitter; qN = cur->shN; qDist = cur->t;                   // dist: the last segment only (quirk of setQuery after ray.o moved)
                         if (dot(cur->shN, -d) > 0) value = transmittance * sc.radiance[ns.emitter];
                     }
+                } else if (!lost && sc.hasEnvironment()) {
+                    // "Intersected nothing -- perhaps there is an environment map?" (GP:2228-2243); fillDirectSamplingRecord succeeds for any ray
+                    // that starts inside the scene's bounding sphere (envmap.cpp:360-378).  Light sampling of the environment is not built
+                    // (create refuses nee != never with an environment emitter), so no emitter pdf is needed here.
+                    value = transmittance * sc.evalEnvironment(d);
                 }
             }
             const bool isDelta = bs.delta;

@@ -8,6 +8,7 @@
 // traffic, shared-memory staging of the hot read-only data, and warp-aggregated atomics.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace ppg {
@@ -97,6 +98,11 @@ struct SceneView {
     const float *emitterCdf; const float4 *emitterInfo; const float *emitterTriCdf; const float4 *emitterGeom; const uint32_t *emitterFlags;
     float emitterNormalization;
     uint32_t kBegin[4];       // group ranges per k (k == 3: degenerate triangles, never tested)
+    // bitmap textures (level 0; src/textures/bitmap.cpp) and the lat-long environment map (src/emitters/envmap.cpp), half precision like the
+    // reference's storage, one uint2 = {r|g<<16, b} per texel (luminance textures are replicated)
+    //   texMeta[2i+0] = {bits(width), bits(height), bits(wrapU | wrapV<<8), bits(first texel)}, texMeta[2i+1] = {uScale, vScale, uOffset, vOffset}
+    const float4 *texMeta; const uint2 *texels; uint32_t nTextures;
+    const uint2 *envTexels; uint32_t envW, envH; float envScale; float worldToEnv[9];
 };
 struct Camera {             // src/sensors/perspective.cpp:271-298 for a lookAt camera
     float3 o, left, up, dir;
@@ -414,8 +420,10 @@ __device__ __forceinline__ float3 square_to_cosine_hemisphere(float sx, float sy
 #define PPG_BSDF_NONLINEAR 2u
 #define PPG_BSDF_MASK 4u
 // 6 float4 per material: {reflectance.rgb, bits(type | flags<<8)}, {specularTransmittance.rgb, eta}, {eta.rgb, 1/eta}, {k.rgb, alpha (negative: Beckmann, else GGX)},
-// {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), -, -}, {opacity.rgb, luminance(opacity)} (mask flag)
-struct Bsdf { float3 refl, trans, etaRgb, k, specRefl, opacity; float eta, invEta, alpha, fdrInt, ssw, maskProb; uint32_t type, flags; int distr; const float *lut; };
+// {specularReflectance.rgb, fdrInt}, {specularSamplingWeight, bits(table), bits(reflectanceTexture), bits(bumpTexture)}, {opacity.rgb, luminance(opacity)} (mask flag)
+#define PPG_BSDF_BUMPMAP 8u
+struct Bsdf { float3 refl, trans, etaRgb, k, specRefl, opacity; float eta, invEta, alpha, fdrInt, ssw, maskProb; uint32_t type, flags; int distr; const float *lut;
+              uint32_t reflTex, bumpTex; };     // 1 + texture index, 0 = none (ppg_bsdf.reflectance_texture / bump_texture)
 // FULL == false: the scene holds diffuse BSDFs and triangles only (host-checked); every other model compiles away
 template <bool FULL, class Acc>
 __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
@@ -423,7 +431,8 @@ __device__ __forceinline__ Bsdf load_bsdf(const Acc &A_, int idx) {
     Bsdf b; b.refl = f3(a.x, a.y, a.z);
     const uint32_t tf = __float_as_uint(a.w); b.type = FULL ? (tf & 0xffu) : PPG_BSDF_T_DIFFUSE; b.flags = tf >> 8;
     b.trans = b.etaRgb = b.k = b.specRefl = f3(0, 0, 0); b.eta = b.invEta = 1.f; b.alpha = 0.1f; b.distr = 1; b.fdrInt = b.ssw = 0.f; b.lut = nullptr;
-    b.opacity = f3(1, 1, 1); b.maskProb = 1.f;
+    b.opacity = f3(1, 1, 1); b.maskProb = 1.f; b.reflTex = b.bumpTex = 0u;
+    if (FULL) { const float4 w = A_.bsdf(PPG_BSDF_F4 * idx + 5); b.reflTex = __float_as_uint(w.z); b.bumpTex = (b.flags & PPG_BSDF_BUMPMAP) ? __float_as_uint(w.w) : 0u; }
     if (FULL && (b.flags & PPG_BSDF_MASK)) { const float4 m = A_.bsdf(PPG_BSDF_F4 * idx + 6); b.opacity = f3(m.x, m.y, m.z); b.maskProb = m.w; }
     if (!FULL) b.flags &= PPG_BSDF_TWOSIDED;
     if (FULL && b.type != PPG_BSDF_T_DIFFUSE) {
@@ -882,6 +891,108 @@ __device__ __forceinline__ float3 bsdf_sample(const Bsdf &b, float3 wi, float sx
     return result;
 }
 
+// ------------------------------------------------------------------ bitmap textures, bump mapping, environment map (full-feature variants only)
+// Not inlined: rare paths that must not cost the main shading code registers.
+__device__ __forceinline__ int tex_wrap(int x, int size, uint32_t mode) {                    // TMIPMap::evalTexel boundary handling, render/mipmap.h:503-563
+    if (x >= 0 && x < size) return x;
+    if (mode == 0u) { const int r = x % size; return r < 0 ? r + size : r; }                 // repeat (math::modulo)
+    if (mode == 1u) return min(max(x, 0), size - 1);                                          // clamp
+    int r = x % (2 * size); if (r < 0) r += 2 * size;                                         // mirror
+    return r >= size ? 2 * size - r - 1 : r;
+}
+__device__ __forceinline__ float3 tex_texel(const uint2 *__restrict__ base, int W, int H, uint32_t wu, uint32_t wv, int x, int y) {
+    x = tex_wrap(x, W, wu); y = tex_wrap(y, H, wv);
+    const uint2 t = __ldg(&base[(size_t) y * (size_t) W + (size_t) x]);
+    return f3(__half2float(__ushort_as_half((unsigned short) (t.x & 0xffffu))), __half2float(__ushort_as_half((unsigned short) (t.x >> 16))),
+              __half2float(__ushort_as_half((unsigned short) (t.y & 0xffffu))));
+}
+// TMIPMap::evalBilinear(0, uv), render/mipmap.h:575-596 (same operation order as the oracle: ((texel * wx) * wy), summed left to right)
+__device__ __forceinline__ float3 tex_bilinear(const uint2 *__restrict__ base, int W, int H, uint32_t wu, uint32_t wv, float uu, float vv) {
+    if (!isfinite(uu) || !isfinite(vv)) return f3(0, 0, 0);
+    const float u = uu * (float) W - 0.5f, v = vv * (float) H - 0.5f;
+    const int xPos = (int) floorf(u), yPos = (int) floorf(v);
+    const float dx1 = u - (float) xPos, dx2 = 1.0f - dx1, dy1 = v - (float) yPos, dy2 = 1.0f - dy1;
+    float3 r = tex_texel(base, W, H, wu, wv, xPos, yPos) * dx2 * dy2;
+    r = r + tex_texel(base, W, H, wu, wv, xPos, yPos + 1) * dx2 * dy1;
+    r = r + tex_texel(base, W, H, wu, wv, xPos + 1, yPos) * dx1 * dy2;
+    r = r + tex_texel(base, W, H, wu, wv, xPos + 1, yPos + 1) * dx1 * dy1;
+    return r;
+}
+// Texture2D::eval(its) without UV partials (librender/texture.cpp:112-121) -> BitmapTexture::eval(uv) (textures/bitmap.cpp:431-453)
+static __device__ __noinline__ float3 tex_eval(const SceneView &sc, uint32_t idx, float2 uv) {
+    const float4 m0 = __ldg(&sc.texMeta[2 * idx]), m1 = __ldg(&sc.texMeta[2 * idx + 1]);
+    const uint32_t wr = __float_as_uint(m0.z);
+    return tex_bilinear(sc.texels + __float_as_uint(m0.w), (int) __float_as_uint(m0.x), (int) __float_as_uint(m0.y), wr & 0xffu, wr >> 8, uv.x * m1.x + m1.z, uv.y * m1.y + m1.w);
+}
+// Texture2D::evalGradient(its) (texture.cpp:123-130) -> evalGradientBilinear (mipmap.h:601-626), reduced to the luminances BumpMap::getFrame uses
+static __device__ __noinline__ float2 tex_gradient_lum(const SceneView &sc, uint32_t idx, float2 uv) {
+    const float4 m0 = __ldg(&sc.texMeta[2 * idx]), m1 = __ldg(&sc.texMeta[2 * idx + 1]);
+    const uint32_t wr = __float_as_uint(m0.z), wu = wr & 0xffu, wv = wr >> 8;
+    const int W = (int) __float_as_uint(m0.x), H = (int) __float_as_uint(m0.y);
+    const uint2 *base = sc.texels + __float_as_uint(m0.w);
+    const float uu = uv.x * m1.x + m1.z, vv = uv.y * m1.y + m1.w;
+    float3 g0 = f3(0, 0, 0), g1 = f3(0, 0, 0);
+    if (isfinite(uu) && isfinite(vv)) {
+        const float u = uu * (float) W - 0.5f, v = vv * (float) H - 0.5f;
+        const int xPos = (int) floorf(u), yPos = (int) floorf(v);
+        const float dx = u - (float) xPos, dy = v - (float) yPos;
+        const float3 p00 = tex_texel(base, W, H, wu, wv, xPos, yPos), p10 = tex_texel(base, W, H, wu, wv, xPos + 1, yPos),
+                     p01 = tex_texel(base, W, H, wu, wv, xPos, yPos + 1), p11 = tex_texel(base, W, H, wu, wv, xPos + 1, yPos + 1);
+        const float3 tmp = p01 + p10 - p11;
+        g0 = (p10 + p00 * (dy - 1.f) - tmp * dy) * (float) W;
+        g1 = (p01 + p00 * (dx - 1.f) - tmp * dx) * (float) H;
+    }
+    g0 = g0 * m1.x; g1 = g1 * m1.y;
+    return make_float2(g0.x * 0.212671f + g0.y * 0.715160f + g0.z * 0.072169f, g1.x * 0.212671f + g1.y * 0.715160f + g1.z * 0.072169f);
+}
+// EnvironmentMap::evalEnvironment without ray differentials (src/emitters/envmap.cpp:380-410): u repeats, v clamps (:176-178)
+static __device__ __noinline__ float3 env_eval(const SceneView &sc, float3 d) {
+    const float3 v = f3(sc.worldToEnv[0] * d.x + sc.worldToEnv[1] * d.y + sc.worldToEnv[2] * d.z, sc.worldToEnv[3] * d.x + sc.worldToEnv[4] * d.y + sc.worldToEnv[5] * d.z,
+                        sc.worldToEnv[6] * d.x + sc.worldToEnv[7] * d.y + sc.worldToEnv[8] * d.z);
+    const float uu = atan2f(v.x, -v.z) * 0.15915494309189533577f;                     // INV_TWOPI
+    const float vv = acosf(fminf(1.0f, fmaxf(-1.0f, v.y))) * PPG_INV_PI;               // math::safe_acos * INV_PI
+    return tex_bilinear(sc.envTexels, (int) sc.envW, (int) sc.envH, 0u, 1u, uu, vv) * sc.envScale;
+}
+__device__ __forceinline__ void coordinate_system(float3 a, float3 &b, float3 &c);
+// Texture coordinates of a triangle hit (skdtree.h:398-405), the textured BSDF parameters there, and BumpMap::getFrame (src/bsdfs/bumpmap.cpp:139-159)
+// with the per-triangle UV tangents of TriMesh::computeUVTangents (src/librender/trimesh.cpp:683-743).  With a bump map the shading frame of `its`
+// is REPLACED by the perturbed one: the wrapper (bumpmap.cpp:161-236) evaluates the nested model there on the same world-space directions; what the
+// integrator and the wrapper still need of the original frame is its normal (the caller keeps it): cos(theta) signs for the strict-normal tests
+// (GP:1929-1932, 2028-2032) and for the wrapper's own `cosTheta(wo) * cosTheta(perturbed wo) <= 0` rejection.
+template <class Acc>
+__device__ __noinline__ void apply_textures(const Acc &A_, const Hit &h, float3 rayD, Its &its, Bsdf &b) {
+    const float4 g0 = A_.geom(6 * h.tri), g1 = A_.geom(6 * h.tri + 1), g2 = A_.geom(6 * h.tri + 2);
+    const float4 h0 = A_.geom(6 * h.tri + 3), h1 = A_.geom(6 * h.tri + 4), h2 = A_.geom(6 * h.tri + 5);
+    const bool hasUv = A_.meta(h.tri).z & 2;
+    const float3 bc = f3(1 - h.u - h.v, h.u, h.v);
+    float2 uv;
+    if (hasUv) { uv.x = h0.z * bc.x + h1.z * bc.y + h2.z * bc.z; uv.y = h0.w * bc.x + h1.w * bc.y + h2.w * bc.z; }
+    else { uv.x = bc.y; uv.y = bc.z; }
+    if (b.reflTex) b.refl = tex_eval(A_.g, b.reflTex - 1u, uv);
+    if (b.bumpTex) {
+        const float2 grad = tex_gradient_lum(A_.g, b.bumpTex - 1u, uv);
+        const float3 dP1 = f3(g1.x - g0.x, g1.y - g0.y, g1.z - g0.z), dP2 = f3(g2.x - g0.x, g2.y - g0.y, g2.z - g0.z);
+        float3 dpdu0 = dP1, dpdv0 = dP2;
+        if (hasUv) {
+            const float du1 = h1.z - h0.z, dv1 = h1.w - h0.w, du2 = h2.z - h0.z, dv2 = h2.w - h0.w;
+            const float3 n = cross(dP1, dP2); const float len = sqrtf(dot(n, n));
+            if (len == 0.f) dpdu0 = dpdv0 = f3(0, 0, 0);
+            else {
+                const float determinant = du1 * dv2 - dv1 * du2;
+                if (determinant == 0.f) coordinate_system(n * (1.0f / len), dpdu0, dpdv0);
+                else { const float invDet = 1.0f / determinant; dpdu0 = (dP1 * dv2 - dP2 * dv1) * invDet; dpdv0 = (dP1 * (-du2) + dP2 * du1) * invDet; }
+            }
+        }
+        const float3 dpdu = dpdu0 + its.shN * (grad.x - dot(its.shN, dpdu0)), dpdv = dpdv0 + its.shN * (grad.y - dot(its.shN, dpdv0));
+        float3 n = normalize(cross(dpdu, dpdv));
+        its.shS = normalize(dpdu - n * dot(n, dpdu));
+        its.shT = cross(n, its.shS);
+        if (dot(n, its.geoN) < 0.f) n = n * -1.0f;
+        its.shN = n;
+        its.wi = its.toLocal(-rayD);
+    }
+}
+
 // ------------------------------------------------------------------ SD-tree views
 // S-tree node: uint2 {child0, child1}; child0 == 0 marks a leaf (node 0 is the root, never a child; GP:844).
 // Axis cycles x,y,z with depth (root 0, children (axis+1)%3, GP:889), so it is not stored.
@@ -1192,7 +1303,8 @@ __device__ __noinline__ float3 look_through(const Acc &A_, float3 o, float3 d, c
         if (surface) { fill_its<true>(A_, h, ro, d, cur); curT = h.t; }
         if (++interactions > 100) return f3(0, 0, 0);
     }
-    if (!surface || cur.emitter < 0) return f3(0, 0, 0);
+    if (!surface) return A_.g.envW ? transmittance * env_eval(A_.g, d) : f3(0, 0, 0);      // "perhaps there is an environment map?" (GP:2228-2243)
+    if (cur.emitter < 0) return f3(0, 0, 0);
     qEmitter = cur.emitter; qN = cur.shN; qDist = curT;
     if (!(dot(cur.shN, -d) > 0.f)) return f3(0, 0, 0);
     const float4 r = A_.radiance(cur.emitter);

@@ -261,7 +261,7 @@ struct ppg_integrator {
 
     // scene
     bool haveScene = false;
-    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom, dSpheres; DevBuf<float> dEmitterCdf, dEmitterTriCdf, dBsdfTables; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
+    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom, dSpheres, dTexMeta; DevBuf<uint2> dTexels, dEnvTexels; DevBuf<float> dEmitterCdf, dEmitterTriCdf, dBsdfTables; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
@@ -426,7 +426,25 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
             return fail(PPG_ERR_INVALID_ARGUMENT, "roughplastic needs its rough-transmittance table (ppg_scene_desc.bsdf_tables)");
         if ((t == PPG_BSDF_DIELECTRIC || t == PPG_BSDF_ROUGHDIELECTRIC || t == PPG_BSDF_THINDIELECTRIC) && !(s->bsdfs[i].eta[0] > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "dielectric needs eta > 0");
         if ((t == PPG_BSDF_DIELECTRIC || t == PPG_BSDF_ROUGHDIELECTRIC || t == PPG_BSDF_THINDIELECTRIC) && (s->bsdfs[i].flags & PPG_BSDF_FLAG_TWOSIDED)) return fail(PPG_ERR_INVALID_ARGUMENT, "twosided cannot wrap a transmissive BSDF (twosided.cpp)");
+        if (s->bsdfs[i].reflectance_texture > s->n_textures || s->bsdfs[i].bump_texture > s->n_textures) return fail(PPG_ERR_INVALID_ARGUMENT, "BSDF texture index out of range");
+        if (s->bsdfs[i].reflectance_texture && t != PPG_BSDF_DIFFUSE && t != PPG_BSDF_ROUGHPLASTIC && t != PPG_BSDF_PLASTIC)
+            return fail(PPG_ERR_UNSUPPORTED, "reflectance_texture: only the diffuse reflectance of diffuse / roughplastic / plastic can be textured");
+        if ((s->bsdfs[i].flags & PPG_BSDF_FLAG_BUMPMAP) && !s->bsdfs[i].bump_texture) return fail(PPG_ERR_INVALID_ARGUMENT, "bumpmap: A displacement texture must be specified");
     }
+    if (s->n_textures && (!s->textures || !s->texels)) return fail(PPG_ERR_INVALID_ARGUMENT, "textures without texel data");
+    for (uint32_t i = 0; i < s->n_textures; ++i) {
+        const ppg_texture &t = s->textures[i];
+        if (!t.width || !t.height || (t.channels != 1 && t.channels != 3) || t.wrap_u > 2 || t.wrap_v > 2) return fail(PPG_ERR_INVALID_ARGUMENT, "texture: bad size, channel count or wrap mode");
+        if (t.first_texel + (uint64_t) t.width * t.height * t.channels > s->n_texels) return fail(PPG_ERR_INVALID_ARGUMENT, "texture: texel range out of bounds");
+    }
+    for (uint32_t k = 0; k < s->n_spheres; ++k)       // spheres carry no texture coordinates here
+        if (s->spheres[k].shape >= 0 && (uint32_t) s->spheres[k].shape < s->n_shapes) {
+            const ppg_bsdf &b = s->bsdfs[s->shapes[s->spheres[k].shape].bsdf];
+            if (b.reflectance_texture || (b.flags & PPG_BSDF_FLAG_BUMPMAP)) return fail(PPG_ERR_UNSUPPORTED, "textured / bump-mapped BSDF on an analytic sphere");
+        }
+    const bool haveEnv = s->envmap.width && s->envmap.height;
+    if (haveEnv && !s->envmap.texels) return fail(PPG_ERR_INVALID_ARGUMENT, "envmap without texel data");
+    if (haveEnv && h->prm.nee != PPG_NEE_NEVER) return fail(PPG_ERR_UNSUPPORTED, "nee != never with an environment emitter (environment light sampling is not built)");
     auto P = [&](uint32_t i) { return h3(s->positions[3 * i], s->positions[3 * i + 1], s->positions[3 * i + 2]); };
     std::vector<H3> tmin(nt), tmax(nt);
     for (uint32_t t = 0; t < nt; ++t) {
@@ -499,11 +517,12 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         }
         const ppg_shape &sh = s->shapes[s->triangle_shape[t]];
         meta[4 * (size_t) slot] = sh.bsdf; meta[4 * (size_t) slot + 1] = sh.emitter;
-        meta[4 * (size_t) slot + 2] = (sh.has_normals && s->normals) ? 1 : 0; meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
+        meta[4 * (size_t) slot + 2] = ((sh.has_normals && s->normals) ? 1 : 0) | ((sh.has_uvs && s->uvs) ? 2 : 0); meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
     }
     h->fullFeature = false;
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) if ((s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) || (s->bsdfs[i].flags & ~PPG_BSDF_FLAG_TWOSIDED)) h->fullFeature = true;   // any non-diffuse model or wrapper other than twosided
     if (s->n_spheres) h->fullFeature = true;                                            // ... or analytic spheres: the full-feature kernel variants
+    if (s->n_textures || haveEnv) h->fullFeature = true;                                // ... or textures / an environment emitter
     std::vector<float> bsdf(4 * PPG_BSDF_F4 * (size_t) s->n_bsdfs, 0.f);
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) {
         float *b = &bsdf[4 * PPG_BSDF_F4 * (size_t) i]; const ppg_bsdf &m = s->bsdfs[i];
@@ -517,6 +536,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         b[15] = std::max(m.alpha, 1e-4f) * (m.distribution == PPG_MICROFACET_BECKMANN ? -1.0f : 1.0f);   // microfacet.h:63 clamp; sign encodes the distribution
         b[16] = m.specular_reflectance[0]; b[17] = m.specular_reflectance[1]; b[18] = m.specular_reflectance[2]; b[19] = m.fdr_int;
         b[20] = m.specular_sampling_weight; const uint32_t tab = (uint32_t) std::max(m.table, 0); memcpy(&b[21], &tab, 4);
+        memcpy(&b[22], &m.reflectance_texture, 4); memcpy(&b[23], &m.bump_texture, 4);
         b[24] = m.opacity[0]; b[25] = m.opacity[1]; b[26] = m.opacity[2];
         b[27] = m.opacity[0] * 0.212671f + m.opacity[1] * 0.715160f + m.opacity[2] * 0.072169f;                // getLuminance (spectrum.h:725-727)
     }
@@ -610,6 +630,42 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         CK(h->dSpheres.alloc(sph.size() / 4));
         CK(cudaMemcpy(h->dSpheres.p, sph.data(), sph.size() * 4, cudaMemcpyHostToDevice));
         v.spheres = h->dSpheres.p; v.nSpheres = s->n_spheres;
+    }
+    {   // bitmap textures and the environment map: half texels repacked to one uint2 {r | g << 16, b} per texel
+        auto pack = [](const uint16_t *src, size_t nTexels, uint32_t channels, uint2 *dst) {
+            for (size_t i = 0; i < nTexels; ++i) {
+                const uint16_t r = src[i * channels], g = channels == 3 ? src[i * channels + 1] : r, b = channels == 3 ? src[i * channels + 2] : r;
+                dst[i] = make_uint2((uint32_t) r | ((uint32_t) g << 16), (uint32_t) b);
+            }
+        };
+        size_t total = 0;
+        for (uint32_t i = 0; i < s->n_textures; ++i) total += (size_t) s->textures[i].width * s->textures[i].height;
+        if (total >= (1ull << 32)) return fail(PPG_ERR_UNSUPPORTED, "more than 2^32 texels");
+        std::vector<uint2> tex(std::max<size_t>(total, 1)); std::vector<float> tmeta(8 * (size_t) std::max<uint32_t>(s->n_textures, 1), 0.f);
+        size_t off = 0;
+        for (uint32_t i = 0; i < s->n_textures; ++i) {
+            const ppg_texture &t = s->textures[i];
+            pack(s->texels + t.first_texel, (size_t) t.width * t.height, t.channels, tex.data() + off);
+            float *m = &tmeta[8 * (size_t) i];
+            const uint32_t wr = t.wrap_u | (t.wrap_v << 8), o32 = (uint32_t) off;
+            memcpy(&m[0], &t.width, 4); memcpy(&m[1], &t.height, 4); memcpy(&m[2], &wr, 4); memcpy(&m[3], &o32, 4);
+            m[4] = t.uv_scale[0]; m[5] = t.uv_scale[1]; m[6] = t.uv_offset[0]; m[7] = t.uv_offset[1];
+            off += (size_t) t.width * t.height;
+        }
+        CK(h->dTexels.alloc(tex.size())); CK(h->dTexMeta.alloc(tmeta.size() / 4));
+        CK(cudaMemcpy(h->dTexels.p, tex.data(), tex.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->dTexMeta.p, tmeta.data(), tmeta.size() * 4, cudaMemcpyHostToDevice));
+        v.texMeta = h->dTexMeta.p; v.texels = h->dTexels.p; v.nTextures = s->n_textures;
+        v.envW = v.envH = 0; v.envScale = 1.f; v.envTexels = nullptr;
+        for (int i = 0; i < 9; ++i) v.worldToEnv[i] = (i % 4 == 0) ? 1.f : 0.f;
+        if (haveEnv) {
+            std::vector<uint2> env((size_t) s->envmap.width * s->envmap.height);
+            pack(s->envmap.texels, env.size(), 3, env.data());
+            CK(h->dEnvTexels.alloc(env.size()));
+            CK(cudaMemcpy(h->dEnvTexels.p, env.data(), env.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+            v.envTexels = h->dEnvTexels.p; v.envW = s->envmap.width; v.envH = s->envmap.height; v.envScale = s->envmap.scale;
+            for (int i = 0; i < 9; ++i) v.worldToEnv[i] = s->envmap.world_to_env[i];
+        }
     }
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
     const size_t sceneBytes = 16 * ((size_t) 3 * nt + 6 * nt + nt + 2 * nBvh + PPG_BSDF_F4 * s->n_bsdfs + v.nEmitters + 2 * std::max<uint32_t>(v.nGroups, 1));
@@ -844,13 +900,9 @@ static int ensure_wavefront(ppg_integrator *h) {
     CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dWork.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
-    if (h->sceneSmemBytes) {
-        if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, true, false>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, true, true>, PPG_BOUNCE_BLOCK, h->sceneSmemBytes));
-    } else {
-        if (!h->fullFeature) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 1, false, false, false>, PPG_BOUNCE_BLOCK_HBM, 0));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, 2, true, false, true>, PPG_BOUNCE_BLOCK_HBM, 0));
-    }
+    if (h->sceneSmemBytes) occ = h->fullFeature ? ppg_bounce_occupancy_11(h->sceneSmemBytes) : ppg_bounce_occupancy_10(h->sceneSmemBytes);
+    else occ = h->fullFeature ? ppg_bounce_occupancy_01(0) : ppg_bounce_occupancy_00(0);
+    CK(cudaGetLastError());
     // one block per resident slot; warps claim their work dynamically (bounce_kernel)
     h->gridBounce = h->numSMs * std::max(occ, 1) * std::max(env_int("PPG_GRID_MULT", 1), 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
@@ -873,26 +925,12 @@ static VertexSlab slab_at(ppg_integrator *h, int k, int set = 0) {
     return s;
 }
 
-template <class K> static void carveout(K kernel) {
-    static const int pct = env_int("PPG_SMEM_CARVEOUT", -1);
-    if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-}
-template <bool FIRST, bool SMEM, bool FULL> static void launch_bounce3(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
-    const size_t sm = P.sceneSmemBytes;
-    carveout(bounce_kernel<FIRST, 0, true, SMEM, FULL>); carveout(bounce_kernel<FIRST, 2, true, SMEM, FULL>); carveout(bounce_kernel<FIRST, 0, false, SMEM, FULL>);
-    carveout(bounce_kernel<FIRST, 1, false, SMEM, FULL>); carveout(bounce_kernel<FIRST, 2, false, SMEM, FULL>);
-    if (nee) {      // next event estimation always runs with full records
-        if (record == 0) bounce_kernel<FIRST, 0, true, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
-        else bounce_kernel<FIRST, 2, true, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
-    } else if (record == 0) bounce_kernel<FIRST, 0, false, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
-    else if (record == 1) bounce_kernel<FIRST, 1, false, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
-    else bounce_kernel<FIRST, 2, false, SMEM, FULL><<<grid, SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, sm, h->stream>>>(P);
+static void launch_bounce(ppg_integrator *h, const RenderParams &P, bool first, int record, int grid, bool nee) {
+    // scene staged in shared memory or read from HBM; lean instantiations for diffuse-only triangle scenes
+    const BounceLaunch L{h->stream, grid, record, nee ? 1 : 0, first ? 1 : 0};
+    if (P.sceneSmemBytes) { if (h->fullFeature) ppg_launch_bounce_11(P, L); else ppg_launch_bounce_10(P, L); }
+    else { if (h->fullFeature) ppg_launch_bounce_01(P, L); else ppg_launch_bounce_00(P, L); }
     h->launches++;
-}
-template <bool FIRST> static void launch_bounce(ppg_integrator *h, const RenderParams &P, int record, int grid, bool nee) {
-    // scene staged in shared memory or read from HBM; lean instantiation for scenes without delta BSDFs
-    if (P.sceneSmemBytes) { if (h->fullFeature) launch_bounce3<FIRST, true, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, true, false>(h, P, record, grid, nee); }
-    else { if (h->fullFeature) launch_bounce3<FIRST, false, true>(h, P, record, grid, nee); else launch_bounce3<FIRST, false, false>(h, P, record, grid, nee); }
 }
 
 // one batch of `nPasses` passes as a single wavefront
@@ -926,7 +964,7 @@ static int render_batch(ppg_integrator *h, int nPasses, uint32_t pixel0, uint32_
         if (nee) { P.neeSlab = slab_at(h, k, 1); P.prevSlab = slab_at(h, std::max(k - 1, 0)); if (depth - 1 >= h->nSlabs) P.prevSlab = slab_at(h, h->nSlabs - 1); }
         const int rec = (depth - 1 < h->nSlabs) ? record : 0;
         h->tic(PPG_K_BOUNCE);
-        if (depth == 1) launch_bounce<true>(h, P, rec, grid, nee); else launch_bounce<false>(h, P, rec, grid, nee);
+        launch_bounce(h, P, depth == 1, rec, grid, nee);
         h->toc();
         lastDepth = depth;
     }

@@ -1,372 +1,9 @@
-// ppg_kernels.cuh -- the wavefront kernels of the guided path tracer (sm_100a).
-//
-// One pass-batch of N paths is processed as
-//     bounce<FIRST>  (ray generation + bounce 1)          GP:1613-1637 + one turn of the Li loop
-//     bounce         (one launch per further path depth)  GP:1798-2146
-//     commit         (all recorded vertices -> building trees)   GP:2150-2154 -> 1730-1768 -> 575-584
-//     film           (per-pixel sum and sum of squares)   GP:1633-1634, imageblock.h:127-186
-// Live paths are compacted between bounces (warp ballot + prefix popcount + one atomic per warp),
-// path state is SoA float4 (5 x 16 B per path, coalesced), the scene (CBOX: ~9 KB) is staged in
-// shared memory, the read-only sampling trees go through the read-only/L1 path.
+// ppg_kernels.cuh -- the non-bounce kernels of the wavefront pipeline (flush, commit, film, SD-tree maintenance, Adam replay).
+// Included by ppg_host.cu only; the structures shared with the bounce kernel live in ppg_wavefront.cuh.
 #pragma once
-#include "ppg_device.cuh"
+#include "ppg_wavefront.cuh"
 
 namespace ppg {
-
-#ifndef PPG_BLOCK
-#define PPG_BLOCK 256
-#endif
-#ifndef PPG_BOUNCE_BLOCK
-#define PPG_BOUNCE_BLOCK 1024          // threads per block of the bounce kernel: one block per SM stages the scene once (measured 256x4 -> 5589, 512x2 -> 5643,
-#endif                                 // 1024x1 -> 5676 Msamples/s on CBOX 1024^2)
-#ifndef PPG_BOUNCE_BLOCK_HBM
-#define PPG_BOUNCE_BLOCK_HBM 256       // scenes that do not fit shared memory (nothing to stage) keep 256 x 4: SPACESHIP 485 vs 450 Msamples/s of bounce-kernel time,
-#endif                                 // 269 vs 232 with the kl loss; the staged CBOX variants gain 1-4 % from 1024 x 1
-#ifndef PPG_MIN_BLOCKS
-#define PPG_MIN_BLOCKS 1               // resident blocks per SM the bounce kernel is compiled for: 1024 threads x 64 registers = the whole register file
-#endif
-#ifndef PPG_CLAIM
-#define PPG_CLAIM 1u                   // groups of 32 paths a warp claims per atomic (measured on CBOX 1024^2: 1 -> 5585, 4 -> 5385, 16 -> 4819 Msamples/s:
-                                       // running warps then sweep ONE contiguous window of the SoA path state)
-#endif
-#ifndef PPG_MIN_BLOCKS_HBM
-#define PPG_MIN_BLOCKS_HBM 4           // 64 registers as well (beat 80 and 128 on the rough CBOX variants)
-#endif
-#define PPG_MAX_VERTICES 32         // MAX_NUM_VERTICES, GP:1771
-#define PPG_INVALID 0xFFFFFFFFu
-
-// ------------------------------------------------------------------ SoA buffers
-struct PathState {      // 5 x float4 per path
-    float4 *s0;         // o.xyz, d.x
-    float4 *s1;         // d.yz, throughput.xy
-    float4 *s2;         // throughput.z, eta, Li.xy
-    float4 *s3;         // Li.z, bits(pathId), bits(rng.lo), bits(rng.hi)
-    float4 *s4;         // bits(sampleIndex.lo), bits(sampleIndex.hi), bits(nVertices | flags<<8), rrRecip
-    float4 *s5;         // NEE only: woPdf of the last sampled direction, refN.xyz of the vertex it left (GP:2084-2087)
-    float4 *s6;         // NEE only: bits(slab slot of the last vertex | isDelta<<31 | hasVertex<<30), 0, 0, 0
-};
-#define PPG_FLAG_NULL 2u             // the ray arrived through an index-matched (ENull) transition: plain intersection, no emitter lookup / MIS (GP:2070-2074)
-#define PPG_FLAG_UNSCATTERED 4u      // `scattered` is still false (camera ray that has only crossed null surfaces so far)
-#define PPG_FLAG_DYING 1u            // lost Russian roulette: trace one more ray for the emitter lookup, then stop (GP:2078-2091 precede GP:2123-2142)
-
-struct VertexSlab {     // one slab per path depth; entry i belongs to the i-th live path of that bounce
-    float4 *v0;         // d.xyz, woPdf
-    float4 *v1;         // throughput.xyz, bits(leafNode)
-    float4 *v2;         // LiPrefix.xyz, bits(pathId | isDelta<<31)   (pathId == PPG_INVALID: no vertex)
-    float4 *v3;         // bsdfVal.xyz, bsdfPdf                       (full mode only)
-    float4 *v4;         // o.xyz, dTreePdf                            (full mode only)
-    float4 *v5;         // bits(sampleIndex.lo), bits(sampleIndex.hi), bits(streeLevels | ordinal<<8), 0   (full mode only)
-};
-
-struct RenderParams {
-    SceneView scene; Camera cam; TreeView tree;
-    PathState in, out;
-    VertexSlab slab;               // slab of the CURRENT depth (already offset by the host)
-    float4 *liFinal;               // per path: Li.rgb, 1
-    const uint32_t *pixelMap;      // local pixel -> x | y<<16
-    const uint32_t *liveIn; uint32_t *liveOut;      // device counters
-    uint32_t *work;                                 // dynamic scheduling: next unclaimed input index of this launch (zeroed by the host), or nullptr
-    unsigned long long *counters;  // [0]: rays traced, [1]: vertices recorded, [2]: sum of S-tree levels over recorded vertices
-    uint32_t nPaths;               // paths of this batch (FIRST kernel)
-    uint32_t nLocalPixels, spp;
-    uint64_t passBase;             // global index of the first pass in the batch
-    uint64_t seed;
-    int depth;                     // rRec.depth of this bounce (1 = primary hit)
-    int maxDepth, rrDepth;
-    int strictNormals, hideEmitters;
-    int isBuilt;                   // m_isBuilt: guide with the sampling trees
-    int lossMode;                  // bsdfSamplingFractionLoss
-    float fixedFraction;           // bsdfSamplingFraction
-    uint32_t sceneSmemBytes;       // >0: stage the scene into shared memory
-    int neeMode, doNee;            // m_nee, m_doNee (GP:1331-1340)
-    int training;                  // vertex records are being written in this iteration (the last bounce kernel itself runs with RECORD == 0)
-    VertexSlab neeSlab;            // half-weight vertices of the sampled light directions (GP:1999-2016), slab of the current depth
-    VertexSlab prevSlab;           // slab of depth-1 (nee == always: the vertex's radiance excludes the emitter hit that follows it, GP:2101)
-};
-
-// warp-wide compaction: returns the output slot of this lane (valid when `alive`); one atomic per warp and
-// no block barrier, so warps of a block never wait for each other inside the path loop.
-__device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) {
-    const unsigned ballot = __ballot_sync(0xffffffffu, alive);
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0 && ballot) base = atomicAdd(counter, (uint32_t) __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    return base + __popc(ballot & ((1u << lane) - 1u));
-}
-
-// ------------------------------------------------------------------ the bounce kernel
-// FIRST: generate the camera ray (renderBlock, GP:1613-1632) instead of loading a path state.
-// RECORD: 0 = no vertex records (final iteration), 1 = basic record (nearest spatial filter, no loss),
-//         2 = full record (stochastic/box spatial filter or a sampling-fraction loss).
-template <bool FIRST, int RECORD, bool NEE, bool SMEM, bool FULL>
-__global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM, SMEM ? PPG_MIN_BLOCKS : PPG_MIN_BLOCKS_HBM) bounce_kernel(const RenderParams P) {
-    const SceneAccess<SMEM> sc(P.scene);
-    sc.stage();
-    const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
-    unsigned long long raysLocal = 0, recLocal = 0, levelsLocal = 0;
-
-    // Work distribution: every warp claims PPG_CLAIM consecutive groups of 32 paths at a time from a launch-wide counter, so exactly one
-    // block per resident slot is launched (the scene is staged once per slot) and the tail still balances.  No block barrier in the loop.
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t claimBase = 0, claimLeft = 0;
-    for (;;) {
-        if (claimLeft == 0) {
-            if (lane == 0) claimBase = atomicAdd(P.work, 32u * PPG_CLAIM);
-            claimBase = __shfl_sync(0xffffffffu, claimBase, 0);
-            claimLeft = PPG_CLAIM;
-        }
-        if (claimBase >= nIn) break;
-        const uint32_t i = claimBase + lane;
-        claimBase += 32u; --claimLeft;
-        bool alive = i < nIn;
-        float3 o, d, thr, Li; float eta = 1.f, rrRecip = 1.f, mint, maxt;
-        float prevWoPdf = 0.f; float3 prevRefN = f3(0, 0, 0); uint32_t prevSlot = 0;      // NEE only
-        uint32_t pathId = 0, nVertices = 0, flags = 0; uint64_t sampleIndex = 0;
-        Pcg32 rng; rng.state = 0; rng.inc = 1;
-        if (alive) {
-            if (FIRST) {
-                pathId = i;
-                const uint32_t perPass = P.nLocalPixels * P.spp;
-                const uint32_t passInBatch = i / perPass, rem = i - passInBatch * perPass;
-                const uint32_t lp = rem / P.spp, s = rem - lp * P.spp;
-                const uint32_t xy = __ldg(&P.pixelMap[lp]);
-                const uint32_t x = xy & 0xffffu, y = xy >> 16;
-                sampleIndex = (((P.passBase + passInBatch) * (uint64_t) P.cam.H + y) * (uint64_t) P.cam.W + x) * P.spp + s;
-                seed_path_rng(rng, P.seed, sampleIndex);
-                const float jx = rng.next1D(), jy = rng.next1D();                 // samplePos = pixel + next2D (GP:1620)
-                const float sx = ((float) x + jx) * (1.0f / (float) P.cam.W), sy = ((float) y + jy) * (1.0f / (float) P.cam.H);
-                const float3 nearP = f3((1.0f - 2.0f * sx) * P.cam.tanX, (1.0f - 2.0f * sy) * P.cam.tanY, 1.0f);
-                const float3 dl = normalize(nearP);
-                const float invZ = 1.0f / dl.z;
-                mint = P.cam.nearClip * invZ; maxt = P.cam.farClip * invZ;
-                o = P.cam.o;
-                d = P.cam.left * dl.x + P.cam.up * dl.y + P.cam.dir * dl.z;
-                thr = f3(1, 1, 1); Li = f3(0, 0, 0);
-            } else {
-                const float4 a = P.in.s0[i], b = P.in.s1[i], c = P.in.s2[i], e = P.in.s3[i], f = P.in.s4[i];
-                o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y); thr = f3(b.z, b.w, c.x); eta = c.y; Li = f3(c.z, c.w, e.x);
-                pathId = __float_as_uint(e.y);
-                rng.state = ((uint64_t) __float_as_uint(e.w) << 32) | __float_as_uint(e.z);
-                sampleIndex = ((uint64_t) __float_as_uint(f.y) << 32) | __float_as_uint(f.x);
-                rng.inc = (sampleIndex << 1) | 1u;
-                const uint32_t nf = __float_as_uint(f.z); nVertices = nf & 0xffu; flags = nf >> 8;
-                rrRecip = f.w;
-                if (NEE) { const float4 g5 = P.in.s5[i], g6 = P.in.s6[i]; prevWoPdf = g5.x; prevRefN = f3(g5.y, g5.z, g5.w); prevSlot = __float_as_uint(g6.x); }
-                // adaptive ray epsilon of rays leaving a surface (skdtree.cpp:125-128)
-                mint = PPG_EPSILON * fmaxf(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), PPG_EPSILON);
-                maxt = __int_as_float(0x7f800000);
-            }
-        }
-        bool wroteVertex = false, wroteNee = false, unscattered = FIRST;
-        if (alive) {
-            ++raysLocal;
-            Hit hit;
-            const bool found = bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
-            bool cont = found;                                                     // miss: no environment emitter in scope (GP:1902-1914)
-            Its its;
-            if (cont) {
-                fill_its<FULL>(sc, hit, o, d, its);
-                // emitted radiance: primary hit via EEmittedRadiance (GP:1917-1919), later hits via the `value`
-                // returned by rayIntersectAndLookForEmitter (GP:2078-2091; miWeight(woPdf, 0) == 1)
-                float3 Lhit = f3(0, 0, 0);
-                const bool viaNull = FULL && !FIRST && (flags & PPG_FLAG_NULL);
-                unscattered = FIRST || (FULL && (flags & PPG_FLAG_UNSCATTERED));
-                if (FULL && viaNull) {
-                    // after a null transition the hit is an ordinary path vertex: emitted radiance only while ERadiance is still
-                    // requested, i.e. the path has not scattered yet (GP:2070-2071, 1917-1919)
-                    if (its.emitter >= 0 && unscattered && !P.hideEmitters && dot(its.shN, -d) > 0.f) {
-                        const float4 r = sc.radiance(its.emitter);
-                        Li = Li + thr * f3(r.x, r.y, r.z);
-                    }
-                } else if (FULL && !FIRST && its.emitter < 0 && bsdf_has_null(load_bsdf<FULL>(sc, its.bsdf))) {
-                    // first hit on an index-matched surface: the emitter lookup continues behind it (GP:2184-2245)
-                    int qEmitter; float3 qN; float qDist;
-                    const float3 value = look_through(sc, o, d, its, hit.t, P.maxDepth - P.depth, qEmitter, qN, qDist);
-                    if (!is_zero(value)) {
-                        Lhit = thr * value;
-                        if (NEE && P.doNee && !(prevSlot >> 31)) Lhit = Lhit * mi_weight(prevWoPdf, pdf_emitter_direct<FULL>(sc.g, qEmitter, o, prevRefN, d, qN, qDist));
-                        Li = Li + Lhit;
-                    }
-                } else if (its.emitter >= 0 && (!FIRST || !P.hideEmitters)) {
-                    if (dot(its.shN, -d) > 0.f) {                                    // area.cpp:104-109
-                        const float4 r = sc.radiance(its.emitter);
-                        Lhit = thr * f3(r.x, r.y, r.z);
-                        if (NEE && !FIRST && P.doNee && !(prevSlot >> 31)) {            // MIS against light sampling, GP:2084-2088
-                            const float emitterPdf = pdf_emitter_direct<FULL>(sc.g, its.emitter, o, prevRefN, d, its.shN, hit.t);
-                            Lhit = Lhit * mi_weight(prevWoPdf, emitterPdf);
-                        }
-                        Li = Li + Lhit;
-                    }
-                }
-                if (NEE && !FIRST && P.training && P.neeMode == 2 && ((prevSlot >> 30) & 1u)) {
-                    // nee == always: the vertex created at the previous bounce starts with radiance 0 instead of L (GP:2101):
-                    // move its radiance prefix past this emitter hit
-                    const uint32_t ps = prevSlot & 0x3fffffffu;
-                    float4 pv = P.prevSlab.v2[ps]; pv.x = Li.x; pv.y = Li.y; pv.z = Li.z; P.prevSlab.v2[ps] = pv;
-                }
-                thr = thr * rrRecip;                                                // throughput /= successProb happens after L was recorded (GP:2141)
-                if (flags & PPG_FLAG_DYING) cont = false;
-                if (P.depth >= P.maxDepth && P.maxDepth != -1) cont = false;        // GP:1925
-            }
-            if (cont) {
-                const float wiDotGeoN = -dot(its.geoN, d);
-                if (wiDotGeoN * its.wi.z < 0.f && P.strictNormals) cont = false;     // GP:1929-1932
-            }
-            if (cont) {
-                const Bsdf bsdf = load_bsdf<FULL>(sc, its.bsdf);
-                const bool smooth = bsdf_has_smooth(bsdf);                           // only smooth BSDFs are guided (GP:1942-1944)
-                int levels = 0; uint32_t leaf = 0; float4 la = make_float4(0, 0, 0, 0);
-                if (smooth) {
-                    leaf = stree_lookup(P.tree.snodes, P.tree.stable, P.tree.aabbMin, P.tree.extent, its.p, levels);
-                    la = __ldg(&P.tree.leafA[leaf]);
-                }
-                float frac = P.fixedFraction;
-                if (smooth && P.lossMode != 0) frac = logistic(la.z);                 // GP:1946-1949
-                // ---- sampleMat, GP:1650-1691
-                float woPdf, bsdfPdf, dTreePdf, bsEta = 1.f; float3 wo, bsdfWeight; bool isDelta = false, isNull = false;
-                float sx = rng.next1D(); const float sy = rng.next1D();
-                if (!P.isBuilt || !smooth) {                                         // not built / no dTree / all-delta BSDF (GP:1654)
-                    bsdfWeight = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng, isNull);
-                    woPdf = bsdfPdf; dTreePdf = 0.f;
-                } else {
-                    const SampNode *tree = P.tree.samp + __float_as_uint(la.x);
-                    const bool valid = __float_as_uint(la.w) & 1u;
-                    float3 result; bool zero = false, deltaEarly = false;
-                    if (sx < frac) {
-                        sx /= frac;
-                        result = bsdf_sample(bsdf, its.wi, sx, sy, wo, bsEta, isDelta, bsdfPdf, rng, isNull);
-                        if (is_zero(result)) { woPdf = bsdfPdf = dTreePdf = 0.f; zero = true; }
-                        else if (FULL && isDelta) { dTreePdf = 0.f; woPdf = bsdfPdf * frac; result = result * (1.0f / frac); deltaEarly = true; }   // GP:1670-1676
-                        else result = result * bsdfPdf;
-                    } else {
-                        const float2 c2 = dtree_sample(tree, valid, rng);
-                        wo = its.toLocal(canonical_to_dir(c2));
-                        result = bsdf_eval(bsdf, its.wi, wo);
-                    }
-                    if (zero) bsdfWeight = f3(0, 0, 0);
-                    else if (deltaEarly) bsdfWeight = result;
-                    else {   // pdfMat, GP:1693-1710
-                        bsdfPdf = bsdf_pdf(bsdf, its.wi, wo);
-                        if (!isfinite(bsdfPdf)) { woPdf = 0.f; dTreePdf = 0.f; }
-                        else {
-                            dTreePdf = dtree_pdf(tree, valid, dir_to_canonical(its.toWorld(wo)));
-                            woPdf = frac * bsdfPdf + (1.f - frac) * dTreePdf;
-                        }
-                        bsdfWeight = (woPdf == 0.f) ? f3(0, 0, 0) : result * (1.0f / woPdf);
-                    }
-                }
-                const float3 refN = bsdf_has_transmission_or_backside(bsdf) ? f3(0, 0, 0) : its.shN;   // DirectSamplingRecord(its), records.inl:160-164
-                if (NEE && P.doNee && smooth) {                                       // GP:1967-1969
-                    // ---- luminaire sampling, GP:1964-2021
-                    const float ex = rng.next1D(), ey = rng.next1D();
-                    DirectSample ds; float dist;
-                    if (sample_emitter_direct<FULL>(sc, its.p, refN, ex, ey, ds, dist)) {
-                        // Scene::evalTransmittance: shadow ray, epsilon scaled without the clamp (skdtree.cpp:154-158)
-                        const float smint = PPG_EPSILON * fmaxf(fmaxf(fabsf(its.p.x), fabsf(its.p.y)), fabsf(its.p.z));
-                        Hit sh;      // (shadow rays are not path vertices: not counted in the samples metric)
-                        bool visible;
-                        if (FULL) {  // index-matched surfaces attenuate instead of blocking (Scene::evalTransmittance, interactions = maxDepth - depth - 1, GP:1970)
-                            const float3 T = eval_transmittance(sc, its.p, ds.d, dist, P.maxDepth - P.depth - 1);
-                            ds.value = ds.value * T; visible = !is_zero(ds.value);
-                        } else visible = !bvh_intersect<FULL>(sc, its.p, ds.d, smint, dist * (1.f - PPG_SHADOW_EPSILON), sh);
-                        if (visible) {
-                            const float3 dl = its.toLocal(ds.d);
-                            if (!P.strictNormals || dot(its.geoN, ds.d) * dl.z > 0.f) {
-                                const float3 bsdfVal = bsdf_eval(bsdf, its.wi, dl);
-                                float nWoPdf = 0.f, nBsdfPdf = bsdf_pdf(bsdf, its.wi, dl), nDTreePdf = 0.f;
-                                if (!P.isBuilt) nWoPdf = nBsdfPdf;
-                                else if (isfinite(nBsdfPdf)) {
-                                    nDTreePdf = dtree_pdf(P.tree.samp + __float_as_uint(la.x), __float_as_uint(la.w) & 1u, dir_to_canonical(ds.d));
-                                    nWoPdf = frac * nBsdfPdf + (1.f - frac) * nDTreePdf;
-                                }
-                                const float3 L = thr * (ds.value * bsdfVal) * mi_weight(ds.pdf, nWoPdf);
-                                if (RECORD && P.neeMode != 2) {                          // GP:1999-2016: half-weight vertex with a fixed radiance
-                                    const float3 tv = thr * bsdfVal * (1.0f / ds.pdf);
-                                    P.neeSlab.v0[i] = make_float4(ds.d.x, ds.d.y, ds.d.z, ds.pdf);
-                                    P.neeSlab.v1[i] = make_float4(tv.x, tv.y, tv.z, __uint_as_float(leaf));
-                                    P.neeSlab.v2[i] = make_float4(L.x, L.y, L.z, __uint_as_float(pathId | 0x40000000u));   // bit 30: absolute radiance
-                                    P.neeSlab.v3[i] = make_float4(bsdfVal.x, bsdfVal.y, bsdfVal.z, nBsdfPdf);
-                                    P.neeSlab.v4[i] = make_float4(its.p.x, its.p.y, its.p.z, nDTreePdf);
-                                    P.neeSlab.v5[i] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
-                                                                  __uint_as_float((uint32_t) levels | ((32u + (uint32_t) P.depth) << 8)), 0.f);
-                                    wroteNee = true;
-                                }
-                                Li = Li + L;                                             // recordRadiance(L)
-                            }
-                        }
-                    }
-                }
-                if (is_zero(bsdfWeight)) cont = false;                               // GP:2024-2025
-                float3 woW = f3(0, 0, 0);
-                if (cont) {
-                    woW = its.toWorld(wo);
-                    if (dot(its.geoN, woW) * wo.z <= 0.f && P.strictNormals) cont = false;   // GP:2028-2032
-                }
-                if (cont) {
-                    o = its.p; d = woW;
-                    thr = thr * bsdfWeight; eta *= bsEta;
-                    // ---- vertex record (GP:2093-2110); its radiance is Li_final - Li_prefix
-                    if (RECORD && smooth && (!isDelta || P.lossMode != 0) && nVertices < PPG_MAX_VERTICES && (1.f / woPdf > 0.f)) {
-                        P.slab.v0[i] = make_float4(d.x, d.y, d.z, woPdf);
-                        P.slab.v1[i] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(leaf));
-                        P.slab.v2[i] = make_float4(Li.x, Li.y, Li.z, __uint_as_float(pathId | (isDelta ? 0x80000000u : 0u)));
-                        if (RECORD == 2) {
-                            const float3 bv = bsdfWeight * woPdf;
-                            P.slab.v3[i] = make_float4(bv.x, bv.y, bv.z, bsdfPdf);
-                            P.slab.v4[i] = make_float4(o.x, o.y, o.z, dTreePdf);
-                            P.slab.v5[i] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
-                                                       __uint_as_float((uint32_t) levels | (nVertices << 8)), 0.f);
-                        }
-                        wroteVertex = true; ++nVertices; ++recLocal; levelsLocal += levels;
-                    }
-                    if (NEE) { prevWoPdf = woPdf; prevRefN = refN; prevSlot = i | (isDelta ? 0x80000000u : 0u) | ((wroteVertex && !(FULL && isNull)) ? 0x40000000u : 0u); }   // a null vertex starts at radiance 0: nothing to move (GP:2058)
-                    // ---- Russian roulette (GP:2123-2142); the decision takes effect after the next emitter lookup
-                    rrRecip = 1.f; flags = 0;
-                    if (FULL && isNull) flags = PPG_FLAG_NULL | (unscattered ? PPG_FLAG_UNSCATTERED : 0u);   // GP:2044-2075: no roulette, `scattered` unchanged
-                    else if (P.depth >= P.rrDepth) {
-                        float successProb = 1.0f;
-                        if (smooth && !isDelta) {
-                            if (!P.isBuilt) successProb = max3(thr) * eta * eta;
-                            successProb = fmaxf(0.1f, fminf(successProb, 0.99f));
-                        }
-                        if (rng.next1D() >= successProb) flags |= PPG_FLAG_DYING;
-                        else rrRecip = 1.0f / successProb;
-                    }
-                }
-            }
-            if (!cont) {
-                P.liFinal[pathId] = make_float4(Li.x, Li.y, Li.z, 1.f);
-                alive = false;
-            }
-        }
-        if (RECORD && i < nIn && !wroteVertex) P.slab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
-        if (NEE && RECORD && P.neeMode != 2 && i < nIn && !wroteNee) P.neeSlab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
-        const uint32_t slot = warp_compact(alive, P.liveOut);
-        if (alive) {
-            P.out.s0[slot] = make_float4(o.x, o.y, o.z, d.x);
-            P.out.s1[slot] = make_float4(d.y, d.z, thr.x, thr.y);
-            P.out.s2[slot] = make_float4(thr.z, eta, Li.x, Li.y);
-            P.out.s3[slot] = make_float4(Li.z, __uint_as_float(pathId), __uint_as_float((uint32_t) rng.state), __uint_as_float((uint32_t) (rng.state >> 32)));
-            P.out.s4[slot] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
-                                         __uint_as_float(nVertices | (flags << 8)), rrRecip);
-            if (NEE) {
-                P.out.s5[slot] = make_float4(prevWoPdf, prevRefN.x, prevRefN.y, prevRefN.z);
-                P.out.s6[slot] = make_float4(__uint_as_float(prevSlot), 0.f, 0.f, 0.f);
-            }
-        }
-    }
-    // per-warp reduction of the statistics counters
-    for (int off = 16; off; off >>= 1) {
-        raysLocal += __shfl_xor_sync(0xffffffffu, raysLocal, off);
-        recLocal += __shfl_xor_sync(0xffffffffu, recLocal, off);
-        levelsLocal += __shfl_xor_sync(0xffffffffu, levelsLocal, off);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (raysLocal) atomicAdd(&P.counters[0], raysLocal);
-        if (recLocal) { atomicAdd(&P.counters[1], recLocal); atomicAdd(&P.counters[2], levelsLocal); }
-    }
-}
 
 // paths still alive after the last bounce (only possible with maxDepth == -1 and the bounce cap) keep their radiance
 __global__ void __launch_bounds__(PPG_BLOCK) flush_kernel(PathState in, const uint32_t *liveIn, float4 *liFinal) {

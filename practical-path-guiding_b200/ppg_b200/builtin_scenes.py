@@ -214,3 +214,72 @@ def cbox_rough_plastic(cbox: SceneDesc) -> SceneDesc:
     shapes = sc.shapes.copy(); shapes[6, 2] = nb; shapes[7, 2] = nb + 1
     sc.shapes = shapes
     return sc
+
+
+def _half_bits(img):
+    with np.errstate(over="ignore"):
+        return np.ascontiguousarray(img, np.float32).astype(np.float16).view(np.uint16).reshape(-1)
+
+
+def cbox_textured(cbox: SceneDesc, bump=True, env=True, size=64) -> SceneDesc:
+    """CBOX with procedural bitmap textures (no assets): a checker/gradient RGB texture on the floor, ceiling and back wall
+    (meshes without texture coordinates: uv = barycentrics, skdtree.h:404) and on the tall box (given explicit, scaled and
+    offset UVs with `repeat` wrapping), a one-channel bump map on the two boxes (tall box: twosided diffuse with a textured
+    reflectance; short box: rough plastic with a textured diffuseReflectance), and a small lat-long environment map that
+    lights the scene through the open front.  Exercises every texture / bumpmap / envmap code path of the hot loop."""
+    import copy
+    from .scene import (BSDF_FLAG_BUMPMAP, BSDF_FLAG_TWOSIDED, TEXTURE_DTYPE, make_roughplastic)
+    sc = copy.copy(cbox)
+    rng = np.random.default_rng(7)
+    # texture 0: RGB checker with a smooth gradient and a little noise (size x size)
+    y, x = np.mgrid[0:size, 0:size].astype(np.float64) / size
+    chk = ((np.floor(x * 8) + np.floor(y * 8)) % 2)
+    rgb = np.stack([0.15 + 0.7 * chk * x, 0.2 + 0.6 * (1 - chk) * y, 0.25 + 0.5 * (0.5 + 0.5 * np.sin(12 * x) * np.cos(9 * y))], -1)
+    rgb = np.clip(rgb + rng.uniform(-0.03, 0.03, rgb.shape), 0.0, 0.95)
+    # texture 1: luminance bump (smooth bumps), texture 2: RGB stripes with non-square size and clamp / mirror wrapping
+    hgt = 0.5 + 0.5 * np.sin(2 * np.pi * 6 * x) * np.sin(2 * np.pi * 5 * y)
+    w2, h2 = 48, 20
+    yy, xx = np.mgrid[0:h2, 0:w2].astype(np.float64)
+    stripes = np.stack([0.2 + 0.6 * ((xx // 4) % 2), 0.3 + 0.5 * (yy / h2), 0.6 - 0.4 * (xx / w2)], -1)
+    texs = [(rgb, 3, 0, 0, (1.0, 1.0), (0.0, 0.0)), (hgt[..., None] * 4.0, 1, 0, 0, (3.0, 2.0), (0.25, 0.5)), (stripes, 3, 1, 2, (2.5, 1.5), (-0.2, 0.1))]
+    meta = np.zeros(len(texs), TEXTURE_DTYPE); texels = []; off = 0
+    for i, (img, ch, wu, wv, scl, ofs) in enumerate(texs):
+        meta[i] = (img.shape[1], img.shape[0], ch, wu, wv, scl, ofs, 0, off)
+        hb = _half_bits(img); texels.append(hb); off += len(hb)
+    sc.textures = meta; sc.texels = np.concatenate(texels)
+    # materials
+    nb = len(sc.bsdfs); B = _pad_bsdfs(sc.bsdfs)
+    def u32(v): return np.array([v], np.uint32).view(np.float32)
+    floor = _make_bsdf(BSDF_DIFFUSE, 0, rgb.reshape(-1, 3).mean(0)); floor[25:26] = u32(1)
+    wall = _make_bsdf(BSDF_DIFFUSE, BSDF_FLAG_TWOSIDED, stripes.reshape(-1, 3).mean(0)); wall[25:26] = u32(3)
+    tall = _make_bsdf(BSDF_DIFFUSE, BSDF_FLAG_TWOSIDED | (BSDF_FLAG_BUMPMAP if bump else 0), rgb.reshape(-1, 3).mean(0)); tall[25:26] = u32(1); tall[26:27] = u32(2 if bump else 0)
+    tables = [t for t in (sc.bsdf_tables if sc.bsdf_tables is not None else [])]
+    short = make_roughplastic(BSDF_FLAG_TWOSIDED | (BSDF_FLAG_BUMPMAP if bump else 0), stripes.reshape(-1, 3).mean(0), np.ones(3, np.float32), 1.49 / 1.000277, 0.15, 1, False, tables)
+    short[25:26] = u32(3); short[26:27] = u32(2 if bump else 0)
+    sc.bsdf_tables = np.asarray(tables, np.float32).reshape(-1, 100)
+    sc.bsdfs = np.concatenate([B, np.stack([floor, wall, tall, short])]).astype(np.float32)
+    sc.bsdf_names = list(sc.bsdf_names) + ["tex_floor", "tex_wall", "tex_bump_tall", "tex_bump_short"]
+    shapes = sc.shapes.copy()
+    shapes[1, 2] = nb          # floor: textured diffuse, uv = barycentrics
+    shapes[3, 2] = nb + 1      # back wall: stripes (clamp / mirror)
+    shapes[7, 2] = nb + 2      # tall box: explicit UVs below
+    shapes[6, 2] = nb + 3      # short box: rough plastic, barycentric uv
+    # explicit texture coordinates for the tall box: planar projection of its vertices, beyond [0,1] to exercise wrapping
+    first, n = int(shapes[7, 0]), int(shapes[7, 1])
+    vid = np.unique(sc.indices[first:first + n].reshape(-1))
+    uv = sc.uvs.copy()
+    P = sc.positions[vid]
+    uv[vid, 0] = (P[:, 0] + 0.37 * P[:, 2]) / 150.0
+    uv[vid, 1] = (P[:, 1] + 0.21 * P[:, 2]) / 120.0 - 0.3
+    sc.uvs = uv.astype(np.float32)
+    shapes[7, 5] = 1
+    sc.shapes = shapes
+    if env:
+        eh, ew = 16, 32
+        t, p = np.mgrid[0:eh, 0:ew].astype(np.float64)
+        sky = np.stack([0.3 + 0.2 * np.cos(p / ew * 2 * np.pi), 0.4 + 0.0 * t, 0.6 - 0.3 * t / eh], -1) * (t[..., None] < eh / 2 + 2)
+        sky[3, 9] += np.array([60.0, 50.0, 40.0])                 # a small bright "sun" texel
+        ang = np.radians(35.0)
+        rot = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+        sc.envmap = {"texels": _half_bits(sky).reshape(eh, ew, 3), "scale": 1.5, "world_to_env": np.linalg.inv(rot).astype(np.float32)}
+    return sc

@@ -33,7 +33,17 @@ class PpgParams(C.Structure):
 class PpgBsdf(C.Structure):
     _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("reflectance", C.c_float * 3), ("specular_transmittance", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3), ("alpha", C.c_float), ("distribution", C.c_int32),
-                ("specular_reflectance", C.c_float * 3), ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("table", C.c_int32), ("opacity", C.c_float * 3), ("reserved", C.c_float * 3)]
+                ("specular_reflectance", C.c_float * 3), ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("table", C.c_int32), ("opacity", C.c_float * 3),
+                ("reflectance_texture", C.c_uint32), ("bump_texture", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class PpgTexture(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32), ("wrap_u", C.c_uint32), ("wrap_v", C.c_uint32),
+                ("uv_scale", C.c_float * 2), ("uv_offset", C.c_float * 2), ("reserved", C.c_uint32), ("first_texel", C.c_uint64)]
+
+
+class PpgEnvmap(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("texels", C.POINTER(C.c_uint16)), ("scale", C.c_float), ("world_to_env", C.c_float * 9)]
 
 
 class PpgShape(C.Structure):
@@ -60,6 +70,8 @@ class PpgSceneDesc(C.Structure):
         ("bsdf_tables", C.POINTER(C.c_float)), ("n_bsdf_tables", C.c_uint32),
         ("n_spheres", C.c_uint32), ("spheres", C.POINTER(PpgSphere)),
         ("camera", PpgCamera), ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3),
+        ("n_textures", C.c_uint32), ("reserved", C.c_uint32), ("textures", C.POINTER(PpgTexture)), ("texels", C.POINTER(C.c_uint16)),
+        ("n_texels", C.c_uint64), ("envmap", PpgEnvmap),
     ]
 
 
@@ -146,6 +158,21 @@ class SceneArrays:
         d.camera = cam
         for i in range(3):
             d.aabb_min[i] = float(scene.aabb_min[i]); d.aabb_max[i] = float(scene.aabb_max[i])
+        tex = getattr(scene, "textures", None)
+        if tex is not None and len(tex):
+            self.textures = np.ascontiguousarray(tex)                           # TEXTURE_DTYPE == ppg_texture
+            self.texels = np.ascontiguousarray(scene.texels, np.uint16)
+            assert self.textures.dtype.itemsize == C.sizeof(PpgTexture)
+            d.n_textures = len(self.textures); d.textures = self.textures.ctypes.data_as(C.POINTER(PpgTexture))
+            d.texels = self.texels.ctypes.data_as(C.POINTER(C.c_uint16)); d.n_texels = len(self.texels)
+        env = getattr(scene, "envmap", None)
+        if env:
+            self.env_texels = np.ascontiguousarray(env["texels"], np.uint16)
+            d.envmap.height, d.envmap.width = self.env_texels.shape[:2]
+            d.envmap.texels = self.env_texels.ctypes.data_as(C.POINTER(C.c_uint16)); d.envmap.scale = float(env["scale"])
+            m = np.asarray(env["world_to_env"], np.float32).reshape(9)
+            for i in range(9):
+                d.envmap.world_to_env[i] = float(m[i])
         self.desc = d
 
 

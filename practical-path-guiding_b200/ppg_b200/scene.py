@@ -20,6 +20,16 @@ Reference behaviour followed (paths under /root/reference/mitsuba):
     (src/librender/scene.cpp:387-413).
   * shapes with an emitter and no BSDF get a black diffuse BSDF, shapes with
     neither get 0.5 grey diffuse (src/librender/shape.cpp:48-72).
+  * bitmap textures: 8-bit files are converted from sRGB (or the explicit
+    ``gamma``) to linear floats and stored in half precision, level 0 only
+    (src/textures/bitmap.cpp:178-183, 301-330; include/mitsuba/render/mipmap.h:226-231);
+    ``bumpmap`` wraps its nested BSDF with the displacement texture
+    (src/bsdfs/bumpmap.cpp:119-137); nested BSDFs that carry an ``id`` are
+    registered on their own like any named object (scenehandler.cpp), so a
+    ``<ref>`` to the inner id of kitchen.xml's bump-mapped cushions gets the
+    un-bumped material, exactly as in the reference.
+  * ``sunsky`` is baked to a lat-long environment map (ppg_b200/sunsky.py);
+    environment emitters do not change the scene AABB (envmap.cpp:558-564).
 """
 from __future__ import annotations
 
@@ -47,6 +57,12 @@ BSDF_THINDIELECTRIC = 8
 BSDF_FLAG_NONLINEAR = 2
 BSDF_FLAG_MASK = 4
 BSDF_FLAG_TWOSIDED = 1
+BSDF_FLAG_BUMPMAP = 8
+WRAP_MODES = {"repeat": 0, "clamp": 1, "mirror": 2}
+# numpy mirror of ppg_texture (include/ppg.h), 48 bytes
+TEXTURE_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("channels", "<u4"), ("wrap_u", "<u4"), ("wrap_v", "<u4"),
+                          ("uv_scale", "<f4", 2), ("uv_offset", "<f4", 2), ("reserved", "<u4"), ("first_texel", "<u8")])
+assert TEXTURE_DTYPE.itemsize == 48
 
 # a few entries of Mitsuba's named indices of refraction (src/bsdfs/ior.h); defaults: intIOR "bk7", extIOR "air"
 _IOR = {"vacuum": 1.0, "air": 1.000277, "water": 1.3330, "bk7": 1.5046, "diamond": 2.419, "pyrex": 1.470, "acrylic glass": 1.49,
@@ -135,6 +151,25 @@ def _integrate_product(l1, v1, l2, v2, lo, hi):
     return float(np.sum((b - a) / 6.0 * (fa + 4.0 * fm + fb)))
 
 
+def continuous_to_rgb(lam, val) -> np.ndarray:
+    """Spectrum::fromContinuousSpectrum of an InterpolatedSpectrum in an RGB build (src/libcore/spectrum.cpp:172-191, 222-227);
+    not clamped."""
+    lam = np.asarray(lam, dtype=np.float64); val = np.asarray(val, dtype=np.float64)
+    c = _cie()
+    cl = c["lambda"]
+    lo, hi = cl[0], cl[-1]
+    X = _integrate_product(lam, val, cl, c["x"], lo, hi)
+    Y = _integrate_product(lam, val, cl, c["y"], lo, hi)
+    Z = _integrate_product(lam, val, cl, c["z"], lo, hi)
+    ynorm = float(np.trapezoid(c["y"], cl))
+    X, Y, Z = X / ynorm, Y / ynorm, Z / ynorm
+    return np.array([
+        3.240479 * X - 1.537150 * Y - 0.498535 * Z,
+        -0.969256 * X + 1.875991 * Y + 0.041556 * Z,
+        0.055648 * X - 0.204043 * Y + 1.057311 * Z,
+    ])
+
+
 def spectrum_to_rgb(wavelengths, values) -> np.ndarray:
     """InterpolatedSpectrum(...).zeroExtend() -> Spectrum::fromContinuousSpectrum
     (RGB build) -> clampNegative."""
@@ -147,20 +182,7 @@ def spectrum_to_rgb(wavelengths, values) -> np.ndarray:
         lam = np.concatenate([[lam[0] - spacing], lam]); val = np.concatenate([[0.0], val])
     if val[-1] != 0:
         lam = np.concatenate([lam, [lam[-1] + spacing]]); val = np.concatenate([val, [0.0]])
-    c = _cie()
-    cl = c["lambda"]
-    lo, hi = cl[0], cl[-1]
-    X = _integrate_product(lam, val, cl, c["x"], lo, hi)
-    Y = _integrate_product(lam, val, cl, c["y"], lo, hi)
-    Z = _integrate_product(lam, val, cl, c["z"], lo, hi)
-    ynorm = float(np.trapezoid(c["y"], cl))
-    X, Y, Z = X / ynorm, Y / ynorm, Z / ynorm
-    rgb = np.array([
-        3.240479 * X - 1.537150 * Y - 0.498535 * Z,
-        -0.969256 * X + 1.875991 * Y + 0.041556 * Z,
-        0.055648 * X - 0.204043 * Y + 1.057311 * Z,
-    ])
-    return np.maximum(rgb, 0.0).astype(np.float32)
+    return np.maximum(continuous_to_rgb(lam, val), 0.0).astype(np.float32)
 
 
 def d65_rgb() -> np.ndarray:
@@ -231,8 +253,52 @@ def _parse_transform(node) -> np.ndarray:
 
 # --------------------------------------------------------------------------- meshes
 
+def _load_obj_fast(path, to_world, face_normals, flip_normals):
+    """Vectorised path for the common export style: triangles only, every corner 'p/t/n' with positive indices.
+    Returns None when the file does not fit (the generic loader takes over).  Vertices are merged per (p, t, n) index
+    triple instead of per value -- same surface, possibly a few more vertices."""
+    v, vn, vt, fl = [], [], [], []
+    with open(path, "r", errors="replace") as f:
+        for line in f:
+            if line.startswith("v "): v.append(line[2:])
+            elif line.startswith("vn "): vn.append(line[3:])
+            elif line.startswith("vt "): vt.append(line[3:])
+            elif line.startswith("f "): fl.append(line[2:])
+    if not fl or not v or not vn or not vt:
+        return None
+    ftxt = " ".join(fl)
+    if "//" in ftxt or "-" in ftxt:
+        return None
+    try:
+        F = np.array(ftxt.replace("/", " ").split(), dtype=np.int64)
+    except ValueError:
+        return None
+    if F.size != 9 * len(fl) or ftxt.count("/") != 6 * len(fl):
+        return None
+    verts = np.array(" ".join(v).split(), dtype=np.float64).reshape(len(v), -1)[:, :3]
+    norms = np.array(" ".join(vn).split(), dtype=np.float64).reshape(len(vn), -1)[:, :3]
+    uvs = np.array(" ".join(vt).split(), dtype=np.float64).reshape(len(vt), -1)[:, :2]
+    corners = F.reshape(-1, 3)                                   # (3T, [p, t, n]) 1-based
+    uniq, inv = np.unique(corners, axis=0, return_inverse=True)
+    M = to_world
+    P = (verts[uniq[:, 0] - 1] @ M[:3, :3].T + M[:3, 3]).astype(np.float32)
+    Nw = norms[uniq[:, 2] - 1] @ np.linalg.inv(M[:3, :3])     # (M^-T n)^T = n^T M^-1
+    l = np.linalg.norm(Nw, axis=1, keepdims=True)
+    N = np.where(l > 0, Nw / np.maximum(l, 1e-300), Nw).astype(np.float32)
+    UV = uvs[uniq[:, 1] - 1].astype(np.float32); UV[:, 1] = 1 - UV[:, 1]        # flipTexCoords default true (obj.cpp:211, 306)
+    I = inv.reshape(-1, 3).astype(np.uint32)
+    if face_normals:
+        if flip_normals: I = I[:, [1, 0, 2]]
+        return P, None, UV, I
+    if flip_normals: N = -N
+    return P, N, UV, I
+
+
 def _load_obj(path, to_world, face_normals=False, flip_normals=False):
     """WavefrontOBJ -> one merged triangle mesh (the bundled OBJs hold one object each)."""
+    fast = _load_obj_fast(path, to_world, face_normals, flip_normals)
+    if fast is not None:
+        return fast
     verts, norms, uvs, tris = [], [], [], []
     with open(path, "r", errors="replace") as f:
         for line in f:
@@ -365,6 +431,9 @@ class SceneDesc:
     bsdf_names: list = field(default_factory=list)
     bsdf_tables: np.ndarray = None   # (T,100) f32 rough-transmittance tables referenced by roughplastic materials
     spheres: np.ndarray = None       # (K,6) f32 view of ppg_sphere: center[3], radius, shape (int bits), flip_normals (int bits)
+    textures: np.ndarray = None      # (N,) TEXTURE_DTYPE == ppg_texture
+    texels: np.ndarray = None        # uint16 (IEEE half bits) of all textures
+    envmap: dict = None              # {"texels": (H,W,3) uint16 half bits, "scale": float, "world_to_env": (3,3) f32} or None
 
     def with_film(self, w: int, h: int) -> "SceneDesc":
         """Same scene, different film size (x fov re-resolved only when the aspect
@@ -381,17 +450,27 @@ class SceneDesc:
             aabb=np.stack([self.aabb_min, self.aabb_max]).astype(np.float32),
             integrator=np.array([f"{k}={v}" for k, v in self.integrator.items()]),
             bsdf_names=np.array(self.bsdf_names), bsdf_tables=(self.bsdf_tables if self.bsdf_tables is not None else np.zeros((0, 100), np.float32)),
-            spheres=(self.spheres if self.spheres is not None else np.zeros((0, 6), np.float32)))
+            spheres=(self.spheres if self.spheres is not None else np.zeros((0, 6), np.float32)),
+            textures=(self.textures if self.textures is not None else np.zeros(0, TEXTURE_DTYPE)).view(np.uint8),
+            texels=(self.texels if self.texels is not None else np.zeros(0, np.uint16)),
+            env_texels=(self.envmap["texels"] if self.envmap else np.zeros((0, 0, 3), np.uint16)),
+            env_meta=(np.concatenate([[self.envmap["scale"]], np.asarray(self.envmap["world_to_env"], np.float64).reshape(9)]) if self.envmap else np.zeros(0)))
 
     @staticmethod
     def load(path) -> "SceneDesc":
         d = np.load(path, allow_pickle=False)
         cam = d["cam"]
         integ = dict(s.split("=", 1) for s in d["integrator"].tolist())
-        return SceneDesc(d["positions"], d["normals"], d["uvs"], d["indices"], d["triangle_shape"], d["shapes"],
-                         d["bsdfs"], d["area_radiance"], d["cam_to_world"], float(cam[0]), float(cam[1]), float(cam[2]),
-                         int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist(),
-                         d["bsdf_tables"] if "bsdf_tables" in d.files else None, d["spheres"] if "spheres" in d.files else None)
+        sc = SceneDesc(d["positions"], d["normals"], d["uvs"], d["indices"], d["triangle_shape"], d["shapes"],
+                       d["bsdfs"], d["area_radiance"], d["cam_to_world"], float(cam[0]), float(cam[1]), float(cam[2]),
+                       int(cam[3]), int(cam[4]), d["aabb"][0], d["aabb"][1], integ, d["bsdf_names"].tolist(),
+                       d["bsdf_tables"] if "bsdf_tables" in d.files else None, d["spheres"] if "spheres" in d.files else None)
+        if "textures" in d.files and d["textures"].size:
+            sc.textures = d["textures"].view(TEXTURE_DTYPE).copy(); sc.texels = d["texels"]
+        if "env_texels" in d.files and d["env_texels"].size:
+            m = d["env_meta"]
+            sc.envmap = {"texels": d["env_texels"], "scale": float(m[0]), "world_to_env": m[1:10].reshape(3, 3).astype(np.float32)}
+        return sc
 
 
 def make_sphere(center, radius, shape, flip_normals=False):
@@ -404,7 +483,8 @@ def make_sphere(center, radius, shape, flip_normals=False):
 
 def _make_bsdf(type_, flags, refl, trans=(0, 0, 0), eta=(0, 0, 0), k=(0, 0, 0), alpha=0.1, distribution=0):
     """One ppg_bsdf (include/ppg.h) as 28 floats: type, flags, reflectance[3], specular_transmittance[3], eta[3], k[3], alpha, distribution (int bits),
-    specular_reflectance[3], fdr_int, specular_sampling_weight, table (int bits), opacity[3], reserved[3]; the trailing fields stay 0 here."""
+    specular_reflectance[3], fdr_int, specular_sampling_weight, table (int bits), opacity[3], reflectance_texture / bump_texture / reserved (uint bits);
+    the trailing fields stay 0 here."""
     b = np.zeros(28, np.float32)
     b[:2] = np.array([type_, flags], np.uint32).view(np.float32)
     b[2:5] = refl; b[5:8] = trans; b[8:11] = eta; b[11:14] = k; b[14] = alpha
@@ -482,53 +562,128 @@ def _parse_color(node, is_emitter=False):
 
 
 _TABLES = []      # rough-transmittance tables collected while parsing one scene
+_TEXTURES = []    # (meta dict, half-bit texel array) collected while parsing one scene
+_TEX_CACHE = {}
 
 
-def _parse_bsdf(node, bsdf_table, names, by_id):
-    typ = node.attrib["type"]
-    flags = 0
-    inner = node
-    id_node = node
-    opacity = None
-    if typ == "mask":                   # src/bsdfs/mask.cpp:63-66: constant opacity around a nested BSDF
-        if any(c.tag == "texture" for c in node):
-            raise NotImplementedError("mask: textured opacity is out of scope (bitmap textures)")
-        opacity = np.full(3, 0.5, np.float32)
-        for c in node:
-            if c.tag in ("rgb", "srgb", "spectrum") and c.attrib.get("name") == "opacity":
-                opacity = _parse_color(c)
-        flags |= BSDF_FLAG_MASK
-        inner = [c for c in node if c.tag == "bsdf"][0]
-        node = inner
-        typ = inner.attrib["type"]
-    if typ == "twosided":
-        flags |= BSDF_FLAG_TWOSIDED
-        inner = [c for c in node if c.tag == "bsdf"][0]
-        typ = inner.attrib["type"]
+def load_bitmap(path, gamma=0.0):
+    """Bitmap(EAuto, file) -> expand()->convert(ERGB | ELuminance, EFloat, gamma 1) like TMIPMap's constructor
+    (include/mitsuba/render/mipmap.h:226-231; src/libcore/bitmap.cpp): 8-bit data are sRGB-decoded (file gamma -1) unless an
+    explicit gamma is given.  Returns float32 (H, W, C) with C = 1 or 3."""
+    import cv2
+    im = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if im is None:
+        raise FileNotFoundError(f"Texture file \"{path}\" could not be found / decoded!")
+    if im.ndim == 2:
+        im = im[:, :, None]
+    elif im.shape[2] >= 3:
+        im = im[:, :, 2::-1]                     # BGR(A) -> RGB, alpha dropped (ERGBA -> ERGB)
+    elif im.shape[2] == 2:
+        im = im[:, :, :1]                        # luminance + alpha
+    if im.dtype == np.uint8:
+        v = im.astype(np.float64) / 255.0
+    elif im.dtype == np.uint16:
+        v = im.astype(np.float64) / 65535.0
+    else:
+        return np.ascontiguousarray(im, np.float32)      # float formats are linear already
+    if gamma == 0:
+        lin = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+    else:
+        lin = v ** gamma
+    return np.ascontiguousarray(lin, np.float32)
+
+
+def _parse_texture(node, base):
+    """<texture type="bitmap"> -> index into the scene's texture list (src/textures/bitmap.cpp:178-330)."""
+    if node.attrib.get("type") != "bitmap":
+        raise NotImplementedError(f"texture '{node.attrib.get('type')}' (only 'bitmap' is in scope)")
+    pr = _prop_children(node)
+    if pr.get("channel"):
+        raise NotImplementedError("bitmap texture: 'channel' extraction")
+    path = os.path.join(base, pr["filename"])
+    gamma = float(pr.get("gamma", 0))
+    wrap = pr.get("wrapMode", "repeat")
+    wu, wv = pr.get("wrapModeU", wrap), pr.get("wrapModeV", wrap)
+    uvscale = float(pr.get("uvscale", 1.0))
+    meta = dict(path=path, gamma=gamma, wrap_u=WRAP_MODES[wu], wrap_v=WRAP_MODES[wv],
+                uv_scale=(float(pr.get("uscale", uvscale)), float(pr.get("vscale", uvscale))),
+                uv_offset=(float(pr.get("uoffset", 0.0)), float(pr.get("voffset", 0.0))))
+    key = tuple(sorted((k, v) for k, v in meta.items()))
+    if key in _TEX_CACHE:
+        return _TEX_CACHE[key]
+    img = load_bitmap(path, gamma)
+    meta["width"], meta["height"], meta["channels"] = img.shape[1], img.shape[0], img.shape[2]
+    meta["average"] = img.reshape(-1, img.shape[2]).mean(axis=0, dtype=np.float64)      # m_average (mipmap.h:230): of the float data
+    with np.errstate(over="ignore"):
+        half = img.astype(np.float16)
+    _TEXTURES.append((meta, half.view(np.uint16).reshape(-1)))
+    _TEX_CACHE[key] = len(_TEXTURES) - 1
+    return _TEX_CACHE[key]
+
+
+def texture_average_rgb(idx):
+    a = _TEXTURES[idx][0]["average"]
+    return (np.full(3, a[0]) if len(a) == 1 else a).astype(np.float32)
+
+
+_WRAPPERS = ("bumpmap", "mask", "twosided")
+
+
+def _parse_bsdf(node, bsdf_table, names, by_id, base="."):
+    """One <bsdf> element -> index into bsdf_table.  Wrappers must nest as bumpmap > mask > twosided > model (the order the
+    device applies them); every level that carries an id is registered on its own."""
+    chain = []
+    cur = node
+    while cur.attrib["type"] in _WRAPPERS:
+        chain.append(cur)
+        kids = [c for c in cur if c.tag == "bsdf"]
+        if len(kids) != 1:
+            raise ValueError(f"{cur.attrib['type']}: exactly one nested BSDF is required")
+        cur = kids[0]
+    order = [_WRAPPERS.index(c.attrib["type"]) for c in chain]
+    if order != sorted(set(order)):
+        raise NotImplementedError("BSDF wrappers must nest as bumpmap > mask > twosided")
+    inner = cur
+    typ = inner.attrib["type"]
+    twosided = any(c.attrib["type"] == "twosided" for c in chain)
     colors = {c.attrib.get("name"): c for c in inner if c.tag in ("rgb", "srgb", "spectrum")}
+    texs = {c.attrib.get("name"): c for c in inner if c.tag == "texture"}
     props = _prop_children(inner)
-    if typ == "diffuse":
-        refl = np.full(3, 0.5, np.float32)  # diffuse.cpp default reflectance
-        for nm in ("reflectance", "diffuseReflectance"):
+
+    def diffuse_input(nm_list, default):
+        """constant colour or bitmap texture for a reflectance slot -> (rgb used for averages, 1-based texture index or 0)"""
+        for nm in nm_list:
+            if nm in texs:
+                ti = _parse_texture(texs[nm], base)
+                return texture_average_rgb(ti), ti + 1
             if nm in colors:
-                refl = _parse_color(colors[nm])
+                return _parse_color(colors[nm]), 0
+        return np.full(3, default, np.float32), 0
+
+    for nm in texs:
+        if nm not in ("reflectance", "diffuseReflectance"):
+            raise NotImplementedError(f"textured BSDF parameter '{nm}'")
+    flags = 0          # wrapper flags are added level by level below; the transmissive models refuse twosided
+    tex_idx = 0
+    if typ == "diffuse":
+        refl, tex_idx = diffuse_input(("reflectance", "diffuseReflectance"), 0.5)   # diffuse.cpp:70-74
         entry = _make_bsdf(BSDF_DIFFUSE, flags, refl)
     elif typ == "dielectric":           # src/bsdfs/dielectric.cpp:157-190
-        if flags & BSDF_FLAG_TWOSIDED:
+        if twosided:
             raise ValueError("twosided cannot wrap a transmissive BSDF")
         eta = _lookup_ior(props.get("intIOR"), "bk7") / _lookup_ior(props.get("extIOR"), "air")
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
         entry = _make_bsdf(BSDF_DIELECTRIC, flags, sr, st, (eta, eta, eta))
     elif typ == "thindielectric":       # src/bsdfs/thindielectric.cpp:88-104
-        if flags & BSDF_FLAG_TWOSIDED:
+        if twosided:
             raise ValueError("twosided cannot wrap a transmissive BSDF")
         eta = _lookup_ior(props.get("intIOR"), "bk7") / _lookup_ior(props.get("extIOR"), "air")
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         st = _parse_color(colors["specularTransmittance"]) if "specularTransmittance" in colors else np.ones(3, np.float32)
         entry = _make_bsdf(BSDF_THINDIELECTRIC, flags, sr, st, (eta, eta, eta))
     elif typ == "roughdielectric":      # src/bsdfs/roughdielectric.cpp:183-210
-        if flags & BSDF_FLAG_TWOSIDED:
+        if twosided:
             raise ValueError("twosided cannot wrap a transmissive BSDF")
         eta = _lookup_ior(props.get("intIOR"), "bk7") / _lookup_ior(props.get("extIOR"), "air")
         distr = props.get("distribution", "beckmann").lower()
@@ -539,7 +694,7 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         entry = _make_bsdf(BSDF_ROUGHDIELECTRIC, flags, sr, st, (eta, eta, eta), (0, 0, 0), float(props.get("alpha", 0.1)), 1 if distr == "ggx" else 0)
     elif typ == "plastic":              # src/bsdfs/plastic.cpp:143-163
         eta = _lookup_ior(props.get("intIOR"), "polypropylene") / _lookup_ior(props.get("extIOR"), "air")
-        dr = _parse_color(colors["diffuseReflectance"]) if "diffuseReflectance" in colors else np.full(3, 0.5, np.float32)
+        dr, tex_idx = diffuse_input(("diffuseReflectance",), 0.5)
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         entry = make_plastic(flags, dr, sr, eta, props.get("nonlinear", "false") == "true")
     elif typ == "roughplastic":         # src/bsdfs/roughplastic.cpp:190-232
@@ -547,7 +702,7 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         distr = props.get("distribution", "beckmann").lower()
         if distr not in ("beckmann", "ggx"):
             raise NotImplementedError(f"microfacet distribution '{distr}'")
-        dr = _parse_color(colors["diffuseReflectance"]) if "diffuseReflectance" in colors else np.full(3, 0.5, np.float32)
+        dr, tex_idx = diffuse_input(("diffuseReflectance",), 0.5)
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         entry = make_roughplastic(flags, dr, sr, eta, float(props.get("alpha", 0.1)), 1 if distr == "ggx" else 0, props.get("nonlinear", "false") == "true", _TABLES)
     elif typ == "roughconductor":       # src/bsdfs/roughconductor.cpp:190-222
@@ -576,23 +731,87 @@ def _parse_bsdf(node, bsdf_table, names, by_id):
         sr = _parse_color(colors["specularReflectance"]) if "specularReflectance" in colors else np.ones(3, np.float32)
         entry = _make_bsdf(BSDF_CONDUCTOR, flags, sr, (0, 0, 0), eta / ext, k / ext)
     else:
-        raise NotImplementedError(f"BSDF '{typ}' is not implemented yet (hot-path scope so far: diffuse, dielectric, conductor, twosided)")
-    if opacity is not None:
-        if int(entry[:1].view(np.uint32)[0]) in (BSDF_THINDIELECTRIC,):
-            raise NotImplementedError("mask around another null-type BSDF")
-        entry[22:25] = opacity
-    idx = len(bsdf_table)
-    bsdf_table.append(entry)
-    names.append(id_node.attrib.get("id", f"bsdf{idx}"))
-    if "id" in id_node.attrib:
-        by_id[id_node.attrib["id"]] = idx
-    return idx
+        raise NotImplementedError(f"BSDF '{typ}' is outside the hot-path scope")
+    entry[25:26] = np.array([tex_idx], np.uint32).view(np.float32)
+
+    def push(e, nd):
+        idx = len(bsdf_table)
+        bsdf_table.append(e)
+        names.append(nd.attrib.get("id", f"bsdf{idx}"))
+        if "id" in nd.attrib:
+            by_id[nd.attrib["id"]] = idx
+        return idx
+
+    def set_flag(e, f):
+        e = e.copy(); e[1:2] = (e[1:2].view(np.uint32) | np.uint32(f)).view(np.float32); return e
+
+    levels = [(inner, entry)]
+    for w in reversed(chain):           # from the innermost wrapper outwards
+        e = levels[-1][1]
+        wt = w.attrib["type"]
+        if wt == "twosided":
+            e = set_flag(e, BSDF_FLAG_TWOSIDED)
+        elif wt == "mask":               # src/bsdfs/mask.cpp:63-66: constant opacity around the nested BSDF
+            if any(c.tag == "texture" for c in w):
+                raise NotImplementedError("mask: textured opacity")
+            if int(e[:1].view(np.uint32)[0]) == BSDF_THINDIELECTRIC:
+                raise NotImplementedError("mask around another null-type BSDF")
+            opacity = np.full(3, 0.5, np.float32)
+            for c in w:
+                if c.tag in ("rgb", "srgb", "spectrum") and c.attrib.get("name") == "opacity":
+                    opacity = _parse_color(c)
+            e = set_flag(e, BSDF_FLAG_MASK); e[22:25] = opacity
+        else:                            # bumpmap.cpp:119-137: one displacement texture
+            tx = [c for c in w if c.tag == "texture"]
+            if len(tx) != 1:
+                raise ValueError("bumpmap: A displacement texture must be specified")
+            if tx[0].attrib.get("type") == "bitmap" and "gamma" not in _prop_children(tx[0]):
+                raise ValueError("When using a bitmap texture as a bump map, please explicitly specify the 'gamma' parameter of the bitmap plugin.")
+            e = set_flag(e, BSDF_FLAG_BUMPMAP); e[26:27] = np.array([_parse_texture(tx[0], base) + 1], np.uint32).view(np.float32)
+        levels.append((w, e))
+    result = None
+    for k, (nd, e) in enumerate(levels):
+        if k == len(levels) - 1 or "id" in nd.attrib:
+            result = push(e, nd)
+    return result
+
+
+def _parse_environment(node, base):
+    """Root-level <emitter>: sunsky (baked, ppg_b200/sunsky.py) or envmap (src/emitters/envmap.cpp:102-190) -> envmap dict."""
+    typ = node.attrib.get("type")
+    pr = _prop_children(node)
+    to_world = np.eye(4)
+    for t in node.findall("transform"):
+        if t.attrib.get("name") == "toWorld":
+            to_world = _parse_transform(t)
+    if typ == "sunsky":
+        from . import sunsky
+        for c in node:
+            if c.attrib.get("name") == "albedo" and c.tag in ("rgb", "srgb", "spectrum"):
+                pr["albedo"] = _parse_color(c)
+        img, _ = sunsky.bake(pr)
+        scale = 1.0                       # sunsky.cpp:209-219 passes no scale to the nested envmap
+    elif typ == "envmap":
+        os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+        img = load_bitmap(os.path.join(base, pr["filename"]), float(pr.get("gamma", 0)))
+        if img.shape[2] == 1:
+            img = np.repeat(img, 3, axis=2)
+        scale = float(pr.get("scale", 1.0))
+    else:
+        raise NotImplementedError(f"emitter '{typ}' (scene-level emitters in scope: sunsky, envmap)")
+    with np.errstate(over="ignore"):
+        half = np.ascontiguousarray(img, np.float32).astype(np.float16)
+    if not np.isfinite(half.astype(np.float32)).all():
+        raise ValueError("The environment map contains an invalid floating point value (nan/inf) -- giving up.")
+    return {"texels": half.view(np.uint16), "scale": scale, "world_to_env": np.linalg.inv(to_world[:3, :3]).astype(np.float32)}
 
 
 def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
     root = ET.parse(path).getroot()
     base = os.path.dirname(os.path.abspath(path))
     del _TABLES[:]
+    del _TEXTURES[:]
+    _TEX_CACHE.clear()
     integrator = {}
     inode = root.find("integrator")
     if inode is not None:
@@ -646,7 +865,12 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
 
     bsdf_table, names, by_id = [], [], {}
     for b in root.findall("bsdf"):
-        _parse_bsdf(b, bsdf_table, names, by_id)
+        _parse_bsdf(b, bsdf_table, names, by_id, base)
+    envmap = None
+    for e in root.findall("emitter"):
+        if envmap is not None:
+            raise NotImplementedError("more than one scene-level emitter")
+        envmap = _parse_environment(e, base)
 
     P_all, N_all, UV_all, I_all, TS_all, shapes, radiance = [], [], [], [], [], [], []
     voff = 0; toff = 0
@@ -684,7 +908,7 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
             bsdf_idx = by_id[ref.attrib["id"]]
         bn = sh.find("bsdf")
         if bn is not None:
-            bsdf_idx = _parse_bsdf(bn, bsdf_table, names, by_id)
+            bsdf_idx = _parse_bsdf(bn, bsdf_table, names, by_id, base)
         em = sh.find("emitter")
         em_idx = -1
         if em is not None:
@@ -712,6 +936,11 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
         TS_all.append(np.full(len(I), len(shapes) - 1, np.uint32))
         voff += len(P); toff += len(I)
 
+    textures = np.zeros(len(_TEXTURES), TEXTURE_DTYPE); off = 0
+    for i, (m, tx) in enumerate(_TEXTURES):
+        textures[i] = (m["width"], m["height"], m["channels"], m["wrap_u"], m["wrap_v"], m["uv_scale"], m["uv_offset"], 0, off)
+        off += len(tx)
+    texels = np.concatenate([tx for _, tx in _TEXTURES]) if _TEXTURES else np.zeros(0, np.uint16)
     P = np.concatenate(P_all).astype(np.float32)
     aabb_min = P.min(axis=0).astype(np.float64); aabb_max = P.max(axis=0).astype(np.float64)
     cam_pos = cam_to_world[:3, 3]
@@ -726,4 +955,5 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
         spheres=np.asarray([make_sphere(c, r, si, fl) for c, r, si, fl in sphere_list], np.float32).reshape(-1, 6),
         area_radiance=np.asarray(radiance, np.float32).reshape(-1, 3), cam_to_world=cam_to_world.astype(np.float32),
         x_fov_deg=float(xfov), near_clip=near, far_clip=far, film_width=W, film_height=H,
-        aabb_min=aabb_min.astype(np.float32), aabb_max=aabb_max.astype(np.float32), integrator=integrator, bsdf_names=names)
+        aabb_min=aabb_min.astype(np.float32), aabb_max=aabb_max.astype(np.float32), integrator=integrator, bsdf_names=names,
+        textures=textures, texels=texels, envmap=envmap)

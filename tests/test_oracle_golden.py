@@ -103,3 +103,31 @@ def test_spaceship_known_answers(kind):
         assert abs(it[k]["depth_avg"] - g[k]["depth"][1]) <= 0.2
     # the log's average depths are exact fractions of the leaf count: 5.066667 = 2432/480, 5.118454 = 4105/802
     assert abs(it[2]["s_tree_leaves"] - 480) <= 40 and abs(it[3]["s_tree_leaves"] - 802) <= 60       # run-to-run spread of the oracle: 480-496, 790-830
+
+
+def test_kitchen_known_answers():
+    """BASELINE config 3's scene.  The authors' own render of scenes/kitchen/kitchen-improved.xml (700x400; log embedded in kitchen-improved.exr)
+    pins what neither CBOX nor SPACESHIP touch: bilinear bitmap textures on diffuse / rough-plastic reflectances, the sunsky emitter baked to an
+    environment map and evaluated on ray misses and through the masked blinds, 1.4 M triangles in 291 meshes with texture coordinates, smooth
+    plastic, thin glass.  Known answers of the first three iterations (log: measured here with the restated SD-tree):
+      iteration 0: one D-tree of 85 nodes; stat. weight 1 276 699 (1 277 775)
+      iteration 1: Var 4.429142 (4.504), avg weight 3466.27 (3438.0)
+      iteration 2: Var 3.988858 (4.001), avg weight 7935.99 (8013.2)
+    (the mean radiance of iteration 0 is dominated by rare sun hits: 0.0913 in the log, 0.072 - 0.10 here depending on the seed).
+    Tolerances: count 0.5 %, later averages 4 %, the heavy-tailed variance estimate 12 %."""
+    from common import load_fixture_scene
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "kitchen_log_stats.json")))["kitchen-improved"]
+    assert (gold["width"], gold["height"]) == (700, 400)
+    sc = load_fixture_scene("kitchen-improved")
+    assert (sc.film_width, sc.film_height) == (700, 400)
+    o = O.Oracle(O.params_from_xml(dict(sc.integrator, budget="15")), sc, kind="port")
+    o.step_reset(0); o.step_passes(1); s0 = o.step_build()
+    g = gold["iterations"]
+    assert s0["nodes_min"] == s0["nodes_max"] == 85 == int(g[0]["node_count"][0])
+    assert abs(s0["weight_avg"] - g[0]["stat_weight"][1]) <= 0.005 * g[0]["stat_weight"][1], s0["weight_avg"]
+    assert 0.5 * g[0]["mean_radiance"][1] < s0["mean_radiance_avg"] < 1.6 * g[0]["mean_radiance"][1]
+    for k, passes in ((1, 2), (2, 4)):
+        o.step_reset(k); var = o.step_passes(passes); st = o.step_build()
+        assert abs(var - g[k]["var"]) <= 0.12 * g[k]["var"], (k, var, g[k]["var"])
+        assert abs(st["weight_avg"] - g[k]["stat_weight"][1]) <= 0.04 * g[k]["stat_weight"][1], (k, st["weight_avg"])
+        assert abs(st["nodes_avg"] - g[k]["node_count"][1]) <= 6 and abs(st["depth_avg"] - g[k]["depth"][1]) <= 0.4

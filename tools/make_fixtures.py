@@ -12,6 +12,12 @@ Writes
                              /root/reference/mitsuba/data/microfacet/{beckmann,ggx}.dat (ppg_b200/rtrans.py)
   scenes/spaceship-improved.npz   flat-array form of /root/reference/scenes/spaceship/spaceship-improved.xml (457 560 triangles + 1 sphere)
   tests/golden/spaceship_log_stats.json   the same for spaceship-improved.exr (first six iterations)
+  scenes/kitchen-improved.npz     flat-array form of /root/reference/scenes/kitchen/kitchen-improved.xml (1 414 391 triangles, 13 bitmap textures as
+                                  half-precision level-0 texels, the sunsky emitter baked to a 512x256 environment map by ppg_b200/sunsky.py)
+  scenes/cbox-textured.npz        procedural CBOX variant with bitmap textures, bump maps and an environment map (builtin_scenes.cbox_textured)
+  scenes/cbox-textured-flat.npz   the same without the bump maps
+  tests/golden/kitchen_log_stats.json     known answers of the authors' kitchen-improved.exr / kitchen.exr logs (first seven iterations)
+  tests/golden/kitchen_improved_175x100.npy, kitchen_reference_175x100.npy   the golden images box-downsampled 4x4 (float16)
   tests/golden/cbox_log_stats.json   known-answer statistics parsed from the logs embedded
                                       in the reference's golden EXRs (hdrfilm attachLog)
 """
@@ -94,7 +100,43 @@ def spaceship_log():
     print("spaceship golden image mean rgb", im.mean(axis=(0, 1)))
 
 
+def kitchen():
+    sc = S.load_mitsuba_xml(f"{REF}/scenes/kitchen/kitchen-improved.xml")
+    sc.save(os.path.join(ROOT, "scenes", "kitchen-improved.npz"))
+    print("kitchen", "tris", len(sc.indices), "verts", len(sc.positions), "bsdfs", len(sc.bsdfs), "textures", len(sc.textures), "texels", sc.texels.size,
+          "envmap", sc.envmap["texels"].shape, sc.integrator)
+
+
+def kitchen_log():
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import cv2
+    out = {}
+    for nm in ("kitchen-improved", "kitchen"):
+        st = parse_log(exr_attr(f"{REF}/scenes/kitchen/{nm}.exr", "log").decode(errors="replace"))
+        st["iterations"] = st["iterations"][:7]
+        out[nm] = st
+    with open(os.path.join(ROOT, "tests", "golden", "kitchen_log_stats.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    for nm, tag in (("kitchen-improved", "improved"), ("kitchen-reference", "reference")):
+        im = cv2.imread(f"{REF}/scenes/kitchen/{nm}.exr", cv2.IMREAD_UNCHANGED)[..., :3][..., ::-1].astype(np.float64)
+        small = im.reshape(100, 4, 175, 4, 3).mean(axis=(1, 3))
+        np.save(os.path.join(ROOT, "tests", "golden", f"kitchen_{tag}_175x100.npy"), small.astype(np.float16))
+        print(nm, "mean rgb", im.mean(axis=(0, 1)))
+
+
+def textured():
+    from ppg_b200.builtin_scenes import cbox_textured
+    sc = cbox_textured(S.SceneDesc.load(os.path.join(ROOT, "scenes", "cbox.npz")))
+    sc.save(os.path.join(ROOT, "scenes", "cbox-textured.npz"))
+    cbox_textured(S.SceneDesc.load(os.path.join(ROOT, "scenes", "cbox.npz")), bump=False).save(os.path.join(ROOT, "scenes", "cbox-textured-flat.npz"))
+    print("cbox-textured", sc.bsdf_names[-4:], "textures", len(sc.textures), "envmap", sc.envmap["texels"].shape)
+
+
 def main():
+    if sys.argv[1:] == ["kitchen"]:
+        kitchen(); return kitchen_log()
+    if sys.argv[1:] == ["textured"]:
+        return textured()
     if sys.argv[1:] == ["spaceship_log"]:
         return spaceship_log()
     if sys.argv[1:] == ["plastic"]:
@@ -122,6 +164,8 @@ def main():
     print(json.dumps(stats["cbox"]["iterations"][:2], indent=1))
     plastic()
     spaceship()
+    textured()
+    kitchen(); kitchen_log()
 
 
 if __name__ == "__main__":
