@@ -280,7 +280,11 @@ typedef struct ppg_stats {
     /* CUDA-event time per kernel class, measured on the launching stream (index: ppg_kernel_class) */
     double   kernel_ms[PPG_KERNEL_CLASSES];
     uint64_t kernel_count[PPG_KERNEL_CLASSES];
-    double   render_device_ms;     /* CUDA-event time of the whole render on the library's stream */
+    double   render_device_ms;     /* CUDA-event time of the whole render on the library's stream (with ppg_nccl_init: including the final film allreduce) */
+    uint64_t truncated_paths;      /* paths still alive at the 64-bounce cap of maxDepth = -1 (they keep the radiance gathered so far) */
+    uint64_t dropped_records;      /* sampling-fraction records beyond the record buffer (0 in every configuration measured) */
+    uint64_t sub_batches;          /* wavefronts the learning iterations were split into (sampling-fraction step-size control) */
+    uint64_t invalid_rays;         /* rays with a non-finite origin or direction, treated as misses (the reference's kd-tree clips them away) */
     ppg_iteration_stats iterations[PPG_MAX_ITERATIONS];
 } ppg_stats;
 
@@ -316,6 +320,26 @@ int ppg_set_shard(ppg_integrator *h, int rank, int world_size);
  * the end. Not set (default) -> single-rank, no exchange. */
 typedef int (*ppg_allreduce_fn)(void *user, void *device_ptr, size_t n_floats);
 int ppg_set_allreduce(ppg_integrator *h, ppg_allreduce_fn cb, void *user);
+
+/* Multi-GPU without a host round trip: the library dlopen()s libnccl.so.2 and enqueues ncclAllReduce on its own stream.
+ * One rank calls ppg_nccl_unique_id (ncclGetUniqueId, 128 bytes), the host distributes the bytes (MPI, a file, torch.distributed
+ * ...), then every rank calls ppg_nccl_init, which creates the communicator (ncclCommInitRank) and implies
+ * ppg_set_shard(rank, world_size).  Takes precedence over a ppg_set_allreduce callback.  PPG_ERR_COMM if NCCL is unavailable. */
+#define PPG_NCCL_UNIQUE_ID_BYTES 128
+int ppg_nccl_unique_id(void *id_out);
+int ppg_nccl_init(ppg_integrator *h, const void *id, int rank, int world_size);
+
+/* budgetType = seconds reads a monotonic clock (GP:1259-1262, 1434-1514).  A host may supply its own (seconds since ppg_render
+ * started rendering; used by the tests to drive the time-based schedule deterministically).  NULL restores the steady clock. */
+typedef double (*ppg_clock_fn)(void *user);
+int ppg_set_clock(ppg_integrator *h, ppg_clock_fn fn, void *user);
+
+/* Progressive film: the reference puts every finished image block into the film while rendering (renderproc.cpp:143-151), which
+ * is what a GUI or a time-limited job reads.  When set, the callback receives the current weight-normalised RGB film (DEVICE pointer,
+ * W*H*3 floats, this rank's pixels) after every performRenderPasses, i.e. after every iteration and after every batch of the
+ * final iteration of a seconds budget (GP:1482-1501); it runs on the host thread that drives ppg_render. */
+typedef void (*ppg_film_fn)(void *user, const float *rgb_dev, int width, int height, int passes_rendered);
+int ppg_set_film_callback(ppg_integrator *h, ppg_film_fn fn, void *user);
 
 /* Integrator::render(). Runs the whole iteration schedule (GP:1342-1514),
  * develops the film into rgb_out (W*H*3 floats, row-major, host memory;

@@ -389,8 +389,8 @@ struct Scene {
                 float ta = (n.bmin[a] - comp(o, a)) * comp(inv, a), tb = (n.bmax[a] - comp(o, a)) * comp(inv, a);
                 if (ta > tb) std::swap(ta, tb);
                 // widen conservatively: degenerate (flat) boxes and NaNs from 0*inf must not cull
-                if (!(ta != ta)) t0 = std::max(t0, ta - std::fabs(ta) * 1e-6f);
-                if (!(tb != tb)) t1 = std::min(t1, tb + std::fabs(tb) * 1e-6f);
+                if (!(ta != ta)) t0 = std::max(t0, ta * (ta > 0 ? 1.0f - 1e-6f : 1.0f + 1e-6f));      // multiplicative: inf - inf would be NaN and never cull
+                if (!(tb != tb)) t1 = std::min(t1, tb * (tb > 0 ? 1.0f + 1e-6f : 1.0f - 1e-6f));
                 if (t0 > t1) { miss = true; break; }
             }
             if (miss) continue;

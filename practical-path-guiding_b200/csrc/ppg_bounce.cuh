@@ -71,9 +71,13 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
         if (alive) {
             ++raysLocal;
             Hit hit;
-            const bool found = bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
+            // a ray with a non-finite origin or direction (a BSDF sample gone wrong) would pass every node's slab test and walk the whole
+            // tree; the reference's kd-tree clips such a ray away (AABB::rayIntersect fails on NaN comparisons): a miss.  Counted in counters[5].
+            const bool rayOk = isfinite(o.x + o.y + o.z) && isfinite(d.x + d.y + d.z);
+            if (!rayOk) atomicAdd(&P.counters[5], 1ull);
+            const bool found = rayOk && bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
             bool cont = found;
-            if (FULL && !found && P.scene.envW) {
+            if (FULL && !found && rayOk && P.scene.envW) {
                 // the ray left the scene: radiance of the environment emitter.  Camera rays and rays that have only crossed index-matched surfaces
                 // take it through the EEmittedRadiance branch (GP:1902-1914: only while unscattered, and not with hideEmitters); after a real
                 // bounce it is the `value` of rayIntersectAndLookForEmitter (GP:2228-2243), always added (MIS weight 1: environment light

@@ -221,7 +221,9 @@ __device__ __noinline__ bool bvh_walk(const Acc &A_, float3 o, float3 d, float m
         nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
         ta = (n0.z - o.z) * inv.z; tb = (n1.z - o.z) * inv.z; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
         nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
-        const float t0 = fmaxf(mint, nearMax - fabsf(nearMax) * 1e-6f), t1 = fminf(fminf(maxt, hit.t), farMin + fabsf(farMin) * 1e-6f);
+        // (multiplicative: `x -+ |x| * 1e-6` is inf - inf = NaN for an infinite bound, which fmaxf / fminf then DROP -- a ray with an exactly
+        // zero direction component was never culled on that axis and walked ~450 000 nodes of KITCHEN: 300 ms for one lane)
+        const float t0 = fmaxf(mint, nearMax * (nearMax > 0.f ? 1.0f - 1e-6f : 1.0f + 1e-6f)), t1 = fminf(fminf(maxt, hit.t), farMin * (farMin > 0.f ? 1.0f + 1e-6f : 1.0f - 1e-6f));
         tEntry = t0;
         return t0 <= t1;
     };

@@ -4,6 +4,8 @@
 #include "../../include/ppg.h"
 #include "ppg_kernels.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -258,6 +260,12 @@ struct ppg_integrator {
     std::string destination;
     int rank = 0, world = 1;
     ppg_allreduce_fn allreduce = nullptr; void *allreduceUser = nullptr;
+    void *ncclComm = nullptr;                              // ncclComm_t when ppg_nccl_init was called: collectives are enqueued on `stream`, no host sync
+    bool multi() const { return world > 1 && (ncclComm || allreduce); }
+    ppg_clock_fn clockFn = nullptr; void *clockUser = nullptr; ppg_film_fn filmFn = nullptr; void *filmUser = nullptr;
+    float clock_s() const { return clockFn ? (float) clockFn(clockUser) : (float) std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - startTime).count() / 1000; }
+    unsigned long long adamProgress[2] = {0, 0};          // [sum steps * |df| * 2^20, sum steps] of the last Adam replay
+    uint64_t lastRecorded = 0;                             // guiding records of the last performRenderPasses (this rank): bounds the growth of the S-tree
 
     // scene
     bool haveScene = false;
@@ -265,7 +273,7 @@ struct ppg_integrator {
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
-    DevBuf<uint32_t> dPixelMap; uint32_t nLocalPixels = 0, minLocalPixels = 0;
+    DevBuf<uint32_t> dPixelMap, dPixelMapPerm; uint32_t nLocalPixels = 0, minLocalPixels = 0, maxLocalPixels = 0;
 
     // film
     DevBuf<float4> dImage, dSqImage, dFilm; DevBuf<float> dRgb; DevBuf<double> dVar;
@@ -273,10 +281,10 @@ struct ppg_integrator {
 
     // SD-tree
     uint32_t capNodes = 0; size_t capPool = 0;
-    DevBuf<uint2> dSnodes; DevBuf<float4> dLeafA; DevBuf<float> dBweight, dSampSum, dSampWeight, dAdam, dAdamDelta, dAdamIterBefore;
+    DevBuf<uint2> dSnodes; DevBuf<float4> dLeafA; DevBuf<float> dBweight, dSampSum, dSampWeight, dAdam, dAdamBefore /* 4 x capNodes: iter, batchAcc, batchGrad, theta before a replay */;
     DevBuf<uint32_t> dAdamCount, dAdamCursor, dAdamOffset; DevBuf<float4> dAdamRecA, dAdamSortA; DevBuf<float2> dAdamRecB, dAdamSortB; size_t adamCap = 0;
     DevBuf<int> dSampDepth, dBuildDepth; DevBuf<uint32_t> dSampCount, dBuildCount, dBuildBase, dScalars /* [0]=nNodes [1]=totalBuild */;
-    DevBuf<uint32_t> dStable;
+    DevBuf<uint32_t> dStable; DevBuf<TreeStats> dTreeStats;
     DevBuf<SampNode> dSamp; DevBuf<uint2> dBchildren; DevBuf<float> dTrain /* bsums | packed tail */;
     uint32_t hNodes = 1; uint32_t hTotalBuild = 1;
     float extent[3];
@@ -309,7 +317,8 @@ struct ppg_integrator {
     std::chrono::steady_clock::time_point startTime;
     ppg_stats stats; uint64_t launches = 0; double deviceMs = 0;
 
-    ~ppg_integrator() {
+    ~ppg_integrator();
+    void destroy_body() {
         for (auto *b : images) delete b;
         for (auto &t : evPool) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
         if (evRender0) cudaEventDestroy(evRender0);
@@ -320,6 +329,7 @@ struct ppg_integrator {
     }
 };
 
+ppg_integrator::~ppg_integrator() { destroy_body(); }
 static float elapsed_s(std::chrono::steady_clock::time_point s) {
     return (float) std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - s).count() / 1000;
 }
@@ -347,10 +357,12 @@ extern "C" int ppg_create(const ppg_params *params, int device, ppg_integrator *
     *out = h;
     return PPG_OK;
 }
+static void release_comm(ppg_integrator *h);
 extern "C" void ppg_destroy(ppg_integrator *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    release_comm(h);
     delete h;
 }
 extern "C" int ppg_set_destination(ppg_integrator *h, const char *destination) {
@@ -362,6 +374,78 @@ extern "C" int ppg_set_allreduce(ppg_integrator *h, ppg_allreduce_fn cb, void *u
 }
 
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }   // tuning experiments only
+
+// ------------------------------------------------------------------ NCCL, resolved at run time (no link-time dependency: single-GPU hosts need no NCCL)
+namespace {
+struct NcclId { char internal[PPG_NCCL_UNIQUE_ID_BYTES]; };                // ncclUniqueId (nccl.h:37-38), passed by value
+struct NcclApi {
+    void *lib = nullptr;
+    int (*getUniqueId)(NcclId *) = nullptr;
+    int (*commInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*allReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*commDestroy)(void *) = nullptr;
+    const char *(*getErrorString)(int) = nullptr;
+};
+static NcclApi *nccl_api() {
+    static NcclApi api; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // a process that already holds NCCL (e.g. PyTorch's bundled copy) gets that one: same soname
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) { api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        if (api.lib) {
+            api.getUniqueId = (int (*)(NcclId *)) dlsym(api.lib, "ncclGetUniqueId");
+            api.commInitRank = (int (*)(void **, int, NcclId, int)) dlsym(api.lib, "ncclCommInitRank");
+            api.allReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t)) dlsym(api.lib, "ncclAllReduce");
+            api.commDestroy = (int (*)(void *)) dlsym(api.lib, "ncclCommDestroy");
+            api.getErrorString = (const char *(*)(int)) dlsym(api.lib, "ncclGetErrorString");
+            if (!api.getUniqueId || !api.commInitRank || !api.allReduce) api.lib = nullptr;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+}  // namespace
+
+static void release_comm(ppg_integrator *h) {
+    if (h->ncclComm) { NcclApi *a = nccl_api(); if (a && a->commDestroy) a->commDestroy(h->ncclComm); h->ncclComm = nullptr; }
+}
+extern "C" int ppg_nccl_unique_id(void *id_out) {
+    NcclApi *a = nccl_api();
+    if (!a || !id_out) return fail(PPG_ERR_COMM, "libnccl.so.2 could not be loaded");
+    NcclId id; const int rc = a->getUniqueId(&id);
+    if (rc != 0) return fail(PPG_ERR_COMM, std::string("ncclGetUniqueId: ") + (a->getErrorString ? a->getErrorString(rc) : "error"));
+    memcpy(id_out, &id, sizeof(id));
+    return PPG_OK;
+}
+extern "C" int ppg_nccl_init(ppg_integrator *h, const void *id, int rank, int world_size) {
+    if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size) return fail(PPG_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    NcclApi *a = nccl_api();
+    if (!a) return fail(PPG_ERR_COMM, "libnccl.so.2 could not be loaded");
+    CK(cudaSetDevice(h->device));
+    release_comm(h);
+    NcclId nid; memcpy(&nid, id, sizeof(nid));
+    void *comm = nullptr;
+    const int rc = a->commInitRank(&comm, world_size, nid, rank);
+    if (rc != 0) return fail(PPG_ERR_COMM, std::string("ncclCommInitRank: ") + (a->getErrorString ? a->getErrorString(rc) : "error"));
+    h->ncclComm = comm;
+    return ppg_set_shard(h, rank, world_size);
+}
+extern "C" int ppg_set_clock(ppg_integrator *h, ppg_clock_fn fn, void *user) { if (!h) return PPG_ERR_INVALID_ARGUMENT; h->clockFn = fn; h->clockUser = user; return PPG_OK; }
+extern "C" int ppg_set_film_callback(ppg_integrator *h, ppg_film_fn fn, void *user) { if (!h) return PPG_ERR_INVALID_ARGUMENT; h->filmFn = fn; h->filmUser = user; return PPG_OK; }
+
+// sum `n` floats in place over all ranks.  NCCL: enqueued on the render stream, nothing waits on the host.  Callback: the stream is drained
+// first and the callback returns once the result is visible in device memory.
+static int allreduce_sum(ppg_integrator *h, float *dev, size_t n) {
+    if (h->world <= 1) return PPG_OK;
+    if (h->ncclComm) {
+        const int rc = nccl_api()->allReduce(dev, dev, n, /* ncclFloat32 */ 7, /* ncclSum */ 0, h->ncclComm, h->stream);
+        if (rc != 0) return fail(PPG_ERR_COMM, "ncclAllReduce failed");
+        return PPG_OK;
+    }
+    if (!h->allreduce) return PPG_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->allreduce(h->allreduceUser, dev, n) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+    return PPG_OK;
+}
 
 static int build_pixel_map(ppg_integrator *h) {
     // 32x32 image blocks (scene.cpp:24), row-major over blocks, interleaved across ranks; row-major inside a block
@@ -382,14 +466,27 @@ static int build_pixel_map(ppg_integrator *h) {
             for (int x = x0; x < std::min(x0 + bs, h->W); ++x) map.push_back((uint32_t) x | ((uint32_t) y << 16));
     }
     h->nLocalPixels = (uint32_t) map.size();
-    h->minLocalPixels = 0xffffffffu;                      // smallest share of any rank: decisions every rank must take alike
+    h->minLocalPixels = 0xffffffffu; h->maxLocalPixels = 0;   // smallest / largest share of any rank: decisions every rank must take alike
     for (int r = 0; r < h->world; ++r) {
         uint64_t c = 0;
         for (int b = r; b < bx * by; b += h->world) { const int x0 = (b % bx) * bs, y0 = (b / bx) * bs; c += (uint64_t) (std::min(x0 + bs, h->W) - x0) * (std::min(y0 + bs, h->H) - y0); }
-        h->minLocalPixels = std::min<uint32_t>(h->minLocalPixels, (uint32_t) c);
+        h->minLocalPixels = std::min<uint32_t>(h->minLocalPixels, (uint32_t) c); h->maxLocalPixels = std::max<uint32_t>(h->maxLocalPixels, (uint32_t) c);
     }
     CK(h->dPixelMap.alloc(std::max<size_t>(map.size(), 1)));
     if (!map.empty()) CK(cudaMemcpy(h->dPixelMap.p, map.data(), map.size() * 4, cudaMemcpyHostToDevice));
+    // A second, scattered order of the same pixels (golden-ratio stride, coprime to the count): any contiguous range of it is spread evenly over
+    // the image.  The sub-batches of a learning iteration (perform_render_passes) take their pixels from it, so that every S-tree leaf receives its
+    // share of every sub-batch -- like the reference, whose worker threads interleave image blocks while the sampling fractions adapt.
+    std::vector<uint32_t> perm(map.size());
+    if (!map.empty()) {
+        const uint64_t n = map.size();
+        uint64_t stride = std::max<uint64_t>(1, (uint64_t) ((double) n * 0.6180339887498949));
+        auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
+        while (gcd(stride, n) != 1) ++stride;
+        for (uint64_t i = 0; i < n; ++i) perm[i] = map[(i * stride) % n];
+    }
+    CK(h->dPixelMapPerm.alloc(std::max<size_t>(perm.size(), 1)));
+    if (!perm.empty()) CK(cudaMemcpy(h->dPixelMapPerm.p, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
     return PPG_OK;
 }
 
@@ -695,7 +792,7 @@ static int ensure_tree_capacity(ppg_integrator *h, uint32_t nodes, size_t pool) 
         const uint32_t cap = std::max<uint32_t>(nodes, std::max<uint32_t>(2 * h->capNodes, 1u << 16));
         CK(h->dSnodes.grow(cap, h->stream)); CK(h->dLeafA.grow(cap, h->stream)); CK(h->dBweight.grow(cap, h->stream));
         CK(h->dSampSum.grow(cap, h->stream)); CK(h->dSampWeight.grow(cap, h->stream)); CK(h->dAdam.grow(6 * (size_t) cap, h->stream));
-        CK(h->dAdamDelta.grow(cap, h->stream)); CK(h->dAdamIterBefore.grow(cap, h->stream)); CK(h->dSampDepth.grow(cap, h->stream));
+        CK(h->dAdamBefore.grow(4 * (size_t) cap, h->stream)); CK(h->dSampDepth.grow(cap, h->stream));
         {   // record-bucket bookkeeping must stay zero between commit launches: reallocate zeroed
             h->dAdamCount.release(); h->dAdamCursor.release(); h->dAdamOffset.release();
             CK(h->dAdamCount.alloc(cap)); CK(h->dAdamCursor.alloc(cap)); CK(h->dAdamOffset.alloc(cap));
@@ -725,7 +822,8 @@ static MaintParams maint(ppg_integrator *h) {
 
 // new STree (GP:1519): one leaf whose sampling tree is a single empty quadtree node
 static int init_tree(ppg_integrator *h) {
-    CK(h->dScalars.alloc(8));
+    CK(h->dScalars.alloc(8)); CK(h->dTreeStats.alloc(1));
+    CK(cudaMemsetAsync(h->dScalars.p, 0, 32, h->stream));
     // buffers persist across renders (cudaMalloc/cudaFree are synchronous and slow): only their contents are reset
     int rc = ensure_tree_capacity(h, std::max<uint32_t>(h->capNodes, 1u << 16), std::max<size_t>(h->capPool, (size_t) 1 << 20));
     if (rc) return rc;
@@ -767,19 +865,14 @@ static int reset_sd_tree(ppg_integrator *h) {
         memCapped = fp / 1000000 >= (size_t) h->prm.sd_tree_max_memory;
     }
     if (!memCapped) {
-        // capacity: the refinement can create at most 2 nodes per threshold worth of recorded weight
-        double totalW = 0;
-        {
-            std::vector<float> w(h->hNodes);
-            CK(cudaMemcpyAsync(w.data(), h->dBweight.p, 4 * (size_t) h->hNodes, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            for (float x : w) totalW += x;
-        }
+        // capacity: the refinement creates at most 2 nodes per threshold worth of recorded weight.  The total weight of the iteration is at most
+        // its number of guiding records (weights <= 1); with several ranks the reduced weights hold about world x this rank's records.
+        const double totalW = 1.25 * (double) h->lastRecorded * h->world + 4096;
         const double est = h->hNodes + 4.0 * totalW / std::max(1.0f, threshold) + 1024;
         int rc = ensure_tree_capacity(h, (uint32_t) std::min<double>(est, 4.0e9), h->capPool);
         if (rc) return rc;
         MaintParams M = maint(h);
-        h->tic(PPG_K_REFINE); stree_refine_kernel<<<1, 1024, 0, h->stream>>>(M, threshold); h->toc(); h->launches++;
+        h->tic(PPG_K_REFINE); stree_refine_kernel<<<1, 1024, 0, h->stream>>>(M, threshold, h->dScalars.p + 5); h->toc(); h->launches++;
     }
     MaintParams M = maint(h);
     const int blocks = h->numSMs * 4;
@@ -787,9 +880,10 @@ static int reset_sd_tree(ppg_integrator *h) {
     dtree_reset_kernel<false><<<blocks, 128, 0, h->stream>>>(M, nullptr, 20, h->prm.d_tree_threshold); h->launches++;
     exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->dBuildCount.p, h->dBuildBase.p, h->dScalars.p, h->dScalars.p + 1); h->launches++;
     h->toc();
-    uint32_t sc[2];
-    CK(cudaMemcpyAsync(sc, h->dScalars.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    uint32_t sc[8];
+    CK(cudaMemcpyAsync(sc, h->dScalars.p, 32, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (sc[5]) return fail(PPG_ERR_CUDA, "S-tree refinement ran out of node capacity");
     h->hNodes = sc[0]; h->hTotalBuild = sc[1];
     int rc = ensure_tree_capacity(h, h->hNodes, std::max<size_t>(h->hTotalBuild, 1));
     if (rc) return rc;
@@ -810,23 +904,22 @@ __global__ void pack_tail_kernel(float *tail, float *bweight, uint32_t n, int di
     }
 }
 static int exchange_training_statistics(ppg_integrator *h) {
-    if (!h->allreduce || h->world <= 1) return PPG_OK;
+    if (!h->multi()) return PPG_OK;
     float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;
     pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->hNodes, 0); h->launches++;
-    CK(cudaStreamSynchronize(h->stream));
-    if (h->allreduce(h->allreduceUser, h->dTrain.p, 4 * (size_t) h->hTotalBuild + (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+    int rc = allreduce_sum(h, h->dTrain.p, 4 * (size_t) h->hTotalBuild + (size_t) h->hNodes); if (rc) return rc;
     pack_tail_kernel<<<h->numSMs, 256, 0, h->stream>>>(tail, h->dBweight.p, h->hNodes, 1); h->launches++;
     return PPG_OK;
 }
 // a host scalar made identical on all ranks (rank 0's value wins): time-based decisions must not diverge
 static int sync_scalar(ppg_integrator *h, float *v) {
-    if (!h->allreduce || h->world <= 1) return PPG_OK;
+    if (!h->multi()) return PPG_OK;
     float *slot = h->dTrain.p + h->dTrain.n - 16;
     const float mine = h->rank == 0 ? *v : 0.f;
     CK(cudaMemcpyAsync(slot, &mine, 4, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce_sum(h, slot, 1); if (rc) return rc;
+    CK(cudaMemcpyAsync(v, slot, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (h->allreduce(h->allreduceUser, slot, 1) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
-    CK(cudaMemcpy(v, slot, 4, cudaMemcpyDeviceToHost));
     return PPG_OK;
 }
 
@@ -837,44 +930,28 @@ static int build_sd_tree(ppg_integrator *h, ppg_iteration_stats &st) {
     MaintParams M = maint(h);
     h->tic(PPG_K_BUILD); dtree_build_kernel<<<h->numSMs * 4, 128, 0, h->stream>>>(M, h->dBuildBase.p); h->toc(); h->launches++;
     CK(cudaGetLastError());
-    // "Distribution statistics" (GP:1121-1186) on the host, in node order like forEachDTreeWrapperConst
-    const uint32_t n = h->hNodes;
-    std::vector<uint2> sn(n); std::vector<float> ssum(n), sw(n); std::vector<int> sd(n); std::vector<uint32_t> scnt(n);
-    CK(cudaMemcpyAsync(sn.data(), h->dSnodes.p, sizeof(uint2) * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(ssum.data(), h->dSampSum.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(sw.data(), h->dSampWeight.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(sd.data(), h->dSampDepth.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(scnt.data(), h->dSampCount.p, 4 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+    // "Distribution statistics" (GP:1121-1186): reduced on the device, 64 bytes come back
+    CK(cudaMemsetAsync(h->dTreeStats.p, 0, sizeof(TreeStats), h->stream));
+    tree_stats_kernel<<<1, 1024, 0, h->stream>>>(M, h->dTreeStats.p); h->launches++;
+    TreeStats ts;
+    CK(cudaMemcpyAsync(&ts, h->dTreeStats.p, sizeof(ts), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream)); h->resolve_timers();
-    int maxDepth = 0, minDepth = std::numeric_limits<int>::max(); float avgDepth = 0;
-    float maxR = 0, minR = std::numeric_limits<float>::max(), avgR = 0;
-    size_t maxN = 0, minN = std::numeric_limits<size_t>::max(); float avgN = 0;
-    float maxW = 0, minW = std::numeric_limits<float>::max(), avgW = 0;
-    int nPoints = 0, nPointsNodes = 0; uint32_t leaves = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        if (sn[i].x != 0u) continue;
-        ++leaves;
-        const int depth = sd[i];
-        maxDepth = std::max(maxDepth, depth); minDepth = std::min(minDepth, depth); avgDepth += depth;
-        float mean = 0; if (sw[i] != 0) { const float factor = 1 / (3.14159265358979323846f * 4 * sw[i]); mean = factor * ssum[i]; }
-        maxR = std::max(maxR, mean); minR = std::min(minR, mean); avgR += mean;
-        if (scnt[i] > 1) { const size_t nodes = scnt[i]; maxN = std::max(maxN, nodes); minN = std::min(minN, nodes); avgN += nodes; ++nPointsNodes; }
-        maxW = std::max(maxW, sw[i]); minW = std::min(minW, sw[i]); avgW += sw[i];
-        ++nPoints;
-    }
+    const uint32_t n = h->hNodes;
+    const int nPoints = (int) ts.leaves, nPointsNodes = (int) ts.leavesWithNodes;
+    float avgDepth = (float) ts.depthSum, avgR = (float) ts.meanSum, avgN = (float) ts.nodesSum, avgW = (float) ts.weightSum;
     if (nPoints > 0) { avgDepth /= nPoints; avgR /= nPoints; if (nPointsNodes > 0) avgN /= nPointsNodes; avgW /= nPoints; }
-    st.depth_min = minDepth; st.depth_max = maxDepth; st.depth_avg = avgDepth;
-    st.mean_radiance_min = minR; st.mean_radiance_avg = avgR; st.mean_radiance_max = maxR;
-    st.nodes_min = minN; st.nodes_max = maxN; st.nodes_avg = avgN;
-    st.weight_min = minW; st.weight_avg = avgW; st.weight_max = maxW;
-    st.s_tree_nodes = n; st.s_tree_leaves = leaves;
+    st.depth_min = nPoints ? ts.depthMin : std::numeric_limits<int>::max(); st.depth_max = ts.depthMax; st.depth_avg = avgDepth;
+    st.mean_radiance_min = nPoints ? ts.meanMin : std::numeric_limits<float>::max(); st.mean_radiance_avg = avgR; st.mean_radiance_max = ts.meanMax;
+    st.nodes_min = nPointsNodes ? ts.nodesMin : std::numeric_limits<size_t>::max(); st.nodes_max = ts.nodesMax; st.nodes_avg = avgN;
+    st.weight_min = nPoints ? ts.weightMin : std::numeric_limits<float>::max(); st.weight_avg = avgW; st.weight_max = ts.weightMax;
+    st.s_tree_nodes = n; st.s_tree_leaves = ts.leaves;
     h->isBuilt = true;
     return PPG_OK;
 }
 
 // ------------------------------------------------------------------ wavefront buffers
 static int ensure_wavefront(ppg_integrator *h) {
-    const size_t perPass = (size_t) h->nLocalPixels * h->prm.spp_per_pass;
+    const size_t perPass = (size_t) h->maxLocalPixels * h->prm.spp_per_pass;       // the largest share of any rank: every rank splits an iteration into the same batches
     h->maxBounces = h->prm.max_depth > 0 ? h->prm.max_depth : 64;
     h->nSlabs = std::max(1, h->maxBounces - 1);
     const bool nee = h->useNee();
@@ -897,7 +974,18 @@ static int ensure_wavefront(ppg_integrator *h) {
         CK(h->dSlabs.alloc((size_t) h->nSlabs * (full ? 6 : 3) * cap * slabSets));
         h->pathCapacity = cap; h->stateVecs = stateVecs; h->slabSets = slabSets;
     }
-    CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dWork.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(4));
+    CK(h->dLive.alloc(h->maxBounces + 2)); CK(h->dWork.alloc(h->maxBounces + 2)); CK(h->dCounters.alloc(8));
+    if (h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) {
+        // sampling-fraction records: one per (recorded vertex, leaf) pair.  Sized once for the largest wavefront with 16 records per path (mean path
+        // lengths of the bundled scenes: 4 - 9 vertices; the spatial box filter touches ~2 leaves per vertex); a record beyond it is dropped and
+        // counted in ppg_stats.dropped_records.  Allocating per batch (cudaMalloc / cudaFree are synchronous) cost 11 ms per sub-batch.
+        const size_t want = cap * 16 * (h->prm.spatial_filter == PPG_SFILTER_BOX ? 2 : 1);
+        if (want > h->adamCap) {
+            h->dAdamRecA.release(); h->dAdamRecB.release(); h->dAdamSortA.release(); h->dAdamSortB.release();
+            CK(h->dAdamRecA.alloc(want)); CK(h->dAdamRecB.alloc(want)); CK(h->dAdamSortA.alloc(want)); CK(h->dAdamSortB.alloc(want));
+            h->adamCap = want;
+        }
+    }
     // persistent grids: resident blocks per SM from the occupancy calculator
     int occ = 0;
     if (h->sceneSmemBytes) occ = h->fullFeature ? ppg_bounce_occupancy_11(h->sceneSmemBytes) : ppg_bounce_occupancy_10(h->sceneSmemBytes);
@@ -933,96 +1021,106 @@ static void launch_bounce(ppg_integrator *h, const RenderParams &P, bool first, 
     h->launches++;
 }
 
-// one batch of `nPasses` passes as a single wavefront
-// one batch of `nPasses` passes as a single wavefront, over this rank's pixels [pixel0, pixel0 + pixelCount) of the pixel map
-static int render_batch(ppg_integrator *h, int nPasses, uint32_t pixel0, uint32_t pixelCount) {
+// one batch of `nPasses` passes as a single wavefront, over `pixelCount` of this rank's pixels taken from `pixelMap` (a range of the block-ordered
+// map or of its scattered permutation).  A rank without pixels in the batch still takes part in the collective of the Adam replay.
+static int render_batch(ppg_integrator *h, int nPasses, const uint32_t *pixelMap, uint32_t pixelCount) {
     const uint32_t nPaths = (uint32_t) ((size_t) nPasses * pixelCount * h->prm.spp_per_pass);
-    if (nPaths == 0) return PPG_OK;
     const int record = h->isFinalIter ? 0 : h->recordMode;
-    CK(cudaMemsetAsync(h->dLive.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
-    CK(cudaMemsetAsync(h->dWork.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
-    CK(cudaMemcpyAsync(h->dLive.p, &nPaths, 4, cudaMemcpyHostToDevice, h->stream));
-    RenderParams P;
-    P.scene = h->sceneView; P.cam = h->cam; P.tree = tree_view(h);
-    P.liFinal = h->dLiFinal.p; P.pixelMap = h->dPixelMap.p + pixel0; P.counters = h->dCounters.p;
-    P.nPaths = nPaths; P.nLocalPixels = pixelCount; P.spp = (uint32_t) h->prm.spp_per_pass;
-    P.passBase = (uint64_t) h->passesRendered; P.seed = h->prm.seed;
-    P.maxDepth = h->prm.max_depth; P.rrDepth = h->prm.rr_depth; P.strictNormals = h->prm.strict_normals; P.hideEmitters = h->prm.hide_emitters;
-    P.isBuilt = h->isBuilt ? 1 : 0; P.lossMode = h->prm.bsdf_sampling_fraction_loss; P.fixedFraction = h->prm.bsdf_sampling_fraction;
-    P.sceneSmemBytes = h->sceneSmemBytes;
     const bool nee = h->useNee();                      // the NEE kernels also carry the MIS state when doNee is off (kickstart after 128 spp)
-    P.neeMode = h->prm.nee; P.doNee = (nee && h->doNee) ? 1 : 0; P.training = record != 0 ? 1 : 0;
-    PathState A = path_state(h->dStateA.p, h->pathCapacity, nee), B = path_state(h->dStateB.p, h->pathCapacity, nee);
-    const int bb = h->sceneSmemBytes ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM;
-    const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + bb - 1) / bb));
-    int lastDepth = 0;
-    for (int depth = 1; depth <= h->maxBounces; ++depth) {
-        P.depth = depth; P.in = (depth & 1) ? B : A; P.out = (depth & 1) ? A : B;
-        P.liveIn = h->dLive.p + (depth - 1); P.liveOut = h->dLive.p + depth; P.work = h->dWork.p + depth;
-        const int k = std::min(depth - 1, h->nSlabs - 1);
-        P.slab = slab_at(h, k);
-        if (nee) { P.neeSlab = slab_at(h, k, 1); P.prevSlab = slab_at(h, std::max(k - 1, 0)); if (depth - 1 >= h->nSlabs) P.prevSlab = slab_at(h, h->nSlabs - 1); }
-        const int rec = (depth - 1 < h->nSlabs) ? record : 0;
-        h->tic(PPG_K_BOUNCE);
-        launch_bounce(h, P, depth == 1, rec, grid, nee);
-        h->toc();
-        lastDepth = depth;
-    }
-    {   // survivors of the bounce cap (maxDepth == -1 only)
-        const PathState last = (lastDepth & 1) ? A : B;
-        flush_kernel<<<std::max(grid / 4, 1), PPG_BLOCK, 0, h->stream>>>(last, h->dLive.p + lastDepth, h->dLiFinal.p); h->launches++;
-    }
-    if (record) {
-        CommitParams C;
-        C.tree = tree_view(h); C.slab0 = slab_at(h, 0); C.slabStride = h->pathCapacity; C.liveCounts = h->dLive.p; C.liFinal = h->dLiFinal.p;
-        C.spatialFilter = h->prm.spatial_filter; C.directionalFilter = h->prm.directional_filter;
-        C.lossMode = h->isBuilt ? h->prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE;       // GP:2152
-        C.statisticalWeight = (h->prm.nee == PPG_NEE_KICKSTART && h->doNee && nee) ? 0.5f : 1.0f;   // GP:2152
-        C.seed = h->prm.seed; C.snodes = h->dSnodes.p; C.nSlabs = (uint32_t) h->nSlabs;
-        const bool neeSlabs = nee && h->doNee && h->prm.nee != PPG_NEE_ALWAYS;
-        C.nee0 = neeSlabs ? slab_at(h, 0, 1) : C.slab0;
-        const bool useAdam = C.lossMode != PPG_LOSS_NONE;
-        if (useAdam) {
-            // one record per (vertex, leaf) pair; the spatial box filter touches several leaves per vertex (records beyond the capacity are dropped)
-            const size_t want = (size_t) nPaths * h->nSlabs * (h->prm.spatial_filter == PPG_SFILTER_BOX ? 2 : 1) * (neeSlabs ? 2 : 1);
-            if (want > h->adamCap) {
-                h->dAdamRecA.release(); h->dAdamRecB.release(); h->dAdamSortA.release(); h->dAdamSortB.release();
-                CK(h->dAdamRecA.alloc(want)); CK(h->dAdamRecB.alloc(want)); CK(h->dAdamSortA.alloc(want)); CK(h->dAdamSortB.alloc(want));
-                h->adamCap = want;
-            }
-            CK(cudaMemsetAsync(h->dScalars.p + 3, 0, 4, h->stream));
-        }
-        C.adamRecA = h->dAdamRecA.p; C.adamRecB = h->dAdamRecB.p; C.adamTotal = h->dScalars.p + 3; C.adamCap = (uint32_t) std::min<size_t>(h->adamCap, 0xFFFFFFFFu);
-        dim3 g(std::min<int>(h->gridCommit, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK)), h->nSlabs * (neeSlabs ? 2 : 1));
-        h->tic(PPG_K_COMMIT);
-        if (record == 1) commit_kernel<1><<<g, PPG_BLOCK, 0, h->stream>>>(C); else commit_kernel<2><<<g, PPG_BLOCK, 0, h->stream>>>(C);
-        h->toc(); h->launches++;
-        if (useAdam) {
-            // replay the sampling-fraction records leaf by leaf (see adam_seq_kernel)
-            MaintParams M = maint(h);
-            const bool multi = h->allreduce && h->world > 1;
-            float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;       // [6 x nNodes] exchange area (the building weights are packed there only at iteration end)
-            h->tic(PPG_K_ADAM);
-            adam_hist_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dAdamRecA.p, h->dScalars.p + 3, (uint32_t) h->adamCap, h->dAdamCount.p); h->launches++;
-            exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->dAdamCount.p, h->dAdamOffset.p, h->dScalars.p, h->dScalars.p + 4); h->launches++;
-            adam_scatter_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dAdamRecA.p, h->dAdamRecB.p, h->dScalars.p + 3, (uint32_t) h->adamCap, h->dAdamOffset.p,
-                                                                      h->dAdamCursor.p, h->dAdamSortA.p, h->dAdamSortB.p); h->launches++;
-            adam_seq_kernel<<<h->numSMs * 4, 128, 0, h->stream>>>(M, h->dAdamSortA.p, h->dAdamSortB.p, h->dAdamOffset.p, h->dAdamCount.p, h->dAdamCursor.p,
-                                                                  C.lossMode == PPG_LOSS_KL ? 1.0f : 2.0f, multi ? h->dAdamDelta.p : nullptr); h->launches++;
+    const int lossMode = (record && h->isBuilt) ? h->prm.bsdf_sampling_fraction_loss : PPG_LOSS_NONE;       // GP:2152
+    const bool useAdam = lossMode != PPG_LOSS_NONE;
+    const bool neeSlabs = nee && h->doNee && h->prm.nee != PPG_NEE_ALWAYS;
+    if (useAdam) CK(cudaMemsetAsync(h->dScalars.p + 3, 0, 4, h->stream));      // record cursor (buffers: ensure_wavefront)
+    if (nPaths) {
+        CK(cudaMemsetAsync(h->dLive.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
+        CK(cudaMemsetAsync(h->dWork.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
+        CK(cudaMemcpyAsync(h->dLive.p, &nPaths, 4, cudaMemcpyHostToDevice, h->stream));
+        RenderParams P;
+        P.scene = h->sceneView; P.cam = h->cam; P.tree = tree_view(h);
+        P.liFinal = h->dLiFinal.p; P.pixelMap = pixelMap; P.counters = h->dCounters.p;
+        P.nPaths = nPaths; P.nLocalPixels = pixelCount; P.spp = (uint32_t) h->prm.spp_per_pass;
+        P.passBase = (uint64_t) h->passesRendered; P.seed = h->prm.seed;
+        P.maxDepth = h->prm.max_depth; P.rrDepth = h->prm.rr_depth; P.strictNormals = h->prm.strict_normals; P.hideEmitters = h->prm.hide_emitters;
+        P.isBuilt = h->isBuilt ? 1 : 0; P.lossMode = h->prm.bsdf_sampling_fraction_loss; P.fixedFraction = h->prm.bsdf_sampling_fraction;
+        P.sceneSmemBytes = h->sceneSmemBytes;
+        P.neeMode = h->prm.nee; P.doNee = (nee && h->doNee) ? 1 : 0; P.training = record != 0 ? 1 : 0;
+        PathState A = path_state(h->dStateA.p, h->pathCapacity, nee), B = path_state(h->dStateB.p, h->pathCapacity, nee);
+        const int bb = h->sceneSmemBytes ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM;
+        const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + bb - 1) / bb));
+        int lastDepth = 0;
+        for (int depth = 1; depth <= h->maxBounces; ++depth) {
+            P.depth = depth; P.in = (depth & 1) ? B : A; P.out = (depth & 1) ? A : B;
+            P.liveIn = h->dLive.p + (depth - 1); P.liveOut = h->dLive.p + depth; P.work = h->dWork.p + depth;
+            const int k = std::min(depth - 1, h->nSlabs - 1);
+            P.slab = slab_at(h, k);
+            if (nee) { P.neeSlab = slab_at(h, k, 1); P.prevSlab = slab_at(h, std::max(k - 1, 0)); if (depth - 1 >= h->nSlabs) P.prevSlab = slab_at(h, h->nSlabs - 1); }
+            const int rec = (depth - 1 < h->nSlabs) ? record : 0;
+            if (h->cancelled.load()) return PPG_ERR_CANCELLED;                 // Integrator::cancel() (GP:1643-1648): the batch in flight is dropped
+            h->tic(PPG_K_BOUNCE);
+            launch_bounce(h, P, depth == 1, rec, grid, nee);
             h->toc();
-            if (multi) {
-                // replicas replayed their own records from the common state: average them (parameter averaging) so that all ranks continue identically
-                adam_pack_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, tail, h->dAdamIterBefore.p, h->dAdamDelta.p, 1); h->launches++;
+            lastDepth = depth;
+            // unbounded path length (maxDepth == -1 runs up to the 64-bounce cap): stop launching once the wavefront is empty.  One tiny
+            // read-back at a few depths; the stream is busy with the launches queued before it, so the host only waits where it would anyway.
+            const bool small = nPaths <= 65536u;          // small wavefronts are launch bound: look every 4 bounces
+            if ((h->prm.max_depth <= 0 || small) && depth < h->maxBounces &&
+                (depth == 8 || depth == 12 || depth == 16 || depth == 24 || depth == 32 || depth == 48 || (small && depth >= 4 && depth % 4 == 0))) {
+                uint32_t live = 1;
+                CK(cudaMemcpyAsync(&live, h->dLive.p + depth, 4, cudaMemcpyDeviceToHost, h->stream));
                 CK(cudaStreamSynchronize(h->stream));
-                if (h->allreduce(h->allreduceUser, tail, 6 * (size_t) h->hNodes) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
-                adam_merge_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, tail, h->dAdamIterBefore.p, 1.0f / (float) h->world); h->launches++;
+                if (live == 0) break;
             }
         }
+        {   // survivors of the bounce cap (maxDepth == -1 only) keep the radiance they have; they are counted (ppg_stats.truncated_paths)
+            const PathState last = (lastDepth & 1) ? A : B;
+            flush_kernel<<<std::max(grid / 4, 1), PPG_BLOCK, 0, h->stream>>>(last, h->dLive.p + lastDepth, h->dLiFinal.p, h->dCounters.p + 3); h->launches++;
+        }
+        if (record) {
+            CommitParams C;
+            C.tree = tree_view(h); C.slab0 = slab_at(h, 0); C.slabStride = h->pathCapacity; C.liveCounts = h->dLive.p; C.liFinal = h->dLiFinal.p;
+            C.spatialFilter = h->prm.spatial_filter; C.directionalFilter = h->prm.directional_filter;
+            C.lossMode = lossMode;
+            C.statisticalWeight = (h->prm.nee == PPG_NEE_KICKSTART && h->doNee && nee) ? 0.5f : 1.0f;   // GP:2152
+            C.seed = h->prm.seed; C.snodes = h->dSnodes.p; C.nSlabs = (uint32_t) std::min(h->nSlabs, lastDepth);
+            C.nee0 = neeSlabs ? slab_at(h, 0, 1) : C.slab0;
+            C.adamRecA = h->dAdamRecA.p; C.adamRecB = h->dAdamRecB.p; C.adamTotal = h->dScalars.p + 3; C.adamCap = (uint32_t) std::min<size_t>(h->adamCap, 0xFFFFFFFFu);
+            C.dropped = h->dCounters.p + 4;
+            dim3 g(std::min<int>(h->gridCommit, (int) ((nPaths + PPG_BLOCK - 1) / PPG_BLOCK)), C.nSlabs * (neeSlabs ? 2 : 1));
+            h->tic(PPG_K_COMMIT);
+            if (record == 1) commit_kernel<1><<<g, PPG_BLOCK, 0, h->stream>>>(C); else commit_kernel<2><<<g, PPG_BLOCK, 0, h->stream>>>(C);
+            h->toc(); h->launches++;
+        }
+        h->tic(PPG_K_FILM);
+        film_kernel<<<std::min<int>(h->numSMs * 8, (int) ((pixelCount + PPG_BLOCK - 1) / PPG_BLOCK)), PPG_BLOCK, 0, h->stream>>>(
+            h->dLiFinal.p, pixelMap, pixelCount, (uint32_t) h->prm.spp_per_pass, (uint32_t) nPasses, h->W, h->dImage.p, h->dSqImage.p);
+        h->toc(); h->launches++;
     }
-    h->tic(PPG_K_FILM);
-    film_kernel<<<std::min<int>(h->numSMs * 8, (int) ((pixelCount + PPG_BLOCK - 1) / PPG_BLOCK)), PPG_BLOCK, 0, h->stream>>>(
-        h->dLiFinal.p, h->dPixelMap.p + pixel0, pixelCount, (uint32_t) h->prm.spp_per_pass, (uint32_t) nPasses, h->W, h->dImage.p, h->dSqImage.p);
-    h->toc(); h->launches++;
+    if (useAdam) {
+        // replay the sampling-fraction records leaf by leaf (see adam_seq_kernel)
+        MaintParams M = maint(h);
+        const bool multi = h->multi();
+        float *tail = h->dTrain.p + 4 * (size_t) h->hTotalBuild;       // [6 x nNodes] exchange area (the building weights are packed there only at iteration end)
+        adam_pack_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, tail, h->dAdamBefore.p, nullptr, 0); h->launches++;
+        h->tic(PPG_K_ADAM);
+        adam_hist_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dAdamRecA.p, h->dScalars.p + 3, (uint32_t) h->adamCap, h->dAdamCount.p); h->launches++;
+        exclusive_scan_kernel<<<1, 1024, 0, h->stream>>>(h->dAdamCount.p, h->dAdamOffset.p, h->dScalars.p, h->dScalars.p + 4); h->launches++;
+        adam_scatter_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dAdamRecA.p, h->dAdamRecB.p, h->dScalars.p + 3, (uint32_t) h->adamCap, h->dAdamOffset.p,
+                                                                  h->dAdamCursor.p, h->dAdamSortA.p, h->dAdamSortB.p); h->launches++;
+        adam_seq_kernel<<<h->numSMs * 16, 128, 0, h->stream>>>(M, h->dAdamSortA.p, h->dAdamSortB.p, h->dAdamOffset.p, h->dAdamCount.p, h->dAdamCursor.p,
+                                                              lossMode == PPG_LOSS_KL ? 1.0f : 2.0f); h->launches++;
+        h->toc();
+        if (multi) {
+            // replicas replayed their own records from the common state: merge them (step counts and batch accumulators add up relative to
+            // the common start, moments and the variable are averaged) so that all ranks continue identically
+            adam_pack_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, tail, h->dAdamBefore.p, nullptr, 1); h->launches++;
+            int rc = allreduce_sum(h, tail, 6 * (size_t) h->hNodes); if (rc) return rc;
+            adam_merge_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, tail, h->dAdamBefore.p, 1.0f / (float) h->world, (float) (h->world - 1)); h->launches++;
+        }
+        // movement of the fractions in this replay (identical on all ranks after the merge): steers the size of the next sub-batch
+        CK(cudaMemsetAsync(h->dCounters.p + 6, 0, 16, h->stream));
+        adam_progress_kernel<<<h->numSMs, 256, 0, h->stream>>>(M, h->dAdamBefore.p, h->dCounters.p + 6); h->launches++;
+        CK(cudaMemcpyAsync(h->adamProgress, h->dCounters.p + 6, 16, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaGetLastError());
     return PPG_OK;
 }
@@ -1032,77 +1130,98 @@ static int perform_render_passes(ppg_integrator *h, float &variance, int numPass
     const size_t npx = (size_t) h->W * h->H;
     CK(cudaMemsetAsync(h->dImage.p, 0, sizeof(float4) * npx, h->stream));
     CK(cudaMemsetAsync(h->dSqImage.p, 0, sizeof(float4) * npx, h->stream));
-    CK(cudaMemsetAsync(h->dCounters.p, 0, 32, h->stream));
+    CK(cudaMemsetAsync(h->dCounters.p, 0, 64, h->stream));
     const auto t0 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(h->evA, h->stream));
     const size_t perPass = (size_t) h->nLocalPixels * h->prm.spp_per_pass;
-    const int maxBatch = (int) std::max<size_t>(1, perPass ? h->pathCapacity / perPass : 1);
+    const size_t perPassMax = (size_t) h->maxLocalPixels * h->prm.spp_per_pass;                 // rank independent
+    const int maxBatch = (int) std::max<size_t>(1, perPassMax ? h->pathCapacity / perPassMax : 1);
+    // Sampling-fraction learning (GP:672-697).  The reference takes an optimiser step after every ~2 records WHILE the passes run, so the
+    // fractions that guide the paths follow the optimiser with a lag of a few paths.  A wavefront samples all its paths with the fractions
+    // it starts with; the Adam replay after it (adam_seq_kernel) then takes every step the reference would.  To bound that staleness a
+    // learning iteration is rendered as a sequence of sub-batches (first fractions of a pass in the scattered pixel order, later whole passes)
+    // whose size follows a step-size control: see `target` below.  All quantities that shape the sequence are identical on every rank.
+    const bool learning = h->isBuilt && !h->isFinalIter && h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE;
+    // Step-size control: after every replay the device reports how far the fractions moved (steps-weighted mean |df|).  The next sub-batch is sized
+    // so that the fractions move by about `target` during it: that movement IS the staleness of the fractions a wavefront samples with.
+    // Measured on SPACESHIP 640x360 (recorded vertices of iterations 1-4 against the oracle, which learns online like the reference; the oracle's
+    // own run-to-run spread is ~0.5 %): target 0.005 -> +0.2 % (2200 sub-batches), 0.01 -> +0.4 % (1130), 0.02 -> +1.2 % (223), 0.04 -> +4 % (58).
+    static const double target = std::max(env_int("PPG_LOSS_TARGET_X1000", 20), 1) * 1e-3;
+    static const double growthMax = std::max(env_int("PPG_LOSS_GROWTH_MAX_PCT", 100), 1) * 0.01;
+    static const double leafPaths = std::max(env_int("PPG_LOSS_LEAF_PATHS_X10", 40), 1) * 0.1;   // paths per S-tree leaf in the first sub-batch
+    const double pathsPerPass = (double) npx * h->prm.spp_per_pass;                                  // whole image
+    const double minFrac = std::min(1.0, std::max(256.0, leafPaths * 0.5 * (h->hNodes + 1)) / std::max(pathsPerPass, 1.0));
+    double done = 0.0, frac = 0.0;          // passes rendered in this call (real number), fraction of the pass in progress
+    double want = learning ? minFrac : (double) maxBatch, lastSize = 0.0;
     int local = 0; int rcode = PPG_OK;
     while (local < numPasses) {
-        int nb = std::min(maxBatch, numPasses - local);
-        // the sampling fraction is learned between pass-batches (theta is constant inside a wavefront): start with small batches
-        if (h->isBuilt && !h->isFinalIter && h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE) nb = std::min(nb, std::max(1, local / 2));
-        // ... and split the first passes of the iteration into pixel sub-batches: the reference updates theta after every ~2 records
-        // WHILE a pass runs (GP:672-697), so its first guided pass already adapts; one wavefront per pass would render it with stale
-        // fractions (visible against the authors' SPACESHIP log as -5 % recorded vertices in iteration 1).  8 / 4 / 2 stripes of
-        // the block-ordered pixel map for passes 0 / 1 / 2; every rank makes the same number of calls (Adam replicas are averaged per call).
-        int rc = PPG_OK;
-        static const int subMax = std::max(env_int("PPG_LOSS_SUBBATCH", 8), 1);
-        const bool learning = h->isBuilt && !h->isFinalIter && h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE;
-        const int K = (learning && nb == 1 && local < 3) ? std::max(subMax >> local, 1) : 1;
-        if (K > 1 && h->minLocalPixels >= (uint32_t) K * 1024u) {
-            for (int k = 0; k < K && !rc; ++k) {
-                const uint32_t p0 = (uint32_t) ((uint64_t) h->nLocalPixels * k / K), p1 = (uint32_t) ((uint64_t) h->nLocalPixels * (k + 1) / K);
-                rc = render_batch(h, 1, p0, p1 - p0);
-            }
-        } else rc = render_batch(h, nb, 0, h->nLocalPixels);
+        int rc = PPG_OK; int nb = 0;
+        if (learning && lastSize > 0.0) {
+            CK(cudaStreamSynchronize(h->stream));                       // the progress read-back of the batch just issued
+            const double moved = h->adamProgress[1] ? (double) h->adamProgress[0] / 1048576.0 / (double) h->adamProgress[1] : 0.0;
+            const double ratio = moved > 0.0 ? target / moved : 2.0;
+            want = lastSize * std::min(2.0, std::max(0.5, ratio));
+            want = std::max(minFrac, std::min(want, std::max(minFrac, growthMax * done)));
+            ++h->stats.sub_batches;
+        }
+        if (frac > 0.0 || want < 1.0) {
+            // a slice [frac, f1) of one pass, in the scattered pixel order
+            double f1 = std::min(1.0, frac + want);
+            if (1.0 - f1 < 0.5 * want) f1 = 1.0;                       // no tiny remainder
+            const uint32_t p0 = (uint32_t) std::llround(frac * h->nLocalPixels), p1 = f1 >= 1.0 ? h->nLocalPixels : (uint32_t) std::llround(f1 * h->nLocalPixels);
+            rc = render_batch(h, 1, h->dPixelMapPerm.p + p0, p1 - p0);
+            lastSize = f1 - frac; done += f1 - frac; frac = f1;
+            if (frac >= 1.0) { frac = 0.0; nb = 1; }
+        } else {
+            nb = std::min(std::min(maxBatch, numPasses - local), std::max(1, (int) want));
+            rc = render_batch(h, nb, h->dPixelMap.p, h->nLocalPixels);
+            lastSize = nb; done += nb;
+        }
+        if (rc == PPG_ERR_CANCELLED) { rcode = rc; break; }
         if (rc) return rc;
         h->passesRendered += nb; local += nb;
+        if (h->cancelled.load()) { rcode = PPG_ERR_CANCELLED; break; }
+        if (nb == 0) continue;
         bool shouldAbort = false;
         if (h->prm.budget_type == PPG_BUDGET_SECONDS) {              // GP:1259-1262, checked per batch
             CK(cudaStreamSynchronize(h->stream));
-            float el = elapsed_s(h->startTime);
+            float el = h->clock_s();
             rc = sync_scalar(h, &el); if (rc) return rc;
             shouldAbort = (int) el > h->prm.budget;
         }
-        if (h->cancelled.load()) { rcode = PPG_ERR_CANCELLED; shouldAbort = true; }
         if (shouldAbort) break;
     }
     add_image_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dFilm.p, h->dImage.p, npx); h->launches++;   // film->put(block), renderproc.cpp:143-151
-    if (h->prm.sample_combination == PPG_COMB_INVERSEVAR) {            // GP:1292-1296: keep the iteration's image
-        DevBuf<float4> *img = new DevBuf<float4>();
-        CK(img->alloc(npx));
-        CK(cudaMemcpyAsync(img->p, h->dImage.p, sizeof(float4) * npx, cudaMemcpyDeviceToDevice, h->stream));
-        h->images.push_back(img);
-        if (h->images.size() > 4) { delete h->images.front(); h->images.erase(h->images.begin()); }
+    if (h->prm.sample_combination == PPG_COMB_INVERSEVAR) {            // GP:1292-1296: keep the iteration's image (ring of the last four)
+        if (h->images.size() < 4) { DevBuf<float4> *img = new DevBuf<float4>(); CK(img->alloc(npx)); h->images.push_back(img); }
+        else std::rotate(h->images.begin(), h->images.begin() + 1, h->images.end());
+        CK(cudaMemcpyAsync(h->images.back()->p, h->dImage.p, sizeof(float4) * npx, cudaMemcpyDeviceToDevice, h->stream));
     }
-    // variance, GP:1298-1319
+    // variance, GP:1298-1319: the numerator is reduced on the device (double), summed over ranks as a float, and read back together with the counters
     const int N = local * h->prm.spp_per_pass;
     CK(cudaMemsetAsync(h->dVar.p, 0, 8, h->stream));
     if (h->nLocalPixels)
         variance_kernel<<<std::min<int>(h->numSMs * 4, (int) ((h->nLocalPixels + PPG_BLOCK - 1) / PPG_BLOCK)), PPG_BLOCK, 0, h->stream>>>(
             h->dImage.p, h->dSqImage.p, h->dPixelMap.p, h->nLocalPixels, h->W, (float) N, h->dVar.p);
     h->launches++;
-    double num = 0; unsigned long long cnt[4];
-    CK(cudaMemcpyAsync(&num, h->dVar.p, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(cnt, h->dCounters.p, 32, cudaMemcpyDeviceToHost, h->stream));
+    float *slot = h->dTrain.p + h->dTrain.n - 16;
+    double_to_float_kernel<<<1, 1, 0, h->stream>>>(h->dVar.p, slot); h->launches++;
+    if (h->multi()) { int rc = allreduce_sum(h, slot, 1); if (rc) return rc; }
+    float numF = 0; unsigned long long cnt[8];
+    CK(cudaMemcpyAsync(&numF, slot, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cnt, h->dCounters.p, 64, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(h->evB, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     float ms = 0; cudaEventElapsedTime(&ms, h->evA, h->evB); h->deviceMs += ms;
     h->resolve_timers();
-    if (h->allreduce && h->world > 1) {
-        float *slot = h->dTrain.p + h->dTrain.n - 16;
-        const float mine = (float) num;
-        CK(cudaMemcpy(slot, &mine, 4, cudaMemcpyHostToDevice));
-        if (h->allreduce(h->allreduceUser, slot, 1) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
-        float total = 0; CK(cudaMemcpy(&total, slot, 4, cudaMemcpyDeviceToHost)); num = total;
-    }
-    variance = (float) (num / ((double) h->W * h->H * (N - 1)));
+    variance = (float) ((double) numF / ((double) h->W * h->H * (N - 1)));
     if (h->prm.sample_combination == PPG_COMB_INVERSEVAR) { h->variances.push_back(variance); if (h->variances.size() > 4) h->variances.erase(h->variances.begin()); }
     st.seconds += elapsed_s(t0); st.passes += local; st.variance = variance; st.total_passes = h->passesRendered;
     st.vertices += cnt[0]; st.paths += (uint64_t) local * perPass; st.recorded_vertices += cnt[1];
     if (cnt[1]) st.s_tree_depth_avg = (double) cnt[2] / (double) cnt[1];
     h->stats.total_vertices += cnt[0]; h->stats.total_paths += (uint64_t) local * perPass;
+    h->stats.truncated_paths += cnt[3]; h->stats.dropped_records += cnt[4]; h->stats.invalid_rays += cnt[5];
+    h->lastRecorded = cnt[1];
     return rcode;
 }
 
@@ -1110,6 +1229,15 @@ static ppg_iteration_stats &iter_stats(ppg_integrator *h) {
     ppg_iteration_stats &st = h->stats.iterations[std::min(h->iter, PPG_MAX_ITERATIONS - 1)];
     memset(&st, 0, sizeof(st)); st.iteration = h->iter;
     return st;
+}
+// progressive film (renderproc.cpp:143-151 puts finished blocks into the film while rendering): hand the current film to the host's callback
+static int flush_film(ppg_integrator *h) {
+    if (!h->filmFn) return PPG_OK;
+    const size_t npx = (size_t) h->W * h->H;
+    develop_kernel<<<h->numSMs * 4, 256, 0, h->stream>>>(h->dFilm.p, h->dRgb.p, npx, 1.0f, 0); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    h->filmFn(h->filmUser, h->dRgb.p, h->W, h->H, h->passesRendered);
+    return PPG_OK;
 }
 static int clear_film(ppg_integrator *h) { CK(cudaMemsetAsync(h->dFilm.p, 0, sizeof(float4) * (size_t) h->W * h->H, h->stream)); return PPG_OK; }
 
@@ -1137,6 +1265,7 @@ static int render_spp(ppg_integrator *h) {
         CK(cudaStreamSynchronize(h->stream)); st.reset_seconds = elapsed_s(t0);
         float variance = 0;
         rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
+        rc = flush_film(h); if (rc) return rc;
         const float lastVarAtEnd = currentVarAtEnd;
         currentVarAtEnd = passesThisIteration * variance / remainingPasses;
         remainingPasses -= passesThisIteration;
@@ -1144,6 +1273,7 @@ static int render_spp(ppg_integrator *h) {
             (remainingPasses < passesThisIteration || (sppRendered > 256 && currentVarAtEnd > lastVarAtEnd))) {
             h->isFinalIter = true;
             rc = perform_render_passes(h, variance, remainingPasses, st); if (rc) return rc;
+            rc = flush_film(h); if (rc) return rc;
         }
         st.is_final = h->isFinalIter;
         t0 = std::chrono::steady_clock::now();
@@ -1165,13 +1295,14 @@ static int render_time(ppg_integrator *h) {
         float remainingTime = nSeconds - elapsedSeconds;
         const int passesThisIteration = 1 << std::min(h->iter, 30);
         ppg_iteration_stats &st = iter_stats(h);
-        const auto startIter = std::chrono::steady_clock::now();
+        const auto startIter = std::chrono::steady_clock::now(); const float startIterClock = h->clock_s();
         int rc = clear_film(h); if (rc) return rc;
         rc = reset_sd_tree(h); if (rc) return rc;
         CK(cudaStreamSynchronize(h->stream)); st.reset_seconds = elapsed_s(startIter);
         float variance = 0;
         rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
-        float secondsIter = elapsed_s(startIter);
+        rc = flush_film(h); if (rc) return rc;
+        float secondsIter = h->clock_s() - startIterClock;
         rc = sync_scalar(h, &secondsIter); if (rc) return rc;
         const float lastVarAtEnd = currentVarAtEnd;
         currentVarAtEnd = secondsIter * variance / remainingTime;
@@ -1181,7 +1312,8 @@ static int render_time(ppg_integrator *h) {
             h->isFinalIter = true;
             do {
                 rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
-                elapsedSeconds = elapsed_s(h->startTime);
+                rc = flush_film(h); if (rc) return rc;
+                elapsedSeconds = h->clock_s();
                 rc = sync_scalar(h, &elapsedSeconds); if (rc) return rc;
             } while (elapsedSeconds < nSeconds);
         }
@@ -1191,7 +1323,7 @@ static int render_time(ppg_integrator *h) {
         st.build_seconds = elapsed_s(t0);
         if (h->prm.dump_sd_tree && !h->isFinalIter) { rc = dump_iteration(h); if (rc) return rc; }     // GP:1504-1506
         ++h->iter; h->stats.n_iterations = std::min(h->iter, PPG_MAX_ITERATIONS);
-        elapsedSeconds = elapsed_s(h->startTime);
+        elapsedSeconds = h->clock_s();
         rc = sync_scalar(h, &elapsedSeconds); if (rc) return rc;
     }
     return PPG_OK;
@@ -1227,11 +1359,14 @@ extern "C" int ppg_render_device(ppg_integrator *h, float **rgb_dev, ppg_stats *
     } else {
         develop_kernel<<<blocks, 256, 0, h->stream>>>(h->dFilm.p, h->dRgb.p, npx, 1.0f, 0); h->launches++;
     }
+    if (h->ncclComm && h->world > 1) {     // disjoint tiles: summing the zero-padded frames assembles the film on every rank; on the render stream
+        int rc2 = allreduce_sum(h, h->dRgb.p, 3 * npx); if (rc2) return rc2;
+    }
     CK(cudaEventRecord(h->evRender1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     { float ms = 0; cudaEventElapsedTime(&ms, h->evRender0, h->evRender1); h->stats.render_device_ms = ms; }
-    if (h->allreduce && h->world > 1) {    // disjoint tiles: summing the zero-padded frames assembles the film on every rank
-        if (h->allreduce(h->allreduceUser, h->dRgb.p, 3 * npx) != 0) return fail(PPG_ERR_COMM, "allreduce callback failed");
+    if (!h->ncclComm && h->multi()) {      // callback path: the collective runs outside the library's stream, after the timed region
+        int rc2 = allreduce_sum(h, h->dRgb.p, 3 * npx); if (rc2) return rc2;
     }
     CK(cudaGetLastError());
     h->stats.total_passes = h->passesRendered;

@@ -5,9 +5,10 @@
 
 namespace ppg {
 
-// paths still alive after the last bounce (only possible with maxDepth == -1 and the bounce cap) keep their radiance
-__global__ void __launch_bounds__(PPG_BLOCK) flush_kernel(PathState in, const uint32_t *liveIn, float4 *liFinal) {
+// paths still alive after the last bounce (only possible with maxDepth == -1 and the bounce cap) keep their radiance; counted in *truncated
+__global__ void __launch_bounds__(PPG_BLOCK) flush_kernel(PathState in, const uint32_t *liveIn, float4 *liFinal, unsigned long long *truncated) {
     const uint32_t nIn = *liveIn;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nIn) atomicAdd(truncated, (unsigned long long) nIn);
     for (uint32_t i = blockIdx.x * PPG_BLOCK + threadIdx.x; i < nIn; i += gridDim.x * PPG_BLOCK) {
         const float4 c = in.s2[i], e = in.s3[i];
         liFinal[__float_as_uint(e.y)] = make_float4(c.z, c.w, e.x, 1.f);
@@ -32,6 +33,7 @@ struct CommitParams {
     float2 *adamRecB;              // dTreePdf, statistical weight
     uint32_t *adamTotal;           // device counter of appended records
     uint32_t adamCap;
+    unsigned long long *dropped;   // records beyond adamCap (surfaced as ppg_stats.dropped_records)
 };
 
 // DTreeWrapper::record (GP:575-584) into the building tree of S-tree node `leaf`.
@@ -59,7 +61,7 @@ __device__ __forceinline__ void record_into_leaf(const CommitParams &C, uint32_t
         if (idx < C.adamCap) {
             C.adamRecA[idx] = make_float4(__uint_as_float(leaf), product, woPdf, bsdfPdf);
             C.adamRecB[idx] = make_float2(dTreePdf, weight);
-        }
+        } else atomicAdd(C.dropped, 1ull);
     }
 }
 
@@ -241,7 +243,7 @@ struct MaintParams {
 // a leaf splits while its building weight exceeds the threshold (GP:953-955), both children inherit the parent's
 // leaf record (shared sampling tree, Adam state) with half the building weight (GP:876-895).  Children are allocated
 // with a block prefix sum, so node numbering is deterministic (required for identical replicas across ranks).
-__global__ void __launch_bounds__(1024) stree_refine_kernel(MaintParams M, float threshold) {
+__global__ void __launch_bounds__(1024) stree_refine_kernel(MaintParams M, float threshold, uint32_t *overflow) {
     __shared__ uint32_t sScan[1024];
     __shared__ uint32_t sBase, sBegin, sEnd, sAny;
     if (threadIdx.x == 0) { sBegin = 0; sEnd = *M.nNodes; }
@@ -267,7 +269,8 @@ __global__ void __launch_bounds__(1024) stree_refine_kernel(MaintParams M, float
             const uint32_t base = sBase;
             if (split) {
                 const uint32_t c0 = base + 2 * (incl - 1);
-                if (c0 + 1 < M.capNodes) {
+                if (c0 + 1 >= M.capNodes) *overflow = 1u;             // the host sizes the arrays from the recorded weight; never seen, but never silent
+                else {
                     const float4 la = M.leafA[n];
                     const float half = M.bweight[n] / 2.f;
                     for (int c = 0; c < 2; ++c) {
@@ -468,70 +471,153 @@ __global__ void __launch_bounds__(256) adam_scatter_kernel(const float4 *recA, c
         }
     }
 }
-// one thread per leaf: AdamOptimizer::append / step exactly as GP:85-109, gradient as GP:672-697
+// One WARP per leaf: AdamOptimizer::append / step exactly as GP:85-109, gradient as GP:672-697.  The chain over a leaf's records is sequential
+// (theta changes every ~2 records), so its speed is the latency of one link.  The 32 lanes fetch the next 32 records with coalesced loads while the
+// chain runs; every lane then walks the chain redundantly on values handed around with shuffles (no divergence, no dependent global load in the
+// chain).  The first version (one THREAD per leaf, a dependent 24-byte fetch per record) spent ~0.3 us per record: 310 of 1000 ms on SPACESHIP
+// 640x360, where the hottest leaf of an iteration holds > 100 000 records.
 __global__ void __launch_bounds__(128) adam_seq_kernel(MaintParams M, const float4 *recA, const float2 *recB, const uint32_t *offset, uint32_t *count,
-                                                       uint32_t *cursor, float ratioPower, float *deltaIter) {
+                                                       uint32_t *cursor, float ratioPower) {
     const uint32_t nNodes = *M.nNodes;
-    for (uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < nNodes; leaf += gridDim.x * blockDim.x) {
+    const uint32_t lane = threadIdx.x & 31u, warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; leaf < nNodes; leaf += warpsPerGrid) {
         const uint32_t n = count[leaf];
-        count[leaf] = 0; cursor[leaf] = 0;              // ready for the next commit launch
-        if (deltaIter) deltaIter[leaf] = 0.f;
+        __syncwarp();
+        if (lane == 0) { count[leaf] = 0; cursor[leaf] = 0; }              // ready for the next commit launch
         if (n == 0) continue;
         float *st = M.adam + 6 * (size_t) leaf;
         int iter = (int) st[0]; float m1 = st[1], m2 = st[2], variable = st[3], batchAcc = st[4], batchGrad = st[5];
-        const int iter0 = iter;
         const uint32_t o = offset[leaf];
         // beta^iter as running double-precision products (the reference evaluates std::pow(float, int) in double, GP:98-99);
-        // a pow() per step would sit on the per-leaf sequential chain
+        // a pow() per step would sit on the sequential chain
         double b1pow = pow((double) 0.9f, (double) iter), b2pow = pow((double) 0.999f, (double) iter);
-        for (uint32_t k = 0; k < n; ++k) {
-            const float4 a = recA[o + k]; const float2 b = recB[o + k];
-            const float product = a.y, woPdf = a.z, bsdfPdf = a.w, dTreePdf = b.x, weight = b.y;
-            const float f = logistic(variable);
-            const float mixPdf = f * bsdfPdf + (1.f - f) * dTreePdf;
-            const float r_ = product / mixPdf;
-            const float ratio = ratioPower == 1.f ? r_ : (ratioPower == 2.f ? r_ * r_ : powf(r_, ratioPower));
-            const float dLoss_df = -ratio / woPdf * (bsdfPdf - dTreePdf);
-            const float dLoss_dv = dLoss_df * (f * (1.f - f));
-            const float g = 0.01f * variable + dLoss_dv;
-            batchGrad += g * weight; batchAcc += weight;
-            if (batchAcc > 1.0f) {                      // batchSize = 1, GP:89
-                const float grad = batchGrad / batchAcc;
-                ++iter; b1pow *= (double) 0.9f; b2pow *= (double) 0.999f;
-                const float lr = 0.01f * sqrtf(1.f - (float) b2pow) / (1.f - (float) b1pow);
-                m1 = 0.9f * m1 + (1.f - 0.9f) * grad;
-                m2 = 0.999f * m2 + (1.f - 0.999f) * grad * grad;
-                variable -= lr * m1 / (sqrtf(m2) + 1e-08f);
-                variable = fminf(fmaxf(variable, -20.0f), 20.0f);
-                batchGrad = 0.f; batchAcc = 0.f;
+        float4 na = make_float4(0, 0, 0, 0); float2 nb = make_float2(0, 0);
+        if (lane < n) { na = __ldg(&recA[o + lane]); nb = __ldg(&recB[o + lane]); }
+        float f = logistic(variable), fdf = f * (1.f - f);      // functions of the variable only: re-evaluated after a step, not per record
+        for (uint32_t base = 0; base < n; base += 32u) {
+            const float4 ca = na; const float2 cb = nb;
+            const uint32_t nxt = base + 32u + lane;
+            if (nxt < n) { na = __ldg(&recA[o + nxt]); nb = __ldg(&recB[o + nxt]); }      // in flight while this chunk's chain runs
+            const uint32_t m = min(32u, n - base);
+            for (uint32_t j = 0; j < m; ++j) {
+                const float product = __shfl_sync(0xffffffffu, ca.y, j), woPdf = __shfl_sync(0xffffffffu, ca.z, j), bsdfPdf = __shfl_sync(0xffffffffu, ca.w, j);
+                const float dTreePdf = __shfl_sync(0xffffffffu, cb.x, j), weight = __shfl_sync(0xffffffffu, cb.y, j);
+                const float mixPdf = f * bsdfPdf + (1.f - f) * dTreePdf;
+                const float r_ = product / mixPdf;
+                const float ratio = ratioPower == 1.f ? r_ : (ratioPower == 2.f ? r_ * r_ : powf(r_, ratioPower));
+                const float dLoss_df = -ratio / woPdf * (bsdfPdf - dTreePdf);
+                const float dLoss_dv = dLoss_df * fdf;
+                const float g = 0.01f * variable + dLoss_dv;
+                batchGrad += g * weight; batchAcc += weight;
+                if (batchAcc > 1.0f) {                      // batchSize = 1, GP:89
+                    const float grad = batchGrad / batchAcc;
+                    ++iter; b1pow *= (double) 0.9f; b2pow *= (double) 0.999f;
+                    const float lr = 0.01f * sqrtf(1.f - (float) b2pow) / (1.f - (float) b1pow);
+                    m1 = 0.9f * m1 + (1.f - 0.9f) * grad;
+                    m2 = 0.999f * m2 + (1.f - 0.999f) * grad * grad;
+                    variable -= lr * m1 / (sqrtf(m2) + 1e-08f);
+                    variable = fminf(fmaxf(variable, -20.0f), 20.0f);
+                    batchGrad = 0.f; batchAcc = 0.f;
+                    f = logistic(variable); fdf = f * (1.f - f);
+                }
             }
         }
-        st[0] = (float) iter; st[1] = m1; st[2] = m2; st[3] = variable; st[4] = batchAcc; st[5] = batchGrad;
-        if (deltaIter) deltaIter[leaf] = (float) (iter - iter0);
-        float4 la = M.leafA[leaf]; la.z = variable; M.leafA[leaf] = la;
+        if (lane == 0) {
+            st[0] = (float) iter; st[1] = m1; st[2] = m2; st[3] = variable; st[4] = batchAcc; st[5] = batchGrad;
+            float4 la = M.leafA[leaf]; la.z = variable; M.leafA[leaf] = la;
+        }
     }
 }
-// N > 1 ranks: every rank replayed its own records from the common state; average the replicas (the exchange buffer holds
-// the SUM over ranks of [deltaIter | m1 | m2 | variable | batchAcc | batchGrad], 6 arrays of nNodes floats)
-__global__ void adam_merge_kernel(MaintParams M, const float *sum6, const float *iterBefore, float invWorld) {
-    const uint32_t nNodes = *M.nNodes;
-    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
-        float *st = M.adam + 6 * (size_t) n;
-        st[0] = iterBefore[n] + sum6[n];
-        st[1] = sum6[(size_t) nNodes + n] * invWorld; st[2] = sum6[2 * (size_t) nNodes + n] * invWorld; st[3] = sum6[3 * (size_t) nNodes + n] * invWorld;
-        st[4] = sum6[4 * (size_t) nNodes + n]; st[5] = sum6[5 * (size_t) nNodes + n];
-        float4 la = M.leafA[n]; la.z = st[3]; M.leafA[n] = la;
-    }
-}
-__global__ void adam_pack_kernel(MaintParams M, float *out6, float *iterBefore, const float *deltaIter, int stage) {
+// N > 1 ranks: every rank replays its own records from the common state; the replicas are then merged.  The exchange buffer holds the SUM over
+// ranks of [iter - iterBefore | m1 | m2 | variable | batchAcc | batchGrad] (6 arrays of nNodes floats).  Step counts add up, moments and the
+// variable are averaged, and the batch accumulators add up RELATIVE to the common start (each rank's value contains the carried-over part once).
+__global__ void adam_pack_kernel(MaintParams M, float *out6, float *before3, const float *unused, int stage) {
     const uint32_t nNodes = *M.nNodes;
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
         const float *st = M.adam + 6 * (size_t) n;
-        if (stage == 0) { iterBefore[n] = st[0]; continue; }          // before the replay
-        out6[n] = deltaIter[n]; iterBefore[n] = st[0] - deltaIter[n];
+        if (stage == 0) { before3[n] = st[0]; before3[(size_t) nNodes + n] = st[4]; before3[2 * (size_t) nNodes + n] = st[5]; before3[3 * (size_t) nNodes + n] = st[3]; continue; }   // before the replay
+        out6[n] = st[0] - before3[n];
         out6[(size_t) nNodes + n] = st[1]; out6[2 * (size_t) nNodes + n] = st[2]; out6[3 * (size_t) nNodes + n] = st[3];
         out6[4 * (size_t) nNodes + n] = st[4]; out6[5 * (size_t) nNodes + n] = st[5];
     }
 }
+__global__ void adam_merge_kernel(MaintParams M, const float *sum6, const float *before3, float invWorld, float worldMinus1) {
+    const uint32_t nNodes = *M.nNodes;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
+        float *st = M.adam + 6 * (size_t) n;
+        st[0] = before3[n] + sum6[n];
+        st[1] = sum6[(size_t) nNodes + n] * invWorld; st[2] = sum6[2 * (size_t) nNodes + n] * invWorld; st[3] = sum6[3 * (size_t) nNodes + n] * invWorld;
+        const float acc = sum6[4 * (size_t) nNodes + n] - worldMinus1 * before3[(size_t) nNodes + n];
+        const float grad = sum6[5 * (size_t) nNodes + n] - worldMinus1 * before3[2 * (size_t) nNodes + n];
+        st[4] = acc > 0.f ? acc : 0.f; st[5] = acc > 0.f ? grad : 0.f;
+        float4 la = M.leafA[n]; la.z = st[3]; M.leafA[n] = la;
+    }
+}
+// "Distribution statistics" of buildSDTree (GP:1121-1186) over all leaves: one block, warp-shuffle + shared-memory reduction
+struct TreeStats {
+    uint32_t leaves, leavesWithNodes; int depthMin, depthMax; float meanMin, meanMax, weightMin, weightMax;
+    unsigned long long nodesMin, nodesMax; double depthSum, meanSum, nodesSum, weightSum;
+};
+__global__ void __launch_bounds__(1024) tree_stats_kernel(MaintParams M, TreeStats *out) {
+    const uint32_t nNodes = *M.nNodes;
+    uint32_t leaves = 0, withNodes = 0; int dMin = 0x7fffffff, dMax = 0; float rMin = 3.4e38f, rMax = 0.f, wMin = 3.4e38f, wMax = 0.f;
+    unsigned long long nMin = ~0ull, nMax = 0ull; double dSum = 0, rSum = 0, nSum = 0, wSum = 0;
+    for (uint32_t i = threadIdx.x; i < nNodes; i += blockDim.x) {
+        if (M.snodes[i].x != 0u) continue;
+        ++leaves;
+        const int depth = M.sampDepth[i]; dMin = min(dMin, depth); dMax = max(dMax, depth); dSum += depth;
+        const float w = M.sampWeight[i];
+        float mean = 0.f; if (w != 0.f) { const float factor = 1.f / (PPG_PI * 4.f * w); mean = factor * M.sampSum[i]; }       // DTree::mean(), GP:387-393
+        rMin = fminf(rMin, mean); rMax = fmaxf(rMax, mean); rSum += mean;
+        const uint32_t cnt = M.sampCount[i];
+        if (cnt > 1u) { nMin = min(nMin, (unsigned long long) cnt); nMax = max(nMax, (unsigned long long) cnt); nSum += cnt; ++withNodes; }
+        wMin = fminf(wMin, w); wMax = fmaxf(wMax, w); wSum += w;
+    }
+    __shared__ TreeStats sh[32];
+    for (int off = 16; off; off >>= 1) {
+        leaves += __shfl_xor_sync(0xffffffffu, leaves, off); withNodes += __shfl_xor_sync(0xffffffffu, withNodes, off);
+        dMin = min(dMin, __shfl_xor_sync(0xffffffffu, dMin, off)); dMax = max(dMax, __shfl_xor_sync(0xffffffffu, dMax, off));
+        rMin = fminf(rMin, __shfl_xor_sync(0xffffffffu, rMin, off)); rMax = fmaxf(rMax, __shfl_xor_sync(0xffffffffu, rMax, off));
+        wMin = fminf(wMin, __shfl_xor_sync(0xffffffffu, wMin, off)); wMax = fmaxf(wMax, __shfl_xor_sync(0xffffffffu, wMax, off));
+        nMin = min(nMin, __shfl_xor_sync(0xffffffffu, nMin, off)); nMax = max(nMax, __shfl_xor_sync(0xffffffffu, nMax, off));
+        dSum += __shfl_xor_sync(0xffffffffu, dSum, off); rSum += __shfl_xor_sync(0xffffffffu, rSum, off);
+        nSum += __shfl_xor_sync(0xffffffffu, nSum, off); wSum += __shfl_xor_sync(0xffffffffu, wSum, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        TreeStats t; t.leaves = leaves; t.leavesWithNodes = withNodes; t.depthMin = dMin; t.depthMax = dMax; t.meanMin = rMin; t.meanMax = rMax; t.weightMin = wMin; t.weightMax = wMax;
+        t.nodesMin = nMin; t.nodesMax = nMax; t.depthSum = dSum; t.meanSum = rSum; t.nodesSum = nSum; t.weightSum = wSum;
+        sh[threadIdx.x >> 5] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TreeStats t = sh[0];
+        for (int w = 1; w < (int) (blockDim.x >> 5); ++w) {
+            const TreeStats &o = sh[w];
+            t.leaves += o.leaves; t.leavesWithNodes += o.leavesWithNodes; t.depthMin = min(t.depthMin, o.depthMin); t.depthMax = max(t.depthMax, o.depthMax);
+            t.meanMin = fminf(t.meanMin, o.meanMin); t.meanMax = fmaxf(t.meanMax, o.meanMax); t.weightMin = fminf(t.weightMin, o.weightMin); t.weightMax = fmaxf(t.weightMax, o.weightMax);
+            t.nodesMin = min(t.nodesMin, o.nodesMin); t.nodesMax = max(t.nodesMax, o.nodesMax);
+            t.depthSum += o.depthSum; t.meanSum += o.meanSum; t.nodesSum += o.nodesSum; t.weightSum += o.weightSum;
+        }
+        *out = t;
+    }
+}
+// How far did the sampling fractions move in the replay that just ended?  Sum over leaves of steps * |f_after - f_before| and of steps, in fixed
+// point (2^-20) so that the result does not depend on the summation order: every rank derives the size of its next sub-batch from it
+// (perform_render_passes), and all ranks must decide alike.  `before4`: [iter | batchAcc | batchGrad | theta] saved by adam_pack_kernel stage 0.
+__global__ void adam_progress_kernel(MaintParams M, const float *before4, unsigned long long *out2) {
+    const uint32_t nNodes = *M.nNodes;
+    unsigned long long moved = 0, steps = 0;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
+        const float *st = M.adam + 6 * (size_t) n;
+        const float ds = st[0] - before4[n];
+        if (!(ds > 0.f)) continue;
+        const float df = fabsf(logistic(st[3]) - logistic(before4[3 * (size_t) nNodes + n]));
+        const unsigned long long s = (unsigned long long) ds;
+        steps += s; moved += s * (unsigned long long) (df * 1048576.0f);
+    }
+    for (int off = 16; off; off >>= 1) { moved += __shfl_xor_sync(0xffffffffu, moved, off); steps += __shfl_xor_sync(0xffffffffu, steps, off); }
+    if ((threadIdx.x & 31) == 0 && steps) { atomicAdd(&out2[0], moved); atomicAdd(&out2[1], steps); }
+}
+__global__ void double_to_float_kernel(const double *in, float *out) { *out = (float) *in; }
 
 }  // namespace ppg

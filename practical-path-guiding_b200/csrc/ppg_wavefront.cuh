@@ -66,7 +66,8 @@ struct RenderParams {
     const uint32_t *pixelMap;      // local pixel -> x | y<<16
     const uint32_t *liveIn; uint32_t *liveOut;      // device counters
     uint32_t *work;                                 // dynamic scheduling: next unclaimed input index of this launch (zeroed by the host), or nullptr
-    unsigned long long *counters;  // [0]: rays traced, [1]: vertices recorded, [2]: sum of S-tree levels over recorded vertices
+    unsigned long long *counters;  // [0]: rays traced, [1]: vertices recorded, [2]: sum of S-tree levels over recorded vertices, [3]: truncated paths,
+                                   // [4]: dropped sampling-fraction records, [5]: rays with a non-finite origin / direction
     uint32_t nPaths;               // paths of this batch (FIRST kernel)
     uint32_t nLocalPixels, spp;
     uint64_t passBase;             // global index of the first pass in the batch

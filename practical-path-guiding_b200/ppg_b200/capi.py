@@ -96,7 +96,7 @@ class PpgStats(C.Structure):
         ("n_iterations", C.c_int32), ("total_passes", C.c_int32), ("total_paths", C.c_uint64), ("total_vertices", C.c_uint64),
         ("render_seconds", C.c_double), ("device_seconds", C.c_double), ("final_variance", C.c_double),
         ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_double * PPG_KERNEL_CLASSES), ("kernel_count", C.c_uint64 * PPG_KERNEL_CLASSES),
-        ("render_device_ms", C.c_double), ("iterations", PpgIterationStats * PPG_MAX_ITERATIONS),
+        ("render_device_ms", C.c_double), ("truncated_paths", C.c_uint64), ("dropped_records", C.c_uint64), ("sub_batches", C.c_uint64), ("invalid_rays", C.c_uint64), ("iterations", PpgIterationStats * PPG_MAX_ITERATIONS),
     ]
 
     def as_dict(self):
@@ -108,6 +108,8 @@ class PpgStats(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+CLOCK_FN = C.CFUNCTYPE(C.c_double, C.c_void_p)
+FILM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int)
 
 
 def _fp(a):
@@ -201,6 +203,10 @@ def load_library(path: str | None = None):
     lib.ppg_set_scene.argtypes = [H, C.POINTER(PpgSceneDesc)]
     lib.ppg_set_shard.argtypes = [H, C.c_int, C.c_int]
     lib.ppg_set_allreduce.argtypes = [H, ALLREDUCE_FN, C.c_void_p]
+    lib.ppg_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.ppg_nccl_init.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
+    lib.ppg_set_clock.argtypes = [H, CLOCK_FN, C.c_void_p]
+    lib.ppg_set_film_callback.argtypes = [H, FILM_FN, C.c_void_p]
     lib.ppg_render.argtypes = [H, C.POINTER(C.c_float), C.POINTER(PpgStats)]
     lib.ppg_render_device.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(PpgStats)]
     lib.ppg_cancel.argtypes = [H]
@@ -219,7 +225,7 @@ def load_library(path: str | None = None):
 
 EXPORTED_SYMBOLS = [
     "ppg_params_default", "ppg_params_set", "ppg_params_validate", "ppg_description", "ppg_abi_version", "ppg_create",
-    "ppg_destroy", "ppg_set_scene", "ppg_set_shard", "ppg_set_allreduce", "ppg_render", "ppg_render_device", "ppg_cancel",
+    "ppg_destroy", "ppg_set_scene", "ppg_set_shard", "ppg_set_allreduce", "ppg_nccl_unique_id", "ppg_nccl_init", "ppg_set_clock", "ppg_set_film_callback", "ppg_render", "ppg_render_device", "ppg_cancel",
     "ppg_dump_sdtree", "ppg_set_destination", "ppg_get_moment_images", "ppg_last_error", "ppg_op_dtree_pdf", "ppg_op_dtree_sample",
     "ppg_op_dtree_record", "ppg_op_stree_lookup",
 ]

@@ -91,6 +91,39 @@ class GuidedPathTracer:
         _check(self.lib, self.lib.ppg_set_allreduce(self._h, self._cb, None))
         return self
 
+    def init_nccl(self, rank: int | None = None, world_size: int | None = None, broadcast=None):
+        """Create the library's own NCCL communicator (ppg_nccl_unique_id / ppg_nccl_init): collectives then run on the render stream
+        without a host round trip.  The 128-byte unique id of rank 0 reaches the other ranks through `broadcast(bytes_or_None) -> bytes`
+        (default: torch.distributed.broadcast_object_list on the default process group -- bootstrap plumbing only)."""
+        if broadcast is None:
+            import torch.distributed as dist
+            rank = dist.get_rank() if rank is None else rank
+            world_size = dist.get_world_size() if world_size is None else world_size
+
+            def broadcast(b):
+                box = [b]
+                dist.broadcast_object_list(box, src=0)
+                return box[0]
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _check(self.lib, self.lib.ppg_nccl_unique_id(buf))
+        ident = broadcast(bytes(buf.raw) if rank == 0 else None)
+        buf = C.create_string_buffer(ident, 128)
+        _check(self.lib, self.lib.ppg_nccl_init(self._h, buf, rank, world_size))
+        return self
+
+    def set_clock(self, fn):
+        """budgetType=seconds reads fn() -> seconds since the render started (None: the steady clock)."""
+        self._clock = capi.CLOCK_FN(lambda user: float(fn())) if fn is not None else C.cast(None, capi.CLOCK_FN)
+        _check(self.lib, self.lib.ppg_set_clock(self._h, self._clock, None))
+        return self
+
+    def set_film_callback(self, fn):
+        """fn(rgb_device_ptr, width, height, passes_rendered) after every performRenderPasses (progressive film)."""
+        self._film = capi.FILM_FN(lambda user, ptr, w, h, n: fn(ptr, w, h, n)) if fn is not None else C.cast(None, capi.FILM_FN)
+        _check(self.lib, self.lib.ppg_set_film_callback(self._h, self._film, None))
+        return self
+
     def render(self):
         """Integrator::render(): returns (rgb HxWx3 float32 on the host, stats dict)."""
         img = np.empty((self.H, self.W, 3), np.float32)

@@ -5,10 +5,17 @@ import csv, re, subprocess, sys, collections, os, tempfile
 rep, kre, fn = sys.argv[1], sys.argv[2], sys.argv[3]
 skip = sys.argv[4] if len(sys.argv) > 4 else "0"
 so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "practical-path-guiding_b200", "csrc", "libppg_b200.so")
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+build = os.path.join(os.path.dirname(os.path.abspath(so)), "build")
+for obj in sorted(os.listdir(build)):          # one object (one cubin) per translation unit: take the one that holds the function
+    if not obj.endswith(".o"): continue
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(build, obj)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+    for cubin in os.listdir(tmp):
+        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+        if any(l.startswith("//--------------------- .text.") and fn in l for l in txt.splitlines()):
+            dis = txt.splitlines()
+    if dis: break
 # map instruction ordinal within function -> (file, line) with inline chain's outermost user line
 infn = False; cur = None; amap = []
 for l in dis:
