@@ -1144,7 +1144,7 @@ static int perform_render_passes(ppg_integrator *h, float &variance, int numPass
     const bool learning = h->isBuilt && !h->isFinalIter && h->prm.bsdf_sampling_fraction_loss != PPG_LOSS_NONE;
     // Step-size control: after every replay the device reports how far the fractions moved (steps-weighted mean |df|).  The next sub-batch is sized
     // so that the fractions move by about `target` during it: that movement IS the staleness of the fractions a wavefront samples with.
-    // Measured on SPACESHIP 640x360 (recorded vertices of iterations 1-4 against the oracle, which learns online like the reference; the oracle's
+    // Measured on SPACESHIP 640x360 (recorded vertices of iterations 1-4 against the CPU restatement of the reference, which learns online like it; its
     // own run-to-run spread is ~0.5 %): target 0.005 -> +0.2 % (2200 sub-batches), 0.01 -> +0.4 % (1130), 0.02 -> +1.2 % (223), 0.04 -> +4 % (58).
     static const double target = std::max(env_int("PPG_LOSS_TARGET_X1000", 20), 1) * 1e-3;
     static const double growthMax = std::max(env_int("PPG_LOSS_GROWTH_MAX_PCT", 100), 1) * 0.01;

@@ -128,14 +128,14 @@ class GuidedPathTracer:
         """Integrator::render(): returns (rgb HxWx3 float32 on the host, stats dict)."""
         img = np.empty((self.H, self.W, 3), np.float32)
         st = capi.PpgStats()
-        _check(self.lib, self.lib.ppg_render(self._h, img.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st)), allow=(-5,))
+        self.last_status = _check(self.lib, self.lib.ppg_render(self._h, img.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st)), allow=(-5,))   # -5: cancelled, partial film
         return img, st.as_dict()
 
     def render_device(self):
         """Same, film left in HBM: returns (device pointer of W*H*3 floats, stats dict)."""
         ptr = C.c_void_p()
         st = capi.PpgStats()
-        _check(self.lib, self.lib.ppg_render_device(self._h, C.byref(ptr), C.byref(st)), allow=(-5,))
+        self.last_status = _check(self.lib, self.lib.ppg_render_device(self._h, C.byref(ptr), C.byref(st)), allow=(-5,))
         return ptr.value, st.as_dict()
 
     def cancel(self):

@@ -3,6 +3,14 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED_OVERRIDE = None     # set by conftest for tests marked `seeds3`
+
+
+def with_seed(props):
+    """props with the seed of the current `seeds3` round (unless the test sets one itself)."""
+    if SEED_OVERRIDE is not None and "seed" not in props:
+        return dict(props, seed=str(SEED_OVERRIDE))
+    return props
 
 
 def load_cbox(size=None, improved=False):

@@ -1,6 +1,7 @@
-"""Worker for the world_size-2 tests (spawned by test_sharded_*.py): one rank of a tile-sharded render whose per-iteration
+"""Worker for the multi-rank tests (spawned by test_sharded_*.py): one rank of a tile-sharded render whose per-iteration
 tree exchange goes through torch.distributed (gloo on CPU tensors).  mode 'oracle': CPU oracle; mode 'gpu': the CUDA
-library on cuda:0 (both ranks share the device; the exchange buffer is staged through the host for gloo)."""
+library on cuda:0 (all ranks share the device; the exchange buffer is staged through the host for gloo); mode 'nccl': one GPU
+per rank, the library's own NCCL communicator (ppg_nccl_init), gloo only carries the unique id."""
 import os
 import sys
 
@@ -47,8 +48,12 @@ def main():
             dist.all_reduce(c)
             t.copy_(c)
             torch.cuda.synchronize()
-        g = GuidedPathTracer(props, device=0)
-        g.set_scene(sc); g.set_shard(rank, world); g.set_allreduce(red)
+        if mode == "nccl":           # one GPU per rank; the library's own NCCL communicator (bootstrap of the unique id over gloo)
+            g = GuidedPathTracer(props, device=rank)
+            g.set_scene(sc); g.init_nccl()
+        else:
+            g = GuidedPathTracer(props, device=0)
+            g.set_scene(sc); g.set_shard(rank, world); g.set_allreduce(red)
         img, st = g.render()
         np.savez(os.path.join(outdir, f"rank{rank}.npz"), img=img, weights=[i["weight_avg"] * i["s_tree_leaves"] for i in st["iterations"]],
                  leaves=[i["s_tree_leaves"] for i in st["iterations"]], paths=st["total_paths"], variance=[i["variance"] for i in st["iterations"]])

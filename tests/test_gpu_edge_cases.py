@@ -11,11 +11,13 @@ pytestmark = pytest.mark.gpu
 
 def _both(sc, props):
     from ppg_b200.integrator import GuidedPathTracer
-    g = GuidedPathTracer(props); g.set_scene(sc); img, st = g.render()
+    import common
+    g = GuidedPathTracer(common.with_seed(props)); g.set_scene(sc); img, st = g.render()
     o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
     return img, st, ref, ost
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("w,h", [(100, 70), (33, 65), (31, 17), (1, 1)])
 def test_ragged_film_sizes(w, h):
     sc = load_cbox().with_film(w, h)
@@ -26,6 +28,7 @@ def test_ragged_film_sizes(w, h):
     assert relmse(img, ref) <= 1e-6, relmse(img, ref)
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(maxDepth="-1", rrDepth="3"), dict(maxDepth="2"), dict(maxDepth="1"), dict(rrDepth="1"), dict(strictNormals="false"),
                                    dict(sppPerPass="1", budget="7"), dict(sppPerPass="8", budget="24"), dict(budget="3"), dict(sdTreeMaxMemory="1"),
                                    dict(sTreeThreshold="200", budget="60"), dict(dTreeThreshold="0.1", budget="60"), dict(bsdfSamplingFraction="0.0", budget="60"),

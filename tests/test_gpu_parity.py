@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 def _gpu(props, scene):
     from ppg_b200.integrator import GuidedPathTracer
-    g = GuidedPathTracer(props)
+    import common
+    g = GuidedPathTracer(common.with_seed(props))
     g.set_scene(scene)
     return g
 
@@ -169,6 +170,7 @@ def test_op_dtree_record_matches_reference(dfilter):
 @pytest.mark.parametrize("extra", [dict(directionalFilter="box"), dict(spatialFilter="stochastic"), dict(spatialFilter="box"), dict(sampleCombination="inversevar"),
                                    dict(sppPerPass="1"), dict(sTreeThreshold="4000"), dict(nee="kickstart"), dict(nee="always"),
                                    dict(nee="kickstart", spatialFilter="stochastic", directionalFilter="box", budget="300")])
+@pytest.mark.seeds3
 def test_each_improvement_matches_oracle_image(extra):
     """Every non-learning option (filters, inverse-variance combination, sppPerPass, sTreeThreshold) follows the same paths as the
     oracle (same PCG32 streams, IEEE arithmetic without FMA contraction): the rendered images agree to relMSE 1e-7 through all
@@ -240,6 +242,7 @@ def test_dump_sdtree_wire_format(tmp_path):
         assert max(nodes) == it["nodes_max"]
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("subdiv,smooth", [(2, True), (3, False)])
 def test_bvh_path_matches_oracle(subdiv, smooth):
     """Scenes with more than 64 triangles intersect through the BVH walk (the tiny-scene lock-step test is off): CBOX plus a
@@ -258,6 +261,7 @@ def test_bvh_path_matches_oracle(subdiv, smooth):
         assert np.isclose(a["weight_avg"], b["weight_avg"], rtol=1e-4)
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("nee", ["never", "kickstart"])
 def test_delta_bsdfs_match_oracle(nee):
     """CBOX with a glass box (dielectric.cpp) and a mirror box (conductor.cpp): delta lobes are sampled with their discrete
@@ -273,6 +277,7 @@ def test_delta_bsdfs_match_oracle(nee):
         assert a["s_tree_leaves"] == b["s_tree_leaves"] and np.isclose(a["weight_avg"], b["weight_avg"], rtol=1e-4)
 
 
+@pytest.mark.seeds3
 def test_torus_standin_scene_matches_oracle():
     """TORUS stand-in (ppg_b200.builtin_scenes.torus_scene: diffuse torus in a glass cube, SDS paths only; the original asset is
     not bundled with the reference): BVH walk + dielectric + guiding.  A single unguided pass is bit-identical to the oracle;
@@ -289,6 +294,7 @@ def test_torus_standin_scene_matches_oracle():
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1 and np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-3)
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(), dict(nee="kickstart", bsdfSamplingFractionLoss="none"), dict(spatialFilter="stochastic", directionalFilter="box")])
 def test_rough_conductor_matches_oracle(extra):
     """CBOX with GGX and Beckmann rough-conductor boxes (roughconductor.cpp + microfacet.h: D, Smith G1, visible-normal
@@ -309,6 +315,7 @@ def test_rough_conductor_matches_oracle(extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(spatialFilter="stochastic", directionalFilter="box", sampleCombination="inversevar")])
 def test_rough_plastic_matches_oracle(extra):
     """CBOX with rough-plastic boxes (roughplastic.cpp: microfacet coat with dielectric Fresnel over a diffuse base attenuated by the
@@ -327,6 +334,7 @@ def test_rough_plastic_matches_oracle(extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(bsdfSamplingFractionLoss="none", spatialFilter="box")])
 def test_rough_dielectric_matches_oracle(extra):
     """CBOX with rough-glass boxes (roughdielectric.cpp: glossy reflection + glossy transmission, one extra path-sampler draw per
@@ -344,6 +352,7 @@ def test_rough_dielectric_matches_oracle(extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(nee="kickstart", spatialFilter="stochastic", directionalFilter="box")])
 def test_analytic_spheres_match_oracle(extra):
     """CBOX + analytic spheres (sphere.cpp): double-precision ray/sphere quadratic, re-projected hit point, frame from dpdu;
@@ -361,6 +370,7 @@ def test_analytic_spheres_match_oracle(extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.seeds3
 def test_spaceship_matches_oracle():
     """BASELINE config 4's scene (spaceship-improved.xml: 457 560 triangles through the BVH walk, twosided rough plastics / conductors,
     GGX glass with alpha 0.01, rectangle emitters, the radius-100 emitting shell), at 160x90 and 31 spp.  Deterministic options
@@ -394,6 +404,7 @@ def test_spaceship_improved_settings_statistics():
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= max(4, 0.15 * b["s_tree_leaves"])   # splits near the threshold flip
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(bsdfSamplingFractionLoss="none", bsdfSamplingFraction="0.3")])
 def test_smooth_plastic_matches_oracle(extra):
     """CBOX with smooth-plastic boxes and floor (plastic.cpp): a delta coat reflection mixed with a diffuse base.  A guided vertex
@@ -410,6 +421,7 @@ def test_smooth_plastic_matches_oracle(extra):
         assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-4)
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(hideEmitters="true", nee="kickstart"), dict(maxDepth="4", nee="always")])
 def test_thin_dielectric_null_transitions_match_oracle(extra):
     """CBOX with thin-dielectric panes (thindielectric.cpp): index-matched (ENull) transitions.  Covers the null branch of Li
@@ -428,6 +440,7 @@ def test_thin_dielectric_null_transitions_match_oracle(extra):
         assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=1e-4)
 
 
+@pytest.mark.seeds3
 @pytest.mark.parametrize("extra", [dict(), dict(nee="always"), dict(nee="kickstart", spatialFilter="box")])
 def test_mask_smooth_null_hybrid_matches_oracle(extra):
     """CBOX with `mask` panes (mask.cpp, kitchen.xml's "Blinds"): nested diffuse lobe scaled by the opacity, else a null transition;

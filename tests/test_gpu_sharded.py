@@ -24,3 +24,37 @@ def test_two_ranks_match_single_rank_on_gpu():
     assert np.allclose(r0["weights"], w, rtol=0.01)
     assert np.allclose(r0["variance"][0], st["iterations"][0]["variance"], rtol=1e-3)
     assert abs(r0["img"].mean() - img.mean()) <= 0.02 * img.mean()
+
+
+def test_three_ranks_with_uneven_shards_learning_and_a_time_budget():
+    """A 100x100 film is 4x4 image blocks (the last row / column 4 pixels wide) over 3 ranks: the ranks own different numbers of pixels, the sampling-fraction
+    loss adds one collective per sub-batch and budgetType=seconds one per batch.  Every rank must issue the same sequence of collectives (batch
+    sizes come from the LARGEST share, a rank without pixels in a sub-batch still joins) and end with the same film and tree."""
+    from test_sharded_cpu import _spawn
+    import tempfile, subprocess, sys, os
+    rs = _spawn("gpu", 100, "40", extra=("bsdfSamplingFractionLoss=kl", "sppPerPass=2"), world=3)
+    assert len({int(r["paths"]) for r in rs}) > 1                       # uneven shares
+    assert sum(int(r["paths"]) for r in rs) == 100 * 100 * 40
+    for r in rs[1:]:
+        assert np.array_equal(rs[0]["img"], r["img"]) and list(rs[0]["leaves"]) == list(r["leaves"]) and np.array_equal(rs[0]["weights"], r["weights"])
+    assert np.isfinite(rs[0]["img"]).all()
+    rs = _spawn("gpu", 100, "2", extra=("budgetType=seconds", "bsdfSamplingFractionLoss=kl"), world=3)      # 2 s wall-clock budget: rank 0's clock decides
+    for r in rs[1:]:
+        assert np.array_equal(rs[0]["img"], r["img"]) and list(rs[0]["leaves"]) == list(r["leaves"])
+
+
+def test_library_nccl_communicator_matches_single_rank():
+    """ppg_nccl_init: one GPU per rank, ncclAllReduce enqueued on the render stream by the library itself (needs two GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from ppg_b200.integrator import GuidedPathTracer
+    from test_sharded_cpu import _spawn
+    r0, r1 = _spawn("nccl", 128, "60", extra=("bsdfSamplingFractionLoss=kl",))
+    assert np.array_equal(r0["img"], r1["img"]) and list(r0["leaves"]) == list(r1["leaves"]) and np.array_equal(r0["weights"], r1["weights"])
+    sc = load_cbox(128)
+    g = GuidedPathTracer(dict(sc.integrator, budget="60", bsdfSamplingFractionLoss="kl")); g.set_scene(sc)
+    img, st = g.render()
+    w = [i["weight_avg"] * i["s_tree_leaves"] for i in st["iterations"]]
+    assert r0["weights"][0] == w[0] and np.allclose(r0["weights"], w, rtol=0.03)
+    assert abs(r0["img"].mean() - img.mean()) <= 0.02 * img.mean()

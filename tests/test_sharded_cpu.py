@@ -12,13 +12,13 @@ import oracle_lib as O
 from common import ROOT, load_cbox
 
 
-def _spawn(mode, size, budget, extra=()):
+def _spawn(mode, size, budget, extra=(), world=2):
     d = tempfile.mkdtemp()
     port = str(29600 + os.getpid() % 300)
-    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(r), "2", port, str(size), budget, d, *extra]) for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), mode, str(r), str(world), port, str(size), budget, d, *extra]) for r in range(world)]
     for p in procs:
         assert p.wait(timeout=600) == 0
-    return [np.load(os.path.join(d, f"rank{r}.npz")) for r in range(2)]
+    return [np.load(os.path.join(d, f"rank{r}.npz")) for r in range(world)]
 
 
 def test_two_ranks_build_identical_trees_and_match_single_rank():
