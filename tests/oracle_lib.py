@@ -99,9 +99,8 @@ _FIELDS = {
 
 def params_from_xml(props: dict, **override):
     """XML (name -> string) to ppg_params, on the test side (the product does this in C: ppg_params_set)."""
-    import common
     p = default_params()
-    allp = dict(common.with_seed(props)); allp.update({k: str(v) for k, v in override.items()})
+    allp = dict(props); allp.update({k: str(v) for k, v in override.items()})
     for k, v in allp.items():
         f = _FIELDS[k]
         if k in _ENUMS:

@@ -12,12 +12,19 @@ from ppg_b200.integrator import GuidedPathTracer
 what = sys.argv[1] if len(sys.argv) > 1 else "spaceship"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 with_oracle = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
-if what == "spaceship":
+extra = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+sys.argv = [a for a in sys.argv if "=" not in a]
+if what == "cboxdef":
+    sc = load_fixture_scene("cbox"); gold = []
+elif what == "cbox":
+    sc = load_fixture_scene("cbox-improved"); gold = json.load(open(os.path.join(ROOT, "tests", "golden", "cbox_log_stats.json")))["cbox-improved"]["iterations"]
+elif what == "spaceship":
     sc = load_fixture_scene("spaceship-improved"); gold = json.load(open(os.path.join(ROOT, "tests", "golden", "spaceship_log_stats.json")))["spaceship-improved"]["iterations"]
 else:
     sc = load_fixture_scene("kitchen-improved"); gold = json.load(open(os.path.join(ROOT, "tests", "golden", "kitchen_log_stats.json")))["kitchen-improved"]["iterations"]
 budget = "63" if what == "spaceship" else "31"
-props = dict(sc.integrator, budget=budget)
+if len(sys.argv) > 4: sc = sc.with_film(int(sys.argv[4]), int(sys.argv[4]))
+props = dict(sc.integrator, budget=budget, **extra)
 rows = []
 for r in range(reps):
     g = GuidedPathTracer(dict(props, seed=str(1234 + r))); g.set_scene(sc)
