@@ -493,32 +493,38 @@ __global__ void __launch_bounds__(128) adam_seq_kernel(MaintParams M, const floa
         double b1pow = pow((double) 0.9f, (double) iter), b2pow = pow((double) 0.999f, (double) iter);
         float4 na = make_float4(0, 0, 0, 0); float2 nb = make_float2(0, 0);
         if (lane < n) { na = __ldg(&recA[o + lane]); nb = __ldg(&recB[o + lane]); }
-        float f = logistic(variable), fdf = f * (1.f - f);      // functions of the variable only: re-evaluated after a step, not per record
+        // The chain's latency is what this kernel costs (the hottest leaf of SPACESHIP 1080p holds > 10^6 records per iteration), so everything
+        // that does not depend on theta is taken off it: each lane reduces ITS record to {k, d, c, w} with
+        //     dL/df = -ratio / woPdf * (bsdfPdf - dTreePdf),  ratio = (product / mix)^p,  mix = c + f * d,  d = bsdfPdf - dTreePdf,  c = dTreePdf
+        //   KL (p = 1):  dL/df = -k / mix,      k = product * d / woPdf
+        //   var (p = 2): dL/df = -k / mix^2,    k = product^2 * d / woPdf
+        // and the chain keeps one fast division per record and {division, rsqrt, exp} per step.  The optimiser is not bit-reproducible in the
+        // reference either (records arrive in thread order): approximate-division rounding is far below that.
+        const bool var = ratioPower == 2.f;
+        float f = __fdividef(1.f, 1.f + __expf(-variable)), fdf = f * (1.f - f);      // logistic (GP:64-66); re-evaluated after a step, not per record
         for (uint32_t base = 0; base < n; base += 32u) {
             const float4 ca = na; const float2 cb = nb;
             const uint32_t nxt = base + 32u + lane;
             if (nxt < n) { na = __ldg(&recA[o + nxt]); nb = __ldg(&recB[o + nxt]); }      // in flight while this chunk's chain runs
+            const float dl = ca.w - cb.x;                                                    // bsdfPdf - dTreePdf
+            const float kl = (var ? ca.y * ca.y : ca.y) * dl / ca.z;
             const uint32_t m = min(32u, n - base);
             for (uint32_t j = 0; j < m; ++j) {
-                const float product = __shfl_sync(0xffffffffu, ca.y, j), woPdf = __shfl_sync(0xffffffffu, ca.z, j), bsdfPdf = __shfl_sync(0xffffffffu, ca.w, j);
-                const float dTreePdf = __shfl_sync(0xffffffffu, cb.x, j), weight = __shfl_sync(0xffffffffu, cb.y, j);
-                const float mixPdf = f * bsdfPdf + (1.f - f) * dTreePdf;
-                const float r_ = product / mixPdf;
-                const float ratio = ratioPower == 1.f ? r_ : (ratioPower == 2.f ? r_ * r_ : powf(r_, ratioPower));
-                const float dLoss_df = -ratio / woPdf * (bsdfPdf - dTreePdf);
-                const float dLoss_dv = dLoss_df * fdf;
-                const float g = 0.01f * variable + dLoss_dv;
-                batchGrad += g * weight; batchAcc += weight;
+                const float k_ = __shfl_sync(0xffffffffu, kl, j), d_ = __shfl_sync(0xffffffffu, dl, j), c_ = __shfl_sync(0xffffffffu, cb.x, j), weight = __shfl_sync(0xffffffffu, cb.y, j);
+                const float mix = fmaf(f, d_, c_);
+                const float dLoss_df = -__fdividef(k_, var ? mix * mix : mix);
+                const float g = fmaf(dLoss_df, fdf, 0.01f * variable);
+                batchGrad = fmaf(g, weight, batchGrad); batchAcc += weight;
                 if (batchAcc > 1.0f) {                      // batchSize = 1, GP:89
-                    const float grad = batchGrad / batchAcc;
+                    const float grad = __fdividef(batchGrad, batchAcc);
                     ++iter; b1pow *= (double) 0.9f; b2pow *= (double) 0.999f;
-                    const float lr = 0.01f * sqrtf(1.f - (float) b2pow) / (1.f - (float) b1pow);
+                    const float lr = 0.01f * sqrtf(1.f - (float) b2pow) / (1.f - (float) b1pow);     // depends on the step count only: off the chain
                     m1 = 0.9f * m1 + (1.f - 0.9f) * grad;
                     m2 = 0.999f * m2 + (1.f - 0.999f) * grad * grad;
-                    variable -= lr * m1 / (sqrtf(m2) + 1e-08f);
+                    variable -= __fdividef(lr * m1, sqrtf(m2) + 1e-08f);
                     variable = fminf(fmaxf(variable, -20.0f), 20.0f);
                     batchGrad = 0.f; batchAcc = 0.f;
-                    f = logistic(variable); fdf = f * (1.f - f);
+                    f = __fdividef(1.f, 1.f + __expf(-variable)); fdf = f * (1.f - f);
                 }
             }
         }
