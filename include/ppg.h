@@ -233,6 +233,13 @@ typedef struct ppg_scene_desc {
     ppg_envmap envmap;
 } ppg_scene_desc;
 
+/* Flat scene files for C / C++ hosts (written by `python -m ppg_b200.convert scene.xml scene.ppgscene`): fills *desc with pointers into
+ * memory owned by *file (free with ppg_scene_file_free after ppg_set_scene).  `integrator_props`, if not NULL, receives the XML's
+ * integrator parameters as "name=value" lines (valid until the file is freed).  No CUDA device is needed. */
+typedef struct ppg_scene_file ppg_scene_file;
+int ppg_scene_file_load(const char *path, ppg_scene_desc *desc, ppg_scene_file **file, const char **integrator_props);
+void ppg_scene_file_free(ppg_scene_file *file);
+
 /* ---- per-iteration statistics (the reference's log lines, GP:1176-1186, 1323-1326) --- */
 
 #define PPG_MAX_ITERATIONS 40
@@ -364,6 +371,10 @@ int ppg_set_destination(ppg_integrator *h, const char *destination);
 /* Copy the variance-estimate helper images (sum, sum of squares; W*H*4 floats
  * each: R,G,B,weight) of the last performRenderPasses to the host. Either may be NULL. */
 int ppg_get_moment_images(ppg_integrator *h, float *sum_rgbw, float *sumsq_rgbw);
+
+/* Copy `bytes` from device memory handed out by the library (ppg_render_device, the film callback) to the host: lets a C / C++ host without the CUDA
+ * runtime (e.g. the Mitsuba plugin shim) read such buffers. */
+int ppg_copy_from_device(void *host_dst, const void *device_src, size_t bytes);
 
 const char *ppg_last_error(void);
 

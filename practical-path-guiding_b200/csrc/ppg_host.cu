@@ -126,6 +126,63 @@ extern "C" const char *ppg_description(void) { return "Guided path tracer"; }
 extern "C" int ppg_abi_version(void) { return PPG_ABI_VERSION; }
 extern "C" const char *ppg_last_error(void) { return g_lastError.c_str(); }
 
+// ------------------------------------------------------------------ flat scene files (python -m ppg_b200.convert)
+struct ppg_scene_file { std::vector<std::vector<char>> blobs; std::string props; };
+extern "C" int ppg_scene_file_load(const char *path, ppg_scene_desc *d, ppg_scene_file **file, const char **integrator_props) {
+    if (!path || !d || !file) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(PPG_ERR_IO, std::string("cannot open ") + path);
+    char magic[8];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "PPGSCN02", 8) != 0) { fclose(f); return fail(PPG_ERR_IO, "not a PPGSCN02 scene file"); }
+    ppg_scene_file *sf = new ppg_scene_file();
+    memset(d, 0, sizeof(*d));
+    struct Arr { const char *p; size_t bytes; uint64_t dims[4]; uint32_t ndim; };
+    auto fail_io = [&](const char *m) { fclose(f); delete sf; return fail(PPG_ERR_IO, m); };
+    static const size_t esz[6] = {4, 4, 4, 2, 1, 8};
+    std::vector<std::pair<std::string, Arr>> arrs;
+    for (;;) {
+        uint32_t nl;
+        if (fread(&nl, 4, 1, f) != 1) break;
+        if (nl > 64) return fail_io("corrupt scene file (name)");
+        std::string name(nl, 0); uint32_t hdr[2];
+        if (fread(&name[0], 1, nl, f) != nl || fread(hdr, 4, 2, f) != 2 || hdr[0] > 5 || hdr[1] > 4) return fail_io("corrupt scene file (header)");
+        Arr a; a.ndim = hdr[1]; size_t count = 1;
+        for (uint32_t k = 0; k < a.ndim; ++k) { if (fread(&a.dims[k], 8, 1, f) != 1) return fail_io("corrupt scene file (dims)"); count *= (size_t) a.dims[k]; }
+        a.bytes = count * esz[hdr[0]];
+        sf->blobs.emplace_back(a.bytes + 8);
+        if (a.bytes && fread(sf->blobs.back().data(), 1, a.bytes, f) != a.bytes) return fail_io("truncated scene file");
+        a.p = sf->blobs.back().data();
+        arrs.emplace_back(name, a);
+    }
+    fclose(f);
+    auto get = [&](const char *n) -> const Arr * { for (auto &kv : arrs) if (kv.first == n) return &kv.second; return nullptr; };
+    const Arr *P = get("positions"), *N = get("normals"), *UV = get("uvs"), *I = get("indices"), *TS = get("triangle_shape"), *SH = get("shapes"), *B = get("bsdfs"),
+              *R = get("area_radiance"), *T = get("bsdf_tables"), *SP = get("spheres"), *CW = get("cam_to_world"), *CAM = get("cam"), *BB = get("aabb"),
+              *TX = get("textures"), *TL = get("texels"), *ET = get("env_texels"), *EM = get("env_meta"), *IP = get("integrator");
+    if (!P || !N || !UV || !I || !TS || !SH || !B || !R || !CW || !CAM || !BB || CW->bytes != 64 || CAM->bytes != 40 || BB->bytes != 24 || B->bytes % sizeof(ppg_bsdf) || SH->bytes % sizeof(ppg_shape))
+        { delete sf; return fail(PPG_ERR_IO, "scene file lacks a required array"); }
+    d->n_vertices = (uint32_t) (P->bytes / 12); d->n_triangles = (uint32_t) (I->bytes / 12); d->n_shapes = (uint32_t) (SH->bytes / sizeof(ppg_shape));
+    d->n_bsdfs = (uint32_t) (B->bytes / sizeof(ppg_bsdf)); d->n_emitters = (uint32_t) (R->bytes / 12);
+    d->positions = (const float *) P->p; d->normals = (const float *) N->p; d->uvs = (const float *) UV->p; d->indices = (const uint32_t *) I->p;
+    d->triangle_shape = (const uint32_t *) TS->p; d->shapes = (const ppg_shape *) SH->p; d->bsdfs = (const ppg_bsdf *) B->p; d->area_radiance = (const float *) R->p;
+    if (T && T->bytes) { d->bsdf_tables = (const float *) T->p; d->n_bsdf_tables = (uint32_t) (T->bytes / (4 * PPG_BSDF_TABLE_SIZE)); }
+    if (SP && SP->bytes) { d->spheres = (const ppg_sphere *) SP->p; d->n_spheres = (uint32_t) (SP->bytes / sizeof(ppg_sphere)); }
+    memcpy(d->camera.to_world, CW->p, 64);
+    const double *cam = (const double *) CAM->p;
+    d->camera.x_fov_deg = (float) cam[0]; d->camera.near_clip = (float) cam[1]; d->camera.far_clip = (float) cam[2]; d->camera.film_width = (int32_t) cam[3]; d->camera.film_height = (int32_t) cam[4];
+    memcpy(d->aabb_min, BB->p, 12); memcpy(d->aabb_max, BB->p + 12, 12);
+    if (TX && TX->bytes && TL) { d->textures = (const ppg_texture *) TX->p; d->n_textures = (uint32_t) (TX->bytes / sizeof(ppg_texture)); d->texels = (const uint16_t *) TL->p; d->n_texels = TL->bytes / 2; }
+    if (ET && ET->bytes && EM && EM->bytes == 40 && ET->ndim == 3) {
+        d->envmap.height = (uint32_t) ET->dims[0]; d->envmap.width = (uint32_t) ET->dims[1]; d->envmap.texels = (const uint16_t *) ET->p;
+        const float *em = (const float *) EM->p; d->envmap.scale = em[0]; memcpy(d->envmap.world_to_env, em + 1, 36);
+    }
+    if (IP) sf->props.assign(IP->p, IP->bytes);
+    if (integrator_props) *integrator_props = sf->props.c_str();
+    *file = sf;
+    return PPG_OK;
+}
+extern "C" void ppg_scene_file_free(ppg_scene_file *file) { delete file; }
+
 // ------------------------------------------------------------------ host BVH (binned SAH) + Wald triangle constants
 namespace {
 struct H3 { float x, y, z; };
@@ -1389,6 +1446,12 @@ extern "C" int ppg_render(ppg_integrator *h, float *rgb_out, ppg_stats *stats) {
     return rc;
 }
 
+extern "C" int ppg_copy_from_device(void *host_dst, const void *device_src, size_t bytes) {
+    if (!host_dst || !device_src) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+
 extern "C" int ppg_get_moment_images(ppg_integrator *h, float *sum_rgbw, float *sumsq_rgbw) {
     if (!h || !h->haveScene) return fail(PPG_ERR_NO_SCENE, "no scene");
     CK(cudaSetDevice(h->device));
@@ -1434,6 +1497,7 @@ extern "C" int ppg_dump_sdtree(ppg_integrator *h, const char *path) {
             const uint64_t w64 = (uint64_t) sw[e.n], nn = scnt[e.n];
             fwrite(&w64, 8, 1, f); fwrite(&nn, 8, 1, f);
             uint32_t base; memcpy(&base, &la[e.n].x, 4);
+            if ((size_t) base + scnt[e.n] > pool.size()) { fclose(f); return fail(PPG_ERR_IO, "SD-tree is being rebuilt (render cancelled between reset and build): nothing consistent to dump"); }
             for (uint32_t k = 0; k < scnt[e.n]; ++k) {
                 const SampNode &q = pool[base + k];
                 const float s4[4] = {q.sums.x, q.sums.y, q.sums.z, q.sums.w};

@@ -201,6 +201,8 @@ def load_library(path: str | None = None):
     lib.ppg_create.argtypes = [C.POINTER(PpgParams), C.c_int, C.POINTER(H)]
     lib.ppg_destroy.argtypes = [H]; lib.ppg_destroy.restype = None
     lib.ppg_set_scene.argtypes = [H, C.POINTER(PpgSceneDesc)]
+    lib.ppg_scene_file_load.argtypes = [C.c_char_p, C.POINTER(PpgSceneDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_char_p)]
+    lib.ppg_scene_file_free.argtypes = [C.c_void_p]; lib.ppg_scene_file_free.restype = None
     lib.ppg_set_shard.argtypes = [H, C.c_int, C.c_int]
     lib.ppg_set_allreduce.argtypes = [H, ALLREDUCE_FN, C.c_void_p]
     lib.ppg_nccl_unique_id.argtypes = [C.c_void_p]
@@ -210,6 +212,7 @@ def load_library(path: str | None = None):
     lib.ppg_render.argtypes = [H, C.POINTER(C.c_float), C.POINTER(PpgStats)]
     lib.ppg_render_device.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(PpgStats)]
     lib.ppg_cancel.argtypes = [H]
+    lib.ppg_copy_from_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.ppg_dump_sdtree.argtypes = [H, C.c_char_p]
     lib.ppg_set_destination.argtypes = [H, C.c_char_p]
     lib.ppg_get_moment_images.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -225,7 +228,7 @@ def load_library(path: str | None = None):
 
 EXPORTED_SYMBOLS = [
     "ppg_params_default", "ppg_params_set", "ppg_params_validate", "ppg_description", "ppg_abi_version", "ppg_create",
-    "ppg_destroy", "ppg_set_scene", "ppg_set_shard", "ppg_set_allreduce", "ppg_nccl_unique_id", "ppg_nccl_init", "ppg_set_clock", "ppg_set_film_callback", "ppg_render", "ppg_render_device", "ppg_cancel",
-    "ppg_dump_sdtree", "ppg_set_destination", "ppg_get_moment_images", "ppg_last_error", "ppg_op_dtree_pdf", "ppg_op_dtree_sample",
+    "ppg_destroy", "ppg_scene_file_load", "ppg_scene_file_free", "ppg_set_scene", "ppg_set_shard", "ppg_set_allreduce", "ppg_nccl_unique_id", "ppg_nccl_init", "ppg_set_clock", "ppg_set_film_callback", "ppg_render", "ppg_render_device", "ppg_cancel",
+    "ppg_copy_from_device", "ppg_dump_sdtree", "ppg_set_destination", "ppg_get_moment_images", "ppg_last_error", "ppg_op_dtree_pdf", "ppg_op_dtree_sample",
     "ppg_op_dtree_record", "ppg_op_stree_lookup",
 ]

@@ -456,6 +456,34 @@ class SceneDesc:
             env_texels=(self.envmap["texels"] if self.envmap else np.zeros((0, 0, 3), np.uint16)),
             env_meta=(np.concatenate([[self.envmap["scale"]], np.asarray(self.envmap["world_to_env"], np.float64).reshape(9)]) if self.envmap else np.zeros(0)))
 
+    def save_flat(self, path):
+        """Flat binary form for C / C++ hosts (read by ppg_scene_file_load, include/ppg.h): magic "PPGSCN02", then named arrays
+        [u32 name length][name][u32 dtype: 0 f32, 1 u32, 2 i32, 3 u16, 4 u8, 5 f64][u32 ndim][u64 dims...][raw little-endian data]."""
+        import struct
+        codes = {"float32": 0, "uint32": 1, "int32": 2, "uint16": 3, "uint8": 4, "float64": 5}
+        arrays = {
+            "positions": np.asarray(self.positions, np.float32), "normals": np.asarray(self.normals, np.float32), "uvs": np.asarray(self.uvs, np.float32),
+            "indices": np.asarray(self.indices, np.uint32), "triangle_shape": np.asarray(self.triangle_shape, np.uint32), "shapes": np.asarray(self.shapes, np.int32),
+            "bsdfs": np.asarray(self.bsdfs, np.float32), "area_radiance": np.asarray(self.area_radiance, np.float32).reshape(-1, 3),
+            "bsdf_tables": np.asarray(self.bsdf_tables if self.bsdf_tables is not None else np.zeros((0, 100)), np.float32),
+            "spheres": np.asarray(self.spheres if self.spheres is not None else np.zeros((0, 6)), np.float32),
+            "cam_to_world": np.asarray(self.cam_to_world, np.float32).reshape(16),
+            "cam": np.array([self.x_fov_deg, self.near_clip, self.far_clip, self.film_width, self.film_height], np.float64),
+            "aabb": np.stack([self.aabb_min, self.aabb_max]).astype(np.float32),
+            "textures": (self.textures if self.textures is not None else np.zeros(0, TEXTURE_DTYPE)).view(np.uint8),
+            "texels": np.asarray(self.texels if self.texels is not None else np.zeros(0), np.uint16),
+            "env_texels": np.asarray(self.envmap["texels"] if self.envmap else np.zeros((0, 0, 3)), np.uint16),
+            "env_meta": (np.concatenate([[self.envmap["scale"]], np.asarray(self.envmap["world_to_env"], np.float64).reshape(9)]) if self.envmap else np.zeros(0)).astype(np.float32),
+            "integrator": np.frombuffer("\n".join(f"{k}={v}" for k, v in self.integrator.items()).encode(), np.uint8),
+        }
+        with open(path, "wb") as f:
+            f.write(b"PPGSCN02")
+            for name, a in arrays.items():
+                a = np.ascontiguousarray(a)
+                f.write(struct.pack("<I", len(name))); f.write(name.encode())
+                f.write(struct.pack("<II", codes[a.dtype.name], a.ndim)); f.write(struct.pack(f"<{a.ndim}Q", *a.shape))
+                f.write(a.tobytes())
+
     @staticmethod
     def load(path) -> "SceneDesc":
         d = np.load(path, allow_pickle=False)

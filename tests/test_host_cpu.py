@@ -248,3 +248,27 @@ def test_loader_parses_every_supported_bsdf_and_shape(tmp_path):
     import oracle_lib as O
     o = O.Oracle(O.params_from_xml(sc.integrator), sc, kind="port"); img, st = o.render()
     assert img.shape == (48, 64, 3) and np.isfinite(img).all() and img.mean() > 0.01 and st["total_paths"] == 64 * 48 * 8
+
+
+def test_flat_scene_file_round_trip(tmp_path):
+    """python -m ppg_b200.convert -> ppg_scene_file_load (the route of the Mitsuba plugin shim, integration/guided_path_b200.cpp): every array of the
+    scene description comes back bit for bit, textures and the environment map included; no CUDA device is involved."""
+    from common import load_fixture_scene
+    sc = load_fixture_scene("cbox-textured")
+    path = str(tmp_path / "scene.ppgscene")
+    sc.save_flat(path)
+    lib = capi.load_library()
+    d = capi.PpgSceneDesc(); fh = C.c_void_p(); props = C.c_char_p()
+    assert lib.ppg_scene_file_load(path.encode(), C.byref(d), C.byref(fh), C.byref(props)) == 0, lib.ppg_last_error()
+    ref = capi.SceneArrays(sc).desc
+    assert (d.n_vertices, d.n_triangles, d.n_shapes, d.n_bsdfs, d.n_emitters, d.n_textures, d.n_texels) == (ref.n_vertices, ref.n_triangles, ref.n_shapes, ref.n_bsdfs, ref.n_emitters, ref.n_textures, ref.n_texels)
+    as_np = lambda ptr, n, t: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(t)), shape=(n,)).copy()
+    assert np.array_equal(as_np(d.positions, 3 * d.n_vertices, C.c_float), sc.positions.reshape(-1)) and np.array_equal(as_np(d.indices, 3 * d.n_triangles, C.c_uint32), sc.indices.reshape(-1))
+    assert np.array_equal(as_np(d.bsdfs, 28 * d.n_bsdfs, C.c_float).view(np.uint32), np.asarray(sc.bsdfs, np.float32).reshape(-1).view(np.uint32))
+    assert np.array_equal(as_np(d.texels, d.n_texels, C.c_uint16), sc.texels) and bytes(as_np(d.textures, 48 * d.n_textures, C.c_uint8)) == sc.textures.tobytes()
+    assert (d.envmap.width, d.envmap.height) == (32, 16) and np.array_equal(as_np(d.envmap.texels, 32 * 16 * 3, C.c_uint16), sc.envmap["texels"].reshape(-1))
+    assert np.isclose(d.envmap.scale, 1.5) and np.allclose(list(d.envmap.world_to_env), np.asarray(sc.envmap["world_to_env"]).reshape(-1))
+    assert (d.camera.film_width, d.camera.film_height) == (sc.film_width, sc.film_height) and np.isclose(d.camera.x_fov_deg, sc.x_fov_deg)
+    assert dict(l.split("=", 1) for l in props.value.decode().splitlines()) == sc.integrator
+    lib.ppg_scene_file_free(fh)
+    assert lib.ppg_scene_file_load(str(tmp_path / "missing").encode(), C.byref(d), C.byref(fh), None) == -7      # PPG_ERR_IO
