@@ -1025,9 +1025,11 @@ __device__ __forceinline__ float sum4(float4 s, int i) { return i == 0 ? s.x : (
 // coordinate (p < 0.5 ? 2p : 2p-1 is exact in fp32), so a prefix table indexed by the interleaved digits replaces them
 // with ONE load; the walk then continues from the table's node with the exact remainders 2^B*p - floor(2^B*p).
 // Table entry: node | levels<<24 | leaf<<31 (built by stree_table_kernel after every refine).
-#define PPG_STREE_TABLE_BITS 6                     // digits per axis -> 3*6 = 18 levels, 2^18 entries (1 MB, L2 resident)
-__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // bit i -> bit 3i (6 bits)
-    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8) | ((v & 32u) << 10);
+#ifndef PPG_STREE_TABLE_BITS
+#define PPG_STREE_TABLE_BITS 7                     // digits per axis -> 3*7 = 21 levels, 2^21 entries (8 MB, L2 resident; CBOX 1024^2 descends 18.5 levels on average)
+#endif
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // bit i -> bit 3i (7 bits)
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8) | ((v & 32u) << 10) | ((v & 64u) << 12);
 }
 __device__ __forceinline__ uint32_t stree_lookup(const uint2 *__restrict__ snodes, const uint32_t *__restrict__ table, float3 aabbMin, float3 extent,
                                                  float3 pw, int &levels) {

@@ -949,6 +949,9 @@ static int reset_sd_tree(ppg_integrator *h) {
     dtree_reset_kernel<true><<<blocks, 128, 0, h->stream>>>(M, h->dBuildBase.p, 20, h->prm.d_tree_threshold); h->launches++;
     leaf_after_reset_kernel<<<blocks, 256, 0, h->stream>>>(M, h->dBuildBase.p); h->launches++;
     h->toc();
+    // prefix table of the refined S-tree (stree_lookup): the first 3 * PPG_STREE_TABLE_BITS levels of every descent become one load
+    CK(h->dStable.alloc((size_t) 1 << (3 * PPG_STREE_TABLE_BITS)));
+    h->tic(PPG_K_REFINE); stree_table_kernel<<<h->numSMs * 8, 256, 0, h->stream>>>(h->dSnodes.p, h->dStable.p); h->toc(); h->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream)); h->resolve_timers();
     return PPG_OK;

@@ -20,7 +20,7 @@ def assert_render_parity(img, ref, st, ost, sc=None, props=None, pixels=0.90, me
     if sc is not None:
         import oracle_lib as O
         from ppg_b200.integrator import GuidedPathTracer
-        p1 = dict(props, budgetType="spp", budget=props.get("sppPerPass", "4"))
+        p1 = dict(props, budgetType="spp", budget=props.get("sppPerPass", "4"), sampleCombination="automatic")      # (inversevar weights a one-sample iteration by 1 / inf)
         g = GuidedPathTracer(p1); g.set_scene(sc); i1, s1 = g.render(); g.close()
         o = O.Oracle(O.params_from_xml(p1), sc, kind="port"); r1, os1 = o.render(); o.close()
         assert abs(s1["total_vertices"] - os1["total_vertices"]) <= max(2, 2e-4 * os1["total_vertices"]), (s1["total_vertices"], os1["total_vertices"])
