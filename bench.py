@@ -90,46 +90,76 @@ def converged_reference(scene, w, h):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md's clocks line). NVML is polled from a thread
+    every 10 ms (nvidia-smi -lms needs >100 ms to start, longer than an 8-GPU timed region); nvidia-smi is the fallback."""
 
-    def __init__(self, index=0):
-        self.index = index; self.rows = []; self.proc = None
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+    def __init__(self, index=0, uuid=None):
+        self.index = index; self.uuid = uuid; self.rows = []; self.active = False; self.stopflag = False; self.thread = None; self.kind = None
+        self.max_mhz = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            def poll():
+                while not self.stopflag:
+                    if self.active:
+                        try:
+                            self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                        except Exception:
+                            pass
+                    time.sleep(0.01)
+            self.kind = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True); self.thread.start()
+            return
+        except Exception:
+            pass
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def read():
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) < 6 or not self.active:
+                        continue
+                    try:
+                        mask = sum(self.REASONS[n] for n, v in zip(names, f[2:6]) if v.lower().startswith("active"))
+                        self.rows.append((float(f[0]), mask)); self.max_mhz = float(f[1])
+                    except ValueError:
+                        pass
+            self.kind = "nvidia-smi"
+            self.thread = threading.Thread(target=read, daemon=True); self.thread.start()
+            time.sleep(0.5)
+        except Exception:
+            self.kind = None
+
+    def region(self, on):
+        self.active = bool(on)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        self.stopflag = True; self.active = False
+        if self.kind == "nvidia-smi":
+            self.proc.terminate()
+        if self.kind is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted(n for n, bit in self.REASONS.items() if any(r[1] & bit for r in self.rows))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": self.kind}
 
 
 def scene_props(args, sc, budget=None):
@@ -218,7 +248,7 @@ def reference_arm(args):
     ref = converged_reference(args.scene, w, h) if same else None
     if ref is not None:
         line["relmse"] = {"reference_algorithm": relmse(vals[-1]["image"], ref), "spp": budget, "against": f"scenes/ref/{args.scene}_{w}x{h}_ref.npy"}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -253,10 +283,15 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- `value`: inputs resident in HBM, film left in HBM
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid); sampler.start()
     for _ in range(args.warmup):
         g.render_device()
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.region(True)
     t0 = time.perf_counter()
     stats = []
     for _ in range(args.steps):
@@ -264,7 +299,7 @@ def gpu_arm(args):
         stats.append(st)
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    sampler.region(False)
     dev_ms = sum(s["render_device_ms"] for s in stats)          # CUDA events on the library's launching stream
     verts = sum(s["total_vertices"] for s in stats); paths = sum(s["total_paths"] for s in stats)
     launches = sum(s["kernel_launches"] for s in stats)
@@ -283,6 +318,7 @@ def gpu_arm(args):
     d2h = args.width * args.height * 3 * 4
     barrier()
     e2e_steps = max(1, min(args.steps, 3))
+    sampler.region(True)
     t0 = time.perf_counter(); ev = 0; img = None
     for _ in range(e2e_steps):
         g.set_scene(sc)
@@ -292,6 +328,7 @@ def gpu_arm(args):
         ev += st["total_vertices"]
     barrier()
     e2e_wall = time.perf_counter() - t0
+    clocks = sampler.stop()                                      # samples cover both timed regions (device-resident and end-to-end)
     if dist is not None:
         t = torch.tensor([e2e_wall], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_wall = float(t[0])
         c = torch.tensor([ev], device="cuda", dtype=torch.float64); dist.all_reduce(c, op=dist.ReduceOp.SUM); ev = int(c[0])
@@ -364,9 +401,29 @@ def gpu_arm(args):
         for it in stats[-1]["iterations"]:
             print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in it.items() if k in ("iteration", "passes", "seconds", "reset_seconds", "build_seconds", "variance", "s_tree_leaves", "vertices", "nodes_avg", "depth_avg", "s_tree_depth_avg")}, file=sys.stderr)
         print({"render_device_ms": stats[-1]["render_device_ms"], "render_seconds": stats[-1]["render_seconds"], "kernel_ms": stats[-1]["kernel_ms"]}, file=sys.stderr)
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner, ...) is sent to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -385,6 +442,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     _, W, H, spp, _ = SCENES[args.scene]
     args.width = args.size or W
     args.height = (args.size * H // W) if args.size else H

@@ -311,8 +311,11 @@ void ppg_destroy(ppg_integrator *h);
 /* Upload the scene (builds the BVH on the host, copies everything to HBM). */
 int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *scene);
 
-/* Tile sharding: this process renders only the 32x32 image blocks
- * whose index (row-major over blocks) satisfies block % world_size == rank.
+/* Tile sharding: this process renders only its share of the 32x32
+ * image blocks.  The blocks are dealt round-robin to the ranks along a
+ * scattered order (block j*s mod B goes to rank j mod world_size, s = the
+ * golden-ratio stride coprime to the block count B), so that every rank's
+ * blocks cover the whole image and the shares differ by at most one block.
  * Default is rank 0 of 1. */
 int ppg_set_shard(ppg_integrator *h, int rank, int world_size);
 

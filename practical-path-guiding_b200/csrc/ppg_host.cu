@@ -313,6 +313,8 @@ struct ppg_integrator {
     int device = 0, numSMs = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
+    TreeStats *hTreeStats = nullptr; bool treeStatsPending[PPG_MAX_ITERATIONS] = {};       // pinned; see build_sd_tree
+    cudaEvent_t evLive[2] = {nullptr, nullptr}; uint32_t *liveHost = nullptr;   // pinned read-backs of the live counts, looked at one check point late
     std::atomic<bool> cancelled{false};
     std::string destination;
     int rank = 0, world = 1;
@@ -352,18 +354,18 @@ struct ppg_integrator {
     int gridBounce = 0, gridCommit = 0;
 
     // per-kernel-class CUDA-event timing on the launching stream
-    struct Timed { cudaEvent_t a, b; int cls; };
+    struct Timed { cudaEvent_t a, b; int cls; uint32_t launches; };
     std::vector<Timed> evPool; size_t evUsed = 0; cudaEvent_t evRender0 = nullptr, evRender1 = nullptr;
     bool kernelTiming = true;
     void tic(int cls) {
         if (!kernelTiming) return;
-        if (evUsed == evPool.size()) { Timed t; cudaEventCreate(&t.a); cudaEventCreate(&t.b); t.cls = cls; evPool.push_back(t); }
-        evPool[evUsed].cls = cls; cudaEventRecord(evPool[evUsed].a, stream);
+        if (evUsed == evPool.size()) { Timed t; cudaEventCreate(&t.a); cudaEventCreate(&t.b); t.cls = cls; t.launches = 1; evPool.push_back(t); }
+        evPool[evUsed].cls = cls; evPool[evUsed].launches = 1; cudaEventRecord(evPool[evUsed].a, stream);
     }
-    void toc() { if (!kernelTiming) return; cudaEventRecord(evPool[evUsed].b, stream); ++evUsed; }
+    void toc(uint32_t nLaunches = 1) { if (!kernelTiming) return; evPool[evUsed].launches = nLaunches; cudaEventRecord(evPool[evUsed].b, stream); ++evUsed; }   // one bracket may hold several launches of a class
     void resolve_timers() {   // call after a stream synchronize
         for (size_t i = 0; i < evUsed; ++i) {
-            float ms = 0; if (cudaEventElapsedTime(&ms, evPool[i].a, evPool[i].b) == cudaSuccess) { stats.kernel_ms[evPool[i].cls] += ms; stats.kernel_count[evPool[i].cls]++; }
+            float ms = 0; if (cudaEventElapsedTime(&ms, evPool[i].a, evPool[i].b) == cudaSuccess) { stats.kernel_ms[evPool[i].cls] += ms; stats.kernel_count[evPool[i].cls] += evPool[i].launches; }
         }
         evUsed = 0;
     }
@@ -382,6 +384,9 @@ struct ppg_integrator {
         if (evRender1) cudaEventDestroy(evRender1);
         if (evA) cudaEventDestroy(evA);
         if (evB) cudaEventDestroy(evB);
+        for (auto &e : evLive) if (e) cudaEventDestroy(e);
+        if (liveHost) cudaFreeHost(liveHost);
+        if (hTreeStats) cudaFreeHost(hTreeStats);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -409,6 +414,9 @@ extern "C" int ppg_create(const ppg_params *params, int device, ppg_integrator *
     h->numSMs = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->evA)); CK(cudaEventCreate(&h->evB)); CK(cudaEventCreate(&h->evRender0)); CK(cudaEventCreate(&h->evRender1));
+    for (auto &e : h->evLive) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaHostAlloc((void **) &h->liveHost, 128 * sizeof(uint32_t), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **) &h->hTreeStats, PPG_MAX_ITERATIONS * sizeof(TreeStats), cudaHostAllocDefault));
     if (const char *e = getenv("PPG_KERNEL_TIMING")) h->kernelTiming = atoi(e) != 0;
     memset(&h->stats, 0, sizeof(h->stats));
     *out = h;
@@ -505,11 +513,21 @@ static int allreduce_sum(ppg_integrator *h, float *dev, size_t n) {
 }
 
 static int build_pixel_map(ppg_integrator *h) {
-    // 32x32 image blocks (scene.cpp:24), row-major over blocks, interleaved across ranks; row-major inside a block
-    const int bs = 32, bx = (h->W + bs - 1) / bs, by = (h->H + bs - 1) / bs;
+    // 32x32 image blocks (scene.cpp:24), dealt to the ranks round-robin along a scattered order of the blocks (golden-ratio stride, coprime to
+    // the block count): every rank's blocks are spread over the whole image whatever the image width (plain `block % world` gives each rank
+    // whole COLUMNS of blocks when the blocks per row are a multiple of the world size, and the columns of an image do not cost the same).
+    // A rank visits its blocks row-major; row-major inside a block.
+    const int bs = 32, bx = (h->W + bs - 1) / bs, by = (h->H + bs - 1) / bs, nb = bx * by;
+    std::vector<int> owner((size_t) nb, 0);
+    if (h->world > 1) {
+        auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
+        uint64_t stride = std::max<uint64_t>(1, (uint64_t) ((double) nb * 0.6180339887498949));
+        while (gcd(stride, (uint64_t) nb) != 1) ++stride;
+        for (uint64_t j = 0; j < (uint64_t) nb; ++j) owner[(j * stride) % nb] = (int) (j % h->world);
+    }
     std::vector<uint32_t> map; map.reserve((size_t) h->W * h->H / h->world + 1024);
-    for (int b = 0; b < bx * by; ++b) {
-        if (b % h->world != h->rank) continue;
+    for (int b = 0; b < nb; ++b) {
+        if (owner[b] != h->rank) continue;
         const int x0 = (b % bx) * bs, y0 = (b / bx) * bs;
         if (env_int("PPG_PIXEL_ORDER", 0) == 1) {      // experiment: Morton order inside the block (results do not depend on the order)
             for (uint32_t m = 0; m < (uint32_t) (bs * bs); ++m) {
@@ -526,7 +544,7 @@ static int build_pixel_map(ppg_integrator *h) {
     h->minLocalPixels = 0xffffffffu; h->maxLocalPixels = 0;   // smallest / largest share of any rank: decisions every rank must take alike
     for (int r = 0; r < h->world; ++r) {
         uint64_t c = 0;
-        for (int b = r; b < bx * by; b += h->world) { const int x0 = (b % bx) * bs, y0 = (b / bx) * bs; c += (uint64_t) (std::min(x0 + bs, h->W) - x0) * (std::min(y0 + bs, h->H) - y0); }
+        for (int b = 0; b < nb; ++b) { if (owner[b] != r) continue; const int x0 = (b % bx) * bs, y0 = (b / bx) * bs; c += (uint64_t) (std::min(x0 + bs, h->W) - x0) * (std::min(y0 + bs, h->H) - y0); }
         h->minLocalPixels = std::min<uint32_t>(h->minLocalPixels, (uint32_t) c); h->maxLocalPixels = std::max<uint32_t>(h->maxLocalPixels, (uint32_t) c);
     }
     CK(h->dPixelMap.alloc(std::max<size_t>(map.size(), 1)));
@@ -953,8 +971,7 @@ static int reset_sd_tree(ppg_integrator *h) {
     CK(h->dStable.alloc((size_t) 1 << (3 * PPG_STREE_TABLE_BITS)));
     h->tic(PPG_K_REFINE); stree_table_kernel<<<h->numSMs * 8, 256, 0, h->stream>>>(h->dSnodes.p, h->dStable.p); h->toc(); h->launches++;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream)); h->resolve_timers();
-    return PPG_OK;
+    return PPG_OK;      // no synchronize: the passes queue behind the reset
 }
 
 // the one exchange step: sum the building statistics over all ranks
@@ -993,20 +1010,28 @@ static int build_sd_tree(ppg_integrator *h, ppg_iteration_stats &st) {
     // "Distribution statistics" (GP:1121-1186): reduced on the device, 64 bytes come back
     CK(cudaMemsetAsync(h->dTreeStats.p, 0, sizeof(TreeStats), h->stream));
     tree_stats_kernel<<<1, 1024, 0, h->stream>>>(M, h->dTreeStats.p); h->launches++;
-    TreeStats ts;
-    CK(cudaMemcpyAsync(&ts, h->dTreeStats.p, sizeof(ts), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream)); h->resolve_timers();
-    const uint32_t n = h->hNodes;
-    const int nPoints = (int) ts.leaves, nPointsNodes = (int) ts.leavesWithNodes;
-    float avgDepth = (float) ts.depthSum, avgR = (float) ts.meanSum, avgN = (float) ts.nodesSum, avgW = (float) ts.weightSum;
-    if (nPoints > 0) { avgDepth /= nPoints; avgR /= nPoints; if (nPointsNodes > 0) avgN /= nPointsNodes; avgW /= nPoints; }
-    st.depth_min = nPoints ? ts.depthMin : std::numeric_limits<int>::max(); st.depth_max = ts.depthMax; st.depth_avg = avgDepth;
-    st.mean_radiance_min = nPoints ? ts.meanMin : std::numeric_limits<float>::max(); st.mean_radiance_avg = avgR; st.mean_radiance_max = ts.meanMax;
-    st.nodes_min = nPointsNodes ? ts.nodesMin : std::numeric_limits<size_t>::max(); st.nodes_max = ts.nodesMax; st.nodes_avg = avgN;
-    st.weight_min = nPoints ? ts.weightMin : std::numeric_limits<float>::max(); st.weight_avg = avgW; st.weight_max = ts.weightMax;
-    st.s_tree_nodes = n; st.s_tree_leaves = ts.leaves;
+    // the statistics are only reported: they go to pinned memory and are folded into ppg_stats after the render's last synchronize
+    const int slot = std::min(h->iter, PPG_MAX_ITERATIONS - 1);
+    CK(cudaMemcpyAsync(h->hTreeStats + slot, h->dTreeStats.p, sizeof(TreeStats), cudaMemcpyDeviceToHost, h->stream));
+    h->treeStatsPending[slot] = true;
+    st.s_tree_nodes = h->hNodes;
     h->isBuilt = true;
     return PPG_OK;
+}
+static void finish_tree_stats(ppg_integrator *h) {      // after a stream synchronize
+    for (int i = 0; i < PPG_MAX_ITERATIONS; ++i) {
+        if (!h->treeStatsPending[i]) continue;
+        h->treeStatsPending[i] = false;
+        const TreeStats &ts = h->hTreeStats[i]; ppg_iteration_stats &st = h->stats.iterations[i];
+        const int nPoints = (int) ts.leaves, nPointsNodes = (int) ts.leavesWithNodes;
+        float avgDepth = (float) ts.depthSum, avgR = (float) ts.meanSum, avgN = (float) ts.nodesSum, avgW = (float) ts.weightSum;
+        if (nPoints > 0) { avgDepth /= nPoints; avgR /= nPoints; if (nPointsNodes > 0) avgN /= nPointsNodes; avgW /= nPoints; }
+        st.depth_min = nPoints ? ts.depthMin : std::numeric_limits<int>::max(); st.depth_max = ts.depthMax; st.depth_avg = avgDepth;
+        st.mean_radiance_min = nPoints ? ts.meanMin : std::numeric_limits<float>::max(); st.mean_radiance_avg = avgR; st.mean_radiance_max = ts.meanMax;
+        st.nodes_min = nPointsNodes ? ts.nodesMin : std::numeric_limits<size_t>::max(); st.nodes_max = ts.nodesMax; st.nodes_avg = avgN;
+        st.weight_min = nPoints ? ts.weightMin : std::numeric_limits<float>::max(); st.weight_avg = avgW; st.weight_max = ts.weightMax;
+        st.s_tree_leaves = ts.leaves;
+    }
 }
 
 // ------------------------------------------------------------------ wavefront buffers
@@ -1107,7 +1132,7 @@ static int render_batch(ppg_integrator *h, int nPasses, const uint32_t *pixelMap
         PathState A = path_state(h->dStateA.p, h->pathCapacity, nee), B = path_state(h->dStateB.p, h->pathCapacity, nee);
         const int bb = h->sceneSmemBytes ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM;
         const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + bb - 1) / bb));
-        int lastDepth = 0;
+        int lastDepth = 0, pendingDepth = 0; uint32_t bracket = 0;
         for (int depth = 1; depth <= h->maxBounces; ++depth) {
             P.depth = depth; P.in = (depth & 1) ? B : A; P.out = (depth & 1) ? A : B;
             P.liveIn = h->dLive.p + (depth - 1); P.liveOut = h->dLive.p + depth; P.work = h->dWork.p + depth;
@@ -1115,22 +1140,27 @@ static int render_batch(ppg_integrator *h, int nPasses, const uint32_t *pixelMap
             P.slab = slab_at(h, k);
             if (nee) { P.neeSlab = slab_at(h, k, 1); P.prevSlab = slab_at(h, std::max(k - 1, 0)); if (depth - 1 >= h->nSlabs) P.prevSlab = slab_at(h, h->nSlabs - 1); }
             const int rec = (depth - 1 < h->nSlabs) ? record : 0;
-            if (h->cancelled.load()) return PPG_ERR_CANCELLED;                 // Integrator::cancel() (GP:1643-1648): the batch in flight is dropped
-            h->tic(PPG_K_BOUNCE);
-            launch_bounce(h, P, depth == 1, rec, grid, nee);
-            h->toc();
+            if (h->cancelled.load()) { if (bracket) h->toc(bracket); return PPG_ERR_CANCELLED; }   // Integrator::cancel() (GP:1643-1648): the batch in flight is dropped
+            if (!bracket) h->tic(PPG_K_BOUNCE);                                // one event pair around the consecutive bounce launches (2 records per launch were
+            launch_bounce(h, P, depth == 1, rec, grid, nee);                   // ~1.5 ms of host time per CBOX step: visible at 8 GPUs, where a step takes 38 ms)
+            ++bracket;
             lastDepth = depth;
-            // unbounded path length (maxDepth == -1 runs up to the 64-bounce cap): stop launching once the wavefront is empty.  One tiny
-            // read-back at a few depths; the stream is busy with the launches queued before it, so the host only waits where it would anyway.
-            const bool small = nPaths <= 65536u;          // small wavefronts are launch bound: look every 4 bounces
-            if ((h->prm.max_depth <= 0 || small) && depth < h->maxBounces &&
-                (depth == 8 || depth == 12 || depth == 16 || depth == 24 || depth == 32 || depth == 48 || (small && depth >= 4 && depth % 4 == 0))) {
-                uint32_t live = 1;
-                CK(cudaMemcpyAsync(&live, h->dLive.p + depth, 4, cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaStreamSynchronize(h->stream));
-                if (live == 0) break;
+            // unbounded path length (maxDepth == -1 runs up to the 64-bounce cap): stop launching once the wavefront is empty.  The live count is
+            // copied to pinned memory at every check point and LOOKED AT one check point later, after the next launches are queued: the host
+            // never drains the stream (a blocking read-back cost ~25 us of idle GPU per check: 3-5 ms per CBOX step), and a dead wavefront costs
+            // at most two check intervals of empty launches (~2 us each).
+            const bool small = nPaths <= 65536u;          // small wavefronts are launch bound: look every 4 bounces from the start
+            if ((h->prm.max_depth <= 0 || small) && depth < h->maxBounces && depth % 4 == 0 && (small || depth >= 8)) {
+                CK(cudaMemcpyAsync(h->liveHost + depth, h->dLive.p + depth, 4, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaEventRecord(h->evLive[(depth >> 2) & 1], h->stream));
+                if (pendingDepth) {
+                    CK(cudaEventSynchronize(h->evLive[(pendingDepth >> 2) & 1]));
+                    if (h->liveHost[pendingDepth] == 0) break;
+                }
+                pendingDepth = depth;
             }
         }
+        if (bracket) h->toc(bracket);
         {   // survivors of the bounce cap (maxDepth == -1 only) keep the radiance they have; they are counted (ppg_stats.truncated_paths)
             const PathState last = (lastDepth & 1) ? A : B;
             flush_kernel<<<std::max(grid / 4, 1), PPG_BLOCK, 0, h->stream>>>(last, h->dLive.p + lastDepth, h->dLiFinal.p, h->dCounters.p + 3); h->launches++;
@@ -1324,7 +1354,7 @@ static int render_spp(ppg_integrator *h) {
         int rc = clear_film(h); if (rc) return rc;
         auto t0 = std::chrono::steady_clock::now();
         rc = reset_sd_tree(h); if (rc) return rc;
-        CK(cudaStreamSynchronize(h->stream)); st.reset_seconds = elapsed_s(t0);
+        st.reset_seconds = elapsed_s(t0);                               // host time up to the node-count read-back inside the reset
         float variance = 0;
         rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
         rc = flush_film(h); if (rc) return rc;
@@ -1360,7 +1390,7 @@ static int render_time(ppg_integrator *h) {
         const auto startIter = std::chrono::steady_clock::now(); const float startIterClock = h->clock_s();
         int rc = clear_film(h); if (rc) return rc;
         rc = reset_sd_tree(h); if (rc) return rc;
-        CK(cudaStreamSynchronize(h->stream)); st.reset_seconds = elapsed_s(startIter);
+        st.reset_seconds = elapsed_s(startIter);
         float variance = 0;
         rc = perform_render_passes(h, variance, passesThisIteration, st); if (rc) return rc;
         rc = flush_film(h); if (rc) return rc;
@@ -1399,6 +1429,7 @@ extern "C" int ppg_render_device(ppg_integrator *h, float **rgb_dev, ppg_stats *
     h->cancelled.store(false);
     const auto wall0 = std::chrono::steady_clock::now();
     memset(&h->stats, 0, sizeof(h->stats)); h->launches = 0; h->deviceMs = 0; h->evUsed = 0;
+    memset(h->treeStatsPending, 0, sizeof(h->treeStatsPending));
     CK(cudaEventRecord(h->evRender0, h->stream));
     int rc = init_tree(h); if (rc) return rc;                                   // m_sdTree = new STree(scene->getAABB()), GP:1519
     rc = ensure_wavefront(h); if (rc) return rc;
@@ -1426,6 +1457,7 @@ extern "C" int ppg_render_device(ppg_integrator *h, float **rgb_dev, ppg_stats *
     }
     CK(cudaEventRecord(h->evRender1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->resolve_timers(); finish_tree_stats(h);
     { float ms = 0; cudaEventElapsedTime(&ms, h->evRender0, h->evRender1); h->stats.render_device_ms = ms; }
     if (!h->ncclComm && h->multi()) {      // callback path: the collective runs outside the library's stream, after the timed region
         int rc2 = allreduce_sum(h, h->dRgb.p, 3 * npx); if (rc2) return rc2;
