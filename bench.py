@@ -177,7 +177,7 @@ def workload_config(args, bounded=None):
                                     f"budgetType=spp budget={args.budget}" + (" (equal-spp stand-in for the 60 s budget of BASELINE config 2)" if args.scene == "cbox" else "")),
          "scene": f"scenes/{SCENES[args.scene][0]}.npz" if not SCENES[args.scene][0].startswith("builtin") else "ppg_b200.builtin_scenes.torus_scene",
          "width": args.width, "height": args.height,
-         "sharding": f"32x32 image blocks interleaved over {args.gpus} rank(s); one NCCL allreduce of the D-tree sums per training iteration, enqueued on the render stream by the library",
+         "sharding": f"32x32 image blocks dealt round-robin in a scattered order over {args.gpus} rank(s); one NCCL allreduce of the D-tree sums per training iteration, enqueued on the render stream by the library",
          "l2": "inputs larger than L2: path state + vertex records of one pass-batch are ~1 GB, every kernel streams them once"}
     if bounded:
         c["bounded_sample"] = bounded

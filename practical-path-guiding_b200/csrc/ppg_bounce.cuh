@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
                 d = P.cam.left * dl.x + P.cam.up * dl.y + P.cam.dir * dl.z;
                 thr = f3(1, 1, 1); Li = f3(0, 0, 0);
             } else {
-                const float4 a = P.in.s0[i], b = P.in.s1[i], c = P.in.s2[i], e = P.in.s3[i], f = P.in.s4[i];
+                const float4 a = __ldcs(&P.in.s0[i]), b = __ldcs(&P.in.s1[i]), c = __ldcs(&P.in.s2[i]), e = __ldcs(&P.in.s3[i]), f = __ldcs(&P.in.s4[i]);   // streamed once: evict-first keeps the L2 for the trees
                 o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y); thr = f3(b.z, b.w, c.x); eta = c.y; Li = f3(c.z, c.w, e.x);
                 pathId = __float_as_uint(e.y);
                 rng.state = ((uint64_t) __float_as_uint(e.w) << 32) | __float_as_uint(e.z);
@@ -61,21 +61,26 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
                 rng.inc = (sampleIndex << 1) | 1u;
                 const uint32_t nf = __float_as_uint(f.z); nVertices = nf & 0xffu; flags = nf >> 8;
                 rrRecip = f.w;
-                if (NEE) { const float4 g5 = P.in.s5[i], g6 = P.in.s6[i]; prevWoPdf = g5.x; prevRefN = f3(g5.y, g5.z, g5.w); prevSlot = __float_as_uint(g6.x); }
+                if (NEE) { const float4 g5 = __ldcs(&P.in.s5[i]), g6 = __ldcs(&P.in.s6[i]); prevWoPdf = g5.x; prevRefN = f3(g5.y, g5.z, g5.w); prevSlot = __float_as_uint(g6.x); }
                 // adaptive ray epsilon of rays leaving a surface (skdtree.cpp:125-128)
                 mint = PPG_EPSILON * fmaxf(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), PPG_EPSILON);
                 maxt = __int_as_float(0x7f800000);
             }
         }
         bool wroteVertex = false, wroteNee = false, unscattered = FIRST;
+        Hit hit; bool rayOk = false, found = false;
         if (alive) {
             ++raysLocal;
-            Hit hit;
             // a ray with a non-finite origin or direction (a BSDF sample gone wrong) would pass every node's slab test and walk the whole
             // tree; the reference's kd-tree clips such a ray away (AABB::rayIntersect fails on NaN comparisons): a miss.  Counted in counters[5].
-            const bool rayOk = isfinite(o.x + o.y + o.z) && isfinite(d.x + d.y + d.z);
+            rayOk = isfinite(o.x + o.y + o.z) && isfinite(d.x + d.y + d.z);
             if (!rayOk) atomicAdd(&P.counters[5], 1ull);
-            const bool found = rayOk && bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
+            found = rayOk && bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
+        }
+        // the lanes leave the walk at different times: make them wait for each other HERE, so that shading runs with the whole warp (without
+        // the barrier the scheduler may carry the early leavers through the shading code on their own)
+        __syncwarp();
+        if (alive) {
             bool cont = found;
             if (FULL && !found && rayOk && P.scene.envW) {
                 // the ray left the scene: radiance of the environment emitter.  Camera rays and rays that have only crossed index-matched surfaces
@@ -213,13 +218,13 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
                                 const float3 L = thr * (ds.value * bsdfVal) * mi_weight(ds.pdf, nWoPdf);
                                 if (RECORD && P.neeMode != 2) {                          // GP:1999-2016: half-weight vertex with a fixed radiance
                                     const float3 tv = thr * bsdfVal * (1.0f / ds.pdf);
-                                    P.neeSlab.v0[i] = make_float4(ds.d.x, ds.d.y, ds.d.z, ds.pdf);
-                                    P.neeSlab.v1[i] = make_float4(tv.x, tv.y, tv.z, __uint_as_float(leaf));
-                                    P.neeSlab.v2[i] = make_float4(L.x, L.y, L.z, __uint_as_float(pathId | 0x40000000u));   // bit 30: absolute radiance
-                                    P.neeSlab.v3[i] = make_float4(bsdfVal.x, bsdfVal.y, bsdfVal.z, nBsdfPdf);
-                                    P.neeSlab.v4[i] = make_float4(its.p.x, its.p.y, its.p.z, nDTreePdf);
-                                    P.neeSlab.v5[i] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
-                                                                  __uint_as_float((uint32_t) levels | ((32u + (uint32_t) P.depth) << 8)), 0.f);
+                                    __stcs(&P.neeSlab.v0[i], make_float4(ds.d.x, ds.d.y, ds.d.z, ds.pdf));
+                                    __stcs(&P.neeSlab.v1[i], make_float4(tv.x, tv.y, tv.z, __uint_as_float(leaf)));
+                                    __stcs(&P.neeSlab.v2[i], make_float4(L.x, L.y, L.z, __uint_as_float(pathId | 0x40000000u)));   // bit 30: absolute radiance
+                                    __stcs(&P.neeSlab.v3[i], make_float4(bsdfVal.x, bsdfVal.y, bsdfVal.z, nBsdfPdf));
+                                    __stcs(&P.neeSlab.v4[i], make_float4(its.p.x, its.p.y, its.p.z, nDTreePdf));
+                                    __stcs(&P.neeSlab.v5[i], make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
+                                                                  __uint_as_float((uint32_t) levels | ((32u + (uint32_t) P.depth) << 8)), 0.f));
                                     wroteNee = true;
                                 }
                                 Li = Li + L;                                             // recordRadiance(L)
@@ -238,15 +243,15 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
                     thr = thr * bsdfWeight; eta *= bsEta;
                     // ---- vertex record (GP:2093-2110); its radiance is Li_final - Li_prefix
                     if (RECORD && smooth && (!isDelta || P.lossMode != 0) && nVertices < PPG_MAX_VERTICES && (1.f / woPdf > 0.f)) {
-                        P.slab.v0[i] = make_float4(d.x, d.y, d.z, woPdf);
-                        P.slab.v1[i] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(leaf));
-                        P.slab.v2[i] = make_float4(Li.x, Li.y, Li.z, __uint_as_float(pathId | (isDelta ? 0x80000000u : 0u)));
+                        __stcs(&P.slab.v0[i], make_float4(d.x, d.y, d.z, woPdf));
+                        __stcs(&P.slab.v1[i], make_float4(thr.x, thr.y, thr.z, __uint_as_float(leaf)));
+                        __stcs(&P.slab.v2[i], make_float4(Li.x, Li.y, Li.z, __uint_as_float(pathId | (isDelta ? 0x80000000u : 0u))));
                         if (RECORD == 2) {
                             const float3 bv = bsdfWeight * woPdf;
-                            P.slab.v3[i] = make_float4(bv.x, bv.y, bv.z, bsdfPdf);
-                            P.slab.v4[i] = make_float4(o.x, o.y, o.z, dTreePdf);
-                            P.slab.v5[i] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
-                                                       __uint_as_float((uint32_t) levels | (nVertices << 8)), 0.f);
+                            __stcs(&P.slab.v3[i], make_float4(bv.x, bv.y, bv.z, bsdfPdf));
+                            __stcs(&P.slab.v4[i], make_float4(o.x, o.y, o.z, dTreePdf));
+                            __stcs(&P.slab.v5[i], make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
+                                                       __uint_as_float((uint32_t) levels | (nVertices << 8)), 0.f));
                         }
                         wroteVertex = true; ++nVertices; ++recLocal; levelsLocal += levels;
                     }
@@ -266,23 +271,23 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
                 }
             }
             if (!cont) {
-                P.liFinal[pathId] = make_float4(Li.x, Li.y, Li.z, 1.f);
+                __stcs(&P.liFinal[pathId], make_float4(Li.x, Li.y, Li.z, 1.f));
                 alive = false;
             }
         }
-        if (RECORD && i < nIn && !wroteVertex) P.slab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
-        if (NEE && RECORD && P.neeMode != 2 && i < nIn && !wroteNee) P.neeSlab.v2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID));
+        if (RECORD && i < nIn && !wroteVertex) __stcs(&P.slab.v2[i], make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID)));
+        if (NEE && RECORD && P.neeMode != 2 && i < nIn && !wroteNee) __stcs(&P.neeSlab.v2[i], make_float4(0.f, 0.f, 0.f, __uint_as_float(PPG_INVALID)));
         const uint32_t slot = warp_compact(alive, P.liveOut);
         if (alive) {
-            P.out.s0[slot] = make_float4(o.x, o.y, o.z, d.x);
-            P.out.s1[slot] = make_float4(d.y, d.z, thr.x, thr.y);
-            P.out.s2[slot] = make_float4(thr.z, eta, Li.x, Li.y);
-            P.out.s3[slot] = make_float4(Li.z, __uint_as_float(pathId), __uint_as_float((uint32_t) rng.state), __uint_as_float((uint32_t) (rng.state >> 32)));
-            P.out.s4[slot] = make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
-                                         __uint_as_float(nVertices | (flags << 8)), rrRecip);
+            __stcs(&P.out.s0[slot], make_float4(o.x, o.y, o.z, d.x));
+            __stcs(&P.out.s1[slot], make_float4(d.y, d.z, thr.x, thr.y));
+            __stcs(&P.out.s2[slot], make_float4(thr.z, eta, Li.x, Li.y));
+            __stcs(&P.out.s3[slot], make_float4(Li.z, __uint_as_float(pathId), __uint_as_float((uint32_t) rng.state), __uint_as_float((uint32_t) (rng.state >> 32))));
+            __stcs(&P.out.s4[slot], make_float4(__uint_as_float((uint32_t) sampleIndex), __uint_as_float((uint32_t) (sampleIndex >> 32)),
+                                         __uint_as_float(nVertices | (flags << 8)), rrRecip));
             if (NEE) {
-                P.out.s5[slot] = make_float4(prevWoPdf, prevRefN.x, prevRefN.y, prevRefN.z);
-                P.out.s6[slot] = make_float4(__uint_as_float(prevSlot), 0.f, 0.f, 0.f);
+                __stcs(&P.out.s5[slot], make_float4(prevWoPdf, prevRefN.x, prevRefN.y, prevRefN.z));
+                __stcs(&P.out.s6[slot], make_float4(__uint_as_float(prevSlot), 0.f, 0.f, 0.f));
             }
         }
     }

@@ -235,17 +235,19 @@ __device__ __noinline__ bool bvh_walk(const Acc &A_, float3 o, float3 d, float m
         if (!slab(r0, r1, te)) return false;
         left = __float_as_uint(r0.w); count = __float_as_uint(r1.w);
     }
+    auto pop = [&]() -> bool {
+        while (sp > 0) {
+            --sp;
+            if (stackT[sp] <= hit.t) { left = stackN[sp] & 0x0fffffffu; count = stackN[sp] >> 28; return true; }
+        }
+        return false;
+    };
+    // "while-while" (Aila & Laine): every lane first descends inner nodes until it HOLDS a leaf (or is done); the warp reconverges
+    // behind that loop, so the triangle tests of all lanes run together instead of one lane's leaf serialising against the other
+    // lanes' box tests in every iteration (ncu, KITCHEN: 3.7 of 32 lanes in the box test, 1.5 in the triangle test before).
+    bool done = false;
     for (;;) {
-        if (count) {
-            for (uint32_t i = left; i < left + count; ++i) {
-                const float4 A = A_.accel(3 * i), B = A_.accel(3 * i + 1), C = A_.accel(3 * i + 2);
-                float u, v, t;
-                if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
-                    const uint32_t prim = __float_as_uint(C.z);
-                    if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i; }
-                }
-            }
-        } else {
+        while (count == 0u && !done) {
             const float4 a0 = A_.bvh(2 * left), a1 = A_.bvh(2 * left + 1), b0 = A_.bvh(2 * left + 2), b1 = A_.bvh(2 * left + 3);
             float ta, tb;
             const bool ha = slab(a0, a1, ta), hb = slab(b0, b1, tb);
@@ -254,17 +256,20 @@ __device__ __noinline__ bool bvh_walk(const Acc &A_, float3 o, float3 d, float m
                 const float4 f0 = aFirst ? b0 : a0, f1 = aFirst ? b1 : a1, n0 = aFirst ? a0 : b0, n1 = aFirst ? a1 : b1;
                 stackN[sp] = __float_as_uint(f0.w) | (__float_as_uint(f1.w) << 28); stackT[sp] = aFirst ? tb : ta; ++sp;
                 left = __float_as_uint(n0.w); count = __float_as_uint(n1.w);
-                continue;
+            } else if (ha) { left = __float_as_uint(a0.w); count = __float_as_uint(a1.w); }
+            else if (hb) { left = __float_as_uint(b0.w); count = __float_as_uint(b1.w); }
+            else done = !pop();
+        }
+        if (done) break;
+        for (uint32_t i = left; i < left + count; ++i) {
+            const float4 A = A_.accel(3 * i), B = A_.accel(3 * i + 1), C = A_.accel(3 * i + 2);
+            float u, v, t;
+            if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
+                const uint32_t prim = __float_as_uint(C.z);
+                if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.tri = i; }
             }
-            if (ha) { left = __float_as_uint(a0.w); count = __float_as_uint(a1.w); continue; }
-            if (hb) { left = __float_as_uint(b0.w); count = __float_as_uint(b1.w); continue; }
         }
-        bool popped = false;
-        while (sp > 0) {
-            --sp;
-            if (stackT[sp] <= hit.t) { left = stackN[sp] & 0x0fffffffu; count = stackN[sp] >> 28; popped = true; break; }
-        }
-        if (!popped) break;
+        if (!pop()) break;
     }
     return hit.prim != 0xFFFFFFFFu;
 }

@@ -392,6 +392,7 @@ struct ppg_integrator {
 };
 
 ppg_integrator::~ppg_integrator() { destroy_body(); }
+static double elapsed_ms(std::chrono::steady_clock::time_point s) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s).count(); }
 static float elapsed_s(std::chrono::steady_clock::time_point s) {
     return (float) std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - s).count() / 1000;
 }
@@ -1255,6 +1256,8 @@ static int perform_render_passes(ppg_integrator *h, float &variance, int numPass
             want = lastSize * std::min(2.0, std::max(0.5, ratio));
             want = std::max(minFrac, std::min(want, std::max(minFrac, growthMax * done)));
             ++h->stats.sub_batches;
+            static const int trace2 = env_int("PPG_TRACE", 0);
+            if (trace2 > 1) fprintf(stderr, "[ppg trace]   sub-batch %.5f passes moved %.4f next %.5f at %.2f ms\n", lastSize, moved, want, elapsed_ms(t0));
         }
         if (frac > 0.0 || want < 1.0) {
             // a slice [frac, f1) of one pass, in the scattered pixel order
@@ -1314,6 +1317,12 @@ static int perform_render_passes(ppg_integrator *h, float &variance, int numPass
     h->stats.total_vertices += cnt[0]; h->stats.total_paths += (uint64_t) local * perPass;
     h->stats.truncated_paths += cnt[3]; h->stats.dropped_records += cnt[4]; h->stats.invalid_rays += cnt[5];
     h->lastRecorded = cnt[1];
+    static const int trace = env_int("PPG_TRACE", 0);
+    if (trace)    // cumulative kernel times after every iteration's passes (stderr): where a render's time goes, iteration by iteration
+        fprintf(stderr, "[ppg trace] iter %d final %d passes %d sub_batches %llu vertices %llu wall %.1f ms | cumulative ms: bounce %.1f commit %.1f adam %.1f other %.1f film %.1f launches %llu\n",
+                h->iter, (int) h->isFinalIter, local, (unsigned long long) h->stats.sub_batches, (unsigned long long) cnt[0], elapsed_ms(t0),
+                h->stats.kernel_ms[PPG_K_BOUNCE], h->stats.kernel_ms[PPG_K_COMMIT], h->stats.kernel_ms[PPG_K_ADAM], h->stats.kernel_ms[PPG_K_OTHER], h->stats.kernel_ms[PPG_K_FILM],
+                (unsigned long long) h->launches);
     return rcode;
 }
 

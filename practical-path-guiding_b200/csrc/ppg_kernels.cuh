@@ -80,18 +80,18 @@ __global__ void __launch_bounds__(PPG_BLOCK) commit_kernel(const CommitParams P)
         bool ok = i < n;
         float4 v0, v1, v2, v4 = make_float4(0, 0, 0, 0), v5 = make_float4(0, 0, 0, 0);
         uint32_t pid = PPG_INVALID;
-        if (ok) { v2 = S.v2[so + i]; pid = __float_as_uint(v2.w); ok = pid != PPG_INVALID; }
+        if (ok) { v2 = __ldcs(&S.v2[so + i]); pid = __float_as_uint(v2.w); ok = pid != PPG_INVALID; }
         float3 d = f3(0, 0, 1), radiance = f3(0, 0, 0), thr = f3(1, 1, 1), bsdfVal = f3(0, 0, 0); float woPdf = 0.f, bsdfPdf = 0.f, dTreePdf = 0.f;
         uint32_t leaf = 0; bool isDelta = false;
         if (ok) {
-            v0 = S.v0[so + i]; v1 = S.v1[so + i];
+            v0 = __ldcs(&S.v0[so + i]); v1 = __ldcs(&S.v1[so + i]);
             isDelta = pid >> 31; const bool absolute = (pid >> 30) & 1u; pid &= 0x3fffffffu;
             const float4 lf = absolute ? make_float4(v2.x * 2.f, v2.y * 2.f, v2.z * 2.f, 0.f) : __ldg(&P.liFinal[pid]);
             d = f3(v0.x, v0.y, v0.z); woPdf = v0.w; thr = f3(v1.x, v1.y, v1.z); leaf = __float_as_uint(v1.w);
             radiance = f3(lf.x - v2.x, lf.y - v2.y, lf.z - v2.z);                  // everything recorded after the vertex was created
             if (RECORD == 2) {
-                const float4 v3 = S.v3[so + i]; bsdfVal = f3(v3.x, v3.y, v3.z); bsdfPdf = v3.w;
-                v4 = S.v4[so + i]; v5 = S.v5[so + i]; dTreePdf = v4.w;
+                const float4 v3 = __ldcs(&S.v3[so + i]); bsdfVal = f3(v3.x, v3.y, v3.z); bsdfPdf = v3.w;
+                v4 = __ldcs(&S.v4[so + i]); v5 = __ldcs(&S.v5[so + i]); dTreePdf = v4.w;
             }
             // Vertex::commit, GP:1730-1768
             if (!(woPdf > 0.f) || !is_valid(radiance) || !is_valid(bsdfVal)) ok = false;
