@@ -364,7 +364,10 @@ def gpu_arm(args):
                 traffic = ent.get("bounce_dram_bytes_per_launch"); traffic_src = ent.get("source")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "bounce_kernel (ray generation + intersection + shade + S/D-tree guide + compaction; one launch per path depth)",
+    kname = "bounce_kernel (ray generation + intersection + shade + S/D-tree guide + compaction; one launch per path depth)"
+    if args.scene != "cbox":
+        kname += " + trace_kernel (nearest hits of wavefronts >= 32768 paths, persistent warps; timed together with the bounce launch it feeds)"
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_vertex": {"training": b_bounce_train, "final": b_bounce_final, "d_S": d_s, "d_D": d_d},
                 "launches": int(bounce_n), "avg_launch_ms": bounce_ms / max(1, bounce_n),

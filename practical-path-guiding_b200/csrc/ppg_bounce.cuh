@@ -14,6 +14,13 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
     sc.stage();
     const uint32_t nIn = FIRST ? P.nPaths : *P.liveIn;
     unsigned long long raysLocal = 0, recLocal = 0, levelsLocal = 0;
+    // material bins left by trace_kernel: position j of the launch is the (j - start)-th entry of the bin that contains it
+    __shared__ uint32_t binStart[PPG_BINS + 1];
+    const bool binned = !SMEM && P.order != nullptr;
+    if (binned) {
+        if (threadIdx.x == 0) { uint32_t acc = 0; for (uint32_t b = 0; b < PPG_BINS; ++b) { binStart[b] = acc; acc += P.binCount[b]; } binStart[PPG_BINS] = acc; }
+        __syncthreads();
+    }
 
     // Work distribution: every warp claims PPG_CLAIM consecutive groups of 32 paths at a time from a launch-wide counter, so exactly one
     // block per resident slot is launched (the scene is staged once per slot) and the tail still balances.  No block barrier in the loop.
@@ -26,9 +33,14 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
             claimLeft = PPG_CLAIM;
         }
         if (claimBase >= nIn) break;
-        const uint32_t i = claimBase + lane;
+        uint32_t i = claimBase + lane;
         claimBase += 32u; --claimLeft;
         bool alive = i < nIn;
+        if (binned && alive) {
+            uint32_t b = 0;
+            while (b + 1 < PPG_BINS && i >= binStart[b + 1]) ++b;
+            i = __ldg(&P.order[(size_t) b * P.binStride + (i - binStart[b])]);
+        }
         float3 o, d, thr, Li; float eta = 1.f, rrRecip = 1.f, mint, maxt;
         float prevWoPdf = 0.f; float3 prevRefN = f3(0, 0, 0); uint32_t prevSlot = 0;      // NEE only
         uint32_t pathId = 0, nVertices = 0, flags = 0; uint64_t sampleIndex = 0;
@@ -36,21 +48,7 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
         if (alive) {
             if (FIRST) {
                 pathId = i;
-                const uint32_t perPass = P.nLocalPixels * P.spp;
-                const uint32_t passInBatch = i / perPass, rem = i - passInBatch * perPass;
-                const uint32_t lp = rem / P.spp, s = rem - lp * P.spp;
-                const uint32_t xy = __ldg(&P.pixelMap[lp]);
-                const uint32_t x = xy & 0xffffu, y = xy >> 16;
-                sampleIndex = (((P.passBase + passInBatch) * (uint64_t) P.cam.H + y) * (uint64_t) P.cam.W + x) * P.spp + s;
-                seed_path_rng(rng, P.seed, sampleIndex);
-                const float jx = rng.next1D(), jy = rng.next1D();                 // samplePos = pixel + next2D (GP:1620)
-                const float sx = ((float) x + jx) * (1.0f / (float) P.cam.W), sy = ((float) y + jy) * (1.0f / (float) P.cam.H);
-                const float3 nearP = f3((1.0f - 2.0f * sx) * P.cam.tanX, (1.0f - 2.0f * sy) * P.cam.tanY, 1.0f);
-                const float3 dl = normalize(nearP);
-                const float invZ = 1.0f / dl.z;
-                mint = P.cam.nearClip * invZ; maxt = P.cam.farClip * invZ;
-                o = P.cam.o;
-                d = P.cam.left * dl.x + P.cam.up * dl.y + P.cam.dir * dl.z;
+                camera_ray(P, i, rng, sampleIndex, o, d, mint, maxt);
                 thr = f3(1, 1, 1); Li = f3(0, 0, 0);
             } else {
                 const float4 a = __ldcs(&P.in.s0[i]), b = __ldcs(&P.in.s1[i]), c = __ldcs(&P.in.s2[i]), e = __ldcs(&P.in.s3[i]), f = __ldcs(&P.in.s4[i]);   // streamed once: evict-first keeps the L2 for the trees
@@ -62,8 +60,7 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
                 const uint32_t nf = __float_as_uint(f.z); nVertices = nf & 0xffu; flags = nf >> 8;
                 rrRecip = f.w;
                 if (NEE) { const float4 g5 = __ldcs(&P.in.s5[i]), g6 = __ldcs(&P.in.s6[i]); prevWoPdf = g5.x; prevRefN = f3(g5.y, g5.z, g5.w); prevSlot = __float_as_uint(g6.x); }
-                // adaptive ray epsilon of rays leaving a surface (skdtree.cpp:125-128)
-                mint = PPG_EPSILON * fmaxf(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), PPG_EPSILON);
+                mint = surface_ray_mint(o);
                 maxt = __int_as_float(0x7f800000);
             }
         }
@@ -75,7 +72,15 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
             // tree; the reference's kd-tree clips such a ray away (AABB::rayIntersect fails on NaN comparisons): a miss.  Counted in counters[5].
             rayOk = isfinite(o.x + o.y + o.z) && isfinite(d.x + d.y + d.z);
             if (!rayOk) atomicAdd(&P.counters[5], 1ull);
-            found = rayOk && bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
+            if (!SMEM && P.hits) {          // the nearest hit was found by trace_kernel (same rays, same tests, same tie rule)
+                const float4 hv = __ldcs(&P.hits[i]);
+                const uint32_t w = __float_as_uint(hv.w);
+                hit.t = hv.x; hit.u = hv.y; hit.v = hv.z; hit.tri = 0; hit.prim = w;
+                found = rayOk && w != 0xFFFFFFFFu;
+                if (found && !(w & PPG_SPHERE_BIT)) { hit.tri = w; hit.prim = __float_as_uint(sc.accel(3 * w + 2).z); }
+                if (!found) { hit.t = __int_as_float(0x7f800000); hit.prim = 0xFFFFFFFFu; }
+            } else
+                found = rayOk && bvh_intersect<FULL>(sc, o, d, mint, maxt, hit);
         }
         // the lanes leave the walk at different times: make them wait for each other HERE, so that shading runs with the whole warp (without
         // the barrier the scheduler may carry the early leavers through the shading code on their own)

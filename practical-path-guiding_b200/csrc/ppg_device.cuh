@@ -203,6 +203,21 @@ __device__ __forceinline__ bool sphere_intersect(float4 cr, float3 ro, float3 rd
     else t = (float) nearT;
     return true;
 }
+// Ray / box test of the BVH walks: entry distance in tEntry; `tmax` = min(maxt, nearest hit so far).
+// fmaxf / fminf drop NaN operands (0 * inf when the ray lies in a box plane); widening once after the reductions equals widening every axis.
+// The widening is multiplicative: `x -+ |x| * 1e-6` is inf - inf = NaN for an infinite bound, which fmaxf / fminf then DROP -- a ray with an
+// exactly zero direction component was never culled on that axis and walked ~450 000 nodes of KITCHEN: 300 ms for one lane.
+__device__ __forceinline__ bool bvh_slab(float3 o, float3 inv, float mint, float tmax, const float4 n0, const float4 n1, float &tEntry) {
+    float ta = (n0.x - o.x) * inv.x, tb = (n1.x - o.x) * inv.x; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
+    float nearMax = fmaxf(__int_as_float(0xff800000), ta), farMin = fminf(__int_as_float(0x7f800000), tb);
+    ta = (n0.y - o.y) * inv.y; tb = (n1.y - o.y) * inv.y; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
+    nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
+    ta = (n0.z - o.z) * inv.z; tb = (n1.z - o.z) * inv.z; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
+    nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
+    const float t0 = fmaxf(mint, nearMax * (nearMax > 0.f ? 1.0f - 1e-6f : 1.0f + 1e-6f)), t1 = fminf(tmax, farMin * (farMin > 0.f ? 1.0f + 1e-6f : 1.0f - 1e-6f));
+    tEntry = t0;
+    return t0 <= t1;
+}
 // Not inlined: the walk's two stacks and its registers stay out of the callers' frames (the tiny-scene path of the bounce
 // kernel never calls it and keeps its register allocation).
 template <class Acc>
@@ -212,21 +227,7 @@ __device__ __noinline__ bool bvh_walk(const Acc &A_, float3 o, float3 d, float m
     // a closer hit has been found since.  The slab test is widened by 1 ulp-ish factors so that flat boxes and NaNs (0 * inf)
     // never cull; results do not depend on the visiting order (ties on t go to the lower original triangle index).
     const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    auto slab = [&](const float4 n0, const float4 n1, float &tEntry) -> bool {
-        // fmaxf / fminf drop NaN operands (0 * inf when the ray lies in a box plane); widening once after the reductions equals
-        // widening every axis because x -> x -+ |x| * 1e-6 is monotone
-        float ta = (n0.x - o.x) * inv.x, tb = (n1.x - o.x) * inv.x; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
-        float nearMax = fmaxf(__int_as_float(0xff800000), ta), farMin = fminf(__int_as_float(0x7f800000), tb);
-        ta = (n0.y - o.y) * inv.y; tb = (n1.y - o.y) * inv.y; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
-        nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
-        ta = (n0.z - o.z) * inv.z; tb = (n1.z - o.z) * inv.z; if (ta > tb) { const float s_ = ta; ta = tb; tb = s_; }
-        nearMax = fmaxf(nearMax, ta); farMin = fminf(farMin, tb);
-        // (multiplicative: `x -+ |x| * 1e-6` is inf - inf = NaN for an infinite bound, which fmaxf / fminf then DROP -- a ray with an exactly
-        // zero direction component was never culled on that axis and walked ~450 000 nodes of KITCHEN: 300 ms for one lane)
-        const float t0 = fmaxf(mint, nearMax * (nearMax > 0.f ? 1.0f - 1e-6f : 1.0f + 1e-6f)), t1 = fminf(fminf(maxt, hit.t), farMin * (farMin > 0.f ? 1.0f + 1e-6f : 1.0f - 1e-6f));
-        tEntry = t0;
-        return t0 <= t1;
-    };
+    auto slab = [&](const float4 n0, const float4 n1, float &tEntry) -> bool { return bvh_slab(o, inv, mint, fminf(maxt, hit.t), n0, n1, tEntry); };
     uint32_t stackN[PPG_BVH_STACK]; float stackT[PPG_BVH_STACK]; int sp = 0;
     uint32_t left, count;      // the current node: children left, left+1 (count == 0) or leaf slots [left, left+count)
     {

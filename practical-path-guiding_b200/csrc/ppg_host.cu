@@ -351,6 +351,8 @@ struct ppg_integrator {
     // wavefront
     size_t pathCapacity = 0; int maxBounces = 0, nSlabs = 0; int recordMode = 0; int stateVecs = 5, slabSets = 1;
     DevBuf<float4> dStateA, dStateB, dSlabs, dLiFinal; DevBuf<uint32_t> dLive, dWork; DevBuf<unsigned long long> dCounters;
+    DevBuf<float4> dHits; DevBuf<uint32_t> dTraceWork; int gridTrace = 0; uint32_t traceMinPaths = 0;   // separate nearest-hit pass (ppg_trace.cu), BVH scenes only
+    DevBuf<uint32_t> dOrder, dBinCount; bool binMaterials = false;                                        // ... which also bins the paths by the BSDF class they hit
     int gridBounce = 0, gridCommit = 0;
 
     // per-kernel-class CUDA-event timing on the launching stream
@@ -1081,6 +1083,17 @@ static int ensure_wavefront(ppg_integrator *h) {
     h->gridBounce = h->numSMs * std::max(occ, 1) * std::max(env_int("PPG_GRID_MULT", 1), 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, commit_kernel<1>, PPG_BLOCK, 0));
     h->gridCommit = h->numSMs * std::max(occ, 1);
+    // Scenes walked through the BVH find their hits in a separate pass of persistent warps (ppg_trace.cu) whenever the wavefront is large enough
+    // to pay for the second launch per depth; tiny learning sub-batches keep the fused kernel.  PPG_TRACE_MIN_PATHS=0 turns the pass off.
+    h->gridTrace = 0;
+    h->traceMinPaths = (uint32_t) std::max(env_int("PPG_TRACE_MIN_PATHS", 32768), 0);
+    if (!h->sceneSmemBytes && h->sceneView.nGroups == 0u && h->sceneView.nTris != 0u && h->traceMinPaths != 0u) {
+        CK(h->dHits.alloc(h->pathCapacity)); CK(h->dTraceWork.alloc(h->maxBounces + 2));
+        h->binMaterials = h->fullFeature && env_int("PPG_BIN_MATERIALS", 1) != 0;       // one kind of BSDF only: nothing to sort
+        if (h->binMaterials) { CK(h->dOrder.alloc((size_t) PPG_BINS * h->pathCapacity)); CK(h->dBinCount.alloc((size_t) PPG_BINS * (h->maxBounces + 2))); }
+        h->gridTrace = h->numSMs * std::max(ppg_trace_occupancy(), 1);
+        CK(cudaGetLastError());
+    }
     return PPG_OK;
 }
 
@@ -1133,6 +1146,12 @@ static int render_batch(ppg_integrator *h, int nPasses, const uint32_t *pixelMap
         PathState A = path_state(h->dStateA.p, h->pathCapacity, nee), B = path_state(h->dStateB.p, h->pathCapacity, nee);
         const int bb = h->sceneSmemBytes ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM;
         const int grid = std::min<int>(h->gridBounce, (int) ((nPaths + bb - 1) / bb));
+        const bool useTrace = h->gridTrace > 0 && nPaths >= h->traceMinPaths;
+        P.hits = useTrace ? h->dHits.p : nullptr; P.traceWork = nullptr;
+        const bool bins = useTrace && h->binMaterials;
+        P.order = bins ? h->dOrder.p : nullptr; P.binCount = nullptr; P.binStride = (uint32_t) h->pathCapacity;
+        if (useTrace) CK(cudaMemsetAsync(h->dTraceWork.p, 0, 4 * (size_t) (h->maxBounces + 2), h->stream));
+        if (bins) CK(cudaMemsetAsync(h->dBinCount.p, 0, 4 * (size_t) PPG_BINS * (h->maxBounces + 2), h->stream));
         int lastDepth = 0, pendingDepth = 0; uint32_t bracket = 0;
         for (int depth = 1; depth <= h->maxBounces; ++depth) {
             P.depth = depth; P.in = (depth & 1) ? B : A; P.out = (depth & 1) ? A : B;
@@ -1143,6 +1162,11 @@ static int render_batch(ppg_integrator *h, int nPasses, const uint32_t *pixelMap
             const int rec = (depth - 1 < h->nSlabs) ? record : 0;
             if (h->cancelled.load()) { if (bracket) h->toc(bracket); return PPG_ERR_CANCELLED; }   // Integrator::cancel() (GP:1643-1648): the batch in flight is dropped
             if (!bracket) h->tic(PPG_K_BOUNCE);                                // one event pair around the consecutive bounce launches (2 records per launch were
+            if (useTrace) {                                                    // nearest hits of this depth's rays, then the bounce kernel shades them
+                P.traceWork = h->dTraceWork.p + depth;
+                if (bins) P.binCount = h->dBinCount.p + (size_t) PPG_BINS * depth;
+                ppg_launch_trace(P, h->stream, std::min<int>(h->gridTrace, (int) ((nPaths + 255) / 256)), depth == 1, h->sceneView.nSpheres != 0u); h->launches++;
+            }
             launch_bounce(h, P, depth == 1, rec, grid, nee);                   // ~1.5 ms of host time per CBOX step: visible at 8 GPUs, where a step takes 38 ms)
             ++bracket;
             lastDepth = depth;
@@ -1319,8 +1343,8 @@ static int perform_render_passes(ppg_integrator *h, float &variance, int numPass
     h->lastRecorded = cnt[1];
     static const int trace = env_int("PPG_TRACE", 0);
     if (trace)    // cumulative kernel times after every iteration's passes (stderr): where a render's time goes, iteration by iteration
-        fprintf(stderr, "[ppg trace] iter %d final %d passes %d sub_batches %llu vertices %llu wall %.1f ms | cumulative ms: bounce %.1f commit %.1f adam %.1f other %.1f film %.1f launches %llu\n",
-                h->iter, (int) h->isFinalIter, local, (unsigned long long) h->stats.sub_batches, (unsigned long long) cnt[0], elapsed_ms(t0),
+        fprintf(stderr, "[ppg trace] iter %d final %d passes %d sub_batches %llu vertices %llu entered at %.1f ms wall %.1f ms | cumulative ms: bounce %.1f commit %.1f adam %.1f other %.1f film %.1f launches %llu\n",
+                h->iter, (int) h->isFinalIter, local, (unsigned long long) h->stats.sub_batches, (unsigned long long) cnt[0], elapsed_ms(h->startTime) - elapsed_ms(t0), elapsed_ms(t0),
                 h->stats.kernel_ms[PPG_K_BOUNCE], h->stats.kernel_ms[PPG_K_COMMIT], h->stats.kernel_ms[PPG_K_ADAM], h->stats.kernel_ms[PPG_K_OTHER], h->stats.kernel_ms[PPG_K_FILM],
                 (unsigned long long) h->launches);
     return rcode;

@@ -83,7 +83,38 @@ struct RenderParams {
     int training;                  // vertex records are being written in this iteration (the last bounce kernel itself runs with RECORD == 0)
     VertexSlab neeSlab;            // half-weight vertices of the sampled light directions (GP:1999-2016), slab of the current depth
     VertexSlab prevSlab;           // slab of depth-1 (nee == always: the vertex's radiance excludes the emitter hit that follows it, GP:2101)
+    float4 *hits;                  // nullptr: the bounce kernel intersects its own ray.  Otherwise trace_kernel (ppg_trace.cu) has left the nearest hit of
+                                   // input path i here: {t, u, v, bits(w)}, w = 0xFFFFFFFF miss | PPG_SPHERE_BIT + sphere | triangle slot
+    uint32_t *traceWork;           // trace_kernel: next unclaimed ray (zeroed by the host)
+    // Material binning (with `hits`): trace_kernel appends every finished ray to the bin of the BSDF class it hit (PPG_BINS - 1: miss);
+    // the bounce kernel walks the bins one after the other, so that the 32 paths of a warp shade the same kind of material.
+    uint32_t *order;               // [PPG_BINS x binStride] input path indices, or nullptr
+    uint32_t *binCount;            // [PPG_BINS] fill of each bin (zeroed by the host)
+    uint32_t binStride;
 };
+#define PPG_BINS 16u
+
+// renderBlock's ray (GP:1613-1632): pixel of path i of the batch, the path's random stream, the jittered film position, the camera ray.
+// Shared by the bounce kernel and the trace kernel, which must generate bit-identical rays.
+__device__ __forceinline__ void camera_ray(const RenderParams &P, uint32_t i, Pcg32 &rng, uint64_t &sampleIndex, float3 &o, float3 &d, float &mint, float &maxt) {
+    const uint32_t perPass = P.nLocalPixels * P.spp;
+    const uint32_t passInBatch = i / perPass, rem = i - passInBatch * perPass;
+    const uint32_t lp = rem / P.spp, s = rem - lp * P.spp;
+    const uint32_t xy = __ldg(&P.pixelMap[lp]);
+    const uint32_t x = xy & 0xffffu, y = xy >> 16;
+    sampleIndex = (((P.passBase + passInBatch) * (uint64_t) P.cam.H + y) * (uint64_t) P.cam.W + x) * P.spp + s;
+    seed_path_rng(rng, P.seed, sampleIndex);
+    const float jx = rng.next1D(), jy = rng.next1D();                 // samplePos = pixel + next2D (GP:1620)
+    const float sx = ((float) x + jx) * (1.0f / (float) P.cam.W), sy = ((float) y + jy) * (1.0f / (float) P.cam.H);
+    const float3 nearP = f3((1.0f - 2.0f * sx) * P.cam.tanX, (1.0f - 2.0f * sy) * P.cam.tanY, 1.0f);
+    const float3 dl = normalize(nearP);
+    const float invZ = 1.0f / dl.z;
+    mint = P.cam.nearClip * invZ; maxt = P.cam.farClip * invZ;
+    o = P.cam.o;
+    d = P.cam.left * dl.x + P.cam.up * dl.y + P.cam.dir * dl.z;
+}
+// adaptive ray epsilon of rays leaving a surface (skdtree.cpp:125-128)
+__device__ __forceinline__ float surface_ray_mint(float3 o) { return PPG_EPSILON * fmaxf(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)), PPG_EPSILON); }
 
 // warp-wide compaction: returns the output slot of this lane (valid when `alive`); one atomic per warp and
 // no block barrier, so warps of a block never wait for each other inside the path loop.
@@ -101,6 +132,9 @@ __device__ __forceinline__ uint32_t warp_compact(bool alive, uint32_t *counter) 
 struct BounceLaunch { cudaStream_t stream; int grid; int record; int nee; int first; };
 void ppg_launch_bounce_00(const RenderParams &P, const BounceLaunch &L); void ppg_launch_bounce_01(const RenderParams &P, const BounceLaunch &L);   // <SMEM, FULL>
 void ppg_launch_bounce_10(const RenderParams &P, const BounceLaunch &L); void ppg_launch_bounce_11(const RenderParams &P, const BounceLaunch &L);
+// Separate nearest-hit pass for scenes that are walked through the BVH (ppg_trace.cu): persistent warps that refill idle lanes with new rays.
+void ppg_launch_trace(const RenderParams &P, cudaStream_t stream, int grid, bool first, bool spheres);
+int ppg_trace_occupancy();
 int ppg_bounce_occupancy_00(size_t smem); int ppg_bounce_occupancy_01(size_t smem); int ppg_bounce_occupancy_10(size_t smem); int ppg_bounce_occupancy_11(size_t smem);
 
 }  // namespace ppg

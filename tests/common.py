@@ -5,7 +5,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def assert_render_parity(img, ref, st, ost, sc=None, props=None, pixels=0.90, mean=0.01, counts=2e-4):
+def assert_render_parity(img, ref, st, ost, sc=None, props=None, pixels=0.90, mean=0.01, counts=2e-4, leaves=1):
     """Parity of a TRAINED render of the CUDA path (img, st) with the oracle's (ref, ost) on the same seeded inputs.
 
     Both implementations accumulate the SD-tree statistics with floating-point atomics (the reference's addToAtomicFloat, GP:59-62;
@@ -15,7 +15,8 @@ def assert_render_parity(img, ref, st, ost, sc=None, props=None, pixels=0.90, me
     split into a deterministic and a robust part, each checked ONCE (no retry):
       * the unguided first pass (no tree involved) is the same computation on both sides: relMSE <= 1e-9, equal vertex counts
         (checked when `sc` and `props` are given: one extra pass of both implementations; libm ulps flip a discrete decision of a few paths in 10^5);
-      * the trained render: total vertices and every iteration's recorded weight within `counts` (2e-4), leaf counts within 1,
+      * the trained render: total vertices and every iteration's recorded weight within `counts` (2e-4; 2e-3 for the big scenes with rough
+        BSDFs, where libm ulps in sincos / pow / erf flip more decisions), leaf counts within `leaves` (1),
         at least `pixels` (90 %) of the pixels equal to 1e-3 relative, the image mean within `mean` (1 %)."""
     if sc is not None:
         import oracle_lib as O
@@ -29,7 +30,7 @@ def assert_render_parity(img, ref, st, ost, sc=None, props=None, pixels=0.90, me
     assert abs(st["total_vertices"] - ost["total_vertices"]) <= max(2, counts * ost["total_vertices"]), (st["total_vertices"], ost["total_vertices"])
     assert len(st["iterations"]) == len(ost["iterations"])
     for a, b in zip(st["iterations"], ost["iterations"]):
-        assert a["passes"] == b["passes"] and abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 1, (a["iteration"], a["s_tree_leaves"], b["s_tree_leaves"])
+        assert a["passes"] == b["passes"] and abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= leaves, (a["iteration"], a["s_tree_leaves"], b["s_tree_leaves"])
         wa, wb = a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"]
         assert abs(wa - wb) <= max(4, counts * wb), (a["iteration"], wa, wb)
     close = np.isclose(img, ref, rtol=1e-3, atol=1e-5).all(axis=2)

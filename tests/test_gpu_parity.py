@@ -373,11 +373,36 @@ def test_spaceship_matches_oracle():
     g = _gpu(props, sc); img, st = g.render()
     o = O.Oracle(O.params_from_xml(props), sc, kind="port"); ref, ost = o.render()
     assert np.isfinite(img).all()
-    assert_render_parity(img, ref, st, ost, sc, props)
+    # trained render: an S-tree split or a quadtree subdivision that sits on its threshold flips with the last ulp of an atomic float sum, and the
+    # region it covers then decorrelates to noise level (leaf counts differ by up to 2 here): a majority of identical pixels is the robust claim
+    assert_render_parity(img, ref, st, ost, sc, props, counts=2e-3, leaves=2, pixels=0.6)
     assert abs(st["total_vertices"] - ost["total_vertices"]) <= 2e-3 * ost["total_vertices"]
     for a, b in zip(st["iterations"], ost["iterations"]):
         assert abs(a["s_tree_leaves"] - b["s_tree_leaves"]) <= 2
         assert np.isclose(a["weight_avg"] * a["s_tree_leaves"], b["weight_avg"] * b["s_tree_leaves"], rtol=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["spaceship-improved", "kitchen-improved"])
+def test_trace_pass_finds_the_same_hits(name, monkeypatch):
+    """Large wavefronts of BVH scenes find their nearest hits in a separate pass of persistent warps that refill idle lanes
+    (csrc/ppg_trace.cu) instead of inside the fused bounce kernel.  Same rays, same tests, same tie rule: the unguided render must be
+    the SAME image bit for bit whichever kernel finds the hits, and a trained render must agree like two runs of one configuration
+    (PPG_TRACE_MIN_PATHS: 0 = pass off, 1 = pass on for every wavefront; the default engages it from 32 768 paths)."""
+    from common import load_fixture_scene
+    sc = load_fixture_scene(name).with_film(160, 90)
+    base = dict(sc.integrator, sampleCombination="automatic", bsdfSamplingFractionLoss="none", spatialFilter="nearest", directionalFilter="nearest")
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PPG_TRACE_MIN_PATHS", mode)
+        out[mode, 1] = _gpu(dict(base, budget="1"), sc).render()
+        out[mode, 15] = _gpu(dict(base, budget="15"), sc).render()
+    (img0, st0), (img1, st1) = out["0", 1], out["1", 1]
+    assert st0["total_vertices"] == st1["total_vertices"]
+    assert st1["kernel_launches"] > st0["kernel_launches"]          # the pass really ran
+    assert np.array_equal(img0, img1)
+    (img0, st0), (img1, st1) = out["0", 15], out["1", 15]
+    assert_render_parity(img1, img0, st1, st0, counts=2e-3, leaves=2, pixels=0.6)
 
 
 @pytest.mark.gpu
