@@ -552,16 +552,21 @@ static int build_pixel_map(ppg_integrator *h) {
     }
     CK(h->dPixelMap.alloc(std::max<size_t>(map.size(), 1)));
     if (!map.empty()) CK(cudaMemcpy(h->dPixelMap.p, map.data(), map.size() * 4, cudaMemcpyHostToDevice));
-    // A second, scattered order of the same pixels (golden-ratio stride, coprime to the count): any contiguous range of it is spread evenly over
+    // A second, scattered order of the same pixels (golden-ratio stride over runs of 8 pixels, coprime to the run count): any contiguous range of it is spread evenly over
     // the image.  The sub-batches of a learning iteration (perform_render_passes) take their pixels from it, so that every S-tree leaf receives its
     // share of every sub-batch -- like the reference, whose worker threads interleave image blocks while the sampling fractions adapt.
     std::vector<uint32_t> perm(map.size());
     if (!map.empty()) {
         const uint64_t n = map.size();
-        uint64_t stride = std::max<uint64_t>(1, (uint64_t) ((double) n * 0.6180339887498949));
         auto gcd = [](uint64_t a, uint64_t b) { while (b) { const uint64_t t = a % b; a = b; b = t; } return a; };
-        while (gcd(stride, n) != 1) ++stride;
-        for (uint64_t i = 0; i < n; ++i) perm[i] = map[(i * stride) % n];
+        // ... in runs of 8 consecutive map entries (8 neighbouring pixels of one block row): a quarter of a warp starts coherent,
+        // which the BVH walk of the first bounce -- the largest launch of a sub-batch -- feels; a slice of 10^4 paths still holds
+        // > 10^3 runs spread over the whole image
+        const uint64_t run = (uint64_t) std::max(env_int("PPG_PERM_RUN", 8), 1), nr = (n + run - 1) / run;
+        uint64_t rs = std::max<uint64_t>(1, (uint64_t) ((double) nr * 0.6180339887498949));
+        while (gcd(rs, nr) != 1) ++rs;
+        uint64_t w = 0;
+        for (uint64_t r = 0; r < nr; ++r) { const uint64_t src = (r * rs) % nr; for (uint64_t k = src * run; k < std::min(n, (src + 1) * run); ++k) perm[w++] = map[k]; }
     }
     CK(h->dPixelMapPerm.alloc(std::max<size_t>(perm.size(), 1)));
     if (!perm.empty()) CK(cudaMemcpy(h->dPixelMapPerm.p, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));

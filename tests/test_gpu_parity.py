@@ -491,7 +491,7 @@ def test_spaceship_known_answers_of_the_reference_log():
     tests/golden/spaceship_log_stats.json): the same known answers as the oracle's pin (tests/test_oracle_golden.py).  Measured with the
     step-size control of the sampling fractions: recorded vertices of iterations 1-3 +3.4 / +2.9 / +3.2 % against the log (the oracle itself:
     +2.6 / +2.5 / +1.3 %), leaf counts 480 / 803 (log: 480 / 802), variances within 4 %.  Tolerances: totals and per-leaf averages 5 %, leaf
-    counts 5 %, the heavy-tailed variance estimate of 2-8 samples per pixel 15 %."""
+    counts 5 %, the heavy-tailed variance estimate of 2-8 samples per pixel 15 % (plus one clamped firefly pixel, see below)."""
     import json, os
     from common import ROOT, load_fixture_scene
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "spaceship_log_stats.json")))["spaceship-improved"]["iterations"]
@@ -504,7 +504,11 @@ def test_spaceship_known_answers_of_the_reference_log():
     assert abs(it[0]["mean_radiance_avg"] - gold[0]["mean_radiance"][1]) <= 0.02 * gold[0]["mean_radiance"][1]
     report = [(k, it[k]["variance"], gold[k]["var"], it[k]["weight_avg"], gold[k]["stat_weight"][1], it[k]["nodes_avg"], it[k]["depth_avg"], it[k]["s_tree_leaves"]) for k in (1, 2, 3)]
     for k in (1, 2, 3):
-        assert abs(it[k]["variance"] - gold[k]["var"]) <= 0.15 * gold[k]["var"], report
+        # The estimate sums min(luminance variance, 1e4) over the pixels (GP:1298-1319): ONE firefly pixel that reaches the clamp adds
+        # 1e4 / (W H (N - 1)) = 0.043 / 0.014 / 0.006 at N = 2 / 4 / 8 samples, 44 % of the logged value of iteration 1.  Eight seeds
+        # (tools/perm_check.py) gave 0.091 - 0.106 against the log's 0.0976; a run with such a pixel gave 0.123.  Hence 15 % plus one clamped pixel.
+        firefly = 1e4 / (640 * 360 * (it[k]["passes"] - 1))
+        assert -0.15 * gold[k]["var"] <= it[k]["variance"] - gold[k]["var"] <= 0.15 * gold[k]["var"] + firefly, report
         assert abs(it[k]["weight_avg"] - gold[k]["stat_weight"][1]) <= 0.06 * gold[k]["stat_weight"][1], report
         assert abs(it[k]["nodes_avg"] - gold[k]["node_count"][1]) <= 6 and abs(it[k]["depth_avg"] - gold[k]["depth"][1]) <= 0.3, report
     assert abs(it[2]["s_tree_leaves"] - 480) <= 24 and abs(it[3]["s_tree_leaves"] - 802) <= 40, report
