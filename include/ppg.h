@@ -413,6 +413,18 @@ int ppg_op_dtree_record(int device,
                         const uint32_t *rec_tree, const float *rec_dir, const float *rec_radiance,
                         const float *rec_wo_pdf, const float *rec_weight, size_t n, int filter);
 
+/* Scene::sampleAttenuatedEmitterDirect (src/librender/scene.cpp:876-897 -> AreaLight / Sphere / EnvironmentMap::sampleDirect, then
+ * Scene::evalTransmittance) at n reference points of the handle's scene, as the light-sampling block of Li calls it (GP:1964-1973):
+ * ref, ref_n 3n floats (ref_n = 0: no front-side test, records.inl:160-164), sample 2n uniforms, max_interactions = maxDepth - depth - 1
+ * (negative: unlimited).  d_out 3n, value_out 3n (radiance x transmittance / pdf), pdf_out n (0: the sample carries nothing), dist_out n.
+ * Needs a scene that runs the full-feature kernels (any non-diffuse BSDF, sphere, texture or an environment emitter). */
+int ppg_op_emitter_sample_direct(ppg_integrator *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,
+                                 float *d_out, float *value_out, float *pdf_out, float *dist_out);
+
+/* Scene::pdfEmitterDirect of the environment emitter (EnvironmentMap::pdfDirect, src/emitters/envmap.cpp:545-548, 603-633, times the
+ * discrete emitter choice) for n world directions d (3n), and optionally its radiance there (evalEnvironment, :380-410; value_out 3n or NULL). */
+int ppg_op_env_pdf(ppg_integrator *h, size_t n, const float *d, float *pdf_out, float *value_out);
+
 /* STree::dTreeWrapper(p, size) (GP:897-905, 761-769): S-tree nodes as uint32
  * pairs (child0, child1); child0 == 0 marks a leaf. Outputs the leaf NODE index
  * and the voxel size (3 floats) per query point. */

@@ -214,6 +214,85 @@ struct Scene {
         dDv = g1.x * 0.212671f + g1.y * 0.715160f + g1.z * 0.072169f;
     }
     bool hasEnvironment() const { return envW != 0; }
+    // ---- light sampling of the environment emitter (nee != never).  EnvironmentMap::configure (src/emitters/envmap.cpp:260-329): marginal row / conditional
+    // column CDFs over texel luminance x sin(theta), in the reference's float / double mix; createShape (:330-335): the scene's bounding sphere x 1.5
+    std::vector<float> envCdfRows, envCdfCols, envRowWeights; float envNormalization = 0, envPixelX = 0, envPixelY = 0, envRadius = 0; F3 envCenter; float envToWorld[9];
+    static float luminance(F3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }   // Color3::getLuminance, spectrum.h:836-838
+    F3 envTexel(int x, int y) const { return texel(envTexels.data(), envW, envH, 3, PPG_WRAP_REPEAT, PPG_WRAP_CLAMP, x, y); }   // evalTexel(0, x, y): u repeats, v clamps
+    void buildEnvSampler() {
+        const uint32_t Wd = envW, Hd = envH;
+        envCdfCols.assign((size_t) (Wd + 1) * Hd, 0.f); envCdfRows.assign((size_t) Hd + 1, 0.f); envRowWeights.assign(Hd, 0.f);
+        size_t colPos = 0, rowPos = 0; float rowSum = 0.0f;
+        envCdfRows[rowPos++] = 0;
+        for (uint32_t y = 0; y < Hd; ++y) {
+            float colSum = 0;
+            envCdfCols[colPos++] = 0;
+            for (uint32_t x = 0; x < Wd; ++x) { colSum += luminance(envTexel((int) x, (int) y)); envCdfCols[colPos++] = colSum; }
+            const float normalization = 1.0f / colSum;
+            for (uint32_t x = 1; x < Wd; ++x) envCdfCols[colPos - x - 1] *= normalization;
+            envCdfCols[colPos - 1] = 1.0f;
+            const float weight = (float) std::sin((double) ((float) y + 0.5f) * 3.14159265358979323846 / (double) Hd);
+            envRowWeights[y] = weight;
+            rowSum += colSum * weight;
+            envCdfRows[rowPos++] = rowSum;
+        }
+        const float normalization = 1.0f / rowSum;
+        for (uint32_t y = 1; y < Hd; ++y) envCdfRows[rowPos - y - 1] *= normalization;
+        envCdfRows[rowPos - 1] = 1.0f;
+        envNormalization = (float) (1.0 / ((double) rowSum * (2 * 3.14159265358979323846 / (double) Wd) * (3.14159265358979323846 / (double) Hd)));
+        envPixelX = (float) (2 * 3.14159265358979323846 / (double) Wd); envPixelY = (float) (3.14159265358979323846 / (double) Hd);
+        envCenter = (aabbMax + aabbMin) * 0.5f;                                                // AABB::getBSphere, libcore/aabb.cpp:44-47
+        envRadius = std::max(kEpsilon, length(envCenter - aabbMax) * 1.5f);
+        const float *m = worldToEnv;                                                           // the emitter-to-world rotation back from its inverse
+        const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+        const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g), id = 1.0 / det;
+        const double inv[9] = {(e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id, (f * g - d * i) * id, (a * i - c * g) * id, (c * d - a * f) * id,
+                               (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id};
+        for (int k = 0; k < 9; ++k) envToWorld[k] = (float) inv[k];
+    }
+    static uint32_t envSampleReuse(const float *cdf, uint32_t size, float &sample) {           // EnvironmentMap::sampleReuse, envmap.cpp:657-662
+        const float *entry = std::lower_bound(cdf, cdf + size + 1, sample);
+        const uint32_t index = std::min((uint32_t) std::max((ptrdiff_t) 0, entry - cdf - 1), size - 1);
+        sample = (sample - cdf[index]) / (cdf[index + 1] - cdf[index]);
+        return index;
+    }
+    static float intervalToTent(float sample) {                                                // libcore/warp.cpp:143-155
+        float sign;
+        if (sample < 0.5f) { sign = 1; sample *= 2; } else { sign = -1; sample = 2 * (sample - 0.5f); }
+        return sign * (1 - std::sqrt(sample));
+    }
+    // bilinear luminance-weighted density shared by internalSampleDirection / internalPdfDirection (envmap.cpp:577-591, 619-632), before the 1/sin(theta)
+    float envDensity(float px, float py, F3 *valueOut) const {
+        const int xPos = (int) std::floor(px), yPos = (int) std::floor(py);
+        const float dx1 = px - (float) xPos, dx2 = 1.0f - dx1, dy1 = py - (float) yPos, dy2 = 1.0f - dy1;
+        const F3 value1 = envTexel(xPos, yPos) * dx2 * dy2 + envTexel(xPos + 1, yPos) * dx1 * dy2;
+        const F3 value2 = envTexel(xPos, yPos + 1) * dx2 * dy1 + envTexel(xPos + 1, yPos + 1) * dx1 * dy1;
+        if (valueOut) *valueOut = (value1 + value2) * envScale;
+        const int H1 = (int) envH - 1;
+        return (luminance(value1) * envRowWeights[std::min(std::max(yPos, 0), H1)] + luminance(value2) * envRowWeights[std::min(std::max(yPos + 1, 0), H1)]) * envNormalization;
+    }
+    // EnvironmentMap::internalSampleDirection, envmap.cpp:567-600 (direction in the emitter's frame)
+    void envSampleDirection(float sx, float sy, F3 &d, F3 &value, float &pdf) const {
+        const uint32_t row = envSampleReuse(envCdfRows.data(), envH, sy);
+        const uint32_t col = envSampleReuse(envCdfCols.data() + (size_t) row * (envW + 1), envW, sx);
+        const float px = (float) col + intervalToTent(sx), py = (float) row + intervalToTent(sy);
+        pdf = envDensity(px, py, &value);
+        float sinPhi, cosPhi, sinTheta, cosTheta;
+        sincosf(envPixelX * (px + 0.5f), &sinPhi, &cosPhi);
+        sincosf(envPixelY * (py + 0.5f), &sinTheta, &cosTheta);
+        d = f3(sinPhi * sinTheta, cosTheta, -cosPhi * sinTheta);
+        pdf /= std::max(std::fabs(sinTheta), kEpsilon);
+    }
+    // EnvironmentMap::pdfDirect (solid angle measure) -> internalPdfDirection, envmap.cpp:545-548, 603-633, for a WORLD direction
+    float envPdfDirection(F3 dw) const {
+        const F3 d = f3(worldToEnv[0] * dw.x + worldToEnv[1] * dw.y + worldToEnv[2] * dw.z, worldToEnv[3] * dw.x + worldToEnv[4] * dw.y + worldToEnv[5] * dw.z,
+                        worldToEnv[6] * dw.x + worldToEnv[7] * dw.y + worldToEnv[8] * dw.z);
+        const float uu = std::atan2(d.x, -d.z) * 0.15915494309189533577f, vv = std::acos(std::min(1.0f, std::max(-1.0f, d.y))) * kInvPiS;
+        if (!std::isfinite(uu) || !std::isfinite(vv)) return 0.0f;
+        const float u = uu * (float) envW - 0.5f, v = vv * (float) envH - 0.5f;
+        const float sinTheta = std::sqrt(std::max(0.0f, 1 - d.y * d.y));                       // math::safe_sqrt
+        return envDensity(u, v, nullptr) / std::max(std::fabs(sinTheta), kEpsilon);
+    }
     // EnvironmentMap::evalEnvironment without ray differentials (src/emitters/envmap.cpp:380-410): u repeats, v clamps (:176-178)
     F3 evalEnvironment(F3 d) const {
         const F3 v = f3(worldToEnv[0] * d.x + worldToEnv[1] * d.y + worldToEnv[2] * d.z, worldToEnv[3] * d.x + worldToEnv[4] * d.y + worldToEnv[5] * d.z,
@@ -249,6 +328,7 @@ struct Scene {
         }
         emitterCdf.assign(1, 0.0f);
         for (size_t e = 0; e < emitterSamplers.size(); ++e) emitterCdf.push_back(emitterCdf.back() + 1.0f);     // getSamplingWeight() == 1
+        if (hasEnvironment()) { buildEnvSampler(); emitterCdf.push_back(emitterCdf.back() + 1.0f); }           // the environment emitter is the last entry of m_emitters here
         if (emitterCdf.back() > 0) { emitterNormalization = 1.0f / emitterCdf.back(); for (size_t i = 1; i < emitterCdf.size(); ++i) emitterCdf[i] *= emitterNormalization; emitterCdf.back() = 1.0f; }
     }
 
@@ -507,13 +587,38 @@ static inline F3 eval_transmittance(const Scene &sc, F3 p1, F3 d, float remainin
 }
 
 struct DirectSample { F3 value, d, n; float dist, pdf; int emitter; };
+static const int kEnvEmitter = -2;       // `dRec.object` is the environment emitter
 // Scene::sampleAttenuatedEmitterDirect (scene.cpp:876-897) -> AreaLight::sampleDirect (emitters/area.cpp:158-173)
 // -> Shape::sampleDirect (shape.cpp:102-115) -> TriMesh::samplePosition (trimesh.cpp:412-423) -> Triangle::sample (libcore/triangle.cpp:24-59)
 static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float sx, float sy, DirectSample &out, int maxInteractions = 0) {
-    if (sc.emitterSamplers.empty()) return false;
+    if (sc.emitterCdf.size() < 2) return false;
     const size_t ei = Scene::cdfSample(sc.emitterCdf, sx);
     const float emPdf = sc.emitterCdf[ei + 1] - sc.emitterCdf[ei];
     sx = (sx - sc.emitterCdf[ei]) / (sc.emitterCdf[ei + 1] - sc.emitterCdf[ei]);            // sampleReuse
+    if (ei == sc.emitterSamplers.size()) {   // the environment emitter: EnvironmentMap::sampleDirect, src/emitters/envmap.cpp:516-543 (no dRec.refN test there)
+        F3 dl, value; float pdf;
+        sc.envSampleDirection(sx, sy, dl, value, pdf);
+        const float *m = sc.envToWorld;
+        const F3 d = f3(m[0] * dl.x + m[1] * dl.y + m[2] * dl.z, m[3] * dl.x + m[4] * dl.y + m[5] * dl.z, m[6] * dl.x + m[7] * dl.y + m[8] * dl.z);
+        out.pdf = 0; out.value = f3(0, 0, 0); out.d = d; out.emitter = kEnvEmitter;
+        // m_sceneBSphere.rayIntersect (bsphere.h:88-95) -> solveQuadratic (util.cpp:447-485)
+        const F3 o = ref - sc.envCenter;
+        const float A = dot(d, d), B = 2 * dot(o, d), C = dot(o, o) - sc.envRadius * sc.envRadius;
+        float nearT, farT;
+        {   if (A == 0) return false;
+            const float discrim = B * B - 4.0f * A * C;
+            if (discrim < 0) return false;
+            const float sq = std::sqrt(discrim), temp = B < 0 ? -0.5f * (B - sq) : -0.5f * (B + sq);
+            nearT = temp / A; farT = C / temp; if (nearT > farT) std::swap(nearT, farT); }
+        if (is_zero(value) || pdf == 0 || nearT >= 0 || farT <= 0) return false;
+        const F3 p = ref + d * farT;
+        out.n = normalize(sc.envCenter - p); out.dist = farT;
+        out.value = value * (1.0f / pdf);                                                       // Spectrum / Float multiplies by the reciprocal
+        out.value = out.value * eval_transmittance(sc, ref, d, farT, maxInteractions);          // isOnSurface(): EOnSurface is set (envmap.cpp:107)
+        out.value = out.value * (1.0f / emPdf);
+        out.pdf = pdf * emPdf;
+        return true;
+    }
     const Scene::EmitterSampler &E = sc.emitterSamplers[ei];
     if (E.sphere >= 0) {                     // Sphere::sampleDirect, src/shapes/sphere.cpp:286-355
         const ppg_sphere &sp = sc.spheres[E.sphere];
@@ -592,6 +697,7 @@ static inline bool sample_emitter_direct(const Scene &sc, F3 ref, F3 refN, float
 }
 // Scene::pdfEmitterDirect (scene.cpp:949-952) for an emitter hit found by BSDF / guiding sampling (dRec.setQuery, records.inl:170-178)
 static inline float pdf_emitter_direct(const Scene &sc, int emitter, F3 ref, F3 refN, F3 d, F3 n, float dist) {
+    if (emitter == kEnvEmitter) return sc.envPdfDirection(d) * (1.0f * sc.emitterNormalization);   // EnvironmentMap::pdfDirect, ESolidAngle (fillDirectSamplingRecord, envmap.cpp:371)
     if (!(dot(d, refN) >= 0 && dot(d, n) < 0)) return 0.0f;                                    // AreaLight::pdfDirect (area.cpp:175-183)
     if (sc.emitterSamplers[emitter].sphere >= 0) {                                             // Sphere::pdfDirect, sphere.cpp:357-392
         const ppg_sphere &sp = sc.spheres[sc.emitterSamplers[emitter].sphere];
@@ -1336,9 +1442,9 @@ public:
                     }
                 } else if (!lost && sc.hasEnvironment()) {
                     // "Intersected nothing -- perhaps there is an environment map?" (GP:2228-2243); fillDirectSamplingRecord succeeds for any ray
-                    // that starts inside the scene's bounding sphere (envmap.cpp:360-378).  Light sampling of the environment is not built
-                    // (create refuses nee != never with an environment emitter), so no emitter pdf is needed here.
+                    // that starts inside the scene's bounding sphere (envmap.cpp:360-378), which every surface point does (radius x 1.5)
                     value = transmittance * sc.evalEnvironment(d);
+                    qEmitter = kEnvEmitter;
                 }
             }
             const bool isDelta = bs.delta;

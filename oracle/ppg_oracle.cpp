@@ -127,6 +127,34 @@ int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *
     return PPG_OK;
 }
 
+// Scene::sampleAttenuatedEmitterDirect at n reference points (area, sphere and environment emitters); pdf 0 = the sample carries nothing
+int ppgo_emitter_sample_direct(ppgo_handle *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,
+                               float *d_out, float *value_out, float *pdf_out, float *dist_out) {
+    if (!h->tracer) return PPG_ERR_NO_SCENE;
+    const Scene &sc = h->tracer->sc;
+    for (size_t i = 0; i < n; ++i) {
+        DirectSample ds; ds.value = f3(0, 0, 0); ds.d = f3(0, 0, 0); ds.pdf = 0; ds.dist = 0;
+        const bool ok = sample_emitter_direct(sc, f3(ref[3 * i], ref[3 * i + 1], ref[3 * i + 2]), f3(ref_n[3 * i], ref_n[3 * i + 1], ref_n[3 * i + 2]),
+                                              sample[2 * i], sample[2 * i + 1], ds, max_interactions);
+        if (!ok) { ds.value = f3(0, 0, 0); ds.pdf = 0; }
+        d_out[3 * i] = ds.d.x; d_out[3 * i + 1] = ds.d.y; d_out[3 * i + 2] = ds.d.z;
+        value_out[3 * i] = ds.value.x; value_out[3 * i + 1] = ds.value.y; value_out[3 * i + 2] = ds.value.z;
+        pdf_out[i] = ds.pdf; dist_out[i] = ok ? ds.dist : 0.f;
+    }
+    return PPG_OK;
+}
+// Scene::pdfEmitterDirect of the environment emitter for n world directions, and its radiance there (evalEnvironment)
+int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float *value_out) {
+    if (!h->tracer || !h->tracer->sc.hasEnvironment()) return PPG_ERR_NO_SCENE;
+    const Scene &sc = h->tracer->sc;
+    for (size_t i = 0; i < n; ++i) {
+        const F3 dw = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        pdf_out[i] = pdf_emitter_direct(sc, kEnvEmitter, f3(0, 0, 0), f3(0, 0, 0), dw, f3(0, 0, 0), 0.f);
+        if (value_out) { const F3 v = sc.evalEnvironment(dw); value_out[3 * i] = v.x; value_out[3 * i + 1] = v.y; value_out[3 * i + 2] = v.z; }
+    }
+    return PPG_OK;
+}
+
 int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb) { h->T().refine((size_t) threshold, max_mb); return PPG_OK; }
 int ppgo_tree_reset(ppgo_handle *h, int max_depth, float threshold) { h->T().resetAll(max_depth, threshold, 1); return PPG_OK; }
 int ppgo_tree_build(ppgo_handle *h) { h->T().buildAll(1); return PPG_OK; }

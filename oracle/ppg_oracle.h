@@ -31,6 +31,13 @@ int ppgo_get_moment_images(ppgo_handle *h, float *sum_rgbw, float *sumsq_rgbw);
 int ppgo_bsdf_eval_pdf(const ppg_bsdf *b, size_t n, const float *wi, const float *wo, float *eval_out, float *pdf_out, const float *tables /* may be NULL */);
 int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *sample, float *wo_out, float *weight_out, float *pdf_out, uint8_t *delta_out, const float *tables);
 
+/* ---- emitter level (handle with a scene): Scene::sampleAttenuatedEmitterDirect at n reference points -- ref, ref_n 3n (ref_n 0 = two-sided),
+ * sample 2n; d_out 3n, value_out 3n (radiance * transmittance / pdf), pdf_out n (0: nothing), dist_out n -- and the environment emitter's
+ * light-sampling density (Scene::pdfEmitterDirect) / radiance for n world directions */
+int ppgo_emitter_sample_direct(ppgo_handle *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,
+                               float *d_out, float *value_out, float *pdf_out, float *dist_out);
+int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float *value_out /* 3n or NULL */);
+
 /* ---- SD-tree level operations (work on the handle's tree) */
 int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb);
 int ppgo_tree_reset(ppgo_handle *h, int max_depth, float threshold);

@@ -90,11 +90,21 @@ __global__ void __launch_bounds__(SMEM ? PPG_BOUNCE_BLOCK : PPG_BOUNCE_BLOCK_HBM
             if (FULL && !found && rayOk && P.scene.envW) {
                 // the ray left the scene: radiance of the environment emitter.  Camera rays and rays that have only crossed index-matched surfaces
                 // take it through the EEmittedRadiance branch (GP:1902-1914: only while unscattered, and not with hideEmitters); after a real
-                // bounce it is the `value` of rayIntersectAndLookForEmitter (GP:2228-2243), always added (MIS weight 1: environment light
-                // sampling is not built, ppg_set_scene refuses nee != never together with an environment emitter)
+                // bounce it is the `value` of rayIntersectAndLookForEmitter (GP:2228-2243), always added -- MIS-weighted against the light
+                // sampling of the environment emitter when that runs (GP:2084-2088)
                 const bool viaNull = !FIRST && (flags & PPG_FLAG_NULL);
                 const bool add = (FIRST || viaNull) ? ((FIRST || (flags & PPG_FLAG_UNSCATTERED)) && !P.hideEmitters) : true;
-                if (add) Li = Li + thr * env_eval(P.scene, d);
+                if (add) {
+                    float3 Lenv = thr * env_eval(P.scene, d);
+                    if (NEE && !FIRST && !viaNull && P.doNee && !(prevSlot >> 31))
+                        Lenv = Lenv * mi_weight(prevWoPdf, pdf_emitter_direct<FULL>(P.scene, PPG_ENV_EMITTER, o, prevRefN, d, f3(0, 0, 0), 0.f));
+                    Li = Li + Lenv;
+                }
+                if (NEE && !FIRST && !viaNull && P.training && P.neeMode == 2 && ((prevSlot >> 30) & 1u)) {
+                    // nee == always: the vertex created at the previous bounce starts with radiance 0 instead of L (GP:2101), also when L came from the environment
+                    const uint32_t ps = prevSlot & 0x3fffffffu;
+                    float4 pv = P.prevSlab.v2[ps]; pv.x = Li.x; pv.y = Li.y; pv.z = Li.z; P.prevSlab.v2[ps] = pv;
+                }
             }
             Its its;
             if (cont) {

@@ -103,7 +103,16 @@ struct SceneView {
     //   texMeta[2i+0] = {bits(width), bits(height), bits(wrapU | wrapV<<8), bits(first texel)}, texMeta[2i+1] = {uScale, vScale, uOffset, vOffset}
     const float4 *texMeta; const uint2 *texels; uint32_t nTextures;
     const uint2 *envTexels; uint32_t envW, envH; float envScale; float worldToEnv[9];
+    // light sampling of the environment emitter (nee != never; EnvironmentMap::configure, src/emitters/envmap.cpp:260-329): marginal row CDF [envH + 1],
+    // conditional column CDFs [envH x (envW + 1)], sin(theta) row weights [envH]; the scene's bounding sphere x 1.5 (createShape, :330-335).
+    // nLights = entries of emitterCdf - 1 (area emitters, then the environment emitter as the LAST light when there is one: envLight, else 0xFFFFFFFF)
+    // The tables live behind one pointer (device memory): only the light-sampling code of the NEE variants reads them, and the kernels that keep a
+    // local copy of this struct (noinline callees take it by reference) stay small.
+    const struct EnvLight *env;
+    uint32_t nLights, envLight;
 };
+struct EnvLight { const float *cdfRows, *cdfCols, *rowWeights; float normalization, pixelX, pixelY, radius; float center[3]; float toWorld[9]; };
+#define PPG_ENV_EMITTER (-2)    // "dRec.object is the environment emitter" in the emitter-pdf queries
 struct Camera {             // src/sensors/perspective.cpp:271-298 for a lookAt camera
     float3 o, left, up, dir;
     float tanX, tanY, nearClip, farClip;
@@ -961,6 +970,56 @@ static __device__ __noinline__ float3 env_eval(const SceneView &sc, float3 d) {
     const float vv = acosf(fminf(1.0f, fmaxf(-1.0f, v.y))) * PPG_INV_PI;               // math::safe_acos * INV_PI
     return tex_bilinear(sc.envTexels, (int) sc.envW, (int) sc.envH, 0u, 1u, uu, vv) * sc.envScale;
 }
+// ---- light sampling of the environment emitter (full-feature NEE variants only; rare path, not inlined)
+// EnvironmentMap::sampleReuse (envmap.cpp:657-662): std::lower_bound over cdf[0..size], clamp, rescale the sample
+__device__ __forceinline__ uint32_t env_sample_reuse(const float *__restrict__ cdf, uint32_t size, float &sample) {
+    uint32_t lo = 0, hi = size + 1;                   // first index with !(cdf[idx] < sample)
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&cdf[mid]) < sample) lo = mid + 1; else hi = mid; }
+    int index = (int) lo - 1; if (index < 0) index = 0; if ((uint32_t) index > size - 1) index = (int) size - 1;
+    const float c0 = __ldg(&cdf[index]), c1 = __ldg(&cdf[index + 1]);
+    sample = (sample - c0) / (c1 - c0);
+    return (uint32_t) index;
+}
+__device__ __forceinline__ float interval_to_tent(float sample) {                     // libcore/warp.cpp:143-155
+    float sign;
+    if (sample < 0.5f) { sign = 1.f; sample *= 2.f; } else { sign = -1.f; sample = 2.f * (sample - 0.5f); }
+    return sign * (1.f - sqrtf(sample));
+}
+__device__ __forceinline__ float luminance(float3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }
+// the bilinear, luminance- and row-weighted density shared by internalSampleDirection / internalPdfDirection (envmap.cpp:577-591, 619-632), before the 1 / sin(theta)
+static __device__ __noinline__ float env_density(const SceneView &sc, float px, float py, float3 *valueOut) {
+    const int W = (int) sc.envW, H = (int) sc.envH;
+    const int xPos = (int) floorf(px), yPos = (int) floorf(py);
+    const float dx1 = px - (float) xPos, dx2 = 1.0f - dx1, dy1 = py - (float) yPos, dy2 = 1.0f - dy1;
+    const float3 value1 = tex_texel(sc.envTexels, W, H, 0u, 1u, xPos, yPos) * dx2 * dy2 + tex_texel(sc.envTexels, W, H, 0u, 1u, xPos + 1, yPos) * dx1 * dy2;
+    const float3 value2 = tex_texel(sc.envTexels, W, H, 0u, 1u, xPos, yPos + 1) * dx2 * dy1 + tex_texel(sc.envTexels, W, H, 0u, 1u, xPos + 1, yPos + 1) * dx1 * dy1;
+    if (valueOut) *valueOut = (value1 + value2) * sc.envScale;
+    const int y0 = min(max(yPos, 0), H - 1), y1 = min(max(yPos + 1, 0), H - 1);
+    const float *rowWeights = sc.env->rowWeights;
+    return (luminance(value1) * __ldg(&rowWeights[y0]) + luminance(value2) * __ldg(&rowWeights[y1])) * sc.env->normalization;
+}
+// EnvironmentMap::internalSampleDirection (envmap.cpp:567-600): direction in the emitter's frame, radiance there, solid-angle density
+static __device__ __noinline__ void env_sample_direction(const SceneView &sc, float sx, float sy, float3 &d, float3 &value, float &pdf) {
+    const uint32_t row = env_sample_reuse(sc.env->cdfRows, sc.envH, sy);
+    const uint32_t col = env_sample_reuse(sc.env->cdfCols + (size_t) row * (sc.envW + 1u), sc.envW, sx);
+    const float px = (float) col + interval_to_tent(sx), py = (float) row + interval_to_tent(sy);
+    pdf = env_density(sc, px, py, &value);
+    float sinPhi, cosPhi, sinTheta, cosTheta;
+    sincosf(sc.env->pixelX * (px + 0.5f), &sinPhi, &cosPhi);
+    sincosf(sc.env->pixelY * (py + 0.5f), &sinTheta, &cosTheta);
+    d = f3(sinPhi * sinTheta, cosTheta, -cosPhi * sinTheta);
+    pdf /= fmaxf(fabsf(sinTheta), PPG_EPSILON);
+}
+// EnvironmentMap::pdfDirect in the solid-angle measure -> internalPdfDirection (envmap.cpp:545-548, 603-633) for a WORLD direction
+static __device__ __noinline__ float env_pdf_direction(const SceneView &sc, float3 dw) {
+    const float3 d = f3(sc.worldToEnv[0] * dw.x + sc.worldToEnv[1] * dw.y + sc.worldToEnv[2] * dw.z, sc.worldToEnv[3] * dw.x + sc.worldToEnv[4] * dw.y + sc.worldToEnv[5] * dw.z,
+                        sc.worldToEnv[6] * dw.x + sc.worldToEnv[7] * dw.y + sc.worldToEnv[8] * dw.z);
+    const float uu = atan2f(d.x, -d.z) * 0.15915494309189533577f, vv = acosf(fminf(1.0f, fmaxf(-1.0f, d.y))) * PPG_INV_PI;
+    if (!isfinite(uu) || !isfinite(vv)) return 0.0f;
+    const float u = uu * (float) sc.envW - 0.5f, v = vv * (float) sc.envH - 0.5f;
+    const float sinTheta = sqrtf(fmaxf(0.0f, 1.f - d.y * d.y));                        // math::safe_sqrt
+    return env_density(sc, u, v, nullptr) / fmaxf(fabsf(sinTheta), PPG_EPSILON);
+}
 __device__ __forceinline__ void coordinate_system(float3 a, float3 &b, float3 &c);
 // Texture coordinates of a triangle hit (skdtree.h:398-405), the textured BSDF parameters there, and BumpMap::getFrame (src/bsdfs/bumpmap.cpp:139-159)
 // with the per-triangle UV tangents of TriMesh::computeUVTangents (src/librender/trimesh.cpp:683-743).  With a bump map the shading frame of `its`
@@ -1313,7 +1372,11 @@ __device__ __noinline__ float3 look_through(const Acc &A_, float3 o, float3 d, c
         if (surface) { fill_its<true>(A_, h, ro, d, cur); curT = h.t; }
         if (++interactions > 100) return f3(0, 0, 0);
     }
-    if (!surface) return A_.g.envW ? transmittance * env_eval(A_.g, d) : f3(0, 0, 0);      // "perhaps there is an environment map?" (GP:2228-2243)
+    if (!surface) {                                                                         // "perhaps there is an environment map?" (GP:2228-2243)
+        if (!A_.g.envW) return f3(0, 0, 0);
+        qEmitter = PPG_ENV_EMITTER;                                                         // fillDirectSamplingRecord: dRec.object = the environment emitter
+        return transmittance * env_eval(A_.g, d);
+    }
     if (cur.emitter < 0) return f3(0, 0, 0);
     qEmitter = cur.emitter; qN = cur.shN; qDist = curT;
     if (!(dot(cur.shN, -d) > 0.f)) return f3(0, 0, 0);
@@ -1334,10 +1397,31 @@ __device__ __forceinline__ void coordinate_system(float3 a, float3 &b, float3 &c
 template <bool SPHERES, class Acc>
 __device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref, float3 refN, float sx, float sy, DirectSample &out, float &dist) {
     const SceneView &sc = A_.g;        // the emitter tables stay in HBM (read-only path)
-    const uint32_t ei = cdf_sample(sc.emitterCdf, sc.nEmitters + 1, sx);
+    const uint32_t ei = cdf_sample(sc.emitterCdf, sc.nLights + 1, sx);
     const float c0 = sc.emitterCdf[ei], c1 = sc.emitterCdf[ei + 1];
     const float emPdf = c1 - c0;
     sx = (sx - c0) / (c1 - c0);
+    if (SPHERES && ei == sc.envLight) {                 // EnvironmentMap::sampleDirect, src/emitters/envmap.cpp:516-543 (no dRec.refN test there)
+        float3 dl, value; float pdf;
+        env_sample_direction(sc, sx, sy, dl, value, pdf);
+        const float *m = sc.env->toWorld;
+        const float3 d = f3(m[0] * dl.x + m[1] * dl.y + m[2] * dl.z, m[3] * dl.x + m[4] * dl.y + m[5] * dl.z, m[6] * dl.x + m[7] * dl.y + m[8] * dl.z);
+        out.d = d;
+        // m_sceneBSphere.rayIntersect (bsphere.h:88-95) -> solveQuadratic (util.cpp:447-485): the far intersection carries the sample
+        const float3 o = ref - f3(sc.env->center[0], sc.env->center[1], sc.env->center[2]);
+        const float A = dot(d, d), B = 2.f * dot(o, d), C = dot(o, o) - sc.env->radius * sc.env->radius;
+        if (A == 0.f) return false;
+        const float discrim = B * B - 4.0f * A * C;
+        if (discrim < 0.f) return false;
+        const float sq = sqrtf(discrim), temp = B < 0.f ? -0.5f * (B - sq) : -0.5f * (B + sq);
+        float nearT = temp / A, farT = C / temp;
+        if (nearT > farT) { const float s_ = nearT; nearT = farT; farT = s_; }
+        if (is_zero(value) || pdf == 0.f || nearT >= 0.f || farT <= 0.f) return false;
+        dist = farT;
+        out.value = (value * (1.0f / pdf)) * (1.0f / emPdf);
+        out.pdf = pdf * emPdf;
+        return true;
+    }
     const float4 info = sc.emitterInfo[ei];
     const uint32_t first = __float_as_uint(info.x), nTris = __float_as_uint(info.y), cdfOff = __float_as_uint(info.w);
     if (SPHERES && (first & PPG_SPHERE_BIT)) {          // Sphere::sampleDirect, src/shapes/sphere.cpp:286-355
@@ -1421,6 +1505,7 @@ __device__ __forceinline__ bool sample_emitter_direct(const Acc &A_, float3 ref,
 // Scene::pdfEmitterDirect (scene.cpp:949-952) for an emitter hit found by BSDF / guiding sampling
 template <bool SPHERES>
 __device__ __forceinline__ float pdf_emitter_direct(const SceneView &sc, int emitter, float3 ref, float3 refN, float3 d, float3 n, float dist) {
+    if (SPHERES && emitter == PPG_ENV_EMITTER) return env_pdf_direction(sc, d) * (1.0f * sc.emitterNormalization);   // EnvironmentMap::pdfDirect, ESolidAngle (envmap.cpp:371, 545-548)
     if (!(dot(d, refN) >= 0.f && dot(d, n) < 0.f)) return 0.0f;
     const float4 info = sc.emitterInfo[emitter];
     if (SPHERES && (__float_as_uint(info.x) & PPG_SPHERE_BIT)) {                                            // Sphere::pdfDirect, sphere.cpp:357-392

@@ -186,6 +186,16 @@ extern "C" void ppg_scene_file_free(ppg_scene_file *file) { delete file; }
 // ------------------------------------------------------------------ host BVH (binned SAH) + Wald triangle constants
 namespace {
 struct H3 { float x, y, z; };
+static inline float half_to_float(uint16_t h) {                                  // IEEE binary16 -> binary32 (host side of the texel tables)
+    const uint32_t sgn = (uint32_t) (h >> 15) << 31, e = (h >> 10) & 31u, m = h & 1023u;
+    uint32_t bits;
+    if (e == 0) {
+        if (m == 0) bits = sgn;
+        else { int sh = 0; uint32_t mm = m; while (!(mm & 1024u)) { mm <<= 1; ++sh; } bits = sgn | ((uint32_t) (113 - sh) << 23) | ((mm & 1023u) << 13); }
+    } else if (e == 31) bits = sgn | 0x7f800000u | (m << 13);
+    else bits = sgn | ((e + 112u) << 23) | (m << 13);
+    float f; memcpy(&f, &bits, 4); return f;
+}
 static inline H3 h3(float x, float y, float z) { return H3{x, y, z}; }
 static inline H3 operator-(H3 a, H3 b) { return h3(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline H3 hcross(H3 a, H3 b) { return h3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
@@ -328,7 +338,7 @@ struct ppg_integrator {
 
     // scene
     bool haveScene = false;
-    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom, dSpheres, dTexMeta; DevBuf<uint2> dTexels, dEnvTexels; DevBuf<float> dEmitterCdf, dEmitterTriCdf, dBsdfTables; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
+    DevBuf<float4> dAccel, dGeom, dBvh, dBsdf, dRadiance, dGroups, dEmitterInfo, dEmitterGeom, dSpheres, dTexMeta; DevBuf<uint2> dTexels, dEnvTexels; DevBuf<float> dEmitterCdf, dEmitterTriCdf, dBsdfTables, dEnvCdfRows, dEnvCdfCols, dEnvRowWeights; DevBuf<EnvLight> dEnvLight; DevBuf<uint32_t> dEmitterFlags; DevBuf<int4> dMeta;
     SceneView sceneView; Camera cam; uint32_t sceneSmemBytes = 0;
     float aabbMin[3], aabbMax[3];
     int W = 0, H = 0;
@@ -624,7 +634,6 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         }
     const bool haveEnv = s->envmap.width && s->envmap.height;
     if (haveEnv && !s->envmap.texels) return fail(PPG_ERR_INVALID_ARGUMENT, "envmap without texel data");
-    if (haveEnv && h->prm.nee != PPG_NEE_NEVER) return fail(PPG_ERR_UNSUPPORTED, "nee != never with an environment emitter (environment light sampling is not built)");
     auto P = [&](uint32_t i) { return h3(s->positions[3 * i], s->positions[3 * i + 1], s->positions[3 * i + 2]); };
     std::vector<H3> tmin(nt), tmax(nt);
     for (uint32_t t = 0; t < nt; ++t) {
@@ -783,9 +792,12 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
             memcpy(&einfo[4 * e], &first, 4); memcpy(&einfo[4 * e + 1], &ntri, 4); einfo[4 * e + 2] = invArea; memcpy(&einfo[4 * e + 3], &cdfOff, 4);
             ecdf.push_back(ecdf.back() + 1.0f);                                                    // getSamplingWeight() == 1
         }
+        v.envLight = 0xFFFFFFFFu;
+        if (haveEnv) { v.envLight = s->n_emitters; ecdf.push_back(ecdf.back() + 1.0f); }          // the environment emitter: last entry of the light list
+        v.nLights = (uint32_t) ecdf.size() - 1u;
         float norm = 0.f;
         if (ecdf.back() > 0) { norm = 1.0f / ecdf.back(); for (size_t i = 1; i < ecdf.size(); ++i) ecdf[i] *= norm; ecdf.back() = 1.0f; }
-        if (ecdf.size() < 2) ecdf.push_back(1.0f);
+        if (ecdf.size() < 2) { ecdf.push_back(1.0f); v.nLights = 1u; }                             // no light at all: one empty entry (never sampled, useNee() is false)
         if (tcdf.empty()) tcdf.assign(2, 0.f);
         if (egeom.empty()) egeom.assign(24, 0.f);
         CK(h->dEmitterCdf.alloc(ecdf.size())); CK(h->dEmitterInfo.alloc(ne)); CK(h->dEmitterTriCdf.alloc(tcdf.size())); CK(h->dEmitterGeom.alloc(egeom.size() / 4)); CK(h->dEmitterFlags.alloc(ne));
@@ -795,7 +807,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         CK(cudaMemcpy(h->dEmitterGeom.p, egeom.data(), egeom.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h->dEmitterFlags.p, eflags.data(), eflags.size() * 4, cudaMemcpyHostToDevice));
         v.emitterCdf = h->dEmitterCdf.p; v.emitterInfo = h->dEmitterInfo.p; v.emitterTriCdf = h->dEmitterTriCdf.p; v.emitterGeom = h->dEmitterGeom.p; v.emitterFlags = h->dEmitterFlags.p;
-        v.emitterNormalization = norm; h->nRealEmitters = s->n_emitters;
+        v.emitterNormalization = norm; h->nRealEmitters = s->n_emitters + (haveEnv ? 1u : 0u);
     }
     {   // analytic spheres
         std::vector<float> sph(8 * (size_t) std::max<uint32_t>(s->n_spheres, 1), 0.f);
@@ -845,6 +857,59 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
             CK(cudaMemcpy(h->dEnvTexels.p, env.data(), env.size() * sizeof(uint2), cudaMemcpyHostToDevice));
             v.envTexels = h->dEnvTexels.p; v.envW = s->envmap.width; v.envH = s->envmap.height; v.envScale = s->envmap.scale;
             for (int i = 0; i < 9; ++i) v.worldToEnv[i] = s->envmap.world_to_env[i];
+        }
+        // light sampling of the environment emitter: the tables of EnvironmentMap::configure (src/emitters/envmap.cpp:260-329), in the reference's float / double mix
+        v.env = nullptr;
+        if (haveEnv) {
+            EnvLight el; memset(&el, 0, sizeof(el));
+            const uint32_t Wd = s->envmap.width, Hd = s->envmap.height;
+            const double kPi = 3.14159265358979323846;
+            auto lum = [&](uint32_t x, uint32_t y) {                                               // Color3::getLuminance of texel (x, y)
+                const uint16_t *px = s->envmap.texels + ((size_t) y * Wd + x) * 3;
+                return half_to_float(px[0]) * 0.212671f + half_to_float(px[1]) * 0.715160f + half_to_float(px[2]) * 0.072169f;
+            };
+            std::vector<float> cols((size_t) (Wd + 1) * Hd, 0.f), rows((size_t) Hd + 1, 0.f), weights(Hd, 0.f);
+            size_t colPos = 0, rowPos = 0; float rowSum = 0.0f;
+            rows[rowPos++] = 0;
+            for (uint32_t y = 0; y < Hd; ++y) {
+                float colSum = 0;
+                cols[colPos++] = 0;
+                for (uint32_t x = 0; x < Wd; ++x) { colSum += lum(x, y); cols[colPos++] = colSum; }
+                const float normalization = 1.0f / colSum;
+                for (uint32_t x = 1; x < Wd; ++x) cols[colPos - x - 1] *= normalization;
+                cols[colPos - 1] = 1.0f;
+                const float weight = (float) std::sin((double) ((float) y + 0.5f) * kPi / (double) Hd);
+                weights[y] = weight;
+                rowSum += colSum * weight;
+                rows[rowPos++] = rowSum;
+            }
+            if (rowSum == 0) return fail(PPG_ERR_INVALID_ARGUMENT, "The environment map is completely black -- this is not allowed.");
+            if (!std::isfinite(rowSum)) return fail(PPG_ERR_INVALID_ARGUMENT, "The environment map contains an invalid floating point value (nan/inf) -- giving up.");
+            const float normalization = 1.0f / rowSum;
+            for (uint32_t y = 1; y < Hd; ++y) rows[rowPos - y - 1] *= normalization;
+            rows[rowPos - 1] = 1.0f;
+            el.normalization = (float) (1.0 / ((double) rowSum * (2 * kPi / (double) Wd) * (kPi / (double) Hd)));
+            el.pixelX = (float) (2 * kPi / (double) Wd); el.pixelY = (float) (kPi / (double) Hd);
+            float ctr[3], dd = 0.f;                                                                // AABB::getBSphere (libcore/aabb.cpp:44-47), radius x 1.5 (envmap.cpp:333)
+            for (int i = 0; i < 3; ++i) { ctr[i] = (s->aabb_max[i] + s->aabb_min[i]) * 0.5f; el.center[i] = ctr[i]; }
+            { const float ex = ctr[0] - s->aabb_max[0], ey = ctr[1] - s->aabb_max[1], ez = ctr[2] - s->aabb_max[2]; dd = std::sqrt(ex * ex + ey * ey + ez * ez); }
+            el.radius = std::max(1e-4f, dd * 1.5f);
+            const float *m = s->envmap.world_to_env;                                               // the emitter-to-world rotation back from its inverse
+            const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], hh = m[7], ii = m[8];
+            const double det = a * (e * ii - f * hh) - b * (d * ii - f * g) + c * (d * hh - e * g);
+            if (!(std::fabs(det) > 0)) return fail(PPG_ERR_INVALID_ARGUMENT, "envmap: singular world_to_env");
+            const double id = 1.0 / det;
+            const double inv[9] = {(e * ii - f * hh) * id, (c * hh - b * ii) * id, (b * f - c * e) * id, (f * g - d * ii) * id, (a * ii - c * g) * id, (c * d - a * f) * id,
+                                   (d * hh - e * g) * id, (b * g - a * hh) * id, (a * e - b * d) * id};
+            for (int k = 0; k < 9; ++k) el.toWorld[k] = (float) inv[k];
+            CK(h->dEnvCdfRows.alloc(rows.size())); CK(h->dEnvCdfCols.alloc(cols.size())); CK(h->dEnvRowWeights.alloc(weights.size()));
+            CK(cudaMemcpy(h->dEnvCdfRows.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->dEnvCdfCols.p, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->dEnvRowWeights.p, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice));
+            el.cdfRows = h->dEnvCdfRows.p; el.cdfCols = h->dEnvCdfCols.p; el.rowWeights = h->dEnvRowWeights.p;
+            CK(h->dEnvLight.alloc(1));
+            CK(cudaMemcpy(h->dEnvLight.p, &el, sizeof(el), cudaMemcpyHostToDevice));
+            v.env = h->dEnvLight.p;
         }
     }
     v.nTris = nt; v.nBvhNodes = (uint32_t) nBvh; v.nBsdfs = s->n_bsdfs; v.nEmitters = std::max<uint32_t>(s->n_emitters, 1);
@@ -1629,6 +1694,28 @@ __global__ void op_lookup_kernel(const uint2 *snodes, const uint32_t *table, flo
         size[3 * i] = v.x; size[3 * i + 1] = v.y; size[3 * i + 2] = v.z;
     }
 }
+// Scene::sampleAttenuatedEmitterDirect at caller-supplied reference points, exactly as the bounce kernel's light-sampling block calls it
+__global__ void op_emitter_sample_kernel(SceneView scene, const float *ref, const float *refN, const float *smp, int maxInteractions, size_t n,
+                                         float *dOut, float *valueOut, float *pdfOut, float *distOut) {
+    const SceneAccess<false> sc(scene);
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const float3 p = f3(ref[3 * i], ref[3 * i + 1], ref[3 * i + 2]), rn = f3(refN[3 * i], refN[3 * i + 1], refN[3 * i + 2]);
+        DirectSample ds; ds.value = f3(0, 0, 0); ds.d = f3(0, 0, 0); ds.pdf = 0.f; float dist = 0.f;
+        const bool ok = sample_emitter_direct<true>(sc, p, rn, smp[2 * i], smp[2 * i + 1], ds, dist);
+        if (ok) ds.value = ds.value * eval_transmittance(sc, p, ds.d, dist, maxInteractions);
+        else { ds.value = f3(0, 0, 0); ds.pdf = 0.f; dist = 0.f; }
+        dOut[3 * i] = ds.d.x; dOut[3 * i + 1] = ds.d.y; dOut[3 * i + 2] = ds.d.z;
+        valueOut[3 * i] = ds.value.x; valueOut[3 * i + 1] = ds.value.y; valueOut[3 * i + 2] = ds.value.z;
+        pdfOut[i] = ds.pdf; distOut[i] = dist;
+    }
+}
+__global__ void op_env_pdf_kernel(SceneView scene, const float *dir, size_t n, float *pdfOut, float *valueOut) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        pdfOut[i] = pdf_emitter_direct<true>(scene, PPG_ENV_EMITTER, f3(0, 0, 0), f3(0, 0, 0), d, f3(0, 0, 0), 0.f);
+        if (valueOut) { const float3 v = env_eval(scene, d); valueOut[3 * i] = v.x; valueOut[3 * i + 1] = v.y; valueOut[3 * i + 2] = v.z; }
+    }
+}
 template <class T> struct Up {
     DevBuf<T> b;
     int up(const T *host, size_t n) { if (b.alloc(std::max<size_t>(n, 1)) != cudaSuccess) return 1; return n ? cudaMemcpy(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess : 0; }
@@ -1699,6 +1786,35 @@ extern "C" int ppg_op_dtree_record(int device, float *sums_inout, const uint16_t
     CK(cudaGetLastError());
     CK(cudaMemcpy(sums_inout, dsums.b.p, 16 * n_nodes, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(tree_weight_inout, dwt.b.p, 4 * n_trees, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+extern "C" int ppg_op_emitter_sample_direct(ppg_integrator *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,
+                                            float *d_out, float *value_out, float *pdf_out, float *dist_out) {
+    if (!h || !h->haveScene) return fail(PPG_ERR_NO_SCENE, "ppg_op_emitter_sample_direct needs a handle with a scene");
+    if (!ref || !ref_n || !sample || !d_out || !value_out || !pdf_out || !dist_out) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    if (!h->fullFeature) return fail(PPG_ERR_UNSUPPORTED, "emitter-level ops run the full-feature code path (scene with spheres, textures, non-diffuse BSDFs or an environment emitter)");
+    CK(cudaSetDevice(h->device));
+    Up<float> dr, dn, ds; DevBuf<float> od, ov, op, ot;
+    if (dr.up(ref, 3 * n) || dn.up(ref_n, 3 * n) || ds.up(sample, 2 * n)) return fail(PPG_ERR_CUDA, "upload failed");
+    CK(od.alloc(std::max<size_t>(3 * n, 1))); CK(ov.alloc(std::max<size_t>(3 * n, 1))); CK(op.alloc(std::max<size_t>(n, 1))); CK(ot.alloc(std::max<size_t>(n, 1)));
+    if (n) op_emitter_sample_kernel<<<296, 128>>>(h->sceneView, dr.b.p, dn.b.p, ds.b.p, max_interactions, n, od.p, ov.p, op.p, ot.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(d_out, od.p, 12 * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(value_out, ov.p, 12 * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pdf_out, op.p, 4 * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(dist_out, ot.p, 4 * n, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+extern "C" int ppg_op_env_pdf(ppg_integrator *h, size_t n, const float *d, float *pdf_out, float *value_out) {
+    if (!h || !h->haveScene) return fail(PPG_ERR_NO_SCENE, "ppg_op_env_pdf needs a handle with a scene");
+    if (!h->sceneView.envW) return fail(PPG_ERR_NO_SCENE, "the scene has no environment emitter");
+    if (!d || !pdf_out) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(h->device));
+    Up<float> dd; DevBuf<float> op, ov;
+    if (dd.up(d, 3 * n)) return fail(PPG_ERR_CUDA, "upload failed");
+    CK(op.alloc(std::max<size_t>(n, 1))); CK(ov.alloc(std::max<size_t>(3 * n, 1)));
+    if (n) op_env_pdf_kernel<<<296, 128>>>(h->sceneView, dd.b.p, n, op.p, value_out ? ov.p : nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(pdf_out, op.p, 4 * n, cudaMemcpyDeviceToHost));
+    if (value_out) CK(cudaMemcpy(value_out, ov.p, 12 * n, cudaMemcpyDeviceToHost));
     return PPG_OK;
 }
 extern "C" int ppg_op_stree_lookup(int device, const uint32_t *node_children, size_t n_nodes, const float aabb_min[3], const float aabb_extent[3],

@@ -283,3 +283,40 @@ def cbox_textured(cbox: SceneDesc, bump=True, env=True, size=64) -> SceneDesc:
         rot = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
         sc.envmap = {"texels": _half_bits(sky).reshape(eh, ew, 3), "scale": 1.5, "world_to_env": np.linalg.inv(rot).astype(np.float32)}
     return sc
+
+
+def env_lit_scene(size=64) -> SceneDesc:
+    """A diffuse ground plate with a diffuse box and a mirror-like rough-conductor slab on it, lit ONLY by a lat-long environment
+    map (dim sky + one bright "sun" texel, rotated about y): no area emitter at all, so every light sample of `nee = always | kickstart`
+    is an environment sample (EnvironmentMap::sampleDirect) and every emitter hit of a BSDF / guided sample is a ray that leaves the scene."""
+    from .scene import BSDF_ROUGHCONDUCTOR
+    meshes = []
+    bsdfs = [_make_bsdf(BSDF_DIFFUSE, 0, (0.6, 0.6, 0.55)), _make_bsdf(BSDF_DIFFUSE, 0, (0.7, 0.3, 0.2)),
+             _make_bsdf(BSDF_ROUGHCONDUCTOR, 0, (0.9, 0.9, 0.9), (0, 0, 0), (0.2, 0.9, 1.1), (3.9, 2.4, 2.2), 0.2, 1)]
+    names = ["ground", "box", "slab"]
+    P, I = _quad((-3, 0, -3), (-3, 0, 3), (3, 0, 3), (3, 0, -3)); meshes.append((P, I, 0))
+    P, I = _box((-0.6, 0.0, -0.5), (0.3, 0.9, 0.4)); meshes.append((P, I, 1))
+    P, I = _quad((0.7, 0.0, -1.0), (0.7, 1.2, -1.0), (1.5, 1.2, 0.2), (1.5, 0.0, 0.2)); meshes.append((P, I, 2))
+    Ps, Is, TS, shapes = [], [], [], []
+    voff = toff = 0
+    for k, (P, I, b) in enumerate(meshes):
+        shapes.append([toff, len(I), b, -1, 0, 0, 0, 0])
+        Ps.append(P); Is.append(I + voff); TS.append(np.full(len(I), k, np.uint32))
+        voff += len(P); toff += len(I)
+    P = np.concatenate(Ps).astype(np.float32)
+    cam = _look_at((2.8, 2.4, 3.6), (0.2, 0.4, 0), (0, 1, 0))
+    mn = np.minimum(P.min(0), cam[:3, 3]); mx = np.maximum(P.max(0), cam[:3, 3])
+    eh, ew = 16, 32
+    t, p = np.mgrid[0:eh, 0:ew].astype(np.float64)
+    sky = np.stack([0.25 + 0.15 * np.cos(p / ew * 2 * np.pi), 0.35 + 0.0 * t, 0.55 - 0.3 * t / eh], -1) * (t[..., None] < eh / 2 + 1)
+    sky[2, 20] += np.array([90.0, 80.0, 60.0])                     # the "sun"
+    sky[5, 3] += np.array([4.0, 6.0, 9.0])                         # a second, dimmer lobe
+    ang = np.radians(-20.0)
+    rot = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    integ = {"strictNormals": "true", "maxDepth": "6", "rrDepth": "5", "budgetType": "spp", "budget": "28", "sppPerPass": "4"}
+    return SceneDesc(positions=P, normals=np.zeros_like(P), uvs=np.zeros((len(P), 2), np.float32),
+                     indices=np.concatenate(Is).astype(np.uint32), triangle_shape=np.concatenate(TS).astype(np.uint32),
+                     shapes=np.asarray(shapes, np.int32), bsdfs=np.asarray(bsdfs, np.float32), area_radiance=np.zeros((0, 3), np.float32),
+                     cam_to_world=cam.astype(np.float32), x_fov_deg=40.0, near_clip=0.1, far_clip=100.0, film_width=size, film_height=size,
+                     aabb_min=mn.astype(np.float32), aabb_max=mx.astype(np.float32), integrator=integ, bsdf_names=names,
+                     envmap={"texels": _half_bits(sky).reshape(eh, ew, 3), "scale": 1.2, "world_to_env": np.linalg.inv(rot).astype(np.float32)})

@@ -149,6 +149,22 @@ class GuidedPathTracer:
     def dump_sdtree(self, path: str):
         _check(self.lib, self.lib.ppg_dump_sdtree(self._h, path.encode()))
 
+    def op_emitter_sample_direct(self, ref, ref_n, sample, max_interactions=-1):
+        """Scene::sampleAttenuatedEmitterDirect at the points `ref` of this handle's scene (ppg_op_emitter_sample_direct): (d, value, pdf, dist)."""
+        f = C.POINTER(C.c_float)
+        ref = np.ascontiguousarray(ref, np.float32); ref_n = np.ascontiguousarray(ref_n, np.float32); smp = np.ascontiguousarray(sample, np.float32)
+        n = len(ref); d = np.zeros((n, 3), np.float32); val = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32); dist = np.zeros(n, np.float32)
+        _check(self.lib, self.lib.ppg_op_emitter_sample_direct(self._h, n, ref.ctypes.data_as(f), ref_n.ctypes.data_as(f), smp.ctypes.data_as(f), max_interactions,
+                                                               d.ctypes.data_as(f), val.ctypes.data_as(f), pdf.ctypes.data_as(f), dist.ctypes.data_as(f)))
+        return d, val, pdf, dist
+
+    def op_env_pdf(self, d):
+        """(light-sampling density incl. the emitter choice, radiance) of the environment emitter for world directions `d` (ppg_op_env_pdf)."""
+        f = C.POINTER(C.c_float)
+        d = np.ascontiguousarray(d, np.float32); pdf = np.zeros(len(d), np.float32); val = np.zeros((len(d), 3), np.float32)
+        _check(self.lib, self.lib.ppg_op_env_pdf(self._h, len(d), d.ctypes.data_as(f), pdf.ctypes.data_as(f), val.ctypes.data_as(f)))
+        return pdf, val
+
     def moment_images(self):
         a = np.empty((self.H, self.W, 4), np.float32)
         b = np.empty_like(a)

@@ -35,6 +35,8 @@ def _declare(lib):
     lib.ppgo_get_moment_images.argtypes = [H, f32p, f32p]
     lib.ppgo_bsdf_eval_pdf.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p]
     lib.ppgo_bsdf_sample.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p, u8p, f32p]
+    lib.ppgo_emitter_sample_direct.argtypes = [H, C.c_size_t, f32p, f32p, f32p, C.c_int, f32p, f32p, f32p, f32p]
+    lib.ppgo_env_pdf.argtypes = [H, C.c_size_t, f32p, f32p, f32p]
     lib.ppgo_tree_refine.argtypes = [H, C.c_uint64, C.c_int]
     lib.ppgo_tree_reset.argtypes = [H, C.c_int, C.c_float]
     lib.ppgo_tree_build.argtypes = [H]
@@ -192,6 +194,21 @@ class Oracle:
         return a, b
 
     # ---- tree level
+    def emitter_sample_direct(self, ref, ref_n, smp, max_interactions=-1):
+        """Scene::sampleAttenuatedEmitterDirect at the points `ref`: (d, value, pdf, dist); pdf == 0 where the sample carries nothing."""
+        ref = np.ascontiguousarray(ref, np.float32); ref_n = np.ascontiguousarray(ref_n, np.float32); smp = np.ascontiguousarray(smp, np.float32)
+        n = len(ref); d = np.zeros((n, 3), np.float32); val = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32); dist = np.zeros(n, np.float32)
+        rc = self.lib.ppgo_emitter_sample_direct(self.h, n, fptr(ref), fptr(ref_n), fptr(smp), max_interactions, fptr(d), fptr(val), fptr(pdf), fptr(dist))
+        assert rc == 0, rc
+        return d, val, pdf, dist
+
+    def env_pdf(self, d):
+        """(light-sampling density incl. the emitter choice, radiance) of the environment emitter for world directions `d`."""
+        d = np.ascontiguousarray(d, np.float32); pdf = np.zeros(len(d), np.float32); val = np.zeros((len(d), 3), np.float32)
+        rc = self.lib.ppgo_env_pdf(self.h, len(d), fptr(d), fptr(pdf), fptr(val))
+        assert rc == 0, rc
+        return pdf, val
+
     def refine(self, threshold, max_mb=-1):
         self.lib.ppgo_tree_refine(self.h, int(threshold), max_mb)
 

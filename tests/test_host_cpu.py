@@ -211,7 +211,7 @@ def test_loader_parses_every_supported_bsdf_and_shape(tmp_path):
     rng = np.random.default_rng(3)
     albedo = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8); cv2.imwrite(str(tmp_path / "albedo.png"), albedo[..., ::-1])
     cv2.imwrite(str(tmp_path / "bump.png"), rng.integers(0, 256, (4, 4), dtype=np.uint8)); cv2.imwrite(str(tmp_path / "env.png"), rng.integers(1, 256, (4, 8, 3), dtype=np.uint8))
-    p = tmp_path / "scene.xml"; p.write_text(xml.replace('<string name="nee" value="always"/>', ""))      # light sampling of an environment emitter is not built
+    p = tmp_path / "scene.xml"; p.write_text(xml)      # nee = always: the lamp, the emitting shell and the environment map are all light-sampled
     sc = S.load_mitsuba_xml(str(p))
     # textures: sRGB-decoded (gamma 0) vs linear (gamma 1), half precision, wrap modes / uv transform in ppg_texture
     assert len(sc.textures) == 2 and sc.texels.dtype == np.uint16
@@ -244,7 +244,7 @@ def test_loader_parses_every_supported_bsdf_and_shape(tmp_path):
     assert sc.spheres[:, 4].view(np.int32).tolist() == [4, 5] and sc.shapes[5, 3] == 1 and sc.shapes[2, 3] == 0     # shape / emitter indices
     assert np.allclose(sc.aabb_min, -50) and np.allclose(sc.aabb_max, 50)
     assert (sc.film_width, sc.film_height) == (64, 48)
-    # and the oracle renders it (all models on one path: light sampling of both emitters through the mask, the glass sphere, the shell)
+    # and the oracle renders it (all models on one path: light sampling of the three emitters through the mask, the glass sphere, the shell)
     import oracle_lib as O
     o = O.Oracle(O.params_from_xml(sc.integrator), sc, kind="port"); img, st = o.render()
     assert img.shape == (48, 64, 3) and np.isfinite(img).all() and img.mean() > 0.01 and st["total_paths"] == 64 * 48 * 8
