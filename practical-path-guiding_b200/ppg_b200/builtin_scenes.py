@@ -285,10 +285,12 @@ def cbox_textured(cbox: SceneDesc, bump=True, env=True, size=64) -> SceneDesc:
     return sc
 
 
-def env_lit_scene(size=64) -> SceneDesc:
+def env_lit_scene(size=64, torus=False) -> SceneDesc:
     """A diffuse ground plate with a diffuse box and a mirror-like rough-conductor slab on it, lit ONLY by a lat-long environment
     map (dim sky + one bright "sun" texel, rotated about y): no area emitter at all, so every light sample of `nee = always | kickstart`
-    is an environment sample (EnvironmentMap::sampleDirect) and every emitter hit of a BSDF / guided sample is a ray that leaves the scene."""
+    is an environment sample (EnvironmentMap::sampleDirect) and every emitter hit of a BSDF / guided sample is a ray that leaves the scene.
+    `torus` adds a smooth-shaded diffuse torus of 2304 triangles: the scene then no longer fits the shared-memory staging and is intersected
+    through the BVH (and, from 32 768 paths per wavefront, by the separate nearest-hit pass)."""
     from .scene import BSDF_ROUGHCONDUCTOR
     meshes = []
     bsdfs = [_make_bsdf(BSDF_DIFFUSE, 0, (0.6, 0.6, 0.55)), _make_bsdf(BSDF_DIFFUSE, 0, (0.7, 0.3, 0.2)),
@@ -297,10 +299,13 @@ def env_lit_scene(size=64) -> SceneDesc:
     P, I = _quad((-3, 0, -3), (-3, 0, 3), (3, 0, 3), (3, 0, -3)); meshes.append((P, I, 0))
     P, I = _box((-0.6, 0.0, -0.5), (0.3, 0.9, 0.4)); meshes.append((P, I, 1))
     P, I = _quad((0.7, 0.0, -1.0), (0.7, 1.2, -1.0), (1.5, 1.2, 0.2), (1.5, 0.0, 0.2)); meshes.append((P, I, 2))
+    normals = [np.zeros((len(m[0]), 3), np.float32) for m in meshes]
+    if torus:
+        P, N, I = _torus(0.55, 0.2, 48, 24, (-1.4, 0.2, 1.2)); meshes.append((P, I, 1)); normals.append(N)
     Ps, Is, TS, shapes = [], [], [], []
     voff = toff = 0
     for k, (P, I, b) in enumerate(meshes):
-        shapes.append([toff, len(I), b, -1, 0, 0, 0, 0])
+        shapes.append([toff, len(I), b, -1, 1 if np.any(normals[k]) else 0, 0, 0, 0])
         Ps.append(P); Is.append(I + voff); TS.append(np.full(len(I), k, np.uint32))
         voff += len(P); toff += len(I)
     P = np.concatenate(Ps).astype(np.float32)
@@ -314,7 +319,7 @@ def env_lit_scene(size=64) -> SceneDesc:
     ang = np.radians(-20.0)
     rot = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
     integ = {"strictNormals": "true", "maxDepth": "6", "rrDepth": "5", "budgetType": "spp", "budget": "28", "sppPerPass": "4"}
-    return SceneDesc(positions=P, normals=np.zeros_like(P), uvs=np.zeros((len(P), 2), np.float32),
+    return SceneDesc(positions=P, normals=np.concatenate(normals).astype(np.float32), uvs=np.zeros((len(P), 2), np.float32),
                      indices=np.concatenate(Is).astype(np.uint32), triangle_shape=np.concatenate(TS).astype(np.uint32),
                      shapes=np.asarray(shapes, np.int32), bsdfs=np.asarray(bsdfs, np.float32), area_radiance=np.zeros((0, 3), np.float32),
                      cam_to_world=cam.astype(np.float32), x_fov_deg=40.0, near_clip=0.1, far_clip=100.0, film_width=size, film_height=size,

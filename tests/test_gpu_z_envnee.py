@@ -62,15 +62,18 @@ def test_op_env_pdf_matches_oracle():
     assert abs(float(pdf.sum()) - float(pdf0.sum())) <= 1e-4 * float(pdf0.sum())
 
 
-@pytest.mark.parametrize("extra", [dict(nee="always"), dict(nee="kickstart", spatialFilter="stochastic", directionalFilter="box")])
+@pytest.mark.parametrize("extra", [dict(nee="always"), dict(nee="kickstart", spatialFilter="stochastic", directionalFilter="box"), dict(nee="always", torus=True)])
 def test_environment_lit_scene_with_light_sampling_matches_oracle(extra):
     """A scene lit ONLY by an environment map (no area emitter): every light sample is EnvironmentMap::sampleDirect, every emitter hit of a BSDF / guided
-    sample is a ray that leaves the scene and is MIS-weighted with EnvironmentMap::pdfDirect; with `always` the vertices' radiance excludes it (GP:2101)."""
-    sc = B.env_lit_scene(96)
+    sample is a ray that leaves the scene and is MIS-weighted with EnvironmentMap::pdfDirect; with `always` the vertices' radiance excludes it (GP:2101).
+    `torus`: 2304 more triangles -- the kernels that read the scene from HBM, the BVH walk and the separate nearest-hit pass.
+    Measured (profiles/r02_envnee_check.log): equal vertex counts, every pixel equal to 1e-3, relMSE 1e-14 (always) / 3e-10 (kickstart + filters)."""
+    extra = dict(extra)
+    sc = B.env_lit_scene(96, torus=extra.pop("torus", False))
     props = dict(dict(sc.integrator, budget="60"), **extra)
     img, st = _gpu(props, sc).render()
     ref, ost = O.Oracle(O.params_from_xml(props), sc, kind="port").render()
-    assert_render_parity(img, ref, st, ost, sc, props, pixels=0.85, counts=2e-3)
+    assert_render_parity(img, ref, st, ost, sc, props)
     # light sampling is really on: without it the same seed gives another (much noisier) image
     img0, _ = _gpu(dict(props, nee="never"), sc).render()
     assert not np.isclose(img0, img, rtol=1e-3, atol=1e-5).all(axis=2).mean() > 0.5
@@ -82,4 +85,4 @@ def test_area_and_environment_lights_with_light_sampling_match_oracle():
     props = dict(sc.integrator, budget="60", nee="always")
     img, st = _gpu(props, sc).render()
     ref, ost = O.Oracle(O.params_from_xml(props), sc, kind="port").render()
-    assert_render_parity(img, ref, st, ost, sc, props, pixels=0.85, counts=2e-3)
+    assert_render_parity(img, ref, st, ost, sc, props)

@@ -57,4 +57,5 @@ if __name__ == "__main__":
     render("env-only", env, nee="always")
     render("env-only", env, nee="kickstart", spatialFilter="stochastic", directionalFilter="box")
     render("area+env", both, nee="always")
+    render("env-torus (BVH, trace pass)", B.env_lit_scene(96, torus=True), nee="always")
     render("env-only", env, nee="never")
