@@ -413,6 +413,15 @@ int ppg_op_dtree_record(int device,
                         const uint32_t *rec_tree, const float *rec_dir, const float *rec_radiance,
                         const float *rec_wo_pdf, const float *rec_weight, size_t n, int filter);
 
+/* The acceleration structure ppg_set_scene builds over the scene's triangles (binned-SAH BVH; it takes the place of the reference's ShapeKDTree,
+ * src/librender/skdtree.cpp), on the HOST alone -- no CUDA device needed: for tests of the builder and for timing it.  positions 3 floats per vertex,
+ * indices 3 per triangle; threads <= 0: the library's default (the cores this process may use, at most 16; PPG_HOST_THREADS overrides).
+ * nodes_out: 8 floats per node {min.xyz, bits(left), max.xyz, bits(count)} -- count == 0: inner node with children `left`, `left + 1`; otherwise a
+ * leaf over order_out[left .. left + count) -- capacity in nodes (2 * n_triangles + 1 always suffices); order_out: n_triangles triangle indices.
+ * The result does not depend on the thread count.  Any output pointer may be NULL. */
+int ppg_op_bvh_build(const float *positions, const uint32_t *indices, size_t n_triangles, int threads,
+                     float *nodes_out, size_t nodes_capacity, uint32_t *order_out, size_t *n_nodes_out, int *max_depth_out, double *ms_out);
+
 /* Scene::sampleAttenuatedEmitterDirect (src/librender/scene.cpp:876-897 -> AreaLight / Sphere / EnvironmentMap::sampleDirect, then
  * Scene::evalTransmittance) at n reference points of the handle's scene, as the light-sampling block of Li calls it (GP:1964-1973):
  * ref, ref_n 3n floats (ref_n = 0: no front-side test, records.inl:160-164), sample 2n uniforms, max_interactions = maxDepth - depth - 1

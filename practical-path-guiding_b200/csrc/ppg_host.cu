@@ -15,7 +15,11 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 using namespace ppg;
 
@@ -218,102 +222,205 @@ static void wald_constants(H3 A, H3 B, H3 C, float out[9], int &k) {
 }
 
 static int bvh_env_int(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }   // tuning experiments only
+
+// Host-side parallelism of ppg_set_scene (per-triangle tables, BVH build, texel repacking): plain std::thread fork / join over index ranges.
+// PPG_HOST_THREADS overrides the count (default: the cores this process may run on, at most 16).  Every parallel loop below computes
+// exactly what its serial form computes (min / max / integer counts / independent elements), so the scene tables do not depend on the count.
+static int host_threads() {
+    static const int n = [] {
+        int t = bvh_env_int("PPG_HOST_THREADS", 0);
+        if (t <= 0) {
+            t = (int) std::thread::hardware_concurrency();
+#ifdef __linux__
+            cpu_set_t set; CPU_ZERO(&set);
+            if (sched_getaffinity(0, sizeof(set), &set) == 0) t = CPU_COUNT(&set);
+#endif
+            t = std::min(t, 16);
+        }
+        return std::max(t, 1);
+    }();
+    return n;
+}
+template <class F> static void parallel_for(size_t n, int threads, size_t minChunk, F fn) {   // fn(begin, end, chunk index)
+    const int T = (int) std::max<size_t>(1, std::min<size_t>((size_t) threads, n / std::max<size_t>(minChunk, 1)));
+    if (T <= 1) { fn((size_t) 0, n, 0); return; }
+    std::vector<std::thread> pool; pool.reserve(T - 1);
+    for (int k = 1; k < T; ++k) pool.emplace_back([&, k] { fn(n * k / T, n * (k + 1) / T, k); });
+    fn((size_t) 0, n / T, 0);
+    for (auto &th : pool) th.join();
+}
+
 struct HostBvh {
     std::vector<float> nodes;        // 8 floats per node
     std::vector<uint32_t> order;     // leaf order -> original triangle
     int maxDepth = 0;                // the device walk keeps one stack entry per level (PPG_BVH_STACK)
 };
-static void build_bvh(const std::vector<H3> &tmin, const std::vector<H3> &tmax, HostBvh &out) {
-    const uint32_t nt = (uint32_t) tmin.size();
+// Binned-SAH BVH (16 bins per axis, leaves of at most PPG_BVH_LEAF triangles, a traversal-cost term decides the last splits).
+// The tree is a function of the triangle bounds alone: a node's split depends only on the triangles of its range, children work on disjoint
+// ranges of `order`.  It is therefore built in any order -- big nodes one after the other with their O(n) loops spread over the threads, the
+// subtrees below them concurrently -- into an arena, and numbered afterwards in the order a depth-first stack visits it (right child first),
+// which is the numbering the device layout (siblings adjacent, `left` = index of the first child) has always had.
+static void build_bvh(const std::vector<H3> &tminV, const std::vector<H3> &tmaxV, HostBvh &out, int threads) {
+    const uint32_t nt = (uint32_t) tminV.size();
     out.order.resize(nt);
-    for (uint32_t i = 0; i < nt; ++i) out.order[i] = i;
-    std::vector<H3> cen(nt);
-    for (uint32_t t = 0; t < nt; ++t) cen[t] = h3(0.5f * (tmin[t].x + tmax[t].x), 0.5f * (tmin[t].y + tmax[t].y), 0.5f * (tmin[t].z + tmax[t].z));
-    struct Node { H3 mn, mx; uint32_t left, count; };
-    std::vector<Node> nodes; nodes.reserve(2 * nt + 1); nodes.push_back(Node());
+    std::vector<H3> cenV(nt);
+    const H3 *const tmin = tminV.data(), *const tmax = tmaxV.data(); H3 *const cen = cenV.data();
+    parallel_for(nt, threads, 1 << 15, [&](size_t b, size_t e, int) {
+        for (size_t t = b; t < e; ++t) { out.order[t] = (uint32_t) t; cen[t] = h3(0.5f * (tmin[t].x + tmax[t].x), 0.5f * (tmin[t].y + tmax[t].y), 0.5f * (tmin[t].z + tmax[t].z)); }
+    });
+    const int maxLeaf = std::min(std::max(bvh_env_int("PPG_BVH_LEAF", 4), 1), 15);   // <= 15: the device stack packs the count in 4 bits
+    const float Ct = (float) bvh_env_int("PPG_BVH_CT_X10", 10) * 0.1f;
+    constexpr int NB = 16;
+    struct Node { H3 mn, mx; uint32_t left, count; };                                 // count == 0: inner node, `left` = arena index of its first child
     struct Job { uint32_t node, first, count; int depth; };
-    std::vector<Job> jobs; jobs.push_back(Job{0, 0, nt, 0});
+    struct Bounds { H3 mn, mx, cmn, cmx; };
+    struct Bins { H3 mn[3][NB], mx[3][NB]; uint32_t c[3][NB]; };
+    const H3 big = h3(1e30f, 1e30f, 1e30f), small = h3(-1e30f, -1e30f, -1e30f);
+    auto hmin = [](H3 a, H3 b) { return h3(std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)); };
+    auto hmax = [](H3 a, H3 b) { return h3(std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)); };
     auto area = [](H3 mn, H3 mx) { const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z; return 2.f * (dx * dy + dy * dz + dz * dx); };
-    while (!jobs.empty()) {
-        const Job j = jobs.back(); jobs.pop_back();
-        out.maxDepth = std::max(out.maxDepth, j.depth);
-        H3 mn = h3(1e30f, 1e30f, 1e30f), mx = h3(-1e30f, -1e30f, -1e30f), cmn = mn, cmx = mx;
-        for (uint32_t i = j.first; i < j.first + j.count; ++i) {
-            const uint32_t t = out.order[i];
-            mn = h3(std::min(mn.x, tmin[t].x), std::min(mn.y, tmin[t].y), std::min(mn.z, tmin[t].z));
-            mx = h3(std::max(mx.x, tmax[t].x), std::max(mx.y, tmax[t].y), std::max(mx.z, tmax[t].z));
-            cmn = h3(std::min(cmn.x, cen[t].x), std::min(cmn.y, cen[t].y), std::min(cmn.z, cen[t].z));
-            cmx = h3(std::max(cmx.x, cen[t].x), std::max(cmx.y, cen[t].y), std::max(cmx.z, cen[t].z));
-        }
-        Node nd; nd.mn = mn; nd.mx = mx; nd.left = j.first; nd.count = j.count;
-        static const int maxLeaf = std::min(std::max(bvh_env_int("PPG_BVH_LEAF", 4), 1), 15);   // <= 15: the device stack packs the count in 4 bits
-        if (j.count > (uint32_t) maxLeaf || j.count > 1) {
-            // binned SAH over the three axes
-            const int NB = 16; float bestCost = std::numeric_limits<float>::infinity(); int bestAxis = -1, bestBin = -1;
-            for (int ax = 0; ax < 3; ++ax) {
-                const float lo = hcomp(cmn, ax), hi = hcomp(cmx, ax);
-                if (!(hi > lo)) continue;
-                H3 bmn[NB], bmx[NB]; uint32_t bc[NB];
-                for (int b = 0; b < NB; ++b) { bmn[b] = h3(1e30f, 1e30f, 1e30f); bmx[b] = h3(-1e30f, -1e30f, -1e30f); bc[b] = 0; }
-                for (uint32_t i = j.first; i < j.first + j.count; ++i) {
-                    const uint32_t t = out.order[i];
-                    int b = (int) (NB * (hcomp(cen[t], ax) - lo) / (hi - lo)); b = std::min(std::max(b, 0), NB - 1);
-                    bc[b]++;
-                    bmn[b] = h3(std::min(bmn[b].x, tmin[t].x), std::min(bmn[b].y, tmin[t].y), std::min(bmn[b].z, tmin[t].z));
-                    bmx[b] = h3(std::max(bmx[b].x, tmax[t].x), std::max(bmx[b].y, tmax[t].y), std::max(bmx[b].z, tmax[t].z));
-                }
-                float rightArea[NB]; uint32_t rightCount[NB];
-                H3 rmn = h3(1e30f, 1e30f, 1e30f), rmx = h3(-1e30f, -1e30f, -1e30f); uint32_t rc = 0;
-                for (int b = NB - 1; b > 0; --b) {
-                    rmn = h3(std::min(rmn.x, bmn[b].x), std::min(rmn.y, bmn[b].y), std::min(rmn.z, bmn[b].z));
-                    rmx = h3(std::max(rmx.x, bmx[b].x), std::max(rmx.y, bmx[b].y), std::max(rmx.z, bmx[b].z));
-                    rc += bc[b]; rightArea[b] = rc ? area(rmn, rmx) : 0.f; rightCount[b] = rc;
-                }
-                H3 lmn = h3(1e30f, 1e30f, 1e30f), lmx = h3(-1e30f, -1e30f, -1e30f); uint32_t lc = 0;
-                for (int b = 0; b < NB - 1; ++b) {
-                    lmn = h3(std::min(lmn.x, bmn[b].x), std::min(lmn.y, bmn[b].y), std::min(lmn.z, bmn[b].z));
-                    lmx = h3(std::max(lmx.x, bmx[b].x), std::max(lmx.y, bmx[b].y), std::max(lmx.z, bmx[b].z));
-                    lc += bc[b];
-                    if (lc == 0 || rightCount[b + 1] == 0) continue;
-                    const float cost = area(lmn, lmx) * lc + rightArea[b + 1] * rightCount[b + 1];
-                    if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestBin = b; }
+    auto binOf = [&](uint32_t t, int ax, float lo, float hi) { int b = (int) (NB * (hcomp(cen[t], ax) - lo) / (hi - lo)); return std::min(std::max(b, 0), NB - 1); };
+
+    std::vector<Node> arena(2 * (size_t) nt + 1);
+    std::atomic<uint32_t> arenaUsed{1};
+    std::atomic<int> deepest{0};
+    const uint32_t *order = out.order.data();
+
+    // one node: bounds, best binned split, partition of its range.  Returns true and the left count when the node was split.
+    auto process = [&](const Job &j, int loopThreads, uint32_t &nlOut) -> bool {
+        Bounds bd{big, small, big, small};
+        if (loopThreads > 1) {
+            std::vector<Bounds> part((size_t) loopThreads, Bounds{big, small, big, small});
+            parallel_for(j.count, loopThreads, 1 << 14, [&](size_t b, size_t e, int k) {
+                Bounds l{big, small, big, small};
+                for (size_t i = j.first + b; i < j.first + e; ++i) { const uint32_t t = order[i]; l.mn = hmin(l.mn, tmin[t]); l.mx = hmax(l.mx, tmax[t]); l.cmn = hmin(l.cmn, cen[t]); l.cmx = hmax(l.cmx, cen[t]); }
+                part[k] = l;
+            });
+            for (const Bounds &l : part) { bd.mn = hmin(bd.mn, l.mn); bd.mx = hmax(bd.mx, l.mx); bd.cmn = hmin(bd.cmn, l.cmn); bd.cmx = hmax(bd.cmx, l.cmx); }
+        } else
+            for (uint32_t i = j.first; i < j.first + j.count; ++i) { const uint32_t t = order[i]; bd.mn = hmin(bd.mn, tmin[t]); bd.mx = hmax(bd.mx, tmax[t]); bd.cmn = hmin(bd.cmn, cen[t]); bd.cmx = hmax(bd.cmx, cen[t]); }
+        Node nd; nd.mn = bd.mn; nd.mx = bd.mx; nd.left = j.first; nd.count = j.count;
+        arena[j.node] = nd;
+        if (j.count <= 1) return false;
+        // binned SAH over the three axes (one pass fills the bins of all axes with a centroid extent)
+        bool axisOk[3]; float lo[3], hi[3];
+        for (int ax = 0; ax < 3; ++ax) { lo[ax] = hcomp(bd.cmn, ax); hi[ax] = hcomp(bd.cmx, ax); axisOk[ax] = hi[ax] > lo[ax]; }
+        auto clearBins = [&](Bins &B) { for (int ax = 0; ax < 3; ++ax) if (axisOk[ax]) for (int b = 0; b < NB; ++b) { B.mn[ax][b] = big; B.mx[ax][b] = small; B.c[ax][b] = 0; } };
+        auto fillBins = [&](Bins &B, size_t b0, size_t e0) {
+            for (size_t i = j.first + b0; i < j.first + e0; ++i) {
+                const uint32_t t = order[i];
+                for (int ax = 0; ax < 3; ++ax) {
+                    if (!axisOk[ax]) continue;
+                    const int b = binOf(t, ax, lo[ax], hi[ax]);
+                    B.c[ax][b]++; B.mn[ax][b] = hmin(B.mn[ax][b], tmin[t]); B.mx[ax][b] = hmax(B.mx[ax][b], tmax[t]);
                 }
             }
-            // SAH with a traversal term: splitting pays when Ct * A + A_L N_L + A_R N_R < A * N (intersection cost 1)
-            static const float Ct = (float) bvh_env_int("PPG_BVH_CT_X10", 10) * 0.1f;
-            const float leafCost = area(mn, mx) * ((float) j.count - Ct);
-            if (bestAxis >= 0 && (j.count > (uint32_t) maxLeaf || bestCost < leafCost)) {
-                const float lo = hcomp(cmn, bestAxis), hi = hcomp(cmx, bestAxis);
-                auto mid = std::partition(out.order.begin() + j.first, out.order.begin() + j.first + j.count, [&](uint32_t t) {
-                    int b = (int) (NB * (hcomp(cen[t], bestAxis) - lo) / (hi - lo)); b = std::min(std::max(b, 0), NB - 1);
-                    return b <= bestBin;
-                });
-                const uint32_t nl = (uint32_t) (mid - (out.order.begin() + j.first));
-                if (nl > 0 && nl < j.count) {
-                    nd.left = (uint32_t) nodes.size(); nd.count = 0; nodes[j.node] = nd;
-                    nodes.push_back(Node()); nodes.push_back(Node());
-                    jobs.push_back(Job{nd.left, j.first, nl, j.depth + 1});
-                    jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl, j.depth + 1});
-                    continue;
-                }
-            }
-            if (j.count > (uint32_t) maxLeaf) {   // degenerate centroids: split in the middle
-                const uint32_t nl = j.count / 2;
-                nd.left = (uint32_t) nodes.size(); nd.count = 0; nodes[j.node] = nd;
-                nodes.push_back(Node()); nodes.push_back(Node());
-                jobs.push_back(Job{nd.left, j.first, nl, j.depth + 1});
-                jobs.push_back(Job{nd.left + 1, j.first + nl, j.count - nl, j.depth + 1});
-                continue;
+        };
+        Bins bins; clearBins(bins);
+        if (loopThreads > 1) {
+            std::vector<Bins> part((size_t) loopThreads);
+            for (Bins &B : part) clearBins(B);
+            parallel_for(j.count, loopThreads, 1 << 14, [&](size_t b, size_t e, int k) { fillBins(part[k], b, e); });
+            for (const Bins &B : part)
+                for (int ax = 0; ax < 3; ++ax) if (axisOk[ax]) for (int b = 0; b < NB; ++b) { bins.c[ax][b] += B.c[ax][b]; bins.mn[ax][b] = hmin(bins.mn[ax][b], B.mn[ax][b]); bins.mx[ax][b] = hmax(bins.mx[ax][b], B.mx[ax][b]); }
+        } else fillBins(bins, 0, j.count);
+        float bestCost = std::numeric_limits<float>::infinity(); int bestAxis = -1, bestBin = -1;
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!axisOk[ax]) continue;
+            const H3 *bmn = bins.mn[ax], *bmx = bins.mx[ax]; const uint32_t *bc = bins.c[ax];
+            float rightArea[NB]; uint32_t rightCount[NB];
+            H3 rmn = big, rmx = small; uint32_t rc = 0;
+            for (int b = NB - 1; b > 0; --b) { rmn = hmin(rmn, bmn[b]); rmx = hmax(rmx, bmx[b]); rc += bc[b]; rightArea[b] = rc ? area(rmn, rmx) : 0.f; rightCount[b] = rc; }
+            H3 lmn = big, lmx = small; uint32_t lc = 0;
+            for (int b = 0; b < NB - 1; ++b) {
+                lmn = hmin(lmn, bmn[b]); lmx = hmax(lmx, bmx[b]); lc += bc[b];
+                if (lc == 0 || rightCount[b + 1] == 0) continue;
+                const float cost = area(lmn, lmx) * lc + rightArea[b + 1] * rightCount[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestBin = b; }
             }
         }
-        nodes[j.node] = nd;
+        // SAH with a traversal term: splitting pays when Ct * A + A_L N_L + A_R N_R < A * N (intersection cost 1)
+        const float leafCost = area(bd.mn, bd.mx) * ((float) j.count - Ct);
+        if (bestAxis >= 0 && (j.count > (uint32_t) maxLeaf || bestCost < leafCost)) {
+            uint32_t *first = out.order.data() + j.first;
+            uint32_t *mid = std::partition(first, first + j.count, [&](uint32_t t) { return binOf(t, bestAxis, lo[bestAxis], hi[bestAxis]) <= bestBin; });
+            const uint32_t nl = (uint32_t) (mid - first);
+            if (nl > 0 && nl < j.count) { nlOut = nl; return true; }
+        }
+        if (j.count > (uint32_t) maxLeaf) { nlOut = j.count / 2; return true; }     // degenerate centroids: split in the middle
+        return false;
+    };
+    auto split = [&](const Job &j, uint32_t nl, Job &l, Job &r) {
+        const uint32_t c0 = arenaUsed.fetch_add(2u);
+        arena[j.node].left = c0; arena[j.node].count = 0;
+        l = Job{c0, j.first, nl, j.depth + 1}; r = Job{c0 + 1, j.first + nl, j.count - nl, j.depth + 1};
+    };
+    auto noteDepth = [&](int d) { int cur = deepest.load(std::memory_order_relaxed); while (d > cur && !deepest.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {} };
+
+    // phase 1: the big nodes, one at a time, loops spread over the threads; everything smaller is queued
+    const uint32_t bigCount = threads > 1 ? std::max<uint32_t>(1u << 16, nt / (4u * (uint32_t) threads)) : 0xFFFFFFFFu;
+    std::vector<Job> top, queued; top.push_back(Job{0, 0, nt, 0});
+    if (threads <= 1) { queued.swap(top); }
+    while (!top.empty()) {
+        const Job j = top.back(); top.pop_back();
+        if (j.count < bigCount) { queued.push_back(j); continue; }
+        noteDepth(j.depth);
+        uint32_t nl = 0;
+        if (process(j, threads, nl)) { Job l, r; split(j, nl, l, r); top.push_back(l); top.push_back(r); }
     }
-    out.nodes.resize(nodes.size() * 8);
-    for (size_t i = 0; i < nodes.size(); ++i) {
-        float *f = &out.nodes[8 * i];
-        f[0] = nodes[i].mn.x; f[1] = nodes[i].mn.y; f[2] = nodes[i].mn.z; memcpy(&f[3], &nodes[i].left, 4);
-        f[4] = nodes[i].mx.x; f[5] = nodes[i].mx.y; f[6] = nodes[i].mx.z; memcpy(&f[7], &nodes[i].count, 4);
+    // phase 2: the subtrees below, each by one thread, largest first
+    std::sort(queued.begin(), queued.end(), [](const Job &a, const Job &b) { return a.count > b.count; });
+    std::atomic<size_t> nextJob{0};
+    auto worker = [&] {
+        std::vector<Job> stack;
+        for (;;) {
+            const size_t q = nextJob.fetch_add(1);
+            if (q >= queued.size()) break;
+            stack.push_back(queued[q]);
+            int localDeepest = 0;
+            while (!stack.empty()) {
+                const Job j = stack.back(); stack.pop_back();
+                localDeepest = std::max(localDeepest, j.depth);
+                uint32_t nl = 0;
+                if (process(j, 1, nl)) { Job l, r; split(j, nl, l, r); stack.push_back(l); stack.push_back(r); }
+            }
+            noteDepth(localDeepest);
+        }
+    };
+    {
+        const int T = (int) std::min<size_t>((size_t) std::max(threads, 1), queued.size());
+        std::vector<std::thread> pool;
+        for (int k = 1; k < T; ++k) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
     }
+    out.maxDepth = deepest.load();
+    // phase 3: number the nodes as the depth-first stack of a serial build allocates them: a split node takes the next two indices when it is
+    // popped, its right child is popped before its left one
+    const uint32_t nNodes = arenaUsed.load();
+    out.nodes.resize((size_t) nNodes * 8);
+    struct Visit { uint32_t finalIndex, arenaIndex; };
+    std::vector<Visit> st; st.push_back(Visit{0, 0});
+    uint32_t finalUsed = 1;
+    while (!st.empty()) {
+        const Visit v = st.back(); st.pop_back();
+        const Node &nd = arena[v.arenaIndex];
+        uint32_t left = nd.left;
+        if (nd.count == 0) { left = finalUsed; finalUsed += 2; st.push_back(Visit{left, nd.left}); st.push_back(Visit{left + 1, nd.left + 1}); }
+        float *f = &out.nodes[8 * (size_t) v.finalIndex];
+        f[0] = nd.mn.x; f[1] = nd.mn.y; f[2] = nd.mn.z; memcpy(&f[3], &left, 4);
+        f[4] = nd.mx.x; f[5] = nd.mx.y; f[6] = nd.mx.z; memcpy(&f[7], &nd.count, 4);
+    }
+}
+static void triangle_bounds(const float *positions, const uint32_t *indices, uint32_t nt, std::vector<H3> &tmin, std::vector<H3> &tmax, int threads) {
+    auto P = [&](uint32_t i) { return h3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]); };
+    parallel_for(nt, threads, 1 << 15, [&](size_t b0, size_t e0, int) {
+        for (size_t t = b0; t < e0; ++t) {
+            const H3 a = P(indices[3 * t]), b = P(indices[3 * t + 1]), c = P(indices[3 * t + 2]);
+            tmin[t] = h3(std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z)));
+            tmax[t] = h3(std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)));
+        }
+    });
 }
 }  // namespace
 
@@ -636,12 +743,8 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     if (haveEnv && !s->envmap.texels) return fail(PPG_ERR_INVALID_ARGUMENT, "envmap without texel data");
     auto P = [&](uint32_t i) { return h3(s->positions[3 * i], s->positions[3 * i + 1], s->positions[3 * i + 2]); };
     std::vector<H3> tmin(nt), tmax(nt);
-    for (uint32_t t = 0; t < nt; ++t) {
-        const H3 a = P(s->indices[3 * t]), b = P(s->indices[3 * t + 1]), c = P(s->indices[3 * t + 2]);
-        tmin[t] = h3(std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z)));
-        tmax[t] = h3(std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z)));
-    }
-    HostBvh bvh; build_bvh(tmin, tmax, bvh);
+    triangle_bounds(s->positions, s->indices, nt, tmin, tmax, host_threads());
+    HostBvh bvh; build_bvh(tmin, tmax, bvh, host_threads());
     if (bvh.maxDepth >= PPG_BVH_STACK) return fail(PPG_ERR_UNSUPPORTED, "BVH deeper than the device traversal stack");
     // brute-force layout for tiny scenes: coplanar groups ordered by projection axis (see bvh_intersect)
     uint32_t kBegin[4] = {0, 0, 0, 0};
@@ -687,7 +790,8 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     const bool bruteForce = !groups.empty();
     if (groups.empty()) groups.assign(8, 0.f);
     std::vector<float> accel(12 * (size_t) nt), geom(24 * (size_t) nt); std::vector<int32_t> meta(4 * (size_t) nt);
-    for (uint32_t slot = 0; slot < nt; ++slot) {
+    parallel_for(nt, host_threads(), 1 << 14, [&](size_t slot0, size_t slot1, int) {
+    for (uint32_t slot = (uint32_t) slot0; slot < (uint32_t) slot1; ++slot) {
         const uint32_t t = bvh.order[slot];
         const uint32_t i0 = s->indices[3 * t], i1 = s->indices[3 * t + 1], i2 = s->indices[3 * t + 2];
         float w[9]; int k; wald_constants(P(i0), P(i1), P(i2), w, k);
@@ -708,6 +812,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
         meta[4 * (size_t) slot] = sh.bsdf; meta[4 * (size_t) slot + 1] = sh.emitter;
         meta[4 * (size_t) slot + 2] = ((sh.has_normals && s->normals) ? 1 : 0) | ((sh.has_uvs && s->uvs) ? 2 : 0); meta[4 * (size_t) slot + 3] = (int32_t) s->triangle_shape[t];
     }
+    });
     h->fullFeature = false;
     for (uint32_t i = 0; i < s->n_bsdfs; ++i) if ((s->bsdfs[i].type != PPG_BSDF_DIFFUSE && s->bsdfs[i].type != PPG_BSDF_NULL_BLACK) || (s->bsdfs[i].flags & ~PPG_BSDF_FLAG_TWOSIDED)) h->fullFeature = true;   // any non-diffuse model or wrapper other than twosided
     if (s->n_spheres) h->fullFeature = true;                                            // ... or analytic spheres: the full-feature kernel variants
@@ -825,10 +930,12 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     }
     {   // bitmap textures and the environment map: half texels repacked to one uint2 {r | g << 16, b} per texel
         auto pack = [](const uint16_t *src, size_t nTexels, uint32_t channels, uint2 *dst) {
-            for (size_t i = 0; i < nTexels; ++i) {
-                const uint16_t r = src[i * channels], g = channels == 3 ? src[i * channels + 1] : r, b = channels == 3 ? src[i * channels + 2] : r;
-                dst[i] = make_uint2((uint32_t) r | ((uint32_t) g << 16), (uint32_t) b);
-            }
+            parallel_for(nTexels, host_threads(), 1 << 18, [&](size_t i0, size_t i1, int) {
+                for (size_t i = i0; i < i1; ++i) {
+                    const uint16_t r = src[i * channels], g = channels == 3 ? src[i * channels + 1] : r, b = channels == 3 ? src[i * channels + 2] : r;
+                    dst[i] = make_uint2((uint32_t) r | ((uint32_t) g << 16), (uint32_t) b);
+                }
+            });
         };
         size_t total = 0;
         for (uint32_t i = 0; i < s->n_textures; ++i) total += (size_t) s->textures[i].width * s->textures[i].height;
@@ -1786,6 +1893,23 @@ extern "C" int ppg_op_dtree_record(int device, float *sums_inout, const uint16_t
     CK(cudaGetLastError());
     CK(cudaMemcpy(sums_inout, dsums.b.p, 16 * n_nodes, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(tree_weight_inout, dwt.b.p, 4 * n_trees, cudaMemcpyDeviceToHost));
+    return PPG_OK;
+}
+// The acceleration structure ppg_set_scene builds, on the host alone (no CUDA device needed): for tests of the builder and for timing it.
+extern "C" int ppg_op_bvh_build(const float *positions, const uint32_t *indices, size_t n_triangles, int threads, float *nodes_out, size_t nodes_capacity,
+                                uint32_t *order_out, size_t *n_nodes_out, int *max_depth_out, double *ms_out) {
+    if (!positions || !indices || !n_triangles || n_triangles >= 0xFFFFFFFFull) return fail(PPG_ERR_INVALID_ARGUMENT, "ppg_op_bvh_build: empty or oversized input");
+    const uint32_t nt = (uint32_t) n_triangles;
+    const auto t0 = std::chrono::steady_clock::now();
+    const int T = threads > 0 ? threads : host_threads();
+    std::vector<H3> tmin(nt), tmax(nt);
+    triangle_bounds(positions, indices, nt, tmin, tmax, T);
+    HostBvh bvh; build_bvh(tmin, tmax, bvh, T);
+    if (ms_out) *ms_out = elapsed_ms(t0);
+    if (n_nodes_out) *n_nodes_out = bvh.nodes.size() / 8;
+    if (max_depth_out) *max_depth_out = bvh.maxDepth;
+    if (nodes_out) { if (nodes_capacity < bvh.nodes.size() / 8) return fail(PPG_ERR_INVALID_ARGUMENT, "ppg_op_bvh_build: nodes_out too small (2 * n_triangles + 1 always suffices)"); memcpy(nodes_out, bvh.nodes.data(), bvh.nodes.size() * 4); }
+    if (order_out) memcpy(order_out, bvh.order.data(), (size_t) nt * 4);
     return PPG_OK;
 }
 extern "C" int ppg_op_emitter_sample_direct(ppg_integrator *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,

@@ -229,6 +229,17 @@ def op_dtree_record(sums, children, tree_first, tree_weight, rec_tree, rec_dir, 
     return sums, tw
 
 
+def op_bvh_build(positions, indices, threads=0):
+    """The BVH ppg_set_scene builds, on the host (no device): (nodes (N,8) float32, order (T,) uint32, max depth, milliseconds)."""
+    lib = capi.load_library()
+    pos = np.ascontiguousarray(positions, np.float32); idx = np.ascontiguousarray(indices, np.uint32)
+    nt = len(idx); nodes = np.zeros((2 * nt + 1, 8), np.float32); order = np.zeros(nt, np.uint32)
+    n = C.c_size_t(); depth = C.c_int(); ms = C.c_double()
+    _check(lib, lib.ppg_op_bvh_build(_p(pos, C.c_float), _p(idx, C.c_uint32), nt, threads, _p(nodes, C.c_float), len(nodes), _p(order, C.c_uint32),
+                                     C.byref(n), C.byref(depth), C.byref(ms)))
+    return nodes[:n.value], order, depth.value, ms.value
+
+
 def op_stree_lookup(node_children, aabb_min, aabb_extent, points, device=0):
     lib = capi.load_library()
     nc = np.ascontiguousarray(node_children, np.uint32); pts = np.ascontiguousarray(points, np.float32)

@@ -272,3 +272,36 @@ def test_flat_scene_file_round_trip(tmp_path):
     assert dict(l.split("=", 1) for l in props.value.decode().splitlines()) == sc.integrator
     lib.ppg_scene_file_free(fh)
     assert lib.ppg_scene_file_load(str(tmp_path / "missing").encode(), C.byref(d), C.byref(fh), None) == -7      # PPG_ERR_IO
+
+
+def test_bvh_build_is_valid_and_independent_of_the_thread_count():
+    """ppg_op_bvh_build (host only): the binned-SAH BVH ppg_set_scene builds over SPACESHIP's 457 560 triangles.  Every triangle sits in exactly one
+    leaf, leaves hold at most 4 triangles, children lie inside their parents, the boxes are tight -- and the arrays are byte-identical for 1, 3 and 8
+    host threads and equal to the layout of the serial builder the GPU parity runs of round 2 were made with (pinned by hash), so parallelising the
+    host set-up cannot move a single hit."""
+    import hashlib
+    from ppg_b200.integrator import op_bvh_build
+    from ppg_b200.scene import SceneDesc
+    sc = SceneDesc.load(os.path.join(ROOT, "scenes", "spaceship-improved.npz"))
+    nodes, order, depth, ms = op_bvh_build(sc.positions, sc.indices, 1)
+    for threads in (3, 8):
+        n2, o2, d2, _ = op_bvh_build(sc.positions, sc.indices, threads)
+        assert d2 == depth and n2.tobytes() == nodes.tobytes() and o2.tobytes() == order.tobytes()
+    assert hashlib.sha256(nodes.tobytes() + order.tobytes()).hexdigest().startswith("e459259d0c4e618a")
+    assert (len(nodes), depth) == (454573, 29) and depth < 64                       # PPG_BVH_STACK
+    assert np.array_equal(np.sort(order), np.arange(len(sc.indices), dtype=np.uint32))
+    left = nodes[:, 3].copy().view(np.uint32); count = nodes[:, 7].copy().view(np.uint32)
+    inner = count == 0
+    assert count[~inner].max() <= 4 and count[~inner].sum() == len(sc.indices)
+    # children inside the parent; every node but the root is the child of exactly one inner node
+    kids = np.concatenate([left[inner], left[inner] + 1]); par = np.concatenate([np.nonzero(inner)[0]] * 2)
+    assert np.array_equal(np.sort(kids), np.arange(1, len(nodes)))
+    assert (nodes[kids, 0:3] >= nodes[par, 0:3]).all() and (nodes[kids, 4:7] <= nodes[par, 4:7]).all()
+    # leaf boxes are the bounds of their triangles
+    tri = sc.positions[sc.indices]                                                   # (T, 3, 3)
+    tmin, tmax = tri.min(axis=1), tri.max(axis=1)
+    leaves = np.nonzero(~inner)[0][:20000]
+    for i in leaves[::97]:
+        t = order[left[i]:left[i] + count[i]]
+        assert np.array_equal(nodes[i, 0:3], tmin[t].min(axis=0)) and np.array_equal(nodes[i, 4:7], tmax[t].max(axis=0))
+    assert np.array_equal(nodes[0, 0:3], tmin.min(axis=0)) and np.array_equal(nodes[0, 4:7], tmax.max(axis=0))
