@@ -702,6 +702,7 @@ extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
     if (!h || !s) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
     if (!s->n_triangles || !s->positions || !s->indices || !s->triangle_shape || !s->shapes || !s->bsdfs)
         return fail(PPG_ERR_INVALID_ARGUMENT, "scene needs triangles, shapes and bsdfs");
+    if ((s->n_emitters && !s->area_radiance) || (s->n_spheres && !s->spheres)) return fail(PPG_ERR_INVALID_ARGUMENT, "emitter / sphere count without its array");
     if (s->camera.film_width <= 0 || s->camera.film_height <= 0 || s->camera.film_width > 65535 || s->camera.film_height > 65535)
         return fail(PPG_ERR_INVALID_ARGUMENT, "film size out of range");
     CK(cudaSetDevice(h->device));
