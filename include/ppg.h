@@ -130,7 +130,7 @@ typedef enum ppg_microfacet { PPG_MICROFACET_BECKMANN = 0, PPG_MICROFACET_GGX = 
 #define PPG_BSDF_FLAG_MASK 4u     /* src/bsdfs/mask.cpp:113-220 wrapping the (possibly twosided) model: constant `opacity`; a smooth/null hybrid */
 #define PPG_BSDF_FLAG_BUMPMAP 8u  /* src/bsdfs/bumpmap.cpp:161-238 wrapping everything above: the shading frame is perturbed by the gradient of the
                                      displacement texture `bump_texture` (Frame getFrame(its), :139-159) */
-#define PPG_BSDF_TABLE_SIZE 100   /* theta samples of the rough-transmittance tables (data/microfacet/*.dat) */
+#define PPG_BSDF_TABLE_SIZE 100   /* theta samples of the rough-transmittance tables (the .dat files of data/microfacet) */
 
 typedef struct ppg_bsdf {
     int32_t  type;            /* ppg_bsdf_type */

@@ -86,3 +86,25 @@ def test_area_and_environment_lights_with_light_sampling_match_oracle():
     img, st = _gpu(props, sc).render()
     ref, ost = O.Oracle(O.params_from_xml(props), sc, kind="port").render()
     assert_render_parity(img, ref, st, ost, sc, props)
+
+
+def test_plain_c_host_renders_like_the_python_host(tmp_path):
+    """integration/ppg_render_cli.c (C99 over include/ppg.h, no Python at run time): flat scene file -> ppg_set_scene -> ppg_render -> PFM, the same
+    film the ctypes host gets for the same scene, parameters and seed."""
+    import os
+    import subprocess
+    from common import ROOT, load_cbox
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "integration")], capture_output=True).returncode == 0
+    sc = load_cbox(64)
+    scene = str(tmp_path / "cbox.ppgscene"); out = str(tmp_path / "out.pfm")
+    sc.save_flat(scene)
+    r = subprocess.run([os.path.join(ROOT, "integration", "ppg_render_cli"), scene, out, "-D", "budget=28", "-D", "budgetType=spp", "--sdt", str(tmp_path / "tree.sdt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "ITERATION 2 (FINAL)" in r.stderr, r.stderr
+    with open(out, "rb") as f:
+        assert f.readline() == b"PF\n" and f.readline() == b"64 64\n" and f.readline() == b"-1.0\n"
+        img = np.frombuffer(f.read(), "<f4").reshape(64, 64, 3)[::-1]
+    ref, st = _gpu(dict(sc.integrator, budget="28", budgetType="spp"), sc).render()
+    assert np.isfinite(img).all() and np.isclose(img, ref, rtol=1e-3, atol=1e-5).all(axis=2).mean() >= 0.9
+    assert abs(float(img.mean()) - float(ref.mean())) <= 0.01 * float(ref.mean())
+    assert os.path.getsize(tmp_path / "tree.sdt") > 64

@@ -305,3 +305,30 @@ def test_bvh_build_is_valid_and_independent_of_the_thread_count():
         t = order[left[i]:left[i] + count[i]]
         assert np.array_equal(nodes[i, 0:3], tmin[t].min(axis=0)) and np.array_equal(nodes[i, 4:7], tmax[t].max(axis=0))
     assert np.array_equal(nodes[0, 0:3], tmin.min(axis=0)) and np.array_equal(nodes[0, 4:7], tmax.max(axis=0))
+
+
+def test_plain_c_host_builds_and_fails_loudly_without_a_device(tmp_path):
+    """integration/ppg_render_cli.c: a C99 host over include/ppg.h alone (-Wall -Wextra -pedantic clean).  Without a CUDA device it loads a flat scene
+    file, applies the XML's integrator block and -D overrides through ppg_params_set (the plugin constructor's validation and messages), and then fails
+    with PPG_ERR_NO_DEVICE -- no CPU fallback behind the C ABI either."""
+    import subprocess
+    from ppg_b200.scene import SceneDesc
+    mk = subprocess.run(["make", "-C", os.path.join(ROOT, "integration")], capture_output=True, text=True)
+    assert mk.returncode == 0 and "warning" not in (mk.stdout + mk.stderr).lower(), mk.stdout + mk.stderr
+    cli = os.path.join(ROOT, "integration", "ppg_render_cli")
+    scene = str(tmp_path / "cbox.ppgscene")
+    SceneDesc.load(os.path.join(ROOT, "scenes", "cbox-improved.npz")).with_film(48, 32).save_flat(scene)
+    r = subprocess.run([cli, scene, "--check", "-D", "budget=28", "-D", "nee=kickstart"], capture_output=True, text=True)
+    assert r.returncode == 0 and "36 triangles" in r.stderr and "film 48 x 32" in r.stderr and "check ok" in r.stderr, r.stderr
+    r = subprocess.run([cli, scene, "--check", "-D", "spatialFilter=gaussian"], capture_output=True, text=True)
+    assert r.returncode == 1 and "spatialFilter" in r.stderr                           # PPG_ERR_INVALID_ARGUMENT, the reference Assert(false)s (GP:1045)
+    r = subprocess.run([cli, str(tmp_path / "missing.ppgscene"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 7                                                            # PPG_ERR_IO
+    import ctypes
+    try:
+        ctypes.CDLL("libcuda.so.1"); have_driver = True
+    except OSError:
+        have_driver = False
+    if not have_driver or not __import__("common").gpu_available():
+        r = subprocess.run([cli, scene, str(tmp_path / "out.pfm")], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr and not os.path.exists(tmp_path / "out.pfm"), r.stderr
