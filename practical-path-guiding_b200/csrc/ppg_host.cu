@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -138,7 +139,10 @@ extern "C" int ppg_scene_file_load(const char *path, ppg_scene_desc *d, ppg_scen
     if (!f) return fail(PPG_ERR_IO, std::string("cannot open ") + path);
     char magic[8];
     if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "PPGSCN02", 8) != 0) { fclose(f); return fail(PPG_ERR_IO, "not a PPGSCN02 scene file"); }
-    ppg_scene_file *sf = new ppg_scene_file();
+    long fileBytes = 0;                                   // no array can be larger than the file: a corrupt header must not turn into a huge allocation
+    if (fseek(f, 0, SEEK_END) != 0 || (fileBytes = ftell(f)) < 8 || fseek(f, 8, SEEK_SET) != 0) { fclose(f); return fail(PPG_ERR_IO, "cannot size the scene file"); }
+    ppg_scene_file *sf = new (std::nothrow) ppg_scene_file();
+    if (!sf) { fclose(f); return fail(PPG_ERR_IO, "out of memory"); }
     memset(d, 0, sizeof(*d));
     struct Arr { const char *p; size_t bytes; uint64_t dims[4]; uint32_t ndim; };
     auto fail_io = [&](const char *m) { fclose(f); delete sf; return fail(PPG_ERR_IO, m); };
@@ -151,9 +155,14 @@ extern "C" int ppg_scene_file_load(const char *path, ppg_scene_desc *d, ppg_scen
         std::string name(nl, 0); uint32_t hdr[2];
         if (fread(&name[0], 1, nl, f) != nl || fread(hdr, 4, 2, f) != 2 || hdr[0] > 5 || hdr[1] > 4) return fail_io("corrupt scene file (header)");
         Arr a; a.ndim = hdr[1]; size_t count = 1;
-        for (uint32_t k = 0; k < a.ndim; ++k) { if (fread(&a.dims[k], 8, 1, f) != 1) return fail_io("corrupt scene file (dims)"); count *= (size_t) a.dims[k]; }
+        for (uint32_t k = 0; k < a.ndim; ++k) {
+            if (fread(&a.dims[k], 8, 1, f) != 1) return fail_io("corrupt scene file (dims)");
+            if (a.dims[k] > (uint64_t) fileBytes || (a.dims[k] && count > (size_t) fileBytes / (size_t) a.dims[k])) return fail_io("corrupt scene file (array larger than the file)");
+            count *= (size_t) a.dims[k];
+        }
         a.bytes = count * esz[hdr[0]];
-        sf->blobs.emplace_back(a.bytes + 8);
+        if (a.bytes > (size_t) fileBytes) return fail_io("corrupt scene file (array larger than the file)");
+        try { sf->blobs.emplace_back(a.bytes + 8); } catch (const std::bad_alloc &) { return fail_io("out of memory"); }
         if (a.bytes && fread(sf->blobs.back().data(), 1, a.bytes, f) != a.bytes) return fail_io("truncated scene file");
         a.p = sf->blobs.back().data();
         arrs.emplace_back(name, a);
@@ -165,6 +174,11 @@ extern "C" int ppg_scene_file_load(const char *path, ppg_scene_desc *d, ppg_scen
               *TX = get("textures"), *TL = get("texels"), *ET = get("env_texels"), *EM = get("env_meta"), *IP = get("integrator");
     if (!P || !N || !UV || !I || !TS || !SH || !B || !R || !CW || !CAM || !BB || CW->bytes != 64 || CAM->bytes != 40 || BB->bytes != 24 || B->bytes % sizeof(ppg_bsdf) || SH->bytes % sizeof(ppg_shape))
         { delete sf; return fail(PPG_ERR_IO, "scene file lacks a required array"); }
+    // per-vertex / per-triangle arrays must cover what the counts promise (ppg_set_scene indexes them without further checks)
+    if (P->bytes % 12 || I->bytes % 12 || R->bytes % 12 || N->bytes != P->bytes || UV->bytes != P->bytes / 12 * 8 || TS->bytes != I->bytes / 12 * 4 ||
+        (T && T->bytes % (4 * PPG_BSDF_TABLE_SIZE)) || (SP && SP->bytes % sizeof(ppg_sphere)) || (TX && TX->bytes % sizeof(ppg_texture)) ||
+        (ET && ET->bytes && (ET->ndim != 3 || ET->dims[2] != 3 || ET->bytes != ET->dims[0] * ET->dims[1] * 6)))
+        { delete sf; return fail(PPG_ERR_IO, "scene file: array sizes do not match each other"); }
     d->n_vertices = (uint32_t) (P->bytes / 12); d->n_triangles = (uint32_t) (I->bytes / 12); d->n_shapes = (uint32_t) (SH->bytes / sizeof(ppg_shape));
     d->n_bsdfs = (uint32_t) (B->bytes / sizeof(ppg_bsdf)); d->n_emitters = (uint32_t) (R->bytes / 12);
     d->positions = (const float *) P->p; d->normals = (const float *) N->p; d->uvs = (const float *) UV->p; d->indices = (const uint32_t *) I->p;

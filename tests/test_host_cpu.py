@@ -332,3 +332,40 @@ def test_plain_c_host_builds_and_fails_loudly_without_a_device(tmp_path):
     if not have_driver or not __import__("common").gpu_available():
         r = subprocess.run([cli, scene, str(tmp_path / "out.pfm")], capture_output=True, text=True)
         assert r.returncode == 2 and "no CPU fallback" in r.stderr and not os.path.exists(tmp_path / "out.pfm"), r.stderr
+
+
+def test_corrupt_scene_files_are_rejected_not_trusted(tmp_path):
+    """ppg_scene_file_load on damaged input: truncated anywhere, dimension fields overwritten with huge or inconsistent values, arrays whose sizes do not
+    match each other -- always PPG_ERR_IO with a message, never a crash, an unbounded allocation or a description that would make ppg_set_scene read out of bounds."""
+    from common import load_fixture_scene
+    sc = load_fixture_scene("cbox-textured")
+    good = str(tmp_path / "good.ppgscene"); sc.save_flat(good)
+    raw = open(good, "rb").read()
+    lib = capi.load_library()
+
+    def load(data):
+        p = str(tmp_path / "t.ppgscene"); open(p, "wb").write(data)
+        d = capi.PpgSceneDesc(); fh = C.c_void_p()
+        rc = lib.ppg_scene_file_load(p.encode(), C.byref(d), C.byref(fh), None)
+        if rc == 0:
+            lib.ppg_scene_file_free(fh)
+        return rc
+
+    assert load(raw) == 0
+    rng = np.random.default_rng(5)
+    for cut in [0, 4, 8, 9, 20] + list(rng.integers(21, len(raw) - 1, 40)):
+        assert load(raw[:int(cut)]) == -7, cut                                      # (a cut exactly between two arrays drops required arrays: also an error)
+    # the first array is "positions": [u32 6]["positi..."][u32 dtype][u32 ndim][u64 dim0][u64 dim1]: blow up its first dimension
+    off = 8 + 4 + len("positions") + 8
+    assert raw[12:21] == b"positions"
+    for dim in (2 ** 62, 2 ** 40, len(raw), sc.positions.shape[0] - 1, sc.positions.shape[0] + 1):
+        bad = bytearray(raw); bad[off:off + 8] = int(dim).to_bytes(8, "little")
+        assert load(bytes(bad)) == -7, dim
+    assert b"array" in lib.ppg_last_error() or b"corrupt" in lib.ppg_last_error() or b"truncated" in lib.ppg_last_error() or b"lacks" in lib.ppg_last_error()
+    bad = bytearray(raw); bad[:8] = b"PPGSCN01"
+    assert load(bytes(bad)) == -7
+    # a file whose normals array is shorter than its positions (consistent in itself, inconsistent as a scene)
+    import copy
+    sc2 = copy.copy(sc); sc2.normals = sc.normals[:-1]
+    p2 = str(tmp_path / "short_normals.ppgscene"); sc2.save_flat(p2)
+    assert load(open(p2, "rb").read()) == -7 and b"do not match" in lib.ppg_last_error()
