@@ -16,6 +16,7 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 #ifdef __linux__
@@ -27,6 +28,12 @@ using namespace ppg;
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_lastError;
 static int fail(int code, const std::string &msg) { g_lastError = msg; return code; }
+// "no exceptions cross this boundary" (ppg.h): the entry points that allocate host memory in proportion to their input run under this guard
+template <class F> static int guarded(const char *what, F body) {
+    try { return body(); }
+    catch (const std::bad_alloc &) { return fail(PPG_ERR_INVALID_ARGUMENT, std::string(what) + ": out of host memory"); }
+    catch (const std::exception &e) { return fail(PPG_ERR_INVALID_ARGUMENT, std::string(what) + ": " + e.what()); }
+}
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -259,8 +266,13 @@ template <class F> static void parallel_for(size_t n, int threads, size_t minChu
     const int T = (int) std::max<size_t>(1, std::min<size_t>((size_t) threads, n / std::max<size_t>(minChunk, 1)));
     if (T <= 1) { fn((size_t) 0, n, 0); return; }
     std::vector<std::thread> pool; pool.reserve(T - 1);
-    for (int k = 1; k < T; ++k) pool.emplace_back([&, k] { fn(n * k / T, n * (k + 1) / T, k); });
+    int started = 1;
+    for (int k = 1; k < T; ++k) {
+        try { pool.emplace_back([&, k] { fn(n * k / T, n * (k + 1) / T, k); }); ++started; }
+        catch (const std::system_error &) { break; }                 // no more threads to be had: the remaining chunks run here
+    }
     fn((size_t) 0, n / T, 0);
+    for (int k = started; k < T; ++k) fn(n * k / T, n * (k + 1) / T, k);
     for (auto &th : pool) th.join();
 }
 
@@ -404,7 +416,7 @@ static void build_bvh(const std::vector<H3> &tminV, const std::vector<H3> &tmaxV
     {
         const int T = (int) std::min<size_t>((size_t) std::max(threads, 1), queued.size());
         std::vector<std::thread> pool;
-        for (int k = 1; k < T; ++k) pool.emplace_back(worker);
+        for (int k = 1; k < T; ++k) { try { pool.emplace_back(worker); } catch (const std::system_error &) { break; } }   // the queue is dynamic: fewer threads, same result
         worker();
         for (auto &th : pool) th.join();
     }
@@ -712,7 +724,9 @@ extern "C" int ppg_set_shard(ppg_integrator *h, int rank, int world_size) {
     return PPG_OK;
 }
 
-extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) {
+static int ppg_set_scene_impl(ppg_integrator *h, const ppg_scene_desc *s);
+extern "C" int ppg_set_scene(ppg_integrator *h, const ppg_scene_desc *s) { return guarded("ppg_set_scene", [&] { return ppg_set_scene_impl(h, s); }); }
+static int ppg_set_scene_impl(ppg_integrator *h, const ppg_scene_desc *s) {
     if (!h || !s) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
     if (!s->n_triangles || !s->positions || !s->indices || !s->triangle_shape || !s->shapes || !s->bsdfs)
         return fail(PPG_ERR_INVALID_ARGUMENT, "scene needs triangles, shapes and bsdfs");
@@ -1647,7 +1661,9 @@ static int render_time(ppg_integrator *h) {
 }
 
 // render, GP:1516-1585
-extern "C" int ppg_render_device(ppg_integrator *h, float **rgb_dev, ppg_stats *stats) {
+static int ppg_render_device_impl(ppg_integrator *h, float **rgb_dev, ppg_stats *stats);
+extern "C" int ppg_render_device(ppg_integrator *h, float **rgb_dev, ppg_stats *stats) { return guarded("ppg_render_device", [&] { return ppg_render_device_impl(h, rgb_dev, stats); }); }
+static int ppg_render_device_impl(ppg_integrator *h, float **rgb_dev, ppg_stats *stats) {
     if (!h) return fail(PPG_ERR_INVALID_ARGUMENT, "null handle");
     if (!h->haveScene) return fail(PPG_ERR_NO_SCENE, "ppg_render called before ppg_set_scene");
     CK(cudaSetDevice(h->device));
@@ -1724,7 +1740,9 @@ extern "C" int ppg_get_moment_images(ppg_integrator *h, float *sum_rgbw, float *
 // dumpSDTree wire format (GP:1191-1208, 699-711, 945-951): 16 floats camera matrix, then for every leaf with
 // sampling weight > 0, in forEachLeaf order (child 0 before child 1): pos, size, mean, u64 weight, u64 nNodes,
 // nNodes x 4 x (f32 sum, u16 child)
-extern "C" int ppg_dump_sdtree(ppg_integrator *h, const char *path) {
+static int ppg_dump_sdtree_impl(ppg_integrator *h, const char *path);
+extern "C" int ppg_dump_sdtree(ppg_integrator *h, const char *path) { return guarded("ppg_dump_sdtree", [&] { return ppg_dump_sdtree_impl(h, path); }); }
+static int ppg_dump_sdtree_impl(ppg_integrator *h, const char *path) {
     if (!h || !path) return fail(PPG_ERR_INVALID_ARGUMENT, "null argument");
     if (!h->haveScene || h->capNodes == 0) return fail(PPG_ERR_NO_SCENE, "no SD-tree yet");
     CK(cudaSetDevice(h->device));
@@ -1913,6 +1931,7 @@ extern "C" int ppg_op_dtree_record(int device, float *sums_inout, const uint16_t
 // The acceleration structure ppg_set_scene builds, on the host alone (no CUDA device needed): for tests of the builder and for timing it.
 extern "C" int ppg_op_bvh_build(const float *positions, const uint32_t *indices, size_t n_triangles, int threads, float *nodes_out, size_t nodes_capacity,
                                 uint32_t *order_out, size_t *n_nodes_out, int *max_depth_out, double *ms_out) {
+  return guarded("ppg_op_bvh_build", [&]() -> int {
     if (!positions || !indices || !n_triangles || n_triangles >= 0xFFFFFFFFull) return fail(PPG_ERR_INVALID_ARGUMENT, "ppg_op_bvh_build: empty or oversized input");
     const uint32_t nt = (uint32_t) n_triangles;
     const auto t0 = std::chrono::steady_clock::now();
@@ -1926,6 +1945,7 @@ extern "C" int ppg_op_bvh_build(const float *positions, const uint32_t *indices,
     if (nodes_out) { if (nodes_capacity < bvh.nodes.size() / 8) return fail(PPG_ERR_INVALID_ARGUMENT, "ppg_op_bvh_build: nodes_out too small (2 * n_triangles + 1 always suffices)"); memcpy(nodes_out, bvh.nodes.data(), bvh.nodes.size() * 4); }
     if (order_out) memcpy(order_out, bvh.order.data(), (size_t) nt * 4);
     return PPG_OK;
+  });
 }
 extern "C" int ppg_op_emitter_sample_direct(ppg_integrator *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,
                                             float *d_out, float *value_out, float *pdf_out, float *dist_out) {
