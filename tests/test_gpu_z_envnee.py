@@ -107,4 +107,4 @@ def test_plain_c_host_renders_like_the_python_host(tmp_path):
     ref, st = _gpu(dict(sc.integrator, budget="28", budgetType="spp"), sc).render()
     assert np.isfinite(img).all() and np.isclose(img, ref, rtol=1e-3, atol=1e-5).all(axis=2).mean() >= 0.9
     assert abs(float(img.mean()) - float(ref.mean())) <= 0.01 * float(ref.mean())
-    assert os.path.getsize(tmp_path / "tree.sdt") > 64
+    assert os.path.getsize(tmp_path / "tree.sdt") >= 64          # the camera matrix; nothing is recorded in the final iteration, so the tree built after it is empty (GP:2150)
