@@ -15,6 +15,9 @@ Reference behaviour followed (paths under /root/reference/mitsuba):
   * OBJ: n-gons are fanned (src/shapes/obj.cpp:313-324), vertices merged per
     (p, n, uv) key, missing normals replaced by angle-weighted smooth normals
     (src/librender/trimesh.cpp:608-690) unless ``faceNormals``.
+  * other mesh sources: ``ply`` (src/shapes/ply.cpp: ascii / binary, triangles and quads), ``serialized``
+    (TriMesh::loadCompressed, src/librender/trimesh.cpp:176-335: zlib stream, versions 3 / 4, ``shapeIndex``),
+    ``cube`` (src/shapes/cube.cpp) and ``rectangle`` as two triangles; ``sphere`` stays analytic.
   * perspective sensor: fovAxis resolution (src/librender/sensor.cpp:239-300).
   * scene AABB = geometry AABB + sensor position + emitter AABBs
     (src/librender/scene.cpp:387-413).
@@ -28,7 +31,7 @@ Reference behaviour followed (paths under /root/reference/mitsuba):
     registered on their own like any named object (scenehandler.cpp), so a
     ``<ref>`` to the inner id of kitchen.xml's bump-mapped cushions gets the
     un-bumped material, exactly as in the reference.
-  * ``sunsky`` is baked to a lat-long environment map (ppg_b200/sunsky.py);
+  * ``sunsky`` (and its halves ``sky`` / ``sun``) is baked to a lat-long environment map (ppg_b200/sunsky.py);
     environment emitters do not change the scene AABB (envmap.cpp:558-564).
 """
 from __future__ import annotations
@@ -371,6 +374,174 @@ def _load_obj(path, to_world, face_normals=False, flip_normals=False):
         N = _smooth_normals(P, I)
         if flip_normals: N = -N
     return P, N, (UV if has_uv else None), I
+
+
+def _finish_mesh(P, N, UV, I, to_world, face_normals, flip_normals):
+    """Object-space arrays of a mesh file -> world space, with the conventions of _load_obj: positions by toWorld, normals by its inverse transpose
+    (normalised), `faceNormals` drops vertex normals (flipNormals then swaps the winding), meshes without normals get angle-weighted ones (TriMesh::configure)."""
+    M = np.asarray(to_world, np.float64)
+    P = (np.asarray(P, np.float64) @ M[:3, :3].T + M[:3, 3]).astype(np.float32)
+    I = np.asarray(I, np.uint32).reshape(-1, 3)
+    if len(I) and int(I.max()) >= len(P):
+        raise ValueError("mesh file: vertex index out of range")
+    UV = None if UV is None else np.asarray(UV, np.float32).reshape(-1, 2)
+    if face_normals:
+        return P, None, UV, (I[:, [1, 0, 2]] if flip_normals else I)
+    if N is not None:
+        Nw = np.asarray(N, np.float64) @ np.linalg.inv(M[:3, :3])            # rows x (M^-1) == (M^-T n) per row
+        l = np.linalg.norm(Nw, axis=1, keepdims=True)
+        N = np.where(l > 0, Nw / np.maximum(l, 1e-300), Nw).astype(np.float32)
+    else:
+        N = _smooth_normals(P, I)
+    return P, (-N if flip_normals else N), UV, I
+
+
+def _load_ply(path, to_world, face_normals=False, flip_normals=False):
+    """Stanford PLY as src/shapes/ply.cpp reads it: ascii / binary_little_endian / binary_big_endian; vertex properties x y z [nx ny nz] [u v | s t |
+    texture_u texture_v] (anything else, e.g. colours, is skipped), faces `vertex_indices` / `vertex_index` with 3 or 4 corners -- a quad (a, b, c, d)
+    becomes (a, b, c), (d, a, c) (ply.cpp:299-312)."""
+    types = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2", "uint16": "u2", "int": "i4", "int32": "i4",
+             "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt = None; elements = []
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: truncated PLY header")
+            tok = line.decode("ascii", "replace").split()
+            if not tok or tok[0] == "comment" or tok[0] == "obj_info":
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append([tok[1], int(tok[2]), []])
+            elif tok[0] == "property":
+                elements[-1][2].append(tuple(tok[1:]))
+            elif tok[0] == "end_header":
+                break
+        if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+            raise ValueError(f"{path}: unknown PLY format {fmt}")
+        end = ">" if fmt == "binary_big_endian" else "<"
+        verts = {}; faces = []
+        for name, count, props in elements:
+            has_list = any(p[0] == "list" for p in props)
+            if fmt == "ascii":
+                rows = [f.readline().split() for _ in range(count)]
+                if name == "vertex":
+                    arr = np.asarray(rows, np.float64).reshape(count, len(props))
+                    verts = {p[-1]: arr[:, k] for k, p in enumerate(props)}
+                elif name == "face":
+                    for r in rows:                                           # (only the index list; leading scalar properties are not used by ply.cpp either)
+                        k = 0
+                        for pr in props:
+                            if pr[0] == "list":
+                                n = int(r[k]); vals = [int(v) for v in r[k + 1:k + 1 + n]]; k += 1 + n
+                                if pr[-1] in ("vertex_indices", "vertex_index"):
+                                    faces.append(vals)
+                            else:
+                                k += 1
+            elif not has_list:
+                dt = np.dtype([(p[-1], end + types[p[0]]) for p in props])
+                arr = np.frombuffer(f.read(dt.itemsize * count), dt, count)
+                if name == "vertex":
+                    verts = {n: arr[n].astype(np.float64) for n in arr.dtype.names}
+            else:
+                if name == "face" and len(props) == 1 and props[0][-1] in ("vertex_indices", "vertex_index"):
+                    # the common case in one pass: every face has the same corner count (all triangles or all quads)
+                    ct, it = np.dtype(end + types[props[0][1]]), np.dtype(end + types[props[0][2]])
+                    pos = f.tell(); n0 = int(np.frombuffer(f.read(ct.itemsize), ct, 1)[0]); f.seek(pos)
+                    rec = np.dtype([("n", ct), ("v", it, (n0,))])
+                    raw = f.read(rec.itemsize * count)
+                    arr = np.frombuffer(raw, rec, count) if len(raw) == rec.itemsize * count else None
+                    if arr is not None and (arr["n"] == n0).all():
+                        faces = arr["v"].astype(np.int64).tolist() if n0 not in (3, 4) else arr["v"].astype(np.int64)
+                        continue
+                    f.seek(pos)
+                for _ in range(count):
+                    for pr in props:
+                        if pr[0] == "list":
+                            ct, it = np.dtype(end + types[pr[1]]), np.dtype(end + types[pr[2]])
+                            n = int(np.frombuffer(f.read(ct.itemsize), ct, 1)[0])
+                            vals = np.frombuffer(f.read(it.itemsize * n), it, n)
+                            if name == "face" and pr[-1] in ("vertex_indices", "vertex_index"):
+                                faces.append([int(v) for v in vals])
+                        else:
+                            f.read(np.dtype(types[pr[0]]).itemsize)
+    if not all(k in verts for k in "xyz"):
+        raise ValueError(f"{path}: PLY without vertex positions")
+    P = np.stack([verts["x"], verts["y"], verts["z"]], 1)
+    N = np.stack([verts["nx"], verts["ny"], verts["nz"]], 1) if all(k in verts for k in ("nx", "ny", "nz")) else None
+    UV = None
+    for a, b in (("u", "v"), ("s", "t"), ("texture_u", "texture_v")):
+        if a in verts and b in verts:
+            UV = np.stack([verts[a], verts[b]], 1)
+    tris = []
+    if isinstance(faces, np.ndarray):
+        tris = faces if faces.shape[1] == 3 else np.concatenate([faces[:, [0, 1, 2]][:, None], faces[:, [3, 0, 2]][:, None]], 1).reshape(-1, 3)
+    else:
+        for fc in faces:
+            if len(fc) not in (3, 4):
+                raise NotImplementedError("Only triangle and quad-based PLY meshes are supported for now.")       # ply.cpp:274-284
+            tris.append(fc[:3])
+            if len(fc) == 4:
+                tris.append([fc[3], fc[0], fc[2]])
+    return _finish_mesh(P, N, UV, np.asarray(tris, np.int64).reshape(-1, 3), to_world, face_normals, flip_normals)
+
+
+def _load_serialized(path, shape_index, to_world, face_normals=False, flip_normals=False):
+    """Mitsuba's .serialized triangle meshes (TriMesh::loadCompressed, src/librender/trimesh.cpp:176-250; shapes/serialized.cpp): little endian,
+    [u16 0x041C][u16 version 3 | 4] then a zlib stream {u32 flags, (v4) name\0, u64 vertices, u64 triangles, positions, [normals], [texcoords],
+    [colours], u32 indices}; several meshes per file are found through the offset table at the end (u64 offsets for v4, u32 for v3, then u32 count)."""
+    import struct
+    import zlib
+    with open(path, "rb") as f:
+        data = f.read()
+    def header(off):
+        fmt, ver = struct.unpack_from("<HH", data, off)
+        if fmt != 0x041C:
+            raise ValueError(f"{path}: Encountered an invalid file format!")
+        if ver not in (3, 4):
+            raise ValueError(f"{path}: Encountered an incompatible file version!")
+        return ver
+    ver = header(0); off = 0
+    if shape_index != 0:
+        count, = struct.unpack_from("<I", data, len(data) - 4)
+        if shape_index < 0 or shape_index >= count:
+            raise ValueError(f"Unable to unserialize mesh, shape index is out of range! (requested {shape_index} out of 0..{count - 1})")
+        if ver == 4:
+            off, = struct.unpack_from("<Q", data, len(data) - 8 * (count - shape_index) - 4)
+        else:
+            off, = struct.unpack_from("<I", data, len(data) - 4 * (count - shape_index + 1))
+        header(off)
+    raw = zlib.decompressobj().decompress(data[off + 4:])
+    flags, = struct.unpack_from("<I", raw, 0); p = 4
+    if ver == 4:
+        p = raw.index(b"\0", p) + 1
+    nv, nt = struct.unpack_from("<QQ", raw, p); p += 16
+    ft = "<f8" if flags & 0x2000 else "<f4"; fs = 8 if flags & 0x2000 else 4
+    def take(ncomp):
+        nonlocal p
+        a = np.frombuffer(raw, ft, nv * ncomp, p).reshape(nv, ncomp).astype(np.float64); p += fs * nv * ncomp
+        return a
+    P = take(3)
+    N = take(3) if flags & 0x0001 else None
+    UV = take(2) if flags & 0x0002 else None
+    if flags & 0x0008:
+        take(3)                                                             # vertex colours: not used by any model in scope
+    I = np.frombuffer(raw, "<u4", nt * 3, p).reshape(nt, 3)
+    return _finish_mesh(P, N, UV, I, to_world, face_normals or bool(flags & 0x0010), flip_normals)
+
+
+def _cube(to_world, flip_normals=False):
+    """shapes/cube.cpp:24-30, 81-108: 24 vertices (4 per face, own normals and [0,1]^2 texture coordinates), 12 triangles, [-1,1]^3 under toWorld."""
+    P = [(1, -1, -1), (1, -1, 1), (-1, -1, 1), (-1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, 1, 1), (1, 1, 1), (1, -1, -1), (1, 1, -1), (1, 1, 1), (1, -1, 1),
+         (1, -1, 1), (1, 1, 1), (-1, 1, 1), (-1, -1, 1), (-1, -1, 1), (-1, 1, 1), (-1, 1, -1), (-1, -1, -1), (1, 1, -1), (1, -1, -1), (-1, -1, -1), (-1, 1, -1)]
+    N = [(0, -1, 0)] * 4 + [(0, 1, 0)] * 4 + [(1, 0, 0)] * 4 + [(0, 0, 1)] * 4 + [(-1, 0, 0)] * 4 + [(0, 0, -1)] * 4
+    UV = [(0, 1), (1, 1), (1, 0), (0, 0)] * 6
+    I = [(0, 1, 2), (3, 0, 2), (4, 5, 6), (7, 4, 6), (8, 9, 10), (11, 8, 10), (12, 13, 14), (15, 12, 14), (16, 17, 18), (19, 16, 18), (20, 21, 22), (23, 20, 22)]
+    return _finish_mesh(np.array(P, np.float64), np.array(N, np.float64), np.array(UV, np.float64), np.array(I), to_world, False, flip_normals)
 
 
 def _smooth_normals(P, I):
@@ -805,18 +976,22 @@ def _parse_bsdf(node, bsdf_table, names, by_id, base="."):
 
 
 def _parse_environment(node, base):
-    """Root-level <emitter>: sunsky (baked, ppg_b200/sunsky.py) or envmap (src/emitters/envmap.cpp:102-190) -> envmap dict."""
+    """Root-level <emitter>: sunsky / sky / sun (baked, ppg_b200/sunsky.py) or envmap (src/emitters/envmap.cpp:102-190) -> envmap dict."""
     typ = node.attrib.get("type")
     pr = _prop_children(node)
     to_world = np.eye(4)
     for t in node.findall("transform"):
         if t.attrib.get("name") == "toWorld":
             to_world = _parse_transform(t)
-    if typ == "sunsky":
+    if typ in ("sunsky", "sky", "sun"):
         from . import sunsky
         for c in node:
             if c.attrib.get("name") == "albedo" and c.tag in ("rgb", "srgb", "spectrum"):
                 pr["albedo"] = _parse_color(c)
+        if typ == "sky":                  # src/emitters/sky.cpp: the sky dome alone -- what sunsky.cpp:122-158 nests with scale = skyScale
+            pr = dict(pr, skyScale=pr.get("scale", "1.0"), sunScale="0")
+        elif typ == "sun":                # src/emitters/sun.cpp:142-225: the sun disc alone, rasterised by the same (0,2)-sequence splat (sunRadiusScale = 0, a directional emitter, is not in scope)
+            pr = dict(pr, sunScale=pr.get("scale", "1.0"), skyScale="0")
         img, _ = sunsky.bake(pr)
         scale = 1.0                       # sunsky.cpp:209-219 passes no scale to the nested envmap
     elif typ == "envmap":
@@ -826,7 +1001,7 @@ def _parse_environment(node, base):
             img = np.repeat(img, 3, axis=2)
         scale = float(pr.get("scale", 1.0))
     else:
-        raise NotImplementedError(f"emitter '{typ}' (scene-level emitters in scope: sunsky, envmap)")
+        raise NotImplementedError(f"emitter '{typ}' (scene-level emitters in scope: sunsky, sky, sun, envmap)")
     with np.errstate(over="ignore"):
         half = np.ascontiguousarray(img, np.float32).astype(np.float16)
     if not np.isfinite(half.astype(np.float32)).all():
@@ -914,6 +1089,14 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
         if typ == "obj":
             P, N, UV, I = _load_obj(os.path.join(base, props["filename"]), to_world,
                                     props.get("faceNormals", "false") == "true", props.get("flipNormals", "false") == "true")
+        elif typ in ("ply", "serialized"):
+            if "maxSmoothAngle" in props:
+                raise NotImplementedError(f"{typ}: maxSmoothAngle")
+            fn, fl = props.get("faceNormals", "false") == "true", props.get("flipNormals", "false") == "true"
+            mesh = os.path.join(base, props["filename"])
+            P, N, UV, I = _load_ply(mesh, to_world, fn, fl) if typ == "ply" else _load_serialized(mesh, int(props.get("shapeIndex", 0)), to_world, fn, fl)
+        elif typ == "cube":
+            P, N, UV, I = _cube(to_world, props.get("flipNormals", "false") == "true")
         elif typ == "rectangle":
             P, N, UV, I = _rectangle(to_world)
         elif typ == "sphere":           # src/shapes/sphere.cpp:107-132: toWorld's scale folds into the radius
@@ -929,7 +1112,7 @@ def load_mitsuba_xml(path: str, film_size=None) -> SceneDesc:
             sphere_list.append([center, radius, len(shapes), props.get("flipNormals", "false") == "true"])
             P = np.zeros((0, 3), np.float32); N = None; UV = None; I = np.zeros((0, 3), np.uint32)
         else:
-            raise NotImplementedError(f"shape '{typ}' is outside the round-1 scope")
+            raise NotImplementedError(f"shape '{typ}' (shapes in scope: obj, ply, serialized, rectangle, cube, sphere)")
         bsdf_idx = None
         ref = sh.find("ref")
         if ref is not None:

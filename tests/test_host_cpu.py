@@ -369,3 +369,107 @@ def test_corrupt_scene_files_are_rejected_not_trusted(tmp_path):
     sc2 = copy.copy(sc); sc2.normals = sc.normals[:-1]
     p2 = str(tmp_path / "short_normals.ppgscene"); sc2.save_flat(p2)
     assert load(open(p2, "rb").read()) == -7 and b"do not match" in lib.ppg_last_error()
+
+
+def _scene_xml(shapes):
+    return f"""<scene version="0.5.0"><integrator type="guided_path"><string name="budgetType" value="spp"/><float name="budget" value="4"/></integrator>
+      <sensor type="perspective"><float name="fov" value="45"/><transform name="toWorld"><lookat origin="0,1,6" target="0,0,0" up="0,1,0"/></transform>
+        <film type="hdrfilm"><integer name="width" value="32"/><integer name="height" value="24"/></film></sensor>
+      <shape type="rectangle"><transform name="toWorld"><rotate x="1" angle="90"/><scale value="0.5"/><translate y="3"/></transform>
+        <emitter type="area"><rgb name="radiance" value="10,10,10"/></emitter></shape>
+      {shapes}</scene>"""
+
+
+def test_loader_reads_ply_meshes(tmp_path):
+    """<shape type="ply"> as src/shapes/ply.cpp reads it: binary little / big endian and ascii, triangles and quads (a quad (a,b,c,d) -> (a,b,c), (d,a,c)),
+    normals and texture coordinates when the file has them, angle-weighted normals when it does not; toWorld applied like every mesh."""
+    import struct
+    from ppg_b200 import scene as S
+    rng = np.random.default_rng(4)
+    V = rng.normal(size=(7, 3)).astype(np.float32); Nn = rng.normal(size=(7, 3)).astype(np.float32); UV = rng.random((7, 2)).astype(np.float32)
+    faces = [[0, 1, 2], [2, 3, 4, 5], [4, 5, 6]]
+    hdr = lambda fmt: (f"ply\nformat {fmt} 1.0\ncomment test\nelement vertex 7\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\n"
+                       "property float nz\nproperty float s\nproperty float t\nproperty uchar red\nelement face 3\nproperty list uchar int vertex_indices\nend_header\n").encode()
+    def binary(end):
+        b = hdr("binary_little_endian" if end == "<" else "binary_big_endian")
+        for i in range(7):
+            b += struct.pack(end + "8fB", *V[i], *Nn[i], *UV[i], 200)
+        for f in faces:
+            b += struct.pack(end + "B%di" % len(f), len(f), *f)
+        return b
+    ascii_ = hdr("ascii") + "".join(" ".join(repr(float(x)) for x in (*V[i], *Nn[i], *UV[i])) + " 200\n" for i in range(7)).encode() + \
+        "".join(f"{len(f)} " + " ".join(map(str, f)) + "\n" for f in faces).encode()
+    M = np.eye(4); M[:3, :3] = np.diag([2.0, 1.0, 0.5]); M[:3, 3] = [1, 2, 3]
+    out = []
+    for name, blob in (("le.ply", binary("<")), ("be.ply", binary(">")), ("a.ply", ascii_)):
+        (tmp_path / name).write_bytes(blob)
+        out.append(S._load_ply(str(tmp_path / name), M))
+    for P, N, uv, I in out:
+        assert np.allclose(P, V * [2, 1, 0.5] + [1, 2, 3], atol=1e-6) and np.allclose(uv, UV, atol=1e-6)
+        nw = Nn / [2, 1, 0.5]; nw /= np.linalg.norm(nw, axis=1, keepdims=True)
+        assert np.allclose(N, nw, atol=1e-6)                                       # normals: inverse transpose, normalised
+        assert I.tolist() == [[0, 1, 2], [2, 3, 4], [5, 2, 4], [4, 5, 6]]
+    # through the XML: face normals + flipNormals swap the winding, no vertex normals are kept
+    (tmp_path / "m.xml").write_text(_scene_xml('<shape type="ply"><string name="filename" value="le.ply"/><boolean name="faceNormals" value="true"/><boolean name="flipNormals" value="true"/><bsdf type="diffuse"/></shape>'))
+    sc = S.load_mitsuba_xml(str(tmp_path / "m.xml"))
+    assert sc.shapes[1, 1] == 4 and sc.shapes[1, 4] == 0 and sc.indices[2:].tolist() == (np.array([[1, 0, 2], [3, 2, 4], [2, 5, 4], [5, 4, 6]]) + 4).tolist()
+    bunny = "/root/reference/mitsuba/data/tests/bunny.ply"                          # the mesh of the reference's test_kd.cpp
+    if os.path.exists(bunny):
+        P, N, uv, I = S._load_ply(bunny, np.eye(4))
+        assert P.shape == (35947, 3) and I.shape == (69451, 3) and uv is None and np.allclose(np.linalg.norm(N, axis=1), 1, atol=1e-4)
+        ctr = P.mean(0); tri = P[I]; fn = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+        assert ((fn * (tri.mean(1) - ctr)).sum(1) > 0).mean() > 0.8                  # outward winding, and the smooth normals follow it
+        assert ((N[I[:, 0]] * fn).sum(1) > 0).mean() > 0.99
+
+
+def test_loader_reads_serialized_meshes_and_cubes(tmp_path):
+    """<shape type="serialized"> (TriMesh::loadCompressed, trimesh.cpp:176-250): header, zlib stream, flags (normals / texcoords / colours / face normals /
+    double precision), versions 3 and 4, several meshes behind the offset table at the end of the file; and <shape type="cube"> (shapes/cube.cpp)."""
+    import struct
+    import zlib
+    from ppg_b200 import scene as S
+    rng = np.random.default_rng(6)
+    def mesh(nv, nt, flags, ver):
+        P = rng.normal(size=(nv, 3)); N = rng.normal(size=(nv, 3)); UV = rng.random((nv, 2)); C = rng.random((nv, 3)); I = rng.integers(0, nv, (nt, 3)).astype("<u4")
+        ft = "<f8" if flags & 0x2000 else "<f4"
+        body = struct.pack("<I", flags) + (b"name\0" if ver == 4 else b"") + struct.pack("<QQ", nv, nt) + P.astype(ft).tobytes()
+        if flags & 1: body += N.astype(ft).tobytes()
+        if flags & 2: body += UV.astype(ft).tobytes()
+        if flags & 8: body += C.astype(ft).tobytes()
+        body += I.tobytes()
+        return struct.pack("<HH", 0x041C, ver) + zlib.compress(body), (P.astype(ft), N.astype(ft), UV.astype(ft), I)
+    for ver in (3, 4):
+        blobs = [mesh(5, 3, 0x0001 | 0x0002 | 0x0008, ver), mesh(9, 6, 0x2000 | 0x0001, ver), mesh(4, 2, 0x0010 | 0x0002, ver)]
+        offs = np.cumsum([0] + [len(b[0]) for b in blobs[:-1]])
+        table = b"".join(struct.pack("<Q" if ver == 4 else "<I", int(o)) for o in offs) + struct.pack("<I", len(blobs))
+        path = tmp_path / f"v{ver}.serialized"; path.write_bytes(b"".join(b[0] for b in blobs) + table)
+        M = np.eye(4); M[:3, 3] = [0.5, -1, 2]
+        for k, (_, (P, N, UV, I)) in enumerate(blobs):
+            p, n, uv, i = S._load_serialized(str(path), k, M)
+            assert np.allclose(p, P + [0.5, -1, 2], atol=1e-6) and np.array_equal(i, I)
+            if k == 2:
+                assert n is None and np.allclose(uv, UV, atol=1e-6)                # EFaceNormals
+            else:
+                assert np.allclose(n, N / np.linalg.norm(N, axis=1, keepdims=True), atol=1e-6) and ((uv is None) == (k == 1))
+        with pytest.raises(ValueError):
+            S._load_serialized(str(path), 3, M)
+    (tmp_path / "bad.serialized").write_bytes(b"\x04\x1c\x04\x00garbage")
+    with pytest.raises(ValueError):
+        S._load_serialized(str(tmp_path / "bad.serialized"), 0, np.eye(4))
+    # cube: [-1,1]^3 under toWorld, outward normals, per-face texture coordinates; rendered by the oracle like any mesh
+    (tmp_path / "c.xml").write_text(_scene_xml('<shape type="cube"><transform name="toWorld"><scale x="1" y="0.5" z="2"/><translate y="-1"/></transform><bsdf type="diffuse"/></shape>'
+                                               '<shape type="serialized"><string name="filename" value="v4.serialized"/><integer name="shapeIndex" value="1"/><bsdf type="diffuse"/></shape>'))
+    sc = S.load_mitsuba_xml(str(tmp_path / "c.xml"))
+    f, n = int(sc.shapes[1, 0]), int(sc.shapes[1, 1])
+    assert n == 12 and sc.shapes[1, 4] == 1 and sc.shapes[1, 5] == 1 and sc.shapes[2, 1] == 6
+    tri = sc.positions[sc.indices[f:f + n]]
+    assert np.allclose(tri.reshape(-1, 3).min(0), [-1, -1.5, -2]) and np.allclose(tri.reshape(-1, 3).max(0), [1, -0.5, 2])
+    fn = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]); ctr = np.array([0, -1.0, 0])
+    assert ((fn * (tri.mean(1) - ctr)).sum(1) > 0).all()                               # counter-clockwise seen from outside
+    assert ((sc.normals[sc.indices[f:f + n, 0]] * fn).sum(1) > 0).all()
+    assert set(map(tuple, sc.uvs[np.unique(sc.indices[f:f + n])].tolist())) == {(0.0, 0.0), (0.0, 1.0), (1.0, 0.0), (1.0, 1.0)}
+    import oracle_lib as O
+    (tmp_path / "only_cube.xml").write_text(_scene_xml('<shape type="cube"><transform name="toWorld"><scale x="1" y="0.5" z="2"/><translate y="-1"/></transform><bsdf type="diffuse"/></shape>'))
+    sc = S.load_mitsuba_xml(str(tmp_path / "only_cube.xml"))
+    img, st = O.Oracle(O.params_from_xml(sc.integrator), sc, kind="port").render()
+    assert np.isfinite(img).all() and img.mean() > 1e-3

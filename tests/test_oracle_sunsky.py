@@ -71,3 +71,23 @@ def test_low_discrepancy_points_of_the_sun_splat():
     i = np.arange(8, dtype=np.uint32)
     assert np.allclose(sunsky._radical_inverse2(i), [0, 0.5, 0.25, 0.75, 0.125, 0.625, 0.375, 0.875])
     assert np.allclose(sunsky._sobol2(i), [0, 0.5, 0.75, 0.25, 0.625, 0.125, 0.375, 0.875])      # direction numbers v ^= v >> 1
+
+
+@pytest.mark.skipif(not HAVE_TABLES, reason="reference tree not present")
+def test_sky_and_sun_emitters_are_the_two_halves_of_sunsky(tmp_path):
+    """The loader bakes <emitter type="sky"> (src/emitters/sky.cpp) and <emitter type="sun"> (src/emitters/sun.cpp:142-225) with the same code as sunsky, which
+    nests exactly these two (sunsky.cpp:122-207): their maps add up to the sunsky map, `scale` acts like skyScale / sunScale."""
+    from ppg_b200 import scene as S
+    body = '<float name="turbidity" value="4"/><float name="hour" value="9"/><float name="latitude" value="48"/><float name="longitude" value="11"/><float name="timezone" value="1"/>'
+    def env(typ, extra=""):
+        xml = f"""<scene version="0.5.0"><integrator type="guided_path"/>
+          <sensor type="perspective"><transform name="toWorld"><lookat origin="0,1,4" target="0,0,0" up="0,1,0"/></transform><film type="hdrfilm"><integer name="width" value="8"/><integer name="height" value="8"/></film></sensor>
+          <emitter type="{typ}">{body}{extra}</emitter>
+          <shape type="rectangle"><bsdf type="diffuse"/></shape></scene>"""
+        p = tmp_path / f"{typ}.xml"; p.write_text(xml)
+        return S.load_mitsuba_xml(str(p)).envmap["texels"].view(np.float16).astype(np.float64)
+    both, sky, sun = env("sunsky"), env("sky"), env("sun")
+    assert sky[sky.shape[0] // 2:].max() == 0 and sky.max() > 0 and (sun > 0).sum() < 0.01 * sun.size and sun.max() > 100 * sky.max()
+    assert np.allclose(sky + sun, both, rtol=2e-3, atol=1e-3)                       # (each map is rounded to half precision on its own)
+    assert np.allclose(env("sky", '<float name="scale" value="2"/>'), 2 * sky, rtol=2e-3, atol=1e-3)
+    assert np.allclose(env("sun", '<float name="scale" value="0.5"/>'), 0.5 * sun, rtol=2e-3, atol=1e-3)
