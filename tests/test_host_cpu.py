@@ -149,10 +149,10 @@ def test_fresnel_diffuse_reflectance_matches_the_published_fits():
 
 
 def test_unsupported_scene_content_is_refused_not_substituted(tmp_path):
-    """Content outside the hot-path scope raises instead of being silently replaced (e.g. a textured mask opacity, a sky-only emitter)."""
+    """Content outside the hot-path scope raises instead of being silently replaced (e.g. a textured mask opacity, a constant environment emitter)."""
     from ppg_b200.scene import load_mitsuba_xml
     head = """<scene version="0.5.0"><integrator type="guided_path"/><sensor type="perspective"><film type="hdrfilm"><rfilter type="box"/></film></sensor>"""
-    for body in ('<emitter type="sky"/>', '<bsdf type="phong" id="x"/>',
+    for body in ('<emitter type="constant"/>', '<shape type="cylinder"/>', '<bsdf type="phong" id="x"/>',
                  '<bsdf type="twosided" id="x"><bsdf type="mask"><bsdf type="diffuse"/></bsdf></bsdf>'):
         p = tmp_path / "bad.xml"; p.write_text(head + body + '<shape type="rectangle"/></scene>')
         with pytest.raises(NotImplementedError):
