@@ -3,6 +3,7 @@ reference constructor, the product path fails loudly without a GPU, and the scen
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -473,3 +474,28 @@ def test_loader_reads_serialized_meshes_and_cubes(tmp_path):
     sc = S.load_mitsuba_xml(str(tmp_path / "only_cube.xml"))
     img, st = O.Oracle(O.params_from_xml(sc.integrator), sc, kind="port").render()
     assert np.isfinite(img).all() and img.mean() > 1e-3
+
+
+def test_python_command_line_host(tmp_path):
+    """python -m ppg_b200 scene -o out [-D name=value]: the reference's `mitsuba -D ... -o ... scene.xml` for this integrator.  On the CPU: scene + parameter
+    handling (--check), the plugin constructor's error for a bad enum value, the loud failure without a device, and the three film writers."""
+    import subprocess
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "practical-path-guiding_b200"))
+    run = lambda *a: subprocess.run([sys.executable, "-m", "ppg_b200", *a], capture_output=True, text=True, env=env)
+    scene = os.path.join(ROOT, "scenes", "cbox-improved.npz")
+    r = run(scene, "--check", "-D", "budget=28", "--size", "40", "30")
+    assert r.returncode == 0 and "film 40 x 30" in r.stderr and "check ok" in r.stderr, r.stderr
+    r = run(scene, "--check", "-D", "sampleCombination=median")
+    assert r.returncode == 1 and "sampleCombination" in r.stderr
+    if not __import__("common").gpu_available():
+        r = run(scene, "-o", str(tmp_path / "o.pfm"))
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr and not os.path.exists(tmp_path / "o.pfm")
+    from ppg_b200.__main__ import write_image
+    img = np.random.default_rng(0).random((5, 7, 3)).astype(np.float32)
+    for ext in ("exr", "pfm", "npy"):
+        write_image(str(tmp_path / f"w.{ext}"), img)
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    assert np.array_equal(cv2.imread(str(tmp_path / "w.exr"), cv2.IMREAD_UNCHANGED)[..., ::-1], img) and np.array_equal(np.load(tmp_path / "w.npy"), img)
+    raw = open(tmp_path / "w.pfm", "rb").read()
+    assert raw.startswith(b"PF\n7 5\n-1.0\n") and np.array_equal(np.frombuffer(raw[12:], "<f4").reshape(5, 7, 3)[::-1], img)
