@@ -155,6 +155,15 @@ int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float
     return PPG_OK;
 }
 
+// dumpSDTree: the .sdt file the reference itself writes for the tree in its current state (reference backend only: its own BlobWriter / dump code)
+int ppgo_tree_dump(ppgo_handle *h, const char *path, const float *cam_to_world) {
+#ifdef PPGO_BACKEND_REF
+    return h->T().dump(path, cam_to_world) ? PPG_OK : PPG_ERR_IO;
+#else
+    (void) h; (void) path; (void) cam_to_world; return PPG_ERR_UNSUPPORTED;
+#endif
+}
+
 int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb) { h->T().refine((size_t) threshold, max_mb); return PPG_OK; }
 int ppgo_tree_reset(ppgo_handle *h, int max_depth, float threshold) { h->T().resetAll(max_depth, threshold, 1); return PPG_OK; }
 int ppgo_tree_build(ppgo_handle *h) { h->T().buildAll(1); return PPG_OK; }

@@ -39,6 +39,8 @@ int ppgo_emitter_sample_direct(ppgo_handle *h, size_t n, const float *ref, const
 int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float *value_out /* 3n or NULL */);
 
 /* ---- SD-tree level operations (work on the handle's tree) */
+/* dumpSDTree (GP:1191-1208) through the reference's own writer code; PPG_ERR_UNSUPPORTED on the restated backend */
+int ppgo_tree_dump(ppgo_handle *h, const char *path, const float *cam_to_world /* 16, row major */);
 int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb);
 int ppgo_tree_reset(ppgo_handle *h, int max_depth, float threshold);
 int ppgo_tree_build(ppgo_handle *h);

@@ -50,6 +50,11 @@ struct RefBackend {
         } else t->record(Point(o[0], o[1], o[2]), Vector(voxel[0], voxel[1], voxel[2]), rec, df, ls);
     }
 
+    // dumpSDTree (GP:1191-1208) with the reference's own writers: BlobWriter (GP:35-57), STree::dump (GP:945-951), DTreeWrapper / DTree::dump (GP:699-711)
+    bool dump(const char *path, const float cam[16]) const {
+        { mitsuba::BlobWriter blob(path); for (int i = 0; i < 16; ++i) blob << (float) cam[i]; t->dump(blob); }
+        std::ifstream check(path, std::ios::binary); return check.good();
+    }
     void refine(size_t thr, int maxMB) { t->refine(thr, maxMB); }
     void resetAll(int maxDepth, float thr, int nthreads) { omp_set_num_threads(nthreads); t->forEachDTreeWrapperParallel([=](mitsuba::DTreeWrapper *d) { d->reset(maxDepth, thr); }); }
     void buildAll(int nthreads) { omp_set_num_threads(nthreads); t->forEachDTreeWrapperParallel([](mitsuba::DTreeWrapper *d) { d->build(); }); }

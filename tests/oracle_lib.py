@@ -37,6 +37,7 @@ def _declare(lib):
     lib.ppgo_bsdf_sample.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p, u8p, f32p]
     lib.ppgo_emitter_sample_direct.argtypes = [H, C.c_size_t, f32p, f32p, f32p, C.c_int, f32p, f32p, f32p, f32p]
     lib.ppgo_env_pdf.argtypes = [H, C.c_size_t, f32p, f32p, f32p]
+    lib.ppgo_tree_dump.argtypes = [H, C.c_char_p, f32p]
     lib.ppgo_tree_refine.argtypes = [H, C.c_uint64, C.c_int]
     lib.ppgo_tree_reset.argtypes = [H, C.c_int, C.c_float]
     lib.ppgo_tree_build.argtypes = [H]
@@ -208,6 +209,11 @@ class Oracle:
         rc = self.lib.ppgo_env_pdf(self.h, len(d), fptr(d), fptr(pdf), fptr(val))
         assert rc == 0, rc
         return pdf, val
+
+    def dump(self, path, cam_to_world):
+        """The .sdt file of the tree's current state, written by the reference's own code (reference backend only)."""
+        cam = np.ascontiguousarray(cam_to_world, np.float32).reshape(16)
+        return self.lib.ppgo_tree_dump(self.h, str(path).encode(), fptr(cam))
 
     def refine(self, threshold, max_mb=-1):
         self.lib.ppgo_tree_refine(self.h, int(threshold), max_mb)

@@ -126,3 +126,52 @@ def test_dtree_sample_matches_pdf_chi2():
     dof = mask.sum() - 1
     assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
     assert abs(H[~mask].sum() - exp[~mask].sum()) < 0.01 * m
+
+
+@needs_ref
+def test_sdt_reader_reads_what_the_reference_writes(tmp_path):
+    """The .sdt wire format (SURVEY 8f row 2), pinned on the reference's OWN writer: the verbatim BlobWriter / STree::dump / DTree::dump code (GP:35-57, 945-951,
+    699-711) dumps a trained tree, ppg_b200.sdt.read (the reader of the visualizer, main.cpp:142-173, restated) reads it back: the camera matrix, one record
+    per leaf with sampling weight > 0 in depth-first order, min corner / size of the leaf's voxel, mean, weight, and the node arrays bit for bit."""
+    from ppg_b200 import sdt
+    o, _ = _run("ref", 2, 1, 0, iters=3, n=4000)
+    cam = np.arange(16, dtype=np.float32).reshape(4, 4) * 0.25 - 1
+    path = tmp_path / "tree-02.sdt"
+    assert o.dump(path, cam) == 0
+    cam2, leaves = sdt.read(path)
+    assert np.array_equal(cam2, cam)
+    e = o.export(0)                                                                 # the sampling trees the dump holds
+    # depth-first order over the S-tree (child 0 first), voxels from the box: the reference dumps leaves with weight > 0 only
+    lo, hi = np.float32(AABB[0]), np.float32(AABB[1])
+    ext = np.float32(hi - lo); ext[:] = ext.max()                                   # STree::STree cubifies the box from the min corner (GP:850-860)
+    order = []
+    def walk(n, p, s):
+        if e["s_is_leaf"][n]:
+            order.append((n, p.copy(), s.copy())); return
+        ax = int(e["s_axis"][n]); s2 = s.copy(); s2[ax] = s2[ax] / 2
+        walk(int(e["s_children"][n, 0]), p, s2)
+        p2 = p.copy(); p2[ax] += s2[ax]
+        walk(int(e["s_children"][n, 1]), p2, s2)
+    walk(0, lo.copy(), ext.copy())
+    kept = [(n, p, s) for n, p, s in order if e["tree_weight"][n] > 0]
+    assert len(leaves) == len(kept) > 4
+    for leaf, (n, p, s) in zip(leaves, kept):
+        f, c = int(e["tree_first"][n]), int(e["tree_count"][n])
+        assert np.array_equal(leaf.sums, e["sums"][f:f + c]) and np.array_equal(leaf.children, e["children"][f:f + c])
+        assert np.allclose(leaf.pos, p, rtol=1e-6, atol=1e-4) and np.allclose(leaf.size, s, rtol=1e-6)
+        assert leaf.weight == int(e["tree_weight"][n]) and leaf.depth() == int(e["tree_depth"][n])
+        w = float(e["tree_weight"][n])
+        assert np.isclose(leaf.mean, float(e["tree_sum"][n]) / (4 * np.pi * w), rtol=1e-5)
+    # the density the reader reconstructs is the density the reference samples with
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(200, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    n0 = kept[0][0]
+    ref = o.pdf(np.full(len(d), n0, np.uint32), d)
+    xy = np.stack([(np.clip(d[:, 2], -1, 1) + 1) / 2, np.mod(np.arctan2(d[:, 1], d[:, 0]), 2 * np.pi) / (2 * np.pi)], 1)      # dirToCanonical, GP:597-608
+    mine = np.array([leaves[0].pdf(float(x), float(y)) for x, y in xy])
+    assert np.allclose(mine, ref, rtol=1e-4, atol=1e-7)
+    # and a damaged file is an error, not a guess
+    raw = open(path, "rb").read(); (tmp_path / "cut.sdt").write_bytes(raw[:len(raw) - 7])
+    with pytest.raises(ValueError):
+        sdt.read(tmp_path / "cut.sdt")
+    assert O.Oracle(O.default_params(), aabb=AABB, kind="port").dump(tmp_path / "x.sdt", cam) == -6      # the restated backend has no writer of its own
