@@ -7,8 +7,11 @@
 // roughdielectric / plastic / thindielectric with the twosided, mask and bumpmap
 // wrappers, bilinear bitmap textures, index-matched (null) transitions, area lights on
 // meshes and spheres with light sampling, a lat-long environment emitter (sunsky is
-// baked into one on the host), box-filtered film.  Pinned against the authors' render logs and images
-// of CBOX and SPACESHIP (tests/test_oracle_golden.py).  Templated on the SD-tree
+// baked into one on the host, light sampling included), box-filtered film.  Pinned against the authors' render logs
+// and images of CBOX, SPACESHIP and KITCHEN (tests/test_oracle_golden.py), and -- function by function, bit for bit --
+// against the reference's own code compiled verbatim where that is possible: the microfacet distribution, erf / erfinv,
+// the Fresnel functions, coordinateSystem and the cosine-hemisphere warp (oracle/microfacet_ref -> oracle/_ref/
+// libmicrofacet_ref.so, tests/test_oracle_bsdf.py), the sky model (libskymodel_ref.so).  Templated on the SD-tree
 // backend so that the same tracer runs either on the restated trees
 // (sdtree_port.h) or on the reference's own SD-tree code compiled verbatim
 // (oracle/sdtree_ref, built into oracle/_ref/).

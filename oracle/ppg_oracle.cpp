@@ -127,6 +127,56 @@ int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *
     return PPG_OK;
 }
 
+// ---- the restated microfacet distribution (ppg_cpu_tracer.h: struct Microfacet, mts_erf / mts_erfinv), entry by entry like oracle/microfacet_ref/wrapper.h
+int ppgo_mf_eval(int type, float alpha, size_t n, const float *m, float *out) {
+    const Microfacet d(type, alpha);
+    for (size_t i = 0; i < n; ++i) out[i] = d.eval(f3(m[3 * i], m[3 * i + 1], m[3 * i + 2]));
+    return PPG_OK;
+}
+int ppgo_mf_smith_g1(int type, float alpha, size_t n, const float *v, const float *m, float *out) {
+    const Microfacet d(type, alpha);
+    for (size_t i = 0; i < n; ++i) out[i] = d.smithG1(f3(v[3 * i], v[3 * i + 1], v[3 * i + 2]), f3(m[3 * i], m[3 * i + 1], m[3 * i + 2]));
+    return PPG_OK;
+}
+int ppgo_mf_pdf(int type, float alpha, size_t n, const float *wi, const float *m, float *out) {
+    const Microfacet d(type, alpha);
+    for (size_t i = 0; i < n; ++i) out[i] = d.pdfVisible(f3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), f3(m[3 * i], m[3 * i + 1], m[3 * i + 2]));
+    return PPG_OK;
+}
+int ppgo_mf_sample(int type, float alpha, size_t n, const float *wi, const float *sample, float *m_out, float *pdf_out) {
+    const Microfacet d(type, alpha);
+    for (size_t i = 0; i < n; ++i) {
+        const F3 w = f3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        const F3 m = d.sampleVisible(w, sample[2 * i], sample[2 * i + 1]);
+        m_out[3 * i] = m.x; m_out[3 * i + 1] = m.y; m_out[3 * i + 2] = m.z; pdf_out[i] = d.pdfVisible(w, m);
+    }
+    return PPG_OK;
+}
+// the restated helpers of src/libcore/util.cpp / warp.cpp
+int ppgo_fresnel_dielectric_ext(size_t n, const float *cosThetaI, float eta, float *f_out, float *cos_t_out) {
+    for (size_t i = 0; i < n; ++i) { float ct = 0; f_out[i] = fresnel_dielectric_ext(cosThetaI[i], ct, eta); cos_t_out[i] = ct; }
+    return PPG_OK;
+}
+int ppgo_fresnel_conductor_exact(size_t n, const float *cosThetaI, const float eta[3], const float k[3], float *out) {
+    for (size_t i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) out[3 * i + c] = fresnel_conductor_exact(cosThetaI[i], eta[c], k[c]);
+    return PPG_OK;
+}
+int ppgo_coordinate_system(size_t n, const float *a, float *b_out, float *c_out) {
+    for (size_t i = 0; i < n; ++i) {
+        F3 b, c; coordinate_system(f3(a[3 * i], a[3 * i + 1], a[3 * i + 2]), b, c);
+        b_out[3 * i] = b.x; b_out[3 * i + 1] = b.y; b_out[3 * i + 2] = b.z; c_out[3 * i] = c.x; c_out[3 * i + 1] = c.y; c_out[3 * i + 2] = c.z;
+    }
+    return PPG_OK;
+}
+int ppgo_square_to_cosine_hemisphere(size_t n, const float *sample, float *out) {
+    for (size_t i = 0; i < n; ++i) { const F3 v = square_to_cosine_hemisphere(sample[2 * i], sample[2 * i + 1]); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
+    return PPG_OK;
+}
+int ppgo_mf_erf(size_t n, const float *x, float *erf_out, float *erfinv_out) {
+    for (size_t i = 0; i < n; ++i) { erf_out[i] = mts_erf(x[i]); erfinv_out[i] = mts_erfinv(x[i]); }
+    return PPG_OK;
+}
+
 // Scene::sampleAttenuatedEmitterDirect at n reference points (area, sphere and environment emitters); pdf 0 = the sample carries nothing
 int ppgo_emitter_sample_direct(ppgo_handle *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,
                                float *d_out, float *value_out, float *pdf_out, float *dist_out) {

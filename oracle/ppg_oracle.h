@@ -31,6 +31,18 @@ int ppgo_get_moment_images(ppgo_handle *h, float *sum_rgbw, float *sumsq_rgbw);
 int ppgo_bsdf_eval_pdf(const ppg_bsdf *b, size_t n, const float *wi, const float *wo, float *eval_out, float *pdf_out, const float *tables /* may be NULL */);
 int ppgo_bsdf_sample(const ppg_bsdf *b, size_t n, const float *wi, const float *sample, float *wo_out, float *weight_out, float *pdf_out, uint8_t *delta_out, const float *tables);
 
+/* ---- microfacet level: the restated MicrofacetDistribution (type: ppg_microfacet; isotropic, visible-normal sampling) -- m, v, wi: 3n local directions */
+int ppgo_mf_eval(int type, float alpha, size_t n, const float *m, float *out);
+int ppgo_mf_smith_g1(int type, float alpha, size_t n, const float *v, const float *m, float *out);
+int ppgo_mf_pdf(int type, float alpha, size_t n, const float *wi, const float *m, float *out);
+int ppgo_mf_sample(int type, float alpha, size_t n, const float *wi, const float *sample, float *m_out, float *pdf_out);
+int ppgo_mf_erf(size_t n, const float *x, float *erf_out, float *erfinv_out);
+/* restated helpers: fresnelDielectricExt / fresnelConductorExact (per channel; out 3n) / coordinateSystem / warp::squareToCosineHemisphere */
+int ppgo_fresnel_dielectric_ext(size_t n, const float *cosThetaI, float eta, float *f_out, float *cos_t_out);
+int ppgo_fresnel_conductor_exact(size_t n, const float *cosThetaI, const float eta[3], const float k[3], float *out);
+int ppgo_coordinate_system(size_t n, const float *a, float *b_out, float *c_out);
+int ppgo_square_to_cosine_hemisphere(size_t n, const float *sample, float *out);
+
 /* ---- emitter level (handle with a scene): Scene::sampleAttenuatedEmitterDirect at n reference points -- ref, ref_n 3n (ref_n 0 = two-sided),
  * sample 2n; d_out 3n, value_out 3n (radiance * transmittance / pdf), pdf_out n (0: nothing), dist_out n -- and the environment emitter's
  * light-sampling density (Scene::pdfEmitterDirect) / radiance for n world directions */

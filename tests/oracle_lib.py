@@ -35,6 +35,10 @@ def _declare(lib):
     lib.ppgo_get_moment_images.argtypes = [H, f32p, f32p]
     lib.ppgo_bsdf_eval_pdf.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p]
     lib.ppgo_bsdf_sample.argtypes = [C.POINTER(capi.PpgBsdf), C.c_size_t, f32p, f32p, f32p, f32p, f32p, u8p, f32p]
+    for fn, at in (("eval", [C.c_int, C.c_float, C.c_size_t, f32p, f32p]), ("smith_g1", [C.c_int, C.c_float, C.c_size_t, f32p, f32p, f32p]),
+                   ("pdf", [C.c_int, C.c_float, C.c_size_t, f32p, f32p, f32p]), ("sample", [C.c_int, C.c_float, C.c_size_t, f32p, f32p, f32p, f32p])):
+        getattr(lib, "ppgo_mf_" + fn).argtypes = at
+    lib.ppgo_mf_erf.argtypes = [C.c_size_t, f32p, f32p, f32p]
     lib.ppgo_emitter_sample_direct.argtypes = [H, C.c_size_t, f32p, f32p, f32p, C.c_int, f32p, f32p, f32p, f32p]
     lib.ppgo_env_pdf.argtypes = [H, C.c_size_t, f32p, f32p, f32p]
     lib.ppgo_tree_dump.argtypes = [H, C.c_char_p, f32p]
@@ -314,3 +318,56 @@ def bsdf_sample(b, wi, smp, kind="port", tables=None):
     keep, tp = _tab(tables)
     lib.ppgo_bsdf_sample(C.byref(b), len(wi), fptr(wi), fptr(smp), fptr(wo), fptr(w), fptr(pdf), d.ctypes.data_as(C.POINTER(C.c_uint8)), tp)
     return wo, w, pdf, d
+
+
+MFREF_SO = os.path.join(ROOT, "oracle", "_ref", "libmicrofacet_ref.so")
+
+
+def microfacet(kind):
+    """Entry points of a microfacet distribution: kind "port" = the restated struct of the oracle, "ref" = the reference's MicrofacetDistribution
+    compiled verbatim (oracle/_ref/libmicrofacet_ref.so).  Returns an object with eval / smith_g1 / pdf / sample / erf over numpy arrays."""
+    f32p = C.POINTER(C.c_float)
+    if kind == "ref":
+        lib = C.CDLL(MFREF_SO); pre = "mfref_"; hp = "mfref_"
+        for fn, at in (("eval", [C.c_int, C.c_float, C.c_size_t, f32p, f32p]), ("smith_g1", [C.c_int, C.c_float, C.c_size_t, f32p, f32p, f32p]),
+                       ("pdf", [C.c_int, C.c_float, C.c_size_t, f32p, f32p, f32p]), ("sample", [C.c_int, C.c_float, C.c_size_t, f32p, f32p, f32p, f32p])):
+            getattr(lib, pre + fn).argtypes = at
+        lib.mfref_erf.argtypes = [C.c_size_t, f32p, f32p, f32p]
+    else:
+        lib = load("port"); pre = "ppgo_mf_"; hp = "ppgo_"
+
+    class MF:
+        def eval(self, t, a, m):
+            m = np.ascontiguousarray(m, np.float32); out = np.zeros(len(m), np.float32); getattr(lib, pre + "eval")(t, a, len(m), fptr(m), fptr(out)); return out
+
+        def smith_g1(self, t, a, v, m):
+            v = np.ascontiguousarray(v, np.float32); m = np.ascontiguousarray(m, np.float32); out = np.zeros(len(m), np.float32)
+            getattr(lib, pre + "smith_g1")(t, a, len(m), fptr(v), fptr(m), fptr(out)); return out
+
+        def pdf(self, t, a, wi, m):
+            wi = np.ascontiguousarray(wi, np.float32); m = np.ascontiguousarray(m, np.float32); out = np.zeros(len(m), np.float32)
+            getattr(lib, pre + "pdf")(t, a, len(m), fptr(wi), fptr(m), fptr(out)); return out
+
+        def sample(self, t, a, wi, smp):
+            wi = np.ascontiguousarray(wi, np.float32); smp = np.ascontiguousarray(smp, np.float32); m = np.zeros_like(wi); pdf = np.zeros(len(wi), np.float32)
+            getattr(lib, pre + "sample")(t, a, len(wi), fptr(wi), fptr(smp), fptr(m), fptr(pdf)); return m, pdf
+
+        def fresnel_dielectric_ext(self, c, eta):
+            c = np.ascontiguousarray(c, np.float32); f = np.zeros_like(c); ct = np.zeros_like(c)
+            getattr(lib, hp + "fresnel_dielectric_ext")(C.c_size_t(len(c)), fptr(c), C.c_float(eta), fptr(f), fptr(ct)); return f, ct
+
+        def fresnel_conductor_exact(self, c, eta, k):
+            c = np.ascontiguousarray(c, np.float32); e = np.ascontiguousarray(eta, np.float32); kk = np.ascontiguousarray(k, np.float32); out = np.zeros((len(c), 3), np.float32)
+            getattr(lib, hp + "fresnel_conductor_exact")(C.c_size_t(len(c)), fptr(c), fptr(e), fptr(kk), fptr(out)); return out
+
+        def coordinate_system(self, a):
+            a = np.ascontiguousarray(a, np.float32); b = np.zeros_like(a); c = np.zeros_like(a)
+            getattr(lib, hp + "coordinate_system")(C.c_size_t(len(a)), fptr(a), fptr(b), fptr(c)); return b, c
+
+        def square_to_cosine_hemisphere(self, smp):
+            smp = np.ascontiguousarray(smp, np.float32); out = np.zeros((len(smp), 3), np.float32)
+            getattr(lib, hp + "square_to_cosine_hemisphere")(C.c_size_t(len(smp)), fptr(smp), fptr(out)); return out
+
+        def erf(self, x):
+            x = np.ascontiguousarray(x, np.float32); a = np.zeros_like(x); b = np.zeros_like(x); getattr(lib, pre + "erf")(len(x), fptr(x), fptr(a), fptr(b)); return a, b
+    return MF()

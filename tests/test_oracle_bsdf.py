@@ -141,3 +141,54 @@ def test_oracle_looks_through_null_surfaces_consistently():
         assert np.isfinite(img).all(); mean[name] = float(img.mean())
     assert 0.85 * mean["plain"] < mean["never"] < mean["plain"]
     assert 1.1 * mean["never"] < mean["always"] < 1.6 * mean["never"]
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(O.MFREF_SO), reason="oracle/_ref/libmicrofacet_ref.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("type_", [0, 1])          # PPG_MICROFACET_BECKMANN, PPG_MICROFACET_GGX
+@pytest.mark.parametrize("alpha", [0.01, 0.1, 0.2, 0.6])
+def test_restated_microfacet_equals_the_reference_class(type_, alpha):
+    """The oracle's microfacet restatement (struct Microfacet of ppg_cpu_tracer.h: D, Smith G1, the Heitz-d'Eon visible-normal sampling with its Newton
+    iteration / rational fits, and mts_erf / mts_erfinv) against the reference's OWN class MicrofacetDistribution (src/bsdfs/microfacet.h:45-721) and math::erf /
+    erfinv (src/libcore/math.cpp:25-72) compiled verbatim: same inputs, every float must agree bit for bit (both sides are built without FMA contraction and
+    call the same libm).  This is what roughconductor / roughplastic / roughdielectric are built on -- and what the CUDA mf_* functions mirror."""
+    ref, port = O.microfacet("ref"), O.microfacet("port")
+    rng = np.random.default_rng(100 * type_ + int(alpha * 100))
+    n = 200000
+    def dirs(upper):
+        d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        if upper:
+            d[:, 2] = np.abs(d[:, 2])
+        return d.astype(np.float32)
+    m, v, wi = dirs(False), dirs(False), dirs(True)
+    # grazing and near-normal incidence, where the sampling code switches branches (theta < 1e-4, cot / tan extremes)
+    wi[:1000] = [0, 0, 1]; wi[1000:2000, 2] = 1e-3 * rng.random(1000); wi[1000:2000] /= np.linalg.norm(wi[1000:2000], axis=1, keepdims=True)
+    assert np.array_equal(ref.eval(type_, alpha, m), port.eval(type_, alpha, m))
+    assert np.array_equal(ref.smith_g1(type_, alpha, v, m), port.smith_g1(type_, alpha, v, m))
+    assert np.array_equal(ref.pdf(type_, alpha, wi, np.abs(m)), port.pdf(type_, alpha, wi, np.abs(m)))
+    smp = rng.random((n, 2), dtype=np.float32); smp[:50] = [[0.0, 0.0]] * 50; smp[50:100] = [[0.99999994, 0.99999994]] * 50
+    mr, pr = ref.sample(type_, alpha, wi, smp); mp, pp = port.sample(type_, alpha, wi, smp)
+    ok = np.isfinite(mr).all(axis=1)
+    assert ok.mean() > 0.999 and np.array_equal(np.isfinite(mp).all(axis=1), ok)
+    assert np.array_equal(mr[ok], mp[ok]) and np.array_equal(pr[ok], pp[ok])
+    x = np.concatenate([rng.uniform(-0.999999, 0.999999, 100000), [-0.99999994, 0.0, 0.99999994], rng.uniform(-6, 6, 1000)]).astype(np.float32)
+    er, eir = ref.erf(x); ep, eip = port.erf(x)
+    assert np.array_equal(er, ep) and np.array_equal(eir[np.abs(x) < 1], eip[np.abs(x) < 1])
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(O.MFREF_SO), reason="oracle/_ref/libmicrofacet_ref.so not built (needs /root/reference at build time)")
+def test_restated_helpers_equal_the_reference_functions():
+    """fresnelDielectricExt, the Spectrum overload of fresnelConductorExact, coordinateSystem (src/libcore/util.cpp:592-601, 651-681, 739-761) and
+    warp::squareToCosineHemisphere (warp.cpp:43-52, 81-102), compiled verbatim, against the oracle's restatements: bit for bit."""
+    ref, port = O.microfacet("ref"), O.microfacet("port")
+    rng = np.random.default_rng(9)
+    c = np.concatenate([rng.uniform(-1, 1, 200000), [0.0, 1.0, -1.0, 1e-6, -1e-6]]).astype(np.float32)
+    for eta in (1.0, 1.5046 / 1.000277, 1 / 1.5, 1.33, 2.4):
+        fr, tr = ref.fresnel_dielectric_ext(c, eta); fp, tp = port.fresnel_dielectric_ext(c, eta)
+        assert np.array_equal(fr, fp) and np.array_equal(tr, tp)
+    for eta, k in (((0.2, 0.9, 1.1), (3.9, 2.4, 2.2)), ((1.65746, 0.880369, 0.521229), (9.22387, 6.26952, 4.837)), ((0, 0, 0), (1, 1, 1)), ((1.5, 1.5, 1.5), (0, 0, 0))):
+        assert np.array_equal(ref.fresnel_conductor_exact(np.abs(c), eta, k), port.fresnel_conductor_exact(np.abs(c), eta, k))
+    a = rng.normal(size=(200000, 3)).astype(np.float32); a /= np.linalg.norm(a, axis=1, keepdims=True); a[:3] = np.eye(3)
+    (br, cr), (bp, cp) = ref.coordinate_system(a), port.coordinate_system(a)
+    assert np.array_equal(br, bp) and np.array_equal(cr, cp)
+    smp = rng.random((200000, 2), dtype=np.float32); smp[:4] = [[0.5, 0.5], [0, 0], [0.99999994, 0.5], [0.5, 0]]
+    assert np.array_equal(ref.square_to_cosine_hemisphere(smp), port.square_to_cosine_hemisphere(smp))
