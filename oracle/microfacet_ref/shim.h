@@ -5,12 +5,15 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
+#include <cstdint>
 #include <cstdio>
 #include <string>
 
 #define MTS_NAMESPACE_BEGIN namespace mitsuba {
 #define MTS_NAMESPACE_END }
 #define MTS_EXPORT_CORE
+#define FINLINE inline
 #define SLog(level, ...) do { if ((level) >= mitsuba::EError) { std::fprintf(stderr, __VA_ARGS__); std::fprintf(stderr, "\n"); } } while (0)
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -35,7 +38,18 @@ struct Vector {
     Vector operator-(const Vector &v) const { return Vector(x - v.x, y - v.y, z - v.z); }
     Vector operator+(const Vector &v) const { return Vector(x + v.x, y + v.y, z + v.z); }
     Float length() const { return std::sqrt(x * x + y * y + z * z); }
+    Float operator[](int i) const { return (&x)[i]; }
+    Float &operator[](int i) { return (&x)[i]; }
 };
+struct Point {                                                                                  // TPoint3<Float>
+    Float x, y, z;
+    Point() : x(0), y(0), z(0) {}
+    Point(Float x_, Float y_, Float z_) : x(x_), y(y_), z(z_) {}
+    Vector operator-(const Point &p) const { return Vector(x - p.x, y - p.y, z - p.z); }
+    Float operator[](int i) const { return (&x)[i]; }
+    operator Vector() const { return Vector(x, y, z); }                                         // `Vector(A)` in TriAccel::load
+};
+struct Ray { Point o; Vector d; };
 struct Normal : public Vector {
     Normal() {}
     Normal(Float x_, Float y_, Float z_) : Vector(x_, y_, z_) {}

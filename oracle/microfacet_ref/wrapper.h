@@ -49,6 +49,26 @@ int mfref_square_to_cosine_hemisphere(size_t n, const float *sample, float *out)
     for (size_t i = 0; i < n; ++i) { const Vector v = mitsuba::warp::squareToCosineHemisphere(Point2(sample[2 * i], sample[2 * i + 1])); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
     return 0;
 }
+// ---- TriAccel (include/mitsuba/render/triaccel.h:27-158) and evalCubicInterp1D (src/libcore/spline.cpp:23-60)
+int mfref_triaccel(size_t n, const float *A, const float *B, const float *C, const float *o, const float *d, const float *mint, const float *maxt,
+                   int *k_out, float *consts_out /* 9n: n_u n_v n_d a_u a_v b_nu b_nv c_nu c_nv */, unsigned char *hit_out, float *tuv_out /* 3n */) {
+    for (size_t i = 0; i < n; ++i) {
+        mitsuba::TriAccel t; t.n_u = t.n_v = t.n_d = t.a_u = t.a_v = t.b_nu = t.b_nv = t.c_nu = t.c_nv = 0;
+        t.load(mitsuba::Point(A[3 * i], A[3 * i + 1], A[3 * i + 2]), mitsuba::Point(B[3 * i], B[3 * i + 1], B[3 * i + 2]), mitsuba::Point(C[3 * i], C[3 * i + 1], C[3 * i + 2]));
+        k_out[i] = (int) t.k;
+        const float c9[9] = {t.n_u, t.n_v, t.n_d, t.a_u, t.a_v, t.b_nu, t.b_nv, t.c_nu, t.c_nv};
+        for (int j = 0; j < 9; ++j) consts_out[9 * i + j] = c9[j];
+        mitsuba::Ray r; r.o = mitsuba::Point(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = Vector(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        mitsuba::Float u = 0, v = 0, tt = 0;
+        hit_out[i] = t.rayIntersect(r, mint[i], maxt[i], u, v, tt) ? 1 : 0;
+        tuv_out[3 * i] = tt; tuv_out[3 * i + 1] = u; tuv_out[3 * i + 2] = v;
+    }
+    return 0;
+}
+int mfref_cubic_interp_1d(size_t n, const float *x, const float *values, size_t size, float mn, float mx, float *out) {
+    for (size_t i = 0; i < n; ++i) out[i] = mitsuba::evalCubicInterp1D(x[i], values, size, mn, mx, false);
+    return 0;
+}
 int mfref_erf(size_t n, const float *x, float *erf_out, float *erfinv_out) {
     for (size_t i = 0; i < n; ++i) { erf_out[i] = mitsuba::math::erf(x[i]); erfinv_out[i] = mitsuba::math::erfinv(x[i]); }
     return 0;

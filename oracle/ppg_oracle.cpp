@@ -172,6 +172,25 @@ int ppgo_square_to_cosine_hemisphere(size_t n, const float *sample, float *out) 
     for (size_t i = 0; i < n; ++i) { const F3 v = square_to_cosine_hemisphere(sample[2 * i], sample[2 * i + 1]); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
     return PPG_OK;
 }
+int ppgo_triaccel(size_t n, const float *A, const float *B, const float *C, const float *o, const float *d, const float *mint, const float *maxt,
+                  int *k_out, float *consts_out, unsigned char *hit_out, float *tuv_out) {
+    for (size_t i = 0; i < n; ++i) {
+        TriAccelP t; t.k = 0; t.n_u = t.n_v = t.n_d = t.a_u = t.a_v = t.b_nu = t.b_nv = t.c_nu = t.c_nv = 0;
+        triaccel_load(t, f3(A[3 * i], A[3 * i + 1], A[3 * i + 2]), f3(B[3 * i], B[3 * i + 1], B[3 * i + 2]), f3(C[3 * i], C[3 * i + 1], C[3 * i + 2]));
+        k_out[i] = t.k;
+        const float c9[9] = {t.n_u, t.n_v, t.n_d, t.a_u, t.a_v, t.b_nu, t.b_nv, t.c_nu, t.c_nv};
+        for (int j = 0; j < 9; ++j) consts_out[9 * i + j] = c9[j];
+        float u = 0, v = 0, tt = 0;
+        hit_out[i] = triaccel_intersect(t, f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i], u, v, tt) ? 1 : 0;
+        tuv_out[3 * i] = tt; tuv_out[3 * i + 1] = u; tuv_out[3 * i + 2] = v;
+    }
+    return PPG_OK;
+}
+// RoughTransmittance::eval with alpha and eta fixed (rtrans.h:183-193): |cos|^(1/4) -> evalCubicInterp1D over PPG_BSDF_TABLE_SIZE samples, then the clamp of :233
+int ppgo_rough_transmittance(size_t n, const float *cosTheta, const float *values, float *out) {
+    for (size_t i = 0; i < n; ++i) out[i] = rough_transmittance(values, cosTheta[i]);
+    return PPG_OK;
+}
 int ppgo_mf_erf(size_t n, const float *x, float *erf_out, float *erfinv_out) {
     for (size_t i = 0; i < n; ++i) { erf_out[i] = mts_erf(x[i]); erfinv_out[i] = mts_erfinv(x[i]); }
     return PPG_OK;

@@ -42,6 +42,10 @@ int ppgo_fresnel_dielectric_ext(size_t n, const float *cosThetaI, float eta, flo
 int ppgo_fresnel_conductor_exact(size_t n, const float *cosThetaI, const float eta[3], const float k[3], float *out);
 int ppgo_coordinate_system(size_t n, const float *a, float *b_out, float *c_out);
 int ppgo_square_to_cosine_hemisphere(size_t n, const float *sample, float *out);
+/* TriAccel::load + rayIntersect for n (triangle, ray) pairs: k, the nine constants, hit flag, (t, u, v) */
+int ppgo_triaccel(size_t n, const float *A, const float *B, const float *C, const float *o, const float *d, const float *mint, const float *maxt,
+                  int *k_out, float *consts_out, unsigned char *hit_out, float *tuv_out);
+int ppgo_rough_transmittance(size_t n, const float *cosTheta, const float *values /* PPG_BSDF_TABLE_SIZE */, float *out);
 
 /* ---- emitter level (handle with a scene): Scene::sampleAttenuatedEmitterDirect at n reference points -- ref, ref_n 3n (ref_n 0 = two-sided),
  * sample 2n; d_out 3n, value_out 3n (radiance * transmittance / pdf), pdf_out n (0: nothing), dist_out n -- and the environment emitter's

@@ -192,3 +192,48 @@ def test_restated_helpers_equal_the_reference_functions():
     assert np.array_equal(br, bp) and np.array_equal(cr, cp)
     smp = rng.random((200000, 2), dtype=np.float32); smp[:4] = [[0.5, 0.5], [0, 0], [0.99999994, 0.5], [0.5, 0]]
     assert np.array_equal(ref.square_to_cosine_hemisphere(smp), port.square_to_cosine_hemisphere(smp))
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(O.MFREF_SO), reason="oracle/_ref/libmicrofacet_ref.so not built (needs /root/reference at build time)")
+def test_restated_triangle_test_and_spline_equal_the_reference():
+    """struct TriAccel (include/mitsuba/render/triaccel.h: Wald's precomputation `load` and `rayIntersect`) and evalCubicInterp1D (src/libcore/spline.cpp:23-60, the
+    rough-transmittance lookup of roughplastic), compiled verbatim, against triaccel_load / triaccel_intersect / rough_transmittance of the oracle: the projection axis, the
+    nine constants, the hit decision and (t, u, v) agree bit for bit -- the numbers every intersection of oracle and CUDA path (same operations) starts from."""
+    import ctypes as C
+    ref = C.CDLL(O.MFREF_SO); port = O.load("port")
+    f32p = C.POINTER(C.c_float)
+    rng = np.random.default_rng(21)
+    n = 300000
+    A = rng.normal(size=(n, 3)).astype(np.float32) * 10; B = A + rng.normal(size=(n, 3)).astype(np.float32); Cc = A + rng.normal(size=(n, 3)).astype(np.float32)
+    A[:100, 0] = 0; B[:100, 0] = 0; Cc[:100, 0] = 0                                  # axis-aligned triangles (k = 0 with exact zeros)
+    B[100:200] = A[100:200]                                                           # degenerate: denom == 0 -> k = 3, never hit
+    # rays aimed at a point near the triangle (about a quarter hit), some parallel to the plane
+    w = rng.random((n, 2)); tgt = A + (B - A) * (w[:, :1] * 1.4 - 0.2) + (Cc - A) * (w[:, 1:] * 1.4 - 0.2)
+    o = (tgt + rng.normal(size=(n, 3)) * 5).astype(np.float32); d = (tgt - o); d /= np.linalg.norm(d, axis=1, keepdims=True); d = d.astype(np.float32)
+    d[200:300] = (B - A)[200:300] / np.linalg.norm((B - A)[200:300], axis=1, keepdims=True)
+    mint = np.full(n, 1e-4, np.float32); maxt = np.where(rng.random(n) < 0.1, 3.0, np.inf).astype(np.float32)
+    outs = []
+    for lib, name in ((ref, "mfref_triaccel"), (port, "ppgo_triaccel")):
+        k = np.zeros(n, np.int32); c9 = np.zeros((n, 9), np.float32); hit = np.zeros(n, np.uint8); tuv = np.zeros((n, 3), np.float32)
+        fn = getattr(lib, name); fn.argtypes = [C.c_size_t] + [f32p] * 7 + [C.POINTER(C.c_int), f32p, C.POINTER(C.c_ubyte), f32p]
+        args = [np.ascontiguousarray(a, np.float32) for a in (A, B, Cc, o, d, mint, maxt)]
+        fn(n, *[a.ctypes.data_as(f32p) for a in args], k.ctypes.data_as(C.POINTER(C.c_int)), c9.ctypes.data_as(f32p), hit.ctypes.data_as(C.POINTER(C.c_ubyte)), tuv.ctypes.data_as(f32p))
+        outs.append((k, c9, hit, tuv))
+    (k0, c0, h0, t0), (k1, c1, h1, t1) = outs
+    assert np.array_equal(k0, k1) and (k0[100:200] == 3).all() and 0.1 < h0.mean() < 0.5
+    ok = k0 < 3
+    assert np.array_equal(c0[ok].view(np.uint32), c1[ok].view(np.uint32))             # (bit patterns: NaN-free here, and -0.0 must stay -0.0)
+    assert np.array_equal(h0, h1) and np.array_equal(t0[h0 == 1], t1[h0 == 1])
+    # spline: the 100-entry transmittance table of a material, looked up at |cos|^(1/4) and clamped to [0, 1] (rtrans.h:183-193, 233)
+    from ppg_b200 import rtrans
+    lut, _ = rtrans.reduce_for_material("ggx", 1.5, 0.2)
+    lut = np.ascontiguousarray(lut, np.float32)
+    cs = np.concatenate([rng.random(100000), [0.0, 1.0, 1e-8]]).astype(np.float32)
+    ref.mfref_cubic_interp_1d.argtypes = [C.c_size_t, f32p, f32p, C.c_size_t, C.c_float, C.c_float, f32p]
+    port.ppgo_rough_transmittance.argtypes = [C.c_size_t, f32p, f32p, f32p]
+    x = np.power(np.abs(cs), np.float32(0.25)).astype(np.float32)
+    a = np.zeros_like(cs); b = np.zeros_like(cs)
+    ref.mfref_cubic_interp_1d(len(cs), x.ctypes.data_as(f32p), lut.ctypes.data_as(f32p), len(lut), 0.0, 1.0, a.ctypes.data_as(f32p))
+    port.ppgo_rough_transmittance(len(cs), cs.ctypes.data_as(f32p), lut.ctypes.data_as(f32p), b.ctypes.data_as(f32p))
+    # (the abscissa |cos|^(1/4) is computed by numpy for the reference function and by libm's powf inside the restatement: equal in most cases, one ulp apart otherwise)
+    assert np.abs(np.clip(a, 0, 1) - b).max() <= 2e-6 and (np.clip(a, 0, 1) == b).mean() > 0.9
