@@ -1266,6 +1266,22 @@ struct CommitRec {   // GP:1713-1724 Vertex, minus the tree pointer (kept as bac
     F3 o, d, voxel, throughput, bsdfVal, radiance; float woPdf, bsdfPdf, dTreePdf; bool isDelta;
 };
 
+// Vertex::commit, GP:1730-1768 (restated; the reference's own struct Vertex is compiled verbatim into oracle/_ref and compared with this in tests/test_oracle_sdtree.py):
+// reject invalid records, radiance / throughput per channel where throughput * woPdf > Epsilon, product with the BSDF value, channel averages, then the spatial filter
+// (Backend::record: nearest / stochastic with the three jitter numbers `rnd` / box)
+template <class Backend>
+static inline void commit_vertex(Backend &tree, typename Backend::Leaf *leaf, const CommitRec &v, float statisticalWeight, int sfilter, int dfilter, int loss, const float rnd[3]) {
+    if (!(v.woPdf > 0) || !is_valid(v.radiance) || !is_valid(v.bsdfVal)) return;
+    F3 local = f3(0, 0, 0);
+    if (v.throughput.x * v.woPdf > kEpsilon) local.x = v.radiance.x / v.throughput.x;
+    if (v.throughput.y * v.woPdf > kEpsilon) local.y = v.radiance.y / v.throughput.y;
+    if (v.throughput.z * v.woPdf > kEpsilon) local.z = v.radiance.z / v.throughput.z;
+    const F3 product = local * v.bsdfVal;
+    const float avgLocal = (local.x + local.y + local.z) * (1.0f / 3.0f);      // Spectrum::average(): sum * (1/N)
+    const float avgProduct = (product.x + product.y + product.z) * (1.0f / 3.0f);
+    tree.record(leaf, &v.o.x, &v.voxel.x, &v.d.x, avgLocal, avgProduct, v.woPdf, v.bsdfPdf, v.dTreePdf, statisticalWeight, v.isDelta, sfilter, dfilter, loss, rnd);
+}
+
 template <class Backend> class Tracer {
 public:
     ppg_params prm; Scene sc; Backend tree; int nthreads;
@@ -1491,21 +1507,13 @@ public:
 
     // Vertex::commit, GP:1730-1768
     void commit(typename Backend::Leaf *leaf, const CommitRec &v, float statisticalWeight, int loss, uint64_t sampleIndex, uint32_t ordinal) {
-        if (!(v.woPdf > 0) || !is_valid(v.radiance) || !is_valid(v.bsdfVal)) return;
-        F3 local = f3(0, 0, 0);
-        if (v.throughput.x * v.woPdf > kEpsilon) local.x = v.radiance.x / v.throughput.x;
-        if (v.throughput.y * v.woPdf > kEpsilon) local.y = v.radiance.y / v.throughput.y;
-        if (v.throughput.z * v.woPdf > kEpsilon) local.z = v.radiance.z / v.throughput.z;
-        const F3 product = local * v.bsdfVal;
-        const float avgLocal = (local.x + local.y + local.z) * (1.0f / 3.0f);      // Spectrum::average(): sum * (1/N)
-        const float avgProduct = (product.x + product.y + product.z) * (1.0f / 3.0f);
+        if (!(v.woPdf > 0) || !is_valid(v.radiance) || !is_valid(v.bsdfVal)) return;        // (before the jitter numbers are drawn, like the reference's early return)
         float rnd[3] = {0, 0, 0};
         if (prm.spatial_filter == PPG_SFILTER_STOCHASTIC) {
             Pcg32 r; seed_vertex_rng(r, prm.seed, sampleIndex, ordinal);
             rnd[0] = r.next1D(); rnd[1] = r.next1D(); rnd[2] = r.next1D();
         }
-        tree.record(leaf, &v.o.x, &v.voxel.x, &v.d.x, avgLocal, avgProduct, v.woPdf, v.bsdfPdf, v.dTreePdf, statisticalWeight, v.isDelta,
-                    prm.spatial_filter, prm.directional_filter, loss, rnd);
+        commit_vertex(tree, leaf, v, statisticalWeight, prm.spatial_filter, prm.directional_filter, loss, rnd);
     }
 
     // renderBlock (GP:1587-1641) over every 32x32 block of one pass, OpenMP over blocks like the LocalWorkers

@@ -224,6 +224,34 @@ int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float
     return PPG_OK;
 }
 
+// Vertex::commit for n path vertices (sequential): leaf = the S-tree leaf of `o`.  verbatim != 0 runs the reference's OWN struct Vertex (reference backend only),
+// otherwise the restated commit_vertex of ppg_cpu_tracer.h.  arrays: o, d, throughput, bsdf_val, radiance, rnd: 3n; the pdfs, weight: n; is_delta: n (u8)
+int ppgo_tree_commit(ppgo_handle *h, size_t n, const float *o, const float *d, const float *throughput, const float *bsdf_val, const float *radiance,
+                     const float *wo_pdf, const float *bsdf_pdf, const float *dtree_pdf, const float *weight, const uint8_t *is_delta, const float *rnd,
+                     int sfilter, int dfilter, int loss, int verbatim) {
+    BackendT &T = h->T();
+#ifndef PPGO_BACKEND_REF
+    if (verbatim) return PPG_ERR_UNSUPPORTED;
+#endif
+    for (size_t i = 0; i < n; ++i) {
+        float voxel[3]; BackendT::Leaf *leaf = T.lookup(o + 3 * i, voxel);
+#ifdef PPGO_BACKEND_REF
+        if (verbatim) {
+            T.commitVerbatim(leaf, o + 3 * i, voxel, d + 3 * i, throughput + 3 * i, bsdf_val + 3 * i, radiance + 3 * i, wo_pdf[i], bsdf_pdf[i], dtree_pdf[i], is_delta[i] != 0,
+                             weight[i], sfilter, dfilter, loss, rnd + 3 * i);
+            continue;
+        }
+#endif
+        CommitRec v;
+        v.o = f3(o[3 * i], o[3 * i + 1], o[3 * i + 2]); v.d = f3(d[3 * i], d[3 * i + 1], d[3 * i + 2]); v.voxel = f3(voxel[0], voxel[1], voxel[2]);
+        v.throughput = f3(throughput[3 * i], throughput[3 * i + 1], throughput[3 * i + 2]); v.bsdfVal = f3(bsdf_val[3 * i], bsdf_val[3 * i + 1], bsdf_val[3 * i + 2]);
+        v.radiance = f3(radiance[3 * i], radiance[3 * i + 1], radiance[3 * i + 2]);
+        v.woPdf = wo_pdf[i]; v.bsdfPdf = bsdf_pdf[i]; v.dTreePdf = dtree_pdf[i]; v.isDelta = is_delta[i] != 0;
+        commit_vertex(T, leaf, v, weight[i], sfilter, dfilter, loss, rnd + 3 * i);
+    }
+    return PPG_OK;
+}
+
 // dumpSDTree: the .sdt file the reference itself writes for the tree in its current state (reference backend only: its own BlobWriter / dump code)
 int ppgo_tree_dump(ppgo_handle *h, const char *path, const float *cam_to_world) {
 #ifdef PPGO_BACKEND_REF

@@ -55,6 +55,10 @@ int ppgo_emitter_sample_direct(ppgo_handle *h, size_t n, const float *ref, const
 int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float *value_out /* 3n or NULL */);
 
 /* ---- SD-tree level operations (work on the handle's tree) */
+/* Vertex::commit (GP:1730-1768) for n vertices; verbatim != 0: the reference's own struct Vertex (reference backend only), else the restated commit_vertex */
+int ppgo_tree_commit(ppgo_handle *h, size_t n, const float *o, const float *d, const float *throughput, const float *bsdf_val, const float *radiance,
+                     const float *wo_pdf, const float *bsdf_pdf, const float *dtree_pdf, const float *weight, const uint8_t *is_delta, const float *rnd,
+                     int sfilter, int dfilter, int loss, int verbatim);
 /* dumpSDTree (GP:1191-1208) through the reference's own writer code; PPG_ERR_UNSUPPORTED on the restated backend */
 int ppgo_tree_dump(ppgo_handle *h, const char *path, const float *cam_to_world /* 16, row major */);
 int ppgo_tree_refine(ppgo_handle *h, uint64_t threshold, int max_mb);

@@ -50,6 +50,20 @@ struct RefBackend {
         } else t->record(Point(o[0], o[1], o[2]), Vector(voxel[0], voxel[1], voxel[2]), rec, df, ls);
     }
 
+    // Vertex::commit (GP:1730-1768) -- the reference's OWN code (struct Vertex is piped in verbatim after the SD-tree extract): validity test, radiance / throughput
+    // per channel above Epsilon, product with the BSDF value, the record, and the spatial-filter switch with its three jitter numbers
+    void commitVerbatim(Leaf *leaf, const float *o, const float *voxel, const float *d, const float *throughput, const float *bsdfVal, const float *radiance,
+                        float woPdf, float bsdfPdf, float dTreePdf, bool isDelta, float weight, int sfilter, int dfilter, int loss, const float *rnd) {
+        typedef mitsuba::EDirectionalFilter EDF; typedef mitsuba::EBsdfSamplingFractionLoss ELS; typedef mitsuba::ESpatialFilter ESF;
+        mitsuba::Vertex v;
+        v.dTree = leaf; v.dTreeVoxelSize = mitsuba::Vector(voxel[0], voxel[1], voxel[2]);
+        v.ray = mitsuba::Ray(mitsuba::Point(o[0], o[1], o[2]), mitsuba::Vector(d[0], d[1], d[2]), 0);
+        for (int c = 0; c < 3; ++c) { v.throughput[c] = throughput[c]; v.bsdfVal[c] = bsdfVal[c]; v.radiance[c] = radiance[c]; }
+        v.woPdf = woPdf; v.bsdfPdf = bsdfPdf; v.dTreePdf = dTreePdf; v.isDelta = isDelta;
+        RefSampler s; s.v = rnd; s.n = 3;
+        v.commit(*t, weight, sfilter == PPG_SFILTER_NEAREST ? ESF::ENearest : (sfilter == PPG_SFILTER_STOCHASTIC ? ESF::EStochasticBox : ESF::EBox),
+                 dfilter == 0 ? EDF::ENearest : EDF::EBox, loss == 0 ? ELS::ENone : (loss == 1 ? ELS::EKL : ELS::EVariance), &s);
+    }
     // dumpSDTree (GP:1191-1208) with the reference's own writers: BlobWriter (GP:35-57), STree::dump (GP:945-951), DTreeWrapper / DTree::dump (GP:699-711)
     bool dump(const char *path, const float cam[16]) const {
         { mitsuba::BlobWriter blob(path); for (int i = 0; i < 16; ++i) blob << (float) cam[i]; t->dump(blob); }

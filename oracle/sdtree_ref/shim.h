@@ -83,6 +83,23 @@ struct AABB {
     }
 };
 
+struct Ray {                                     /* core/ray.h: origin + direction is all Vertex::commit (GP:1730-1768) touches */
+    Point o; Vector d;
+    Ray() {}
+    Ray(const Point &o_, const Vector &d_, Float /* time */) : o(o_), d(d_) {}
+};
+struct Spectrum {                                /* TSpectrum<Float, 3> (core/spectrum.h): the members Vertex uses, with the reference's arithmetic (:467-486) */
+    Float s[3];
+    Spectrum() { s[0] = s[1] = s[2] = 0; }
+    Spectrum(Float v) { s[0] = s[1] = s[2] = v; }
+    Float &operator[](int i) { return s[i]; }
+    const Float &operator[](int i) const { return s[i]; }
+    Spectrum operator*(const Spectrum &o) const { Spectrum r; for (int i = 0; i < 3; ++i) r.s[i] = s[i] * o.s[i]; return r; }
+    Spectrum &operator+=(const Spectrum &o) { for (int i = 0; i < 3; ++i) s[i] += o.s[i]; return *this; }
+    bool isValid() const { for (int i = 0; i < 3; ++i) if (!std::isfinite(s[i]) || s[i] < 0.0f) return false; return true; }
+    Float average() const { Float result = 0.0f; for (int i = 0; i < 3; ++i) result += s[i]; return result * (1.0f / 3); }
+};
+
 class Sampler {
 public:
     virtual ~Sampler() {}

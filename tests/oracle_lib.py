@@ -42,6 +42,7 @@ def _declare(lib):
     lib.ppgo_emitter_sample_direct.argtypes = [H, C.c_size_t, f32p, f32p, f32p, C.c_int, f32p, f32p, f32p, f32p]
     lib.ppgo_env_pdf.argtypes = [H, C.c_size_t, f32p, f32p, f32p]
     lib.ppgo_tree_dump.argtypes = [H, C.c_char_p, f32p]
+    lib.ppgo_tree_commit.argtypes = [H, C.c_size_t] + [f32p] * 9 + [u8p, f32p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ppgo_tree_refine.argtypes = [H, C.c_uint64, C.c_int]
     lib.ppgo_tree_reset.argtypes = [H, C.c_int, C.c_float]
     lib.ppgo_tree_build.argtypes = [H]
@@ -213,6 +214,14 @@ class Oracle:
         rc = self.lib.ppgo_env_pdf(self.h, len(d), fptr(d), fptr(pdf), fptr(val))
         assert rc == 0, rc
         return pdf, val
+
+    def commit(self, o, d, throughput, bsdf_val, radiance, wo_pdf, bsdf_pdf, dtree_pdf, weight, is_delta, rnd, sfilter=0, dfilter=0, loss=0, verbatim=False):
+        """Vertex::commit for n vertices: the restated commit_vertex, or (verbatim, reference backend only) the reference's own struct Vertex."""
+        A = lambda a: np.ascontiguousarray(a, np.float32)
+        o, d, thr, bv, rad, wp, bp, dp, w, rnd = map(A, (o, d, throughput, bsdf_val, radiance, wo_pdf, bsdf_pdf, dtree_pdf, weight, rnd))
+        dl = np.ascontiguousarray(is_delta, np.uint8)
+        return self.lib.ppgo_tree_commit(self.h, len(wp), fptr(o), fptr(d), fptr(thr), fptr(bv), fptr(rad), fptr(wp), fptr(bp), fptr(dp), fptr(w),
+                                         dl.ctypes.data_as(C.POINTER(C.c_uint8)), fptr(rnd), sfilter, dfilter, loss, 1 if verbatim else 0)
 
     def dump(self, path, cam_to_world):
         """The .sdt file of the tree's current state, written by the reference's own code (reference backend only)."""

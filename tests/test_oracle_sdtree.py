@@ -175,3 +175,36 @@ def test_sdt_reader_reads_what_the_reference_writes(tmp_path):
     with pytest.raises(ValueError):
         sdt.read(tmp_path / "cut.sdt")
     assert O.Oracle(O.default_params(), aabb=AABB, kind="port").dump(tmp_path / "x.sdt", cam) == -6      # the restated backend has no writer of its own
+
+
+@needs_ref
+@pytest.mark.parametrize("sfilter,dfilter,loss", [(0, 0, 0), (1, 1, 1), (2, 1, 2), (1, 0, 0), (2, 0, 1)])
+def test_restated_commit_equals_the_reference_vertex_commit(sfilter, dfilter, loss):
+    """Vertex::commit (GP:1730-1768) -- validity test, radiance / throughput per channel above Epsilon, the product with the BSDF value, channel averages, the
+    spatial filters (nearest / stochastic with its three jitter numbers and the clip to the scene box / box) -- in the reference's OWN struct Vertex, compiled
+    verbatim into oracle/_ref, against the restated commit_vertex of the tracer: the same vertices, committed in the same order, must leave the same trees
+    bit for bit -- on the reference's trees and on the restated trees."""
+    rng = np.random.default_rng(40 + sfilter * 9 + dfilter * 3 + loss)
+    trees = {"verbatim": O.Oracle(O.default_params(), aabb=AABB, kind="ref"), "restated on ref trees": O.Oracle(O.default_params(), aabb=AABB, kind="ref"),
+             "restated on port trees": O.Oracle(O.default_params(), aabb=AABB, kind="port")}
+    for it in range(3):
+        n = 5000 * 2 ** it
+        pos, d, rad, prod, wo, bp, dp, rnd, delta = _records(n, 300 + it)
+        thr = (rng.lognormal(-1, 1.5, (n, 3))).astype(np.float32); bv = rng.random((n, 3)).astype(np.float32)
+        radiance = (thr * rng.lognormal(0, 1, (n, 3))).astype(np.float32)
+        # the cases the early return and the per-channel guard exist for
+        radiance[::97, 0] = np.nan; radiance[::89, 1] = -1.0; bv[::83, 2] = np.inf; wo[::79] = 0.0; wo[::73] = -0.5
+        thr[::71, 0] = 1e-6; thr[::67] = 0.0; thr[::61, 2] = 3e-5
+        weight = np.where(rng.random(n) < 0.3, 0.5, 1.0).astype(np.float32)
+        for name, o in trees.items():
+            o.refine(int(np.sqrt(2 ** it) * 300)); o.reset(20, 0.01)
+            assert o.commit(pos, d, thr, bv, radiance, wo, bp, dp, weight, delta, rnd, sfilter, dfilter, loss if it > 0 else 0, verbatim=(name == "verbatim")) == 0
+        ex = {name: o.export(1) for name, o in trees.items()}
+        for key in ("sums", "children", "tree_weight", "tree_sum", "adam", "s_children"):
+            a = ex["verbatim"][key]
+            for name in ("restated on ref trees", "restated on port trees"):
+                assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, ex[name][key].view(np.uint32) if a.dtype == np.float32 else ex[name][key]), (it, key, name)
+        assert ex["verbatim"]["tree_weight"].sum() > 0.1 * n                        # (the box filter spreads a record over the overlapped leaves by volume)
+        for o in trees.values():
+            o.build()
+    assert trees["restated on port trees"].commit(pos, d, thr, bv, radiance, wo, bp, dp, weight, delta, rnd, verbatim=True) == -6      # no reference code in the restated build
