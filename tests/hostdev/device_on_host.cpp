@@ -1,0 +1,41 @@
+// TEST INFRASTRUCTURE -- C entry points over the product's CUDA device functions compiled for the host (see cuda_host_shim.h); same shape as oracle/microfacet_ref/wrapper.h.
+#include "cuda_host_shim.h"
+#include "../../practical-path-guiding_b200/csrc/ppg_device.cuh"
+#include <cstddef>
+using namespace ppg;
+static inline float3 v3(const float *p, size_t i) { return make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+extern "C" {
+int dev_mf_eval(int type, float alpha, size_t n, const float *m, float *out) { for (size_t i = 0; i < n; ++i) out[i] = mf_eval(type, alpha, v3(m, i)); return 0; }
+int dev_mf_smith_g1(int type, float alpha, size_t n, const float *v, const float *m, float *out) { for (size_t i = 0; i < n; ++i) out[i] = mf_smithG1(type, alpha, v3(v, i), v3(m, i)); return 0; }
+int dev_mf_pdf(int type, float alpha, size_t n, const float *wi, const float *m, float *out) { for (size_t i = 0; i < n; ++i) out[i] = mf_pdfVisible(type, alpha, v3(wi, i), v3(m, i)); return 0; }
+int dev_mf_sample(int type, float alpha, size_t n, const float *wi, const float *sample, float *m_out, float *pdf_out) {
+    for (size_t i = 0; i < n; ++i) {
+        const float3 m = mf_sampleVisible(type, alpha, v3(wi, i), sample[2 * i], sample[2 * i + 1]);
+        m_out[3 * i] = m.x; m_out[3 * i + 1] = m.y; m_out[3 * i + 2] = m.z; pdf_out[i] = mf_pdfVisible(type, alpha, v3(wi, i), m);
+    }
+    return 0;
+}
+int dev_erf(size_t n, const float *x, float *erf_out, float *erfinv_out) { for (size_t i = 0; i < n; ++i) { erf_out[i] = mts_erf(x[i]); erfinv_out[i] = mts_erfinv(x[i]); } return 0; }
+int dev_fresnel_dielectric_ext(size_t n, const float *c, float eta, float *f_out, float *ct_out) { for (size_t i = 0; i < n; ++i) { float ct = 0; f_out[i] = fresnel_dielectric_ext(c[i], ct, eta); ct_out[i] = ct; } return 0; }
+int dev_fresnel_conductor_exact(size_t n, const float *c, const float eta[3], const float k[3], float *out) {
+    for (size_t i = 0; i < n; ++i) for (int ch = 0; ch < 3; ++ch) out[3 * i + ch] = fresnel_conductor_exact(c[i], eta[ch], k[ch]);
+    return 0;
+}
+int dev_coordinate_system(size_t n, const float *a, float *b_out, float *c_out) {
+    for (size_t i = 0; i < n; ++i) { float3 b, c; coordinate_system(v3(a, i), b, c); b_out[3 * i] = b.x; b_out[3 * i + 1] = b.y; b_out[3 * i + 2] = b.z; c_out[3 * i] = c.x; c_out[3 * i + 1] = c.y; c_out[3 * i + 2] = c.z; }
+    return 0;
+}
+int dev_square_to_cosine_hemisphere(size_t n, const float *s, float *out) { for (size_t i = 0; i < n; ++i) { const float3 v = square_to_cosine_hemisphere(s[2 * i], s[2 * i + 1]); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; } return 0; }
+// the kernels' triangle test on the accel rows ppg_set_scene packs: {n_u, n_v, n_d, bits(k)}, {a_u, a_v, b_nu, b_nv}, {c_nu, c_nv, -, -}
+int dev_tri_intersect(size_t n, const int *k, const float *consts /* 9n, TriAccel order */, const float *o, const float *d, const float *mint, const float *maxt, unsigned char *hit_out, float *tuv_out) {
+    for (size_t i = 0; i < n; ++i) {
+        const float *c = consts + 9 * i;
+        const float4 A = make_float4(c[0], c[1], c[2], __int_as_float(k[i])), B = make_float4(c[3], c[4], c[5], c[6]), C = make_float4(c[7], c[8], 0.f, 0.f);
+        float u = 0, v = 0, t = 0;
+        hit_out[i] = tri_intersect(A, B, C, v3(o, i), v3(d, i), mint[i], maxt[i], u, v, t) ? 1 : 0;
+        tuv_out[3 * i] = t; tuv_out[3 * i + 1] = u; tuv_out[3 * i + 2] = v;
+    }
+    return 0;
+}
+int dev_rough_transmittance(size_t n, const float *c, const float *values, float *out) { for (size_t i = 0; i < n; ++i) out[i] = rough_transmittance(values, c[i]); return 0; }
+}
