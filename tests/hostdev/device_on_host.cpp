@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE -- C entry points over the product's CUDA device functions compiled for the host (see cuda_host_shim.h); same shape as oracle/microfacet_ref/wrapper.h.
 #include "cuda_host_shim.h"
 #include "../../practical-path-guiding_b200/csrc/ppg_device.cuh"
+#include "../../include/ppg.h"
 #include <cstddef>
 using namespace ppg;
 static inline float3 v3(const float *p, size_t i) { return make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
@@ -34,6 +35,41 @@ int dev_tri_intersect(size_t n, const int *k, const float *consts /* 9n, TriAcce
         float u = 0, v = 0, t = 0;
         hit_out[i] = tri_intersect(A, B, C, v3(o, i), v3(d, i), mint[i], maxt[i], u, v, t) ? 1 : 0;
         tuv_out[3 * i] = t; tuv_out[3 * i + 1] = u; tuv_out[3 * i + 2] = v;
+    }
+    return 0;
+}
+// ---- whole BSDF models: the device Bsdf record as load_bsdf() rebuilds it from the 28 floats ppg_set_scene packs per material (ppg_host.cu: "bsdf" table)
+static Bsdf make_bsdf(const ppg_bsdf &m, const float *tables) {
+    Bsdf b; b.refl = make_float3(m.reflectance[0], m.reflectance[1], m.reflectance[2]);
+    b.type = (uint32_t) m.type; b.flags = m.flags & 0xffffffu;
+    if (m.type == PPG_BSDF_NULL_BLACK) { b.refl = make_float3(0, 0, 0); b.type = PPG_BSDF_T_DIFFUSE; }
+    b.trans = b.etaRgb = b.k = b.specRefl = make_float3(0, 0, 0); b.eta = b.invEta = 1.f; b.alpha = 0.1f; b.distr = 1; b.fdrInt = b.ssw = 0.f; b.lut = nullptr;
+    b.opacity = make_float3(1, 1, 1); b.maskProb = 1.f; b.reflTex = b.bumpTex = 0u;
+    if (b.flags & PPG_BSDF_MASK) { b.opacity = make_float3(m.opacity[0], m.opacity[1], m.opacity[2]); b.maskProb = m.opacity[0] * 0.212671f + m.opacity[1] * 0.715160f + m.opacity[2] * 0.072169f; }
+    if (b.type != PPG_BSDF_T_DIFFUSE) {
+        b.trans = make_float3(m.specular_transmittance[0], m.specular_transmittance[1], m.specular_transmittance[2]); b.eta = m.eta[0];
+        b.etaRgb = make_float3(m.eta[0], m.eta[1], m.eta[2]); b.invEta = m.eta[0] != 0.f ? 1.0f / m.eta[0] : 0.f; b.k = make_float3(m.k[0], m.k[1], m.k[2]);
+        b.alpha = std::max(m.alpha, 1e-4f); b.distr = m.distribution == PPG_MICROFACET_BECKMANN ? 0 : 1;
+        if (b.type == PPG_BSDF_T_ROUGHPLASTIC || b.type == PPG_BSDF_T_PLASTIC) {
+            b.specRefl = make_float3(m.specular_reflectance[0], m.specular_reflectance[1], m.specular_reflectance[2]); b.fdrInt = m.fdr_int; b.ssw = m.specular_sampling_weight;
+            b.lut = tables ? tables + (size_t) std::max(m.table, 0) * PPG_BSDF_LUT : nullptr;
+        }
+    }
+    return b;
+}
+int dev_bsdf_eval_pdf(const ppg_bsdf *m, size_t n, const float *wi, const float *wo, float *eval_out, float *pdf_out, const float *tables) {
+    const Bsdf b = make_bsdf(*m, tables);
+    for (size_t i = 0; i < n; ++i) { const float3 e = bsdf_eval(b, v3(wi, i), v3(wo, i)); eval_out[3 * i] = e.x; eval_out[3 * i + 1] = e.y; eval_out[3 * i + 2] = e.z; pdf_out[i] = bsdf_pdf(b, v3(wi, i), v3(wo, i)); }
+    return 0;
+}
+int dev_bsdf_sample(const ppg_bsdf *m, size_t n, const float *wi, const float *sample, float *wo_out, float *weight_out, float *pdf_out, unsigned char *delta_out, const float *tables) {
+    const Bsdf b = make_bsdf(*m, tables);
+    for (size_t i = 0; i < n; ++i) {
+        float3 wo = make_float3(0, 0, 0); float eta = 1.f, pdf = 0.f; bool delta = false, isNull = false;
+        Pcg32 extra; extra.seed(splitmix64(i), i);                      // like ppgo_bsdf_sample: the model's own draws from the path sampler (roughdielectric)
+        const float3 w = bsdf_sample(b, v3(wi, i), sample[2 * i], sample[2 * i + 1], wo, eta, delta, pdf, extra, isNull);
+        wo_out[3 * i] = wo.x; wo_out[3 * i + 1] = wo.y; wo_out[3 * i + 2] = wo.z; weight_out[3 * i] = w.x; weight_out[3 * i + 1] = w.y; weight_out[3 * i + 2] = w.z;
+        pdf_out[i] = pdf; if (delta_out) delta_out[i] = delta ? 1 : 0;
     }
     return 0;
 }

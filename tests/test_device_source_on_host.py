@@ -125,3 +125,57 @@ def test_device_triangle_test_and_transmittance_sources_equal_the_reference(dev)
     port = O.load("port"); port.ppgo_rough_transmittance.argtypes = [C.c_size_t, f32p, f32p, f32p]
     port.ppgo_rough_transmittance(len(cs), cs.ctypes.data_as(f32p), lut.ctypes.data_as(f32p), b.ctypes.data_as(f32p))
     assert np.array_equal(a, b)                                                     # (the oracle's lookup is itself checked against evalCubicInterp1D, tests/test_oracle_bsdf.py)
+
+
+def _materials():
+    """Every BSDF model of the hot path with the wrappers that change its arithmetic: (name, ppg_bsdf, tables)."""
+    from ppg_b200 import scene as S
+    out = []
+    mk = lambda **kw: O.make_bsdf(**kw)
+    out.append(("diffuse", mk(type=0, reflectance=(0.6, 0.5, 0.4)), None))
+    out.append(("diffuse twosided", mk(type=0, flags=1, reflectance=(0.6, 0.5, 0.4)), None))
+    out.append(("black (emitter without a BSDF)", mk(type=1, reflectance=(0, 0, 0)), None))      # (the loaders hand NULL_BLACK over with zero reflectance)
+    out.append(("dielectric bk7", mk(type=2, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5046 / 1.000277,) * 3), None))
+    out.append(("conductor", mk(type=3, reflectance=(1, 1, 1), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2)), None))
+    out.append(("roughconductor ggx 0.1 twosided", mk(type=4, flags=1, reflectance=(1, 1, 1), eta=(1.65746, 0.880369, 0.521229), k=(9.22387, 6.26952, 4.837), alpha=0.1, distribution=1), None))
+    out.append(("roughconductor beckmann 0.3", mk(type=4, reflectance=(0.9, 0.9, 0.9), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), alpha=0.3, distribution=0), None))
+    out.append(("roughdielectric ggx 0.1", mk(type=6, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5,) * 3, alpha=0.1, distribution=1), None))
+    out.append(("roughdielectric beckmann 0.3 tinted", mk(type=6, reflectance=(0.9, 0.8, 1), transmittance=(0.7, 0.9, 1), eta=(1.33,) * 3, alpha=0.3, distribution=0), None))
+    out.append(("thindielectric", mk(type=8, reflectance=(1, 1, 1), transmittance=(0.9, 0.95, 1), eta=(1.5,) * 3), None))
+    for name, args in (("roughplastic ggx 0.2", (0, (0.256, 0.013, 0.08), (1, 1, 1), 1.5 / 1.000277, 0.2, 1, False)), ("roughplastic beckmann 0.4 nonlinear twosided", (1, (0.5, 0.4, 0.3), (0.9, 0.9, 0.9), 1.49, 0.4, 0, True))):
+        tables = []
+        row = S.make_roughplastic(*args, tables)
+        out.append((name, O.bsdf_from_row(row), np.ascontiguousarray(tables, np.float32)))
+    out.append(("plastic nonlinear", O.bsdf_from_row(S.make_plastic(0, (0.6, 0.3, 0.2), (1, 1, 1), 1.49, True)), None))
+    out.append(("plastic twosided", O.bsdf_from_row(S.make_plastic(1, (0.2, 0.3, 0.6), (0.8, 0.8, 0.8), 1.9, False)), None))
+    m = mk(type=0, flags=1 | 4, reflectance=(0.6, 0.5, 0.4)); m.opacity[0], m.opacity[1], m.opacity[2] = 0.6, 0.5, 0.7
+    out.append(("mask over twosided diffuse", m, None))
+    m = mk(type=4, flags=4, reflectance=(1, 1, 1), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), alpha=0.2, distribution=1); m.opacity[0], m.opacity[1], m.opacity[2] = 0.3, 0.3, 0.3
+    out.append(("mask over roughconductor", m, None))
+    return out
+
+
+@pytest.mark.parametrize("name,b,tables", _materials(), ids=[m[0] for m in _materials()])
+def test_device_bsdf_sources_equal_the_oracle(dev, name, b, tables):
+    """bsdf_eval / bsdf_pdf / bsdf_sample of csrc/ppg_device.cuh (host-compiled) against the oracle's restatement of the same Mitsuba models, on the same directions and
+    random numbers: every value bit for bit -- eval and pdf on 10^5 direction pairs over the whole sphere (both sides of the surface), sampling on 10^5 (wi, u) pairs
+    incl. the model's own extra draw (roughdielectric) and the delta / null lobes."""
+    rng = np.random.default_rng(abs(hash(name)) % 2 ** 31); n = 100000
+    wi, wo = _dirs(rng, n, False), _dirs(rng, n, False)
+    wi[:200, 2] = np.abs(wi[:200, 2]) * 1e-3; wi[:200] /= np.linalg.norm(wi[:200], axis=1, keepdims=True)         # grazing incidence
+    wo[200:1200] = wi[200:1200] * [-1, -1, 1]                                                                    # the mirror direction (delta lobes evaluate to 0 without the discrete measure)
+    tp = tables.ctypes.data_as(f32p) if tables is not None else None
+    ev = np.zeros((n, 3), np.float32); pd = np.zeros(n, np.float32)
+    dev.dev_bsdf_eval_pdf.argtypes = [C.POINTER(type(b)), C.c_size_t, f32p, f32p, f32p, f32p, f32p]
+    dev.dev_bsdf_eval_pdf(C.byref(b), n, wi.ctypes.data_as(f32p), wo.ctypes.data_as(f32p), ev.ctypes.data_as(f32p), pd.ctypes.data_as(f32p), tp)
+    ev0, pd0 = O.bsdf_eval_pdf(b, wi, wo, tables=tables)
+    assert np.array_equal(ev.view(np.uint32), ev0.view(np.uint32)) and np.array_equal(pd.view(np.uint32), pd0.view(np.uint32))
+    smp = rng.random((n, 2), dtype=np.float32)
+    so = np.zeros((n, 3), np.float32); sw = np.zeros((n, 3), np.float32); sp = np.zeros(n, np.float32); sd = np.zeros(n, np.uint8)
+    dev.dev_bsdf_sample.argtypes = [C.POINTER(type(b)), C.c_size_t, f32p, f32p, f32p, f32p, f32p, C.POINTER(C.c_ubyte), f32p]
+    dev.dev_bsdf_sample(C.byref(b), n, wi.ctypes.data_as(f32p), smp.ctypes.data_as(f32p), so.ctypes.data_as(f32p), sw.ctypes.data_as(f32p), sp.ctypes.data_as(f32p), sd.ctypes.data_as(C.POINTER(C.c_ubyte)), tp)
+    so0, sw0, sp0, sd0 = O.bsdf_sample(b, wi, smp, tables=tables)
+    lit = (sw0 != 0).any(axis=1)                                                    # a failed sample carries weight 0; its wo is unspecified on both sides
+    assert np.array_equal(lit, (sw != 0).any(axis=1)) and (lit.mean() > 0.2 or b.type == 1)
+    assert np.array_equal(sw[lit].view(np.uint32), sw0[lit].view(np.uint32)) and np.array_equal(so[lit].view(np.uint32), so0[lit].view(np.uint32))
+    assert np.array_equal(sp[lit].view(np.uint32), sp0[lit].view(np.uint32)) and np.array_equal(sd[lit], sd0[lit])
