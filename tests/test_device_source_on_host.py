@@ -116,6 +116,8 @@ def test_device_triangle_test_and_transmittance_sources_equal_the_reference(dev)
     dev.dev_tri_intersect(n, k.ctypes.data_as(C.POINTER(C.c_int)), c9.ctypes.data_as(f32p), arrs[3].ctypes.data_as(f32p), arrs[4].ctypes.data_as(f32p), mint.ctypes.data_as(f32p),
                           maxt.ctypes.data_as(f32p), hit2.ctypes.data_as(C.POINTER(C.c_ubyte)), tuv2.ctypes.data_as(f32p))
     assert 0.1 < hit.mean() < 0.5 and np.array_equal(hit, hit2) and np.array_equal(tuv[hit == 1], tuv2[hit == 1])
+    if not __import__("os").path.exists("/root/reference/mitsuba/data/microfacet/ggx.dat"):
+        return                                                              # (the table comes from the reference's data files)
     from ppg_b200 import rtrans
     lut, _ = rtrans.reduce_for_material("beckmann", 1.49, 0.1); lut = np.ascontiguousarray(lut, np.float32)
     cs = np.concatenate([rng.uniform(-0.2, 1, 100000), [0.0, 1.0]]).astype(np.float32)
@@ -127,40 +129,53 @@ def test_device_triangle_test_and_transmittance_sources_equal_the_reference(dev)
     assert np.array_equal(a, b)                                                     # (the oracle's lookup is itself checked against evalCubicInterp1D, tests/test_oracle_bsdf.py)
 
 
-def _materials():
-    """Every BSDF model of the hot path with the wrappers that change its arithmetic: (name, ppg_bsdf, tables)."""
+def _material(name):
+    """One BSDF configuration of the hot path with the wrappers that change its arithmetic: (ppg_bsdf, tables).  Built inside the test: the
+    rough-plastic tables are reduced from the reference's data files, which exist only where /root/reference does."""
     from ppg_b200 import scene as S
-    out = []
     mk = lambda **kw: O.make_bsdf(**kw)
-    out.append(("diffuse", mk(type=0, reflectance=(0.6, 0.5, 0.4)), None))
-    out.append(("diffuse twosided", mk(type=0, flags=1, reflectance=(0.6, 0.5, 0.4)), None))
-    out.append(("black (emitter without a BSDF)", mk(type=1, reflectance=(0, 0, 0)), None))      # (the loaders hand NULL_BLACK over with zero reflectance)
-    out.append(("dielectric bk7", mk(type=2, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5046 / 1.000277,) * 3), None))
-    out.append(("conductor", mk(type=3, reflectance=(1, 1, 1), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2)), None))
-    out.append(("roughconductor ggx 0.1 twosided", mk(type=4, flags=1, reflectance=(1, 1, 1), eta=(1.65746, 0.880369, 0.521229), k=(9.22387, 6.26952, 4.837), alpha=0.1, distribution=1), None))
-    out.append(("roughconductor beckmann 0.3", mk(type=4, reflectance=(0.9, 0.9, 0.9), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), alpha=0.3, distribution=0), None))
-    out.append(("roughdielectric ggx 0.1", mk(type=6, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5,) * 3, alpha=0.1, distribution=1), None))
-    out.append(("roughdielectric beckmann 0.3 tinted", mk(type=6, reflectance=(0.9, 0.8, 1), transmittance=(0.7, 0.9, 1), eta=(1.33,) * 3, alpha=0.3, distribution=0), None))
-    out.append(("thindielectric", mk(type=8, reflectance=(1, 1, 1), transmittance=(0.9, 0.95, 1), eta=(1.5,) * 3), None))
-    for name, args in (("roughplastic ggx 0.2", (0, (0.256, 0.013, 0.08), (1, 1, 1), 1.5 / 1.000277, 0.2, 1, False)), ("roughplastic beckmann 0.4 nonlinear twosided", (1, (0.5, 0.4, 0.3), (0.9, 0.9, 0.9), 1.49, 0.4, 0, True))):
+    if name in ROUGHPLASTICS:
+        if not os.path.exists("/root/reference/mitsuba/data/microfacet/ggx.dat"):
+            pytest.skip("the rough-transmittance tables of the reference are not present")
         tables = []
-        row = S.make_roughplastic(*args, tables)
-        out.append((name, O.bsdf_from_row(row), np.ascontiguousarray(tables, np.float32)))
-    out.append(("plastic nonlinear", O.bsdf_from_row(S.make_plastic(0, (0.6, 0.3, 0.2), (1, 1, 1), 1.49, True)), None))
-    out.append(("plastic twosided", O.bsdf_from_row(S.make_plastic(1, (0.2, 0.3, 0.6), (0.8, 0.8, 0.8), 1.9, False)), None))
-    m = mk(type=0, flags=1 | 4, reflectance=(0.6, 0.5, 0.4)); m.opacity[0], m.opacity[1], m.opacity[2] = 0.6, 0.5, 0.7
-    out.append(("mask over twosided diffuse", m, None))
-    m = mk(type=4, flags=4, reflectance=(1, 1, 1), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), alpha=0.2, distribution=1); m.opacity[0], m.opacity[1], m.opacity[2] = 0.3, 0.3, 0.3
-    out.append(("mask over roughconductor", m, None))
-    return out
+        row = S.make_roughplastic(*ROUGHPLASTICS[name], tables)
+        return O.bsdf_from_row(row), np.ascontiguousarray(tables, np.float32)
+    if name == "plastic nonlinear":
+        return O.bsdf_from_row(S.make_plastic(0, (0.6, 0.3, 0.2), (1, 1, 1), 1.49, True)), None
+    if name == "plastic twosided":
+        return O.bsdf_from_row(S.make_plastic(1, (0.2, 0.3, 0.6), (0.8, 0.8, 0.8), 1.9, False)), None
+    if name.startswith("mask"):
+        m = mk(type=0, flags=1 | 4, reflectance=(0.6, 0.5, 0.4)) if "diffuse" in name else mk(type=4, flags=4, reflectance=(1, 1, 1), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), alpha=0.2, distribution=1)
+        op = (0.6, 0.5, 0.7) if "diffuse" in name else (0.3, 0.3, 0.3)
+        m.opacity[0], m.opacity[1], m.opacity[2] = op
+        return m, None
+    return mk(**SIMPLE[name]), None
 
 
-@pytest.mark.parametrize("name,b,tables", _materials(), ids=[m[0] for m in _materials()])
-def test_device_bsdf_sources_equal_the_oracle(dev, name, b, tables):
+SIMPLE = {
+    "diffuse": dict(type=0, reflectance=(0.6, 0.5, 0.4)),
+    "diffuse twosided": dict(type=0, flags=1, reflectance=(0.6, 0.5, 0.4)),
+    "black (emitter without a BSDF)": dict(type=1, reflectance=(0, 0, 0)),                 # (the loaders hand NULL_BLACK over with zero reflectance)
+    "dielectric bk7": dict(type=2, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5046 / 1.000277,) * 3),
+    "conductor": dict(type=3, reflectance=(1, 1, 1), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2)),
+    "roughconductor ggx 0.1 twosided": dict(type=4, flags=1, reflectance=(1, 1, 1), eta=(1.65746, 0.880369, 0.521229), k=(9.22387, 6.26952, 4.837), alpha=0.1, distribution=1),
+    "roughconductor beckmann 0.3": dict(type=4, reflectance=(0.9, 0.9, 0.9), eta=(0.2, 0.9, 1.1), k=(3.9, 2.4, 2.2), alpha=0.3, distribution=0),
+    "roughdielectric ggx 0.1": dict(type=6, reflectance=(1, 1, 1), transmittance=(1, 1, 1), eta=(1.5,) * 3, alpha=0.1, distribution=1),
+    "roughdielectric beckmann 0.3 tinted": dict(type=6, reflectance=(0.9, 0.8, 1), transmittance=(0.7, 0.9, 1), eta=(1.33,) * 3, alpha=0.3, distribution=0),
+    "thindielectric": dict(type=8, reflectance=(1, 1, 1), transmittance=(0.9, 0.95, 1), eta=(1.5,) * 3),
+}
+ROUGHPLASTICS = {"roughplastic ggx 0.2": (0, (0.256, 0.013, 0.08), (1, 1, 1), 1.5 / 1.000277, 0.2, 1, False),
+                 "roughplastic beckmann 0.4 nonlinear twosided": (1, (0.5, 0.4, 0.3), (0.9, 0.9, 0.9), 1.49, 0.4, 0, True)}
+MATERIALS = list(SIMPLE) + list(ROUGHPLASTICS) + ["plastic nonlinear", "plastic twosided", "mask over twosided diffuse", "mask over roughconductor"]
+
+
+@pytest.mark.parametrize("name", MATERIALS)
+def test_device_bsdf_sources_equal_the_oracle(dev, name):
     """bsdf_eval / bsdf_pdf / bsdf_sample of csrc/ppg_device.cuh (host-compiled) against the oracle's restatement of the same Mitsuba models, on the same directions and
     random numbers: every value bit for bit -- eval and pdf on 10^5 direction pairs over the whole sphere (both sides of the surface), sampling on 10^5 (wi, u) pairs
     incl. the model's own extra draw (roughdielectric) and the delta / null lobes."""
-    rng = np.random.default_rng(abs(hash(name)) % 2 ** 31); n = 100000
+    b, tables = _material(name)
+    rng = np.random.default_rng(MATERIALS.index(name)); n = 100000
     wi, wo = _dirs(rng, n, False), _dirs(rng, n, False)
     wi[:200, 2] = np.abs(wi[:200, 2]) * 1e-3; wi[:200] /= np.linalg.norm(wi[:200], axis=1, keepdims=True)         # grazing incidence
     wo[200:1200] = wi[200:1200] * [-1, -1, 1]                                                                    # the mirror direction (delta lobes evaluate to 0 without the discrete measure)
