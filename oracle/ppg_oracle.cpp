@@ -212,6 +212,18 @@ int ppgo_emitter_sample_direct(ppgo_handle *h, size_t n, const float *ref, const
     }
     return PPG_OK;
 }
+// Texture2D::eval / evalGradient of texture `tex` of the handle's scene at n texture coordinates (the per-vertex uv BEFORE the texture's own scale / offset):
+// rgb_out 3n (BitmapTexture::eval -> evalBilinear level 0), grad_out 2n (the luminances of d/du, d/dv that BumpMap::getFrame uses)
+int ppgo_texture_eval(ppgo_handle *h, uint32_t tex, size_t n, const float *uv, float *rgb_out, float *grad_out) {
+    if (!h->tracer || tex >= h->tracer->sc.textures.size()) return PPG_ERR_INVALID_ARGUMENT;
+    const Scene &sc = h->tracer->sc;
+    for (size_t i = 0; i < n; ++i) {
+        const F3 c = sc.evalTexture(tex, uv[2 * i], uv[2 * i + 1]);
+        rgb_out[3 * i] = c.x; rgb_out[3 * i + 1] = c.y; rgb_out[3 * i + 2] = c.z;
+        sc.evalTextureGradientLum(tex, uv[2 * i], uv[2 * i + 1], grad_out[2 * i], grad_out[2 * i + 1]);
+    }
+    return PPG_OK;
+}
 // Scene::pdfEmitterDirect of the environment emitter for n world directions, and its radiance there (evalEnvironment)
 int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float *value_out) {
     if (!h->tracer || !h->tracer->sc.hasEnvironment()) return PPG_ERR_NO_SCENE;

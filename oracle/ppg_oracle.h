@@ -53,6 +53,8 @@ int ppgo_rough_transmittance(size_t n, const float *cosTheta, const float *value
 int ppgo_emitter_sample_direct(ppgo_handle *h, size_t n, const float *ref, const float *ref_n, const float *sample, int max_interactions,
                                float *d_out, float *value_out, float *pdf_out, float *dist_out);
 int ppgo_env_pdf(ppgo_handle *h, size_t n, const float *d, float *pdf_out, float *value_out /* 3n or NULL */);
+/* bitmap texture `tex` of the handle's scene at n uv pairs: bilinear value (3n) and the luminance gradient the bump map uses (2n) */
+int ppgo_texture_eval(ppgo_handle *h, uint32_t tex, size_t n, const float *uv, float *rgb_out, float *grad_out);
 
 /* ---- SD-tree level operations (work on the handle's tree) */
 /* Vertex::commit (GP:1730-1768) for n vertices; verbatim != 0: the reference's own struct Vertex (reference backend only), else the restated commit_vertex */

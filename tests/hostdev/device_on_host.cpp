@@ -3,6 +3,7 @@
 #include "../../practical-path-guiding_b200/csrc/ppg_device.cuh"
 #include "../../include/ppg.h"
 #include <cstddef>
+#include <vector>
 using namespace ppg;
 static inline float3 v3(const float *p, size_t i) { return make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
 extern "C" {
@@ -70,6 +71,27 @@ int dev_bsdf_sample(const ppg_bsdf *m, size_t n, const float *wi, const float *s
         const float3 w = bsdf_sample(b, v3(wi, i), sample[2 * i], sample[2 * i + 1], wo, eta, delta, pdf, extra, isNull);
         wo_out[3 * i] = wo.x; wo_out[3 * i + 1] = wo.y; wo_out[3 * i + 2] = wo.z; weight_out[3 * i] = w.x; weight_out[3 * i + 1] = w.y; weight_out[3 * i + 2] = w.z;
         pdf_out[i] = pdf; if (delta_out) delta_out[i] = delta ? 1 : 0;
+    }
+    return 0;
+}
+// bitmap textures: one ppg_texture packed the way ppg_set_scene packs it (uint2 {r | g << 16, b} per texel, two float4 of meta), then tex_eval / tex_gradient_lum
+int dev_texture_eval(const ppg_texture *t, const uint16_t *texels /* the whole texel array of the scene */, size_t n, const float *uv, float *rgb_out, float *grad_out) {
+    const size_t nTexels = (size_t) t->width * t->height;
+    std::vector<uint2> tex(nTexels);
+    const uint16_t *src = texels + t->first_texel;
+    for (size_t i = 0; i < nTexels; ++i) {
+        const uint16_t r = src[i * t->channels], g = t->channels == 3 ? src[i * t->channels + 1] : r, b = t->channels == 3 ? src[i * t->channels + 2] : r;
+        tex[i] = make_uint2((uint32_t) r | ((uint32_t) g << 16), (uint32_t) b);
+    }
+    float4 meta[2];
+    const uint32_t wr = t->wrap_u | (t->wrap_v << 8);
+    meta[0] = make_float4(__uint_as_float(t->width), __uint_as_float(t->height), __uint_as_float(wr), __uint_as_float(0u));
+    meta[1] = make_float4(t->uv_scale[0], t->uv_scale[1], t->uv_offset[0], t->uv_offset[1]);
+    SceneView sc; memset(&sc, 0, sizeof(sc)); sc.texMeta = meta; sc.texels = tex.data(); sc.nTextures = 1;
+    for (size_t i = 0; i < n; ++i) {
+        const float2 q = make_float2(uv[2 * i], uv[2 * i + 1]);
+        const float3 c = tex_eval(sc, 0u, q); const float2 g = tex_gradient_lum(sc, 0u, q);
+        rgb_out[3 * i] = c.x; rgb_out[3 * i + 1] = c.y; rgb_out[3 * i + 2] = c.z; grad_out[2 * i] = g.x; grad_out[2 * i + 1] = g.y;
     }
     return 0;
 }

@@ -194,3 +194,27 @@ def test_device_bsdf_sources_equal_the_oracle(dev, name):
     assert np.array_equal(lit, (sw != 0).any(axis=1)) and (lit.mean() > 0.2 or b.type == 1)
     assert np.array_equal(sw[lit].view(np.uint32), sw0[lit].view(np.uint32)) and np.array_equal(so[lit].view(np.uint32), so0[lit].view(np.uint32))
     assert np.array_equal(sp[lit].view(np.uint32), sp0[lit].view(np.uint32)) and np.array_equal(sd[lit], sd0[lit])
+
+
+def test_device_texture_source_equals_the_oracle(dev):
+    """tex_eval (BitmapTexture::eval -> TMIPMap::evalBilinear, level 0) and tex_gradient_lum (evalGradientBilinear -> the luminances BumpMap::getFrame uses) of the
+    device source on the textures of the cbox-textured fixture (RGB and one-channel, repeat / clamp / mirror wrapping, uv scale and offset), packed the way
+    ppg_set_scene packs them, against the oracle's texture code at 10^5 texture coordinates reaching far outside [0, 1]^2: bit for bit."""
+    from common import load_fixture_scene
+    from ppg_b200 import capi
+    sc = load_fixture_scene("cbox-textured")
+    o = O.Oracle(O.params_from_xml(sc.integrator), sc, kind="port")
+    lib = O.load("port"); lib.ppgo_texture_eval.argtypes = [C.c_void_p, C.c_uint32, C.c_size_t, f32p, f32p, f32p]
+    arrays = o.scene_arrays
+    rng = np.random.default_rng(17); n = 100000
+    uv = (rng.random((n, 2)) * 6 - 2.5).astype(np.float32); uv[:4] = [[0, 0], [1, 1], [0.5, 0.5], [np.nan, 0.3]]
+    dev.dev_texture_eval.argtypes = [C.POINTER(capi.PpgTexture), C.POINTER(C.c_uint16), C.c_size_t, f32p, f32p, f32p]
+    assert len(sc.textures) == 3
+    for k in range(len(sc.textures)):
+        a = np.zeros((n, 3), np.float32); ga = np.zeros((n, 2), np.float32); b = np.zeros((n, 3), np.float32); gb = np.zeros((n, 2), np.float32)
+        assert lib.ppgo_texture_eval(o.h, k, n, uv.ctypes.data_as(f32p), a.ctypes.data_as(f32p), ga.ctypes.data_as(f32p)) == 0
+        t = capi.PpgTexture.from_buffer_copy(np.ascontiguousarray(sc.textures[k:k + 1]).tobytes())
+        texels = np.ascontiguousarray(sc.texels, np.uint16)
+        dev.dev_texture_eval(C.byref(t), texels.ctypes.data_as(C.POINTER(C.c_uint16)), n, uv.ctypes.data_as(f32p), b.ctypes.data_as(f32p), gb.ctypes.data_as(f32p))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ga.view(np.uint32), gb.view(np.uint32)), k
+        assert np.abs(a[4:]).max() > 0.1 and np.abs(ga[4:]).max() > 0
