@@ -8,12 +8,15 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <sstream>
 #include <string>
+#include <vector>
 
 #define MTS_NAMESPACE_BEGIN namespace mitsuba {
 #define MTS_NAMESPACE_END }
 #define MTS_EXPORT_CORE
 #define FINLINE inline
+#define SAssert(cond) do { } while (0)
 #define SLog(level, ...) do { if ((level) >= mitsuba::EError) { std::fprintf(stderr, __VA_ARGS__); std::fprintf(stderr, "\n"); } } while (0)
 #ifndef M_PI
 #define M_PI 3.14159265358979323846

@@ -69,6 +69,16 @@ int mfref_cubic_interp_1d(size_t n, const float *x, const float *values, size_t 
     for (size_t i = 0; i < n; ++i) out[i] = mitsuba::evalCubicInterp1D(x[i], values, size, mn, mx, false);
     return 0;
 }
+// ---- DiscreteDistribution (include/mitsuba/core/pmf.h:35-210): append / normalize / sample / sampleReuse -- the emitter choice and the per-emitter triangle choice
+int mfref_discrete(size_t n_entries, const float *weights, size_t n, const float *sample, float *pdf_out /* n_entries: the normalised entries */, float *sum_out,
+                   unsigned *index_out, float *reused_out) {
+    mitsuba::DiscreteDistribution d(n_entries);
+    for (size_t i = 0; i < n_entries; ++i) d.append(weights[i]);
+    *sum_out = d.normalize();
+    for (size_t i = 0; i < n_entries; ++i) pdf_out[i] = d[i];
+    for (size_t i = 0; i < n; ++i) { mitsuba::Float s = sample[i]; index_out[i] = (unsigned) d.sampleReuse(s); reused_out[i] = s; }
+    return 0;
+}
 int mfref_erf(size_t n, const float *x, float *erf_out, float *erfinv_out) {
     for (size_t i = 0; i < n; ++i) { erf_out[i] = mitsuba::math::erf(x[i]); erfinv_out[i] = mitsuba::math::erfinv(x[i]); }
     return 0;

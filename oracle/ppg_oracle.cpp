@@ -191,6 +191,20 @@ int ppgo_rough_transmittance(size_t n, const float *cosTheta, const float *value
     for (size_t i = 0; i < n; ++i) out[i] = rough_transmittance(values, cosTheta[i]);
     return PPG_OK;
 }
+// the discrete distributions of the light sampling as the tracer builds and uses them: cumulative weights normalised like DiscreteDistribution::normalize
+// (Scene::buildEmitterSamplers), Scene::cdfSample, and the sample reuse of sample_emitter_direct
+int ppgo_discrete(size_t n_entries, const float *weights, size_t n, const float *sample, float *pdf_out, float *sum_out, unsigned *index_out, float *reused_out) {
+    std::vector<float> cdf(1, 0.0f);
+    for (size_t i = 0; i < n_entries; ++i) cdf.push_back(cdf.back() + weights[i]);
+    const float sum = cdf.back(); *sum_out = sum;
+    if (sum > 0) { const float nrm = 1.0f / sum; for (size_t i = 1; i < cdf.size(); ++i) cdf[i] *= nrm; cdf.back() = 1.0f; }
+    for (size_t i = 0; i < n_entries; ++i) pdf_out[i] = cdf[i + 1] - cdf[i];
+    for (size_t i = 0; i < n; ++i) {
+        const size_t k = Scene::cdfSample(cdf, sample[i]);
+        index_out[i] = (unsigned) k; reused_out[i] = (sample[i] - cdf[k]) / (cdf[k + 1] - cdf[k]);
+    }
+    return PPG_OK;
+}
 int ppgo_mf_erf(size_t n, const float *x, float *erf_out, float *erfinv_out) {
     for (size_t i = 0; i < n; ++i) { erf_out[i] = mts_erf(x[i]); erfinv_out[i] = mts_erfinv(x[i]); }
     return PPG_OK;

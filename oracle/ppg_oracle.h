@@ -45,6 +45,8 @@ int ppgo_square_to_cosine_hemisphere(size_t n, const float *sample, float *out);
 /* TriAccel::load + rayIntersect for n (triangle, ray) pairs: k, the nine constants, hit flag, (t, u, v) */
 int ppgo_triaccel(size_t n, const float *A, const float *B, const float *C, const float *o, const float *d, const float *mint, const float *maxt,
                   int *k_out, float *consts_out, unsigned char *hit_out, float *tuv_out);
+/* discrete distribution over n_entries weights as the light sampling builds and samples it: normalised entries, sum, and for n samples index + reused sample */
+int ppgo_discrete(size_t n_entries, const float *weights, size_t n, const float *sample, float *pdf_out, float *sum_out, unsigned *index_out, float *reused_out);
 int ppgo_rough_transmittance(size_t n, const float *cosTheta, const float *values /* PPG_BSDF_TABLE_SIZE */, float *out);
 
 /* ---- emitter level (handle with a scene): Scene::sampleAttenuatedEmitterDirect at n reference points -- ref, ref_n 3n (ref_n 0 = two-sided),

@@ -95,5 +95,14 @@ int dev_texture_eval(const ppg_texture *t, const uint16_t *texels /* the whole t
     }
     return 0;
 }
+// cdf_sample + the sample reuse of the device's sample_emitter_direct, on a normalised cdf (n_entries + 1 values) the host built
+int dev_discrete(size_t n_entries, const float *cdf, size_t n, const float *sample, unsigned *index_out, float *reused_out) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t k = cdf_sample(cdf, (uint32_t) n_entries + 1u, sample[i]);
+        const float c0 = cdf[k], c1 = cdf[k + 1];
+        index_out[i] = k; reused_out[i] = (sample[i] - c0) / (c1 - c0);
+    }
+    return 0;
+}
 int dev_rough_transmittance(size_t n, const float *c, const float *values, float *out) { for (size_t i = 0; i < n; ++i) out[i] = rough_transmittance(values, c[i]); return 0; }
 }

@@ -218,3 +218,32 @@ def test_device_texture_source_equals_the_oracle(dev):
         dev.dev_texture_eval(C.byref(t), texels.ctypes.data_as(C.POINTER(C.c_uint16)), n, uv.ctypes.data_as(f32p), b.ctypes.data_as(f32p), gb.ctypes.data_as(f32p))
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ga.view(np.uint32), gb.view(np.uint32)), k
         assert np.abs(a[4:]).max() > 0.1 and np.abs(ga[4:]).max() > 0
+
+
+def test_device_discrete_sampling_source_equals_the_reference(dev):
+    """cdf_sample + the sample reuse of the device's sample_emitter_direct on the normalised table ppg_set_scene uploads, against DiscreteDistribution::sampleReuse of the
+    reference compiled verbatim (or the oracle's, bit-equal to it): index and reused sample bit for bit, zero-weight entries skipped the same way."""
+    have_ref = os.path.exists(O.MFREF_SO)
+    truth = C.CDLL(O.MFREF_SO) if have_ref else O.load("port"); name = "mfref_discrete" if have_ref else "ppgo_discrete"
+    u32p = C.POINTER(C.c_uint32)
+    rng = np.random.default_rng(44)
+    for ne in (1, 3, 40, 1000):
+        w = rng.lognormal(0, 2, ne).astype(np.float32)
+        if ne > 2:
+            w[rng.integers(0, ne, max(1, ne // 5))] = 0; w[0] = 0; w[-1] = 0
+            w[ne // 2] = max(w[ne // 2], 1e-3)
+        n = 100000
+        smp = rng.random(n, dtype=np.float32); smp[0] = 0.0
+        pdf = np.zeros(ne, np.float32); s = C.c_float(); idx = np.zeros(n, np.uint32); reuse = np.zeros(n, np.float32)
+        fn = getattr(truth, name); fn.argtypes = [C.c_size_t, f32p, C.c_size_t, f32p, f32p, C.POINTER(C.c_float), u32p, f32p]
+        fn(ne, w.ctypes.data_as(f32p), n, smp.ctypes.data_as(f32p), pdf.ctypes.data_as(f32p), C.byref(s), idx.ctypes.data_as(u32p), reuse.ctypes.data_as(f32p))
+        # the table as the host builds it (ppg_host.cu, emitter tables: cumulative sum, x 1/sum, last entry = 1): DiscreteDistribution::normalize
+        cdf = np.zeros(ne + 1, np.float32)
+        for i in range(ne):
+            cdf[i + 1] = np.float32(cdf[i] + w[i])
+        nrm = np.float32(1.0) / cdf[-1]; cdf[1:] = cdf[1:] * nrm; cdf[-1] = 1.0
+        assert np.array_equal(np.diff(cdf), pdf) or np.allclose(np.diff(cdf), pdf, rtol=0, atol=0)
+        idx2 = np.zeros(n, np.uint32); reuse2 = np.zeros(n, np.float32)
+        dev.dev_discrete.argtypes = [C.c_size_t, f32p, C.c_size_t, f32p, u32p, f32p]
+        dev.dev_discrete(ne, cdf.ctypes.data_as(f32p), n, smp.ctypes.data_as(f32p), idx2.ctypes.data_as(u32p), reuse2.ctypes.data_as(f32p))
+        assert np.array_equal(idx, idx2) and np.array_equal(reuse.view(np.uint32), reuse2.view(np.uint32)), ne

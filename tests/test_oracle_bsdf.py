@@ -239,3 +239,32 @@ def test_restated_triangle_test_and_spline_equal_the_reference():
     port.ppgo_rough_transmittance(len(cs), cs.ctypes.data_as(f32p), lut.ctypes.data_as(f32p), b.ctypes.data_as(f32p))
     # (the abscissa |cos|^(1/4) is computed by numpy for the reference function and by libm's powf inside the restatement: equal in most cases, one ulp apart otherwise)
     assert np.abs(np.clip(a, 0, 1) - b).max() <= 2e-6 and (np.clip(a, 0, 1) == b).mean() > 0.9
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(O.MFREF_SO), reason="oracle/_ref/libmicrofacet_ref.so not built (needs /root/reference at build time)")
+def test_restated_discrete_distribution_equals_the_reference():
+    """struct DiscreteDistribution (include/mitsuba/core/pmf.h:35-210: append, normalize, sample, sampleReuse), compiled verbatim, against the cumulative tables the
+    oracle's light sampling builds and Scene::cdfSample: the normalised entries, the sum, the chosen index and the reused sample agree bit for bit -- with zero-weight
+    entries (which `sample` skips), a dominant entry and samples on the table's own boundaries."""
+    import ctypes as C
+    ref = C.CDLL(O.MFREF_SO); port = O.load("port")
+    f32p = C.POINTER(C.c_float); u32p = C.POINTER(C.c_uint32)
+    rng = np.random.default_rng(33)
+    for ne in (1, 2, 7, 300):
+        w = rng.lognormal(0, 2, ne).astype(np.float32)
+        if ne > 2:
+            w[rng.integers(0, ne, max(1, ne // 5))] = 0; w[0] = 0; w[-1] = 0
+        w[ne // 2] = max(w[ne // 2], 1e-3)
+        n = 100000
+        smp = rng.random(n, dtype=np.float32)
+        cdf = np.concatenate([[0], np.cumsum(w, dtype=np.float32)]); smp[:ne + 1] = np.minimum(cdf / cdf[-1], np.float32(0.99999994))     # boundaries (approximately: float32 cumsum)
+        smp[ne + 1] = 0.0
+        outs = []
+        for lib, name in ((ref, "mfref_discrete"), (port, "ppgo_discrete")):
+            pdf = np.zeros(ne, np.float32); s = C.c_float(); idx = np.zeros(n, np.uint32); reuse = np.zeros(n, np.float32)
+            fn = getattr(lib, name); fn.argtypes = [C.c_size_t, f32p, C.c_size_t, f32p, f32p, C.POINTER(C.c_float), u32p, f32p]
+            fn(ne, w.ctypes.data_as(f32p), n, smp.ctypes.data_as(f32p), pdf.ctypes.data_as(f32p), C.byref(s), idx.ctypes.data_as(u32p), reuse.ctypes.data_as(f32p))
+            outs.append((pdf, s.value, idx, reuse))
+        (p0, s0, i0, r0), (p1, s1, i1, r1) = outs
+        assert np.array_equal(p0, p1) and s0 == s1 and np.array_equal(i0, i1) and np.array_equal(r0.view(np.uint32), r1.view(np.uint32)), ne
+        assert (w[i0] > 0).all()                                                   # an entry of probability 0 is never returned (pmf.h:131-134)
