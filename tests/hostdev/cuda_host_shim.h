@@ -23,10 +23,13 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s
 static inline double __dmul_rn(double a, double b) { return a * b; }          // (no contraction: -ffp-contract=off)
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
+#define __expf(x) expf(x)                                                      /* fast-math exp on the device (only where stated in the kernels); glibc declares but does not export the name */
 static inline float __fdividef(float a, float b) { return a / b; }            // approximate on the device; only the conservative pre-filter of the tiny-scene test uses it
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline unsigned __match_any_sync(unsigned, unsigned long long) { return 1u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T, int) { return T(); }   // a one-lane warp: the other lane of a butterfly does not exist (only compiled, never run here)
+static inline double atomicAdd(double *a, double v) { const double o = *a; *a += v; return o; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __activemask() { return 1u; }

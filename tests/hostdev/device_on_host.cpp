@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE -- C entry points over the product's CUDA device functions compiled for the host (see cuda_host_shim.h); same shape as oracle/microfacet_ref/wrapper.h.
 #include "cuda_host_shim.h"
-#include "../../practical-path-guiding_b200/csrc/ppg_device.cuh"
+#include "../../practical-path-guiding_b200/csrc/ppg_kernels.cuh"      // (includes ppg_device.cuh; the __global__ functions run here as plain loops of one thread)
 #include "../../include/ppg.h"
 #include <cstddef>
 #include <vector>
@@ -101,6 +101,38 @@ int dev_discrete(size_t n_entries, const float *cdf, size_t n, const float *samp
         const uint32_t k = cdf_sample(cdf, (uint32_t) n_entries + 1u, sample[i]);
         const float c0 = cdf[k], c1 = cdf[k + 1];
         index_out[i] = k; reused_out[i] = (sample[i] - c0) / (c1 - c0);
+    }
+    return 0;
+}
+// ---- SD-tree: S-tree descent through the prefix table stree_table_kernel builds, D-tree pdf / sample on a sampling pool laid out like the device's (SampNode)
+int dev_stree_lookup(const uint32_t *node_children /* 2 per node */, size_t n_nodes, const float aabb_min[3], const float extent[3], const float *points, size_t n, uint32_t *leaf_out, float *size_out) {
+    std::vector<uint2> sn(n_nodes);
+    for (size_t i = 0; i < n_nodes; ++i) sn[i] = make_uint2(node_children[2 * i], node_children[2 * i + 1]);
+    std::vector<uint32_t> table((size_t) 1 << (3 * PPG_STREE_TABLE_BITS));
+    stree_table_kernel(sn.data(), table.data());
+    const float3 mn = make_float3(aabb_min[0], aabb_min[1], aabb_min[2]), ex = make_float3(extent[0], extent[1], extent[2]);
+    for (size_t i = 0; i < n; ++i) {
+        int lv = 0; leaf_out[i] = stree_lookup(sn.data(), table.data(), mn, ex, v3(points, i), lv);
+        const float3 v = voxel_size(ex, lv); size_out[3 * i] = v.x; size_out[3 * i + 1] = v.y; size_out[3 * i + 2] = v.z;
+    }
+    return 0;
+}
+struct ReplayRng { const float *v; uint32_t n, i; float next1D() { return i < n ? v[i++] : 0.5f; } };
+int dev_dtree(const float *sums, const uint16_t *children, size_t n_nodes, const uint32_t *tree_first, const float *tree_sum, const float *tree_weight,
+              const uint32_t *query_tree, const float *query_dir, const float *rnd, size_t rnd_stride, size_t n, float *pdf_out, float *dir_out) {
+    std::vector<SampNode> pool(n_nodes);
+    for (size_t i = 0; i < n_nodes; ++i) {
+        pool[i].sums = make_float4(sums[4 * i], sums[4 * i + 1], sums[4 * i + 2], sums[4 * i + 3]);
+        pool[i].children = make_uint2((uint32_t) children[4 * i] | ((uint32_t) children[4 * i + 1] << 16), (uint32_t) children[4 * i + 2] | ((uint32_t) children[4 * i + 3] << 16));
+        pool[i].pad = make_uint2(0u, 0u);
+    }
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t t = query_tree[i];
+        float mean = 0.f; if (tree_weight[t] != 0.f) mean = (1.f / (PPG_PI * 4.f * tree_weight[t])) * tree_sum[t];       // DTree::mean, GP:386-394
+        pdf_out[i] = dtree_pdf(pool.data() + tree_first[t], mean > 0.f, dir_to_canonical(v3(query_dir, i)));
+        ReplayRng r{rnd + rnd_stride * i, (uint32_t) rnd_stride, 0u};
+        const float3 d = canonical_to_dir(dtree_sample(pool.data() + tree_first[t], mean > 0.f, r));
+        dir_out[3 * i] = d.x; dir_out[3 * i + 1] = d.y; dir_out[3 * i + 2] = d.z;
     }
     return 0;
 }

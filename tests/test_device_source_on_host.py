@@ -23,7 +23,7 @@ f32p = C.POINTER(C.c_float)
 def dev(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("hostdev") / "libdevice_on_host.so")
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + CUDA_INC, "-D__device__=", "-D__host__=", "-D__global__=", "-D__shared__=",
-           "-D__forceinline__=inline", "-D__noinline__=", "-Wno-unused-function", os.path.join(ROOT, "tests", "hostdev", "device_on_host.cpp"), "-o", so]
+           "-D__forceinline__=inline", "-D__noinline__=", "-D__launch_bounds__(...)=", "-Wno-unused-function", os.path.join(ROOT, "tests", "hostdev", "device_on_host.cpp"), "-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)
@@ -247,3 +247,35 @@ def test_device_discrete_sampling_source_equals_the_reference(dev):
         dev.dev_discrete.argtypes = [C.c_size_t, f32p, C.c_size_t, f32p, u32p, f32p]
         dev.dev_discrete(ne, cdf.ctypes.data_as(f32p), n, smp.ctypes.data_as(f32p), idx2.ctypes.data_as(u32p), reuse2.ctypes.data_as(f32p))
         assert np.array_equal(idx, idx2) and np.array_equal(reuse.view(np.uint32), reuse2.view(np.uint32)), ne
+
+
+def test_device_sdtree_sources_against_the_reference_trees(dev):
+    """stree_lookup (through the prefix table stree_table_kernel builds -- the __global__ function runs here as a plain loop), dtree_pdf, dtree_sample and the
+    cylindrical maps of the device source on trees trained by the oracle (the reference's own SD-tree code where oracle/_ref exists): leaf index and voxel size bit
+    for bit; sampled directions within 2e-6 (the fold of the per-level origins is the reference's, the two leaf numbers enter in its order); pdf to 2e-6 relative
+    (top-down product here, bottom-up recursion there) -- the tolerances of the same comparison on the GPU (tests/test_gpu_parity.py::test_op_*)."""
+    from common import load_cbox
+    sc = load_cbox(96)
+    o = O.Oracle(O.params_from_xml(dict(sc.integrator, budget="60")), sc, kind="ref" if O.have_ref() else "port"); o.render()
+    e = o.export(0)
+    rng = np.random.default_rng(8); n = 100000
+    mn, mx = e["aabb"]; ext = (mx - mn).astype(np.float32)
+    pts = (mn + rng.random((n, 3)) * (mx - mn)).astype(np.float32); pts[:8] = [mn, mx, (mn + mx) / 2, mn - 1, mx + 1, [mn[0], mx[1], mn[2]], [mx[0], mn[1], mx[2]], (mn + mx) / 2 + 1e-3]
+    leaf, size = o.lookup(pts)
+    u32p = C.POINTER(C.c_uint32)
+    sch = np.ascontiguousarray(e["s_children"], np.uint32); gl = np.zeros(n, np.uint32); gs = np.zeros((n, 3), np.float32)
+    dev.dev_stree_lookup.argtypes = [u32p, C.c_size_t, f32p, f32p, f32p, C.c_size_t, u32p, f32p]
+    dev.dev_stree_lookup(sch.ctypes.data_as(u32p), len(sch), np.float32(mn).ctypes.data_as(f32p), ext.ctypes.data_as(f32p), pts.ctypes.data_as(f32p), n, gl.ctypes.data_as(u32p), gs.ctypes.data_as(f32p))
+    assert np.array_equal(gl, leaf) and np.array_equal(gs, size) and len(np.unique(leaf)) > 10
+    leaves = np.nonzero(e["s_is_leaf"])[0].astype(np.uint32)
+    ql = rng.choice(leaves, n).astype(np.uint32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rnd = rng.random((n, 24), dtype=np.float32)
+    pdf = np.zeros(n, np.float32); dirs = np.zeros((n, 3), np.float32)
+    sums = np.ascontiguousarray(e["sums"], np.float32); ch = np.ascontiguousarray(e["children"], np.uint16); first = e["tree_first"].astype(np.uint32)
+    dev.dev_dtree.argtypes = [f32p, C.POINTER(C.c_uint16), C.c_size_t, u32p, f32p, f32p, u32p, f32p, f32p, C.c_size_t, C.c_size_t, f32p, f32p]
+    dev.dev_dtree(sums.ctypes.data_as(f32p), ch.ctypes.data_as(C.POINTER(C.c_uint16)), len(sums), first.ctypes.data_as(u32p), e["tree_sum"].ctypes.data_as(f32p),
+                  e["tree_weight"].ctypes.data_as(f32p), ql.ctypes.data_as(u32p), d.ctypes.data_as(f32p), rnd.ctypes.data_as(f32p), 24, n, pdf.ctypes.data_as(f32p), dirs.ctypes.data_as(f32p))
+    ref_pdf = o.pdf(ql, d); ref_dir = o.sample(ql, rnd)
+    assert np.allclose(pdf, ref_pdf, rtol=2e-6, atol=1e-12) and np.abs(dirs - ref_dir).max() <= 2e-6
+    assert (dirs == ref_dir).all(axis=1).mean() > 0.9                              # (mostly bit-equal: same libm here)
